@@ -1,0 +1,89 @@
+"""Model dimensions of the HydraVox hot path (SURVEY.md §8 header).
+
+``hydravox.yaml`` is not in the reference tree; the FULL presets are the
+CosyVoice3-derived dims pinned by scripts/post_process/
+add_mtp_weights_to_cosyvoice3lm_ckpt.py:130-154, llm_multi_head_v3.py:643-652,
+flow.py:436-451 and generator.py:739-746.  TINY presets keep every structural
+property (GQA, partial rotary, grouped conv, 3 upsample stages, MTP heads) at
+sizes whose weights fit in a committed fixture.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field, asdict
+from typing import Tuple
+
+
+@dataclass(frozen=True)
+class HiftDims:
+    mel: int = 80
+    base: int = 512
+    f0_ch: int = 512
+    harmonics: int = 9            # nb_harmonics(8) + fundamental
+    sr: int = 24000
+    ups: Tuple[int, ...] = (8, 5, 3)
+    up_k: Tuple[int, ...] = (16, 11, 7)
+    n_fft: int = 16
+    hop: int = 4
+    rb_k: Tuple[int, ...] = (3, 7, 11)
+    rb_d: Tuple[int, ...] = (1, 3, 5)
+    src_k: Tuple[int, ...] = (7, 7, 11)
+
+    @property
+    def frame_samples(self) -> int:      # 480 at full dims
+        p = self.hop
+        for u in self.ups:
+            p *= u
+        return p
+
+
+@dataclass(frozen=True)
+class FlowDims:
+    mel: int = 80
+    spk_in: int = 192
+    vocab: int = 6561
+    pla_ch: int = 1024
+    dim: int = 1024
+    depth: int = 22
+    heads: int = 16
+    dim_head: int = 64
+    ff_mult: int = 2
+    chunk: int = 50               # static_chunk_size (frames) for the streaming mask
+    pos_k: int = 31
+    pos_groups: int = 16
+    cfg_rate: float = 0.7
+    noise_frames: int = 15000
+
+
+@dataclass(frozen=True)
+class LlmDims:
+    hidden: int = 896
+    layers: int = 24
+    q_heads: int = 14
+    kv_heads: int = 2
+    head_dim: int = 64
+    inter: int = 4864
+    text_vocab: int = 151936
+    speech_vocab: int = 6761      # speech_token_size(6561) + 200
+    rope_theta: float = 1e6
+    mtp_heads: int = 5
+    mtp_attn_heads: int = 14
+    mtp_inter: int = 22016
+    eps: float = 1e-6
+
+    @property
+    def speech_token_size(self) -> int:
+        return self.speech_vocab - 200
+
+
+HIFT_FULL = HiftDims()
+FLOW_FULL = FlowDims()
+LLM_FULL = LlmDims()
+
+HIFT_TINY = HiftDims(base=64, f0_ch=64)
+FLOW_TINY = FlowDims(vocab=512, pla_ch=128, dim=128, depth=2, heads=2, noise_frames=600)
+LLM_TINY = LlmDims(hidden=128, layers=2, q_heads=2, kv_heads=1, inter=256, text_vocab=512,
+                   speech_vocab=456, mtp_heads=3, mtp_attn_heads=2, mtp_inter=384)
+
+
+def to_dict(d):
+    return asdict(d)

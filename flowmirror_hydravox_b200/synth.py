@@ -1,0 +1,193 @@
+"""Synthetic (seeded, random-init) checkpoints and inputs for the HydraVox hot path.
+
+The real ``llm.pt / flow.pt / hift.pt`` are downloaded from ModelScope at install time
+(reference README.md:73) and are not available offline, so bench.py and the parity tests
+use state_dicts with *exactly the reference's parameter names and shapes*
+(checked against the real reference modules by oracle/make_golden.py) filled from a
+seeded ``torch.Generator``.  Scales are chosen so activations stay O(1) through each stage
+(no saturation of the vocoder's exp/clamp, no softmax collapse), which keeps parity
+comparisons meaningful.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+from .dims import FlowDims, HiftDims, LlmDims
+
+
+def _gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def _randn(g, *shape, std=1.0):
+    return torch.randn(*shape, generator=g) * std
+
+
+# --------------------------------------------------------------------------- HiFT
+def hift_state_dict(d: HiftDims, seed: int = 0) -> Dict[str, torch.Tensor]:
+    g = _gen(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def wn_conv(name, cout, cin, k, gain=1.0):
+        v = _randn(g, cout, cin, k)
+        gmag = v.reshape(cout, -1).norm(dim=1).reshape(cout, 1, 1) * (gain / (cin * k) ** 0.5)
+        sd[name + ".bias"] = _randn(g, cout, std=0.05)
+        sd[name + ".parametrizations.weight.original0"] = gmag
+        sd[name + ".parametrizations.weight.original1"] = v
+
+    def plain_conv(name, cout, cin, k, gain=1.0):
+        sd[name + ".weight"] = _randn(g, cout, cin, k, std=gain / (cin * k) ** 0.5)
+        sd[name + ".bias"] = _randn(g, cout, std=0.05)
+
+    def resblock(pfx, ch, k):
+        for c in ("convs1", "convs2"):
+            for i in range(len(d.rb_d)):
+                wn_conv(f"{pfx}.{c}.{i}", ch, ch, k, gain=0.6)
+        for a in ("activations1", "activations2"):
+            for i in range(len(d.rb_d)):
+                sd[f"{pfx}.{a}.{i}.alpha"] = 0.5 + torch.rand(ch, generator=g)
+
+    sd["m_source.l_linear.weight"] = _randn(g, 1, d.harmonics, std=1.0)
+    sd["m_source.l_linear.bias"] = _randn(g, 1, std=0.1)
+    wn_conv("conv_pre", d.base, d.mel, 5, gain=0.5)
+    n_up = len(d.ups)
+    for i in range(n_up):
+        wn_conv(f"ups.{i}", d.base >> (i + 1), d.base >> i, d.up_k[i])
+    cum = [1]
+    for u in list(d.ups)[::-1][:-1]:
+        cum.append(cum[-1] * u)
+    for i, u in enumerate(cum[::-1]):
+        plain_conv(f"source_downs.{i}", d.base >> (i + 1), d.n_fft + 2, 1 if u == 1 else 2 * u, gain=2.0)
+        resblock(f"source_resblocks.{i}", d.base >> (i + 1), d.src_k[i])
+    for i in range(n_up):
+        for j, k in enumerate(d.rb_k):
+            resblock(f"resblocks.{i * len(d.rb_k) + j}", d.base >> (i + 1), k)
+    wn_conv("conv_post", d.n_fft + 2, d.base >> n_up, 7, gain=0.25)
+    p = "f0_predictor."
+    wn_conv(p + "condnet.0", d.f0_ch, d.mel, 4, gain=0.5)
+    for i in (2, 4, 6, 8):
+        wn_conv(p + f"condnet.{i}", d.f0_ch, d.f0_ch, 3, gain=1.4)
+    # classifier scaled so |f0| straddles the voiced threshold (10 Hz) and reaches a few 100 Hz
+    sd[p + "classifier.weight"] = _randn(g, 1, d.f0_ch, std=400.0 / d.f0_ch ** 0.5)
+    sd[p + "classifier.bias"] = torch.tensor([5.0])
+    return sd
+
+
+def hift_sine_table(d: HiftDims, n_frames: int, seed: int = 11) -> torch.Tensor:
+    """Stand-in for SineGen2.sine_waves (generator.py:226): uniform[0,1) rows, (n_frames*frame, H)."""
+    return torch.rand(n_frames * d.frame_samples, d.harmonics, generator=_gen(seed))
+
+
+# --------------------------------------------------------------------------- flow
+def flow_state_dict(d: FlowDims, seed: int = 0) -> Dict[str, torch.Tensor]:
+    g = _gen(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def lin(name, out, inp, gain=1.0, bias=True):
+        sd[name + ".weight"] = _randn(g, out, inp, std=gain / inp ** 0.5)
+        if bias:
+            sd[name + ".bias"] = _randn(g, out, std=0.05)
+
+    sd["input_embedding.weight"] = _randn(g, d.vocab, d.mel)
+    lin("spk_embed_affine_layer", d.mel, d.spk_in)
+    sd["pre_lookahead_layer.conv1.weight"] = _randn(g, d.pla_ch, d.mel, 4, std=1.0 / (d.mel * 4) ** 0.5)
+    sd["pre_lookahead_layer.conv1.bias"] = _randn(g, d.pla_ch, std=0.05)
+    sd["pre_lookahead_layer.conv2.weight"] = _randn(g, d.mel, d.pla_ch, 3, std=1.0 / (d.pla_ch * 3) ** 0.5)
+    sd["pre_lookahead_layer.conv2.bias"] = _randn(g, d.mel, std=0.05)
+    p = "decoder.estimator."
+    lin(p + "time_embed.time_mlp.0", d.dim, 256)
+    lin(p + "time_embed.time_mlp.2", d.dim, d.dim)
+    lin(p + "input_embed.proj", d.dim, 4 * d.mel)
+    cg = d.dim // d.pos_groups
+    for c in ("conv1", "conv2"):
+        sd[p + f"input_embed.conv_pos_embed.{c}.0.weight"] = _randn(g, d.dim, cg, d.pos_k, std=1.0 / (cg * d.pos_k) ** 0.5)
+        sd[p + f"input_embed.conv_pos_embed.{c}.0.bias"] = _randn(g, d.dim, std=0.05)
+    sd[p + "rotary_embed.inv_freq"] = 1.0 / (10000.0 ** (torch.arange(0, d.dim_head, 2).float() / d.dim_head))
+    inner = d.heads * d.dim_head
+    for i in range(d.depth):
+        bp = p + f"transformer_blocks.{i}."
+        lin(bp + "attn_norm.linear", 6 * d.dim, d.dim, gain=0.5)
+        lin(bp + "attn.to_q", inner, d.dim)
+        lin(bp + "attn.to_k", inner, d.dim)
+        lin(bp + "attn.to_v", inner, d.dim)
+        lin(bp + "attn.to_out.0", d.dim, inner)
+        lin(bp + "ff.ff.0.0", d.dim * d.ff_mult, d.dim)
+        lin(bp + "ff.ff.2", d.dim, d.dim * d.ff_mult)
+    lin(p + "norm_out.linear", 2 * d.dim, d.dim, gain=0.5)
+    lin(p + "proj_out", d.mel, d.dim)
+    return sd
+
+
+def flow_noise(d: FlowDims) -> torch.Tensor:
+    """CausalConditionalCFM.rand_noise (flow_matching.py:200-201): randn(1,80,15000) right after
+    set_all_random_seed(0).  torch.manual_seed(0) + randn reproduces it bit-for-bit on CPU
+    (first values -1.1258, -1.1524, -0.2506)."""
+    g = _gen(0)
+    return torch.randn(1, d.mel, 50 * 300, generator=g)[:, :, : d.noise_frames].contiguous()
+
+
+# --------------------------------------------------------------------------- LLM
+def llm_state_dict(d: LlmDims, seed: int = 0, dtype=torch.float32) -> Dict[str, torch.Tensor]:
+    g = _gen(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def lin(name, out, inp, gain=1.0, bias=False):
+        sd[name + ".weight"] = _randn(g, out, inp, std=gain / inp ** 0.5).to(dtype)
+        if bias:
+            sd[name + ".bias"] = _randn(g, out, std=0.1).to(dtype)
+
+    def norm(name):
+        sd[name + ".weight"] = (1.0 + 0.1 * _randn(g, d.hidden)).to(dtype)
+
+    sd["llm.model.model.embed_tokens.weight"] = _randn(g, d.text_vocab, d.hidden).to(dtype)
+    for l in range(d.layers):
+        p = f"llm.model.model.layers.{l}."
+        lin(p + "self_attn.q_proj", d.q_heads * d.head_dim, d.hidden, bias=True)
+        lin(p + "self_attn.k_proj", d.kv_heads * d.head_dim, d.hidden, bias=True)
+        lin(p + "self_attn.v_proj", d.kv_heads * d.head_dim, d.hidden, bias=True)
+        lin(p + "self_attn.o_proj", d.hidden, d.q_heads * d.head_dim, gain=0.5)
+        lin(p + "mlp.gate_proj", d.inter, d.hidden)
+        lin(p + "mlp.up_proj", d.inter, d.hidden)
+        lin(p + "mlp.down_proj", d.hidden, d.inter, gain=0.5)
+        norm(p + "input_layernorm")
+        norm(p + "post_attention_layernorm")
+    norm("llm.model.model.norm")
+    sd["llm.model.lm_head.weight"] = sd["llm.model.model.embed_tokens.weight"]
+    lin("llm_decoder", d.speech_vocab, d.hidden, gain=3.0)
+    mh = d.mtp_attn_heads * (d.hidden // d.mtp_attn_heads)
+    for j in range(d.mtp_heads):
+        p = f"mtp_block.{j}."
+        lin(p + "self_attn.q_proj", mh, d.hidden, bias=True)
+        lin(p + "self_attn.k_proj", mh, d.hidden, bias=True)
+        lin(p + "self_attn.v_proj", mh, d.hidden, bias=True)
+        lin(p + "self_attn.o_proj", d.hidden, mh, gain=0.5)
+        lin(p + "mlp.gate_proj", d.mtp_inter, d.hidden)
+        lin(p + "mlp.up_proj", d.mtp_inter, d.hidden)
+        lin(p + "mlp.down_proj", d.hidden, d.mtp_inter, gain=0.5)
+        norm(p + "input_layernorm")
+        norm(p + "post_attention_layernorm")
+    sd["speech_embedding.weight"] = _randn(g, d.speech_vocab, d.hidden).to(dtype)
+    return sd
+
+
+# --------------------------------------------------------------------------- inputs
+def utterance(ld: LlmDims, fd: FlowDims, n_text: int, seed: int = 1986, zero_shot: bool = True,
+              prompt_tokens: int = 125, prompt_text: int = 16):
+    """One synthetic request: text ids, prompt, speaker embedding (seed 1986 as in SURVEY §8d)."""
+    g = _gen(seed)
+    u = dict(
+        text=torch.randint(0, ld.text_vocab, (n_text,), generator=g, dtype=torch.int32),
+        embedding=torch.rand(fd.spk_in, generator=g),
+    )
+    if zero_shot:
+        u["prompt_text"] = torch.randint(0, ld.text_vocab, (prompt_text,), generator=g, dtype=torch.int32)
+        u["prompt_speech"] = torch.randint(0, min(ld.speech_token_size, fd.vocab), (prompt_tokens,), generator=g,
+                                           dtype=torch.int32)
+        u["prompt_feat"] = (torch.rand(2 * prompt_tokens, fd.mel, generator=g) * -6.0)
+    else:
+        u["prompt_text"] = torch.zeros(0, dtype=torch.int32)
+        u["prompt_speech"] = torch.zeros(0, dtype=torch.int32)
+        u["prompt_feat"] = None
+    return u

@@ -1,0 +1,186 @@
+"""TEST INFRASTRUCTURE ONLY — mint tests/golden/*.pt from the UNMODIFIED reference modules.
+
+Run in the build container (needs /root/reference):  python -m oracle.make_golden
+For every stage and for TINY and FULL dims it
+  1. builds the reference module (oracle/refshim.py) and loads the synthetic checkpoint
+     (flowmirror_hydravox_b200/synth.py) with strict=True  -> pins parameter names/shapes;
+  2. runs the reference's own inference on seeded inputs;
+  3. runs the restated oracle on the same inputs and asserts agreement;
+  4. stores inputs + reference outputs (+ a checkpoint checksum) as a small fixture.
+The fixtures travel to the GPU box; the reference does not.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from functools import partial
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from flowmirror_hydravox_b200 import dims as D, synth  # noqa: E402
+from oracle import flow_ref, hift_ref, llm_ref, refshim  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def checksum(sd):
+    return float(sum(v.double().abs().sum() for v in sd.values() if v.is_floating_point()))
+
+
+class _TorchF32Proxy:
+    """flow.py:378-385 casts to bf16/fp16 unconditionally; evaluate the reference in fp32 by
+    presenting torch.bfloat16/float16 as float32 to that module only (source untouched)."""
+
+    def __getattr__(self, n):
+        return torch.float32 if n in ("bfloat16", "float16") else getattr(torch, n)
+
+
+def golden_hift(name, dims, T, seed):
+    m = refshim.build_hift(dims)
+    sd = synth.hift_state_dict(dims, seed)
+    m.load_state_dict(sd, strict=True)
+    table = synth.hift_sine_table(dims, T)
+    m.m_source.l_sin_gen.sine_waves = table[None]
+    g = torch.Generator().manual_seed(seed + 100)
+    mel = torch.rand(1, dims.mel, T, generator=g) * 6.0 - 6.0
+    wav, src = m.inference(speech_feat=mel, finalize=True)
+    f0 = m.f0_predictor(mel)
+    w = hift_ref.fold_weight_norm(sd)
+    f0_o = hift_ref.f0_predict(w, mel)
+    ef0 = ((f0 - f0_o).abs() / (f0.abs() + 1.0)).max().item()
+    wav_o, src_o = hift_ref.inference(sd, mel, table, dims, f0=f0)          # F0 pinned
+    e = (wav - wav_o).abs().max().item()
+    wav_free, _ = hift_ref.inference(sd, mel, table, dims)                  # F0 from the oracle itself
+    e_free = (wav - wav_free).abs().max().item()
+    wav_s, _ = m.inference(speech_feat=mel, finalize=False)
+    f0_s = m.f0_predictor(mel, finalize=False)
+    wav_so, _ = hift_ref.inference(sd, mel, table, dims, finalize=False, f0=f0_s)
+    es = (wav_s - wav_so).abs().max().item()
+    voiced = (f0 > 10).float().mean().item()
+    print(f"[hift:{name}] T={T} ref-vs-oracle: f0 rel {ef0:.2e}; wav max-abs (F0 pinned) {e:.2e} (stream {es:.2e}), "
+          f"(F0 free) {e_free:.2e}; rms {wav.pow(2).mean().sqrt():.3f} sat {(wav.abs() >= 0.99).float().mean():.3f} "
+          f"voiced {voiced:.2f} f0 max {f0.max():.0f}")
+    assert ef0 < 1e-4 and e < 5e-6 and es < 5e-6
+    torch.save(dict(dims=name, seed=seed, T=T, mel=mel, wav=wav, src=src, f0=f0, wav_stream=wav_s, f0_stream=f0_s,
+                    sd_checksum=checksum(sd)), os.path.join(OUT, f"hift_{name}.pt"))
+
+
+def golden_flow(name, dims, N, P, n_steps, seed):
+    import cosyvoice.flow.flow as flowmod
+    flowmod.torch = _TorchF32Proxy()
+    m = refshim.build_flow(dims)
+    sd = synth.flow_state_dict(dims, seed)
+    m.load_state_dict(sd, strict=True)
+    m.bf16 = True
+    noise = synth.flow_noise(dims)
+    assert torch.equal(m.decoder.rand_noise[:, :, : noise.shape[2]], noise), "rand_noise recipe drifted"
+    g = torch.Generator().manual_seed(seed + 100)
+    tok = torch.randint(0, dims.vocab, (1, N), generator=g)
+    ptok = torch.randint(0, dims.vocab, (1, P), generator=g)
+    pfeat = torch.rand(1, 2 * P, dims.mel, generator=g) * -6.0
+    emb = torch.rand(1, dims.spk_in, generator=g)
+    orig = m.decoder.forward
+    m.decoder.forward = lambda **kw: orig(**{**kw, "n_timesteps": n_steps})
+    kw = dict(token=tok, token_len=torch.tensor([N]), embedding=emb, prompt_token=ptok,
+              prompt_token_len=torch.tensor([P]), prompt_feat=pfeat, prompt_feat_len=torch.tensor([2 * P]))
+    out = {}
+    for key, streaming, finalize in (("full", False, True), ("stream", True, True), ("chunk", True, False)):
+        ref, _ = m.inference(finalize=finalize, streaming=streaming, **kw)
+        ora = flow_ref.inference(sd, tok, emb, noise, dims, n_steps, ptok, pfeat, streaming=streaming, finalize=finalize)
+        e = (ref - ora).abs().max().item()
+        print(f"[flow:{name}] {key} mel {tuple(ref.shape)} ref-vs-oracle max-abs {e:.2e} mean|mel| {ref.abs().mean():.3f}")
+        assert e < 2e-4
+        out["mel_" + key] = ref
+    # one estimator call (the TRT seam, flow_matching.py:126-153) for kernel-level parity
+    T = 2 * (N + P)
+    xg = torch.randn(2, dims.mel, T, generator=g)
+    mug = torch.randn(2, dims.mel, T, generator=g)
+    cg = torch.randn(2, dims.mel, T, generator=g)
+    sg = torch.randn(2, dims.mel, generator=g)
+    tg = torch.tensor([0.3, 0.3])
+    est = m.decoder.estimator(xg, torch.ones(2, 1, T), mug, tg, sg, cg, streaming=False)
+    est_o = flow_ref.dit_forward(sd, xg, mug, tg, sg, cg, dims)
+    assert (est - est_o).abs().max().item() < 1e-4
+    # what the reference's own low-precision path loses against fp32 (parity budget)
+    mb = refshim.build_flow(dims, dtype=torch.bfloat16)
+    mb.load_state_dict({k: v.to(torch.bfloat16) for k, v in sd.items()}, strict=True)
+    flowmod.torch = torch
+    mb.bf16 = True
+    origb = mb.decoder.forward
+    mb.decoder.forward = lambda **k2: origb(**{**k2, "n_timesteps": n_steps})
+    refb, _ = mb.inference(finalize=True, streaming=False, **kw)
+    dev = (refb - out["mel_full"]).abs()
+    print(f"[flow:{name}] reference bf16 path vs fp32: max-abs {dev.max():.3e} mean-abs {dev.mean():.3e}")
+    torch.save(dict(dims=name, seed=seed, N=N, P=P, n_steps=n_steps, token=tok, prompt_token=ptok, prompt_feat=pfeat,
+                    embedding=emb, est_in=dict(x=xg, mu=mug, cond=cg, spks=sg, t=tg), est_out=est,
+                    ref_bf16_maxabs=float(dev.max()), ref_bf16_meanabs=float(dev.mean()),
+                    sd_checksum=checksum(sd), **out), os.path.join(OUT, f"flow_{name}.pt"))
+
+
+def golden_llm(name, dims, n_text, n_ptext, P, cases, seed):
+    from cosyvoice.utils.common import ras_sampling
+    m = refshim.build_llm(dims)
+    sd = synth.llm_state_dict(dims, seed)
+    m.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(seed + 100)
+    text = torch.randint(0, dims.text_vocab, (1, n_text), generator=g)
+    ptext = torch.randint(0, dims.text_vocab, (1, n_ptext), generator=g)
+    pspeech = torch.randint(0, dims.speech_token_size, (1, P), generator=g)
+    u = torch.rand(8192, generator=g)
+    rec = []
+    for K, ratio, sp in cases:
+        m.sampling = partial(ras_sampling, **sp)
+        m.inference_head_num = K
+        us = llm_ref.UStream(u)
+        orig = torch.Tensor.multinomial
+        torch.Tensor.multinomial = lambda self, n, replacement=False: torch.tensor(
+            [llm_ref.multinomial_u(self, us.next())])
+        try:
+            ref = list(m.inference(text=text, text_len=torch.tensor([n_text]), prompt_text=ptext,
+                                   prompt_text_len=torch.tensor([n_ptext]), prompt_speech_token=pspeech,
+                                   prompt_speech_token_len=torch.tensor([P]), embedding=None,
+                                   min_token_text_ratio=ratio[0], max_token_text_ratio=ratio[1]))
+        finally:
+            torch.Tensor.multinomial = orig
+        ora, logps = llm_ref.inference(sd, dims, text[0], ptext[0], pspeech[0], u, head_k=K, sp=sp,
+                                       min_ratio=ratio[0], max_ratio=ratio[1], return_logp=True)
+        print(f"[llm:{name}] K={K} ratio={ratio} sp={sp} ref {len(ref)} tok, oracle equal: {ref == ora}, u used {us.pos}")
+        assert ref == ora
+        rec.append(dict(K=K, ratio=ratio, sp=sp, tokens=ref, u_used=us.pos, logp0=logps[0]))
+    # first-step head log-probs straight from the reference modules (teacher-forced logits parity)
+    lm_in = llm_ref.LlmOracle(sd, dims).prompt_embeds(text[0], ptext[0], pspeech[0])[None]
+    y, _ = m.llm.forward_one_step(lm_in, masks=torch.tril(torch.ones(1, lm_in.shape[1], lm_in.shape[1])).bool())
+    last = y[:, -1:, :]
+    ref_lp = torch.stack([m.llm_decoder(m.mtp_block[j](last)[0][:, -1]).log_softmax(-1)[0] for j in range(dims.mtp_heads)])
+    o = llm_ref.LlmOracle(sd, dims)
+    hid = o.forward_rows(lm_in[0])
+    ora_lp = torch.stack([o.head_logp(j, hid[-1]) for j in range(dims.mtp_heads)])
+    e = (ref_lp - ora_lp).abs().max().item()
+    print(f"[llm:{name}] head log-prob ref-vs-oracle max-abs {e:.2e}")
+    assert e < 2e-4
+    torch.save(dict(dims=name, seed=seed, text=text[0], prompt_text=ptext[0], prompt_speech=pspeech[0], u=u,
+                    cases=rec, head_logp=ref_lp, last_hidden=y[0, -1], sd_checksum=checksum(sd)),
+               os.path.join(OUT, f"llm_{name}.pt"))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        golden_hift("tiny", D.HIFT_TINY, 37, 0)
+        golden_hift("full", D.HIFT_FULL, 24, 0)
+        golden_flow("tiny", D.FLOW_TINY, 21, 10, 10, 0)
+        golden_flow("full", D.FLOW_FULL, 24, 8, 4, 0)
+        sp1 = dict(top_p=0.9, top_k=10, win_size=24, tau_r=0.2)     # server tts defaults (router.py:22-44)
+        sp2 = dict(top_p=0.8, top_k=25, win_size=10, tau_r=0.1)     # ras_sampling defaults (common.py:138)
+        sp3 = dict(top_p=0.9, top_k=10, win_size=0, tau_r=0.2)      # win_size=0 edge: always random sampling
+        golden_llm("tiny", D.LLM_TINY, 12, 4, 6,
+                   [(1, (2, 20), sp1), (3, (8, 8), sp1), (2, (2, 6), sp2), (5, (2, 3), sp3)], 0)
+        golden_llm("full", D.LLM_FULL, 6, 2, 3, [(2, (4, 4), sp1)], 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,95 @@
+"""Oracle (oracle/*.py, CPU fp32) against the fixtures minted from the UNMODIFIED reference
+modules by oracle/make_golden.py.  These run without a GPU and without /root/reference."""
+import pytest
+import torch
+
+from flowmirror_hydravox_b200 import dims as D, synth
+from oracle import flow_ref, hift_ref, llm_ref
+
+
+def _checksum(sd):
+    return float(sum(v.double().abs().sum() for v in sd.values() if v.is_floating_point()))
+
+
+@pytest.mark.parametrize("name,dims", [("tiny", D.HIFT_TINY), ("full", D.HIFT_FULL)])
+def test_hift_oracle_matches_reference(golden, name, dims):
+    g = golden(f"hift_{name}")
+    sd = synth.hift_state_dict(dims, g["seed"])
+    assert abs(_checksum(sd) - g["sd_checksum"]) < 1e-6 * g["sd_checksum"]
+    table = synth.hift_sine_table(dims, g["T"])
+    w = hift_ref.fold_weight_norm(sd)
+    f0 = hift_ref.f0_predict(w, g["mel"])
+    assert ((f0 - g["f0"]).abs() / (g["f0"].abs() + 1)).max() < 1e-4
+    wav, src = hift_ref.inference(sd, g["mel"], table, dims, f0=g["f0"])
+    assert wav.shape == g["wav"].shape == (1, g["T"] * dims.frame_samples)
+    assert (wav - g["wav"]).abs().max() < 5e-6            # fp32, F0 pinned (see hift_ref.inference)
+    assert (src - g["src"]).abs().max() < 5e-6
+    wav_s, _ = hift_ref.inference(sd, g["mel"], table, dims, finalize=False, f0=g["f0_stream"])
+    assert (wav_s - g["wav_stream"]).abs().max() < 5e-6
+    # causal-vocoder self-check of the reference (generator.py:729-746): streamed prefix == offline prefix
+    n = wav_s.shape[1]
+    assert (wav_s - g["wav"][:, :n]).abs().max() < 2e-3   # F0 differs in the look-ahead frames only
+
+
+@pytest.mark.parametrize("name,dims", [("tiny", D.FLOW_TINY), ("full", D.FLOW_FULL)])
+def test_flow_oracle_matches_reference(golden, name, dims):
+    g = golden(f"flow_{name}")
+    sd = synth.flow_state_dict(dims, g["seed"])
+    assert abs(_checksum(sd) - g["sd_checksum"]) < 1e-6 * g["sd_checksum"]
+    noise = synth.flow_noise(dims)
+    assert abs(noise[0, 0, 0].item() + 1.1258) < 1e-4      # flow_matching.py:200-201 table
+    for key, streaming, finalize in (("full", False, True), ("stream", True, True), ("chunk", True, False)):
+        mel = flow_ref.inference(sd, g["token"], g["embedding"], noise, dims, g["n_steps"], g["prompt_token"],
+                                 g["prompt_feat"], streaming=streaming, finalize=finalize)
+        assert mel.shape == g["mel_" + key].shape
+        assert (mel - g["mel_" + key]).abs().max() < 2e-4
+    e = g["est_in"]
+    est = flow_ref.dit_forward({k: v.float() for k, v in sd.items()}, e["x"], e["mu"], e["t"], e["spks"], e["cond"], dims)
+    assert (est - g["est_out"]).abs().max() < 1e-4
+
+
+def test_flow_t_schedule_and_mask():
+    ts = flow_ref.t_schedule(10)
+    assert ts[0] == 0 and abs(ts[-1].item() - 1.0) < 1e-6 and (ts[1:] > ts[:-1]).all()
+    m = flow_ref.attn_mask(4, [4], True, 2)[0]
+    assert m.int().tolist() == [[1, 1, 0, 0], [1, 1, 0, 0], [1, 1, 1, 1], [1, 1, 1, 1]]   # mask.py:141-146
+    m = flow_ref.attn_mask(4, [3], False, 2)[0]
+    assert m.int().tolist() == [[1, 1, 1, 0]] * 4
+
+
+@pytest.mark.parametrize("name,dims", [("tiny", D.LLM_TINY), pytest.param("full", D.LLM_FULL, marks=pytest.mark.slow)])
+def test_llm_oracle_matches_reference(golden, name, dims):
+    g = golden(f"llm_{name}")
+    sd = synth.llm_state_dict(dims, g["seed"])
+    assert abs(_checksum(sd) - g["sd_checksum"]) < 1e-6 * g["sd_checksum"]
+    for c in g["cases"]:
+        us = llm_ref.UStream(g["u"])
+        toks = llm_ref.inference(sd, dims, g["text"], g["prompt_text"], g["prompt_speech"], us, head_k=c["K"],
+                                 sp=c["sp"], min_ratio=c["ratio"][0], max_ratio=c["ratio"][1])
+        assert toks == c["tokens"]                          # bit-exact token ids on the pinned u-stream
+        assert us.pos == c["u_used"]
+    o = llm_ref.LlmOracle(sd, dims)
+    hid = o.forward_rows(o.prompt_embeds(g["text"], g["prompt_text"], g["prompt_speech"]))
+    assert (hid[-1] - g["last_hidden"]).abs().max() < 1e-4
+    lp = torch.stack([o.head_logp(j, hid[-1]) for j in range(dims.mtp_heads)])
+    assert (lp - g["head_logp"]).abs().max() < 2e-4
+
+
+def test_sampler_edges():
+    # kept set = longest prefix with cum_before < top_p and count < top_k (common.py:146-156)
+    logp = torch.log(torch.tensor([0.5, 0.3, 0.1, 0.06, 0.04]))
+    us = llm_ref.UStream(torch.tensor([0.0, 0.7]))
+    assert llm_ref.nucleus_sampling(logp, us, top_p=0.8, top_k=25) == 0
+    assert llm_ref.nucleus_sampling(logp, us, top_p=0.8, top_k=25) == 1     # kept {0,1}: 0.7*0.8=0.56 > 0.5
+    us = llm_ref.UStream(torch.tensor([0.99]))
+    assert llm_ref.nucleus_sampling(logp, us, top_p=0.8, top_k=25) == 1     # crossing element (0.3) is kept, 0.1 is not
+    us = llm_ref.UStream(torch.tensor([0.99]))
+    assert llm_ref.nucleus_sampling(logp, us, top_p=0.99, top_k=1) == 0     # top_k bound
+    # repetition-aware fallback draws a second u over the full distribution (common.py:139-143)
+    us = llm_ref.UStream(torch.tensor([0.0, 0.999]))
+    assert llm_ref.ras_sampling(logp, [0, 0, 0], us, top_p=0.8, top_k=25, win_size=3, tau_r=0.1) == 4
+    assert us.pos == 2
+    # stable sort: equal probabilities keep index order
+    logp = torch.log(torch.tensor([0.25, 0.25, 0.25, 0.25]))
+    us = llm_ref.UStream(torch.tensor([0.30]))
+    assert llm_ref.nucleus_sampling(logp, us, top_p=0.6, top_k=25) == 0   # kept {0,1,2}: .3*.75=.225<.25
