@@ -1,0 +1,69 @@
+// C-ABI plumbing: engine lifecycle, tensor registry, error state (include/hydravox_b200.h).
+#include "common.cuh"
+#include <cstring>
+
+namespace hvx {
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace hvx
+
+using namespace hvx;
+
+extern "C" const char* hvx_last_error(void) { return g_err; }
+extern "C" int hvx_version(void) { return 100; }
+
+extern "C" hvx_status hvx_create(hvx_engine** out, const hvx_config* cfg) {
+  HVX_CHECK(out && cfg, HVX_ERR_ARG, "hvx_create: null argument");
+  int dev = 0, n = 0;
+  cudaError_t ce = cudaGetDeviceCount(&n);
+  HVX_CHECK(ce == cudaSuccess && n > 0, HVX_ERR_CUDA, "hvx_create: no CUDA device (%s) — this engine has no CPU fallback",
+            cudaGetErrorString(ce));
+  HVX_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  HVX_CUDA(cudaGetDeviceProperties(&prop, dev));
+  HVX_CHECK(prop.major == 10, HVX_ERR_UNSUPPORTED, "hvx_create: device sm_%d%d is not Blackwell sm_100 (kernels are sm_100a only)",
+            prop.major, prop.minor);
+  hvx_engine* e = new hvx_engine();
+  e->cfg = *cfg;
+  e->sm_count = prop.multiProcessorCount;
+  *out = e;
+  return HVX_OK;
+}
+
+extern "C" hvx_status hvx_destroy(hvx_engine* e) {
+  if (!e) return HVX_OK;
+  hift_free(e);
+  flow_free(e);
+  llm_free(e);
+  delete e;
+  return HVX_OK;
+}
+
+extern "C" hvx_status hvx_set_tensor(hvx_engine* e, int stage, const char* name, const void* dptr, int dtype,
+                                     const int64_t* shape, int ndim) {
+  HVX_CHECK(e && name && dptr && shape, HVX_ERR_ARG, "hvx_set_tensor: null argument");
+  HVX_CHECK(stage >= 0 && stage < 3 && ndim >= 1 && ndim <= 4, HVX_ERR_ARG, "hvx_set_tensor(%s): bad stage/ndim", name);
+  Tensor t;
+  t.p = dptr; t.dtype = dtype; t.ndim = ndim;
+  for (int i = 0; i < ndim; i++) t.shape[i] = shape[i];
+  e->tensors[stage][name] = t;
+  return HVX_OK;
+}
+
+extern "C" hvx_status hvx_finalize(hvx_engine* e, int stage) {
+  HVX_CHECK(e, HVX_ERR_ARG, "hvx_finalize: null engine");
+  switch (stage) {
+    case HVX_STAGE_HIFT: return hift_finalize(e);
+    case HVX_STAGE_FLOW: return flow_finalize(e);
+    case HVX_STAGE_LLM: return llm_finalize(e);
+  }
+  set_error("hvx_finalize: bad stage %d", stage);
+  return HVX_ERR_ARG;
+}
+
+extern "C" int64_t hvx_kernel_launches(hvx_engine* e) { return e ? e->launches : 0; }

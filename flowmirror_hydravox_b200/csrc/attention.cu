@@ -1,0 +1,221 @@
+// tcgen05 flash-style attention for the DiT estimator (see attention.cuh).
+#include "attention.cuh"
+
+namespace hvx {
+
+constexpr int AT_Q_BYTES = 128 * 128;        // 128 rows x 64 bf16
+constexpr int AT_K_BYTES = 128 * 128;        // 128 keys x 64 bf16
+constexpr int AT_V_BYTES = 2 * 64 * 128;     // two K-halves of V^T: 64 dims x 64 keys each
+constexpr int AT_P_BYTES = 2 * 128 * 128;    // two 64-key atoms of P
+constexpr int AT_OFF_Q = 0;
+constexpr int AT_OFF_K = AT_OFF_Q + AT_Q_BYTES;
+constexpr int AT_OFF_V = AT_OFF_K + 2 * AT_K_BYTES;
+constexpr int AT_OFF_P = AT_OFF_V + 2 * AT_V_BYTES;
+constexpr int AT_OFF_BAR = AT_OFF_P + AT_P_BYTES;
+constexpr int AT_SMEM = AT_OFF_BAR + 128 + 1024;
+constexpr uint32_t AT_TMEM_COLS = 256;
+
+__global__ void __launch_bounds__(128)
+dit_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                     const __grid_constant__ CUtensorMap tm_v, int k_col0, AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + AT_OFF_BAR);
+  uint64_t* kv_full = q_full + 1;    // [2]
+  uint64_t* s_full = kv_full + 2;
+  uint64_t* o_full = s_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * 128;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int T = a.T;
+  const int row_in_batch = q0 + tid;
+  const int klim_row = a.chunk > 0 ? min(T, (row_in_batch / a.chunk + 1) * a.chunk) : T;
+  const int klim_tile = a.chunk > 0 ? min(T, ((min(q0 + 127, T - 1)) / a.chunk + 1) * a.chunk) : T;
+  const int nkv = (klim_tile + 127) / 128;
+
+  if (tid == 0) {
+    tc::tma_prefetch_desc(&tm_q); tc::tma_prefetch_desc(&tm_k); tc::tma_prefetch_desc(&tm_v);
+    tc::mbar_init(q_full, 1); tc::mbar_init(&kv_full[0], 1); tc::mbar_init(&kv_full[1], 1);
+    tc::mbar_init(s_full, 1); tc::mbar_init(o_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 0) tc::tmem_alloc(tmem_slot, AT_TMEM_COLS);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_s = *tmem_slot;
+  const uint32_t tmem_o = tmem_s + 128;
+  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+
+  auto load_kv = [&](int j) {
+    const int bsel = j & 1;
+    tc::mbar_expect_tx(&kv_full[bsel], AT_K_BYTES + AT_V_BYTES);
+    tc::tma_load_2d(smem + AT_OFF_K + bsel * AT_K_BYTES, &tm_k, &kv_full[bsel], k_col0 + h * 64, b * T + j * 128);
+    uint8_t* sv = smem + AT_OFF_V + bsel * AT_V_BYTES;
+    tc::tma_load_2d(sv, &tm_v, &kv_full[bsel], j * 128, (b * a.heads + h) * 64);
+    tc::tma_load_2d(sv + 64 * 128, &tm_v, &kv_full[bsel], j * 128 + 64, (b * a.heads + h) * 64);
+  };
+  if (tid == 0) {
+    tc::mbar_expect_tx(q_full, AT_Q_BYTES);
+    tc::tma_load_2d(smem + AT_OFF_Q, &tm_q, q_full, h * 64, b * T + q0);
+    load_kv(0);
+  }
+
+  constexpr uint32_t idesc_s = tc::umma_idesc_bf16(128, 128);
+  constexpr uint32_t idesc_o = tc::umma_idesc_bf16(128, 64);
+  const float sc = 0.125f * 1.4426950408889634f;     // dim_head^-0.5 * log2(e)
+  float m_run = -INFINITY, l_run = 0.f;
+  float o_acc[64];
+#pragma unroll
+  for (int i = 0; i < 64; i++) o_acc[i] = 0.f;
+  uint8_t* sp = smem + AT_OFF_P;
+
+  for (int j = 0; j < nkv; j++) {
+    const int bsel = j & 1;
+    if (tid == 0) {
+      if (j == 0) tc::mbar_wait(q_full, 0);
+      tc::mbar_wait(&kv_full[bsel], (j >> 1) & 1);
+      tc::tc_fence_after();
+      const uint64_t dq = tc::umma_desc_k128(tc::smem_u32(smem + AT_OFF_Q));
+      const uint64_t dk = tc::umma_desc_k128(tc::smem_u32(smem + AT_OFF_K + bsel * AT_K_BYTES));
+#pragma unroll
+      for (int k = 0; k < 4; k++) tc::umma_f16(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
+      tc::umma_commit(s_full);
+      if (j + 1 < nkv) load_kv(j + 1);
+    }
+    __syncwarp();
+    tc::mbar_wait(s_full, j & 1);
+    tc::tc_fence_after();
+
+    // ---- online softmax on this thread's row; P written straight into the swizzled A-operand tile
+    float m_new = m_run;
+    const int kbase = j * 128;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tc::tmem_ld_32x32(tmem_s + lane_off + (uint32_t)c0, v);
+        tc::tmem_ld_wait();
+        if (pass == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            const float s = (kbase + c0 + i < klim_row) ? __uint_as_float(v[i]) * sc : -INFINITY;
+            m_new = fmaxf(m_new, s);
+          }
+        } else {
+          float psum = 0.f;
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float s0 = (kbase + c0 + i < klim_row) ? __uint_as_float(v[i]) * sc : -INFINITY;
+            const float s1 = (kbase + c0 + i + 1 < klim_row) ? __uint_as_float(v[i + 1]) * sc : -INFINITY;
+            const float p0 = exp2f(s0 - m_new), p1 = exp2f(s1 - m_new);
+            psum += p0 + p1;
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(p0, p1);
+            pk[i >> 1] = *reinterpret_cast<uint32_t*>(&t2);
+          }
+          l_run += psum;
+          // 32 keys = 4 chunks of 16 B in atom (c0/64), chunk index ((c0%64)/8 + q) ^ (row & 7)
+          uint8_t* rowp = sp + (c0 >> 6) * (128 * 128) + tid * 128;
+          const int cb = (c0 & 63) >> 3;
+#pragma unroll
+          for (int qd = 0; qd < 4; qd++) {
+            uint4 val = make_uint4(pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2], pk[4 * qd + 3]);
+            *reinterpret_cast<uint4*>(rowp + (((cb + qd) ^ (tid & 7)) << 4)) = val;
+          }
+        }
+      }
+      if (pass == 0) {
+        // rescale the running sum before adding this tile's probabilities
+        const float alpha = exp2f(m_run - m_new);      // m_run=-inf on the first tile -> 0
+        l_run *= alpha;
+#pragma unroll
+        for (int i = 0; i < 64; i++) o_acc[i] *= alpha;
+        m_run = m_new;
+      }
+    }
+    tc::fence_proxy_async();          // make the generic-proxy P stores visible to the tensor core
+    tc::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc::tc_fence_after();
+      const uint32_t pv = tc::smem_u32(smem + AT_OFF_V + bsel * AT_V_BYTES);
+      const uint32_t pp = tc::smem_u32(sp);
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        const uint64_t dp = tc::umma_desc_k128(pp + half * (128 * 128));
+        const uint64_t dv = tc::umma_desc_k128(pv + half * (64 * 128));
+#pragma unroll
+        for (int k = 0; k < 4; k++) tc::umma_f16(tmem_o, dp + 2 * k, dv + 2 * k, idesc_o, (half | k) ? 1u : 0u);
+      }
+      tc::umma_commit(o_full);
+    }
+    __syncwarp();
+    tc::mbar_wait(o_full, j & 1);
+    tc::tc_fence_after();
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      uint32_t v[32];
+      tc::tmem_ld_32x32(tmem_o + lane_off + (uint32_t)c0, v);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i++) o_acc[c0 + i] += __uint_as_float(v[i]);
+    }
+    tc::tc_fence_before();
+  }
+
+  if (row_in_batch < T) {
+    const float inv = 1.0f / l_run;
+    __nv_bfloat16* o = a.out + (size_t)(b * T + row_in_batch) * a.ld_out + h * 64;
+#pragma unroll
+    for (int i = 0; i < 64; i += 8) {
+      uint4 pk;
+      __nv_bfloat162 t0 = __floats2bfloat162_rn(o_acc[i] * inv, o_acc[i + 1] * inv);
+      __nv_bfloat162 t1 = __floats2bfloat162_rn(o_acc[i + 2] * inv, o_acc[i + 3] * inv);
+      __nv_bfloat162 t2 = __floats2bfloat162_rn(o_acc[i + 4] * inv, o_acc[i + 5] * inv);
+      __nv_bfloat162 t3 = __floats2bfloat162_rn(o_acc[i + 6] * inv, o_acc[i + 7] * inv);
+      pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+      pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+      *reinterpret_cast<uint4*>(o + i) = pk;
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { __syncwarp(); tc::tmem_dealloc(tmem_s, AT_TMEM_COLS); }
+}
+
+hvx_status dit_attention(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* qk, int ld_qk, int k_col0,
+                         const __nv_bfloat16* vt, int vt_ld, const AttnArgs& a) {
+  CUtensorMap tq, tk, tv;
+  const uint64_t rows = (uint64_t)a.n_batch * a.T;
+  HVX_CHECK(make_tmap_bf16_2d(&tq, qk, rows, ld_qk, ld_qk, 128, 64), HVX_ERR_CUDA, "attention: tensor map Q failed");
+  HVX_CHECK(make_tmap_bf16_2d(&tk, qk, rows, ld_qk, ld_qk, 128, 64), HVX_ERR_CUDA, "attention: tensor map K failed");
+  HVX_CHECK(make_tmap_bf16_2d(&tv, vt, (uint64_t)a.n_batch * a.heads * 64, vt_ld, vt_ld, 64, 64), HVX_ERR_CUDA,
+            "attention: tensor map V^T failed");
+  static bool attr_set = false;
+  if (!attr_set) {
+    HVX_CUDA(cudaFuncSetAttribute(dit_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(a.T, 128), a.heads, a.n_batch);
+  dit_attention_kernel<<<grid, 128, AT_SMEM, st>>>(tq, tk, tv, k_col0, a);
+  HVX_LAUNCH_CHECK(e);
+  return HVX_OK;
+}
+
+}  // namespace hvx
+
+using namespace hvx;
+
+// Diagnostic entry (tests/test_attention_gpu.py): qk = [B*T][2*H*64] (q | k), vt = [B*H*64][vt_ld]
+extern "C" hvx_status hvx_attention_bf16(hvx_engine* e, const void* qk, const void* vt, int vt_ld, void* out, int B, int T,
+                                         int H, int chunk, void* stream) {
+  HVX_CHECK(e, HVX_ERR_ARG, "null engine");
+  AttnArgs a;
+  a.T = T; a.heads = H; a.n_batch = B; a.chunk = chunk; a.ld_out = H * 64; a.out = (__nv_bfloat16*)out;
+  return dit_attention(e, (cudaStream_t)stream, (const __nv_bfloat16*)qk, 2 * H * 64, H * 64, (const __nv_bfloat16*)vt,
+                       vt_ld, a);
+}

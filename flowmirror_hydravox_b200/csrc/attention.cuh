@@ -1,0 +1,30 @@
+// DiT self-attention on tcgen05 (replaces F.scaled_dot_product_attention in
+// cosyvoice/flow/DiT/modules.py:349-407; masks from cosyvoice/utils/mask.py:127-236).
+//
+// One CTA = (batch, head, 128-query tile), 128 threads.  TMEM lane == query row == thread, so the
+// online softmax needs no cross-thread reduction:
+//   S (128x128 fp32, TMEM cols 0..127)   = Q K_j^T      tcgen05.mma M128 N128 K16 x4, operands by TMA (SW128)
+//   P (bf16, smem, SW128 K-major)        = exp2(S*c - m) written by the row's own thread
+//   O_j (128x64 fp32, TMEM cols 128..191) = P V_j        tcgen05.mma M128 N64 K16 x8, V^T tile by TMA
+//   o_acc (registers)                    = o_acc*alpha + O_j
+// K/V^T tiles are double-buffered; two CTAs co-reside per SM (112 KB smem, 256 TMEM columns each) so
+// one CTA's softmax overlaps the other's MMAs.
+#pragma once
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace hvx {
+
+struct AttnArgs {
+  int T;            // frames per batch row (queries == keys)
+  int heads;
+  int n_batch;
+  int chunk;        // >0: streaming block-causal mask, key j visible to query i iff j < (i/chunk+1)*chunk
+  int ld_out;       // = heads*64
+  __nv_bfloat16* out;   // [n_batch*T][heads*64]
+};
+
+hvx_status dit_attention(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* qk, int ld_qk, int k_col0,
+                         const __nv_bfloat16* vt, int vt_ld, const AttnArgs& a);
+
+}  // namespace hvx

@@ -1,0 +1,96 @@
+// Shared host-side plumbing of libhydravox_b200 (engine object, tensor registry, error state).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <cstdio>
+#include <cstdarg>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "../../include/hydravox_b200.h"
+
+namespace hvx {
+
+void set_error(const char* fmt, ...);
+
+struct Tensor {
+  const void* p = nullptr;
+  int dtype = HVX_F32;
+  int ndim = 0;
+  int64_t shape[4] = {0, 0, 0, 0};
+  int64_t numel() const { int64_t n = 1; for (int i = 0; i < ndim; i++) n *= shape[i]; return n; }
+  const float* f32() const { return (const float*)p; }
+  const __nv_bfloat16* bf16() const { return (const __nv_bfloat16*)p; }
+};
+
+struct DevBuf {              // engine-owned scratch that grows on demand (never shrinks)
+  void* p = nullptr;
+  size_t bytes = 0;
+  void* get(size_t need) {
+    if (need > bytes) {
+      if (p) cudaFree(p);
+      size_t cap = need + need / 4;
+      if (cudaMalloc(&p, cap) != cudaSuccess) { p = nullptr; bytes = 0; return nullptr; }
+      bytes = cap;
+    }
+    return p;
+  }
+  ~DevBuf() { if (p) cudaFree(p); }
+};
+
+struct HiftState;
+struct FlowState;
+struct LlmState;
+
+}  // namespace hvx
+
+struct hvx_engine {
+  hvx_config cfg;
+  std::unordered_map<std::string, hvx::Tensor> tensors[3];
+  hvx::HiftState* hift = nullptr;
+  hvx::FlowState* flow = nullptr;
+  hvx::LlmState* llm = nullptr;
+  int64_t launches = 0;
+  int sm_count = 148;
+  const hvx::Tensor* find(int stage, const std::string& name) const {
+    auto it = tensors[stage].find(name);
+    return it == tensors[stage].end() ? nullptr : &it->second;
+  }
+};
+
+#define HVX_CUDA(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      hvx::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return HVX_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+#define HVX_CHECK(cond, code, ...)                 \
+  do {                                             \
+    if (!(cond)) { hvx::set_error(__VA_ARGS__); return (code); } \
+  } while (0)
+
+#define HVX_LAUNCH_CHECK(e)                                                                    \
+  do {                                                                                         \
+    (e)->launches++;                                                                           \
+    cudaError_t _e = cudaGetLastError();                                                       \
+    if (_e != cudaSuccess) {                                                                   \
+      hvx::set_error("%s:%d kernel launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return HVX_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+namespace hvx {
+// stage entry points implemented in hift.cu / flow.cu / llm.cu
+hvx_status hift_finalize(hvx_engine* e);
+void hift_free(hvx_engine* e);
+hvx_status flow_finalize(hvx_engine* e);
+void flow_free(hvx_engine* e);
+hvx_status llm_finalize(hvx_engine* e);
+void llm_free(hvx_engine* e);
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+}  // namespace hvx

@@ -1,0 +1,298 @@
+// tcgen05 + TMA GEMM (see gemm.cuh).  Used by the DiT estimator's linears (DiT/modules.py:349-407,
+// 500-530) and by anything else on the path that is a dense projection over >= 16 rows.
+#include "gemm.cuh"
+#include <cuda.h>
+#include <mutex>
+
+namespace hvx {
+
+// ------------------------------------------------------------------ host: tensor maps
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  });
+  return fn;
+}
+
+bool make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                       uint32_t box_rows, uint32_t box_cols) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+bool make_tmap_bf16_3d(CUtensorMap* out, const void* gptr, uint64_t batches, uint64_t rows, uint64_t cols,
+                       uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {cols, rows, batches};
+  cuuint64_t strides[2] = {row_stride_elems * 2, row_stride_elems * 2 * rows};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(gptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// ------------------------------------------------------------------ device
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // barriers + tmem slot + alignment slack
+};
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == ACT_GELU_TANH) {
+    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+    return 0.5f * v * (1.0f + tanhf(k0 * (v + k1 * v * v * v)));
+  }
+  if (act == ACT_SILU) return v / (1.0f + __expf(-v));
+  if (act == ACT_MISH) { const float sp = v > 20.0f ? v : log1pf(expf(v)); return v * tanhf(sp); }
+  return v;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N, int K,
+                 GemmEpi epi, GemmAddr ad, int tiles_per_batch) {
+  using S = GemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int batch = blockIdx.y / tiles_per_batch;
+  const int m0 = (blockIdx.y - batch * tiles_per_batch) * BM;      // row inside the batch
+  const int nkb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tma_a);
+    tc::tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < STAGES; s++) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    tc::mbar_init(tmem_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, BN);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; kb++) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        tc::mbar_wait(&empty_bar[s], ph ^ 1);
+        tc::mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+        uint8_t* sa = smem + s * S::STAGE_BYTES;
+        tc::tma_load_3d(sa, &tma_a, &full_bar[s], ad.a_col0 + blockIdx.x * ad.a_col_per_ntile + kb * ad.a_col_step,
+                        m0 + ad.a_row0 + kb * ad.a_row_step, batch);
+        tc::tma_load_2d(sa + S::A_BYTES, &tma_b, &full_bar[s], kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::umma_idesc_bf16(BM, BN);
+      for (int kb = 0; kb < nkb; kb++) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        tc::mbar_wait(&full_bar[s], ph);
+        tc::tc_fence_after();
+        const uint32_t sa = tc::smem_u32(smem + s * S::STAGE_BYTES);
+        const uint64_t adesc = tc::umma_desc_k128(sa);
+        const uint64_t bdesc = tc::umma_desc_k128(sa + S::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; k++)
+          tc::umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+        tc::umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs retire
+      }
+      tc::umma_commit(tmem_full);                // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: warp q owns TMEM lanes [32q, 32q+32) = tile rows
+    const int q = warp & 3;
+    const int row_b = m0 + q * 32 + lane;
+    const int row = batch * ad.rows_per_batch + row_b;
+    tc::mbar_wait(tmem_full, 0);
+    tc::tc_fence_after();
+    const bool row_ok = row_b < ad.rows_per_batch && row < M;
+    const int bidx = row / epi.rows_per_batch;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tc::tmem_ld_wait();
+      const int col0 = n0 + c0;
+      if (!row_ok || col0 >= N) continue;
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        float x = __uint_as_float(v[j]);
+        if (epi.bias && col0 + j < N) x += __ldg(epi.bias + col0 + j);
+        f[j] = act_apply(x, epi.act);
+      }
+      if (epi.mode == EPI_BF16) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(epi.out) + (size_t)row * epi.ldo + col0;
+        if (col0 + 32 <= N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 pk;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(f[j], f[j + 1]), t1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), t3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+            pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+            *reinterpret_cast<uint4*>(o + j) = pk;
+          }
+        } else {
+          #pragma unroll
+          for (int j = 0; j < 32; j++) if (col0 + j < N) o[j] = __float2bfloat16(f[j]);
+        }
+      } else if (epi.mode == EPI_F32) {
+        float* o = reinterpret_cast<float*>(epi.out) + (size_t)row * epi.ldo + col0;
+        if (epi.resid) {
+          const float* r = epi.resid + (size_t)row * epi.ldo + col0;
+          #pragma unroll
+          for (int j = 0; j < 32; j++) if (col0 + j < N) f[j] += r[j];
+        }
+        #pragma unroll
+        for (int j = 0; j < 32; j++) if (col0 + j < N) o[j] = f[j];
+        if (epi.out2) {
+          __nv_bfloat16* o2 = epi.out2 + (size_t)row * epi.ldo + col0;
+          #pragma unroll
+          for (int j = 0; j < 32; j++) if (col0 + j < N) o2[j] = __float2bfloat16(f[j]);
+        }
+      } else if (epi.mode == EPI_RESID_GATE) {
+        float* o = reinterpret_cast<float*>(epi.out) + (size_t)row * epi.ldo + col0;
+        const float* g = epi.gate + (size_t)bidx * epi.gate_ld + col0;
+        if (col0 + 32 <= N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 cur = *reinterpret_cast<float4*>(o + j);
+            const float4 gg = __ldg(reinterpret_cast<const float4*>(g + j));
+            cur.x = fmaf(gg.x, f[j], cur.x); cur.y = fmaf(gg.y, f[j + 1], cur.y);
+            cur.z = fmaf(gg.z, f[j + 2], cur.z); cur.w = fmaf(gg.w, f[j + 3], cur.w);
+            *reinterpret_cast<float4*>(o + j) = cur;
+          }
+        } else {
+          #pragma unroll
+          for (int j = 0; j < 32; j++) if (col0 + j < N) o[j] = fmaf(__ldg(g + j), f[j], o[j]);
+        }
+      } else {  // EPI_QKV
+        const int t = row - bidx * epi.T;       // rows_per_batch == T
+        if (col0 < epi.n_qk) {
+          const int dq = epi.n_qk >> 1;
+          const int cl = col0 % dq;
+          if (cl < 64) {
+            const float* cs = epi.rope_cos + (size_t)t * 32 + (cl >> 1);
+            const float* sn = epi.rope_sin + (size_t)t * 32 + (cl >> 1);
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+              const float c = __ldg(cs + i), s = __ldg(sn + i);
+              const float x1 = f[2 * i], x2 = f[2 * i + 1];
+              f[2 * i] = x1 * c - x2 * s;
+              f[2 * i + 1] = x2 * c + x1 * s;
+            }
+          }
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(epi.out) + (size_t)row * epi.ldo + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 pk;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(f[j], f[j + 1]), t1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), t3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+            pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+            *reinterpret_cast<uint4*>(o + j) = pk;
+          }
+        } else {
+          const int cv = col0 - epi.n_qk;
+          const int h = cv >> 6, d0 = cv & 63;
+          __nv_bfloat16* o = epi.vt + ((size_t)(bidx * epi.heads + h) * 64 + d0) * epi.vt_ld + t;
+#pragma unroll
+          for (int j = 0; j < 32; j++) o[(size_t)j * epi.vt_ld] = __float2bfloat16(f[j]);
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tc::tmem_dealloc(tmem_base, BN); }
+}
+
+template <int BN, int STAGES>
+static hvx_status launch_gemm(hvx_engine* e, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
+                              int K, const GemmEpi& epi, const GemmAddr& ad) {
+  using S = GemmSmem<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    HVX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr_set = true;
+  }
+  const int tiles_per_batch = cdiv(ad.rows_per_batch, BM);
+  dim3 grid(cdiv(N, BN), tiles_per_batch * ad.n_batch);
+  gemm_bf16_kernel<BN, STAGES><<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, M, N, K, epi, ad, tiles_per_batch);
+  HVX_LAUNCH_CHECK(e);
+  return HVX_OK;
+}
+
+hvx_status gemm_bf16(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb,
+                     int M, int N, int K, const GemmEpi& epi, const GemmAddr* addr) {
+  HVX_CHECK(M > 0 && N > 0 && K > 0, HVX_ERR_ARG, "gemm: empty problem %dx%dx%d", M, N, K);
+  GemmAddr ad;
+  if (addr) ad = *addr;
+  if (ad.rows_per_batch == 0) ad.rows_per_batch = M;
+  if (ad.a_cols == 0) ad.a_cols = K;
+  HVX_CHECK((lda % 8) == 0 && (ldb % 8) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0, HVX_ERR_ARG,
+            "gemm: operands must be 16-byte aligned with leading dims multiple of 8 (lda=%d ldb=%d)", lda, ldb);
+  CUtensorMap ta, tb;
+  HVX_CHECK(make_tmap_bf16_3d(&ta, A, ad.n_batch, ad.rows_per_batch, ad.a_cols, lda, BM, BK), HVX_ERR_CUDA,
+            "gemm: cuTensorMapEncodeTiled(A) failed");
+  if (N <= 64 || ad.a_col_per_ntile == 64) {
+    HVX_CHECK(make_tmap_bf16_2d(&tb, B, N, K, ldb, 64, BK), HVX_ERR_CUDA, "gemm: cuTensorMapEncodeTiled(B) failed");
+    return launch_gemm<64, 4>(e, st, ta, tb, M, N, K, epi, ad);
+  }
+  HVX_CHECK(make_tmap_bf16_2d(&tb, B, N, K, ldb, 128, BK), HVX_ERR_CUDA, "gemm: cuTensorMapEncodeTiled(B) failed");
+  return launch_gemm<128, 3>(e, st, ta, tb, M, N, K, epi, ad);
+}
+
+}  // namespace hvx
+
+using namespace hvx;
+
+// Diagnostic entry (tests/test_gemm_gpu.py): C = act(A*B^T + bias) with bf16 or fp32 output.
+extern "C" hvx_status hvx_gemm_bf16(hvx_engine* e, const void* A, const void* B, const float* bias, void* C, int M, int N,
+                                    int K, int out_f32, int act, void* stream) {
+  HVX_CHECK(e, HVX_ERR_ARG, "null engine");
+  GemmEpi epi;
+  epi.mode = out_f32 ? EPI_F32 : EPI_BF16;
+  epi.act = act;
+  epi.bias = bias;
+  epi.out = C;
+  epi.ldo = N;
+  return gemm_bf16(e, (cudaStream_t)stream, (const __nv_bfloat16*)A, K, (const __nv_bfloat16*)B, K, M, N, K, epi);
+}

@@ -1,0 +1,503 @@
+// HiFT vocoder stage (mel -> waveform) for sm_100a.
+// Replaces CausalHiFTGenerator.inference / decode (cosyvoice/hifigan/generator.py:672-726),
+// CausalConvRNNF0Predictor.forward (cosyvoice/hifigan/f0_predictor.py:95-103),
+// SourceModuleHnNSF/SineGen2 (generator.py:233-375) and _stft/_istft (:491-505).
+//
+// Data layout: every activation is channel-major fp32 [C][L] (time contiguous), one utterance per
+// call.  Conv weights are pre-folded (weight-norm) and packed [Cin][K][Cout] by
+// flowmirror_hydravox_b200/weights.py so a (ci-chunk, all taps, 64 co) slab is one coalesced read.
+//
+// Kernels (all fp32 on the CUDA cores: the F0 track and the exp/sin ISTFT head are precision
+// critical — generator.py:715 — and the stage is <15 % of the pipeline):
+//   conv1d_tile_kernel   smem-tiled causal conv: 64 co x 256 t per CTA, 8x8 register tile per
+//                        thread, fused nearest-upsample / dilation / Snake|lrelu pre-activation
+//                        on the staged input tile, fused bias + ELU + residual(s) + scaled
+//                        accumulate epilogue (the 3-resblock mean never materialises).
+//   conv1d_strided_kernel  direct kernel for the three tiny source down-convs (18 -> C, k<=30).
+//   f0_head / phase_scan / frame_sin / source_synth / stft16 / istft16 (frame + overlap-add).
+#include "common.cuh"
+#include <cmath>
+#include <cstring>
+
+namespace hvx {
+
+constexpr int CO_TILE = 64;
+constexpr int T_TILE = 256;
+constexpr int CI_CHUNK = 8;
+constexpr int K_MAX = 16;
+constexpr int HALO_MAX = 64;          // (K-1)*dil <= 50 on this path
+constexpr int XW = T_TILE + HALO_MAX;
+
+struct ConvArgs {
+  const float* x; const float* w; const float* bias; float* y;
+  const float* res1; const float* res2; const float* alpha;
+  int Cin, Cout, K, dil, up, pad_left, Lin, Lout, ldx;
+  int pre_act;          // 0 none, 1 leaky-relu(slope), 2 snake(alpha)
+  float slope;
+  int post_elu, accumulate, reflect1;
+  float out_scale;
+};
+
+__device__ __forceinline__ float pre_activate(float v, int mode, float slope, float a) {
+  if (mode == 1) return v > 0.f ? v : v * slope;
+  if (mode == 2) { float s = sinf(v * a); return v + (1.0f / (a + 1e-9f)) * (s * s); }
+  return v;
+}
+
+__global__ void __launch_bounds__(256) conv1d_tile_kernel(ConvArgs p) {
+  __shared__ __align__(16) float sw[CI_CHUNK][K_MAX][CO_TILE];
+  __shared__ float sx[CI_CHUNK][XW];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int t0 = blockIdx.x * T_TILE;
+  const int co0 = blockIdx.y * CO_TILE;
+  const int halo = (p.K - 1) * p.dil;
+  const int W = T_TILE + halo;
+  const int Lup = p.Lin * p.up;
+  float acc[8][8];
+#pragma unroll
+  for (int c = 0; c < 8; c++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[c][j] = 0.f;
+
+  for (int ci0 = 0; ci0 < p.Cin; ci0 += CI_CHUNK) {
+    // stage weights [ci][k][co]
+    const int nw = CI_CHUNK * p.K * CO_TILE;
+    for (int i = tid; i < nw; i += 256) {
+      int c = i % CO_TILE, r = i / CO_TILE;
+      int k = r % p.K, ci = r / p.K;
+      float v = 0.f;
+      if (ci0 + ci < p.Cin && co0 + c < p.Cout)
+        v = __ldg(p.w + ((size_t)(ci0 + ci) * p.K + k) * p.Cout + co0 + c);
+      sw[ci][k][c] = v;
+    }
+    // stage input tile with fused upsample + pre-activation
+    for (int i = tid; i < CI_CHUNK * W; i += 256) {
+      int ci = i / W, o = i - ci * W;
+      int v = t0 + o - p.pad_left;
+      float val = 0.f;
+      if (ci0 + ci < p.Cin && v >= 0 && v < Lup) {
+        float a = (p.pre_act == 2) ? __ldg(p.alpha + ci0 + ci) : 0.f;
+        val = pre_activate(__ldg(p.x + (size_t)(ci0 + ci) * p.ldx + v / p.up), p.pre_act, p.slope, a);
+      }
+      sx[ci][o] = val;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int ci = 0; ci < CI_CHUNK; ci++) {
+#pragma unroll 1
+      for (int k = 0; k < p.K; k++) {
+        const float4 wa = *reinterpret_cast<const float4*>(&sw[ci][k][wid * 8]);
+        const float4 wb = *reinterpret_cast<const float4*>(&sw[ci][k][wid * 8 + 4]);
+        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+        float xv[8];
+        const float* xr = &sx[ci][lane + k * p.dil];
+#pragma unroll
+        for (int j = 0; j < 8; j++) xv[j] = xr[32 * j];
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+#pragma unroll
+          for (int j = 0; j < 8; j++) acc[c][j] = fmaf(wv[c], xv[j], acc[c][j]);
+      }
+    }
+    __syncthreads();
+  }
+  // epilogue
+  const int Ly = p.Lout + (p.reflect1 ? 1 : 0);
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const int co = co0 + wid * 8 + c;
+    if (co >= p.Cout) continue;
+    const float b = p.bias ? __ldg(p.bias + co) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int t = t0 + lane + 32 * j;
+      if (t >= p.Lout) continue;
+      float v = acc[c][j] + b;
+      if (p.post_elu) v = v > 0.f ? v : expm1f(v);
+      const int nrep = (p.reflect1 && t == 1) ? 2 : 1;
+      for (int r = 0; r < nrep; r++) {
+        const size_t idx = (size_t)co * Ly + (r == 1 ? 0 : t + (p.reflect1 ? 1 : 0));
+        float o = v;
+        if (p.res1) o += p.res1[idx];
+        if (p.res2) o += p.res2[idx];
+        o *= p.out_scale;
+        if (p.accumulate) o += p.y[idx];
+        p.y[idx] = o;
+      }
+    }
+  }
+}
+
+// y[co][t] = b[co] + sum_{ci,k} w[ci][k][co] * x[ci][t*stride + k - pad_left]   (zero outside)
+__global__ void conv1d_strided_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                      const float* __restrict__ bias, float* __restrict__ y, int Cin, int Cout,
+                                      int K, int stride, int pad_left, int Lin, int Lout) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int co = blockIdx.y;
+  if (t >= Lout) return;
+  float acc = bias ? bias[co] : 0.f;
+  for (int ci = 0; ci < Cin; ci++) {
+    const float* xr = x + (size_t)ci * Lin;
+    for (int k = 0; k < K; k++) {
+      int v = t * stride + k - pad_left;
+      if (v >= 0 && v < Lin) acc = fmaf(__ldg(w + ((size_t)ci * K + k) * Cout + co), xr[v], acc);
+    }
+  }
+  y[(size_t)co * Lout + t] = acc;
+}
+
+// f0[t] = | b + sum_c w[c] * h[c][t] |      (f0_predictor.py:101-103)
+__global__ void f0_head_kernel(const float* __restrict__ h, const float* __restrict__ w, const float* __restrict__ b,
+                               float* __restrict__ f0, int C, int L) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= L) return;
+  float acc = 0.f;
+  for (int c = 0; c < C; c++) acc = fmaf(__ldg(w + c), h[(size_t)c * L + t], acc);
+  f0[t] = fabsf(acc + b[0]);
+}
+
+// cumulative phase per harmonic at frame rate, accumulated in fp64 like torch's CPU cumsum
+// (generator.py:239-255 after the exact x1/480 linear down-sampling).  One block, H*32 threads.
+__global__ void phase_scan_kernel(const float* __restrict__ f0, float* __restrict__ cum, int T, int H, float sr) {
+  extern __shared__ double part[];               // [H][32]
+  const int h = threadIdx.x / 32, c = threadIdx.x % 32;
+  const int chunk = (T + 31) / 32;
+  const int i0 = c * chunk, i1 = min(T, i0 + chunk);
+  const float hm = (float)(h + 1);
+  double s = 0.0;
+  for (int i = i0; i < i1; i++) s += (double)fmodf((f0[i] * hm) / sr, 1.0f);
+  part[h * 32 + c] = s;
+  __syncthreads();
+  double run = 0.0;
+  for (int k = 0; k < c; k++) run += part[h * 32 + k];
+  for (int i = i0; i < i1; i++) {
+    run += (double)fmodf((f0[i] * hm) / sr, 1.0f);
+    cum[(size_t)i * H + h] = (float)run;
+  }
+}
+
+// per frame/harmonic: 0.1*sin(((c*2)*pi)*frame)  (generator.py:255-258,300)
+__global__ void frame_sin_kernel(const float* __restrict__ cum, float* __restrict__ sinamp, int n, float frame) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float ph = ((cum[i] * 2.0f) * 3.14159265358979323846f) * frame;
+  sinamp[i] = sinf(ph) * 0.1f;
+}
+
+// s[n] = tanh(b + sum_h w[h]*(sinamp[i][h]*uv_i + namp_i*U[n][h]))   (generator.py:303-316,366-368)
+__global__ void source_synth_kernel(const float* __restrict__ f0, const float* __restrict__ sinamp,
+                                    const float* __restrict__ table, const float* __restrict__ lw,
+                                    const float* __restrict__ lb, float* __restrict__ s, int n_samples, int frame,
+                                    int H) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_samples) return;
+  const int i = n / frame;
+  const float uv = f0[i] > 10.0f ? 1.0f : 0.0f;
+  const float namp = uv * 0.003f + ((1.0f - uv) * 0.1f) / 3.0f;
+  float acc = 0.f;
+  for (int h = 0; h < H; h++) {
+    float sw = sinamp[(size_t)i * H + h] * uv + namp * __ldg(table + (size_t)n * H + h);
+    acc = fmaf(__ldg(lw + h), sw, acc);
+  }
+  s[n] = tanhf(acc + lb[0]);
+}
+
+__constant__ float c_cos16[16];
+__constant__ float c_sin16[16];
+__constant__ float c_hann16[16];
+
+// torch.stft(s, 16, hop 4, hann(periodic), center=True, reflect) -> out[18][F]  (generator.py:491-497)
+__global__ void stft16_kernel(const float* __restrict__ s, float* __restrict__ out, int N, int F) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= F) return;
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    int idx = 4 * m - 8 + j;
+    if (idx < 0) idx = -idx;
+    if (idx >= N) idx = 2 * (N - 1) - idx;
+    v[j] = s[idx] * c_hann16[j];
+  }
+#pragma unroll
+  for (int f = 0; f < 9; f++) {
+    float re = 0.f, im = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      re = fmaf(v[j], c_cos16[(f * j) & 15], re);
+      im = fmaf(-v[j], c_sin16[(f * j) & 15], im);
+    }
+    out[(size_t)f * F + m] = re;
+    out[(size_t)(9 + f) * F + m] = im;
+  }
+}
+
+// windowed 16-point inverse real DFT of every frame (generator.py:499-505, 704-707)
+__global__ void istft_frames_kernel(const float* __restrict__ x, float* __restrict__ fb, int F) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= F) return;
+  float re[9], im[9];
+#pragma unroll
+  for (int f = 0; f < 9; f++) {
+    float mag = fminf(expf(x[(size_t)f * F + m]), 100.0f);
+    float ph = sinf(x[(size_t)(9 + f) * F + m]);
+    re[f] = mag * cosf(ph);
+    im[f] = mag * sinf(ph);
+  }
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    float acc = re[0] + ((j & 1) ? -re[8] : re[8]);
+#pragma unroll
+    for (int f = 1; f < 8; f++)
+      acc += 2.0f * (re[f] * c_cos16[(f * j) & 15] - im[f] * c_sin16[(f * j) & 15]);
+    fb[(size_t)m * 16 + j] = acc * (1.0f / 16.0f) * c_hann16[j];
+  }
+}
+
+// overlap-add / window-envelope normalisation / centre trim / clamp (torch.istft + generator.py:710)
+__global__ void istft_ola_kernel(const float* __restrict__ fb, float* __restrict__ y, int F, int n_out, float limit) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_out) return;
+  const int p = n + 8;
+  int m_hi = p >> 2;
+  if (m_hi > F - 1) m_hi = F - 1;
+  int m_lo = (p - 15 + 3) >> 2;
+  if (m_lo < 0) m_lo = 0;
+  float acc = 0.f, env = 0.f;
+  for (int m = m_lo; m <= m_hi; m++) {
+    const int j = p - 4 * m;
+    acc += fb[(size_t)m * 16 + j];
+    env += c_hann16[j] * c_hann16[j];
+  }
+  float v = acc / env;
+  y[n] = fminf(fmaxf(v, -limit), limit);
+}
+
+// ------------------------------------------------------------------------------------------
+struct ConvW { const float* w = nullptr; const float* b = nullptr; int Cin = 0, K = 0, Cout = 0; };
+struct ResBlockW { ConvW c1[4], c2[4]; const float* a1[4]; const float* a2[4]; };
+
+struct HiftState {
+  ConvW f0c[5]; const float* cls_w; const float* cls_b;
+  const float* lin_w; const float* lin_b;
+  ConvW conv_pre, ups[4], sdown[4], conv_post;
+  ResBlockW srb[4], rb[12];
+  DevBuf ws;
+  bool tables_ready = false;
+};
+
+static hvx_status get_conv(hvx_engine* e, const std::string& name, ConvW* c) {
+  const Tensor* w = e->find(HVX_STAGE_HIFT, name + ".w");
+  const Tensor* b = e->find(HVX_STAGE_HIFT, name + ".b");
+  HVX_CHECK(w && b && w->ndim == 3 && w->dtype == HVX_F32, HVX_ERR_STATE, "hift: missing/invalid tensor %s", name.c_str());
+  c->w = w->f32(); c->b = b->f32();
+  c->Cin = (int)w->shape[0]; c->K = (int)w->shape[1]; c->Cout = (int)w->shape[2];
+  return HVX_OK;
+}
+
+static hvx_status get_vec(hvx_engine* e, const std::string& name, const float** p) {
+  const Tensor* t = e->find(HVX_STAGE_HIFT, name);
+  HVX_CHECK(t && t->dtype == HVX_F32, HVX_ERR_STATE, "hift: missing tensor %s", name.c_str());
+  *p = t->f32();
+  return HVX_OK;
+}
+
+static hvx_status get_rb(hvx_engine* e, const std::string& pfx, int ndil, ResBlockW* r) {
+  for (int j = 0; j < ndil; j++) {
+    hvx_status s;
+    if ((s = get_conv(e, pfx + ".c1." + std::to_string(j), &r->c1[j]))) return s;
+    if ((s = get_conv(e, pfx + ".c2." + std::to_string(j), &r->c2[j]))) return s;
+    if ((s = get_vec(e, pfx + ".a1." + std::to_string(j), &r->a1[j]))) return s;
+    if ((s = get_vec(e, pfx + ".a2." + std::to_string(j), &r->a2[j]))) return s;
+  }
+  return HVX_OK;
+}
+
+hvx_status hift_finalize(hvx_engine* e) {
+  const hvx_config& c = e->cfg;
+  HVX_CHECK(c.hift_n_fft == 16 && c.hift_hop == 4, HVX_ERR_UNSUPPORTED, "hift: only n_fft=16/hop=4 ISTFT head is built");
+  HVX_CHECK(c.hift_n_ups <= 4 && c.hift_n_rb <= 4 && c.hift_n_dil <= 4, HVX_ERR_UNSUPPORTED, "hift: too many stages");
+  if (!e->hift) e->hift = new HiftState();
+  HiftState* h = e->hift;
+  hvx_status s;
+  for (int i = 0; i < 5; i++)
+    if ((s = get_conv(e, "f0.c" + std::to_string(i), &h->f0c[i]))) return s;
+  if ((s = get_vec(e, "f0.cls.w", &h->cls_w))) return s;
+  if ((s = get_vec(e, "f0.cls.b", &h->cls_b))) return s;
+  if ((s = get_vec(e, "src.lin.w", &h->lin_w))) return s;
+  if ((s = get_vec(e, "src.lin.b", &h->lin_b))) return s;
+  if ((s = get_conv(e, "conv_pre", &h->conv_pre))) return s;
+  if ((s = get_conv(e, "conv_post", &h->conv_post))) return s;
+  for (int i = 0; i < c.hift_n_ups; i++) {
+    if ((s = get_conv(e, "ups." + std::to_string(i), &h->ups[i]))) return s;
+    if ((s = get_conv(e, "sdown." + std::to_string(i), &h->sdown[i]))) return s;
+    if ((s = get_rb(e, "srb." + std::to_string(i), c.hift_n_dil, &h->srb[i]))) return s;
+    for (int j = 0; j < c.hift_n_rb; j++)
+      if ((s = get_rb(e, "rb." + std::to_string(i * c.hift_n_rb + j), c.hift_n_dil, &h->rb[i * c.hift_n_rb + j]))) return s;
+  }
+  if (!h->tables_ready) {
+    float cs[16], sn[16], hn[16];
+    for (int j = 0; j < 16; j++) {
+      cs[j] = (float)cos(2.0 * M_PI * j / 16.0);
+      sn[j] = (float)sin(2.0 * M_PI * j / 16.0);
+      hn[j] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * j / 16.0));
+    }
+    HVX_CUDA(cudaMemcpyToSymbol(c_cos16, cs, sizeof(cs)));
+    HVX_CUDA(cudaMemcpyToSymbol(c_sin16, sn, sizeof(sn)));
+    HVX_CUDA(cudaMemcpyToSymbol(c_hann16, hn, sizeof(hn)));
+    h->tables_ready = true;
+  }
+  return HVX_OK;
+}
+
+void hift_free(hvx_engine* e) { delete e->hift; e->hift = nullptr; }
+
+struct ConvOpt {
+  int dil = 1, up = 1, pad_left = -1 /* -1: (K-1)*dil */, pre_act = 0, post_elu = 0, accumulate = 0, reflect1 = 0;
+  float slope = 0.f, out_scale = 1.f;
+  const float* alpha = nullptr; const float* res1 = nullptr; const float* res2 = nullptr;
+  int Lout = -1, ldx = -1;
+};
+
+static hvx_status run_conv(hvx_engine* e, cudaStream_t st, const ConvW& c, const float* x, int Lin, float* y,
+                           const ConvOpt& o) {
+  HVX_CHECK(c.K <= K_MAX && (c.K - 1) * o.dil <= HALO_MAX, HVX_ERR_UNSUPPORTED, "conv tile: K=%d dil=%d unsupported", c.K, o.dil);
+  ConvArgs a;
+  a.x = x; a.w = c.w; a.bias = c.b; a.y = y; a.res1 = o.res1; a.res2 = o.res2; a.alpha = o.alpha;
+  a.Cin = c.Cin; a.Cout = c.Cout; a.K = c.K; a.dil = o.dil; a.up = o.up;
+  a.pad_left = o.pad_left < 0 ? (c.K - 1) * o.dil : o.pad_left;
+  a.Lin = Lin; a.Lout = o.Lout < 0 ? Lin * o.up : o.Lout; a.ldx = o.ldx < 0 ? Lin : o.ldx;
+  a.pre_act = o.pre_act; a.slope = o.slope; a.post_elu = o.post_elu; a.accumulate = o.accumulate;
+  a.reflect1 = o.reflect1; a.out_scale = o.out_scale;
+  dim3 grid(cdiv(a.Lout, T_TILE), cdiv(c.Cout, CO_TILE));
+  conv1d_tile_kernel<<<grid, 256, 0, st>>>(a);
+  HVX_LAUNCH_CHECK(e);
+  return HVX_OK;
+}
+
+// x_out = resblock(x_in); the last conv's epilogue optionally adds `extra` and/or accumulates
+// out_scale*(result) into `acc_out` instead of writing x_out.
+static hvx_status run_resblock(hvx_engine* e, cudaStream_t st, const ResBlockW& r, int ndil, const int* dils,
+                               const float* x_in, float* work, float* tmp, int L, const float* extra, float* final_out,
+                               int final_accumulate, float final_scale) {
+  const float* cur = x_in;
+  for (int j = 0; j < ndil; j++) {
+    ConvOpt o1; o1.dil = dils[j]; o1.pre_act = 2; o1.alpha = r.a1[j];
+    hvx_status s = run_conv(e, st, r.c1[j], cur, L, tmp, o1);
+    if (s) return s;
+    ConvOpt o2; o2.pre_act = 2; o2.alpha = r.a2[j]; o2.res1 = cur;
+    float* dst = work;
+    if (j == ndil - 1) {
+      o2.res2 = extra; o2.accumulate = final_accumulate; o2.out_scale = final_scale;
+      dst = final_out;
+    }
+    s = run_conv(e, st, r.c2[j], tmp, L, dst, o2);
+    if (s) return s;
+    cur = work;
+  }
+  return HVX_OK;
+}
+
+}  // namespace hvx
+
+using namespace hvx;
+
+extern "C" hvx_status hvx_hift_vocode(hvx_engine* e, const float* mel, int T, int finalize, const float* table,
+                                      const float* f0_in, float* f0_out, float* wav, float* src, void* stream) {
+  HVX_CHECK(e && e->hift, HVX_ERR_STATE, "hift stage not finalized");
+  const hvx_config& c = e->cfg;
+  HiftState* h = e->hift;
+  cudaStream_t st = (cudaStream_t)stream;
+  int frame = c.hift_hop, up_prod = 1;
+  for (int i = 0; i < c.hift_n_ups; i++) { frame *= c.hift_ups[i]; up_prod *= c.hift_ups[i]; }
+  const int H = c.hift_harmonics;
+  const int Tf0 = finalize ? T : T - 3;            // f0_predictor.py:96-99
+  const int Tx = finalize ? T : T - 7;             // generator.py:676-679,725
+  HVX_CHECK(Tx >= 1 && (finalize || Tx >= 2), HVX_ERR_ARG, "hift: T=%d too short", T);
+  const int Ns = Tf0 * frame;                      // source samples
+  const int Fs = Ns / 4 + 1;                       // stft frames of the source
+  const int F = Tx * up_prod + 1;                  // frames entering the ISTFT
+  const int n_out = finalize ? Tx * frame : (Tx - 1) * frame;
+  const int C0 = c.hift_base, CF = c.hift_f0_ch;
+
+  // workspace carve-up (floats)
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += (n + 63) & ~(size_t)63; return o; };
+  const size_t o_fa = take((size_t)CF * Tf0), o_fb = take((size_t)CF * Tf0), o_f0 = take(Tf0);
+  const size_t o_cum = take((size_t)Tf0 * H), o_sin = take((size_t)Tf0 * H), o_s = take(Ns);
+  const size_t o_stft = take((size_t)18 * Fs);
+  const size_t o_x0 = take((size_t)C0 * Tx);
+  size_t maxCL = 0;
+  { int L = Tx; for (int i = 0; i < c.hift_n_ups; i++) { L = L * c.hift_ups[i]; size_t cl = (size_t)(C0 >> (i + 1)) * (L + 1); if (cl > maxCL) maxCL = cl; } }
+  const size_t o_x = take(maxCL), o_xs = take(maxCL), o_si = take(maxCL), o_work = take(maxCL), o_tmp = take(maxCL);
+  const size_t o_post = take((size_t)18 * F), o_fbuf = take((size_t)16 * F);
+  float* ws = (float*)h->ws.get(off * sizeof(float));
+  HVX_CHECK(ws, HVX_ERR_CUDA, "hift: workspace allocation of %zu bytes failed", off * sizeof(float));
+  float *fa = ws + o_fa, *fb = ws + o_fb, *f0 = ws + o_f0, *cum = ws + o_cum, *sinamp = ws + o_sin, *s = ws + o_s;
+  float *sstft = ws + o_stft, *x0 = ws + o_x0, *x = ws + o_x, *xs = ws + o_xs, *si = ws + o_si, *work = ws + o_work;
+  float *tmp = ws + o_tmp, *post = ws + o_post, *fbuf = ws + o_fbuf;
+  hvx_status rc;
+
+  // ---- F0 predictor (fp32; reference runs it on the CPU for precision, generator.py:715-717)
+  if (f0_in) {
+    HVX_CUDA(cudaMemcpyAsync(f0, f0_in, sizeof(float) * Tf0, cudaMemcpyDeviceToDevice, st));
+  } else {
+    ConvOpt o; o.pad_left = 0; o.post_elu = 1; o.Lout = Tf0;      // right-causal k4 (look-ahead 3)
+    if ((rc = run_conv(e, st, h->f0c[0], mel, T, fa, o))) return rc;
+    float *a = fa, *b = fb;
+    for (int i = 1; i < 5; i++) {
+      ConvOpt oi; oi.post_elu = 1;
+      if ((rc = run_conv(e, st, h->f0c[i], a, Tf0, b, oi))) return rc;
+      float* t2 = a; a = b; b = t2;
+    }
+    f0_head_kernel<<<cdiv(Tf0, 128), 128, 0, st>>>(a, h->cls_w, h->cls_b, f0, CF, Tf0);
+    HVX_LAUNCH_CHECK(e);
+  }
+  if (f0_out) HVX_CUDA(cudaMemcpyAsync(f0_out, f0, sizeof(float) * Tf0, cudaMemcpyDeviceToDevice, st));
+
+  // ---- harmonic source
+  phase_scan_kernel<<<1, H * 32, H * 32 * sizeof(double), st>>>(f0, cum, Tf0, H, (float)c.hift_sr);
+  HVX_LAUNCH_CHECK(e);
+  frame_sin_kernel<<<cdiv(Tf0 * H, 256), 256, 0, st>>>(cum, sinamp, Tf0 * H, (float)frame);
+  HVX_LAUNCH_CHECK(e);
+  source_synth_kernel<<<cdiv(Ns, 256), 256, 0, st>>>(f0, sinamp, table, h->lin_w, h->lin_b, s, Ns, frame, H);
+  HVX_LAUNCH_CHECK(e);
+  if (src) HVX_CUDA(cudaMemcpyAsync(src, s, sizeof(float) * Ns, cudaMemcpyDeviceToDevice, st));
+  stft16_kernel<<<cdiv(Fs, 128), 128, 0, st>>>(s, sstft, Ns, Fs);
+  HVX_LAUNCH_CHECK(e);
+
+  // ---- decode
+  { ConvOpt o; o.pad_left = 0; o.Lout = Tx; o.ldx = T;           // conv_pre k5, look-right 4
+    if ((rc = run_conv(e, st, h->conv_pre, mel, finalize ? T : T - 3, x0, o))) return rc; }
+  const float* cur = x0;
+  int L = Tx;
+  int down = up_prod;
+  for (int i = 0; i < c.hift_n_ups; i++) {
+    const int u = c.hift_ups[i];
+    const int last = (i == c.hift_n_ups - 1);
+    const int Lo = L * u + (last ? 1 : 0);
+    const int ch = C0 >> (i + 1);
+    { ConvOpt o; o.pre_act = 1; o.slope = 0.1f; o.up = u; o.reflect1 = last;
+      if ((rc = run_conv(e, st, h->ups[i], cur, L, x, o))) return rc; }
+    // source branch: strided causal down-conv of the source STFT, then its resblock, fused "+ x"
+    down /= u;                                                     // 15, 3, 1 at full dims
+    { const ConvW& d = h->sdown[i];
+      const int stride = down, pad = down > 1 ? down - 1 : 0;
+      dim3 grid(cdiv(Lo, 128), d.Cout);
+      conv1d_strided_kernel<<<grid, 128, 0, st>>>(sstft, d.w, d.b, si, d.Cin, d.Cout, d.K, stride, pad, Fs, Lo);
+      HVX_LAUNCH_CHECK(e); }
+    if ((rc = run_resblock(e, st, h->srb[i], c.hift_n_dil, c.hift_rb_d, si, work, tmp, Lo, x, x, 0, 1.0f))) return rc;
+    // mean of the parallel resblocks, accumulated in the final conv epilogues
+    for (int j = 0; j < c.hift_n_rb; j++)
+      if ((rc = run_resblock(e, st, h->rb[i * c.hift_n_rb + j], c.hift_n_dil, c.hift_rb_d, x, work, tmp, Lo, nullptr, xs,
+                             j > 0, 1.0f / c.hift_n_rb))) return rc;
+    float* t2 = x; x = xs; xs = t2;
+    cur = x; L = Lo; (void)ch;
+  }
+  { ConvOpt o; o.pre_act = 1; o.slope = 0.01f;
+    if ((rc = run_conv(e, st, h->conv_post, cur, L, post, o))) return rc; }
+  istft_frames_kernel<<<cdiv(F, 128), 128, 0, st>>>(post, fbuf, F);
+  HVX_LAUNCH_CHECK(e);
+  istft_ola_kernel<<<cdiv(n_out, 256), 256, 0, st>>>(fbuf, wav, F, n_out, 0.99f);
+  HVX_LAUNCH_CHECK(e);
+  return HVX_OK;
+}

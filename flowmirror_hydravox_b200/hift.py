@@ -1,0 +1,62 @@
+"""NativeHiFT — drop-in for models['hift'] (CausalHiFTGenerator, cosyvoice/hifigan/generator.py:572-726)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from .weights import pack_hift
+
+
+class NativeHiFT:
+    def __init__(self, engine: "L.Engine", sine_table: torch.Tensor | None = None):
+        self.engine = engine
+        self.dims = engine.hd
+        self.sine_table = None
+        if sine_table is not None:
+            self.set_sine_table(sine_table)
+
+    # ---- nn.Module-like surface used by ModelManager.load_models (infer_speech_model.py:92-118)
+    def load_state_dict(self, sd, strict=True):
+        self.engine.set_tensors(L.STAGE_HIFT, pack_hift(sd, self.dims))
+        self.engine.finalize(L.STAGE_HIFT)
+        return self
+
+    def eval(self):
+        return self
+
+    def cuda(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def set_sine_table(self, table: torch.Tensor):
+        """SineGen2.sine_waves rows (generator.py:226): (n_samples, harmonics) uniform[0,1)."""
+        t = table.reshape(-1, self.dims.harmonics).to(self.engine.device, torch.float32).contiguous()
+        self.sine_table = t
+
+    @torch.no_grad()
+    def inference(self, speech_feat: torch.Tensor, finalize: bool = True, f0: torch.Tensor | None = None,
+                  return_f0: bool = False):
+        """speech_feat (1, mel, T) fp32 -> (speech (1, n), source (1, 1, frame*T_f0))  [generator.py:713-726]."""
+        assert speech_feat.dim() == 3 and speech_feat.shape[0] == 1, "reference asserts batch 1 (flow.py:387)"
+        d, dev = self.dims, self.engine.device
+        mel = speech_feat[0].to(dev, torch.float32).contiguous()
+        T = mel.shape[1]
+        frame = d.frame_samples
+        Tf0 = T if finalize else T - 3
+        Tx = T if finalize else T - 7
+        n_out = Tx * frame if finalize else (Tx - 1) * frame
+        if self.sine_table is None or self.sine_table.shape[0] < Tf0 * frame:
+            raise L.HvxError("sine table missing or shorter than the utterance (set_sine_table)")
+        wav = torch.empty(1, n_out, device=dev, dtype=torch.float32)
+        src = torch.empty(1, 1, Tf0 * frame, device=dev, dtype=torch.float32)
+        f0_out = torch.empty(Tf0, device=dev, dtype=torch.float32)
+        f0_in = None if f0 is None else f0.reshape(-1).to(dev, torch.float32).contiguous()
+        L.check(L.lib().hvx_hift_vocode(self.engine.h, L.ptr(mel), T, int(bool(finalize)), L.ptr(self.sine_table),
+                                        L.ptr(f0_in), L.ptr(f0_out), L.ptr(wav), L.ptr(src), L.stream_ptr()))
+        if return_f0:
+            return wav, src, f0_out
+        return wav, src

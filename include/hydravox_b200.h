@@ -1,0 +1,158 @@
+/*
+ * hydravox_b200 — C-ABI of the B200-native HydraVox hot path (AR decode -> CFM -> HiFT).
+ *
+ * Drop-in boundary.  Every entry point replaces one call the reference makes
+ * into PyTorch on its hot path; the reference-side binding is the ctypes stub shown in
+ * INTEGRATION.md (the reference is Python, so its "FFI" is ctypes / data_ptr()).
+ *
+ * Conventions (they mirror the reference's own raw-pointer seam for the TensorRT estimator,
+ * cosyvoice/flow/flow_matching.py:126-153 and cosyvoice/utils/common.py:198-213):
+ *   - plain C linkage, no exceptions; every call returns hvx_status (0 = OK) and
+ *     hvx_last_error() returns a description of the last failure on the calling thread;
+ *   - `*_dev` pointers are device pointers owned by the caller (torch tensors via data_ptr()),
+ *     contiguous, valid for the duration of the call; `*_host` pointers are host memory
+ *     (pinned for best throughput) — the *_host entry points include the H2D/D2H copies;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); calls are
+ *     stream-ordered and do not synchronise unless they return host data;
+ *   - one engine per process/GPU, not thread-safe (the reference runs one worker per GPU,
+ *     server/worker.py:25-44).
+ */
+#ifndef HYDRAVOX_B200_H
+#define HYDRAVOX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int hvx_status;
+enum { HVX_OK = 0, HVX_ERR_ARG = 1, HVX_ERR_CUDA = 2, HVX_ERR_STATE = 3, HVX_ERR_UNSUPPORTED = 4 };
+
+enum { HVX_STAGE_LLM = 0, HVX_STAGE_FLOW = 1, HVX_STAGE_HIFT = 2 };
+enum { HVX_F32 = 0, HVX_BF16 = 1, HVX_I32 = 2, HVX_F16 = 3 };
+
+typedef struct hvx_engine hvx_engine;
+
+/* Model dimensions (flowmirror_hydravox_b200/dims.py; SURVEY.md §8 header). */
+typedef struct hvx_config {
+  /* HiFT: cosyvoice/hifigan/generator.py:577-670 */
+  int hift_mel, hift_base, hift_f0_ch, hift_harmonics, hift_sr;
+  int hift_n_ups, hift_ups[4], hift_up_k[4];
+  int hift_n_fft, hift_hop;
+  int hift_n_rb, hift_rb_k[4], hift_n_dil, hift_rb_d[4], hift_src_k[4];
+  /* flow: cosyvoice/flow/flow.py:296-310, cosyvoice/flow/DiT/dit.py:104-143 */
+  int flow_mel, flow_spk_in, flow_vocab, flow_pla_ch, flow_dim, flow_depth, flow_heads, flow_dim_head;
+  int flow_ff_mult, flow_chunk, flow_pos_k, flow_pos_groups, flow_noise_frames;
+  float flow_cfg_rate;
+  /* llm: cosyvoice/llm/llm_multi_head_v3.py:622-689 + HF Qwen2Config */
+  int llm_hidden, llm_layers, llm_q_heads, llm_kv_heads, llm_head_dim, llm_inter, llm_text_vocab;
+  int llm_speech_vocab, llm_mtp_heads, llm_mtp_inter, llm_max_ctx, llm_max_seqs;
+  float llm_rope_theta, llm_eps;
+} hvx_config;
+
+/* Sampler parameters bound per request by server/worker.py:57-65 (ras_sampling keywords,
+ * cosyvoice/utils/common.py:138). */
+typedef struct hvx_sampler {
+  float top_p;
+  int top_k;
+  int win_size;
+  float tau_r;
+} hvx_sampler;
+
+const char* hvx_last_error(void);
+int hvx_version(void);
+
+/* lifecycle — replaces ModelManager.load_models object construction
+ * (server/model_utils/infer_speech_model.py:50-143). */
+hvx_status hvx_create(hvx_engine** out, const hvx_config* cfg);
+hvx_status hvx_destroy(hvx_engine* e);
+
+/* Weight ingest — replaces module.load_state_dict(...) in load_models / load_pt
+ * (infer_speech_model.py:69-94,169-184).  The engine borrows `dptr` (device memory kept alive
+ * by the caller).  Names are the engine's packed-tensor names (flowmirror_hydravox_b200/
+ * weights.py documents the mapping from the reference's state_dict keys). */
+hvx_status hvx_set_tensor(hvx_engine* e, int stage, const char* name, const void* dptr, int dtype,
+                          const int64_t* shape, int ndim);
+hvx_status hvx_finalize(hvx_engine* e, int stage);
+
+/* ---- HiFT: replaces CausalHiFTGenerator.inference (cosyvoice/hifigan/generator.py:713-726) ----
+ * mel_dev (mel, T) fp32 -> wav_dev (frame*T') fp32 clamped to +-0.99, src_dev (frame*T) source.
+ * finalize=0 follows the streaming branch (:676-679,708-709,725): T' = T-3-4 frames... see DESIGN.md.
+ * sine_table_dev: SineGen2.sine_waves rows (n_samples, harmonics) uniform[0,1) (generator.py:226).
+ * f0_in_dev (optional, T): pins the F0 track (parity tests); f0_out_dev (optional, T) receives it. */
+hvx_status hvx_hift_vocode(hvx_engine* e, const float* mel_dev, int T, int finalize,
+                           const float* sine_table_dev, const float* f0_in_dev, float* f0_out_dev,
+                           float* wav_dev, float* src_dev, void* stream);
+
+/* ---- flow: replaces CausalMaskedDiffWithDiT.inference (cosyvoice/flow/flow.py:367-430) ----
+ * tokens = prompt||new speech tokens (n_prompt + n_tok), embedding (spk_in) fp32,
+ * prompt_feat (2*n_prompt, mel) fp32 or NULL; noise_dev = CausalConditionalCFM.rand_noise
+ * (mel, noise_frames) fp32 (flow_matching.py:200-201).  mel_out_dev (mel, 2*n_tok) fp32. */
+hvx_status hvx_flow_inference(hvx_engine* e, const int32_t* tokens_dev, int n_prompt, int n_tok,
+                              const float* embedding_dev, const float* prompt_feat_dev,
+                              const float* noise_dev, int n_timesteps, int streaming, int finalize,
+                              float* mel_out_dev, void* stream);
+
+/* Estimator seam — replaces ConditionalCFM.forward_estimator's TensorRT branch
+ * (cosyvoice/flow/flow_matching.py:126-153): x,mu,cond (2,mel,T), t (2), spks (2,mel) fp32;
+ * writes dphi/dt (2,mel,T) into out_dev. */
+hvx_status hvx_dit_estimator(hvx_engine* e, const float* x_dev, const float* mu_dev, const float* t_dev,
+                             const float* spks_dev, const float* cond_dev, int T, int streaming,
+                             float* out_dev, void* stream);
+
+/* ---- LLM: replaces CosyVoice3LM.inference / inference_wrapper
+ * (cosyvoice/llm/llm_multi_head_v3.py:861-960).
+ * hvx_llm_begin resets sequence slot `seq` and stores its prompt rows
+ * [sos, embed(prompt_text||text), task_id, speech_emb(prompt_speech)] (:943-952).
+ * hvx_llm_generate runs prefill + the multi-head loop for all begun sequences until each has
+ * stopped (stop token / max_len) and writes tokens to out_tokens_dev[seq*max_out + i], counts to
+ * out_counts_dev[seq].  u_dev: uniform stream per sequence (n_seq, u_stride) consumed in call
+ * order by the sampler (oracle/llm_ref.py documents the order). */
+hvx_status hvx_llm_begin(hvx_engine* e, int seq, const int32_t* text_ids_dev, int n_text_total,
+                         int n_text_new, const int32_t* prompt_speech_dev, int n_prompt_speech,
+                         float min_ratio, float max_ratio);
+hvx_status hvx_llm_generate(hvx_engine* e, int n_seq, int head_k, const hvx_sampler* sp,
+                            const float* u_dev, int u_stride, int32_t* out_tokens_dev, int max_out,
+                            int32_t* out_counts_dev, void* stream);
+/* Teacher-forced probe for parity tests: final-normed hidden of the last prompt row and the
+ * log-softmax of every MTP head on it (llm_multi_head_v3.py:886-888). */
+hvx_status hvx_llm_probe(hvx_engine* e, int seq, float* last_hidden_dev, float* head_logp_dev, void* stream);
+/* Sampler alone on caller-provided log-probs (n_heads, vocab) — parity of sampling_ids
+ * (llm_multi_head_v3.py:151-166) independent of the transformer numerics. */
+hvx_status hvx_sample(hvx_engine* e, const float* logp_dev, int n_heads, const int32_t* history_dev,
+                      int n_history, int min_len, const hvx_sampler* sp, const float* u_dev, int n_u,
+                      int32_t* out_ids_dev, int32_t* u_used_dev, void* stream);
+
+/* ---- end to end with HOST buffers: replaces inference_zero_shot / inference_tts
+ * (server/model_utils/infer_speech_model.py:523-689) from token ids to waveform.
+ * Copies inputs H2D, runs LLM -> flow -> (speed interp) -> HiFT, copies wav D2H, synchronises. */
+typedef struct hvx_request {
+  const int32_t* text_ids_host;      int n_text_total; int n_text_new;   /* prompt_text||text */
+  const int32_t* prompt_speech_host; int n_prompt_speech;
+  const float* prompt_feat_host;                                         /* (2*n_prompt_speech, mel) or NULL */
+  const float* embedding_host;                                           /* (spk_in) */
+  const float* u_host;               int n_u;
+  float min_ratio, max_ratio, speed;
+} hvx_request;
+hvx_status hvx_synthesize_host(hvx_engine* e, const hvx_request* reqs, int n_req, int head_k,
+                               const hvx_sampler* sp, int n_timesteps, const float* noise_dev,
+                               const float* sine_table_dev, float* wav_host, int wav_stride,
+                               int32_t* wav_len_host, int32_t* tokens_host, int tok_stride,
+                               int32_t* n_tokens_host, float* stage_ms_host, void* stream);
+
+/* ---- diagnostic entries for the kernel-level parity tests (tests/test_gemm_gpu.py) ----
+ * C = act(A*B^T + bias): A (M,K) bf16, B (N,K) bf16 (nn.Linear weight layout), C bf16 or fp32. */
+hvx_status hvx_gemm_bf16(hvx_engine* e, const void* A_dev, const void* B_dev, const float* bias_dev, void* C_dev,
+                         int M, int N, int K, int out_f32, int act, void* stream);
+/* softmax(q k^T / 8 + mask) v per (batch, head): qk (B*T, 2*H*64) = q|k, vt (B*H*64, vt_ld) = V^T. */
+hvx_status hvx_attention_bf16(hvx_engine* e, const void* qk_dev, const void* vt_dev, int vt_ld, void* out_dev,
+                              int B, int T, int H, int chunk, void* stream);
+
+/* bookkeeping for bench.py: number of kernels this library has launched since creation. */
+int64_t hvx_kernel_launches(hvx_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
