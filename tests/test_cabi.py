@@ -11,7 +11,7 @@ def test_library_exports_header_symbols():
     path = build.build()
     lib = ctypes.CDLL(path)
     hdr = open(os.path.join(ROOT, "include", "hydravox_b200.h")).read()
-    names = set(re.findall(r"\b(hvx_[a-z0-9_]+)\s*\(", hdr))
+    names = set(re.findall(r"\b(hvx_[a-z0-9_]+)\s*\(", hdr)) - {"hvx_status"}
     assert len(names) >= 10
     missing = [n for n in sorted(names) if not hasattr(lib, n)]
     assert not missing, missing
