@@ -490,8 +490,7 @@ extern "C" hvx_status hvx_hift_vocode(hvx_engine* e, const float* mel, int T, in
     for (int j = 0; j < c.hift_n_rb; j++)
       if ((rc = run_resblock(e, st, h->rb[i * c.hift_n_rb + j], c.hift_n_dil, c.hift_rb_d, x, work, tmp, Lo, nullptr, xs,
                              j > 0, 1.0f / c.hift_n_rb))) return rc;
-    float* t2 = x; x = xs; xs = t2;
-    cur = x; L = Lo; (void)ch;
+    cur = xs; L = Lo; (void)ch;     // next stage reads xs and writes x (never in place: shapes differ)
   }
   { ConvOpt o; o.pre_act = 1; o.slope = 0.01f;
     if ((rc = run_conv(e, st, h->conv_post, cur, L, post, o))) return rc; }
