@@ -63,8 +63,8 @@ dit_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     load_kv(0);
   }
 
-  constexpr uint32_t idesc_s = tc::umma_idesc_bf16(128, 128);
-  constexpr uint32_t idesc_o = tc::umma_idesc_bf16(128, 64);
+  const uint32_t idesc_s = a.f16 ? tc::umma_idesc_f16(128, 128) : tc::umma_idesc_bf16(128, 128);
+  const uint32_t idesc_o = a.f16 ? tc::umma_idesc_f16(128, 64) : tc::umma_idesc_bf16(128, 64);
   const float sc = 0.125f * 1.4426950408889634f;     // dim_head^-0.5 * log2(e)
   float m_run = -INFINITY, l_run = 0.f;
   float o_acc[64];
@@ -114,8 +114,7 @@ dit_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             const float s1 = (kbase + c0 + i + 1 < klim_row) ? __uint_as_float(v[i + 1]) * sc : -INFINITY;
             const float p0 = exp2f(s0 - m_new), p1 = exp2f(s1 - m_new);
             psum += p0 + p1;
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(p0, p1);
-            pk[i >> 1] = *reinterpret_cast<uint32_t*>(&t2);
+            pk[i >> 1] = tc::pack16(p0, p1, a.f16);
           }
           l_run += psum;
           // 32 keys = 4 chunks of 16 B in atom (c0/64), chunk index ((c0%64)/8 + q) ^ (row & 7)
@@ -173,12 +172,8 @@ dit_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 #pragma unroll
     for (int i = 0; i < 64; i += 8) {
       uint4 pk;
-      __nv_bfloat162 t0 = __floats2bfloat162_rn(o_acc[i] * inv, o_acc[i + 1] * inv);
-      __nv_bfloat162 t1 = __floats2bfloat162_rn(o_acc[i + 2] * inv, o_acc[i + 3] * inv);
-      __nv_bfloat162 t2 = __floats2bfloat162_rn(o_acc[i + 4] * inv, o_acc[i + 5] * inv);
-      __nv_bfloat162 t3 = __floats2bfloat162_rn(o_acc[i + 6] * inv, o_acc[i + 7] * inv);
-      pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-      pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+      pk.x = tc::pack16(o_acc[i] * inv, o_acc[i + 1] * inv, a.f16); pk.y = tc::pack16(o_acc[i + 2] * inv, o_acc[i + 3] * inv, a.f16);
+      pk.z = tc::pack16(o_acc[i + 4] * inv, o_acc[i + 5] * inv, a.f16); pk.w = tc::pack16(o_acc[i + 6] * inv, o_acc[i + 7] * inv, a.f16);
       *reinterpret_cast<uint4*>(o + i) = pk;
     }
   }
@@ -215,7 +210,8 @@ extern "C" hvx_status hvx_attention_bf16(hvx_engine* e, const void* qk, const vo
                                          int H, int chunk, void* stream) {
   HVX_CHECK(e, HVX_ERR_ARG, "null engine");
   AttnArgs a;
-  a.T = T; a.heads = H; a.n_batch = B; a.chunk = chunk; a.ld_out = H * 64; a.out = (__nv_bfloat16*)out;
+  a.T = T; a.heads = H; a.n_batch = B; a.chunk = chunk & 0xffff; a.f16 = (chunk >> 16) & 1;   // bit 16 of chunk: fp16 operands
+  a.ld_out = H * 64; a.out = (__nv_bfloat16*)out;
   return dit_attention(e, (cudaStream_t)stream, (const __nv_bfloat16*)qk, 2 * H * 64, H * 64, (const __nv_bfloat16*)vt,
                        vt_ld, a);
 }

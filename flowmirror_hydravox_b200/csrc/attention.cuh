@@ -20,6 +20,7 @@ struct AttnArgs {
   int heads;
   int n_batch;
   int chunk;        // >0: streaming block-causal mask, key j visible to query i iff j < (i/chunk+1)*chunk
+  int f16;          // 1: q/k/v/out are fp16 instead of bf16
   int ld_out;       // = heads*64
   __nv_bfloat16* out;   // [n_batch*T][heads*64]
 };

@@ -1,10 +1,507 @@
-#include "common.cuh"
+// Flow stage (speech tokens -> mel) for sm_100a.
+// Replaces CausalMaskedDiffWithDiT.inference (cosyvoice/flow/flow.py:367-430), PreLookaheadLayer
+// (cosyvoice/transformer/upsample_encoder.py:82-103), CausalConditionalCFM.forward / solve_euler
+// (cosyvoice/flow/flow_matching.py:71-124,203-228) and the DiT estimator (cosyvoice/flow/DiT/dit.py:145-176,
+// DiT/modules.py) — restated in oracle/flow_ref.py.
+//
+// Data layout (one utterance per call, CFG rows stacked: row r<T conditional, r>=T unconditional):
+//   ODE state x, mu, cond      fp32 [T][mel]      frame-major (a row is one 320 B line)
+//   residual stream h          fp32 [2T][dim]
+//   GEMM operands              fp16 [2T][*]       (the reference runs this stage in fp16: infer_speech_model.py:105-117)
+//   V^T for attention          fp16 [2*heads*64][Tp]
+//   adaLN modulations          fp32 [n_steps][depth*6*dim + 2*dim], computed once per solve (they depend on t only)
+// Every dense contraction is the tcgen05/TMA GEMM of gemm.cu (fp16 in, fp32 accumulate) with the
+// elementwise work fused into its epilogue (bias, Mish/GELU/leaky-relu, rotary + V transpose, gated residual);
+// the two convolution families are run as implicit GEMMs through TMA addressing alone:
+//   PreLookahead conv k4 / k3    = GEMM over an *overlapping-row* view (row stride = C, K = taps*C)
+//   grouped causal conv k31      = one k-block per tap, A rows shifted by the tap, 64-channel groups
+#include "attention.cuh"
+#include "gemm.cuh"
+#include <cmath>
+#include <cstring>
+
 namespace hvx {
-hvx_status flow_finalize(hvx_engine*) { set_error("flow not built"); return HVX_ERR_UNSUPPORTED; }
-void flow_free(hvx_engine*) {}
+
+// ------------------------------------------------------------------ small kernels
+// spks = Linear(normalize(emb))   (flow.py:389-390)
+__global__ void flow_spk_kernel(const float* __restrict__ emb, const float* __restrict__ w, const float* __restrict__ b,
+                                float* __restrict__ spks, int n_in, int n_out) {
+  __shared__ float s_e[1024];
+  __shared__ float s_red[32];
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < n_in; i += blockDim.x) { float v = emb[i]; s_e[i] = v; ss += v * v; }
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); i++) tot += s_red[i];
+  const float inv = 1.0f / fmaxf(sqrtf(tot), 1e-12f);                  // F.normalize eps
+  for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
+    float acc = 0.f;
+    for (int i = 0; i < n_in; i++) acc = fmaf(w[(size_t)o * n_in + i], s_e[i] * inv, acc);
+    spks[o] = acc + b[o];
+  }
 }
+
+// token embedding rows: fp32 copy (residual) and a fp16 copy padded to Cp columns and followed by zero
+// rows (conv look-ahead pad)
+__global__ void flow_embed_kernel(const int32_t* __restrict__ tok, const float* __restrict__ table, float* __restrict__ e32,
+                                  __half* __restrict__ e16, int n_tok, int n_rows16, int C, int Cp, int vocab) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows16 * Cp) return;
+  const int r = i / Cp, c = i - r * Cp;
+  float v = 0.f;
+  if (r < n_tok && c < C) {
+    int id = tok[r];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);               // torch.clamp(token, min=0) (flow.py:397)
+    v = table[(size_t)id * C + c];
+    e32[(size_t)r * C + c] = v;
+  }
+  e16[i] = __float2half_rn(v);
+}
+
+// mu = repeat_interleave(mu_tok, 2); cond = prompt mel | 0; x = noise^T   (flow.py:404-419, flow_matching.py:223)
+__global__ void flow_init_kernel(const float* __restrict__ mu_tok, const float* __restrict__ prompt_feat,
+                                 const float* __restrict__ noise, float* __restrict__ mu, float* __restrict__ cond,
+                                 float* __restrict__ x, int T, int C, int mel_len1, int noise_ld) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * C) return;
+  const int t = i / C, c = i - t * C;
+  mu[i] = mu_tok[(size_t)(t >> 1) * C + c];
+  cond[i] = (t < mel_len1) ? prompt_feat[i] : 0.f;
+  x[i] = noise[(size_t)c * noise_ld + t];
+}
+
+// xin[r] = [x | cond | mu | spks] (DiT InputEmbedding order, dit.py:91-95); rows >= T are the CFG
+// unconditional copy: same x, everything else zero (flow_matching.py:100-112)
+__global__ void dit_pack_fm_kernel(const float* __restrict__ x, const float* __restrict__ cond, const float* __restrict__ mu,
+                                   const float* __restrict__ spks, __half* __restrict__ xin, int T, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int W = 4 * C;
+  if (i >= 2 * T * W) return;
+  const int r = i / W, j = i - r * W;
+  const int t = r < T ? r : r - T;
+  const int part = j / C, c = j - part * C;
+  float v;
+  if (part == 0) v = x[(size_t)t * C + c];
+  else if (r >= T) v = 0.f;
+  else if (part == 1) v = cond[(size_t)t * C + c];
+  else if (part == 2) v = mu[(size_t)t * C + c];
+  else v = spks[c];
+  xin[i] = __float2half_rn(v);
+}
+
+// same from the estimator seam's channel-major (2, C, T) tensors (flow_matching.py:126-153)
+__global__ void dit_pack_cm_kernel(const float* __restrict__ x, const float* __restrict__ cond, const float* __restrict__ mu,
+                                   const float* __restrict__ spks, __half* __restrict__ xin, int T, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int W = 4 * C;
+  if (i >= 2 * T * W) return;
+  const int r = i / W, j = i - r * W;
+  const int b = r / T, t = r - b * T;
+  const int part = j / C, c = j - part * C;
+  const size_t idx = ((size_t)b * C + c) * T + t;
+  float v;
+  if (part == 0) v = x[idx];
+  else if (part == 1) v = cond[idx];
+  else if (part == 2) v = mu[idx];
+  else v = spks[b * C + c];
+  xin[i] = __float2half_rn(v);
+}
+
+// v (2T, C) frame-major -> out (2, C, T)
+__global__ void dit_unpack_cm_kernel(const float* __restrict__ v, float* __restrict__ out, int T, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * T * C) return;
+  const int b = i / (C * T), rem = i - b * C * T;
+  const int c = rem / T, t = rem - c * T;
+  out[i] = v[((size_t)b * T + t) * C + c];
+}
+
+// SinusPositionEmbedding(256) -> Linear -> SiLU -> Linear, then the SiLU every adaLN applies first
+// (modules.py:71-83,606-616,236).  One block per t value; a warp per output feature.
+__global__ void __launch_bounds__(256) flow_time_embed_kernel(const float* __restrict__ t_dev, const float* __restrict__ freqs,
+                                                               const float* __restrict__ w0, const float* __restrict__ b0,
+                                                               const float* __restrict__ w2, const float* __restrict__ b2,
+                                                               __half* __restrict__ st16, int dim) {
+  __shared__ float s_in[256];
+  __shared__ float s_h[2048];
+  const float t = t_dev[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 128) {
+    const float a = (1000.0f * t) * freqs[tid];
+    s_in[tid] = sinf(a);
+    s_in[tid + 128] = cosf(a);
+  }
+  __syncthreads();
+  for (int j = warp; j < dim; j += 8) {
+    float acc = 0.f;
+    for (int i = lane; i < 256; i += 32) acc = fmaf(w0[(size_t)j * 256 + i], s_in[i], acc);
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) { const float v = acc + b0[j]; s_h[j] = v / (1.0f + expf(-v)); }
+  }
+  __syncthreads();
+  for (int j = warp; j < dim; j += 8) {
+    float acc = 0.f;
+    for (int i = lane; i < dim; i += 32) acc = fmaf(w2[(size_t)j * dim + i], s_h[i], acc);
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) { const float v = acc + b2[j]; st16[(size_t)blockIdx.x * dim + j] = __float2half_rn(v / (1.0f + expf(-v))); }
+  }
+}
+
+// rotary table of the x_transformers convention: ang[t][i] = t * inv_freq[i]  (dit.py:158, modules.py:367-373)
+__global__ void flow_rope_kernel(const float* __restrict__ inv_freq, float* __restrict__ cs, float* __restrict__ sn, int T) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * 32) return;
+  const float a = (float)(i >> 5) * inv_freq[i & 31];
+  cs[i] = cosf(a);
+  sn[i] = sinf(a);
+}
+
+// out16 = LayerNorm(h) * (1 + scale) + shift   (modules.py:230-244,262-265; eps 1e-6, no affine)
+__global__ void __launch_bounds__(256) dit_ln_mod_kernel(const float* __restrict__ h, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, __half* __restrict__ out, int M,
+                                                          int D) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* hr = h + (size_t)row * D;
+  float v[32];
+  const int n = D >> 5;                    // D <= 1024, multiple of 32
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; k++)
+    if (k < n) { v[k] = hr[k * 32 + lane]; s += v[k]; }
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; k++)
+    if (k < n) { const float d = v[k] - mean; q += d * d; }
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)D + 1e-6f);
+  __half* orow = out + (size_t)row * D;
+#pragma unroll
+  for (int k = 0; k < 32; k++)
+    if (k < n) {
+      const int c = k * 32 + lane;
+      orow[c] = __float2half_rn((v[k] - mean) * rstd * (1.0f + scale[c]) + shift[c]);
+    }
+}
+
+// classifier-free guidance + Euler step (flow_matching.py:113-118)
+__global__ void flow_euler_kernel(const float* __restrict__ v, float* __restrict__ x, int n, float dt, float cfg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float d = (1.0f + cfg) * v[i] - cfg * v[n + i];
+  x[i] = x[i] + dt * d;
+}
+
+// mel_out (C, T_out) = x[mel_len1:, :]^T   (flow.py:427-429)
+__global__ void flow_out_kernel(const float* __restrict__ x, float* __restrict__ out, int T_out, int C, int mel_len1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T_out * C) return;
+  const int c = i / T_out, t = i - c * T_out;
+  out[i] = x[(size_t)(mel_len1 + t) * C + c];
+}
+
+// ------------------------------------------------------------------ state
+struct FlowBlk { const __half *qkv_w, *out_w, *ff1_w, *ff2_w; const float *qkv_b, *out_b, *ff1_b, *ff2_b; };
+
+struct FlowState {
+  const float *spk_w, *spk_b, *emb, *pla1_b, *pla2_b, *tm0_w, *tm0_b, *tm2_w, *tm2_b, *in_b, *pos1_b, *pos2_b, *mod_b, *proj_b;
+  const float* inv_freq;
+  const __half *pla1_w, *pla2_w, *in_w, *pos1_w, *pos2_w, *mod_w, *proj_w;
+  FlowBlk blk[64];
+  float* freqs_dev = nullptr;
+  DevBuf ws, ws_small;
+  int rope_T = -1;
+  // carve-up of ws for the current T (set by flow_plan)
+  int T = 0, Tp = 0;
+  __half *xin, *h0h, *c1, *n16, *qk, *vt, *ao, *f1;
+  float *h0, *h, *v, *rope_c, *rope_s;
+  // solve-level buffers (ws_small)
+  float *spks, *e32, *mu_tok, *mu, *cond, *x, *mod, *t_dev;
+  __half *e16, *y1p, *st16;
+};
+
+template <typename T>
+static hvx_status get_t(hvx_engine* e, const std::string& name, int dtype, const T** p, int64_t numel = -1) {
+  const Tensor* t = e->find(HVX_STAGE_FLOW, name);
+  HVX_CHECK(t && t->dtype == dtype, HVX_ERR_STATE, "flow: missing tensor %s (or wrong dtype)", name.c_str());
+  HVX_CHECK(numel < 0 || t->numel() == numel, HVX_ERR_STATE, "flow: tensor %s has %lld elements, expected %lld", name.c_str(),
+            (long long)t->numel(), (long long)numel);
+  *p = reinterpret_cast<const T*>(t->p);
+  return HVX_OK;
+}
+
+#define FLOW_GET(call) do { hvx_status _s = (call); if (_s) return _s; } while (0)
+
+hvx_status flow_finalize(hvx_engine* e) {
+  const hvx_config& c = e->cfg;
+  const int dim = c.flow_dim, inner = c.flow_heads * c.flow_dim_head, ff = dim * c.flow_ff_mult, mel = c.flow_mel;
+  HVX_CHECK(c.flow_dim_head == 64, HVX_ERR_UNSUPPORTED, "flow: dim_head must be 64");
+  HVX_CHECK(dim % 64 == 0 && dim <= 1024 && dim / c.flow_pos_groups == 64, HVX_ERR_UNSUPPORTED,
+            "flow: dim must be a multiple of 64 (<=1024) with 64-channel conv groups (dim=%d groups=%d)", dim, c.flow_pos_groups);
+  HVX_CHECK(c.flow_depth <= 64 && mel % 8 == 0 && c.flow_pla_ch % 64 == 0, HVX_ERR_UNSUPPORTED, "flow: unsupported dims");
+  if (!e->flow) e->flow = new FlowState();
+  FlowState* f = e->flow;
+  const int64_t kpos = (int64_t)c.flow_pos_k * 64;
+  FLOW_GET(get_t(e, "spk.w", HVX_F32, &f->spk_w, (int64_t)mel * c.flow_spk_in));
+  FLOW_GET(get_t(e, "spk.b", HVX_F32, &f->spk_b, mel));
+  FLOW_GET(get_t(e, "emb", HVX_F32, &f->emb, (int64_t)c.flow_vocab * mel));
+  FLOW_GET(get_t(e, "pla1.w", HVX_F16, &f->pla1_w, (int64_t)c.flow_pla_ch * 4 * ((mel + 63) / 64 * 64)));
+  FLOW_GET(get_t(e, "pla1.b", HVX_F32, &f->pla1_b, c.flow_pla_ch));
+  FLOW_GET(get_t(e, "pla2.w", HVX_F16, &f->pla2_w, (int64_t)mel * 3 * c.flow_pla_ch));
+  FLOW_GET(get_t(e, "pla2.b", HVX_F32, &f->pla2_b, mel));
+  FLOW_GET(get_t(e, "tm0.w", HVX_F32, &f->tm0_w, (int64_t)dim * 256));
+  FLOW_GET(get_t(e, "tm0.b", HVX_F32, &f->tm0_b, dim));
+  FLOW_GET(get_t(e, "tm2.w", HVX_F32, &f->tm2_w, (int64_t)dim * dim));
+  FLOW_GET(get_t(e, "tm2.b", HVX_F32, &f->tm2_b, dim));
+  FLOW_GET(get_t(e, "in.w", HVX_F16, &f->in_w, (int64_t)dim * 4 * mel));
+  FLOW_GET(get_t(e, "in.b", HVX_F32, &f->in_b, dim));
+  FLOW_GET(get_t(e, "pos1.w", HVX_F16, &f->pos1_w, dim * kpos));
+  FLOW_GET(get_t(e, "pos1.b", HVX_F32, &f->pos1_b, dim));
+  FLOW_GET(get_t(e, "pos2.w", HVX_F16, &f->pos2_w, dim * kpos));
+  FLOW_GET(get_t(e, "pos2.b", HVX_F32, &f->pos2_b, dim));
+  FLOW_GET(get_t(e, "rope.inv_freq", HVX_F32, &f->inv_freq, 32));
+  const int64_t nmod = (int64_t)c.flow_depth * 6 * dim + 2 * dim;
+  FLOW_GET(get_t(e, "mod.w", HVX_F16, &f->mod_w, nmod * dim));
+  FLOW_GET(get_t(e, "mod.b", HVX_F32, &f->mod_b, nmod));
+  FLOW_GET(get_t(e, "proj.w", HVX_F16, &f->proj_w, (int64_t)mel * dim));
+  FLOW_GET(get_t(e, "proj.b", HVX_F32, &f->proj_b, mel));
+  for (int i = 0; i < c.flow_depth; i++) {
+    const std::string p = "blk" + std::to_string(i) + ".";
+    FlowBlk& b = f->blk[i];
+    FLOW_GET(get_t(e, p + "qkv.w", HVX_F16, &b.qkv_w, (int64_t)3 * inner * dim));
+    FLOW_GET(get_t(e, p + "qkv.b", HVX_F32, &b.qkv_b, 3 * inner));
+    FLOW_GET(get_t(e, p + "out.w", HVX_F16, &b.out_w, (int64_t)dim * inner));
+    FLOW_GET(get_t(e, p + "out.b", HVX_F32, &b.out_b, dim));
+    FLOW_GET(get_t(e, p + "ff1.w", HVX_F16, &b.ff1_w, (int64_t)ff * dim));
+    FLOW_GET(get_t(e, p + "ff1.b", HVX_F32, &b.ff1_b, ff));
+    FLOW_GET(get_t(e, p + "ff2.w", HVX_F16, &b.ff2_w, (int64_t)dim * ff));
+    FLOW_GET(get_t(e, p + "ff2.b", HVX_F32, &b.ff2_b, dim));
+  }
+  if (!f->freqs_dev) {
+    // SinusPositionEmbedding: exp(arange(128) * -(ln(1e4)/127)) in fp32 (modules.py:76-80)
+    float fr[128];
+    const float e32 = (float)(-(std::log(10000.0) / 127.0));
+    for (int k = 0; k < 128; k++) fr[k] = expf((float)k * e32);
+    HVX_CUDA(cudaMalloc(&f->freqs_dev, sizeof(fr)));
+    HVX_CUDA(cudaMemcpy(f->freqs_dev, fr, sizeof(fr), cudaMemcpyHostToDevice));
+  }
+  return HVX_OK;
+}
+
+void flow_free(hvx_engine* e) {
+  if (e->flow && e->flow->freqs_dev) cudaFree(e->flow->freqs_dev);
+  delete e->flow;
+  e->flow = nullptr;
+}
+
+static inline size_t al256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+// estimator workspace for T frames (2T rows)
+static hvx_status flow_plan(hvx_engine* e, cudaStream_t st, int T) {
+  FlowState* f = e->flow;
+  const hvx_config& c = e->cfg;
+  const int dim = c.flow_dim, inner = c.flow_heads * 64, ff = dim * c.flow_ff_mult, mel = c.flow_mel;
+  const size_t M = 2 * (size_t)T;
+  const int Tp = (T + 7) & ~7;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
+  const size_t o_xin = take(M * 4 * mel * 2), o_h0 = take(M * dim * 4), o_h0h = take(M * dim * 2), o_c1 = take(M * dim * 2);
+  const size_t o_h = take(M * dim * 4), o_n = take(M * dim * 2), o_qk = take(M * 2 * inner * 2);
+  const size_t o_vt = take((size_t)2 * inner * Tp * 2), o_ao = take(M * inner * 2), o_f1 = take(M * ff * 2);
+  const size_t o_v = take(M * mel * 4), o_rc = take((size_t)T * 32 * 4), o_rs = take((size_t)T * 32 * 4);
+  const bool grew = off > f->ws.bytes;
+  uint8_t* w = (uint8_t*)f->ws.get(off);
+  HVX_CHECK(w, HVX_ERR_CUDA, "flow: workspace allocation of %zu bytes failed", off);
+  if (grew) { HVX_CUDA(cudaMemsetAsync(w, 0, f->ws.bytes, st)); f->rope_T = -1; }     // V^T pad columns must be finite
+  f->xin = (__half*)(w + o_xin); f->h0 = (float*)(w + o_h0); f->h0h = (__half*)(w + o_h0h); f->c1 = (__half*)(w + o_c1);
+  f->h = (float*)(w + o_h); f->n16 = (__half*)(w + o_n); f->qk = (__half*)(w + o_qk); f->vt = (__half*)(w + o_vt);
+  f->ao = (__half*)(w + o_ao); f->f1 = (__half*)(w + o_f1); f->v = (float*)(w + o_v);
+  f->rope_c = (float*)(w + o_rc); f->rope_s = (float*)(w + o_rs);
+  if (f->T != T || f->rope_T != T) {
+    // the carve-up moved: V^T pad columns of the new layout may hold stale non-finite bit patterns
+    HVX_CUDA(cudaMemsetAsync(f->vt, 0, (size_t)2 * inner * Tp * 2, st));
+    flow_rope_kernel<<<cdiv(T * 32, 256), 256, 0, st>>>(f->inv_freq, f->rope_c, f->rope_s, T);
+    HVX_LAUNCH_CHECK(e);
+    f->rope_T = T;
+  }
+  f->T = T; f->Tp = Tp;
+  return HVX_OK;
+}
+
+static GemmEpi epi16(void* out, int ldo, const float* bias, int act) {
+  GemmEpi p; p.mode = EPI_BF16; p.f16 = 1; p.act = act; p.bias = bias; p.out = out; p.ldo = ldo; return p;
+}
+
+// one estimator evaluation: xin (2T, 4*mel) fp16 -> v (2T, mel) fp32   (DiT.forward, dit.py:145-176)
+static hvx_status flow_nfe(hvx_engine* e, cudaStream_t st, const float* mod, int streaming) {
+  FlowState* f = e->flow;
+  const hvx_config& c = e->cfg;
+  const int T = f->T, M = 2 * T, dim = c.flow_dim, inner = c.flow_heads * 64, ff = dim * c.flow_ff_mult, mel = c.flow_mel;
+  hvx_status rc;
+  // input embedding: Linear(320 -> dim) + causal grouped conv position embedding (dit.py:76-98, modules.py:115-144)
+  { GemmEpi p; p.mode = EPI_F32; p.f16 = 1; p.bias = f->in_b; p.out = f->h0; p.ldo = dim; p.out2 = (__nv_bfloat16*)f->h0h;
+    if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->xin, 4 * mel, (const __nv_bfloat16*)f->in_w, 4 * mel, M, dim, 4 * mel, p))) return rc; }
+  GemmAddr ga; ga.n_batch = 2; ga.rows_per_batch = T; ga.a_cols = dim; ga.a_col_per_ntile = 64; ga.kb_per_tap = 1;
+  ga.a_row0 = -(c.flow_pos_k - 1); ga.a_row_step = 1;
+  const int kpos = c.flow_pos_k * 64;
+  { GemmEpi p = epi16(f->c1, dim, f->pos1_b, ACT_MISH);
+    if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->h0h, dim, (const __nv_bfloat16*)f->pos1_w, kpos, M, dim, kpos, p, &ga))) return rc; }
+  { GemmEpi p; p.mode = EPI_F32; p.f16 = 1; p.act = ACT_MISH; p.bias = f->pos2_b; p.out = f->h; p.ldo = dim; p.resid = f->h0;
+    if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->c1, dim, (const __nv_bfloat16*)f->pos2_w, kpos, M, dim, kpos, p, &ga))) return rc; }
+  for (int i = 0; i < c.flow_depth; i++) {
+    const FlowBlk& b = f->blk[i];
+    const float* m = mod + (size_t)i * 6 * dim;       // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
+    dit_ln_mod_kernel<<<cdiv(M, 8), 256, 0, st>>>(f->h, m + dim, m, f->n16, M, dim);
+    HVX_LAUNCH_CHECK(e);
+    { GemmEpi p; p.mode = EPI_QKV; p.f16 = 1; p.bias = b.qkv_b; p.out = f->qk; p.ldo = 2 * inner; p.n_qk = 2 * inner;
+      p.vt = (__nv_bfloat16*)f->vt; p.vt_ld = f->Tp; p.T = T; p.heads = c.flow_heads; p.rows_per_batch = T;
+      p.rope_cos = f->rope_c; p.rope_sin = f->rope_s;
+      if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->n16, dim, (const __nv_bfloat16*)b.qkv_w, dim, M, 3 * inner, dim, p))) return rc; }
+    { AttnArgs a; a.T = T; a.heads = c.flow_heads; a.n_batch = 2; a.chunk = streaming ? c.flow_chunk : 0; a.f16 = 1;
+      a.ld_out = inner; a.out = (__nv_bfloat16*)f->ao;
+      if ((rc = dit_attention(e, st, (const __nv_bfloat16*)f->qk, 2 * inner, inner, (const __nv_bfloat16*)f->vt, f->Tp, a))) return rc; }
+    { GemmEpi p; p.mode = EPI_RESID_GATE; p.f16 = 1; p.bias = b.out_b; p.out = f->h; p.ldo = dim; p.gate = m + 2 * dim;
+      p.gate_ld = 0; p.rows_per_batch = T;
+      if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->ao, inner, (const __nv_bfloat16*)b.out_w, inner, M, dim, inner, p))) return rc; }
+    dit_ln_mod_kernel<<<cdiv(M, 8), 256, 0, st>>>(f->h, m + 4 * dim, m + 3 * dim, f->n16, M, dim);
+    HVX_LAUNCH_CHECK(e);
+    { GemmEpi p = epi16(f->f1, ff, b.ff1_b, ACT_GELU_TANH);
+      if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->n16, dim, (const __nv_bfloat16*)b.ff1_w, dim, M, ff, dim, p))) return rc; }
+    { GemmEpi p; p.mode = EPI_RESID_GATE; p.f16 = 1; p.bias = b.ff2_b; p.out = f->h; p.ldo = dim; p.gate = m + 5 * dim;
+      p.gate_ld = 0; p.rows_per_batch = T;
+      if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->f1, ff, (const __nv_bfloat16*)b.ff2_w, ff, M, dim, ff, p))) return rc; }
+  }
+  const float* mf = mod + (size_t)c.flow_depth * 6 * dim;     // AdaLayerNormZero_Final: (scale, shift)  (modules.py:262)
+  dit_ln_mod_kernel<<<cdiv(M, 8), 256, 0, st>>>(f->h, mf, mf + dim, f->n16, M, dim);
+  HVX_LAUNCH_CHECK(e);
+  { GemmEpi p; p.mode = EPI_F32; p.f16 = 1; p.bias = f->proj_b; p.out = f->v; p.ldo = mel;
+    if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->n16, dim, (const __nv_bfloat16*)f->proj_w, dim, M, mel, dim, p))) return rc; }
+  return HVX_OK;
+}
+
+// adaLN modulations of all blocks for n t-values (t_dev on device): mod (n, depth*6*dim + 2*dim)
+static hvx_status flow_mods(hvx_engine* e, cudaStream_t st, const float* t_dev, int n, __half* st16, float* mod) {
+  FlowState* f = e->flow;
+  const hvx_config& c = e->cfg;
+  const int dim = c.flow_dim;
+  const int nmod = c.flow_depth * 6 * dim + 2 * dim;
+  flow_time_embed_kernel<<<n, 256, 0, st>>>(t_dev, f->freqs_dev, f->tm0_w, f->tm0_b, f->tm2_w, f->tm2_b, st16, dim);
+  HVX_LAUNCH_CHECK(e);
+  GemmEpi p; p.mode = EPI_F32; p.f16 = 1; p.bias = f->mod_b; p.out = mod; p.ldo = nmod;
+  return gemm_bf16(e, st, (const __nv_bfloat16*)st16, dim, (const __nv_bfloat16*)f->mod_w, dim, n, nmod, dim, p);
+}
+
+}  // namespace hvx
+
 using namespace hvx;
-extern "C" hvx_status hvx_flow_inference(hvx_engine*, const int32_t*, int, int, const float*, const float*, const float*, int,
-                                         int, int, float*, void*) { set_error("flow not built"); return HVX_ERR_UNSUPPORTED; }
-extern "C" hvx_status hvx_dit_estimator(hvx_engine*, const float*, const float*, const float*, const float*, const float*, int,
-                                        int, float*, void*) { set_error("flow not built"); return HVX_ERR_UNSUPPORTED; }
+
+extern "C" hvx_status hvx_flow_inference(hvx_engine* e, const int32_t* tokens, int n_prompt, int n_tok, const float* embedding,
+                                         const float* prompt_feat, const float* noise, int n_timesteps, int streaming,
+                                         int finalize, float* mel_out, void* stream) {
+  HVX_CHECK(e && e->flow, HVX_ERR_STATE, "flow stage not finalized");
+  HVX_CHECK(tokens && embedding && noise && mel_out, HVX_ERR_ARG, "flow: null argument");
+  HVX_CHECK(n_timesteps >= 1 && n_timesteps <= 64, HVX_ERR_ARG, "flow: n_timesteps=%d out of range [1,64]", n_timesteps);
+  HVX_CHECK(n_prompt == 0 || prompt_feat, HVX_ERR_ARG, "flow: prompt tokens without prompt_feat");
+  FlowState* f = e->flow;
+  const hvx_config& c = e->cfg;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int mel = c.flow_mel, dim = c.flow_dim, pc = c.flow_pla_ch;
+  const int ntok = n_prompt + n_tok;
+  const int L1 = finalize ? ntok : ntok - 3;                       // look-ahead tokens are context only (flow.py:399-403)
+  HVX_CHECK(L1 >= 1 && n_tok - (finalize ? 0 : 3) >= 1, HVX_ERR_ARG, "flow: too few tokens (%d)", n_tok);
+  const int T = 2 * L1, mel_len1 = 2 * n_prompt, T_out = T - mel_len1;
+  HVX_CHECK(T <= c.flow_noise_frames, HVX_ERR_ARG, "flow: %d frames exceed the noise table (%d)", T, c.flow_noise_frames);
+  const int nmod = c.flow_depth * 6 * dim + 2 * dim;
+
+  // solve-level buffers
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
+  const int Cp = (mel + 63) / 64 * 64;                              // embedding rows padded to whole 64-wide k-blocks
+  const size_t o_spk = take(mel * 4), o_e32 = take((size_t)ntok * mel * 4), o_e16 = take((size_t)(ntok + 3) * Cp * 2);
+  const size_t o_y1 = take((size_t)L1 * pc * 2), o_mut = take((size_t)L1 * mel * 4);
+  const size_t o_mu = take((size_t)T * mel * 4), o_cond = take((size_t)T * mel * 4), o_x = take((size_t)T * mel * 4);
+  const size_t o_mod = take((size_t)n_timesteps * nmod * 4), o_t = take(64 * 4), o_st = take((size_t)64 * dim * 2);
+  uint8_t* w = (uint8_t*)f->ws_small.get(off);
+  HVX_CHECK(w, HVX_ERR_CUDA, "flow: buffer allocation of %zu bytes failed", off);
+  f->spks = (float*)(w + o_spk); f->e32 = (float*)(w + o_e32); f->e16 = (__half*)(w + o_e16); f->y1p = (__half*)(w + o_y1);
+  f->mu_tok = (float*)(w + o_mut); f->mu = (float*)(w + o_mu); f->cond = (float*)(w + o_cond); f->x = (float*)(w + o_x);
+  f->mod = (float*)(w + o_mod); f->t_dev = (float*)(w + o_t); f->st16 = (__half*)(w + o_st);
+  hvx_status rc;
+  if ((rc = flow_plan(e, st, T))) return rc;
+
+  // ---- pre-net (flow.py:387-419)
+  flow_spk_kernel<<<1, 256, 0, st>>>(embedding, f->spk_w, f->spk_b, f->spks, c.flow_spk_in, mel);
+  HVX_LAUNCH_CHECK(e);
+  flow_embed_kernel<<<cdiv((ntok + 3) * Cp, 256), 256, 0, st>>>(tokens, f->emb, f->e32, f->e16, ntok, ntok + 3, mel, Cp, c.flow_vocab);
+  HVX_LAUNCH_CHECK(e);
+  { // conv1 k4, 3 look-ahead rows (zero rows after the last token when finalize): implicit GEMM, K = 4*Cp
+    GemmEpi p = epi16(f->y1p, pc, f->pla1_b, ACT_LRELU);
+    GemmAddr ga; ga.rows_per_batch = L1; ga.a_rows = ntok + 3; ga.a_cols = Cp; ga.kb_per_tap = Cp / 64; ga.a_row_step = 1;
+    if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->e16, Cp, (const __nv_bfloat16*)f->pla1_w, 4 * Cp, L1, pc, 4 * Cp, p, &ga))) return rc; }
+  { // conv2 k3 causal (left pad 2 = out-of-bounds rows) + residual
+    GemmEpi p; p.mode = EPI_F32; p.f16 = 1; p.bias = f->pla2_b; p.out = f->mu_tok; p.ldo = mel; p.resid = f->e32;
+    GemmAddr ga; ga.rows_per_batch = L1; ga.a_cols = pc; ga.kb_per_tap = pc / 64; ga.a_row0 = -2; ga.a_row_step = 1;
+    if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->y1p, pc, (const __nv_bfloat16*)f->pla2_w, 3 * pc, L1, mel, 3 * pc, p, &ga))) return rc; }
+  flow_init_kernel<<<cdiv(T * mel, 256), 256, 0, st>>>(f->mu_tok, prompt_feat, noise, f->mu, f->cond, f->x, T, mel, mel_len1,
+                                                        c.flow_noise_frames);
+  HVX_LAUNCH_CHECK(e);
+
+  // ---- cosine t-schedule carried in fp32 exactly like solve_euler (flow_matching.py:93-122,225-227)
+  float ts[65], tv[64], dtv[64];
+  for (int i = 0; i <= n_timesteps; i++) {
+    const float step = 1.0f / (float)n_timesteps;
+    const float lin = (i < (n_timesteps + 1) / 2) ? (float)i * step : 1.0f - (float)(n_timesteps - i) * step;   // torch.linspace
+    ts[i] = 1.0f - cosf((lin * 0.5f) * 3.14159265358979323846f);
+  }
+  { float t = ts[0], dt = ts[1] - ts[0];
+    for (int s = 1; s <= n_timesteps; s++) {
+      tv[s - 1] = t; dtv[s - 1] = dt;
+      t = t + dt;
+      if (s < n_timesteps) dt = ts[s + 1] - t;
+    } }
+  HVX_CUDA(cudaMemcpyAsync(f->t_dev, tv, sizeof(float) * n_timesteps, cudaMemcpyHostToDevice, st));
+  if ((rc = flow_mods(e, st, f->t_dev, n_timesteps, f->st16, f->mod))) return rc;
+
+  // ---- Euler steps
+  for (int s = 0; s < n_timesteps; s++) {
+    dit_pack_fm_kernel<<<cdiv(2 * T * 4 * mel, 256), 256, 0, st>>>(f->x, f->cond, f->mu, f->spks, f->xin, T, mel);
+    HVX_LAUNCH_CHECK(e);
+    if ((rc = flow_nfe(e, st, f->mod + (size_t)s * nmod, streaming))) return rc;
+    flow_euler_kernel<<<cdiv(T * mel, 256), 256, 0, st>>>(f->v, f->x, T * mel, dtv[s], c.flow_cfg_rate);
+    HVX_LAUNCH_CHECK(e);
+  }
+  flow_out_kernel<<<cdiv(T_out * mel, 256), 256, 0, st>>>(f->x, mel_out, T_out, mel, mel_len1);
+  HVX_LAUNCH_CHECK(e);
+  return HVX_OK;
+}
+
+extern "C" hvx_status hvx_dit_estimator(hvx_engine* e, const float* x, const float* mu, const float* t, const float* spks,
+                                        const float* cond, int T, int streaming, float* out, void* stream) {
+  HVX_CHECK(e && e->flow, HVX_ERR_STATE, "flow stage not finalized");
+  HVX_CHECK(x && mu && t && spks && cond && out && T >= 1, HVX_ERR_ARG, "estimator: bad argument");
+  FlowState* f = e->flow;
+  const hvx_config& c = e->cfg;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int mel = c.flow_mel, dim = c.flow_dim;
+  const int nmod = c.flow_depth * 6 * dim + 2 * dim;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
+  const size_t o_mod = take((size_t)nmod * 4), o_st = take((size_t)64 * dim * 2);
+  uint8_t* w = (uint8_t*)f->ws_small.get(off);
+  HVX_CHECK(w, HVX_ERR_CUDA, "estimator: buffer allocation failed");
+  float* mod = (float*)(w + o_mod);
+  __half* st16 = (__half*)(w + o_st);
+  hvx_status rc;
+  if ((rc = flow_plan(e, st, T))) return rc;
+  if ((rc = flow_mods(e, st, t, 1, st16, mod))) return rc;         // both CFG rows share t (flow_matching.py:104)
+  dit_pack_cm_kernel<<<cdiv(2 * T * 4 * mel, 256), 256, 0, st>>>(x, cond, mu, spks, f->xin, T, mel);
+  HVX_LAUNCH_CHECK(e);
+  if ((rc = flow_nfe(e, st, mod, streaming))) return rc;
+  dit_unpack_cm_kernel<<<cdiv(2 * T * mel, 256), 256, 0, st>>>(f->v, out, T, mel);
+  HVX_LAUNCH_CHECK(e);
+  return HVX_OK;
+}

@@ -69,6 +69,7 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   }
   if (act == ACT_SILU) return v / (1.0f + __expf(-v));
   if (act == ACT_MISH) { const float sp = v > 20.0f ? v : log1pf(expf(v)); return v * tanhf(sp); }
+  if (act == ACT_LRELU) return v > 0.f ? v : 0.01f * v;
   return v;
 }
 
@@ -111,14 +112,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         tc::mbar_wait(&empty_bar[s], ph ^ 1);
         tc::mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
         uint8_t* sa = smem + s * S::STAGE_BYTES;
-        tc::tma_load_3d(sa, &tma_a, &full_bar[s], ad.a_col0 + blockIdx.x * ad.a_col_per_ntile + kb * ad.a_col_step,
-                        m0 + ad.a_row0 + kb * ad.a_row_step, batch);
+        const int tap = ad.kb_per_tap ? kb / ad.kb_per_tap : 0;
+        const int kin = ad.kb_per_tap ? kb - tap * ad.kb_per_tap : kb;
+        tc::tma_load_3d(sa, &tma_a, &full_bar[s], ad.a_col0 + blockIdx.x * ad.a_col_per_ntile + kin * BK,
+                        m0 + ad.a_row0 + tap * ad.a_row_step, batch);
         tc::tma_load_2d(sa + S::A_BYTES, &tma_b, &full_bar[s], kb * BK, n0);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = tc::umma_idesc_bf16(BM, BN);
+      const uint32_t idesc = epi.f16 ? tc::umma_idesc_f16(BM, BN) : tc::umma_idesc_bf16(BM, BN);
       for (int kb = 0; kb < nkb; kb++) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -163,15 +166,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             uint4 pk;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(f[j], f[j + 1]), t1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), t3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-            pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-            pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+            pk.x = tc::pack16(f[j], f[j + 1], epi.f16); pk.y = tc::pack16(f[j + 2], f[j + 3], epi.f16);
+            pk.z = tc::pack16(f[j + 4], f[j + 5], epi.f16); pk.w = tc::pack16(f[j + 6], f[j + 7], epi.f16);
             *reinterpret_cast<uint4*>(o + j) = pk;
           }
         } else {
           #pragma unroll
-          for (int j = 0; j < 32; j++) if (col0 + j < N) o[j] = __float2bfloat16(f[j]);
+          for (int j = 0; j < 32; j++) if (col0 + j < N) reinterpret_cast<uint16_t*>(o)[j] = tc::cvt16(f[j], epi.f16);
         }
       } else if (epi.mode == EPI_F32) {
         float* o = reinterpret_cast<float*>(epi.out) + (size_t)row * epi.ldo + col0;
@@ -185,7 +186,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if (epi.out2) {
           __nv_bfloat16* o2 = epi.out2 + (size_t)row * epi.ldo + col0;
           #pragma unroll
-          for (int j = 0; j < 32; j++) if (col0 + j < N) o2[j] = __float2bfloat16(f[j]);
+          for (int j = 0; j < 32; j++) if (col0 + j < N) reinterpret_cast<uint16_t*>(o2)[j] = tc::cvt16(f[j], epi.f16);
         }
       } else if (epi.mode == EPI_RESID_GATE) {
         float* o = reinterpret_cast<float*>(epi.out) + (size_t)row * epi.ldo + col0;
@@ -223,10 +224,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             uint4 pk;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(f[j], f[j + 1]), t1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), t3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-            pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-            pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+            pk.x = tc::pack16(f[j], f[j + 1], epi.f16); pk.y = tc::pack16(f[j + 2], f[j + 3], epi.f16);
+            pk.z = tc::pack16(f[j + 4], f[j + 5], epi.f16); pk.w = tc::pack16(f[j + 6], f[j + 7], epi.f16);
             *reinterpret_cast<uint4*>(o + j) = pk;
           }
         } else {
@@ -234,7 +233,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           const int h = cv >> 6, d0 = cv & 63;
           __nv_bfloat16* o = epi.vt + ((size_t)(bidx * epi.heads + h) * 64 + d0) * epi.vt_ld + t;
 #pragma unroll
-          for (int j = 0; j < 32; j++) o[(size_t)j * epi.vt_ld] = __float2bfloat16(f[j]);
+          for (int j = 0; j < 32; j++) reinterpret_cast<uint16_t*>(o)[(size_t)j * epi.vt_ld] = tc::cvt16(f[j], epi.f16);
         }
       }
     }
@@ -267,10 +266,11 @@ hvx_status gemm_bf16(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* A, int
   if (addr) ad = *addr;
   if (ad.rows_per_batch == 0) ad.rows_per_batch = M;
   if (ad.a_cols == 0) ad.a_cols = K;
+  if (ad.a_rows == 0) ad.a_rows = ad.rows_per_batch;
   HVX_CHECK((lda % 8) == 0 && (ldb % 8) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0, HVX_ERR_ARG,
             "gemm: operands must be 16-byte aligned with leading dims multiple of 8 (lda=%d ldb=%d)", lda, ldb);
   CUtensorMap ta, tb;
-  HVX_CHECK(make_tmap_bf16_3d(&ta, A, ad.n_batch, ad.rows_per_batch, ad.a_cols, lda, BM, BK), HVX_ERR_CUDA,
+  HVX_CHECK(make_tmap_bf16_3d(&ta, A, ad.n_batch, ad.a_rows, ad.a_cols, lda, BM, BK), HVX_ERR_CUDA,
             "gemm: cuTensorMapEncodeTiled(A) failed");
   if (N <= 64 || ad.a_col_per_ntile == 64) {
     HVX_CHECK(make_tmap_bf16_2d(&tb, B, N, K, ldb, 64, BK), HVX_ERR_CUDA, "gemm: cuTensorMapEncodeTiled(B) failed");
@@ -289,7 +289,8 @@ extern "C" hvx_status hvx_gemm_bf16(hvx_engine* e, const void* A, const void* B,
                                     int K, int out_f32, int act, void* stream) {
   HVX_CHECK(e, HVX_ERR_ARG, "null engine");
   GemmEpi epi;
-  epi.mode = out_f32 ? EPI_F32 : EPI_BF16;
+  epi.mode = (out_f32 & 1) ? EPI_F32 : EPI_BF16;     // bit 1 of out_f32: operands are fp16
+  epi.f16 = (out_f32 >> 1) & 1;
   epi.act = act;
   epi.bias = bias;
   epi.out = C;

@@ -12,11 +12,12 @@
 namespace hvx {
 
 enum { EPI_BF16 = 0, EPI_F32 = 1, EPI_RESID_GATE = 2, EPI_QKV = 3 };
-enum { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_SILU = 2, ACT_MISH = 3 };
+enum { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_SILU = 2, ACT_MISH = 3, ACT_LRELU = 4 /* slope 0.01 */ };
 
 struct GemmEpi {
   int mode = EPI_BF16;
   int act = ACT_NONE;
+  int f16 = 0;                      // 1: operands and 16-bit outputs are IEEE fp16 instead of bf16 (flow stage)
   const float* bias = nullptr;      // [N]
   void* out = nullptr;              // bf16 (EPI_BF16/EPI_QKV) or fp32
   int ldo = 0;
@@ -35,17 +36,23 @@ struct GemmEpi {
   __nv_bfloat16* out2 = nullptr;
 };
 
-// A-operand addressing.  A is viewed as [n_batch][rows_per_batch][lda] and tiles never straddle a
-// batch, so TMA zero-fills above/below each batch row range.  k-block kb reads columns
-// a_col0 + (n0/BN)*a_col_per_ntile + kb*a_col_step and rows m0 + a_row0 + kb*a_row_step:
-//   plain GEMM      : {0, 0, 64, 0, 0}
-//   causal grouped conv as implicit GEMM (CausalConvPositionEmbedding, DiT/modules.py:115-144):
-//     one k-block per tap, A rows shifted by the tap, columns = the group's 64 channels.
+// A-operand addressing.  A is viewed as [n_batch][a_rows][lda]; output tiles never straddle a batch and
+// rows outside [0, a_rows) of the batch read as zero (TMA out-of-bounds fill), which is what gives
+// convolutions their zero padding.  k-block kb reads
+//   columns a_col0 + (n0/BN)*a_col_per_ntile + (kb % kb_per_tap)*64,  rows m0 + a_row0 + (kb / kb_per_tap)*a_row_step
+// (kb_per_tap == 0: plain GEMM, columns kb*64, rows m0):
+//   Conv1d over frame-major activations as implicit GEMM: K = taps * C, kb_per_tap = C/64, a_row_step = 1,
+//     a_row0 = -(left pad)                       (PreLookaheadLayer, upsample_encoder.py:82-103)
+//   causal grouped conv, 64-channel groups: kb_per_tap = 1, a_col_per_ntile = 64 (BN = 64 -> one group per n-tile)
+//                                                (CausalConvPositionEmbedding, DiT/modules.py:115-144)
 struct GemmAddr {
   int n_batch = 1;
-  int rows_per_batch = 0;      // 0 -> M
-  int a_col0 = 0, a_col_per_ntile = 0, a_col_step = 64, a_row0 = 0, a_row_step = 0;
-  int a_cols = 0;              // 0 -> K (width of the A matrix in elements)
+  int rows_per_batch = 0;      // output rows per batch; 0 -> M
+  int a_rows = 0;              // rows of the A tensor per batch; 0 -> rows_per_batch
+  int a_cols = 0;              // width of the A matrix in elements; 0 -> K
+  int a_col0 = 0, a_col_per_ntile = 0;
+  int kb_per_tap = 0;
+  int a_row0 = 0, a_row_step = 0;
 };
 
 hvx_status gemm_bf16(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb,

@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace hvx {
@@ -115,6 +116,21 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major (cute InstrDescriptor bitfields)
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// same with A=B=fp16 (format code 0)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// two floats -> packed 16-bit pair (bf16 or fp16), low half = a
+__device__ __forceinline__ uint32_t pack16(float a, float b, int f16) {
+  if (f16) { __half2 t = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&t); }
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ uint16_t cvt16(float a, int f16) {
+  if (f16) { __half t = __float2half_rn(a); return *reinterpret_cast<uint16_t*>(&t); }
+  __nv_bfloat16 t = __float2bfloat16(a);
+  return *reinterpret_cast<uint16_t*>(&t);
 }
 
 __device__ __forceinline__ bool elect_one() {

@@ -80,7 +80,7 @@ FLOW_FULL = FlowDims()
 LLM_FULL = LlmDims()
 
 HIFT_TINY = HiftDims(base=64, f0_ch=64)
-FLOW_TINY = FlowDims(vocab=512, pla_ch=128, dim=128, depth=2, heads=2, noise_frames=600)
+FLOW_TINY = FlowDims(vocab=512, pla_ch=128, depth=2, noise_frames=600)   # dim stays 1024: the reference hard-codes 16 conv groups
 LLM_TINY = LlmDims(hidden=128, layers=2, q_heads=2, kv_heads=1, inter=256, text_vocab=512,
                    speech_vocab=456, mtp_heads=3, mtp_attn_heads=2, mtp_inter=384)
 

@@ -1,0 +1,79 @@
+"""NativeFlow — drop-in for models['flow'] (CausalMaskedDiffWithDiT, cosyvoice/flow/flow.py:283-430)."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+from .weights import pack_flow
+
+
+def rand_noise(mel: int = 80, frames: int = 15000) -> torch.Tensor:
+    """CausalConditionalCFM.rand_noise (flow_matching.py:200-201): randn(1, 80, 50*300) drawn right after
+    set_all_random_seed(0); a CPU generator seeded 0 reproduces it bit for bit (checked against the
+    reference module by oracle/make_golden.py)."""
+    g = torch.Generator().manual_seed(0)
+    return torch.randn(1, mel, 50 * 300, generator=g)[:, :, :frames].contiguous()
+
+
+class NativeFlow:
+    def __init__(self, engine: "L.Engine", noise: torch.Tensor | None = None, n_timesteps: int = 10):
+        self.engine = engine
+        self.dims = engine.fd
+        self.bf16 = False          # attributes ModelManager.load_models sets (infer_speech_model.py:105-117)
+        self.fp16 = True
+        self.n_timesteps = n_timesteps     # the reference hard-codes 10 (flow.py:425)
+        n = rand_noise(self.dims.mel, self.dims.noise_frames) if noise is None else noise
+        self.noise = n.reshape(self.dims.mel, -1).to(engine.device, torch.float32).contiguous()
+        assert self.noise.shape[1] == self.dims.noise_frames
+
+    def load_state_dict(self, sd, strict=True):
+        self.engine.set_tensors(L.STAGE_FLOW, pack_flow(sd, self.dims))
+        self.engine.finalize(L.STAGE_FLOW)
+        return self
+
+    def eval(self):
+        return self
+
+    def cuda(self):
+        return self
+
+    def half(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    @torch.no_grad()
+    def inference(self, token, token_len=None, embedding=None, finalize=True, prompt_token=None, prompt_token_len=None,
+                  prompt_feat=None, prompt_feat_len=None, streaming=False, n_timesteps=None):
+        """token (1,N) int, embedding (1,spk_in), prompt_token (1,P), prompt_feat (1,2P,mel)
+        -> (mel fp32 (1, mel, 2N'), None)   [flow.py:367-430]"""
+        assert token.shape[0] == 1, "reference asserts batch 1 (flow.py:387)"
+        d, dev = self.dims, self.engine.device
+        n_tok = int(token.shape[1])
+        n_prompt = 0 if prompt_token is None else int(prompt_token.shape[1])
+        toks = token.reshape(-1) if n_prompt == 0 else torch.cat([prompt_token.reshape(-1), token.reshape(-1)])
+        toks = toks.to(dev, torch.int32).contiguous()
+        emb = embedding.reshape(-1).to(dev, torch.float32).contiguous()
+        pf = None
+        if n_prompt:
+            pf = prompt_feat.reshape(-1, d.mel).to(dev, torch.float32).contiguous()
+            assert pf.shape[0] == 2 * n_prompt, "prompt_feat must hold token_mel_ratio frames per prompt token"
+        n_out = 2 * (n_tok if finalize else n_tok - 3)
+        mel = torch.empty(1, d.mel, n_out, device=dev, dtype=torch.float32)
+        steps = int(n_timesteps or self.n_timesteps)
+        L.check(L.lib().hvx_flow_inference(self.engine.h, L.ptr(toks), n_prompt, n_tok, L.ptr(emb), L.ptr(pf),
+                                           L.ptr(self.noise), steps, int(bool(streaming)), int(bool(finalize)),
+                                           L.ptr(mel), L.stream_ptr()))
+        return mel, None
+
+    @torch.no_grad()
+    def estimator(self, x, mask, mu, t, spks, cond, streaming=False):
+        """The TensorRT seam of ConditionalCFM.forward_estimator (flow_matching.py:126-153): (2,mel,T) tensors."""
+        dev = self.engine.device
+        T = int(x.shape[2])
+        args = [a.to(dev, torch.float32).contiguous() for a in (x, mu, t, spks, cond)]
+        out = torch.empty(2, self.dims.mel, T, device=dev, dtype=torch.float32)
+        L.check(L.lib().hvx_dit_estimator(self.engine.h, *[L.ptr(a) for a in args], T, int(bool(streaming)), L.ptr(out),
+                                          L.stream_ptr()))
+        return out

@@ -55,3 +55,55 @@ def pack_hift(sd: Dict[str, torch.Tensor], d: D.HiftDims) -> Dict[str, torch.Ten
             n = i * len(d.rb_k) + j
             rb(f"resblocks.{n}", f"rb.{n}")
     return o
+
+
+def pack_flow(sd: Dict[str, torch.Tensor], d: D.FlowDims) -> Dict[str, torch.Tensor]:
+    """CausalMaskedDiffWithDiT state_dict (flow.py:296-365, DiT/dit.py:104-143) -> engine tensors.
+    GEMM operands are fp16 (the reference serves this stage with .half(), infer_speech_model.py:105-117),
+    biases / tiny layers fp32.  Conv weights become implicit-GEMM B operands: column = tap*C + ci."""
+    h, f = torch.float16, torch.float32
+    o: Dict[str, torch.Tensor] = {}
+    o["spk.w"] = sd["spk_embed_affine_layer.weight"].to(f).contiguous()
+    o["spk.b"] = sd["spk_embed_affine_layer.bias"].to(f).contiguous()
+    o["emb"] = sd["input_embedding.weight"].to(f).contiguous()
+    cp = (d.mel + 63) // 64 * 64
+    w1 = sd["pre_lookahead_layer.conv1.weight"].to(f)                      # (pla, mel, 4)
+    w1p = torch.zeros(w1.shape[0], w1.shape[2], cp)
+    w1p[:, :, : d.mel] = w1.permute(0, 2, 1)
+    o["pla1.w"] = w1p.reshape(w1.shape[0], -1).to(h).contiguous()
+    o["pla1.b"] = sd["pre_lookahead_layer.conv1.bias"].to(f).contiguous()
+    w2 = sd["pre_lookahead_layer.conv2.weight"].to(f)                      # (mel, pla, 3)
+    o["pla2.w"] = w2.permute(0, 2, 1).reshape(w2.shape[0], -1).to(h).contiguous()
+    o["pla2.b"] = sd["pre_lookahead_layer.conv2.bias"].to(f).contiguous()
+    p = "decoder.estimator."
+    o["tm0.w"] = sd[p + "time_embed.time_mlp.0.weight"].to(f).contiguous()
+    o["tm0.b"] = sd[p + "time_embed.time_mlp.0.bias"].to(f).contiguous()
+    o["tm2.w"] = sd[p + "time_embed.time_mlp.2.weight"].to(f).contiguous()
+    o["tm2.b"] = sd[p + "time_embed.time_mlp.2.bias"].to(f).contiguous()
+    o["in.w"] = sd[p + "input_embed.proj.weight"].to(h).contiguous()
+    o["in.b"] = sd[p + "input_embed.proj.bias"].to(f).contiguous()
+    for i, c in enumerate(("conv1", "conv2"), 1):
+        w = sd[p + f"input_embed.conv_pos_embed.{c}.0.weight"].to(f)        # (dim, dim/groups, k)
+        o[f"pos{i}.w"] = w.permute(0, 2, 1).reshape(w.shape[0], -1).to(h).contiguous()
+        o[f"pos{i}.b"] = sd[p + f"input_embed.conv_pos_embed.{c}.0.bias"].to(f).contiguous()
+    o["rope.inv_freq"] = sd[p + "rotary_embed.inv_freq"].to(f).contiguous()
+    mods_w, mods_b = [], []
+    for i in range(d.depth):
+        bp = p + f"transformer_blocks.{i}."
+        o[f"blk{i}.qkv.w"] = torch.cat([sd[bp + f"attn.to_{n}.weight"] for n in "qkv"], 0).to(h).contiguous()
+        o[f"blk{i}.qkv.b"] = torch.cat([sd[bp + f"attn.to_{n}.bias"] for n in "qkv"], 0).to(f).contiguous()
+        o[f"blk{i}.out.w"] = sd[bp + "attn.to_out.0.weight"].to(h).contiguous()
+        o[f"blk{i}.out.b"] = sd[bp + "attn.to_out.0.bias"].to(f).contiguous()
+        o[f"blk{i}.ff1.w"] = sd[bp + "ff.ff.0.0.weight"].to(h).contiguous()
+        o[f"blk{i}.ff1.b"] = sd[bp + "ff.ff.0.0.bias"].to(f).contiguous()
+        o[f"blk{i}.ff2.w"] = sd[bp + "ff.ff.2.weight"].to(h).contiguous()
+        o[f"blk{i}.ff2.b"] = sd[bp + "ff.ff.2.bias"].to(f).contiguous()
+        mods_w.append(sd[bp + "attn_norm.linear.weight"])
+        mods_b.append(sd[bp + "attn_norm.linear.bias"])
+    mods_w.append(sd[p + "norm_out.linear.weight"])
+    mods_b.append(sd[p + "norm_out.linear.bias"])
+    o["mod.w"] = torch.cat(mods_w, 0).to(h).contiguous()
+    o["mod.b"] = torch.cat(mods_b, 0).to(f).contiguous()
+    o["proj.w"] = sd[p + "proj_out.weight"].to(h).contiguous()
+    o["proj.b"] = sd[p + "proj_out.bias"].to(f).contiguous()
+    return o

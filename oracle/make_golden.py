@@ -69,6 +69,7 @@ def golden_hift(name, dims, T, seed):
 
 
 def golden_flow(name, dims, N, P, n_steps, seed):
+    refshim.install()
     import cosyvoice.flow.flow as flowmod
     flowmod.torch = _TorchF32Proxy()
     m = refshim.build_flow(dims)
