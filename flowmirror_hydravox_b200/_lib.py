@@ -33,12 +33,12 @@ class Config(C.Structure):
         ("llm_hidden", C.c_int), ("llm_layers", C.c_int), ("llm_q_heads", C.c_int), ("llm_kv_heads", C.c_int),
         ("llm_head_dim", C.c_int), ("llm_inter", C.c_int), ("llm_text_vocab", C.c_int), ("llm_speech_vocab", C.c_int),
         ("llm_mtp_heads", C.c_int), ("llm_mtp_inter", C.c_int), ("llm_max_ctx", C.c_int), ("llm_max_seqs", C.c_int),
-        ("llm_rope_theta", C.c_float), ("llm_eps", C.c_float),
+        ("llm_rope_theta", C.c_float), ("llm_eps", C.c_float), ("llm_kv_f32", C.c_int),
     ]
 
 
 class Sampler(C.Structure):
-    _fields_ = [("top_p", C.c_float), ("top_k", C.c_int), ("win_size", C.c_int), ("tau_r", C.c_float)]
+    _fields_ = [("top_p", C.c_double), ("tau_r", C.c_double), ("top_k", C.c_int), ("win_size", C.c_int)]
 
 
 class Request(C.Structure):
@@ -51,7 +51,8 @@ class Request(C.Structure):
     ]
 
 
-def make_config(hd: D.HiftDims, fd: D.FlowDims, ld: D.LlmDims, max_ctx: int = 8192, max_seqs: int = 32) -> Config:
+def make_config(hd: D.HiftDims, fd: D.FlowDims, ld: D.LlmDims, max_ctx: int = 8192, max_seqs: int = 32,
+                kv_f32: bool = False) -> Config:
     c = Config()
     c.hift_mel, c.hift_base, c.hift_f0_ch, c.hift_harmonics, c.hift_sr = hd.mel, hd.base, hd.f0_ch, hd.harmonics, hd.sr
     c.hift_n_ups = len(hd.ups)
@@ -73,6 +74,7 @@ def make_config(hd: D.HiftDims, fd: D.FlowDims, ld: D.LlmDims, max_ctx: int = 81
     c.llm_head_dim, c.llm_inter, c.llm_text_vocab, c.llm_speech_vocab = ld.head_dim, ld.inter, ld.text_vocab, ld.speech_vocab
     c.llm_mtp_heads, c.llm_mtp_inter, c.llm_max_ctx, c.llm_max_seqs = ld.mtp_heads, ld.mtp_inter, max_ctx, max_seqs
     c.llm_rope_theta, c.llm_eps = ld.rope_theta, ld.eps
+    c.llm_kv_f32 = int(bool(kv_f32))
     return c
 
 
@@ -107,14 +109,15 @@ def stream_ptr():
 class Engine:
     """Owns one hvx_engine (one per process/GPU, like one reference worker per GPU)."""
 
-    def __init__(self, hd=D.HIFT_FULL, fd=D.FLOW_FULL, ld=D.LLM_FULL, max_ctx=8192, max_seqs=32, device="cuda:0"):
+    def __init__(self, hd=D.HIFT_FULL, fd=D.FLOW_FULL, ld=D.LLM_FULL, max_ctx=8192, max_seqs=32, device="cuda:0",
+                 kv_f32=False):
         if not torch.cuda.is_available():
             raise HvxError("no CUDA device: the HydraVox B200 engine has no CPU fallback")
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
         torch.zeros(1, device=self.device)          # make sure the primary context exists
         self.hd, self.fd, self.ld = hd, fd, ld
-        self.cfg = make_config(hd, fd, ld, max_ctx, max_seqs)
+        self.cfg = make_config(hd, fd, ld, max_ctx, max_seqs, kv_f32)
         self.h = C.c_void_p()
         check(lib().hvx_create(C.byref(self.h), C.byref(self.cfg)))
         self._keep = {0: {}, 1: {}, 2: {}}          # tensors borrowed by the engine

@@ -67,7 +67,7 @@ __device__ __forceinline__ float act_apply(float v, int act) {
     const float k0 = 0.7978845608028654f, k1 = 0.044715f;
     return 0.5f * v * (1.0f + tanhf(k0 * (v + k1 * v * v * v)));
   }
-  if (act == ACT_SILU) return v / (1.0f + __expf(-v));
+  if (act == ACT_SILU) return v / (1.0f + expf(-v));
   if (act == ACT_MISH) { const float sp = v > 20.0f ? v : log1pf(expf(v)); return v * tanhf(sp); }
   if (act == ACT_LRELU) return v > 0.f ? v : 0.01f * v;
   return v;
@@ -116,7 +116,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int kin = ad.kb_per_tap ? kb - tap * ad.kb_per_tap : kb;
         tc::tma_load_3d(sa, &tma_a, &full_bar[s], ad.a_col0 + blockIdx.x * ad.a_col_per_ntile + kin * BK,
                         m0 + ad.a_row0 + tap * ad.a_row_step, batch);
-        tc::tma_load_2d(sa + S::A_BYTES, &tma_b, &full_bar[s], kb * BK, n0);
+        tc::tma_load_2d(sa + S::A_BYTES, &tma_b, &full_bar[s], (ad.b_kb_mod ? kb % ad.b_kb_mod : kb) * BK, n0);
       }
     }
   } else if (warp == 1) {
@@ -162,6 +162,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
       if (epi.mode == EPI_BF16) {
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(epi.out) + (size_t)row * epi.ldo + col0;
+        if (epi.lo_off) {
+#pragma unroll
+          for (int j = 0; j < 32; j++)
+            if (col0 + j < N) o[epi.lo_off + j] = __float2bfloat16(f[j] - __bfloat162float(__float2bfloat16(f[j])));
+        }
         if (col0 + 32 <= N) {
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
@@ -184,9 +189,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         #pragma unroll
         for (int j = 0; j < 32; j++) if (col0 + j < N) o[j] = f[j];
         if (epi.out2) {
-          __nv_bfloat16* o2 = epi.out2 + (size_t)row * epi.ldo + col0;
+          __nv_bfloat16* o2 = epi.out2 + (size_t)row * (epi.ldo2 ? epi.ldo2 : epi.ldo) + col0;
           #pragma unroll
-          for (int j = 0; j < 32; j++) if (col0 + j < N) reinterpret_cast<uint16_t*>(o2)[j] = tc::cvt16(f[j], epi.f16);
+          for (int j = 0; j < 32; j++) if (col0 + j < N) {
+            reinterpret_cast<uint16_t*>(o2)[j] = tc::cvt16(f[j], epi.f16);
+            if (epi.lo_off) o2[epi.lo_off + j] = __float2bfloat16(f[j] - __bfloat162float(__float2bfloat16(f[j])));
+          }
         }
       } else if (epi.mode == EPI_RESID_GATE) {
         float* o = reinterpret_cast<float*>(epi.out) + (size_t)row * epi.ldo + col0;
@@ -204,6 +212,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           #pragma unroll
           for (int j = 0; j < 32; j++) if (col0 + j < N) o[j] = fmaf(__ldg(g + j), f[j], o[j]);
         }
+      } else if (epi.mode == EPI_LLM_QKV) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2)
+          if (col0 + j < N) llm_qkv_store(epi.llm, row, col0 + j, f[j], f[j + 1]);
+      } else if (epi.mode == EPI_SWIGLU) {
+        uint16_t* o = reinterpret_cast<uint16_t*>(epi.out) + (size_t)row * epi.ldo + (col0 >> 1);
+#pragma unroll
+        for (int j = 0; j < 32; j += 2)
+          if (col0 + j < N) {
+            const float y = (f[j] / (1.0f + expf(-f[j]))) * f[j + 1];
+            o[j >> 1] = tc::cvt16(y, epi.f16);
+            if (epi.lo_off) o[epi.lo_off + (j >> 1)] = tc::cvt16(y - __bfloat162float(__float2bfloat16(y)), 0);
+          }
       } else {  // EPI_QKV
         const int t = row - bidx * epi.T;       // rows_per_batch == T
         if (col0 < epi.n_qk) {
@@ -270,13 +291,15 @@ hvx_status gemm_bf16(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* A, int
   HVX_CHECK((lda % 8) == 0 && (ldb % 8) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0, HVX_ERR_ARG,
             "gemm: operands must be 16-byte aligned with leading dims multiple of 8 (lda=%d ldb=%d)", lda, ldb);
   CUtensorMap ta, tb;
+  const uint64_t kB = ad.b_kb_mod ? (uint64_t)ad.b_kb_mod * BK : (uint64_t)K;      // width of the weight matrix
   HVX_CHECK(make_tmap_bf16_3d(&ta, A, ad.n_batch, ad.a_rows, ad.a_cols, lda, BM, BK), HVX_ERR_CUDA,
             "gemm: cuTensorMapEncodeTiled(A) failed");
-  if (N <= 64 || ad.a_col_per_ntile == 64) {
-    HVX_CHECK(make_tmap_bf16_2d(&tb, B, N, K, ldb, 64, BK), HVX_ERR_CUDA, "gemm: cuTensorMapEncodeTiled(B) failed");
+  const int ctas128 = cdiv(N, 128) * cdiv(ad.rows_per_batch, BM) * ad.n_batch;
+  if (N <= 64 || ad.a_col_per_ntile == 64 || ctas128 < 96) {
+    HVX_CHECK(make_tmap_bf16_2d(&tb, B, N, kB, ldb, 64, BK), HVX_ERR_CUDA, "gemm: cuTensorMapEncodeTiled(B) failed");
     return launch_gemm<64, 4>(e, st, ta, tb, M, N, K, epi, ad);
   }
-  HVX_CHECK(make_tmap_bf16_2d(&tb, B, N, K, ldb, 128, BK), HVX_ERR_CUDA, "gemm: cuTensorMapEncodeTiled(B) failed");
+  HVX_CHECK(make_tmap_bf16_2d(&tb, B, N, kB, ldb, 128, BK), HVX_ERR_CUDA, "gemm: cuTensorMapEncodeTiled(B) failed");
   return launch_gemm<128, 3>(e, st, ta, tb, M, N, K, epi, ad);
 }
 

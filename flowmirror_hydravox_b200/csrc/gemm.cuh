@@ -8,10 +8,11 @@
 #pragma once
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "llm_common.cuh"
 
 namespace hvx {
 
-enum { EPI_BF16 = 0, EPI_F32 = 1, EPI_RESID_GATE = 2, EPI_QKV = 3 };
+enum { EPI_BF16 = 0, EPI_F32 = 1, EPI_RESID_GATE = 2, EPI_QKV = 3, EPI_LLM_QKV = 4, EPI_SWIGLU = 5 };
 enum { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_SILU = 2, ACT_MISH = 3, ACT_LRELU = 4 /* slope 0.01 */ };
 
 struct GemmEpi {
@@ -34,6 +35,12 @@ struct GemmEpi {
   // EPI_F32 extras: out_f32 = act(acc+bias) (+ resid[row][col]); optional bf16 copy of the same value
   const float* resid = nullptr;
   __nv_bfloat16* out2 = nullptr;
+  // 16-bit outputs (EPI_BF16, EPI_SWIGLU, out2) written as hi at [col] and lo = x - hi at [lo_off + col] when lo_off > 0
+  int lo_off = 0;
+  int ldo2 = 0;                     // row stride of out2 (0 -> ldo)
+  // EPI_LLM_QKV (Qwen2 prefill / batched decode): RoPE + KV-cache write, see llm_common.cuh
+  LlmQkvEpi llm;
+  // EPI_SWIGLU: weight rows interleaved (gate_n, up_n); out16[row][n] = silu(acc[2n]) * acc[2n+1], ldo = N/2
 };
 
 // A-operand addressing.  A is viewed as [n_batch][a_rows][lda]; output tiles never straddle a batch and
@@ -53,6 +60,9 @@ struct GemmAddr {
   int a_col0 = 0, a_col_per_ntile = 0;
   int kb_per_tap = 0;
   int a_row0 = 0, a_row_step = 0;
+  // split-precision activations: A = [hi | lo] (two bf16 halves of an fp32 value, K' = 2K) against the same
+  // weights: k-block kb of A multiplies k-block kb % b_kb_mod of B (0 = off)
+  int b_kb_mod = 0;
 };
 
 hvx_status gemm_bf16(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb,

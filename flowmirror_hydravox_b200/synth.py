@@ -129,7 +129,10 @@ def flow_noise(d: FlowDims) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- LLM
-def llm_state_dict(d: LlmDims, seed: int = 0, dtype=torch.float32) -> Dict[str, torch.Tensor]:
+def llm_state_dict(d: LlmDims, seed: int = 0, dtype=torch.float32, eos_scale: float = 1.0) -> Dict[str, torch.Tensor]:
+    """eos_scale scales the llm_decoder rows of the stop range (ids >= speech_token_size).  Random weights put a stop
+    id on top of the nucleus every few dozen steps, which under the fixed-length protocol (min_len == max_len)
+    exhausts the reference's 100 EOS retries; bench.py and the long-run tests use eos_scale=0 (stop logits == 0)."""
     g = _gen(seed)
     sd: Dict[str, torch.Tensor] = {}
 
@@ -156,6 +159,8 @@ def llm_state_dict(d: LlmDims, seed: int = 0, dtype=torch.float32) -> Dict[str, 
     norm("llm.model.model.norm")
     sd["llm.model.lm_head.weight"] = sd["llm.model.model.embed_tokens.weight"]
     lin("llm_decoder", d.speech_vocab, d.hidden, gain=3.0)
+    if eos_scale != 1.0:
+        sd["llm_decoder.weight"][d.speech_token_size:] *= eos_scale
     mh = d.mtp_attn_heads * (d.hidden // d.mtp_attn_heads)
     for j in range(d.mtp_heads):
         p = f"mtp_block.{j}."

@@ -107,3 +107,49 @@ def pack_flow(sd: Dict[str, torch.Tensor], d: D.FlowDims) -> Dict[str, torch.Ten
     o["proj.w"] = sd[p + "proj_out.weight"].to(h).contiguous()
     o["proj.b"] = sd[p + "proj_out.bias"].to(f).contiguous()
     return o
+
+
+def _rope_pair_perm(n_heads: int, head_dim: int = 64) -> torch.Tensor:
+    """Row order that puts the HF half-split RoPE pair (d, d + head_dim/2) on adjacent rows (2i, 2i+1)."""
+    half = head_dim // 2
+    one = torch.tensor([i // 2 + half * (i % 2) for i in range(head_dim)])
+    return torch.cat([one + h * head_dim for h in range(n_heads)])
+
+
+def pack_llm(sd: Dict[str, torch.Tensor], d: D.LlmDims) -> Dict[str, torch.Tensor]:
+    """CosyVoice3LM state_dict (llm_multi_head_v3.py:622-689; HF Qwen2 names under llm.model.*) -> engine tensors.
+    bf16 weights (the reference serves the LLM with .to(bfloat16), infer_speech_model.py:102), fp32 norms/biases.
+    q/k rows are permuted per head for adjacent RoPE pairs, gate/up rows interleaved for fused SwiGLU, the MTP heads'
+    dead q/k projections are dropped and their tensors stacked over heads."""
+    b, f = torch.bfloat16, torch.float32
+    o: Dict[str, torch.Tensor] = {}
+    o["embed"] = sd["llm.model.model.embed_tokens.weight"].to(b).contiguous()
+    o["speech_emb"] = sd["speech_embedding.weight"].to(b).contiguous()
+    o["dec.w"] = sd["llm_decoder.weight"].to(b).contiguous()
+    o["norm"] = sd["llm.model.model.norm.weight"].to(f).contiguous()
+    pq, pk = _rope_pair_perm(d.q_heads, d.head_dim), _rope_pair_perm(d.kv_heads, d.head_dim)
+
+    def gu(p):
+        g, u = sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"]
+        return torch.stack([g, u], dim=1).reshape(2 * g.shape[0], g.shape[1]).to(b).contiguous()
+
+    for l in range(d.layers):
+        p = f"llm.model.model.layers.{l}."
+        o[f"L{l}.qkv.w"] = torch.cat([sd[p + "self_attn.q_proj.weight"][pq], sd[p + "self_attn.k_proj.weight"][pk],
+                                      sd[p + "self_attn.v_proj.weight"]], 0).to(b).contiguous()
+        o[f"L{l}.qkv.b"] = torch.cat([sd[p + "self_attn.q_proj.bias"][pq], sd[p + "self_attn.k_proj.bias"][pk],
+                                      sd[p + "self_attn.v_proj.bias"]], 0).to(f).contiguous()
+        o[f"L{l}.o.w"] = sd[p + "self_attn.o_proj.weight"].to(b).contiguous()
+        o[f"L{l}.gu.w"] = gu(p)
+        o[f"L{l}.down.w"] = sd[p + "mlp.down_proj.weight"].to(b).contiguous()
+        o[f"L{l}.ln1"] = sd[p + "input_layernorm.weight"].to(f).contiguous()
+        o[f"L{l}.ln2"] = sd[p + "post_attention_layernorm.weight"].to(f).contiguous()
+    hs = [f"mtp_block.{j}." for j in range(d.mtp_heads)]
+    o["mtp.v.w"] = torch.stack([sd[p + "self_attn.v_proj.weight"] for p in hs]).to(b).contiguous()
+    o["mtp.v.b"] = torch.stack([sd[p + "self_attn.v_proj.bias"] for p in hs]).to(f).contiguous()
+    o["mtp.o.w"] = torch.stack([sd[p + "self_attn.o_proj.weight"] for p in hs]).to(b).contiguous()
+    o["mtp.gu.w"] = torch.stack([gu(p) for p in hs]).contiguous()
+    o["mtp.down.w"] = torch.stack([sd[p + "mlp.down_proj.weight"] for p in hs]).to(b).contiguous()
+    o["mtp.ln1"] = torch.stack([sd[p + "input_layernorm.weight"] for p in hs]).to(f).contiguous()
+    o["mtp.ln2"] = torch.stack([sd[p + "post_attention_layernorm.weight"] for p in hs]).to(f).contiguous()
+    return o

@@ -49,15 +49,16 @@ typedef struct hvx_config {
   int llm_hidden, llm_layers, llm_q_heads, llm_kv_heads, llm_head_dim, llm_inter, llm_text_vocab;
   int llm_speech_vocab, llm_mtp_heads, llm_mtp_inter, llm_max_ctx, llm_max_seqs;
   float llm_rope_theta, llm_eps;
+  int llm_kv_f32;   /* 0: KV cache in bf16 (serving default); 1: fp32 (parity mode, tests) */
 } hvx_config;
 
 /* Sampler parameters bound per request by server/worker.py:57-65 (ras_sampling keywords,
  * cosyvoice/utils/common.py:138). */
 typedef struct hvx_sampler {
-  float top_p;
+  double top_p;   /* doubles: the reference compares fp32 tensors against Python floats (common.py:150,141) */
+  double tau_r;
   int top_k;
   int win_size;
-  float tau_r;
 } hvx_sampler;
 
 const char* hvx_last_error(void);

@@ -102,9 +102,12 @@ def rope_half(x, pos, theta):
 
 
 class LlmOracle:
-    def __init__(self, sd: Dict[str, torch.Tensor], dims):
+    def __init__(self, sd: Dict[str, torch.Tensor], dims, kv_dtype=None):
+        """kv_dtype=torch.bfloat16 rounds K (after RoPE) and V as they enter the cache, mirroring an engine that
+        keeps its KV cache in bf16 (the reference's own GPU path keeps every activation in bf16)."""
         self.sd = {k: v.float() for k, v in sd.items()}
         self.d = dims
+        self.kv_dtype = kv_dtype
         self.reset()
 
     def reset(self):
@@ -125,6 +128,8 @@ class LlmOracle:
             k = F.linear(a, sd[p + "self_attn.k_proj.weight"], sd[p + "self_attn.k_proj.bias"]).view(n, d.kv_heads, d.head_dim)
             v = F.linear(a, sd[p + "self_attn.v_proj.weight"], sd[p + "self_attn.v_proj.bias"]).view(n, d.kv_heads, d.head_dim)
             q, k = rope_half(q, pos, d.rope_theta), rope_half(k, pos, d.rope_theta)
+            if self.kv_dtype is not None:
+                k, v = k.to(self.kv_dtype).float(), v.to(self.kv_dtype).float()
             self.k[l] = k if self.k[l] is None else torch.cat([self.k[l], k], 0)
             self.v[l] = v if self.v[l] is None else torch.cat([self.v[l], v], 0)
             K, V = self.k[l], self.v[l]                                   # (ctx, kvh, 64)
@@ -169,10 +174,10 @@ class LlmOracle:
 
 @torch.no_grad()
 def inference(sd, dims, text, prompt_text, prompt_speech, u, head_k=1, sp=None,
-              min_ratio=2.0, max_ratio=20.0, return_logp=False):
+              min_ratio=2.0, max_ratio=20.0, return_logp=False, kv_dtype=None):
     """1-D int tensors in; returns list of emitted speech tokens (and per-step head log-probs)."""
     sp = sp or dict(top_p=0.8, top_k=25, win_size=10, tau_r=0.1)
-    m = LlmOracle(sd, dims)
+    m = LlmOracle(sd, dims, kv_dtype)
     head_k = max(1, min(int(head_k), dims.mtp_heads))          # llm_multi_head_v3.py:866-868
     us = u if isinstance(u, UStream) else UStream(u)
     x = m.prompt_embeds(text, prompt_text, prompt_speech)
