@@ -759,6 +759,8 @@ static hvx_status llm_bufs(hvx_engine* e, LlmState* L, DevBuf& buf, int rows, in
   b->m_o = (float*)(w + o_mo); b->logits = (float*)(w + o_log); b->part = (float*)(w + o_part); b->counters = (int*)(w + o_cnt);
   b->x16 = (__nv_bfloat16*)(w + o_x16); b->att16 = (__nv_bfloat16*)(w + o_att16); b->act16 = (__nv_bfloat16*)(w + o_act16);
   b->hn16 = (__nv_bfloat16*)(w + o_hn16); b->m16 = (__nv_bfloat16*)(w + o_m16);
+  // the split-attention arrival counters must start at zero; the carve-up moves with (rows, n_seq, head_k)
+  HVX_CUDA(cudaMemsetAsync(b->counters, 0, (size_t)rows * c.llm_kv_heads * 4, st));
   return HVX_OK;
 }
 
@@ -1085,8 +1087,3 @@ extern "C" hvx_status hvx_sample(hvx_engine* e, const float* logp, int n_heads, 
   return launch_sampler(e, (cudaStream_t)stream, sa, 1);
 }
 
-extern "C" hvx_status hvx_synthesize_host(hvx_engine*, const hvx_request*, int, int, const hvx_sampler*, int, const float*,
-                                          const float*, float*, int, int32_t*, int32_t*, int, int32_t*, float*, void*) {
-  set_error("hvx_synthesize_host: not built yet");
-  return HVX_ERR_UNSUPPORTED;
-}

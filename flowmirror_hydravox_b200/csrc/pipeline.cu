@@ -1,0 +1,163 @@
+// End-to-end entry with HOST buffers: token ids -> speech tokens -> mel -> waveform.
+// Replaces the three-stage body of inference_zero_shot / inference_tts
+// (server/model_utils/infer_speech_model.py:549-592, 631-670): llm.inference -> flow.inference ->
+// F.interpolate for `speed` -> hift.inference -> .cpu().  Host<->device copies are inside the call.
+#include "common.cuh"
+#include <algorithm>
+#include <vector>
+
+namespace hvx {
+
+// F.interpolate(mel, size=T_out, mode='linear') (align_corners=False), mel (C, T) channel-major
+// (infer_speech_model.py:584-587, 662-665)
+__global__ void speed_interp_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int T, int T_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * T_out) return;
+  const int c = i / T_out, t = i - c * T_out;
+  const float scale = (float)T / (float)T_out;
+  float src = ((float)t + 0.5f) * scale - 0.5f;
+  if (src < 0.f) src = 0.f;
+  const int i0 = min((int)src, T - 1);
+  const int i1 = min(i0 + 1, T - 1);
+  const float l1 = src - (float)i0, l0 = 1.0f - l1;
+  y[i] = l0 * x[(size_t)c * T + i0] + l1 * x[(size_t)c * T + i1];
+}
+
+struct PipeState {
+  DevBuf in, mid;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // start, llm end, flow start, flow end, utterance end
+};
+static PipeState* g_pipe = nullptr;      // one engine per process (server/worker.py:25-44)
+
+}  // namespace hvx
+
+using namespace hvx;
+
+extern "C" hvx_status hvx_speed_interp(hvx_engine* e, const float* mel_dev, int C, int T, int T_out, float* out_dev, void* stream) {
+  HVX_CHECK(e && mel_dev && out_dev && T >= 1 && T_out >= 1, HVX_ERR_ARG, "speed_interp: bad argument");
+  speed_interp_kernel<<<cdiv(C * T_out, 256), 256, 0, (cudaStream_t)stream>>>(mel_dev, out_dev, C, T, T_out);
+  HVX_LAUNCH_CHECK(e);
+  return HVX_OK;
+}
+
+extern "C" hvx_status hvx_synthesize_host(hvx_engine* e, const hvx_request* reqs, int n_req, int head_k, const hvx_sampler* sp,
+                                          int n_timesteps, const float* noise_dev, const float* sine_table_dev, float* wav_host,
+                                          int wav_stride, int32_t* wav_len_host, int32_t* tokens_host, int tok_stride,
+                                          int32_t* n_tokens_host, float* stage_ms_host, void* stream) {
+  HVX_CHECK(e && e->llm && e->flow && e->hift, HVX_ERR_STATE, "synthesize: all three stages must be finalized");
+  HVX_CHECK(reqs && sp && noise_dev && sine_table_dev && wav_host && wav_len_host, HVX_ERR_ARG, "synthesize: null argument");
+  HVX_CHECK(n_req >= 1 && n_req <= e->cfg.llm_max_seqs, HVX_ERR_ARG, "synthesize: n_req=%d exceeds max_seqs=%d", n_req, e->cfg.llm_max_seqs);
+  const hvx_config& c = e->cfg;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!g_pipe) {
+    g_pipe = new PipeState();
+    for (auto& ev : g_pipe->ev) HVX_CUDA(cudaEventCreate(&ev));
+  }
+  PipeState* P = g_pipe;
+  const int mel = c.flow_mel;
+  int frame = c.hift_hop;
+  for (int i = 0; i < c.hift_n_ups; i++) frame *= c.hift_ups[i];
+
+  // ---- stage inputs: one H2D copy per host array
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  struct Off { size_t text, ps, pf, emb, u, out; int max_out; };
+  std::vector<Off> of(n_req);
+  int max_out = 0, u_stride = 0;
+  for (int i = 0; i < n_req; i++) {
+    const hvx_request& r = reqs[i];
+    HVX_CHECK(r.text_ids_host && r.embedding_host && r.u_host && r.n_u > 0, HVX_ERR_ARG, "synthesize: request %d incomplete", i);
+    HVX_CHECK(r.n_prompt_speech == 0 || (r.prompt_speech_host && r.prompt_feat_host), HVX_ERR_ARG, "synthesize: request %d prompt incomplete", i);
+    of[i].max_out = (int)((float)r.n_text_new * r.max_ratio);
+    max_out = std::max(max_out, of[i].max_out);
+    u_stride = std::max(u_stride, r.n_u);
+  }
+  HVX_CHECK(tokens_host == nullptr || tok_stride >= max_out, HVX_ERR_ARG, "synthesize: tok_stride %d < max tokens %d", tok_stride, max_out);
+  max_out = std::max(max_out, 1);
+  for (int i = 0; i < n_req; i++) {
+    const hvx_request& r = reqs[i];
+    of[i].text = take(sizeof(int32_t) * std::max(1, r.n_text_total));
+    of[i].ps = take(sizeof(int32_t) * std::max(1, r.n_prompt_speech));
+    of[i].pf = take(sizeof(float) * std::max(1, 2 * r.n_prompt_speech * mel));
+    of[i].emb = take(sizeof(float) * c.flow_spk_in);
+  }
+  const size_t o_u = take(sizeof(float) * (size_t)n_req * u_stride);
+  const size_t o_tok = take(sizeof(int32_t) * (size_t)n_req * max_out), o_cnt = take(sizeof(int32_t) * n_req);
+  uint8_t* din = (uint8_t*)P->in.get(off);
+  HVX_CHECK(din, HVX_ERR_CUDA, "synthesize: input staging allocation failed");
+  HVX_CUDA(cudaEventRecord(P->ev[0], st));
+  for (int i = 0; i < n_req; i++) {
+    const hvx_request& r = reqs[i];
+    HVX_CUDA(cudaMemcpyAsync(din + of[i].text, r.text_ids_host, sizeof(int32_t) * r.n_text_total, cudaMemcpyHostToDevice, st));
+    if (r.n_prompt_speech) {
+      HVX_CUDA(cudaMemcpyAsync(din + of[i].ps, r.prompt_speech_host, sizeof(int32_t) * r.n_prompt_speech, cudaMemcpyHostToDevice, st));
+      HVX_CUDA(cudaMemcpyAsync(din + of[i].pf, r.prompt_feat_host, sizeof(float) * 2 * r.n_prompt_speech * mel, cudaMemcpyHostToDevice, st));
+    }
+    HVX_CUDA(cudaMemcpyAsync(din + of[i].emb, r.embedding_host, sizeof(float) * c.flow_spk_in, cudaMemcpyHostToDevice, st));
+    HVX_CUDA(cudaMemcpyAsync(din + o_u + sizeof(float) * (size_t)i * u_stride, r.u_host, sizeof(float) * r.n_u, cudaMemcpyHostToDevice, st));
+  }
+  // ---- stage 1: multi-head AR decode of all requests together
+  hvx_status rc;
+  for (int i = 0; i < n_req; i++) {
+    const hvx_request& r = reqs[i];
+    if ((rc = hvx_llm_begin(e, i, (const int32_t*)(din + of[i].text), r.n_text_total, r.n_text_new,
+                            r.n_prompt_speech ? (const int32_t*)(din + of[i].ps) : nullptr, r.n_prompt_speech, r.min_ratio, r.max_ratio)))
+      return rc;
+  }
+  int32_t* tok_dev = (int32_t*)(din + o_tok);
+  int32_t* cnt_dev = (int32_t*)(din + o_cnt);
+  if ((rc = hvx_llm_generate(e, n_req, head_k, sp, (const float*)(din + o_u), u_stride, tok_dev, max_out, cnt_dev, stream))) return rc;
+  std::vector<int32_t> cnt(n_req);
+  HVX_CUDA(cudaMemcpyAsync(cnt.data(), cnt_dev, sizeof(int32_t) * n_req, cudaMemcpyDeviceToHost, st));
+  if (tokens_host)
+    for (int i = 0; i < n_req; i++)
+      HVX_CUDA(cudaMemcpyAsync(tokens_host + (size_t)i * tok_stride, tok_dev + (size_t)i * max_out, sizeof(int32_t) * of[i].max_out,
+                               cudaMemcpyDeviceToHost, st));
+  HVX_CUDA(cudaEventRecord(P->ev[1], st));
+  HVX_CUDA(cudaStreamSynchronize(st));            // token counts size the next two stages
+  float ms_llm = 0.f, ms_flow = 0.f, ms_hift = 0.f;
+  cudaEventElapsedTime(&ms_llm, P->ev[0], P->ev[1]);
+  // ---- stages 2+3 per utterance (the reference's flow asserts batch 1, flow.py:387)
+  for (int i = 0; i < n_req; i++) {
+    const hvx_request& r = reqs[i];
+    const int n_tok = cnt[i];
+    if (n_tokens_host) n_tokens_host[i] = n_tok;
+    if (n_tok <= 0) { wav_len_host[i] = 0; continue; }
+    const int T = 2 * n_tok;
+    const int T_sp = (r.speed != 1.0f && r.speed > 0.f) ? (int)((float)T / r.speed) : T;       // int(tts_mel.shape[2] / speed)
+    HVX_CHECK(T_sp >= 1 && (size_t)T_sp * frame <= (size_t)wav_stride, HVX_ERR_ARG, "synthesize: wav_stride %d too small for %d samples",
+              wav_stride, T_sp * frame);
+    size_t m = 0;
+    auto take2 = [&](size_t bytes) { size_t o = m; m += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_all = take2(sizeof(int32_t) * (r.n_prompt_speech + n_tok)), o_mel = take2(sizeof(float) * mel * T);
+    const size_t o_mel2 = take2(sizeof(float) * mel * T_sp), o_wav = take2(sizeof(float) * (size_t)T_sp * frame);
+    uint8_t* dm = (uint8_t*)P->mid.get(m);
+    HVX_CHECK(dm, HVX_ERR_CUDA, "synthesize: intermediate allocation failed");
+    int32_t* all_tok = (int32_t*)(dm + o_all);
+    if (r.n_prompt_speech)
+      HVX_CUDA(cudaMemcpyAsync(all_tok, din + of[i].ps, sizeof(int32_t) * r.n_prompt_speech, cudaMemcpyDeviceToDevice, st));
+    HVX_CUDA(cudaMemcpyAsync(all_tok + r.n_prompt_speech, tok_dev + (size_t)i * max_out, sizeof(int32_t) * n_tok, cudaMemcpyDeviceToDevice, st));
+    HVX_CUDA(cudaEventRecord(P->ev[2], st));
+    float* mel_dev = (float*)(dm + o_mel);
+    if ((rc = hvx_flow_inference(e, all_tok, r.n_prompt_speech, n_tok, (const float*)(din + of[i].emb),
+                                 r.n_prompt_speech ? (const float*)(din + of[i].pf) : nullptr, noise_dev, n_timesteps, 0, 1, mel_dev, stream)))
+      return rc;
+    if (T_sp != T) {
+      if ((rc = hvx_speed_interp(e, mel_dev, mel, T, T_sp, (float*)(dm + o_mel2), stream))) return rc;
+      mel_dev = (float*)(dm + o_mel2);
+    }
+    HVX_CUDA(cudaEventRecord(P->ev[3], st));
+    float* wav_dev = (float*)(dm + o_wav);
+    if ((rc = hvx_hift_vocode(e, mel_dev, T_sp, 1, sine_table_dev, nullptr, nullptr, wav_dev, nullptr, stream))) return rc;
+    HVX_CUDA(cudaMemcpyAsync(wav_host + (size_t)i * wav_stride, wav_dev, sizeof(float) * (size_t)T_sp * frame, cudaMemcpyDeviceToHost, st));
+    HVX_CUDA(cudaEventRecord(P->ev[4], st));
+    HVX_CUDA(cudaStreamSynchronize(st));
+    wav_len_host[i] = T_sp * frame;
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, P->ev[2], P->ev[3]);
+    cudaEventElapsedTime(&b, P->ev[3], P->ev[4]);
+    ms_flow += a; ms_hift += b;
+  }
+  if (stage_ms_host) { stage_ms_host[0] = ms_llm; stage_ms_host[1] = ms_flow; stage_ms_host[2] = ms_hift; }
+  return HVX_OK;
+}

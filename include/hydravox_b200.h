@@ -142,6 +142,10 @@ hvx_status hvx_synthesize_host(hvx_engine* e, const hvx_request* reqs, int n_req
                                int32_t* wav_len_host, int32_t* tokens_host, int tok_stride,
                                int32_t* n_tokens_host, float* stage_ms_host, void* stream);
 
+/* speed control: replaces F.interpolate(tts_mel, size=int(T/speed), mode='linear')
+ * (infer_speech_model.py:584-587,662-665).  mel_dev (C, T) -> out_dev (C, T_out). */
+hvx_status hvx_speed_interp(hvx_engine* e, const float* mel_dev, int C, int T, int T_out, float* out_dev, void* stream);
+
 /* ---- diagnostic entries for the kernel-level parity tests (tests/test_gemm_gpu.py) ----
  * C = act(A*B^T + bias): A (M,K) bf16, B (N,K) bf16 (nn.Linear weight layout), C bf16 or fp32. */
 hvx_status hvx_gemm_bf16(hvx_engine* e, const void* A_dev, const void* B_dev, const float* bias_dev, void* C_dev,

@@ -22,10 +22,11 @@ def llms():
     out = {}
     sds = {}
     for name, ld, mc, ms, kv32 in (("tiny", D.LLM_TINY, 512, 4, False), ("tiny32", D.LLM_TINY, 512, 4, True),
+                                   ("tinyz", D.LLM_TINY, 512, 4, False),
                                    ("full", D.LLM_FULL, 2048, 2, False), ("full32", D.LLM_FULL, 2048, 2, True)):
         e = L.Engine(ld=ld, max_ctx=mc, max_seqs=ms, kv_f32=kv32)
         m = NativeLLM(e)
-        eos = 0.0 if name == "full" else 1.0        # "full" also runs the long fixed-length sample (see synth.llm_state_dict)
+        eos = 0.0 if name in ("full", "tinyz") else 1.0        # "full" also runs the long fixed-length sample (see synth.llm_state_dict)
         sd = sds.setdefault((ld, eos), synth.llm_state_dict(ld, 0, eos_scale=eos))
         m.load_state_dict(sd)
         out[name] = (e, m, ld, sd)
@@ -124,7 +125,7 @@ def test_generate_matches_oracle_tiny(llms, golden, name):
 
 def test_generate_batch_equals_single(llms):
     """Utterances are independent: a batch of 3 gives each request the tokens it gets alone (same u rows)."""
-    e, m, ld, sd = llms["tiny"]
+    e, m, ld, sd = llms["tinyz"]
     g = torch.Generator().manual_seed(3)
     reqs = [dict(text=torch.randint(0, ld.text_vocab, (n,), generator=g), prompt_text=torch.randint(0, ld.text_vocab, (3,), generator=g),
                  prompt_speech=torch.randint(0, ld.speech_token_size, (p,), generator=g)) for n, p in ((5, 0), (9, 4), (7, 11))]
