@@ -61,28 +61,55 @@ struct GemvArgs {
   const float* resid = nullptr; int ldr = 0;        // out = resid + y (resid may alias out)
   int N = 0, K = 0, mode = GEMV_PLAIN;
   int rows = 0;                                     // live rows (<= R); rows beyond are not written
+  int kc = 0;                                       // activation chunk staged in shared memory (floats per row)
   // blockIdx.y batches independent problems (the MTP heads): element strides
   size_t sW = 0, sBias = 0, sNorm = 0, sX = 0, sOut = 0, sResid = 0;
   LlmQkvEpi qkv;
 };
 
 // Each warp produces output features (2p, 2p+1) for all R rows: a RoPE pair (GEMV_QKV), a (gate, up)
-// pair (GEMV_SWIGLU) or two plain features.
+// pair (GEMV_SWIGLU) or two plain features.  The grid is persistent (a few CTAs per SM, warps stride
+// over the pairs) so the activation staging is paid once per CTA.  Launched with programmatic dependent
+// launch: the first weight rows are requested *before* griddepcontrol.wait, i.e. while the producer of
+// x is still draining, so the HBM latency of the weight stream overlaps the previous kernel's tail.
+__device__ __forceinline__ void gemv_fma8(float& acc, const uint4 u, const float* xs) {
+  const float4 xa = *reinterpret_cast<const float4*>(xs);
+  const float4 xb = *reinterpret_cast<const float4*>(xs + 4);
+  acc = fmaf(bf_lo(u.x), xa.x, acc); acc = fmaf(bf_hi(u.x), xa.y, acc);
+  acc = fmaf(bf_lo(u.y), xa.z, acc); acc = fmaf(bf_hi(u.y), xa.w, acc);
+  acc = fmaf(bf_lo(u.z), xb.x, acc); acc = fmaf(bf_hi(u.z), xb.y, acc);
+  acc = fmaf(bf_lo(u.w), xb.z, acc); acc = fmaf(bf_hi(u.w), xb.w, acc);
+}
+
 template <int R>
 __global__ void __launch_bounds__(256) llm_gemv_kernel(GemvArgs a) {
   extern __shared__ float sx[];                     // [R][kc]
   __shared__ float s_scale[8];
+  asm volatile("griddepcontrol.launch_dependents;");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
   const int by = blockIdx.y;
   const float* x = a.x + by * a.sX;
   const __nv_bfloat16* W = a.W + by * a.sW;
-  const int K = a.K;
-  const int kc = K < GEMV_KC ? K : GEMV_KC;
-  const int pair = blockIdx.x * nwarp + warp;
-  const int n0 = 2 * pair;
-  const bool active = n0 < a.N;
-  const __nv_bfloat16* w0 = W + (size_t)n0 * K;
-  const __nv_bfloat16* w1 = w0 + ((n0 + 1 < a.N) ? K : 0);
+  const int K = a.K, kc = a.kc;
+  const int npairs = (a.N + 1) >> 1;
+  const int first = blockIdx.x * nwarp + warp, stride = gridDim.x * nwarp;
+  const bool multi = K > kc;                        // host guarantees <= 1 pair per warp in that case
+
+  // ---- independent of the previous kernel: request the first weight rows of this warp
+  uint4 p0[4], p1[4];
+  {
+    const int n0 = 2 * first;
+    const __nv_bfloat16* w0 = W + (size_t)n0 * K;
+    const __nv_bfloat16* w1 = w0 + ((n0 + 1 < a.N) ? K : 0);
+    const int kn = K < kc ? K : kc;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int k = lane * 8 + i * 256;
+      if (first < npairs && k < kn) { p0[i] = ldg_stream(w0 + k); p1[i] = ldg_stream(w1 + k); }
+      else { p0[i] = make_uint4(0, 0, 0, 0); p1[i] = make_uint4(0, 0, 0, 0); }
+    }
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (a.norm_w) {                                   // fused RMSNorm (HF Qwen2RMSNorm: fp32, eps inside rsqrt)
     for (int r = warp; r < R; r += nwarp) {
@@ -93,9 +120,10 @@ __global__ void __launch_bounds__(256) llm_gemv_kernel(GemvArgs a) {
     }
     __syncthreads();
   }
+  const float* bias = a.bias ? a.bias + by * a.sBias : nullptr;
+  float* out = a.out + by * a.sOut;
+  const float* resid = a.resid ? a.resid + by * a.sResid : nullptr;
   float acc0[R], acc1[R];
-#pragma unroll
-  for (int r = 0; r < R; r++) { acc0[r] = 0.f; acc1[r] = 0.f; }
 
   for (int kb = 0; kb < K; kb += kc) {
     const int kn = (K - kb) < kc ? (K - kb) : kc;
@@ -108,57 +136,64 @@ __global__ void __launch_bounds__(256) llm_gemv_kernel(GemvArgs a) {
       sx[r * kc + k] = v;
     }
     __syncthreads();
-    if (active) {
-#pragma unroll 2
-      for (int k = lane * 8; k < kn; k += 256) {
-        const uint4 u0 = ldg_stream(w0 + kb + k);
-        const uint4 u1 = ldg_stream(w1 + kb + k);
-        const float a0[8] = {bf_lo(u0.x), bf_hi(u0.x), bf_lo(u0.y), bf_hi(u0.y), bf_lo(u0.z), bf_hi(u0.z), bf_lo(u0.w), bf_hi(u0.w)};
-        const float a1[8] = {bf_lo(u1.x), bf_hi(u1.x), bf_lo(u1.y), bf_hi(u1.y), bf_lo(u1.z), bf_hi(u1.z), bf_lo(u1.w), bf_hi(u1.w)};
+    for (int pair = first; pair < npairs; pair += stride) {
+      const int n0 = 2 * pair;
+      const __nv_bfloat16* w0 = W + (size_t)n0 * K + kb;
+      const __nv_bfloat16* w1 = w0 + ((n0 + 1 < a.N) ? K : 0);
+      if (!multi || kb == 0) {
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-          const float4 xa = *reinterpret_cast<const float4*>(&sx[r * kc + k]);
-          const float4 xb = *reinterpret_cast<const float4*>(&sx[r * kc + k + 4]);
-          acc0[r] = fmaf(a0[0], xa.x, acc0[r]); acc0[r] = fmaf(a0[1], xa.y, acc0[r]);
-          acc0[r] = fmaf(a0[2], xa.z, acc0[r]); acc0[r] = fmaf(a0[3], xa.w, acc0[r]);
-          acc0[r] = fmaf(a0[4], xb.x, acc0[r]); acc0[r] = fmaf(a0[5], xb.y, acc0[r]);
-          acc0[r] = fmaf(a0[6], xb.z, acc0[r]); acc0[r] = fmaf(a0[7], xb.w, acc0[r]);
-          acc1[r] = fmaf(a1[0], xa.x, acc1[r]); acc1[r] = fmaf(a1[1], xa.y, acc1[r]);
-          acc1[r] = fmaf(a1[2], xa.z, acc1[r]); acc1[r] = fmaf(a1[3], xa.w, acc1[r]);
-          acc1[r] = fmaf(a1[4], xb.x, acc1[r]); acc1[r] = fmaf(a1[5], xb.y, acc1[r]);
-          acc1[r] = fmaf(a1[6], xb.z, acc1[r]); acc1[r] = fmaf(a1[7], xb.w, acc1[r]);
+        for (int r = 0; r < R; r++) { acc0[r] = 0.f; acc1[r] = 0.f; }
+      }
+      const bool pre = (pair == first) && kb == 0;
+      for (int k0 = lane * 8; k0 < kn; k0 += 1024) {
+        uint4 u0[4], u1[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int k = k0 + i * 256;
+          if (pre && k0 == lane * 8) { u0[i] = p0[i]; u1[i] = p1[i]; }
+          else if (k < kn) { u0[i] = ldg_stream(w0 + k); u1[i] = ldg_stream(w1 + k); }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int k = k0 + i * 256;
+          if (k < kn) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+              gemv_fma8(acc0[r], u0[i], &sx[r * kc + k]);
+              gemv_fma8(acc1[r], u1[i], &sx[r * kc + k]);
+            }
+          }
         }
       }
-    }
-  }
-  if (!active) return;
+      if (multi && kb + kc < K) continue;
 #pragma unroll
-  for (int r = 0; r < R; r++) {
+      for (int r = 0; r < R; r++) {
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      acc0[r] += __shfl_xor_sync(0xffffffffu, acc0[r], o);
-      acc1[r] += __shfl_xor_sync(0xffffffffu, acc1[r], o);
-    }
-  }
-  if (lane != 0) return;
-  const float* bias = a.bias ? a.bias + by * a.sBias : nullptr;
-  const float b0 = bias ? bias[n0] : 0.f;
-  const float b1 = (bias && n0 + 1 < a.N) ? bias[n0 + 1] : 0.f;
-  float* out = a.out + by * a.sOut;
-  const float* resid = a.resid ? a.resid + by * a.sResid : nullptr;
+        for (int o = 16; o; o >>= 1) {
+          acc0[r] += __shfl_xor_sync(0xffffffffu, acc0[r], o);
+          acc1[r] += __shfl_xor_sync(0xffffffffu, acc1[r], o);
+        }
+      }
+      if (lane == 0) {
+        const float b0 = bias ? bias[n0] : 0.f;
+        const float b1 = (bias && n0 + 1 < a.N) ? bias[n0 + 1] : 0.f;
 #pragma unroll
-  for (int r = 0; r < R; r++) {
-    if (r >= a.rows) break;
-    const float y0 = acc0[r] + b0, y1 = acc1[r] + b1;
-    if (a.mode == GEMV_QKV) {
-      llm_qkv_store(a.qkv, r, n0, y0, y1);
-    } else if (a.mode == GEMV_SWIGLU) {
-      out[(size_t)r * a.ldo + pair] = (y0 / (1.0f + expf(-y0))) * y1;
-    } else {
-      float o0 = y0, o1 = y1;
-      if (resid) { o0 += resid[(size_t)r * a.ldr + n0]; if (n0 + 1 < a.N) o1 += resid[(size_t)r * a.ldr + n0 + 1]; }
-      out[(size_t)r * a.ldo + n0] = o0;
-      if (n0 + 1 < a.N) out[(size_t)r * a.ldo + n0 + 1] = o1;
+        for (int r = 0; r < R; r++) {
+          if (r < a.rows) {
+            const float y0 = acc0[r] + b0, y1 = acc1[r] + b1;
+            if (a.mode == GEMV_QKV) {
+              llm_qkv_store(a.qkv, r, n0, y0, y1);
+            } else if (a.mode == GEMV_SWIGLU) {
+              out[(size_t)r * a.ldo + pair] = (y0 / (1.0f + expf(-y0))) * y1;
+            } else {
+              float o0 = y0, o1 = y1;
+              if (resid) { o0 += resid[(size_t)r * a.ldr + n0]; if (n0 + 1 < a.N) o1 += resid[(size_t)r * a.ldr + n0 + 1]; }
+              out[(size_t)r * a.ldo + n0] = o0;
+              if (n0 + 1 < a.N) out[(size_t)r * a.ldo + n0 + 1] = o1;
+            }
+          }
+        }
+      }
     }
   }
 }
@@ -632,7 +667,7 @@ hvx_status llm_finalize(hvx_engine* e) {
   const int64_t H = c.llm_hidden, QD = (int64_t)c.llm_q_heads * c.llm_head_dim, KD = (int64_t)c.llm_kv_heads * c.llm_head_dim;
   HVX_CHECK(c.llm_head_dim == 64, HVX_ERR_UNSUPPORTED, "llm: head_dim must be 64");
   HVX_CHECK(QD == H, HVX_ERR_UNSUPPORTED, "llm: q_heads*head_dim must equal hidden");
-  HVX_CHECK(H % 64 == 0 && H <= GEMV_KC && c.llm_inter % 64 == 0 && c.llm_mtp_inter % 64 == 0, HVX_ERR_UNSUPPORTED, "llm: unsupported dims");
+  HVX_CHECK(H % 64 == 0 && H <= 2048 && c.llm_inter % 64 == 0 && c.llm_mtp_inter % 64 == 0, HVX_ERR_UNSUPPORTED, "llm: unsupported dims");
   HVX_CHECK(c.llm_q_heads % c.llm_kv_heads == 0 && c.llm_q_heads / c.llm_kv_heads <= 8, HVX_ERR_UNSUPPORTED, "llm: GQA group > 8");
   HVX_CHECK(c.llm_layers <= 64 && c.llm_mtp_heads <= LLM_MAX_HEADS, HVX_ERR_UNSUPPORTED, "llm: too many layers/heads");
   HVX_CHECK(c.llm_max_seqs >= 1 && c.llm_max_ctx >= 16, HVX_ERR_ARG, "llm: bad max_seqs/max_ctx");
@@ -705,20 +740,38 @@ void llm_free(hvx_engine* e) {
 static hvx_status launch_gemv(hvx_engine* e, cudaStream_t st, GemvArgs a, int R, int n_batch = 1) {
   a.rows = R;
   const int pairs = (a.N + 1) / 2;
-  // enough CTAs to cover the machine: fewer warps per CTA for small N
-  int warps = 8;
-  while (warps > 2 && cdiv(pairs, warps) * n_batch < 2 * e->sm_count) warps >>= 1;
-  const int kc = a.K < GEMV_KC ? a.K : GEMV_KC;
-  HVX_CHECK(!a.norm_w || a.K <= GEMV_KC, HVX_ERR_UNSUPPORTED, "gemv: fused norm needs K <= %d", GEMV_KC);
+  const int Rt = R <= 1 ? 1 : R <= 2 ? 2 : R <= 4 ? 4 : 8;
   HVX_CHECK(a.K % 8 == 0, HVX_ERR_UNSUPPORTED, "gemv: K must be a multiple of 8");
-  int Rt = R <= 1 ? 1 : R <= 2 ? 2 : R <= 4 ? 4 : 8;
-  const size_t smem = (size_t)Rt * kc * sizeof(float);
-  dim3 grid(cdiv(pairs, warps), n_batch);
+  // activation staging: the whole row when it fits ~96 KB, else chunks (then every warp owns at most one pair)
+  const int kc_max = (96 * 1024 / 4 / Rt) & ~7;
+  a.kc = a.K <= kc_max ? a.K : kc_max;
+  HVX_CHECK(!a.norm_w || a.K <= a.kc, HVX_ERR_UNSUPPORTED, "gemv: fused norm needs the whole row staged (K=%d)", a.K);
+  const size_t smem = (size_t)Rt * a.kc * sizeof(float);
+  int warps = 8;
+  int ctas;
+  if (a.K > a.kc) {
+    ctas = cdiv(pairs, warps);
+  } else {
+    // persistent: about two waves of CTAs over the machine, fewer warps per CTA when there is little work
+    while (warps > 2 && cdiv(pairs, warps) * n_batch < e->sm_count) warps >>= 1;
+    ctas = std::min(cdiv(pairs, warps), std::max(1, 2 * e->sm_count / n_batch));
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(ctas, n_batch, 1);
+  cfg.blockDim = dim3(warps * 32, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
   static bool attr[4] = {false, false, false, false};
 #define GEMV_CASE(RR, idx)                                                                                        \
   case RR:                                                                                                        \
-    if (!attr[idx]) { HVX_CUDA(cudaFuncSetAttribute(llm_gemv_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, RR * GEMV_KC * 4)); attr[idx] = true; } \
-    llm_gemv_kernel<RR><<<grid, warps * 32, smem, st>>>(a);                                                       \
+    if (!attr[idx]) { HVX_CUDA(cudaFuncSetAttribute(llm_gemv_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr[idx] = true; } \
+    HVX_CUDA(cudaLaunchKernelEx(&cfg, llm_gemv_kernel<RR>, a));                                                   \
     break;
   switch (Rt) {
     GEMV_CASE(1, 0)
