@@ -3,6 +3,8 @@
 #include "gemm.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <algorithm>
+#include <cstdlib>
 
 namespace hvx {
 
@@ -73,86 +75,8 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   return v;
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N, int K,
-                 GemmEpi epi, GemmAddr ad, int tiles_per_batch) {
-  using S = GemmSmem<BN, STAGES>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int batch = blockIdx.y / tiles_per_batch;
-  const int m0 = (blockIdx.y - batch * tiles_per_batch) * BM;      // row inside the batch
-  const int nkb = (K + BK - 1) / BK;
-
-  if (warp == 0 && lane == 0) {
-    tc::tma_prefetch_desc(&tma_a);
-    tc::tma_prefetch_desc(&tma_b);
-    for (int s = 0; s < STAGES; s++) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    tc::mbar_init(tmem_full, 1);
-    tc::fence_barrier_init();
-  }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, BN);
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      for (int kb = 0; kb < nkb; kb++) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        tc::mbar_wait(&empty_bar[s], ph ^ 1);
-        tc::mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
-        uint8_t* sa = smem + s * S::STAGE_BYTES;
-        const int tap = ad.kb_per_tap ? kb / ad.kb_per_tap : 0;
-        const int kin = ad.kb_per_tap ? kb - tap * ad.kb_per_tap : kb;
-        tc::tma_load_3d(sa, &tma_a, &full_bar[s], ad.a_col0 + blockIdx.x * ad.a_col_per_ntile + kin * BK,
-                        m0 + ad.a_row0 + tap * ad.a_row_step, batch);
-        tc::tma_load_2d(sa + S::A_BYTES, &tma_b, &full_bar[s], (ad.b_kb_mod ? kb % ad.b_kb_mod : kb) * BK, n0);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = epi.f16 ? tc::umma_idesc_f16(BM, BN) : tc::umma_idesc_bf16(BM, BN);
-      for (int kb = 0; kb < nkb; kb++) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        tc::mbar_wait(&full_bar[s], ph);
-        tc::tc_fence_after();
-        const uint32_t sa = tc::smem_u32(smem + s * S::STAGE_BYTES);
-        const uint64_t adesc = tc::umma_desc_k128(sa);
-        const uint64_t bdesc = tc::umma_desc_k128(sa + S::A_BYTES);
-#pragma unroll
-        for (int k = 0; k < BK / 16; k++)
-          tc::umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
-        tc::umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs retire
-      }
-      tc::umma_commit(tmem_full);                // accumulator complete
-    }
-  } else {
-    // ---------------- epilogue: warp q owns TMEM lanes [32q, 32q+32) = tile rows
-    const int q = warp & 3;
-    const int row_b = m0 + q * 32 + lane;
-    const int row = batch * ad.rows_per_batch + row_b;
-    tc::mbar_wait(tmem_full, 0);
-    tc::tc_fence_after();
-    const bool row_ok = row_b < ad.rows_per_batch && row < M;
-    const int bidx = row / epi.rows_per_batch;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      tc::tmem_ld_wait();
-      const int col0 = n0 + c0;
-      if (!row_ok || col0 >= N) continue;
+// fused epilogue of one 32-column chunk of one output row: v = raw fp32 accumulators of columns [col0, col0+32)
+__device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx, int col0, int N, const uint32_t* v) {
       float f[32];
 #pragma unroll
       for (int j = 0; j < 32; j++) {
@@ -257,11 +181,225 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           for (int j = 0; j < 32; j++) reinterpret_cast<uint16_t*>(o)[(size_t)j * epi.vt_ld] = tc::cvt16(f[j], epi.f16);
         }
       }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N, int K,
+                 GemmEpi epi, GemmAddr ad, int tiles_per_batch) {
+  using S = GemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int batch = blockIdx.y / tiles_per_batch;
+  const int m0 = (blockIdx.y - batch * tiles_per_batch) * BM;      // row inside the batch
+  const int nkb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tma_a);
+    tc::tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < STAGES; s++) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    tc::mbar_init(tmem_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, BN);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; kb++) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        tc::mbar_wait(&empty_bar[s], ph ^ 1);
+        tc::mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+        uint8_t* sa = smem + s * S::STAGE_BYTES;
+        const int tap = ad.kb_per_tap ? kb / ad.kb_per_tap : 0;
+        const int kin = ad.kb_per_tap ? kb - tap * ad.kb_per_tap : kb;
+        tc::tma_load_3d(sa, &tma_a, &full_bar[s], ad.a_col0 + blockIdx.x * ad.a_col_per_ntile + kin * BK,
+                        m0 + ad.a_row0 + tap * ad.a_row_step, batch);
+        tc::tma_load_2d(sa + S::A_BYTES, &tma_b, &full_bar[s], (ad.b_kb_mod ? kb % ad.b_kb_mod : kb) * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = epi.f16 ? tc::umma_idesc_f16(BM, BN) : tc::umma_idesc_bf16(BM, BN);
+      for (int kb = 0; kb < nkb; kb++) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        tc::mbar_wait(&full_bar[s], ph);
+        tc::tc_fence_after();
+        const uint32_t sa = tc::smem_u32(smem + s * S::STAGE_BYTES);
+        const uint64_t adesc = tc::umma_desc_k128(sa);
+        const uint64_t bdesc = tc::umma_desc_k128(sa + S::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; k++)
+          tc::umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+        tc::umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs retire
+      }
+      tc::umma_commit(tmem_full);                // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: warp q owns TMEM lanes [32q, 32q+32) = tile rows
+    const int q = warp & 3;
+    const int row_b = m0 + q * 32 + lane;
+    const int row = batch * ad.rows_per_batch + row_b;
+    tc::mbar_wait(tmem_full, 0);
+    tc::tc_fence_after();
+    const bool row_ok = row_b < ad.rows_per_batch && row < M;
+    const int bidx = row / epi.rows_per_batch;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tc::tmem_ld_wait();
+      const int col0 = n0 + c0;
+      if (!row_ok || col0 >= N) continue;
+      epi_store(epi, row, bidx, col0, N, v);
     }
   }
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) { __syncwarp(); tc::tmem_dealloc(tmem_base, BN); }
+}
+
+// ------------------------------------------------------------------ persistent variant for the big flow GEMMs
+// One CTA per SM walks the output tiles (128 x PBN).  The accumulator is double-buffered in TMEM
+// (2 x PBN fp32 columns = all 512 columns), so the epilogue of tile i (tcgen05.ld -> fused math -> global) runs
+// while the tensor core already accumulates tile i+1; operands stream through a 4-stage TMA ring.
+// 128 x 256 tiles read 96 B/cycle of operands from shared memory (A 4 KB + B 8 KB per 128-cycle MMA), under
+// the 128 B/cycle port limit that caps 128 x 128 tiles.
+constexpr int PBN = 256;
+constexpr int PSTAGES = 4;
+struct PersistSmem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = PBN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = PSTAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N, int K,
+                    GemmEpi epi, GemmAddr ad, int tiles_m, int tiles_n) {
+  using S = PersistSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+  uint64_t* empty_bar = full_bar + PSTAGES;
+  uint64_t* tmem_full = empty_bar + PSTAGES;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (K + BK - 1) / BK;
+  const int n_tiles = tiles_m * tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tma_a);
+    tc::tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < PSTAGES; s++) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; s++) { tc::mbar_init(&tmem_full[s], 1); tc::mbar_init(&tmem_empty[s], 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 2 * PBN);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;                                  // running k-block counter across tiles
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int mt = tile / tiles_n, nt = tile - mt * tiles_n;
+        for (int kb = 0; kb < nkb; kb++, it++) {
+          const int s = it % PSTAGES;
+          const uint32_t ph = (it / PSTAGES) & 1;
+          tc::mbar_wait(&empty_bar[s], ph ^ 1);
+          tc::mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+          uint8_t* sa = smem + s * S::STAGE_BYTES;
+          tc::tma_load_3d(sa, &tma_a, &full_bar[s], kb * BK, mt * BM, 0);
+          tc::tma_load_2d(sa + S::A_BYTES, &tma_b, &full_bar[s], kb * BK, nt * PBN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = epi.f16 ? tc::umma_idesc_f16(BM, PBN) : tc::umma_idesc_bf16(BM, PBN);
+      int it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t++) {
+        const int as = t & 1;
+        tc::mbar_wait(&tmem_empty[as], ((t >> 1) & 1) ^ 1);      // epilogue drained this accumulator
+        tc::tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(as * PBN);
+        for (int kb = 0; kb < nkb; kb++, it++) {
+          const int s = it % PSTAGES;
+          const uint32_t ph = (it / PSTAGES) & 1;
+          tc::mbar_wait(&full_bar[s], ph);
+          tc::tc_fence_after();
+          const uint32_t sa = tc::smem_u32(smem + s * S::STAGE_BYTES);
+          const uint64_t adesc = tc::umma_desc_k128(sa);
+          const uint64_t bdesc = tc::umma_desc_k128(sa + S::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; k++)
+            tc::umma_f16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          tc::umma_commit(&empty_bar[s]);
+        }
+        tc::umma_commit(&tmem_full[as]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int t = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t++) {
+      const int mt = tile / tiles_n, nt = tile - mt * tiles_n;
+      const int as = t & 1;
+      const int row = mt * BM + q * 32 + lane;
+      const bool row_ok = row < M;
+      const int bidx = row / epi.rows_per_batch;
+      tc::mbar_wait(&tmem_full[as], (t >> 1) & 1);
+      tc::tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < PBN; c0 += 32) {
+        uint32_t v[32];
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * PBN + c0), v);
+        tc::tmem_ld_wait();
+        const int col0 = nt * PBN + c0;
+        if (!row_ok || col0 >= N) continue;
+        epi_store(epi, row, bidx, col0, N, v);
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tmem_empty[as]);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tc::tmem_dealloc(tmem_base, 2 * PBN); }
+}
+
+static hvx_status launch_gemm_persist(hvx_engine* e, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
+                                      int K, const GemmEpi& epi, const GemmAddr& ad) {
+  using S = PersistSmem;
+  static bool attr_set = false;
+  if (!attr_set) {
+    HVX_CUDA(cudaFuncSetAttribute(gemm_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr_set = true;
+  }
+  const int tiles_m = cdiv(M, BM), tiles_n = cdiv(N, PBN);
+  const int grid = std::min(tiles_m * tiles_n, e->sm_count);
+  gemm_persist_kernel<<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, M, N, K, epi, ad, tiles_m, tiles_n);
+  HVX_LAUNCH_CHECK(e);
+  return HVX_OK;
 }
 
 template <int BN, int STAGES>
@@ -294,6 +432,12 @@ hvx_status gemm_bf16(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* A, int
   const uint64_t kB = ad.b_kb_mod ? (uint64_t)ad.b_kb_mod * BK : (uint64_t)K;      // width of the weight matrix
   HVX_CHECK(make_tmap_bf16_3d(&ta, A, ad.n_batch, ad.a_rows, ad.a_cols, lda, BM, BK), HVX_ERR_CUDA,
             "gemm: cuTensorMapEncodeTiled(A) failed");
+  // big plain GEMMs (the DiT linears): persistent 128 x 256 tiles
+  if (ad.n_batch == 1 && ad.kb_per_tap == 0 && ad.b_kb_mod == 0 && ad.a_col0 == 0 && ad.a_col_per_ntile == 0 && ad.a_row0 == 0 &&
+      N % PBN == 0 && cdiv(M, BM) * (N / PBN) >= e->sm_count / 2 && !getenv("HVX_NO_PERSIST")) {
+    HVX_CHECK(make_tmap_bf16_2d(&tb, B, N, kB, ldb, PBN, BK), HVX_ERR_CUDA, "gemm: cuTensorMapEncodeTiled(B) failed");
+    return launch_gemm_persist(e, st, ta, tb, M, N, K, epi, ad);
+  }
   const int ctas128 = cdiv(N, 128) * cdiv(ad.rows_per_batch, BM) * ad.n_batch;
   if (N <= 64 || ad.a_col_per_ntile == 64 || ctas128 < 96) {
     HVX_CHECK(make_tmap_bf16_2d(&tb, B, N, kB, ldb, 64, BK), HVX_ERR_CUDA, "gemm: cuTensorMapEncodeTiled(B) failed");

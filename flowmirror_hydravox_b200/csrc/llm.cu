@@ -40,6 +40,11 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
+// 1-D bulk copy global -> shared (TMA engine, no tensor map): bytes % 16 == 0, both addresses 16 B aligned
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 // fp32 value as two bf16 halves: row[k] = hi, row[off_lo + k] = x - hi
@@ -109,31 +114,44 @@ __global__ void __launch_bounds__(256) llm_gemv_kernel(GemvArgs a) {
       else { p0[i] = make_uint4(0, 0, 0, 0); p1[i] = make_uint4(0, 0, 0, 0); }
     }
   }
+  __shared__ __align__(8) uint64_t s_bar;
+  if (tid == 0) { tc::mbar_init(&s_bar, 1); tc::fence_barrier_init(); }
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  __syncthreads();
 
-  if (a.norm_w) {                                   // fused RMSNorm (HF Qwen2RMSNorm: fp32, eps inside rsqrt)
-    for (int r = warp; r < R; r += nwarp) {
-      float ss = 0.f;
-      if (r < a.rows) for (int k = lane; k < K; k += 32) { const float v = x[(size_t)r * a.ldx + k]; ss += v * v; }
-      for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      if (lane == 0) s_scale[r] = rsqrtf(ss / (float)K + a.eps);
-    }
-    __syncthreads();
-  }
   const float* bias = a.bias ? a.bias + by * a.sBias : nullptr;
   float* out = a.out + by * a.sOut;
   const float* resid = a.resid ? a.resid + by * a.sResid : nullptr;
+  const float* nw = a.norm_w ? a.norm_w + by * a.sNorm : nullptr;
   float acc0[R], acc1[R];
+  uint32_t bar_phase = 0;
 
   for (int kb = 0; kb < K; kb += kc) {
     const int kn = (K - kb) < kc ? (K - kb) : kc;
     if (kb) __syncthreads();
-    const float* nw = a.norm_w ? a.norm_w + by * a.sNorm : nullptr;
-    for (int i = tid; i < R * kn; i += blockDim.x) {
-      const int r = i / kn, k = i - r * kn;
-      float v = r < a.rows ? x[(size_t)r * a.ldx + kb + k] : 0.f;
-      if (nw) v = nw[kb + k] * (v * s_scale[r]);
-      sx[r * kc + k] = v;
+    // activation rows -> shared memory through the bulk-copy engine: one L2 round trip for the whole chunk
+    if (tid == 0) {
+      tc::mbar_expect_tx(&s_bar, (uint32_t)(a.rows * kn * 4));
+      for (int r = 0; r < a.rows; r++) bulk_g2s(&sx[r * kc], x + (size_t)r * a.ldx + kb, (uint32_t)(kn * 4), &s_bar);
+    }
+    for (int i = tid; i < (R - a.rows) * kn; i += blockDim.x) sx[a.rows * kc + (i / kn) * kc + (i % kn)] = 0.f;   // padding rows
+    tc::mbar_wait(&s_bar, bar_phase);
+    bar_phase ^= 1;
+    if (nw) {                                       // fused RMSNorm (HF Qwen2RMSNorm: fp32, eps inside rsqrt); K == kn here
+      for (int r = warp; r < a.rows; r += nwarp) {
+        float ss = 0.f;
+        for (int k = lane * 4; k < kn; k += 128) {
+          const float4 v = *reinterpret_cast<const float4*>(&sx[r * kc + k]);
+          ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+        for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0) s_scale[r] = rsqrtf(ss / (float)K + a.eps);
+      }
+      __syncthreads();
+      for (int i = tid; i < a.rows * kn; i += blockDim.x) {
+        const int r = i / kn, k = i - r * kn;
+        sx[r * kc + k] = nw[k] * (sx[r * kc + k] * s_scale[r]);
+      }
     }
     __syncthreads();
     for (int pair = first; pair < npairs; pair += stride) {

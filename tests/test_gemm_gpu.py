@@ -16,21 +16,23 @@ def eng():
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 256), (300, 1024, 1024), (4596, 3072, 1024),
-                                   (25, 2048, 1024), (517, 80, 1024), (1000, 1024, 2048), (64, 6144, 320)])
-@pytest.mark.parametrize("out_f32,act", [(0, 0), (1, 0), (0, 1)])
+                                   (25, 2048, 1024), (517, 80, 1024), (1000, 1024, 2048), (64, 6144, 320),
+                                   (4596, 1024, 1024), (4596, 2048, 1024), (4596, 1024, 2048), (20000, 1024, 1024)])
+@pytest.mark.parametrize("out_f32,act", [(0, 0), (1, 0), (0, 1), (2, 0), (3, 1)])     # bit 1 of out_f32: fp16 operands
 def test_gemm(eng, M, N, K, out_f32, act):
     from flowmirror_hydravox_b200 import _lib as L
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
-    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
-    B = (torch.randn(N, K, device="cuda", generator=g) * (1.0 / K ** 0.5)).bfloat16()
+    dt = torch.float16 if out_f32 & 2 else torch.bfloat16
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(dt)
+    B = (torch.randn(N, K, device="cuda", generator=g) * (1.0 / K ** 0.5)).to(dt)
     bias = torch.randn(N, device="cuda", generator=g)
-    Cout = torch.zeros(M, N, device="cuda", dtype=torch.float32 if out_f32 else torch.bfloat16)
+    Cout = torch.zeros(M, N, device="cuda", dtype=torch.float32 if out_f32 & 1 else dt)
     L.check(L.lib().hvx_gemm_bf16(eng.h, L.ptr(A), L.ptr(B), L.ptr(bias), L.ptr(Cout), M, N, K, out_f32, act, L.stream_ptr()))
     torch.cuda.synchronize()
     ref = A.float() @ B.float().T + bias
     if act == 1:
         ref = torch.nn.functional.gelu(ref, approximate="tanh")
-    tol = 2e-3 if out_f32 else 2e-2
+    tol = 2e-3 if out_f32 & 1 else (4e-3 if out_f32 & 2 else 2e-2)
     err = (Cout.float() - ref).abs().max().item()
     assert err < tol, err
 
