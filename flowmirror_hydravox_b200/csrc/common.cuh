@@ -52,6 +52,8 @@ struct hvx_engine {
   hvx::FlowState* flow = nullptr;
   hvx::LlmState* llm = nullptr;
   int64_t launches = 0;
+  hvx::DevBuf samp_ws;             // sampler tables (llm.cu)
+  void* samp_arrive = nullptr;
   int64_t graph_launches = 0;      // kernels inside the captured decode-step graph
   int sm_count = 148;
   const hvx::Tensor* find(int stage, const std::string& name) const {

@@ -76,7 +76,8 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 }
 
 // fused epilogue of one 32-column chunk of one output row: v = raw fp32 accumulators of columns [col0, col0+32)
-__device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx, int col0, int N, const uint32_t* v) {
+__device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx, int col0, int N, const uint32_t* v,
+                                          const float* pre = nullptr) {
       float f[32];
 #pragma unroll
       for (int j = 0; j < 32; j++) {
@@ -126,7 +127,7 @@ __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx,
         if (col0 + 32 <= N) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            float4 cur = *reinterpret_cast<float4*>(o + j);
+            float4 cur = pre ? make_float4(pre[j], pre[j + 1], pre[j + 2], pre[j + 3]) : *reinterpret_cast<float4*>(o + j);
             const float4 gg = __ldg(reinterpret_cast<const float4*>(g + j));
             cur.x = fmaf(gg.x, f[j], cur.x); cur.y = fmaf(gg.y, f[j + 1], cur.y);
             cur.z = fmaf(gg.z, f[j + 2], cur.z); cur.w = fmaf(gg.w, f[j + 3], cur.w);
@@ -287,7 +288,8 @@ struct PersistSmem {
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;
 };
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+constexpr int PERSIST_THREADS = 320;     // TMA warp, MMA warp, 8 epilogue warps
+__global__ void __launch_bounds__(PERSIST_THREADS, 1)
 gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N, int K,
                     GemmEpi epi, GemmAddr ad, int tiles_m, int tiles_n) {
   using S = PersistSmem;
@@ -307,7 +309,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     tc::tma_prefetch_desc(&tma_a);
     tc::tma_prefetch_desc(&tma_b);
     for (int s = 0; s < PSTAGES; s++) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; s++) { tc::mbar_init(&tmem_full[s], 1); tc::mbar_init(&tmem_empty[s], 4); }
+    for (int s = 0; s < 2; s++) { tc::mbar_init(&tmem_full[s], 1); tc::mbar_init(&tmem_empty[s], 8); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, 2 * PBN);
@@ -358,7 +360,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
     }
   } else {
-    const int q = warp & 3;
+    // 8 epilogue warps: warp%4 selects the TMEM lane quarter (hardware rule), (warp-2)/4 the column half
+    const int q = warp & 3, half = (warp - 2) >> 2;
     int t = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t++) {
       const int mt = tile / tiles_n, nt = tile - mt * tiles_n;
@@ -366,16 +369,25 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const int row = mt * BM + q * 32 + lane;
       const bool row_ok = row < M;
       const int bidx = row / epi.rows_per_batch;
+      const int colh = nt * PBN + half * (PBN / 2);
+      // the residual this tile updates does not depend on its accumulator: fetch it while the MMAs run
+      float pre[PBN / 2];
+      const bool use_pre = epi.mode == EPI_RESID_GATE && row_ok && colh + PBN / 2 <= N;
+      if (use_pre) {
+        const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(epi.out) + (size_t)row * epi.ldo + colh);
+#pragma unroll
+        for (int j = 0; j < PBN / 8; j++) { const float4 x4 = src[j]; pre[4 * j] = x4.x; pre[4 * j + 1] = x4.y; pre[4 * j + 2] = x4.z; pre[4 * j + 3] = x4.w; }
+      }
       tc::mbar_wait(&tmem_full[as], (t >> 1) & 1);
       tc::tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < PBN; c0 += 32) {
+#pragma unroll
+      for (int c = 0; c < PBN / 2; c += 32) {
         uint32_t v[32];
-        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * PBN + c0), v);
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * PBN + half * (PBN / 2) + c), v);
         tc::tmem_ld_wait();
-        const int col0 = nt * PBN + c0;
+        const int col0 = colh + c;
         if (!row_ok || col0 >= N) continue;
-        epi_store(epi, row, bidx, col0, N, v);
+        epi_store(epi, row, bidx, col0, N, v, use_pre ? &pre[c] : nullptr);
       }
       tc::tc_fence_before();
       __syncwarp();
@@ -397,7 +409,7 @@ static hvx_status launch_gemm_persist(hvx_engine* e, cudaStream_t st, const CUte
   }
   const int tiles_m = cdiv(M, BM), tiles_n = cdiv(N, PBN);
   const int grid = std::min(tiles_m * tiles_n, e->sm_count);
-  gemm_persist_kernel<<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, M, N, K, epi, ad, tiles_m, tiles_n);
+  gemm_persist_kernel<<<grid, PERSIST_THREADS, S::TOTAL, st>>>(ta, tb, M, N, K, epi, ad, tiles_m, tiles_n);
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
 }
@@ -434,7 +446,7 @@ hvx_status gemm_bf16(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* A, int
             "gemm: cuTensorMapEncodeTiled(A) failed");
   // big plain GEMMs (the DiT linears): persistent 128 x 256 tiles
   if (ad.n_batch == 1 && ad.kb_per_tap == 0 && ad.b_kb_mod == 0 && ad.a_col0 == 0 && ad.a_col_per_ntile == 0 && ad.a_row0 == 0 &&
-      N % PBN == 0 && cdiv(M, BM) * (N / PBN) >= e->sm_count / 2 && !getenv("HVX_NO_PERSIST")) {
+      N % PBN == 0 && cdiv(M, BM) * (N / PBN) >= e->sm_count / 2 && getenv("HVX_PERSIST_GEMM")) {   // opt-in: measured slower than 2 CTAs/SM of 128x128 (both L2-bound)
     HVX_CHECK(make_tmap_bf16_2d(&tb, B, N, kB, ldb, PBN, BK), HVX_ERR_CUDA, "gemm: cuTensorMapEncodeTiled(B) failed");
     return launch_gemm_persist(e, st, ta, tb, M, N, K, epi, ad);
   }

@@ -25,6 +25,7 @@
 #include <type_traits>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 namespace hvx {
 
@@ -88,8 +89,8 @@ __device__ __forceinline__ void gemv_fma8(float& acc, const uint4 u, const float
 
 template <int R>
 __global__ void __launch_bounds__(256) llm_gemv_kernel(GemvArgs a) {
-  extern __shared__ float sx[];                     // [R][kc]
-  __shared__ float s_scale[8];
+  extern __shared__ float sx[];                     // [R][kc] activations, then [kc] norm weights
+  __shared__ __align__(8) uint64_t s_bar;
   asm volatile("griddepcontrol.launch_dependents;");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
   const int by = blockIdx.y;
@@ -99,8 +100,10 @@ __global__ void __launch_bounds__(256) llm_gemv_kernel(GemvArgs a) {
   const int npairs = (a.N + 1) >> 1;
   const int first = blockIdx.x * nwarp + warp, stride = gridDim.x * nwarp;
   const bool multi = K > kc;                        // host guarantees <= 1 pair per warp in that case
+  const float* nw = a.norm_w ? a.norm_w + by * a.sNorm : nullptr;
+  float* snw = sx + R * kc;
 
-  // ---- independent of the previous kernel: request the first weight rows of this warp
+  // ---- independent of the previous kernel: request the first weight rows of this warp, stage the norm weights
   uint4 p0[4], p1[4];
   {
     const int n0 = 2 * first;
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(256) llm_gemv_kernel(GemvArgs a) {
       else { p0[i] = make_uint4(0, 0, 0, 0); p1[i] = make_uint4(0, 0, 0, 0); }
     }
   }
-  __shared__ __align__(8) uint64_t s_bar;
+  if (nw) for (int k = tid * 4; k < K; k += blockDim.x * 4) *reinterpret_cast<float4*>(&snw[k]) = __ldg(reinterpret_cast<const float4*>(nw + k));
   if (tid == 0) { tc::mbar_init(&s_bar, 1); tc::fence_barrier_init(); }
   asm volatile("griddepcontrol.wait;" ::: "memory");
   __syncthreads();
@@ -122,7 +125,6 @@ __global__ void __launch_bounds__(256) llm_gemv_kernel(GemvArgs a) {
   const float* bias = a.bias ? a.bias + by * a.sBias : nullptr;
   float* out = a.out + by * a.sOut;
   const float* resid = a.resid ? a.resid + by * a.sResid : nullptr;
-  const float* nw = a.norm_w ? a.norm_w + by * a.sNorm : nullptr;
   float acc0[R], acc1[R];
   uint32_t bar_phase = 0;
 
@@ -137,20 +139,29 @@ __global__ void __launch_bounds__(256) llm_gemv_kernel(GemvArgs a) {
     for (int i = tid; i < (R - a.rows) * kn; i += blockDim.x) sx[a.rows * kc + (i / kn) * kc + (i % kn)] = 0.f;   // padding rows
     tc::mbar_wait(&s_bar, bar_phase);
     bar_phase ^= 1;
-    if (nw) {                                       // fused RMSNorm (HF Qwen2RMSNorm: fp32, eps inside rsqrt); K == kn here
-      for (int r = warp; r < a.rows; r += nwarp) {
+    if (nw) {
+      // fused RMSNorm (HF Qwen2RMSNorm: fp32, eps inside rsqrt; K == kn here): x <- nw * (x * rsqrt(mean(x^2)+eps)),
+      // each warp normalises a slice of every row after all warps have computed the row scales redundantly
+      float sc[R];
+#pragma unroll
+      for (int r = 0; r < R; r++) {
         float ss = 0.f;
         for (int k = lane * 4; k < kn; k += 128) {
           const float4 v = *reinterpret_cast<const float4*>(&sx[r * kc + k]);
           ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
         }
         for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        if (lane == 0) s_scale[r] = rsqrtf(ss / (float)K + a.eps);
+        sc[r] = rsqrtf(ss / (float)K + a.eps);
       }
-      __syncthreads();
-      for (int i = tid; i < a.rows * kn; i += blockDim.x) {
-        const int r = i / kn, k = i - r * kn;
-        sx[r * kc + k] = nw[k] * (sx[r * kc + k] * s_scale[r]);
+      __syncthreads();                              // every warp has read the raw rows
+      for (int k = tid * 4; k < kn; k += blockDim.x * 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&snw[k]);
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          float4 v = *reinterpret_cast<float4*>(&sx[r * kc + k]);
+          v.x = w4.x * (v.x * sc[r]); v.y = w4.y * (v.y * sc[r]); v.z = w4.z * (v.z * sc[r]); v.w = w4.w * (v.w * sc[r]);
+          *reinterpret_cast<float4*>(&sx[r * kc + k]) = v;
+        }
       }
     }
     __syncthreads();
@@ -162,7 +173,20 @@ __global__ void __launch_bounds__(256) llm_gemv_kernel(GemvArgs a) {
 #pragma unroll
         for (int r = 0; r < R; r++) { acc0[r] = 0.f; acc1[r] = 0.f; }
       }
-      const bool pre = (pair == first) && kb == 0;
+      // software pipeline across pairs: the next pair's first rows are requested before this pair is reduced
+      uint4 q0[4], q1[4];
+      const int npair = pair + stride;
+      const bool have_next = !multi && npair < npairs;
+      if (have_next) {
+        const __nv_bfloat16* v0 = W + (size_t)(2 * npair) * K;
+        const __nv_bfloat16* v1 = v0 + ((2 * npair + 1 < a.N) ? K : 0);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int k = lane * 8 + i * 256;
+          if (k < kn) { q0[i] = ldg_stream(v0 + k); q1[i] = ldg_stream(v1 + k); }
+        }
+      }
+      const bool pre = !multi || kb == 0;           // p0/p1 hold the first 1024 columns of this pair
       for (int k0 = lane * 8; k0 < kn; k0 += 1024) {
         uint4 u0[4], u1[4];
 #pragma unroll
@@ -183,6 +207,10 @@ __global__ void __launch_bounds__(256) llm_gemv_kernel(GemvArgs a) {
           }
         }
       }
+      if (have_next) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) { p0[i] = q0[i]; p1[i] = q1[i]; }
+      }
       if (multi && kb + kc < K) continue;
 #pragma unroll
       for (int r = 0; r < R; r++) {
@@ -192,27 +220,169 @@ __global__ void __launch_bounds__(256) llm_gemv_kernel(GemvArgs a) {
           acc1[r] += __shfl_xor_sync(0xffffffffu, acc1[r], o);
         }
       }
-      if (lane == 0) {
-        const float b0 = bias ? bias[n0] : 0.f;
-        const float b1 = (bias && n0 + 1 < a.N) ? bias[n0 + 1] : 0.f;
+      // lane r finishes row r (bias, RoPE / SwiGLU / residual, store)
+      float y0 = 0.f, y1 = 0.f;
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-          if (r < a.rows) {
-            const float y0 = acc0[r] + b0, y1 = acc1[r] + b1;
-            if (a.mode == GEMV_QKV) {
-              llm_qkv_store(a.qkv, r, n0, y0, y1);
-            } else if (a.mode == GEMV_SWIGLU) {
-              out[(size_t)r * a.ldo + pair] = (y0 / (1.0f + expf(-y0))) * y1;
-            } else {
-              float o0 = y0, o1 = y1;
-              if (resid) { o0 += resid[(size_t)r * a.ldr + n0]; if (n0 + 1 < a.N) o1 += resid[(size_t)r * a.ldr + n0 + 1]; }
-              out[(size_t)r * a.ldo + n0] = o0;
-              if (n0 + 1 < a.N) out[(size_t)r * a.ldo + n0 + 1] = o1;
-            }
-          }
+      for (int r = 0; r < R; r++) if (lane == r) { y0 = acc0[r]; y1 = acc1[r]; }
+      if (lane < a.rows) {
+        const int r = lane;
+        y0 += bias ? bias[n0] : 0.f;
+        y1 += (bias && n0 + 1 < a.N) ? bias[n0 + 1] : 0.f;
+        if (a.mode == GEMV_QKV) {
+          llm_qkv_store(a.qkv, r, n0, y0, y1);
+        } else if (a.mode == GEMV_SWIGLU) {
+          out[(size_t)r * a.ldo + pair] = (y0 / (1.0f + expf(-y0))) * y1;
+        } else {
+          if (resid) { y0 += resid[(size_t)r * a.ldr + n0]; if (n0 + 1 < a.N) y1 += resid[(size_t)r * a.ldr + n0 + 1]; }
+          out[(size_t)r * a.ldo + n0] = y0;
+          if (n0 + 1 < a.N) out[(size_t)r * a.ldo + n0 + 1] = y1;
         }
       }
     }
+  }
+}
+
+// ---- TMA-fed variant (K <= GT_KMAX): the weight stream is decoupled from the warps.  A CTA owns a contiguous
+// range of output pairs, i.e. one contiguous byte range of W; a producer lane streams that range through a ring of
+// shared-memory slots with 1-D bulk copies (cp.async.bulk) and starts doing so *before* griddepcontrol.wait, so
+// bytes keep arriving while the previous kernel drains and while the activations are staged and normalised.  Eight
+// consumer warps take the pairs of a landed slot round-robin and read their weights from shared memory.
+constexpr int GT_SLOT = 40 * 1024;     // 2 pairs at K=4864, 11 pairs at K=896
+constexpr int GT_NS = 3;
+constexpr int GT_CONS = 8;             // consumer warps
+constexpr int GT_KMAX = 5120;          // a pair (2 rows x K bf16) must fit a slot
+
+template <int R>
+__global__ void __launch_bounds__((GT_CONS + 1) * 32, 1) llm_gemv_tma_kernel(GemvArgs a) {
+  extern __shared__ __align__(128) uint8_t smraw[];
+  __shared__ __align__(8) uint64_t full_bar[GT_NS], empty_bar[GT_NS], x_bar;
+  asm volatile("griddepcontrol.launch_dependents;");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int by = blockIdx.y;
+  const int K = a.K;
+  const float* x = a.x + by * a.sX;
+  const __nv_bfloat16* W = a.W + by * a.sW;
+  const float* nw = a.norm_w ? a.norm_w + by * a.sNorm : nullptr;
+  uint8_t* ring = smraw;
+  float* sx = reinterpret_cast<float*>(smraw + GT_NS * GT_SLOT);      // [R][K]
+  float* snw = sx + R * K;                                            // [K]
+  const int npairs = (a.N + 1) >> 1;
+  const int ppc = (npairs + gridDim.x - 1) / gridDim.x;               // pairs per CTA (contiguous)
+  const int p_begin = blockIdx.x * ppc, p_end = min(npairs, p_begin + ppc);
+  const int pps = GT_SLOT / (4 * K);                                  // pairs per slot
+  const int nslots = p_end > p_begin ? (p_end - p_begin + pps - 1) / pps : 0;
+
+  if (tid == 0) {
+    for (int i = 0; i < GT_NS; i++) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], GT_CONS); }
+    tc::mbar_init(&x_bar, 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp == GT_CONS) {
+    // ---------------- producer: weights only, never waits for the previous kernel
+    if (lane == 0) {
+      for (int i = 0; i < nslots; i++) {
+        const int sl = i % GT_NS;
+        if (i >= GT_NS) tc::mbar_wait(&empty_bar[sl], ((i / GT_NS) - 1) & 1);
+        const int p0 = p_begin + i * pps;
+        const int row0 = 2 * p0, row1 = min(a.N, 2 * min(p_end, p0 + pps));
+        const uint32_t bytes = (uint32_t)(row1 - row0) * (uint32_t)K * 2u;
+        tc::mbar_expect_tx(&full_bar[sl], bytes);
+        bulk_g2s(ring + sl * GT_SLOT, W + (size_t)row0 * K, bytes, &full_bar[sl]);
+      }
+    }
+    return;
+  }
+  // ---------------- consumers
+  if (nw) for (int k = tid * 4; k < K; k += GT_CONS * 128) *reinterpret_cast<float4*>(&snw[k]) = __ldg(reinterpret_cast<const float4*>(nw + k));
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (tid == 0) {
+    tc::mbar_expect_tx(&x_bar, (uint32_t)(a.rows * K * 4));
+    for (int r = 0; r < a.rows; r++) bulk_g2s(&sx[r * K], x + (size_t)r * a.ldx, (uint32_t)(K * 4), &x_bar);
+  }
+  for (int i = tid; i < (R - a.rows) * K; i += GT_CONS * 32) sx[a.rows * K + i] = 0.f;      // padding rows
+  tc::mbar_wait(&x_bar, 0);
+  if (nw) {
+    float sc[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      float ss = 0.f;
+      for (int k = lane * 4; k < K; k += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(&sx[r * K + k]);
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      }
+      for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      sc[r] = rsqrtf(ss / (float)K + a.eps);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(GT_CONS * 32));            // consumers only: every warp has read the raw rows
+    for (int k = tid * 4; k < K; k += GT_CONS * 128) {
+      const float4 w4 = *reinterpret_cast<const float4*>(&snw[k]);
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        float4 v = *reinterpret_cast<float4*>(&sx[r * K + k]);
+        v.x = w4.x * (v.x * sc[r]); v.y = w4.y * (v.y * sc[r]); v.z = w4.z * (v.z * sc[r]); v.w = w4.w * (v.w * sc[r]);
+        *reinterpret_cast<float4*>(&sx[r * K + k]) = v;
+      }
+    }
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(GT_CONS * 32));
+  const float* bias = a.bias ? a.bias + by * a.sBias : nullptr;
+  float* out = a.out + by * a.sOut;
+  const float* resid = a.resid ? a.resid + by * a.sResid : nullptr;
+
+  for (int i = 0; i < nslots; i++) {
+    const int sl = i % GT_NS;
+    tc::mbar_wait(&full_bar[sl], (i / GT_NS) & 1);
+    const int p0 = p_begin + i * pps;
+    const int np = min(pps, p_end - p0);
+    const __nv_bfloat16* ws = reinterpret_cast<const __nv_bfloat16*>(ring + sl * GT_SLOT);
+    for (int pi = warp; pi < np; pi += GT_CONS) {
+      const int pair = p0 + pi, n0 = 2 * pair;
+      const bool two = n0 + 1 < a.N;
+      const __nv_bfloat16* w0 = ws + (size_t)(2 * pi) * K;
+      const __nv_bfloat16* w1 = two ? w0 + K : w0;
+      float acc0[R], acc1[R];
+#pragma unroll
+      for (int r = 0; r < R; r++) { acc0[r] = 0.f; acc1[r] = 0.f; }
+#pragma unroll 2
+      for (int k = lane * 8; k < K; k += 256) {
+        const uint4 u0 = *reinterpret_cast<const uint4*>(w0 + k);
+        const uint4 u1 = *reinterpret_cast<const uint4*>(w1 + k);
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          gemv_fma8(acc0[r], u0, &sx[r * K + k]);
+          gemv_fma8(acc1[r], u1, &sx[r * K + k]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+          acc0[r] += __shfl_xor_sync(0xffffffffu, acc0[r], o);
+          acc1[r] += __shfl_xor_sync(0xffffffffu, acc1[r], o);
+        }
+      }
+      float y0 = 0.f, y1 = 0.f;
+#pragma unroll
+      for (int r = 0; r < R; r++) if (lane == r) { y0 = acc0[r]; y1 = acc1[r]; }
+      if (lane < a.rows) {
+        const int r = lane;
+        y0 += bias ? bias[n0] : 0.f;
+        y1 += (bias && two) ? bias[n0 + 1] : 0.f;
+        if (a.mode == GEMV_QKV) {
+          llm_qkv_store(a.qkv, r, n0, y0, y1);
+        } else if (a.mode == GEMV_SWIGLU) {
+          out[(size_t)r * a.ldo + pair] = (y0 / (1.0f + expf(-y0))) * y1;
+        } else {
+          if (resid) { y0 += resid[(size_t)r * a.ldr + n0]; if (two) y1 += resid[(size_t)r * a.ldr + n0 + 1]; }
+          out[(size_t)r * a.ldo + n0] = y0;
+          if (two) out[(size_t)r * a.ldo + n0 + 1] = y1;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(&empty_bar[sl]);
   }
 }
 
@@ -243,6 +413,8 @@ __global__ void __launch_bounds__(256) llm_attn_kernel(AttnDecArgs a) {
   __shared__ __align__(16) KT sk[ATT_KEYS * LD];
   __shared__ __align__(16) KT sv[ATT_KEYS * LD];
   __shared__ int s_last;
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
   const int split = blockIdx.x;
   const int row = blockIdx.y / a.kv_heads, kvh = blockIdx.y - row * a.kv_heads;
@@ -420,6 +592,8 @@ __global__ void __launch_bounds__(256) llm_last_norm_kernel(const float* __restr
                                                              float* __restrict__ hn, __nv_bfloat16* __restrict__ hn16, int H,
                                                              float eps) {
   __shared__ float red[8];
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int seq = blockIdx.x;
   const SeqState& s = seqs[seq];
   const int r = s.n_new > 0 ? s.n_new - 1 : 0;
@@ -457,159 +631,189 @@ struct SampArgs {
   int* n_active = nullptr;
   int max_ctx = 0x7fffffff;               // KV-cache capacity: a sequence that would overflow it stops
   float* logp_out = nullptr;              // optional [head][seq][vocab]
+  float* tables = nullptr;                // [seq][head][SAMP_TAB + vocab] scratch
+  int* arrive = nullptr;                  // [seq] arrival counters (zero)
   // standalone mode (hvx_sample): explicit history instead of out_tokens
   const int32_t* history = nullptr; int n_history = 0; int min_len_override = -1;
   int32_t* ids_out = nullptr; int32_t* u_used = nullptr;
 };
 
-__device__ __forceinline__ float block_reduce_max(float v, float* red) {
+// block-wide reductions on double-buffered scratch: one __syncthreads each
+__device__ __forceinline__ float block_max(float v, float* red /*[8]*/) {
   for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  __syncthreads();
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
   float r = red[0];
-  for (int i = 1; i < (int)(blockDim.x >> 5); i++) r = fmaxf(r, red[i]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) r = fmaxf(r, red[i]);
   return r;
 }
-__device__ __forceinline__ float block_reduce_sum(float v, float* red) {
+__device__ __forceinline__ float block_sum(float v, float* red /*[8]*/) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
   float r = 0.f;
-  for (int i = 0; i < (int)(blockDim.x >> 5); i++) r += red[i];
+#pragma unroll
+  for (int i = 0; i < 8; i++) r += red[i];
   return r;
 }
 
-// One block per sequence.  For every head: log_softmax -> softmax (common.py:149), stable descending top-k
-// prefix with cum < top_p (:150-156), inverse-CDF draws on the explicit uniform stream (oracle/llm_ref.py
-// documents the order: one u per multinomial call), repetition-aware fallback over the full vocabulary
-// (:139-143), EOS retry (llm_multi_head_v3.py:151-166); then the emit / stop logic of :902-916 and the
-// embedding fetch of the next step's rows (:919-922).
-__global__ void __launch_bounds__(256) llm_sampler_kernel(SampArgs a) {
-  extern __shared__ float smem[];
-  float* p = smem;                         // [vocab]
-  float* cum = smem + a.vocab;             // [vocab]
-  __shared__ float red[8];
-  __shared__ int redi[8];
-  __shared__ double dpart[256];
-  __shared__ float topv[SAMP_MAXK];
-  __shared__ int topi[SAMP_MAXK];
-  __shared__ int s_n, s_stop, s_ids[LLM_MAX_HEADS], s_group, s_alive;
-  const int seq = blockIdx.x, tid = threadIdx.x, V = a.vocab;
+constexpr int SAMP_THREADS = 256;
+constexpr int SAMP_PER = 32;              // values per thread in registers: vocab <= 8192
+constexpr int SAMP_TAB = 2 * SAMP_MAXK + 8;   // per (seq, head) table header: topv[64] | topi[64] | n | pad
+
+// grid (n_seq, head_k).  Phase 1 (every block, one head of one sequence): log_softmax -> softmax (common.py:149),
+// stable descending top-k prefix with cum < top_p (:150-156) and the fp64-accumulated cumulative sums needed by the
+// inverse-CDF draws, written to a small table.  Phase 2 (the block that arrives last for its sequence): the serial
+// part — draws on the explicit uniform stream (oracle/llm_ref.py documents the order: one u per multinomial call),
+// repetition-aware fallback over the full vocabulary (:139-143), EOS retry (llm_multi_head_v3.py:151-166), the
+// emit / stop logic of :902-916 and the embedding fetch of the next step's rows (:919-922).
+__global__ void __launch_bounds__(SAMP_THREADS) llm_sampler_kernel(SampArgs a) {
+  extern __shared__ float p[];                       // [vocab] probabilities
+  __shared__ float red[4][8];
+  __shared__ int redi[2][8];
+  __shared__ double dwarp[8];
+  __shared__ int s_flag;
+  __shared__ int s_ids[LLM_MAX_HEADS], s_group, s_alive;
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int seq = blockIdx.x, j = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, V = a.vocab;
   SeqState* st = a.seqs ? &a.seqs[seq] : nullptr;
   if (st && st->done) return;
-  const int n_hist = st ? st->n_out : a.n_history;
-  const int32_t* hist = st ? a.out_tokens + (size_t)seq * a.max_out : a.history;
-  const int min_len = st ? st->min_len : a.min_len_override;
-  int u_pos = st ? st->u_pos : 0;
-  int status = 0;
   const int topk = a.top_k < SAMP_MAXK ? a.top_k : SAMP_MAXK;
+  float* tab = a.tables + ((size_t)seq * a.head_k + j) * (SAMP_TAB + V);
+  float* cum = tab + SAMP_TAB;
 
-  for (int j = 0; j < a.head_k; j++) {
+  // ---------------- phase 1
+  {
     const float* x = a.logits + ((size_t)j * a.n_seq + seq) * V;
-    // log_softmax then softmax, both fp32
+    float v[SAMP_PER];
     float mx = -INFINITY;
-    for (int i = tid; i < V; i += blockDim.x) mx = fmaxf(mx, x[i]);
-    mx = block_reduce_max(mx, red);
+#pragma unroll
+    for (int q = 0; q < SAMP_PER; q++) { const int i = tid + q * SAMP_THREADS; v[q] = i < V ? x[i] : -INFINITY; mx = fmaxf(mx, v[q]); }
+    mx = block_max(mx, red[0]);
     float lse = 0.f;
     if (!a.input_is_logp) {
       float se = 0.f;
-      for (int i = tid; i < V; i += blockDim.x) se += expf(x[i] - mx);
-      se = block_reduce_sum(se, red);
-      lse = logf(se);
+#pragma unroll
+      for (int q = 0; q < SAMP_PER; q++) if (tid + q * SAMP_THREADS < V) se += expf(v[q] - mx);
+      lse = logf(block_sum(se, red[1]));
     }
-    float m2 = -INFINITY;
-    for (int i = tid; i < V; i += blockDim.x) {
-      const float lp = a.input_is_logp ? x[i] : (x[i] - mx) - lse;
-      p[i] = lp;
-      if (a.logp_out) a.logp_out[((size_t)j * a.n_seq + seq) * V + i] = lp;
-      m2 = fmaxf(m2, lp);
-    }
-    m2 = block_reduce_max(m2, red);
+    // softmax(log_softmax(x)): the maximum of logp is (mx - mx) - lse = -lse exactly (or max(x) if x already is logp)
+    const float m2 = a.input_is_logp ? mx : -lse;
     float z = 0.f;
-    for (int i = tid; i < V; i += blockDim.x) { const float e = expf(p[i] - m2); p[i] = e; z += e; }
-    z = block_reduce_sum(z, red);
-    for (int i = tid; i < V; i += blockDim.x) p[i] = p[i] / z;
+#pragma unroll
+    for (int q = 0; q < SAMP_PER; q++) {
+      const int i = tid + q * SAMP_THREADS;
+      if (i < V) {
+        const float lp = a.input_is_logp ? v[q] : (v[q] - mx) - lse;
+        if (a.logp_out) a.logp_out[((size_t)j * a.n_seq + seq) * V + i] = lp;
+        v[q] = expf(lp - m2);
+        z += v[q];
+      } else v[q] = -1.f;
+    }
+    z = block_sum(z, red[2]);
+    float bv = -1.f; int bq = 0;
+#pragma unroll
+    for (int q = 0; q < SAMP_PER; q++) {
+      const int i = tid + q * SAMP_THREADS;
+      if (i < V) { v[q] = v[q] / z; p[i] = v[q]; if (v[q] > bv) { bv = v[q]; bq = q; } }
+    }
     __syncthreads();
     // inclusive cumulative sum accumulated in fp64, rounded to fp32 per element (torch CPU cumsum)
     {
-      const int per = (V + blockDim.x - 1) / blockDim.x;
+      const int per = (V + SAMP_THREADS - 1) / SAMP_THREADS;
       const int i0 = tid * per, i1 = min(V, i0 + per);
       double s = 0.0;
       for (int i = i0; i < i1; i++) s += (double)p[i];
-      dpart[tid] = s;
+      double inc = s;                                   // warp-inclusive scan of the segment sums
+      for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      if (lane == 31) dwarp[warp] = inc;
       __syncthreads();
-      double run = 0.0;
-      for (int k = 0; k < tid; k++) run += dpart[k];
+      double run = inc - s;
+      for (int w = 0; w < warp; w++) run += dwarp[w];
       for (int i = i0; i < i1; i++) { run += (double)p[i]; cum[i] = (float)run; }
-      __syncthreads();
     }
-    // stable descending selection of the nucleus prefix
-    if (tid == 0) { s_n = 0; s_stop = 0; }
-    __syncthreads();
-    float csum = 0.f;                      // thread 0's running fp32 sum (cum = cum + sv[n])
+    // stable descending selection of the nucleus prefix: every thread caches the best of its own values
+    float csum = 0.f;
+    int n = 0;
     for (int t = 0; t < topk; t++) {
-      float bv = -1.f; int bi = 0x7fffffff;
-      for (int i = tid; i < V; i += blockDim.x) { const float v = p[i]; if (v > bv) { bv = v; bi = i; } }   // strided: first max has the lowest index
+      float cv = bv; int ci = bv >= 0.f ? tid + bq * SAMP_THREADS : 0x7fffffff;
       for (int o = 16; o; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        const float ov = __shfl_xor_sync(0xffffffffu, cv, o); const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
+        if (ov > cv || (ov == cv && oi < ci)) { cv = ov; ci = oi; }
       }
-      if ((tid & 31) == 0) { red[tid >> 5] = bv; redi[tid >> 5] = bi; }
+      float* rv = red[t & 1]; int* ri = redi[t & 1];
+      if (lane == 0) { rv[warp] = cv; ri[warp] = ci; }
       __syncthreads();
-      if (tid == 0) {
-        for (int w = 1; w < (int)(blockDim.x >> 5); w++)
-          if (red[w] > bv || (red[w] == bv && redi[w] < bi)) { bv = red[w]; bi = redi[w]; }
-        topv[t] = bv; topi[t] = bi;
-        p[bi] = -2.f;                       // taken
-        csum = csum + bv;
-        s_n = t + 1;
-        if (!((double)csum < a.top_p)) s_stop = 1;
+      cv = rv[0]; ci = ri[0];
+#pragma unroll
+      for (int w = 1; w < 8; w++) if (rv[w] > cv || (rv[w] == cv && ri[w] < ci)) { cv = rv[w]; ci = ri[w]; }
+      if (tid == 0) { tab[t] = cv; reinterpret_cast<int*>(tab)[SAMP_MAXK + t] = ci; }
+      csum = csum + cv;                               // cum = cum + sv[n] in fp32, same in every thread
+      n = t + 1;
+      if ((ci & (SAMP_THREADS - 1)) == tid) {         // owner: retire the winner, rescan own values
+        const int qq = ci / SAMP_THREADS;
+        bv = -1.f; bq = 0;
+#pragma unroll
+        for (int q = 0; q < SAMP_PER; q++) { if (q == qq) v[q] = -1.f; if (v[q] > bv) { bv = v[q]; bq = q; } }
       }
-      __syncthreads();
-      if (s_stop) break;
+      if (!((double)csum < a.top_p)) break;
     }
-    if (tid == 0) {
-      const int n = s_n;
-      for (int t = 0; t < n; t++) p[topi[t]] = topv[t];          // restore
-      // prefix cumsum of the kept probabilities (fp64 accumulate, fp32 values)
+    if (tid == 0) reinterpret_cast<int*>(tab)[2 * SAMP_MAXK] = n;
+  }
+  // ---------------- hand over to the last block of this sequence
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_flag = (atomicAdd(&a.arrive[seq], 1) == a.head_k - 1);
+  __syncthreads();
+  if (!s_flag) return;
+  __threadfence();
+
+  // ---------------- phase 2 (one thread; the tables are tiny)
+  if (tid == 0) {
+    a.arrive[seq] = 0;
+    const int n_hist = st ? st->n_out : a.n_history;
+    const int32_t* hist = st ? a.out_tokens + (size_t)seq * a.max_out : a.history;
+    const int min_len = st ? st->min_len : a.min_len_override;
+    int u_pos = st ? st->u_pos : 0;
+    int status = 0;
+    for (int h = 0; h < a.head_k; h++) {
+      const float* tb = a.tables + ((size_t)seq * a.head_k + h) * (SAMP_TAB + V);
+      const float* cm = tb + SAMP_TAB;
+      const int n = __ldcg(reinterpret_cast<const int*>(tb) + 2 * SAMP_MAXK);
       float kc[SAMP_MAXK];
-      { double run = 0.0; for (int t = 0; t < n; t++) { run += (double)topv[t]; kc[t] = (float)run; } }
-      const bool ignore_eos = (n_hist + j) < min_len;
+      { double run = 0.0; for (int t = 0; t < n; t++) { run += (double)__ldcg(tb + t); kc[t] = (float)run; } }
+      const bool ignore_eos = (n_hist + h) < min_len;
       int trials = 0, tok = 0;
       while (true) {
         if (u_pos + 2 > a.u_stride) { status = 2; tok = a.stop_from; break; }
         const float target = a.u[(size_t)seq * a.u_stride + u_pos++] * kc[n - 1];
         int i = 0;
         while (i < n - 1 && !(kc[i] > target)) i++;
-        tok = topi[i];
+        tok = __ldcg(reinterpret_cast<const int*>(tb) + SAMP_MAXK + i);
         // repetition check over the last win_size emitted tokens (whole history when win_size == 0)
-        int lo = a.win_size != 0 ? max(0, n_hist - a.win_size) : 0;
+        const int lo = a.win_size != 0 ? max(0, n_hist - a.win_size) : 0;
         int rep = 0;
-        for (int h = lo; h < n_hist; h++) rep += (hist[h] == tok);
+        for (int q = lo; q < n_hist; q++) rep += (hist[q] == tok);
         if ((double)rep >= a.rep_thr) {
-          const float tg = a.u[(size_t)seq * a.u_stride + u_pos++] * cum[V - 1];
+          const float tg = a.u[(size_t)seq * a.u_stride + u_pos++] * __ldcg(cm + V - 1);
           int lo2 = 0, hi2 = V - 1;                               // first index with cum > tg
-          while (lo2 < hi2) { const int mid = (lo2 + hi2) >> 1; if (cum[mid] > tg) hi2 = mid; else lo2 = mid + 1; }
+          while (lo2 < hi2) { const int mid = (lo2 + hi2) >> 1; if (__ldcg(cm + mid) > tg) hi2 = mid; else lo2 = mid + 1; }
           tok = lo2;
         }
         if (!ignore_eos || tok < a.stop_from) break;
         if (++trials > 100) { status = 1; break; }
       }
-      s_ids[j] = tok;
+      s_ids[h] = tok;
     }
-    __syncthreads();
-  }
-
-  if (tid == 0) {
     if (a.u_used) a.u_used[seq] = u_pos;
-    if (a.ids_out) for (int j = 0; j < a.head_k; j++) a.ids_out[seq * a.head_k + j] = s_ids[j];
+    if (a.ids_out) for (int h = 0; h < a.head_k; h++) a.ids_out[seq * a.head_k + h] = s_ids[h];
     s_group = 0; s_alive = 0;
     if (st) {
       int n_out = st->n_out, group = 0, stop = (status != 0);
-      for (int j = 0; j < a.head_k && !stop; j++) {
-        const int t = s_ids[j];
+      for (int h = 0; h < a.head_k && !stop; h++) {
+        const int t = s_ids[h];
         if (t >= a.stop_from) { stop = 1; break; }
         a.out_tokens[(size_t)seq * a.max_out + n_out++] = t;
         st->new_tok[group++] = t;
@@ -755,8 +959,57 @@ void llm_free(hvx_engine* e) {
 }
 
 // ---- launch helpers
+// launch with programmatic dependent launch allowed: the kernel may be scheduled while its predecessor drains
+// (every such kernel executes griddepcontrol.wait before it touches dependent data)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+template <int R>
+static hvx_status launch_gemv_tma(hvx_engine* e, cudaStream_t st, const GemvArgs& a, int n_batch, size_t smem) {
+  static bool attr = false;
+  if (!attr) { HVX_CUDA(cudaFuncSetAttribute(llm_gemv_tma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
+  const int pairs = (a.N + 1) / 2;
+  // one CTA per SM (all of them request bytes concurrently), each with a contiguous range of pairs
+  const int ctas = std::max(1, std::min(e->sm_count / n_batch, pairs));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(ctas, n_batch, 1);
+  cfg.blockDim = dim3((GT_CONS + 1) * 32, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  HVX_CUDA(cudaLaunchKernelEx(&cfg, llm_gemv_tma_kernel<R>, a));
+  HVX_LAUNCH_CHECK(e);
+  return HVX_OK;
+}
+
 static hvx_status launch_gemv(hvx_engine* e, cudaStream_t st, GemvArgs a, int R, int n_batch = 1) {
   a.rows = R;
+  {
+    const int Rt0 = R <= 1 ? 1 : R <= 2 ? 2 : R <= 4 ? 4 : 8;
+    const size_t smem_t = (size_t)GT_NS * GT_SLOT + ((size_t)Rt0 * a.K + (a.norm_w ? a.K : 0)) * sizeof(float) + 128;
+    if (a.K <= GT_KMAX && a.K % 8 == 0 && smem_t <= 220 * 1024 && !getenv("HVX_NO_TMA_GEMV")) {
+      switch (Rt0) {
+        case 1: return launch_gemv_tma<1>(e, st, a, n_batch, smem_t);
+        case 2: return launch_gemv_tma<2>(e, st, a, n_batch, smem_t);
+        case 4: return launch_gemv_tma<4>(e, st, a, n_batch, smem_t);
+        default: return launch_gemv_tma<8>(e, st, a, n_batch, smem_t);
+      }
+    }
+  }
   const int pairs = (a.N + 1) / 2;
   const int Rt = R <= 1 ? 1 : R <= 2 ? 2 : R <= 4 ? 4 : 8;
   HVX_CHECK(a.K % 8 == 0, HVX_ERR_UNSUPPORTED, "gemv: K must be a multiple of 8");
@@ -764,15 +1017,31 @@ static hvx_status launch_gemv(hvx_engine* e, cudaStream_t st, GemvArgs a, int R,
   const int kc_max = (96 * 1024 / 4 / Rt) & ~7;
   a.kc = a.K <= kc_max ? a.K : kc_max;
   HVX_CHECK(!a.norm_w || a.K <= a.kc, HVX_ERR_UNSUPPORTED, "gemv: fused norm needs the whole row staged (K=%d)", a.K);
-  const size_t smem = (size_t)Rt * a.kc * sizeof(float);
+  const size_t smem = ((size_t)Rt * a.kc + (a.norm_w ? a.K : 0)) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    HVX_CUDA(cudaFuncSetAttribute(llm_gemv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    HVX_CUDA(cudaFuncSetAttribute(llm_gemv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    HVX_CUDA(cudaFuncSetAttribute(llm_gemv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    HVX_CUDA(cudaFuncSetAttribute(llm_gemv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    attr_done = true;
+  }
   int warps = 8;
   int ctas;
   if (a.K > a.kc) {
     ctas = cdiv(pairs, warps);
   } else {
-    // persistent: about two waves of CTAs over the machine, fewer warps per CTA when there is little work
-    while (warps > 2 && cdiv(pairs, warps) * n_batch < e->sm_count) warps >>= 1;
-    ctas = std::min(cdiv(pairs, warps), std::max(1, 2 * e->sm_count / n_batch));
+    // persistent: at most two CTAs per SM; small matrices get 4-warp CTAs so that ~one CTA per SM covers them
+    if (pairs * n_batch <= 4 * e->sm_count) warps = 4;
+    int occ = 1;
+    switch (Rt) {
+      case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, llm_gemv_kernel<1>, warps * 32, smem); break;
+      case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, llm_gemv_kernel<2>, warps * 32, smem); break;
+      case 4: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, llm_gemv_kernel<4>, warps * 32, smem); break;
+      default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, llm_gemv_kernel<8>, warps * 32, smem); break;
+    }
+    occ = std::max(1, std::min(occ, 2));
+    ctas = std::min(cdiv(pairs, warps), std::max(1, occ * e->sm_count / n_batch));     // one resident wave
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -785,10 +1054,8 @@ static hvx_status launch_gemv(hvx_engine* e, cudaStream_t st, GemvArgs a, int R,
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  static bool attr[4] = {false, false, false, false};
 #define GEMV_CASE(RR, idx)                                                                                        \
   case RR:                                                                                                        \
-    if (!attr[idx]) { HVX_CUDA(cudaFuncSetAttribute(llm_gemv_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr[idx] = true; } \
     HVX_CUDA(cudaLaunchKernelEx(&cfg, llm_gemv_kernel<RR>, a));                                                   \
     break;
   switch (Rt) {
@@ -858,8 +1125,8 @@ static hvx_status launch_attn(hvx_engine* e, cudaStream_t st, LlmState* L, int l
   a.part = b.part; a.counters = b.counters; a.out = b.att; a.out16 = want16 ? b.att16 : nullptr; a.ldo = c.llm_hidden;
   a.scale = 1.0f / sqrtf((float)c.llm_head_dim);
   dim3 grid(splits, rows * c.llm_kv_heads);
-  if (L->kv_f32) llm_attn_kernel<true><<<grid, 32 * a.group, 0, st>>>(a);
-  else llm_attn_kernel<false><<<grid, 32 * a.group, 0, st>>>(a);
+  if (L->kv_f32) HVX_CUDA(launch_pdl(llm_attn_kernel<true>, grid, dim3(32 * a.group), 0, st, a));
+  else HVX_CUDA(launch_pdl(llm_attn_kernel<false>, grid, dim3(32 * a.group), 0, st, a));
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
 }
@@ -916,7 +1183,8 @@ static hvx_status llm_heads(hvx_engine* e, cudaStream_t st, LlmState* L, const S
   const int H = c.llm_hidden, MI = c.llm_mtp_inter, V = c.llm_speech_vocab;
   hvx_status rc;
   const bool tc = n_seq > 8;
-  llm_last_norm_kernel<<<n_seq, 256, 0, st>>>(b.h, L->norm, L->seqs, rows_per_seq, b.hn, nullptr, H, c.llm_eps);
+  HVX_CUDA(launch_pdl(llm_last_norm_kernel, dim3(n_seq), dim3(256), 0, st, (const float*)b.h, L->norm, (const SeqState*)L->seqs, rows_per_seq, b.hn,
+                      (__nv_bfloat16*)nullptr, H, c.llm_eps));
   HVX_LAUNCH_CHECK(e);
   const size_t sH = (size_t)n_seq * H;
   if (!tc) {
@@ -965,12 +1233,24 @@ static hvx_status llm_heads(hvx_engine* e, cudaStream_t st, LlmState* L, const S
   return HVX_OK;
 }
 
-static hvx_status launch_sampler(hvx_engine* e, cudaStream_t st, const SampArgs& a, int n_blocks) {
-  const size_t smem = (size_t)2 * a.vocab * sizeof(float);
+static hvx_status launch_sampler(hvx_engine* e, cudaStream_t st, SampArgs a, int n_seq) {
+  HVX_CHECK(a.vocab <= SAMP_THREADS * SAMP_PER, HVX_ERR_UNSUPPORTED, "sampler: vocab %d too large", a.vocab);
+  const size_t smem = (size_t)a.vocab * sizeof(float);
+  const size_t tab_bytes = (size_t)n_seq * a.head_k * (SAMP_TAB + a.vocab) * sizeof(float);
+  const size_t cnt_off = (tab_bytes + 255) & ~(size_t)255;
+  const bool grew = cnt_off + (size_t)n_seq * 4 > e->samp_ws.bytes;
+  uint8_t* w = (uint8_t*)e->samp_ws.get(cnt_off + (size_t)n_seq * 4 + 256);
+  HVX_CHECK(w, HVX_ERR_CUDA, "sampler: scratch allocation failed");
+  a.tables = (float*)w;
+  a.arrive = (int*)(w + cnt_off);
+  // arrival counters start at zero and every launch leaves them at zero; (re)initialise when the scratch moved
+  if (grew || e->samp_arrive != (void*)a.arrive) {
+    HVX_CUDA(cudaMemsetAsync(a.arrive, 0, (size_t)n_seq * 4, st));
+    e->samp_arrive = a.arrive;
+  }
   static bool attr = false;
-  if (!attr) { HVX_CUDA(cudaFuncSetAttribute(llm_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
-  HVX_CHECK(smem <= 160 * 1024, HVX_ERR_UNSUPPORTED, "sampler: vocab %d too large", a.vocab);
-  llm_sampler_kernel<<<n_blocks, 256, smem, st>>>(a);
+  if (!attr) { HVX_CUDA(cudaFuncSetAttribute(llm_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
+  HVX_CUDA(launch_pdl(llm_sampler_kernel, dim3(n_seq, a.head_k), dim3(SAMP_THREADS), smem, st, a));
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
 }
