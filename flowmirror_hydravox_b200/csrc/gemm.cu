@@ -76,6 +76,9 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 }
 
 // fused epilogue of one 32-column chunk of one output row: v = raw fp32 accumulators of columns [col0, col0+32)
+// MODE / ACT are compile-time: one kernel instance carries exactly one epilogue.  (With every mode inlined the kernel was
+// 21.6k SASS instructions and each tile's epilogue ran out of a cold instruction cache: ~25 us of fetch stalls per tile.)
+template <int MODE, int ACT>
 __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx, int col0, int N, const uint32_t* v,
                                           const float* pre = nullptr) {
       float f[32];
@@ -83,9 +86,9 @@ __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx,
       for (int j = 0; j < 32; j++) {
         float x = __uint_as_float(v[j]);
         if (epi.bias && col0 + j < N) x += __ldg(epi.bias + col0 + j);
-        f[j] = act_apply(x, epi.act);
+        f[j] = act_apply(x, ACT);
       }
-      if (epi.mode == EPI_BF16) {
+      if (MODE == EPI_BF16) {
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(epi.out) + (size_t)row * epi.ldo + col0;
         if (epi.lo_off) {
 #pragma unroll
@@ -104,7 +107,7 @@ __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx,
           #pragma unroll
           for (int j = 0; j < 32; j++) if (col0 + j < N) reinterpret_cast<uint16_t*>(o)[j] = tc::cvt16(f[j], epi.f16);
         }
-      } else if (epi.mode == EPI_F32) {
+      } else if (MODE == EPI_F32) {
         float* o = reinterpret_cast<float*>(epi.out) + (size_t)row * epi.ldo + col0;
         if (epi.resid) {
           const float* r = epi.resid + (size_t)row * epi.ldo + col0;
@@ -121,7 +124,7 @@ __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx,
             if (epi.lo_off) o2[epi.lo_off + j] = __float2bfloat16(f[j] - __bfloat162float(__float2bfloat16(f[j])));
           }
         }
-      } else if (epi.mode == EPI_RESID_GATE) {
+      } else if (MODE == EPI_RESID_GATE) {
         float* o = reinterpret_cast<float*>(epi.out) + (size_t)row * epi.ldo + col0;
         const float* g = epi.gate + (size_t)bidx * epi.gate_ld + col0;
         if (col0 + 32 <= N) {
@@ -137,11 +140,11 @@ __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx,
           #pragma unroll
           for (int j = 0; j < 32; j++) if (col0 + j < N) o[j] = fmaf(__ldg(g + j), f[j], o[j]);
         }
-      } else if (epi.mode == EPI_LLM_QKV) {
+      } else if (MODE == EPI_LLM_QKV) {
 #pragma unroll
         for (int j = 0; j < 32; j += 2)
           if (col0 + j < N) llm_qkv_store(epi.llm, row, col0 + j, f[j], f[j + 1]);
-      } else if (epi.mode == EPI_SWIGLU) {
+      } else if (MODE == EPI_SWIGLU) {
         uint16_t* o = reinterpret_cast<uint16_t*>(epi.out) + (size_t)row * epi.ldo + (col0 >> 1);
 #pragma unroll
         for (int j = 0; j < 32; j += 2)
@@ -150,7 +153,7 @@ __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx,
             o[j >> 1] = tc::cvt16(y, epi.f16);
             if (epi.lo_off) o[epi.lo_off + (j >> 1)] = tc::cvt16(y - __bfloat162float(__float2bfloat16(y)), 0);
           }
-      } else {  // EPI_QKV
+      } else if (MODE == EPI_QKV) {
         const int t = row - bidx * epi.T;       // rows_per_batch == T
         if (col0 < epi.n_qk) {
           const int dq = epi.n_qk >> 1;
@@ -184,7 +187,7 @@ __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx,
       }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MODE, int ACT>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N, int K,
                  GemmEpi epi, GemmAddr ad, int tiles_per_batch) {
@@ -264,7 +267,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       tc::tmem_ld_wait();
       const int col0 = n0 + c0;
       if (!row_ok || col0 >= N) continue;
-      epi_store(epi, row, bidx, col0, N, v);
+      epi_store<MODE, ACT>(epi, row, bidx, col0, N, v);
     }
   }
   tc::tc_fence_before();
@@ -289,6 +292,7 @@ struct PersistSmem {
 };
 
 constexpr int PERSIST_THREADS = 320;     // TMA warp, MMA warp, 8 epilogue warps
+template <int MODE, int ACT>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1)
 gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N, int K,
                     GemmEpi epi, GemmAddr ad, int tiles_m, int tiles_n) {
@@ -372,7 +376,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const int colh = nt * PBN + half * (PBN / 2);
       // the residual this tile updates does not depend on its accumulator: fetch it while the MMAs run
       float pre[PBN / 2];
-      const bool use_pre = epi.mode == EPI_RESID_GATE && row_ok && colh + PBN / 2 <= N;
+      const bool use_pre = MODE == EPI_RESID_GATE && row_ok && colh + PBN / 2 <= N;
       if (use_pre) {
         const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(epi.out) + (size_t)row * epi.ldo + colh);
 #pragma unroll
@@ -387,7 +391,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         tc::tmem_ld_wait();
         const int col0 = colh + c;
         if (!row_ok || col0 >= N) continue;
-        epi_store(epi, row, bidx, col0, N, v, use_pre ? &pre[c] : nullptr);
+        epi_store<MODE, ACT>(epi, row, bidx, col0, N, v, use_pre ? &pre[c] : nullptr);
       }
       tc::tc_fence_before();
       __syncwarp();
@@ -399,17 +403,62 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (warp == 1) { __syncwarp(); tc::tmem_dealloc(tmem_base, 2 * PBN); }
 }
 
-static hvx_status launch_gemm_persist(hvx_engine* e, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
-                                      int K, const GemmEpi& epi, const GemmAddr& ad) {
+template <int MODE, int ACT>
+static hvx_status launch_gemm_persist_t(hvx_engine* e, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
+                                        int K, const GemmEpi& epi, const GemmAddr& ad) {
   using S = PersistSmem;
   static bool attr_set = false;
   if (!attr_set) {
-    HVX_CUDA(cudaFuncSetAttribute(gemm_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    HVX_CUDA(cudaFuncSetAttribute(gemm_persist_kernel<MODE, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set = true;
   }
   const int tiles_m = cdiv(M, BM), tiles_n = cdiv(N, PBN);
   const int grid = std::min(tiles_m * tiles_n, e->sm_count);
-  gemm_persist_kernel<<<grid, PERSIST_THREADS, S::TOTAL, st>>>(ta, tb, M, N, K, epi, ad, tiles_m, tiles_n);
+  gemm_persist_kernel<MODE, ACT><<<grid, PERSIST_THREADS, S::TOTAL, st>>>(ta, tb, M, N, K, epi, ad, tiles_m, tiles_n);
+  HVX_LAUNCH_CHECK(e);
+  return HVX_OK;
+}
+
+// the (mode, activation) pairs the path uses; anything else is a programming error
+#define HVX_EPI_DISPATCH(CALL)                                                                   \
+  do {                                                                                           \
+    const int key = epi.mode * 8 + epi.act;                                                      \
+    switch (key) {                                                                               \
+      case EPI_BF16 * 8 + ACT_NONE: return CALL(EPI_BF16, ACT_NONE);                             \
+      case EPI_BF16 * 8 + ACT_GELU_TANH: return CALL(EPI_BF16, ACT_GELU_TANH);                   \
+      case EPI_BF16 * 8 + ACT_MISH: return CALL(EPI_BF16, ACT_MISH);                             \
+      case EPI_BF16 * 8 + ACT_LRELU: return CALL(EPI_BF16, ACT_LRELU);                           \
+      case EPI_F32 * 8 + ACT_NONE: return CALL(EPI_F32, ACT_NONE);                               \
+      case EPI_F32 * 8 + ACT_GELU_TANH: return CALL(EPI_F32, ACT_GELU_TANH);                     \
+      case EPI_F32 * 8 + ACT_MISH: return CALL(EPI_F32, ACT_MISH);                               \
+      case EPI_RESID_GATE * 8 + ACT_NONE: return CALL(EPI_RESID_GATE, ACT_NONE);                 \
+      case EPI_QKV * 8 + ACT_NONE: return CALL(EPI_QKV, ACT_NONE);                               \
+      case EPI_LLM_QKV * 8 + ACT_NONE: return CALL(EPI_LLM_QKV, ACT_NONE);                       \
+      case EPI_SWIGLU * 8 + ACT_NONE: return CALL(EPI_SWIGLU, ACT_NONE);                         \
+    }                                                                                            \
+    set_error("gemm: epilogue mode %d with activation %d is not instantiated", epi.mode, epi.act); \
+    return HVX_ERR_UNSUPPORTED;                                                                  \
+  } while (0)
+
+static hvx_status launch_gemm_persist(hvx_engine* e, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
+                                      int K, const GemmEpi& epi, const GemmAddr& ad) {
+#define PCALL(MD, AC) launch_gemm_persist_t<MD, AC>(e, st, ta, tb, M, N, K, epi, ad)
+  HVX_EPI_DISPATCH(PCALL);
+#undef PCALL
+}
+
+template <int BN, int STAGES, int MODE, int ACT>
+static hvx_status launch_gemm_t(hvx_engine* e, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
+                                int K, const GemmEpi& epi, const GemmAddr& ad) {
+  using S = GemmSmem<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    HVX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, MODE, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr_set = true;
+  }
+  const int tiles_per_batch = cdiv(ad.rows_per_batch, BM);
+  dim3 grid(cdiv(N, BN), tiles_per_batch * ad.n_batch);
+  gemm_bf16_kernel<BN, STAGES, MODE, ACT><<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, M, N, K, epi, ad, tiles_per_batch);
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
 }
@@ -417,17 +466,9 @@ static hvx_status launch_gemm_persist(hvx_engine* e, cudaStream_t st, const CUte
 template <int BN, int STAGES>
 static hvx_status launch_gemm(hvx_engine* e, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
                               int K, const GemmEpi& epi, const GemmAddr& ad) {
-  using S = GemmSmem<BN, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    HVX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr_set = true;
-  }
-  const int tiles_per_batch = cdiv(ad.rows_per_batch, BM);
-  dim3 grid(cdiv(N, BN), tiles_per_batch * ad.n_batch);
-  gemm_bf16_kernel<BN, STAGES><<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, M, N, K, epi, ad, tiles_per_batch);
-  HVX_LAUNCH_CHECK(e);
-  return HVX_OK;
+#define GCALL(MD, AC) launch_gemm_t<BN, STAGES, MD, AC>(e, st, ta, tb, M, N, K, epi, ad)
+  HVX_EPI_DISPATCH(GCALL);
+#undef GCALL
 }
 
 hvx_status gemm_bf16(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb,
@@ -446,7 +487,7 @@ hvx_status gemm_bf16(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* A, int
             "gemm: cuTensorMapEncodeTiled(A) failed");
   // big plain GEMMs (the DiT linears): persistent 128 x 256 tiles
   if (ad.n_batch == 1 && ad.kb_per_tap == 0 && ad.b_kb_mod == 0 && ad.a_col0 == 0 && ad.a_col_per_ntile == 0 && ad.a_row0 == 0 &&
-      N % PBN == 0 && cdiv(M, BM) * (N / PBN) >= e->sm_count / 2 && getenv("HVX_PERSIST_GEMM")) {   // opt-in: measured slower than 2 CTAs/SM of 128x128 (both L2-bound)
+      N % PBN == 0 && cdiv(M, BM) * (N / PBN) >= e->sm_count / 2 && !getenv("HVX_NO_PERSIST")) {
     HVX_CHECK(make_tmap_bf16_2d(&tb, B, N, kB, ldb, PBN, BK), HVX_ERR_CUDA, "gemm: cuTensorMapEncodeTiled(B) failed");
     return launch_gemm_persist(e, st, ta, tb, M, N, K, epi, ad);
   }

@@ -46,6 +46,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 // fp32 value as two bf16 halves: row[k] = hi, row[off_lo + k] = x - hi
@@ -68,6 +69,8 @@ struct GemvArgs {
   int N = 0, K = 0, mode = GEMV_PLAIN;
   int rows = 0;                                     // live rows (<= R); rows beyond are not written
   int kc = 0;                                       // activation chunk staged in shared memory (floats per row)
+  int slot_bytes = 0, n_slots = 0;                  // TMA-fed variant: weight ring geometry
+  unsigned long long* dbg = nullptr;                // optional timeline of CTA 0 (globaltimer ns), scripts/bench_llm_kernels.py
   // blockIdx.y batches independent problems (the MTP heads): element strides
   size_t sW = 0, sBias = 0, sNorm = 0, sX = 0, sOut = 0, sResid = 0;
   LlmQkvEpi qkv;
@@ -247,9 +250,9 @@ __global__ void __launch_bounds__(256) llm_gemv_kernel(GemvArgs a) {
 // shared-memory slots with 1-D bulk copies (cp.async.bulk) and starts doing so *before* griddepcontrol.wait, so
 // bytes keep arriving while the previous kernel drains and while the activations are staged and normalised.  Eight
 // consumer warps take the pairs of a landed slot round-robin and read their weights from shared memory.
-constexpr int GT_SLOT = 40 * 1024;     // 2 pairs at K=4864, 11 pairs at K=896
-constexpr int GT_NS = 3;
-constexpr int GT_CONS = 8;             // consumer warps
+constexpr int GT_SLOT = 40 * 1024;     // largest slot: 2 pairs at K=4864, 11 pairs at K=896
+constexpr int GT_NS = 3;               // most slots; the launcher sizes the ring to the CTA's share so two CTAs co-reside
+constexpr int GT_CONS = 16;            // consumer warps (8 warps + CTA co-residency measured slower: the pair loop, not the stream, is the critical path)
 constexpr int GT_KMAX = 5120;          // a pair (2 rows x K bf16) must fit a slot
 
 template <int R>
@@ -263,13 +266,16 @@ __global__ void __launch_bounds__((GT_CONS + 1) * 32, 1) llm_gemv_tma_kernel(Gem
   const float* x = a.x + by * a.sX;
   const __nv_bfloat16* W = a.W + by * a.sW;
   const float* nw = a.norm_w ? a.norm_w + by * a.sNorm : nullptr;
+  const bool dbg = a.dbg && blockIdx.x == 0 && by == 0 && tid == 0;
+  if (dbg) a.dbg[0] = gtime();
   uint8_t* ring = smraw;
-  float* sx = reinterpret_cast<float*>(smraw + GT_NS * GT_SLOT);      // [R][K]
+  const int SLOT = a.slot_bytes, NS = a.n_slots;
+  float* sx = reinterpret_cast<float*>(smraw + NS * SLOT);            // [R][K]
   float* snw = sx + R * K;                                            // [K]
   const int npairs = (a.N + 1) >> 1;
   const int ppc = (npairs + gridDim.x - 1) / gridDim.x;               // pairs per CTA (contiguous)
   const int p_begin = blockIdx.x * ppc, p_end = min(npairs, p_begin + ppc);
-  const int pps = GT_SLOT / (4 * K);                                  // pairs per slot
+  const int pps = SLOT / (4 * K);                                     // pairs per slot
   const int nslots = p_end > p_begin ? (p_end - p_begin + pps - 1) / pps : 0;
 
   if (tid == 0) {
@@ -283,13 +289,13 @@ __global__ void __launch_bounds__((GT_CONS + 1) * 32, 1) llm_gemv_tma_kernel(Gem
     // ---------------- producer: weights only, never waits for the previous kernel
     if (lane == 0) {
       for (int i = 0; i < nslots; i++) {
-        const int sl = i % GT_NS;
-        if (i >= GT_NS) tc::mbar_wait(&empty_bar[sl], ((i / GT_NS) - 1) & 1);
+        const int sl = i % NS;
+        if (i >= NS) tc::mbar_wait(&empty_bar[sl], ((i / NS) - 1) & 1);
         const int p0 = p_begin + i * pps;
         const int row0 = 2 * p0, row1 = min(a.N, 2 * min(p_end, p0 + pps));
         const uint32_t bytes = (uint32_t)(row1 - row0) * (uint32_t)K * 2u;
         tc::mbar_expect_tx(&full_bar[sl], bytes);
-        bulk_g2s(ring + sl * GT_SLOT, W + (size_t)row0 * K, bytes, &full_bar[sl]);
+        bulk_g2s(ring + sl * SLOT, W + (size_t)row0 * K, bytes, &full_bar[sl]);
       }
     }
     return;
@@ -297,12 +303,14 @@ __global__ void __launch_bounds__((GT_CONS + 1) * 32, 1) llm_gemv_tma_kernel(Gem
   // ---------------- consumers
   if (nw) for (int k = tid * 4; k < K; k += GT_CONS * 128) *reinterpret_cast<float4*>(&snw[k]) = __ldg(reinterpret_cast<const float4*>(nw + k));
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (dbg) a.dbg[1] = gtime();
   if (tid == 0) {
     tc::mbar_expect_tx(&x_bar, (uint32_t)(a.rows * K * 4));
     for (int r = 0; r < a.rows; r++) bulk_g2s(&sx[r * K], x + (size_t)r * a.ldx, (uint32_t)(K * 4), &x_bar);
   }
   for (int i = tid; i < (R - a.rows) * K; i += GT_CONS * 32) sx[a.rows * K + i] = 0.f;      // padding rows
   tc::mbar_wait(&x_bar, 0);
+  if (dbg) a.dbg[2] = gtime();
   if (nw) {
     float sc[R];
 #pragma unroll
@@ -327,26 +335,43 @@ __global__ void __launch_bounds__((GT_CONS + 1) * 32, 1) llm_gemv_tma_kernel(Gem
     }
   }
   asm volatile("bar.sync 1, %0;" ::"n"(GT_CONS * 32));
+  if (dbg) a.dbg[3] = gtime();
   const float* bias = a.bias ? a.bias + by * a.sBias : nullptr;
   float* out = a.out + by * a.sOut;
   const float* resid = a.resid ? a.resid + by * a.sResid : nullptr;
 
   for (int i = 0; i < nslots; i++) {
-    const int sl = i % GT_NS;
-    tc::mbar_wait(&full_bar[sl], (i / GT_NS) & 1);
+    const int sl = i % NS;
+    tc::mbar_wait(&full_bar[sl], (i / NS) & 1);
+    if (dbg && i < 3) a.dbg[4 + i] = gtime();
     const int p0 = p_begin + i * pps;
     const int np = min(pps, p_end - p0);
-    const __nv_bfloat16* ws = reinterpret_cast<const __nv_bfloat16*>(ring + sl * GT_SLOT);
-    for (int pi = warp; pi < np; pi += GT_CONS) {
+    const __nv_bfloat16* ws = reinterpret_cast<const __nv_bfloat16*>(ring + sl * SLOT);
+    // rotate the warp -> pair assignment from slot to slot so that warps without a pair in this slot move straight on
+    // to the next one (all slots of a small matrix have already landed)
+    for (int pi = (warp + i * 5) % GT_CONS; pi < np; pi += GT_CONS) {
       const int pair = p0 + pi, n0 = 2 * pair;
       const bool two = n0 + 1 < a.N;
       const __nv_bfloat16* w0 = ws + (size_t)(2 * pi) * K;
       const __nv_bfloat16* w1 = two ? w0 + K : w0;
-      float acc0[R], acc1[R];
+      float acc0[R], acc1[R], bcc0[R], bcc1[R];          // two independent chains per output (even / odd k-blocks)
 #pragma unroll
-      for (int r = 0; r < R; r++) { acc0[r] = 0.f; acc1[r] = 0.f; }
-#pragma unroll 2
-      for (int k = lane * 8; k < K; k += 256) {
+      for (int r = 0; r < R; r++) { acc0[r] = 0.f; acc1[r] = 0.f; bcc0[r] = 0.f; bcc1[r] = 0.f; }
+      int k = lane * 8;
+      for (; k + 256 < K; k += 512) {
+        const uint4 u0 = *reinterpret_cast<const uint4*>(w0 + k);
+        const uint4 u1 = *reinterpret_cast<const uint4*>(w1 + k);
+        const uint4 v0 = *reinterpret_cast<const uint4*>(w0 + k + 256);
+        const uint4 v1 = *reinterpret_cast<const uint4*>(w1 + k + 256);
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          gemv_fma8(acc0[r], u0, &sx[r * K + k]);
+          gemv_fma8(acc1[r], u1, &sx[r * K + k]);
+          gemv_fma8(bcc0[r], v0, &sx[r * K + k + 256]);
+          gemv_fma8(bcc1[r], v1, &sx[r * K + k + 256]);
+        }
+      }
+      if (k < K) {
         const uint4 u0 = *reinterpret_cast<const uint4*>(w0 + k);
         const uint4 u1 = *reinterpret_cast<const uint4*>(w1 + k);
 #pragma unroll
@@ -357,6 +382,7 @@ __global__ void __launch_bounds__((GT_CONS + 1) * 32, 1) llm_gemv_tma_kernel(Gem
       }
 #pragma unroll
       for (int r = 0; r < R; r++) {
+        acc0[r] += bcc0[r]; acc1[r] += bcc1[r];
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
           acc0[r] += __shfl_xor_sync(0xffffffffu, acc0[r], o);
@@ -384,6 +410,7 @@ __global__ void __launch_bounds__((GT_CONS + 1) * 32, 1) llm_gemv_tma_kernel(Gem
     __syncwarp();
     if (lane == 0) tc::mbar_arrive(&empty_bar[sl]);
   }
+  if (dbg) a.dbg[7] = gtime();
 }
 
 // ------------------------------------------------------------------ attention over the KV cache
@@ -396,7 +423,7 @@ struct AttnDecArgs {
   const SeqState* seqs = nullptr; int rows_per_seq = 1;   // decode; nullptr: prefill
   int seq0 = 0, pos0 = 0, n_rows = 0;               // prefill
   int splits = 1;
-  float* part = nullptr;                            // [row][q_head][split][66] partial (m, l, o[64])
+  float* part = nullptr;                            // [row][q_head][split][68] partial (m, l, -, -, o[64])
   int* counters = nullptr;                          // [row][kv_head]
   float* out = nullptr; __nv_bfloat16* out16 = nullptr; int ldo = 0;   // [rows][q_dim]
   float scale = 0.125f;
@@ -434,15 +461,18 @@ __global__ void __launch_bounds__(256) llm_attn_kernel(AttnDecArgs a) {
   const int per = (n_keys + a.splits - 1) / a.splits;
   const int k_begin = split * per, k_end = min(n_keys, k_begin + per);
   const int qh = kvh * a.group + g;
-  float qv[64];
+  // 4 lanes share a key (16 of the 64 dims each), 8 keys per warp iteration: the dot product needs two shuffles and
+  // the final merge of the 8 key slots three
+  const int sub = lane & 3, kslot = lane >> 2;
+  float qv[16];
   {
-    const float4* qp = reinterpret_cast<const float4*>(a.q + (size_t)row * a.ldq + qh * 64);
+    const float4* qp = reinterpret_cast<const float4*>(a.q + (size_t)row * a.ldq + qh * 64 + sub * 16);
 #pragma unroll
-    for (int i = 0; i < 16; i++) { const float4 t = qp[i]; qv[4 * i] = t.x * a.scale; qv[4 * i + 1] = t.y * a.scale; qv[4 * i + 2] = t.z * a.scale; qv[4 * i + 3] = t.w * a.scale; }
+    for (int i = 0; i < 4; i++) { const float4 t = qp[i]; qv[4 * i] = t.x * a.scale; qv[4 * i + 1] = t.y * a.scale; qv[4 * i + 2] = t.z * a.scale; qv[4 * i + 3] = t.w * a.scale; }
   }
-  float m = -INFINITY, l = 0.f, o[64];
+  float m = -INFINITY, l = 0.f, o[16];
 #pragma unroll
-  for (int i = 0; i < 64; i++) o[i] = 0.f;
+  for (int i = 0; i < 16; i++) o[i] = 0.f;
   const KT* kb = reinterpret_cast<const KT*>(a.kc) + (size_t)seq * a.seq_stride + (size_t)kvh * a.max_ctx * 64;
   const KT* vb = reinterpret_cast<const KT*>(a.vc) + (size_t)seq * a.seq_stride + (size_t)kvh * a.max_ctx * 64;
   constexpr int EPS = 16 / (int)sizeof(KT);         // elements per 16 B segment
@@ -455,81 +485,85 @@ __global__ void __launch_bounds__(256) llm_attn_kernel(AttnDecArgs a) {
       *reinterpret_cast<uint4*>(&sv[key * LD + seg * EPS]) = *reinterpret_cast<const uint4*>(vb + (size_t)(c0 + key) * 64 + seg * EPS);
     }
     __syncthreads();
-    for (int key = lane; key < nk; key += 32) {
-      float s = 0.f;
-      if constexpr (KV32) {
+    for (int k0 = 0; k0 < nk; k0 += 8) {
+      const int key = k0 + kslot;
+      const bool live = key < nk;
+      float kf[16], vf[16];
+      if (live) {
+        if constexpr (KV32) {
 #pragma unroll
-        for (int seg = 0; seg < 16; seg++) {
-          const float4 u = *reinterpret_cast<const float4*>(&sk[key * LD + seg * 4]);
-          s = fmaf(qv[seg * 4 + 0], u.x, s); s = fmaf(qv[seg * 4 + 1], u.y, s);
-          s = fmaf(qv[seg * 4 + 2], u.z, s); s = fmaf(qv[seg * 4 + 3], u.w, s);
+          for (int i = 0; i < 4; i++) {
+            const float4 u = *reinterpret_cast<const float4*>(&sk[key * LD + sub * 16 + 4 * i]);
+            const float4 w = *reinterpret_cast<const float4*>(&sv[key * LD + sub * 16 + 4 * i]);
+            kf[4 * i] = u.x; kf[4 * i + 1] = u.y; kf[4 * i + 2] = u.z; kf[4 * i + 3] = u.w;
+            vf[4 * i] = w.x; vf[4 * i + 1] = w.y; vf[4 * i + 2] = w.z; vf[4 * i + 3] = w.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 2; i++) {
+            const uint4 u = *reinterpret_cast<const uint4*>(&sk[key * LD + sub * 16 + 8 * i]);
+            const uint4 w = *reinterpret_cast<const uint4*>(&sv[key * LD + sub * 16 + 8 * i]);
+            kf[8 * i] = bf_lo(u.x); kf[8 * i + 1] = bf_hi(u.x); kf[8 * i + 2] = bf_lo(u.y); kf[8 * i + 3] = bf_hi(u.y);
+            kf[8 * i + 4] = bf_lo(u.z); kf[8 * i + 5] = bf_hi(u.z); kf[8 * i + 6] = bf_lo(u.w); kf[8 * i + 7] = bf_hi(u.w);
+            vf[8 * i] = bf_lo(w.x); vf[8 * i + 1] = bf_hi(w.x); vf[8 * i + 2] = bf_lo(w.y); vf[8 * i + 3] = bf_hi(w.y);
+            vf[8 * i + 4] = bf_lo(w.z); vf[8 * i + 5] = bf_hi(w.z); vf[8 * i + 6] = bf_lo(w.w); vf[8 * i + 7] = bf_hi(w.w);
+          }
         }
       } else {
 #pragma unroll
-        for (int seg = 0; seg < 8; seg++) {
-          const uint4 u = *reinterpret_cast<const uint4*>(&sk[key * LD + seg * 8]);
-          s = fmaf(qv[seg * 8 + 0], bf_lo(u.x), s); s = fmaf(qv[seg * 8 + 1], bf_hi(u.x), s);
-          s = fmaf(qv[seg * 8 + 2], bf_lo(u.y), s); s = fmaf(qv[seg * 8 + 3], bf_hi(u.y), s);
-          s = fmaf(qv[seg * 8 + 4], bf_lo(u.z), s); s = fmaf(qv[seg * 8 + 5], bf_hi(u.z), s);
-          s = fmaf(qv[seg * 8 + 6], bf_lo(u.w), s); s = fmaf(qv[seg * 8 + 7], bf_hi(u.w), s);
-        }
+        for (int i = 0; i < 16; i++) { kf[i] = 0.f; vf[i] = 0.f; }
       }
-      if (s > m) {
-        const float al = expf(m - s);
-        l *= al;
+      float sc = 0.f;
 #pragma unroll
-        for (int i = 0; i < 64; i++) o[i] *= al;
-        m = s;
-      }
-      const float p = expf(s - m);
-      l += p;
-      if constexpr (KV32) {
+      for (int i = 0; i < 16; i++) sc = fmaf(qv[i], kf[i], sc);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+      if (live) {
+        if (sc > m) {
+          const float al = expf(m - sc);
+          l *= al;
 #pragma unroll
-        for (int seg = 0; seg < 16; seg++) {
-          const float4 u = *reinterpret_cast<const float4*>(&sv[key * LD + seg * 4]);
-          o[seg * 4 + 0] = fmaf(p, u.x, o[seg * 4 + 0]); o[seg * 4 + 1] = fmaf(p, u.y, o[seg * 4 + 1]);
-          o[seg * 4 + 2] = fmaf(p, u.z, o[seg * 4 + 2]); o[seg * 4 + 3] = fmaf(p, u.w, o[seg * 4 + 3]);
+          for (int i = 0; i < 16; i++) o[i] *= al;
+          m = sc;
         }
-      } else {
+        const float pw = expf(sc - m);
+        l += pw;
 #pragma unroll
-        for (int seg = 0; seg < 8; seg++) {
-          const uint4 u = *reinterpret_cast<const uint4*>(&sv[key * LD + seg * 8]);
-          o[seg * 8 + 0] = fmaf(p, bf_lo(u.x), o[seg * 8 + 0]); o[seg * 8 + 1] = fmaf(p, bf_hi(u.x), o[seg * 8 + 1]);
-          o[seg * 8 + 2] = fmaf(p, bf_lo(u.y), o[seg * 8 + 2]); o[seg * 8 + 3] = fmaf(p, bf_hi(u.y), o[seg * 8 + 3]);
-          o[seg * 8 + 4] = fmaf(p, bf_lo(u.z), o[seg * 8 + 4]); o[seg * 8 + 5] = fmaf(p, bf_hi(u.z), o[seg * 8 + 5]);
-          o[seg * 8 + 6] = fmaf(p, bf_lo(u.w), o[seg * 8 + 6]); o[seg * 8 + 7] = fmaf(p, bf_hi(u.w), o[seg * 8 + 7]);
-        }
+        for (int i = 0; i < 16; i++) o[i] = fmaf(pw, vf[i], o[i]);
       }
     }
   }
-  // merge the 32 lanes
+  // merge the 8 key slots (lanes with equal `sub`)
   float M = m;
-  for (int s = 16; s; s >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, s));
+  for (int sft = 4; sft < 32; sft <<= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, sft));
   const float wgt = (m == -INFINITY) ? 0.f : expf(m - M);
   float L = l * wgt;
-  for (int s = 16; s; s >>= 1) L += __shfl_xor_sync(0xffffffffu, L, s);
+  for (int sft = 4; sft < 32; sft <<= 1) L += __shfl_xor_sync(0xffffffffu, L, sft);
 #pragma unroll
-  for (int i = 0; i < 64; i++) {
+  for (int i = 0; i < 16; i++) {
     float v = o[i] * wgt;
-    for (int s = 16; s; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    for (int sft = 4; sft < 32; sft <<= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
     o[i] = v;
   }
   const int q_heads = a.kv_heads * a.group;
-  // lane i keeps o[i] and o[32+i] (static indexing only, so o[] stays in registers)
-  float o_lo = 0.f, o_hi = 0.f;
-#pragma unroll
-  for (int i = 0; i < 32; i++) { if (lane == i) { o_lo = o[i]; o_hi = o[32 + i]; } }
+  // lanes 0..3 (kslot 0) now hold dims [16*sub, 16*sub+16)
   if (a.splits == 1) {
-    const float inv = 1.0f / L;
-    if (a.out) { a.out[(size_t)row * a.ldo + qh * 64 + lane] = o_lo * inv; a.out[(size_t)row * a.ldo + qh * 64 + 32 + lane] = o_hi * inv; }
-    if (a.out16) {
-      store_split(a.out16 + (size_t)row * 2 * a.ldo, a.ldo, qh * 64 + lane, o_lo * inv);
-      store_split(a.out16 + (size_t)row * 2 * a.ldo, a.ldo, qh * 64 + 32 + lane, o_hi * inv);
+    if (kslot == 0) {
+      const float inv = 1.0f / L;
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const float y = o[i] * inv;
+        if (a.out) a.out[(size_t)row * a.ldo + qh * 64 + sub * 16 + i] = y;
+        if (a.out16) store_split(a.out16 + (size_t)row * 2 * a.ldo, a.ldo, qh * 64 + sub * 16 + i, y);
+      }
     }
     return;
   }
-  float* pp = a.part + (((size_t)row * q_heads + qh) * a.splits + split) * 66;
-  pp[2 + lane] = o_lo; pp[2 + 32 + lane] = o_hi;
+  float* pp = a.part + (((size_t)row * q_heads + qh) * a.splits + split) * 68;
+  if (kslot == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) *reinterpret_cast<float4*>(&pp[4 + sub * 16 + 4 * i]) = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+  }
   if (lane == 0) { pp[0] = M; pp[1] = L; }
   __threadfence();
   __syncthreads();
@@ -538,16 +572,16 @@ __global__ void __launch_bounds__(256) llm_attn_kernel(AttnDecArgs a) {
   if (!s_last) return;
   __threadfence();
   // last block for this (row, kv head): merge the split partials of its heads
-  const float* pb = a.part + ((size_t)row * q_heads + qh) * a.splits * 66;
+  const float* pb = a.part + ((size_t)row * q_heads + qh) * a.splits * 68;
   float Mx = -INFINITY;
-  for (int s = 0; s < a.splits; s++) Mx = fmaxf(Mx, __ldcg(pb + s * 66));
+  for (int s = 0; s < a.splits; s++) Mx = fmaxf(Mx, __ldcg(pb + s * 68));
   float Ls = 0.f, a_lo = 0.f, a_hi = 0.f;
   for (int s = 0; s < a.splits; s++) {
-    const float ms = __ldcg(pb + s * 66);
+    const float ms = __ldcg(pb + s * 68);
     const float w = (ms == -INFINITY) ? 0.f : expf(ms - Mx);
-    Ls += __ldcg(pb + s * 66 + 1) * w;
-    a_lo += __ldcg(pb + s * 66 + 2 + lane) * w;
-    a_hi += __ldcg(pb + s * 66 + 34 + lane) * w;
+    Ls += __ldcg(pb + s * 68 + 1) * w;
+    a_lo += __ldcg(pb + s * 68 + 4 + lane) * w;
+    a_hi += __ldcg(pb + s * 68 + 36 + lane) * w;
   }
   const float inv = 1.0f / Ls;
   if (a.out) { a.out[(size_t)row * a.ldo + qh * 64 + lane] = a_lo * inv; a.out[(size_t)row * a.ldo + qh * 64 + 32 + lane] = a_hi * inv; }
@@ -974,17 +1008,29 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 }
 
 template <int R>
-static hvx_status launch_gemv_tma(hvx_engine* e, cudaStream_t st, const GemvArgs& a, int n_batch, size_t smem) {
+static hvx_status launch_gemv_tma(hvx_engine* e, cudaStream_t st, GemvArgs a, int n_batch) {
   static bool attr = false;
   if (!attr) { HVX_CUDA(cudaFuncSetAttribute(llm_gemv_tma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
   const int pairs = (a.N + 1) / 2;
   // one CTA per SM (all of them request bytes concurrently), each with a contiguous range of pairs
   const int ctas = std::max(1, std::min(e->sm_count / n_batch, pairs));
+  // ring sized to the CTA's share of W (whole pairs per slot), capped so that two CTAs fit one SM: the next kernel's
+  // CTA must be able to become resident (and prefetch its weights) while this one still computes
+  const int ppc = cdiv(pairs, ctas);
+  const size_t pair_bytes = (size_t)4 * a.K;
+  const size_t x_bytes = ((size_t)R * a.K + (a.norm_w ? a.K : 0)) * sizeof(float) + 128;
+  const size_t budget = x_bytes < 100 * 1024 ? 108 * 1024 - x_bytes : 216 * 1024 - x_bytes;
+  size_t slot = std::min((size_t)GT_SLOT / pair_bytes, (size_t)ppc) * pair_bytes;        // whole pairs, at most the share
+  slot = std::max(slot, pair_bytes);
+  int ns = (int)std::min((size_t)GT_NS, std::max((size_t)1, budget / slot));
+  ns = std::min(ns, cdiv(ppc, (int)(slot / pair_bytes)));
+  HVX_CHECK(slot * ns + x_bytes <= 220 * 1024, HVX_ERR_UNSUPPORTED, "gemv: shared memory budget exceeded (K=%d R=%d)", a.K, R);
+  a.slot_bytes = (int)slot; a.n_slots = ns;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(ctas, n_batch, 1);
   cfg.blockDim = dim3((GT_CONS + 1) * 32, 1, 1);
-  cfg.dynamicSmemBytes = smem;
+  cfg.dynamicSmemBytes = slot * ns + x_bytes;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1000,13 +1046,13 @@ static hvx_status launch_gemv(hvx_engine* e, cudaStream_t st, GemvArgs a, int R,
   a.rows = R;
   {
     const int Rt0 = R <= 1 ? 1 : R <= 2 ? 2 : R <= 4 ? 4 : 8;
-    const size_t smem_t = (size_t)GT_NS * GT_SLOT + ((size_t)Rt0 * a.K + (a.norm_w ? a.K : 0)) * sizeof(float) + 128;
-    if (a.K <= GT_KMAX && a.K % 8 == 0 && smem_t <= 220 * 1024 && !getenv("HVX_NO_TMA_GEMV")) {
+    const size_t x_bytes = ((size_t)Rt0 * a.K + (a.norm_w ? a.K : 0)) * sizeof(float) + 128;
+    if (a.K <= GT_KMAX && a.K % 8 == 0 && x_bytes + (size_t)4 * a.K <= 216 * 1024 && !getenv("HVX_NO_TMA_GEMV")) {
       switch (Rt0) {
-        case 1: return launch_gemv_tma<1>(e, st, a, n_batch, smem_t);
-        case 2: return launch_gemv_tma<2>(e, st, a, n_batch, smem_t);
-        case 4: return launch_gemv_tma<4>(e, st, a, n_batch, smem_t);
-        default: return launch_gemv_tma<8>(e, st, a, n_batch, smem_t);
+        case 1: return launch_gemv_tma<1>(e, st, a, n_batch);
+        case 2: return launch_gemv_tma<2>(e, st, a, n_batch);
+        case 4: return launch_gemv_tma<4>(e, st, a, n_batch);
+        default: return launch_gemv_tma<8>(e, st, a, n_batch);
       }
     }
   }
@@ -1085,7 +1131,7 @@ static hvx_status llm_bufs(hvx_engine* e, LlmState* L, DevBuf& buf, int rows, in
   const size_t o_h = take(rp * H * 4), o_q = take(rp * H * 4), o_att = take(rp * H * 4), o_act = take(rp * I * 4);
   const size_t o_hn = take(sp * H * 4), o_mv = take(head_k * sp * H * 4), o_mh1 = take(head_k * sp * H * 4);
   const size_t o_mact = take(head_k * sp * MI * 4), o_mo = take(head_k * sp * H * 4), o_log = take(head_k * sp * V * 4);
-  const size_t o_part = take((size_t)rows * c.llm_q_heads * splits * 66 * 4), o_cnt = take((size_t)rows * c.llm_kv_heads * 4);
+  const size_t o_part = take((size_t)rows * c.llm_q_heads * splits * 68 * 4), o_cnt = take((size_t)rows * c.llm_kv_heads * 4);
   const size_t o_x16 = take(rp * H * 4), o_att16 = take(rp * H * 4), o_act16 = take(std::max(rp * I, sp * MI) * 4);
   const size_t o_hn16 = take(256), o_m16 = take(sp * H * 4);        // split bf16 [hi | lo] rows
   const bool grew = off > buf.bytes;
@@ -1438,3 +1484,79 @@ extern "C" hvx_status hvx_sample(hvx_engine* e, const float* logp, int n_heads, 
   return launch_sampler(e, (cudaStream_t)stream, sa, 1);
 }
 
+
+// Kernel-class timing for bench.py's roofline: runs one class of decode-step kernels back to back on the engine's own
+// stream (same launch path as the decode graph: PDL, persistent grids) over the real weights, CUDA-event timed.
+//   which: 0 whole step without sampler, 1 qkv gemv, 2 attention, 3 o-proj gemv, 4 gate-up gemv, 5 down gemv, 6 MTP heads + logits
+// ms_out[0] = milliseconds per repetition (one repetition = all layers' kernels of that class)
+extern "C" hvx_status hvx_llm_bench_kernels(hvx_engine* e, int n_seq, int head_k, int ctx, int which, int reps, float* ms_out) {
+  HVX_CHECK(e && e->llm && ms_out && reps >= 1, HVX_ERR_ARG, "llm_bench_kernels: bad argument");
+  const hvx_config& c = e->cfg;
+  HVX_CHECK(n_seq >= 1 && n_seq <= c.llm_max_seqs && n_seq * head_k <= 8 && ctx + head_k < c.llm_max_ctx, HVX_ERR_ARG, "llm_bench_kernels: bad shape");
+  LlmState* L = e->llm;
+  cudaStream_t st = L->own;
+  const int rows = n_seq * head_k, H = c.llm_hidden, I = c.llm_inter, NQKV = (c.llm_q_heads + 2 * c.llm_kv_heads) * 64;
+  const int splits = attn_splits(e->sm_count, rows, c.llm_kv_heads);
+  StepBufs b;
+  hvx_status rc;
+  if ((rc = llm_bufs(e, L, L->ws, rows, n_seq, head_k, splits, &b, st))) return rc;
+  std::vector<SeqState> hs(n_seq);
+  for (auto& x : hs) { memset(&x, 0, sizeof(x)); x.ctx = ctx; x.n_new = head_k; x.ctx_add = 0; x.max_len = 1 << 30; }
+  HVX_CUDA(cudaMemcpyAsync(L->seqs, hs.data(), sizeof(SeqState) * n_seq, cudaMemcpyHostToDevice, st));
+  HVX_CUDA(cudaStreamSynchronize(st));
+  cudaEvent_t e0, e1;
+  HVX_CUDA(cudaEventCreate(&e0)); HVX_CUDA(cudaEventCreate(&e1));
+  unsigned long long* dbg_dev = nullptr;
+  if (which == 4 && getenv("HVX_GEMV_TIMELINE")) { HVX_CUDA(cudaMalloc(&dbg_dev, 64 * 8 * 8)); HVX_CUDA(cudaMemset(dbg_dev, 0, 64 * 8 * 8)); }
+  auto body = [&]() -> hvx_status {
+    if (which == 0) {
+      if ((rc = llm_layers(e, st, L, b, rows, L->seqs, head_k, 0, 0, splits))) return rc;
+      return llm_heads(e, st, L, b, n_seq, head_k, head_k);
+    }
+    if (which == 6) return llm_heads(e, st, L, b, n_seq, head_k, head_k);
+    for (int l = 0; l < c.llm_layers; l++) {
+      const LlmLayer& y = L->layer[l];
+      if (which == 1) {
+        GemvArgs g; g.x = b.h; g.ldx = H; g.W = y.qkv_w; g.bias = y.qkv_b; g.norm_w = y.ln1; g.eps = c.llm_eps; g.N = NQKV; g.K = H;
+        g.mode = GEMV_QKV; g.qkv = make_qkv(e, L, l, b.q, L->seqs, head_k, 0, 0, rows);
+        if ((rc = launch_gemv(e, st, g, rows))) return rc;
+      } else if (which == 2) {
+        if ((rc = launch_attn(e, st, L, l, b, rows, L->seqs, head_k, 0, 0, splits, false))) return rc;
+      } else if (which == 3) {
+        GemvArgs o; o.x = b.att; o.ldx = H; o.W = y.o_w; o.N = H; o.K = H; o.out = b.h; o.ldo = H; o.resid = b.h; o.ldr = H;
+        if ((rc = launch_gemv(e, st, o, rows))) return rc;
+      } else if (which == 4) {
+        GemvArgs u; u.x = b.h; u.ldx = H; u.W = y.gu_w; u.norm_w = y.ln2; u.eps = c.llm_eps; u.N = 2 * I; u.K = H; u.mode = GEMV_SWIGLU;
+        u.out = b.act; u.ldo = I;
+        u.dbg = dbg_dev ? dbg_dev + (size_t)l * 8 : nullptr;
+        if ((rc = launch_gemv(e, st, u, rows))) return rc;
+      } else if (which == 5) {
+        GemvArgs d; d.x = b.act; d.ldx = I; d.W = y.down_w; d.N = H; d.K = I; d.out = b.q; d.ldo = H; d.resid = b.h; d.ldr = H;
+        if ((rc = launch_gemv(e, st, d, rows))) return rc;
+      }
+    }
+    return HVX_OK;
+  };
+  if ((rc = body())) return rc;                       // warm-up
+  HVX_CUDA(cudaEventRecord(e0, st));
+  for (int i = 0; i < reps; i++) if ((rc = body())) return rc;
+  HVX_CUDA(cudaEventRecord(e1, st));
+  HVX_CUDA(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  ms_out[0] = ms / reps;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (dbg_dev) {
+    unsigned long long h[64 * 8];
+    cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
+    for (int l = 0; l < 6; l++) {
+      fprintf(stderr, "[gemv timeline layer %d] start %llu ns; +wait %llu  +x %llu  +norm %llu  +slot0 %llu  +slot1 %llu  +slot2 %llu  +end %llu   (next start +%llu)\n", l,
+              h[l * 8], h[l * 8 + 1] - h[l * 8], h[l * 8 + 2] - h[l * 8], h[l * 8 + 3] - h[l * 8], h[l * 8 + 4] - h[l * 8],
+              h[l * 8 + 5] > h[l * 8] ? h[l * 8 + 5] - h[l * 8] : 0, h[l * 8 + 6] > h[l * 8] ? h[l * 8 + 6] - h[l * 8] : 0, h[l * 8 + 7] - h[l * 8],
+              h[(l + 1) * 8] - h[l * 8]);
+    }
+    cudaFree(dbg_dev);
+  }
+  if (L->graph) { cudaGraphExecDestroy(L->graph); L->graph = nullptr; }
+  return HVX_OK;
+}

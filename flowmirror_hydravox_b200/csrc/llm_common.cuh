@@ -39,6 +39,9 @@ struct LlmQkvEpi {
   int n_rows = 0;                               // valid rows (row slots beyond are padding)
 };
 
+// one out-of-line copy of the accurate sincosf (its slow path is ~100 instructions; 16 inlined copies per chunk bloat the epilogue)
+static __device__ __noinline__ void sincos_noinline(float a, float* sn, float* cs) { sincosf(a, sn, cs); }
+
 // store the pair (n, n+1) (n even) of row `row`
 __device__ __forceinline__ void llm_qkv_store(const LlmQkvEpi& q, int row, int n, float v0, float v1) {
   int seq, pos;
@@ -60,7 +63,7 @@ __device__ __forceinline__ void llm_qkv_store(const LlmQkvEpi& q, int row, int n
     const int i = (n & 63) >> 1;
     const float a = (float)pos * q.inv_freq[i];
     float sn, cs;
-    sincosf(a, &sn, &cs);
+    sincos_noinline(a, &sn, &cs);
     const float r0 = v0 * cs - v1 * sn;
     const float r1 = v1 * cs + v0 * sn;
     v0 = r0; v1 = r1;

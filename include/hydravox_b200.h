@@ -154,6 +154,11 @@ hvx_status hvx_gemm_bf16(hvx_engine* e, const void* A_dev, const void* B_dev, co
 hvx_status hvx_attention_bf16(hvx_engine* e, const void* qk_dev, const void* vt_dev, int vt_ld, void* out_dev,
                               int B, int T, int H, int chunk, void* stream);
 
+/* bench.py roofline helper: one class of decode-step kernels (0 whole step w/o sampler, 1 qkv, 2 attention, 3 o-proj,
+ * 4 gate-up, 5 down, 6 MTP heads + logits) repeated `reps` times on the engine's stream, CUDA-event timed;
+ * ms_out[0] = ms per repetition (all layers' launches of that class). */
+hvx_status hvx_llm_bench_kernels(hvx_engine* e, int n_seq, int head_k, int ctx, int which, int reps, float* ms_out);
+
 /* bookkeeping for bench.py: number of kernels this library has launched since creation. */
 int64_t hvx_kernel_launches(hvx_engine* e);
 
