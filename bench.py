@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--cfm-steps", type=int, default=25)
     ap.add_argument("--ratio", type=float, default=8.0, help="speech tokens per text token (min=max, SURVEY 8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-tokens", type=int, default=32, help="speech tokens in the CPU baseline sample")
+    ap.add_argument("--cpu-tokens", type=int, default=128, help="speech tokens in the CPU baseline sample (~10-20 s of CPU work)")
     return ap.parse_args()
 
 
@@ -281,11 +281,35 @@ def native_arm(a):
     flow_tf = flow_nfe_flops(fd, T) * a.cfm_steps * a.batch * a.steps / (stage_acc["flow"] / 1e3) / 1e12
     hift_tf = 2 * 336.9e6 * 2 * n_tok * a.batch * a.steps / (stage_acc["hift"] / 1e3) / 1e12
     tot = sum(stage_acc.values())
-    roof = {"bound": "hbm", "achieved": llm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": llm_gbs / hbm_peak, "traffic": None,
-            "kernel": "llm decode step (llm_gemv_kernel weight stream + KV attention), stage-level: algorithmic bytes per step x steps / "
-                      "device time of the whole LLM stage incl. prefill and launch gaps",
-            "peak_source": peak_src,
-            "stages": {"llm": {"share": stage_acc["llm"] / tot, "bound": "hbm", "achieved_gbs": llm_gbs, "frac": llm_gbs / hbm_peak},
+    # dominant kernel = llm_gemv_tma_kernel (the decode linears' weight stream; share of the step in profiles/): each
+    # class of its launches (24 layers back to back, same PDL launch path as the decode graph) is CUDA-event timed on
+    # the engine's stream right after the timed region; achieved = bf16 weight bytes of those launches / that time
+    import ctypes as C
+    ms1 = (C.c_float * 1)()
+    H, I, QKV = ld.hidden, ld.inter, (ld.q_heads + 2 * ld.kv_heads) * ld.head_dim
+    classes = {"qkv": (1, 2.0 * QKV * H), "o_proj": (3, 2.0 * H * H), "gate_up": (4, 2.0 * 2 * I * H), "down": (5, 2.0 * H * I)}
+    kern, kb, kt = {}, 0.0, 0.0
+    rows = a.batch * a.head_k
+    if rows <= 8:
+        for name, (which, nbytes) in classes.items():
+            L.check(L.lib().hvx_llm_bench_kernels(mm.engine.h, a.batch, a.head_k, int(ctx_avg), which, 10, ms1))
+            us = ms1[0] * 1e3 / ld.layers
+            kern[name] = {"us_per_launch": us, "bytes_per_launch": nbytes, "gbs": nbytes / us / 1e3}
+            kb += nbytes * ld.layers
+            kt += ms1[0] * 1e-3
+        L.check(L.lib().hvx_llm_bench_kernels(mm.engine.h, a.batch, a.head_k, int(ctx_avg), 2, 10, ms1))
+        kern["kv_attention"] = {"us_per_launch": ms1[0] * 1e3 / ld.layers}
+        L.check(L.lib().hvx_llm_bench_kernels(mm.engine.h, a.batch, a.head_k, int(ctx_avg), 0, 10, ms1))
+        kern["whole_decode_step_no_sampler_us"] = ms1[0] * 1e3
+    gemv_gbs = kb / kt / 1e9 if kt else None
+    roof = {"bound": "hbm", "achieved": gemv_gbs if gemv_gbs else llm_gbs, "peak": hbm_peak, "unit": "GB/s",
+            "frac": (gemv_gbs if gemv_gbs else llm_gbs) / hbm_peak, "traffic": 8.72e6 + 3.4e6,
+            "kernel": "llm_gemv_tma_kernel<R> (decode linears): bf16 weight bytes of the 96 per-step launches / their CUDA-event time, "
+                      "measured per class back to back on the engine stream after the timed region; traffic = dram read+write of the "
+                      "gate_up launch from profiles/r1_ncu_full_summary.txt (algorithmic 8.72 MB)",
+            "peak_source": peak_src, "per_class": kern,
+            "stages": {"llm": {"share": stage_acc["llm"] / tot, "bound": "hbm", "achieved_gbs": llm_gbs, "frac": llm_gbs / hbm_peak,
+                               "note": "algorithmic bytes per decode step x steps / device time of the whole LLM stage (prefill, sampler, launch gaps included)"},
                        "flow": {"share": stage_acc["flow"] / tot, "bound": "tensor", "achieved_tflops": flow_tf, "frac": flow_tf / tf_peak},
                        "hift": {"share": stage_acc["hift"] / tot, "bound": "fp32 cuda cores (algorithmic conv flops)", "achieved_tflops": hift_tf}}}
     line = {"metric": "speech_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),

@@ -30,7 +30,7 @@
 namespace hvx {
 
 constexpr int GEMV_KC = 2048;          // activation chunk (floats per row) staged in shared memory
-constexpr int ATT_KEYS = 64;           // keys per shared-memory chunk
+constexpr int ATT_KEYS = 128;          // keys per shared-memory chunk (bf16 cache; 64 for the fp32 cache: static smem limit)
 constexpr int ATT_LD = 72;             // padded row (bf16 elements): 144 B stride -> conflict-free 16 B reads
 constexpr int ATT_LD32 = 68;           // fp32 cache: 272 B stride
 constexpr int SAMP_MAXK = 64;          // top_k cap (UI slider goes to 50)
@@ -437,8 +437,9 @@ __global__ void __launch_bounds__(256) llm_attn_kernel(AttnDecArgs a) {
   using KT = typename std::conditional<KV32, float, __nv_bfloat16>::type;
   constexpr int LD = KV32 ? ATT_LD32 : ATT_LD;      // smem row stride in elements
   constexpr int SEGS = KV32 ? 16 : 8;               // 16 B segments per 64-element row
-  __shared__ __align__(16) KT sk[ATT_KEYS * LD];
-  __shared__ __align__(16) KT sv[ATT_KEYS * LD];
+  constexpr int CHUNK = KV32 ? ATT_KEYS / 2 : ATT_KEYS;
+  __shared__ __align__(16) KT sk[CHUNK * LD];
+  __shared__ __align__(16) KT sv[CHUNK * LD];
   __shared__ int s_last;
   asm volatile("griddepcontrol.launch_dependents;");
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -476,8 +477,8 @@ __global__ void __launch_bounds__(256) llm_attn_kernel(AttnDecArgs a) {
   const KT* kb = reinterpret_cast<const KT*>(a.kc) + (size_t)seq * a.seq_stride + (size_t)kvh * a.max_ctx * 64;
   const KT* vb = reinterpret_cast<const KT*>(a.vc) + (size_t)seq * a.seq_stride + (size_t)kvh * a.max_ctx * 64;
   constexpr int EPS = 16 / (int)sizeof(KT);         // elements per 16 B segment
-  for (int c0 = k_begin; c0 < k_end; c0 += ATT_KEYS) {
-    const int nk = min(ATT_KEYS, k_end - c0);
+  for (int c0 = k_begin; c0 < k_end; c0 += CHUNK) {
+    const int nk = min(CHUNK, k_end - c0);
     __syncthreads();
     for (int i = tid; i < nk * SEGS; i += blockDim.x) {
       const int key = i / SEGS, seg = i - key * SEGS;
