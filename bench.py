@@ -290,7 +290,7 @@ def native_arm(a):
     classes = {"qkv": (1, 2.0 * QKV * H), "o_proj": (3, 2.0 * H * H), "gate_up": (4, 2.0 * 2 * I * H), "down": (5, 2.0 * H * I)}
     kern, kb, kt = {}, 0.0, 0.0
     rows = a.batch * a.head_k
-    if rows <= 8:
+    if rows <= 32:
         for name, (which, nbytes) in classes.items():
             L.check(L.lib().hvx_llm_bench_kernels(mm.engine.h, a.batch, a.head_k, int(ctx_avg), which, 10, ms1))
             us = ms1[0] * 1e3 / ld.layers
@@ -317,7 +317,7 @@ def native_arm(a):
             "dtype": "bf16 weights / fp32 accumulate (llm), fp16 operands / fp32 accumulate (flow), fp32 (hift)", "data": "synthetic",
             "config": {"workload": workload_name(a), "l2": "256 MiB flush between timed steps; per-step weight traffic (2.3 GB) exceeds L2",
                        "utterances_per_gpu": a.batch},
-            "rtf": 25.0 * world / value if value else None,
+            "rtf": 25.0 / value if value else None, "rtf_per_gpu": 25.0 * world / value if value else None,
             "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": mm.h2d_bytes, "d2h_bytes_per_step": mm.d2h_bytes,
                     "ms_per_step": ms_e2e / a.steps, "rtf": 25.0 * world / e2e if e2e else None,
                     "stage_ms_per_step": {k: v / a.steps for k, v in stage_acc.items()}},

@@ -68,6 +68,7 @@ struct GemvArgs {
   const float* resid = nullptr; int ldr = 0;        // out = resid + y (resid may alias out)
   int N = 0, K = 0, mode = GEMV_PLAIN;
   int rows = 0;                                     // live rows (<= R); rows beyond are not written
+  int row0 = 0;                                     // global row slot of row 0 (row groups of 8, see launch_gemv)
   int kc = 0;                                       // activation chunk staged in shared memory (floats per row)
   int slot_bytes = 0, n_slots = 0;                  // TMA-fed variant: weight ring geometry
   unsigned long long* dbg = nullptr;                // optional timeline of CTA 0 (globaltimer ns), scripts/bench_llm_kernels.py
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(256) llm_gemv_kernel(GemvArgs a) {
         y0 += bias ? bias[n0] : 0.f;
         y1 += (bias && n0 + 1 < a.N) ? bias[n0 + 1] : 0.f;
         if (a.mode == GEMV_QKV) {
-          llm_qkv_store(a.qkv, r, n0, y0, y1);
+          llm_qkv_store(a.qkv, a.row0 + r, n0, y0, y1);
         } else if (a.mode == GEMV_SWIGLU) {
           out[(size_t)r * a.ldo + pair] = (y0 / (1.0f + expf(-y0))) * y1;
         } else {
@@ -397,7 +398,7 @@ __global__ void __launch_bounds__((GT_CONS + 1) * 32, 1) llm_gemv_tma_kernel(Gem
         y0 += bias ? bias[n0] : 0.f;
         y1 += (bias && two) ? bias[n0 + 1] : 0.f;
         if (a.mode == GEMV_QKV) {
-          llm_qkv_store(a.qkv, r, n0, y0, y1);
+          llm_qkv_store(a.qkv, a.row0 + r, n0, y0, y1);
         } else if (a.mode == GEMV_SWIGLU) {
           out[(size_t)r * a.ldo + pair] = (y0 / (1.0f + expf(-y0))) * y1;
         } else {
@@ -1043,7 +1044,7 @@ static hvx_status launch_gemv_tma(hvx_engine* e, cudaStream_t st, GemvArgs a, in
   return HVX_OK;
 }
 
-static hvx_status launch_gemv(hvx_engine* e, cudaStream_t st, GemvArgs a, int R, int n_batch = 1) {
+static hvx_status launch_gemv8(hvx_engine* e, cudaStream_t st, GemvArgs a, int R, int n_batch) {
   a.rows = R;
   {
     const int Rt0 = R <= 1 ? 1 : R <= 2 ? 2 : R <= 4 ? 4 : 8;
@@ -1116,6 +1117,22 @@ static hvx_status launch_gemv(hvx_engine* e, cudaStream_t st, GemvArgs a, int R,
   return HVX_OK;
 }
 
+constexpr int GEMV_MAX_ROWS = 32;      // up to 4 weight passes of 8 rows beat the tensor-core path (few CTAs at small N)
+
+// rows > 8: one pass over the weights per group of 8 rows
+static hvx_status launch_gemv(hvx_engine* e, cudaStream_t st, GemvArgs a, int R, int n_batch = 1) {
+  for (int r0 = 0; r0 < R; r0 += 8) {
+    GemvArgs g = a;
+    g.x = a.x + (size_t)r0 * a.ldx;
+    if (a.out) g.out = a.out + (size_t)r0 * a.ldo;
+    if (a.resid) g.resid = a.resid + (size_t)r0 * a.ldr;
+    g.row0 = r0;
+    hvx_status rc = launch_gemv8(e, st, g, std::min(8, R - r0), n_batch);
+    if (rc) return rc;
+  }
+  return HVX_OK;
+}
+
 struct StepBufs {          // per-step activations, `rows` row slots
   float *h, *q, *att, *act, *hn, *m_v, *m_h1, *m_act, *m_o, *logits, *part;
   __nv_bfloat16 *x16, *att16, *act16, *hn16, *m16;
@@ -1185,7 +1202,7 @@ static hvx_status llm_layers(hvx_engine* e, cudaStream_t st, LlmState* L, const 
   const hvx_config& c = e->cfg;
   const int H = c.llm_hidden, I = c.llm_inter, NQKV = (c.llm_q_heads + 2 * c.llm_kv_heads) * 64;
   hvx_status rc;
-  const bool tc = rows > 8;
+  const bool tc = rows > GEMV_MAX_ROWS;
   for (int l = 0; l < c.llm_layers; l++) {
     const LlmLayer& y = L->layer[l];
     const LlmQkvEpi qe = make_qkv(e, L, l, b.q, seqs, rows_per_seq, seq0, pos0, rows);
@@ -1229,7 +1246,7 @@ static hvx_status llm_heads(hvx_engine* e, cudaStream_t st, LlmState* L, const S
   const hvx_config& c = e->cfg;
   const int H = c.llm_hidden, MI = c.llm_mtp_inter, V = c.llm_speech_vocab;
   hvx_status rc;
-  const bool tc = n_seq > 8;
+  const bool tc = n_seq > GEMV_MAX_ROWS;
   HVX_CUDA(launch_pdl(llm_last_norm_kernel, dim3(n_seq), dim3(256), 0, st, (const float*)b.h, L->norm, (const SeqState*)L->seqs, rows_per_seq, b.hn,
                       (__nv_bfloat16*)nullptr, H, c.llm_eps));
   HVX_LAUNCH_CHECK(e);
@@ -1249,7 +1266,7 @@ static hvx_status llm_heads(hvx_engine* e, cudaStream_t st, LlmState* L, const S
     d.sW = (size_t)H * MI; d.sX = (size_t)n_seq * MI; d.sOut = sH; d.sResid = sH;
     if ((rc = launch_gemv(e, st, d, n_seq, head_k))) return rc;
     // logits: one weight matrix for all heads; rows = head_k * n_seq when that fits the GEMV
-    if (head_k * n_seq <= 8) {
+    if (head_k * n_seq <= GEMV_MAX_ROWS) {
       GemvArgs g; g.x = b.m_o; g.ldx = H; g.W = L->dec_w; g.N = V; g.K = H; g.out = b.logits; g.ldo = V;
       if ((rc = launch_gemv(e, st, g, head_k * n_seq))) return rc;
     } else {
@@ -1493,7 +1510,7 @@ extern "C" hvx_status hvx_sample(hvx_engine* e, const float* logp, int n_heads, 
 extern "C" hvx_status hvx_llm_bench_kernels(hvx_engine* e, int n_seq, int head_k, int ctx, int which, int reps, float* ms_out) {
   HVX_CHECK(e && e->llm && ms_out && reps >= 1, HVX_ERR_ARG, "llm_bench_kernels: bad argument");
   const hvx_config& c = e->cfg;
-  HVX_CHECK(n_seq >= 1 && n_seq <= c.llm_max_seqs && n_seq * head_k <= 8 && ctx + head_k < c.llm_max_ctx, HVX_ERR_ARG, "llm_bench_kernels: bad shape");
+  HVX_CHECK(n_seq >= 1 && n_seq <= c.llm_max_seqs && n_seq * head_k <= GEMV_MAX_ROWS && ctx + head_k < c.llm_max_ctx, HVX_ERR_ARG, "llm_bench_kernels: bad shape");
   LlmState* L = e->llm;
   cudaStream_t st = L->own;
   const int rows = n_seq * head_k, H = c.llm_hidden, I = c.llm_inter, NQKV = (c.llm_q_heads + 2 * c.llm_kv_heads) * 64;

@@ -138,6 +138,35 @@ def test_generate_batch_equals_single(llms):
         assert batch[i] == single
 
 
+def test_generate_batch_tensor_core_path(llms):
+    """More than 32 live rows (7 sequences x 5 heads) take the tcgen05 path (split-bf16 activations) for every decode
+    linear, 9..32 rows take several 8-row GEMV passes (4 sequences x 3 heads); each sequence must still produce the
+    tokens it produces alone on the single-pass weight-streaming GEMV path."""
+    e, m, ld, sd = llms["tinyz"]
+    from flowmirror_hydravox_b200 import _lib as L
+    from flowmirror_hydravox_b200.llm import NativeLLM
+    e8 = L.Engine(ld=ld, max_ctx=512, max_seqs=8)
+    m8 = NativeLLM(e8)
+    m8.load_state_dict(sd)
+    g = torch.Generator().manual_seed(11)
+    reqs = [dict(text=torch.randint(0, ld.text_vocab, (n,), generator=g), prompt_text=torch.randint(0, ld.text_vocab, (2,), generator=g),
+                 prompt_speech=torch.randint(0, ld.speech_token_size, (p,), generator=g)) for n, p in ((5, 0), (9, 4), (7, 11), (4, 2), (6, 6), (8, 1), (3, 3))]
+    u = torch.rand(7, 2048, generator=g)
+    sp = dict(top_p=0.9, top_k=10, win_size=24, tau_r=0.2)
+    for hk, sub in ((5, list(range(7))), (3, [0, 1, 2, 3])):
+        rq = [reqs[i] for i in sub]
+        batch = m8.generate_batch(rq, head_k=hk, u=u[sub], sampling=sp, min_ratio=4, max_ratio=4)
+        same = 0
+        for j, i in enumerate(sub):
+            single = m.generate_batch([reqs[i]], head_k=hk, u=u[i:i + 1], sampling=sp, min_ratio=4, max_ratio=4)[0]
+            assert len(batch[j]) == len(single) == 4 * reqs[i]["text"].numel()
+            n_same = next((k for k, (a, b) in enumerate(zip(batch[j], single)) if a != b), len(single))
+            same += batch[j] == single
+            assert n_same >= 8, (hk, i, n_same)
+        assert same >= len(sub) - 1
+    e8.close()
+
+
 def test_generate_full_matches_oracle(llms, golden):
     """Full dims (24 layers, 5 MTP heads), fp32 KV cache: the engine reproduces the oracle's token ids on the fixture's
     u-stream (oracle on the engine's bf16 weights; the fixture's own tokens were minted on fp32 weights)."""
