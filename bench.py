@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--cfm-steps", type=int, default=25)
     ap.add_argument("--ratio", type=float, default=8.0, help="speech tokens per text token (min=max, SURVEY 8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--first-audio-runs", type=int, default=20, help="streaming first-audio latency samples (0 = skip)")
     ap.add_argument("--cpu-tokens", type=int, default=128, help="speech tokens in the CPU baseline sample (~10-20 s of CPU work)")
     return ap.parse_args()
 
@@ -322,6 +323,24 @@ def native_arm(a):
                     "ms_per_step": ms_e2e / a.steps, "rtf": 25.0 * world / e2e if e2e else None,
                     "stage_ms_per_step": {k: v / a.steps for k, v in stage_acc.items()}},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof}
+    # BASELINE config 5: first-audio latency of the streaming path (AR decode overlapped with chunked flow + vocoder)
+    if a.first_audio_runs > 0:
+        from flowmirror_hydravox_b200.streaming import StreamingSynthesizer
+        ss = StreamingSynthesizer(mm)
+        rq = synth.utterance(ld, fd, 64, seed=77)
+        lat, tot_ms = [], []
+        for i in range(a.first_audio_runs + 2):
+            dbg = {}
+            t0 = time.perf_counter()
+            n_s = sum(c["tts_speech"].shape[1] for c in ss.tts(rq, head_k=2, sampling=SAMPLING, n_timesteps=10, min_ratio=a.ratio,
+                                                                 max_ratio=a.ratio, debug=dbg))
+            if i >= 2:
+                lat.append(dbg["first_audio_ms"]); tot_ms.append((time.perf_counter() - t0) * 1e3)
+        lat.sort(); tot_ms.sort()
+        line["first_audio"] = {"p50_ms": lat[len(lat) // 2], "min_ms": lat[0], "max_ms": lat[-1], "runs": len(lat),
+                               "total_ms_p50": tot_ms[len(tot_ms) // 2], "audio_s": n_s / hd.sr,
+                               "config": "batch=1, 16+64 text tokens, 125-token prompt, inference_head_num=2, 10 CFM steps, first chunk = "
+                                         "25+3 tokens; request -> first waveform chunk on the host (wall clock)"}
     if not a.no_cpu_baseline:
         threads = os.cpu_count() or 1
         r = cpu_oracle_run(a, a.cpu_tokens, threads)

@@ -859,6 +859,7 @@ __global__ void __launch_bounds__(SAMP_THREADS) llm_sampler_kernel(SampArgs a) {
       st->u_pos = u_pos;
       st->status = status;
       st->ctx += st->ctx_add;
+      __threadfence();                              // tokens before the count: a streaming consumer polls out_counts from another stream
       if (a.out_counts) a.out_counts[seq] = n_out;
       if (stop || group == 0 || st->ctx + group > a.max_ctx) { st->done = 1; st->n_new = 0; st->ctx_add = 0; atomicSub(a.n_active, 1); }
       else { st->n_new = group; st->ctx_add = group; s_group = group; s_alive = 1; }

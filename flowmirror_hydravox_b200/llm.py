@@ -20,6 +20,7 @@ class NativeLLM:
         self.inference_head_num = 1        # server/worker.py:64-65
         self.bf16, self.fp16 = True, False
         self._gen = torch.Generator().manual_seed(seed)
+        self._u_bufs = {}
 
     def load_state_dict(self, sd, strict=True):
         self.engine.set_tensors(L.STAGE_LLM, pack_llm(sd, self.dims))
@@ -50,8 +51,11 @@ class NativeLLM:
 
     @torch.no_grad()
     def generate_batch(self, requests: Sequence[Dict], head_k: Optional[int] = None, u: Optional[torch.Tensor] = None,
-                       sampling: Optional[Dict] = None, min_ratio: float = 2.0, max_ratio: float = 20.0) -> List[List[int]]:
-        """requests: dicts with 1-D int tensors text, prompt_text, prompt_speech.  One u-stream row per request."""
+                       sampling: Optional[Dict] = None, min_ratio: float = 2.0, max_ratio: float = 20.0,
+                       out: Optional[torch.Tensor] = None, cnt: Optional[torch.Tensor] = None) -> List[List[int]]:
+        """requests: dicts with 1-D int tensors text, prompt_text, prompt_speech.  One u-stream row per request.
+        `out` (n, max_out) / `cnt` (n,) int32 device tensors may be passed in so that a streaming consumer can watch the
+        tokens appear while this call is still running (streaming.py)."""
         e, dev, d = self.engine, self.engine.device, self.dims
         n = len(requests)
         head_k = int(self.inference_head_num if head_k is None else head_k)
@@ -68,9 +72,20 @@ class NativeLLM:
             max_out = max(max_out, int(n_new * r.get("max_ratio", max_ratio)) + 8)
         if u is None:
             u = torch.rand(n, 4 * max_out + 1024, generator=self._gen)
-        u = u.reshape(n, -1).to(dev, torch.float32).contiguous()
-        out = torch.zeros(n, max_out, device=dev, dtype=torch.int32)
-        cnt = torch.zeros(n, device=dev, dtype=torch.int32)
+        u = u.reshape(n, -1)
+        if u.device != dev:                         # keep one device buffer per shape: a stable pointer lets the engine reuse its decode graph
+            key = tuple(u.shape)
+            buf = self._u_bufs.get(key)
+            if buf is None:
+                buf = self._u_bufs[key] = torch.empty(key, device=dev, dtype=torch.float32)
+            buf.copy_(u.to(torch.float32))
+            u = buf
+        u = u.to(torch.float32).contiguous()
+        if out is None:
+            out = torch.zeros(n, max_out, device=dev, dtype=torch.int32)
+        if cnt is None:
+            cnt = torch.zeros(n, device=dev, dtype=torch.int32)
+        max_out = int(out.shape[1])
         sp = self._sampler(sampling)
         L.check(L.lib().hvx_llm_generate(e.h, n, head_k, C.byref(sp), L.ptr(u), int(u.shape[1]), L.ptr(out), max_out,
                                          L.ptr(cnt), L.stream_ptr()))

@@ -1,0 +1,127 @@
+"""Streaming synthesis: AR decode overlapped with chunked flow + vocoder (BASELINE config 5).
+
+Mirrors the upstream streaming orchestration the reference vendors in cosyvoice/cli/model.py:
+``CosyVoice2Model.tts(stream=True)`` (:315-360) and ``CosyVoice3Model.token2wav`` (:405-430) —
+  * the LLM runs in its own thread / CUDA stream and appends speech tokens;
+  * every ``token_hop_len`` (25) tokens (+ ``pre_lookahead_len`` 3, + the prompt padding on the first chunk) the flow is
+    re-run over *all tokens so far* with ``streaming=True, finalize=False`` and the new mel frames are appended to a cache;
+  * the vocoder is re-run over the cached mel with ``finalize=False`` and only the new samples are emitted;
+  * the last call uses ``finalize=True``.
+The reference polls the token list every 100 ms (:334); here the consumer watches the device-side token counter that the
+on-device sampler advances every step, so the first chunk starts as soon as its 28 tokens exist.
+"""
+from __future__ import annotations
+
+import math
+import threading
+import time
+from typing import Dict, Generator, Optional
+
+import torch
+
+from . import _lib as L
+
+
+class StreamingSynthesizer:
+    token_hop_len = 25            # cli/model.py:396 (must match the flow's static_chunk_size / token_mel_ratio)
+    pre_lookahead_len = 3         # flow.pre_lookahead_len
+
+    def __init__(self, model_manager):
+        self.mm = model_manager
+        self.dev = model_manager.engine.device
+        self.side = torch.cuda.Stream(self.dev)           # flow + vocoder + counter polling; the LLM has its own stream
+        self._cnt_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._bufs = {}
+
+    def _poll(self, cnt: torch.Tensor) -> int:
+        with torch.cuda.stream(self.side):
+            self._cnt_host.copy_(cnt, non_blocking=True)
+        self.side.synchronize()
+        return int(self._cnt_host[0])
+
+    @torch.no_grad()
+    def tts(self, request: Dict, head_k: Optional[int] = None, sampling: Optional[Dict] = None, n_timesteps: int = 10,
+            min_ratio: float = 2.0, max_ratio: float = 20.0, u: Optional[torch.Tensor] = None,
+            debug: Optional[Dict] = None) -> Generator[Dict, None, None]:
+        """request: dict with text, prompt_text, prompt_speech, prompt_feat, embedding (CPU or device tensors).
+        Yields {'tts_speech': (1, n) CPU tensor} chunks exactly like CosyVoice2Model.tts(stream=True)."""
+        mm, dev = self.mm, self.dev
+        llm, flow, hift = mm.models["llm"], mm.models["flow"], mm.models["hift"]
+        n_new = int(request["text"].numel())
+        mn, mx = float(request.get("min_ratio", min_ratio)), float(request.get("max_ratio", max_ratio))
+        max_out = int(n_new * mx) + 8
+        if max_out not in self._bufs:                  # stable device pointers -> the engine reuses its decode graph
+            self._bufs[max_out] = (torch.zeros(1, max_out, device=dev, dtype=torch.int32), torch.zeros(1, device=dev, dtype=torch.int32))
+        out, cnt = self._bufs[max_out]
+        out.zero_(); cnt.zero_()
+        if u is None:
+            u = torch.rand(1, 4 * max_out + 1024, generator=llm._gen)
+        err = []
+
+        def llm_job():
+            try:
+                torch.cuda.set_device(dev)
+                llm.generate_batch([dict(text=request["text"], prompt_text=request["prompt_text"], prompt_speech=request["prompt_speech"])],
+                                   head_k=head_k, u=u, sampling=sampling, min_ratio=mn, max_ratio=mx, out=out, cnt=cnt)
+            except Exception as ex:         # surfaced by the consumer, like the worker turns exceptions into {"error": ...}
+                err.append(ex)
+
+        torch.cuda.synchronize(dev)
+        th = threading.Thread(target=llm_job, daemon=True)
+        t_start = time.perf_counter()
+        th.start()
+        P = int(request["prompt_speech"].numel())
+        ptok = request["prompt_speech"].reshape(1, -1).to(dev, torch.int32) if P else None
+        pfeat = request["prompt_feat"].reshape(1, -1, flow.dims.mel).to(dev, torch.float32) if P else None
+        emb = request["embedding"].reshape(1, -1).to(dev, torch.float32)
+        hop, la = self.token_hop_len, self.pre_lookahead_len
+        prompt_pad = int(math.ceil(P / hop) * hop - P)
+        token_offset, speech_offset, mel_cache = 0, 0, None
+
+        def token2wav(n_tok: int, finalize: bool):
+            nonlocal mel_cache, speech_offset
+            with torch.cuda.stream(self.side):
+                mel, _ = flow.inference(token=out[:, :n_tok], embedding=emb, prompt_token=ptok, prompt_feat=pfeat,
+                                        streaming=True, finalize=finalize, n_timesteps=n_timesteps)
+                mel = mel[:, :, token_offset * 2:]
+                mel_cache = mel if mel_cache is None else torch.cat([mel_cache, mel], dim=2)
+                wav, _ = hift.inference(speech_feat=mel_cache, finalize=finalize)
+                wav = wav[:, speech_offset:]
+                speech_offset += wav.shape[1]
+                res = wav.cpu()                       # D2H on the side stream, synchronises it
+            if debug is not None:
+                debug.setdefault("mel", []).append(mel.cpu())
+                debug.setdefault("n_tok", []).append(n_tok)
+            return res
+
+        first = True
+        while True:
+            this_hop = hop + prompt_pad if token_offset == 0 else hop
+            n = self._poll(cnt)
+            alive = th.is_alive()
+            if n - token_offset >= this_hop + la:
+                wav = token2wav(token_offset + this_hop + la, finalize=False)
+                token_offset += this_hop
+                if first and debug is not None:
+                    debug["first_audio_ms"] = (time.perf_counter() - t_start) * 1e3
+                first = False
+                yield {"tts_speech": wav}
+                continue
+            if not alive:
+                n = self._poll(cnt)
+                if n - token_offset < this_hop + la:
+                    break
+                continue
+            time.sleep(0.0002)
+        th.join()
+        if err:
+            raise err[0]
+        n = self._poll(cnt)
+        if debug is not None:
+            debug["tokens"] = out[0, :n].cpu().tolist()
+            debug["mel_cache"] = lambda: mel_cache
+        if n > 0:
+            wav = token2wav(n, finalize=True)
+            if first and debug is not None:
+                debug["first_audio_ms"] = (time.perf_counter() - t_start) * 1e3
+            yield {"tts_speech": wav}
