@@ -433,7 +433,9 @@ struct AttnDecArgs {
 // grid (splits, rows*kv_heads): one block = one row, one kv head, one slice of the visible keys; warp g of
 // the block is q head kv*group+g.  Lanes own keys (a key's 128 B row is read by one lane from padded smem),
 // so the only cross-lane traffic is the final merge.
-template <bool KV32>
+// CL: the `splits` CTAs of one (row, kv head) form a thread-block cluster and merge their partial softmax results
+// through distributed shared memory (one cluster barrier) instead of global partials + fence + atomic counter.
+template <bool KV32, bool CL>
 __global__ void __launch_bounds__(256) llm_attn_kernel(AttnDecArgs a) {
   using KT = typename std::conditional<KV32, float, __nv_bfloat16>::type;
   constexpr int LD = KV32 ? ATT_LD32 : ATT_LD;      // smem row stride in elements
@@ -559,6 +561,47 @@ __global__ void __launch_bounds__(256) llm_attn_kernel(AttnDecArgs a) {
         if (a.out16) store_split(a.out16 + (size_t)row * 2 * a.ldo, a.ldo, qh * 64 + sub * 16 + i, y);
       }
     }
+    return;
+  }
+  if constexpr (CL) {
+    __shared__ __align__(16) float s_part[8][68];
+    if (kslot == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) *reinterpret_cast<float4*>(&s_part[g][4 + sub * 16 + 4 * i]) = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+    }
+    if (lane == 0) { s_part[g][0] = M; s_part[g][1] = L; }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    if ((uint32_t)(g % a.splits) == rank) {            // this CTA merges head g: read its partial from every CTA of the cluster
+      const uint32_t local = tc::smem_u32(&s_part[g][0]);
+      float Mx = -INFINITY;
+      for (int c = 0; c < a.splits; c++) {
+        uint32_t ra; float mv;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local), "r"(c));
+        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(mv) : "r"(ra));
+        Mx = fmaxf(Mx, mv);
+      }
+      float Ls = 0.f, a_lo = 0.f, a_hi = 0.f;
+      for (int c = 0; c < a.splits; c++) {
+        uint32_t ra; float mv, lv, x0, x1;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local), "r"(c));
+        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(mv) : "r"(ra));
+        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(lv) : "r"(ra + 4));
+        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(x0) : "r"(ra + 16 + 4 * lane));
+        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(x1) : "r"(ra + 16 + 128 + 4 * lane));
+        const float w = (mv == -INFINITY) ? 0.f : expf(mv - Mx);
+        Ls += lv * w; a_lo += x0 * w; a_hi += x1 * w;
+      }
+      const float inv = 1.0f / Ls;
+      if (a.out) { a.out[(size_t)row * a.ldo + qh * 64 + lane] = a_lo * inv; a.out[(size_t)row * a.ldo + qh * 64 + 32 + lane] = a_hi * inv; }
+      if (a.out16) {
+        store_split(a.out16 + (size_t)row * 2 * a.ldo, a.ldo, qh * 64 + lane, a_lo * inv);
+        store_split(a.out16 + (size_t)row * 2 * a.ldo, a.ldo, qh * 64 + 32 + lane, a_hi * inv);
+      }
+    }
+    // nobody may exit while a peer can still read its shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     return;
   }
   float* pp = a.part + (((size_t)row * q_heads + qh) * a.splits + split) * 68;
@@ -1190,8 +1233,26 @@ static hvx_status launch_attn(hvx_engine* e, cudaStream_t st, LlmState* L, int l
   a.part = b.part; a.counters = b.counters; a.out = b.att; a.out16 = want16 ? b.att16 : nullptr; a.ldo = c.llm_hidden;
   a.scale = 1.0f / sqrtf((float)c.llm_head_dim);
   dim3 grid(splits, rows * c.llm_kv_heads);
-  if (L->kv_f32) HVX_CUDA(launch_pdl(llm_attn_kernel<true>, grid, dim3(32 * a.group), 0, st, a));
-  else HVX_CUDA(launch_pdl(llm_attn_kernel<false>, grid, dim3(32 * a.group), 0, st, a));
+  if (splits > 1 && splits <= 16 && !getenv("HVX_NO_CLUSTER_ATTN")) {
+    static bool np_set = false;
+    if (!np_set) {
+      cudaFuncSetAttribute(llm_attn_kernel<true, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      cudaFuncSetAttribute(llm_attn_kernel<false, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      np_set = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = dim3(32 * a.group); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = splits; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 2;
+    if (L->kv_f32) HVX_CUDA(cudaLaunchKernelEx(&cfg, llm_attn_kernel<true, true>, a));
+    else HVX_CUDA(cudaLaunchKernelEx(&cfg, llm_attn_kernel<false, true>, a));
+  } else if (L->kv_f32) HVX_CUDA(launch_pdl(llm_attn_kernel<true, false>, grid, dim3(32 * a.group), 0, st, a));
+  else HVX_CUDA(launch_pdl(llm_attn_kernel<false, false>, grid, dim3(32 * a.group), 0, st, a));
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
 }
@@ -1322,7 +1383,8 @@ static hvx_status launch_sampler(hvx_engine* e, cudaStream_t st, SampArgs a, int
 
 static int attn_splits(int sm, int rows, int kv_heads) {
   int s = (2 * sm) / std::max(1, rows * kv_heads);
-  return std::max(1, std::min(s, 16));
+  const char* cap = getenv("HVX_ATTN_SPLITS");
+  return std::max(1, std::min(s, cap ? atoi(cap) : 16));   // the splits of a row form one cluster (16 = non-portable maximum) and merge through DSMEM
 }
 
 }  // namespace hvx
