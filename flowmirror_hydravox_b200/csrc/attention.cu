@@ -1,5 +1,6 @@
 // tcgen05 flash-style attention for the DiT estimator (see attention.cuh).
 #include "attention.cuh"
+#include <cstdlib>
 
 namespace hvx {
 
@@ -182,6 +183,176 @@ dit_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   if (warp == 0) { __syncwarp(); tc::tmem_dealloc(tmem_s, AT_TMEM_COLS); }
 }
 
+// v2: one pass over S (the 128 scores of a row are held in registers), O stays in TMEM across KV tiles and is rescaled
+// in place only when the running maximum grows by more than 2^8 (probabilities may exceed 1 by that factor; fp32 row sum
+// and the final 1/l absorb it), so a tile costs one TMEM read of S instead of two plus an O read-back.
+__global__ void __launch_bounds__(128)
+dit_attention_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                        const __grid_constant__ CUtensorMap tm_v, int k_col0, AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + AT_OFF_BAR);
+  uint64_t* kv_full = q_full + 1;    // [2]
+  uint64_t* s_full = kv_full + 2;
+  uint64_t* o_full = s_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * 128;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int T = a.T;
+  const int row_in_batch = q0 + tid;
+  const int klim_row = a.chunk > 0 ? min(T, (row_in_batch / a.chunk + 1) * a.chunk) : T;
+  const int klim_tile = a.chunk > 0 ? min(T, ((min(q0 + 127, T - 1)) / a.chunk + 1) * a.chunk) : T;
+  const int nkv = (klim_tile + 127) / 128;
+
+  if (tid == 0) {
+    tc::tma_prefetch_desc(&tm_q); tc::tma_prefetch_desc(&tm_k); tc::tma_prefetch_desc(&tm_v);
+    tc::mbar_init(q_full, 1); tc::mbar_init(&kv_full[0], 1); tc::mbar_init(&kv_full[1], 1);
+    tc::mbar_init(s_full, 1); tc::mbar_init(o_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 0) tc::tmem_alloc(tmem_slot, AT_TMEM_COLS);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_s = *tmem_slot;
+  const uint32_t tmem_o = tmem_s + 128;
+  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+
+  auto load_kv = [&](int j) {
+    const int bsel = j & 1;
+    tc::mbar_expect_tx(&kv_full[bsel], AT_K_BYTES + AT_V_BYTES);
+    tc::tma_load_2d(smem + AT_OFF_K + bsel * AT_K_BYTES, &tm_k, &kv_full[bsel], k_col0 + h * 64, b * T + j * 128);
+    uint8_t* sv = smem + AT_OFF_V + bsel * AT_V_BYTES;
+    tc::tma_load_2d(sv, &tm_v, &kv_full[bsel], j * 128, (b * a.heads + h) * 64);
+    tc::tma_load_2d(sv + 64 * 128, &tm_v, &kv_full[bsel], j * 128 + 64, (b * a.heads + h) * 64);
+  };
+  if (tid == 0) {
+    tc::mbar_expect_tx(q_full, AT_Q_BYTES);
+    tc::tma_load_2d(smem + AT_OFF_Q, &tm_q, q_full, h * 64, b * T + q0);
+    load_kv(0);
+  }
+  const uint32_t idesc_s = a.f16 ? tc::umma_idesc_f16(128, 128) : tc::umma_idesc_bf16(128, 128);
+  const uint32_t idesc_o = a.f16 ? tc::umma_idesc_f16(128, 64) : tc::umma_idesc_bf16(128, 64);
+  const float sc = 0.125f * 1.4426950408889634f;     // dim_head^-0.5 * log2(e)
+  float m_run = -INFINITY, l_run = 0.f;
+  uint8_t* sp = smem + AT_OFF_P;
+
+  for (int j = 0; j < nkv; j++) {
+    const int bsel = j & 1;
+    if (tid == 0) {
+      if (j == 0) tc::mbar_wait(q_full, 0);
+      tc::mbar_wait(&kv_full[bsel], (j >> 1) & 1);
+      tc::tc_fence_after();
+      const uint64_t dq = tc::umma_desc_k128(tc::smem_u32(smem + AT_OFF_Q));
+      const uint64_t dk = tc::umma_desc_k128(tc::smem_u32(smem + AT_OFF_K + bsel * AT_K_BYTES));
+#pragma unroll
+      for (int k = 0; k < 4; k++) tc::umma_f16(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
+      tc::umma_commit(s_full);
+    }
+    __syncwarp();
+    tc::mbar_wait(s_full, j & 1);      // S_j ready; tcgen05 ops retire in order, so P.V of tile j-1 has retired too
+    tc::tc_fence_after();
+    if (tid == 0 && j + 1 < nkv) load_kv(j + 1);       // its K/V^T/P buffers are free now
+
+    uint32_t sreg[128];
+    tc::tmem_ld_32x32(tmem_s + lane_off + 0, sreg);
+    tc::tmem_ld_32x32(tmem_s + lane_off + 32, sreg + 32);
+    tc::tmem_ld_32x32(tmem_s + lane_off + 64, sreg + 64);
+    tc::tmem_ld_32x32(tmem_s + lane_off + 96, sreg + 96);
+    tc::tmem_ld_wait();
+    const int kbase = j * 128;
+    float m_tile = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 128; i++) {
+      const float s = (kbase + i < klim_row) ? __uint_as_float(sreg[i]) * sc : -INFINITY;
+      sreg[i] = __float_as_uint(s);
+      m_tile = fmaxf(m_tile, s);
+    }
+    // lazy rescale, decided per warp so the TMEM accesses stay warp-uniform
+    const bool need = m_tile > m_run + 8.0f;
+    if (__any_sync(0xffffffffu, need)) {
+      const float m_new = need ? m_tile : m_run;
+      const float alpha = need ? tc::ex2(m_run - m_new) : 1.0f;      // first tile: ex2(-inf) = 0
+      m_run = m_new;
+      l_run *= alpha;
+      if (j > 0) {
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t v[32];
+          tc::tmem_ld_32x32(tmem_o + lane_off + (uint32_t)c0, v);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tc::tmem_st_32x32(tmem_o + lane_off + (uint32_t)c0, v);
+        }
+        tc::tmem_st_wait();
+      }
+    }
+    float psum = 0.f;
+#pragma unroll
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const float p0 = tc::ex2(__uint_as_float(sreg[c0 + i]) - m_run), p1 = tc::ex2(__uint_as_float(sreg[c0 + i + 1]) - m_run);
+        psum += p0 + p1;
+        pk[i >> 1] = tc::pack16(p0, p1, a.f16);
+      }
+      uint8_t* rowp = sp + (c0 >> 6) * (128 * 128) + tid * 128;
+      const int cb = (c0 & 63) >> 3;
+#pragma unroll
+      for (int qd = 0; qd < 4; qd++) {
+        uint4 val = make_uint4(pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2], pk[4 * qd + 3]);
+        *reinterpret_cast<uint4*>(rowp + (((cb + qd) ^ (tid & 7)) << 4)) = val;
+      }
+    }
+    l_run += psum;
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc::tc_fence_after();
+      const uint32_t pv = tc::smem_u32(smem + AT_OFF_V + bsel * AT_V_BYTES);
+      const uint32_t pp = tc::smem_u32(sp);
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        const uint64_t dp = tc::umma_desc_k128(pp + half * (128 * 128));
+        const uint64_t dv = tc::umma_desc_k128(pv + half * (64 * 128));
+#pragma unroll
+        for (int k = 0; k < 4; k++) tc::umma_f16(tmem_o, dp + 2 * k, dv + 2 * k, idesc_o, (j | half | k) ? 1u : 0u);
+      }
+      if (j == nkv - 1) tc::umma_commit(o_full);
+    }
+    __syncwarp();
+  }
+  tc::mbar_wait(o_full, 0);
+  tc::tc_fence_after();
+  {
+    uint32_t v[64];
+    tc::tmem_ld_32x32(tmem_o + lane_off, v);
+    tc::tmem_ld_32x32(tmem_o + lane_off + 32, v + 32);
+    tc::tmem_ld_wait();
+    if (row_in_batch < T) {
+      const float inv = 1.0f / l_run;
+      __nv_bfloat16* o = a.out + (size_t)(b * T + row_in_batch) * a.ld_out + h * 64;
+#pragma unroll
+      for (int i = 0; i < 64; i += 8) {
+        uint4 pk;
+        pk.x = tc::pack16(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv, a.f16);
+        pk.y = tc::pack16(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv, a.f16);
+        pk.z = tc::pack16(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv, a.f16);
+        pk.w = tc::pack16(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv, a.f16);
+        *reinterpret_cast<uint4*>(o + i) = pk;
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { __syncwarp(); tc::tmem_dealloc(tmem_s, AT_TMEM_COLS); }
+}
+
 hvx_status dit_attention(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* qk, int ld_qk, int k_col0,
                          const __nv_bfloat16* vt, int vt_ld, const AttnArgs& a) {
   CUtensorMap tq, tk, tv;
@@ -193,10 +364,12 @@ hvx_status dit_attention(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* qk
   static bool attr_set = false;
   if (!attr_set) {
     HVX_CUDA(cudaFuncSetAttribute(dit_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    HVX_CUDA(cudaFuncSetAttribute(dit_attention_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
     attr_set = true;
   }
   dim3 grid(cdiv(a.T, 128), a.heads, a.n_batch);
-  dit_attention_kernel<<<grid, 128, AT_SMEM, st>>>(tq, tk, tv, k_col0, a);
+  if (getenv("HVX_ATTN_V1")) dit_attention_kernel<<<grid, 128, AT_SMEM, st>>>(tq, tk, tv, k_col0, a);
+  else dit_attention_v2_kernel<<<grid, 128, AT_SMEM, st>>>(tq, tk, tv, k_col0, a);
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
 }

@@ -66,8 +66,10 @@ struct GemmSmem {
 
 __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == ACT_GELU_TANH) {
+    // 0.5 x (1 + tanh(u)) == x / (1 + exp(-2u)),  u = sqrt(2/pi) (x + 0.044715 x^3): one ex2 + one rcp instead of tanhf
     const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-    return 0.5f * v * (1.0f + tanhf(k0 * (v + k1 * v * v * v)));
+    const float u = k0 * (v + k1 * v * v * v);
+    return __fdividef(v, 1.0f + __expf(-2.0f * u));
   }
   if (act == ACT_SILU) return v / (1.0f + expf(-v));
   if (act == ACT_MISH) { const float sp = v > 20.0f ? v : log1pf(expf(v)); return v * tanhf(sp); }

@@ -1,0 +1,87 @@
+"""Host-side logic that needs no GPU: checkpoint packing (the layouts the kernels rely on), roofline arithmetic,
+and the no-CPU-fallback contract of the reference-facing objects."""
+import pytest
+import torch
+
+from flowmirror_hydravox_b200 import dims as D, synth, weights
+from oracle import hift_ref, llm_ref
+
+
+def test_rope_pair_permutation_keeps_q_dot_k():
+    """pack_llm permutes q/k rows so the HF half-split RoPE pair (d, d+32) sits on adjacent features; rotating adjacent
+    pairs of the permuted vectors must give the same q.k as the reference rotation of the original ones."""
+    g = torch.Generator().manual_seed(0)
+    perm = weights._rope_pair_perm(1, 64)
+    q, k = torch.randn(1, 1, 64, generator=g), torch.randn(1, 1, 64, generator=g)
+    pq, pk = torch.tensor([17]), torch.tensor([5])
+    ref = (llm_ref.rope_half(q, pq, 1e6) * llm_ref.rope_half(k, pk, 1e6)).sum()
+
+    def rot_pairs(x, pos):
+        inv = 1.0 / (1e6 ** (torch.arange(0, 64, 2).float() / 64))
+        a = pos.float() * inv
+        x = x.reshape(32, 2)
+        return torch.stack([x[:, 0] * a.cos() - x[:, 1] * a.sin(), x[:, 1] * a.cos() + x[:, 0] * a.sin()], 1).reshape(64)
+    got = (rot_pairs(q[0, 0][perm], pq) * rot_pairs(k[0, 0][perm], pk)).sum()
+    assert abs(ref - got) < 1e-4
+
+
+def test_pack_llm_layouts():
+    d = D.LLM_TINY
+    sd = synth.llm_state_dict(d, 0)
+    o = weights.pack_llm(sd, d)
+    qd, kd = d.q_heads * d.head_dim, d.kv_heads * d.head_dim
+    assert o["L0.qkv.w"].shape == (qd + 2 * kd, d.hidden) and o["L0.qkv.w"].dtype == torch.bfloat16
+    assert o["L0.qkv.b"].dtype == torch.float32
+    # v rows are not permuted; q row 1 is original row 32 of head 0
+    assert torch.equal(o["L0.qkv.w"][qd + kd:], sd["llm.model.model.layers.0.self_attn.v_proj.weight"].bfloat16())
+    assert torch.equal(o["L0.qkv.w"][1], sd["llm.model.model.layers.0.self_attn.q_proj.weight"][32].bfloat16())
+    # gate/up interleave: row 2n = gate_n, row 2n+1 = up_n
+    assert torch.equal(o["L1.gu.w"][6], sd["llm.model.model.layers.1.mlp.gate_proj.weight"][3].bfloat16())
+    assert torch.equal(o["L1.gu.w"][7], sd["llm.model.model.layers.1.mlp.up_proj.weight"][3].bfloat16())
+    # MTP heads stacked, dead q/k projections dropped
+    assert o["mtp.gu.w"].shape == (d.mtp_heads, 2 * d.mtp_inter, d.hidden)
+    assert not any("q_proj" in k or ".q." in k for k in o if k.startswith("mtp"))
+
+
+def test_pack_flow_conv_as_gemm_operands():
+    d = D.FLOW_TINY
+    sd = synth.flow_state_dict(d, 0)
+    o = weights.pack_flow(sd, d)
+    w = sd["decoder.estimator.input_embed.conv_pos_embed.conv1.0.weight"]          # (dim, 64, k)
+    assert o["pos1.w"].shape == (d.dim, d.pos_k * 64)
+    assert o["pos1.w"][5, 7 * 64 + 9] == w[5, 9, 7].half()                           # column = tap*64 + ci
+    w1 = sd["pre_lookahead_layer.conv1.weight"]                                      # (pla, mel, 4)
+    assert o["pla1.w"].shape == (d.pla_ch, 4 * 128)
+    assert o["pla1.w"][3, 2 * 128 + 11] == w1[3, 11, 2].half() and o["pla1.w"][3, 2 * 128 + 100] == 0   # padded to 128
+    assert o["mod.w"].shape == (d.depth * 6 * d.dim + 2 * d.dim, d.dim)
+    assert o["blk0.qkv.w"].shape == (3 * d.heads * d.dim_head, d.dim)
+
+
+def test_pack_hift_folds_weight_norm_like_the_oracle():
+    d = D.HIFT_TINY
+    sd = synth.hift_state_dict(d, 0)
+    o = weights.pack_hift(sd, d)
+    w = hift_ref.fold_weight_norm(sd)
+    assert torch.allclose(o["conv_pre.w"], w["conv_pre.weight"].permute(1, 2, 0), atol=0, rtol=0)     # [Cin][K][Cout]
+    assert torch.allclose(o["rb.2.c1.1.w"], w["resblocks.2.convs1.1.weight"].permute(1, 2, 0), atol=0, rtol=0)
+
+
+def test_roofline_arithmetic_matches_survey():
+    import bench
+    # 971 MB of live bf16 weights per decode step at K=2 (+ KV traffic)
+    b = bench.llm_step_bytes(D.LLM_FULL, 2, 0, 0)
+    assert abs(b - 970.98e6) < 0.5e6
+    kv = bench.llm_step_bytes(D.LLM_FULL, 2, 1000, 1) - b
+    assert abs(kv - 24 * 2 * 128 * 2 * 1002) < 1
+    # 0.756*T + 1.80e-4*T^2 GFLOP per NFE
+    f = bench.flow_nfe_flops(D.FLOW_FULL, 2298) / 1e9
+    assert abs(f - (0.756 * 2298 + 1.80e-4 * 2298 ** 2)) / f < 0.01
+
+
+def test_no_cpu_fallback():
+    from flowmirror_hydravox_b200 import _lib as L
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from flowmirror_hydravox_b200.model_manager import ModelManager
+    with pytest.raises(L.HvxError):
+        ModelManager(hd=D.HIFT_TINY, fd=D.FLOW_TINY, ld=D.LLM_TINY)
