@@ -71,6 +71,7 @@ struct GemvArgs {
   int row0 = 0;                                     // global row slot of row 0 (row groups of 8, see launch_gemv)
   int kc = 0;                                       // activation chunk staged in shared memory (floats per row)
   int slot_bytes = 0, n_slots = 0;                  // TMA-fed variant: weight ring geometry
+  int piece_bytes = 0;                              // bulk-copy granularity inside a slot (0 = one copy per slot)
   unsigned long long* dbg = nullptr;                // optional timeline of CTA 0 (globaltimer ns), scripts/bench_llm_kernels.py
   // blockIdx.y batches independent problems (the MTP heads): element strides
   size_t sW = 0, sBias = 0, sNorm = 0, sX = 0, sOut = 0, sResid = 0;
@@ -85,6 +86,16 @@ struct GemvArgs {
 __device__ __forceinline__ void gemv_fma8(float& acc, const uint4 u, const float* xs) {
   const float4 xa = *reinterpret_cast<const float4*>(xs);
   const float4 xb = *reinterpret_cast<const float4*>(xs + 4);
+  acc = fmaf(bf_lo(u.x), xa.x, acc); acc = fmaf(bf_hi(u.x), xa.y, acc);
+  acc = fmaf(bf_lo(u.y), xa.z, acc); acc = fmaf(bf_hi(u.y), xa.w, acc);
+  acc = fmaf(bf_lo(u.z), xb.x, acc); acc = fmaf(bf_hi(u.z), xb.y, acc);
+  acc = fmaf(bf_lo(u.w), xb.z, acc); acc = fmaf(bf_hi(u.w), xb.w, acc);
+}
+
+// activations stored as two planes per row (elements k%8 < 4 | k%8 >= 4) so that the lanes' float4 reads are bank-conflict free
+__device__ __forceinline__ void gemv_fma8p(float& acc, const uint4 u, const float* xa_p, const float* xb_p) {
+  const float4 xa = *reinterpret_cast<const float4*>(xa_p);
+  const float4 xb = *reinterpret_cast<const float4*>(xb_p);
   acc = fmaf(bf_lo(u.x), xa.x, acc); acc = fmaf(bf_hi(u.x), xa.y, acc);
   acc = fmaf(bf_lo(u.y), xa.z, acc); acc = fmaf(bf_hi(u.y), xa.w, acc);
   acc = fmaf(bf_lo(u.z), xb.x, acc); acc = fmaf(bf_hi(u.z), xb.y, acc);
@@ -271,8 +282,10 @@ __global__ void __launch_bounds__((GT_CONS + 1) * 32, 1) llm_gemv_tma_kernel(Gem
   if (dbg) a.dbg[0] = gtime();
   uint8_t* ring = smraw;
   const int SLOT = a.slot_bytes, NS = a.n_slots;
-  float* sx = reinterpret_cast<float*>(smraw + NS * SLOT);            // [R][K]
+  float* sx = reinterpret_cast<float*>(smraw + NS * SLOT);            // [R][2 planes][K/2]: conflict-free layout read by the pair loop
   float* snw = sx + R * K;                                            // [K]
+  float* sraw = snw + K;                                              // [R][K]: rows as they land from global memory
+  const int KH = K >> 1;
   const int npairs = (a.N + 1) >> 1;
   const int ppc = (npairs + gridDim.x - 1) / gridDim.x;               // pairs per CTA (contiguous)
   const int p_begin = blockIdx.x * ppc, p_end = min(npairs, p_begin + ppc);
@@ -296,7 +309,11 @@ __global__ void __launch_bounds__((GT_CONS + 1) * 32, 1) llm_gemv_tma_kernel(Gem
         const int row0 = 2 * p0, row1 = min(a.N, 2 * min(p_end, p0 + pps));
         const uint32_t bytes = (uint32_t)(row1 - row0) * (uint32_t)K * 2u;
         tc::mbar_expect_tx(&full_bar[sl], bytes);
-        bulk_g2s(ring + sl * SLOT, W + (size_t)row0 * K, bytes, &full_bar[sl]);
+        // several bulk copies per slot: one copy is executed by the TMA unit with limited request depth (a single 39 KB
+        // copy streams at ~23 GB/s per SM), independent copies overlap
+        const uint32_t piece = a.piece_bytes ? (uint32_t)a.piece_bytes : bytes;
+        for (uint32_t off = 0; off < bytes; off += piece)
+          bulk_g2s(ring + sl * SLOT + off, reinterpret_cast<const uint8_t*>(W + (size_t)row0 * K) + off, min(piece, bytes - off), &full_bar[sl]);
       }
     }
     return;
@@ -307,31 +324,38 @@ __global__ void __launch_bounds__((GT_CONS + 1) * 32, 1) llm_gemv_tma_kernel(Gem
   if (dbg) a.dbg[1] = gtime();
   if (tid == 0) {
     tc::mbar_expect_tx(&x_bar, (uint32_t)(a.rows * K * 4));
-    for (int r = 0; r < a.rows; r++) bulk_g2s(&sx[r * K], x + (size_t)r * a.ldx, (uint32_t)(K * 4), &x_bar);
+    for (int r = 0; r < a.rows; r++) bulk_g2s(&sraw[r * K], x + (size_t)r * a.ldx, (uint32_t)(K * 4), &x_bar);
   }
   for (int i = tid; i < (R - a.rows) * K; i += GT_CONS * 32) sx[a.rows * K + i] = 0.f;      // padding rows
   tc::mbar_wait(&x_bar, 0);
   if (dbg) a.dbg[2] = gtime();
-  if (nw) {
+  {
     float sc[R];
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      float ss = 0.f;
-      for (int k = lane * 4; k < K; k += 128) {
-        const float4 v = *reinterpret_cast<const float4*>(&sx[r * K + k]);
-        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-      }
-      for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      sc[r] = rsqrtf(ss / (float)K + a.eps);
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(GT_CONS * 32));            // consumers only: every warp has read the raw rows
-    for (int k = tid * 4; k < K; k += GT_CONS * 128) {
-      const float4 w4 = *reinterpret_cast<const float4*>(&snw[k]);
+    if (nw) {                      // fused RMSNorm (HF Qwen2RMSNorm: fp32, eps inside rsqrt); every warp computes the row scales
 #pragma unroll
       for (int r = 0; r < R; r++) {
-        float4 v = *reinterpret_cast<float4*>(&sx[r * K + k]);
-        v.x = w4.x * (v.x * sc[r]); v.y = w4.y * (v.y * sc[r]); v.z = w4.z * (v.z * sc[r]); v.w = w4.w * (v.w * sc[r]);
-        *reinterpret_cast<float4*>(&sx[r * K + k]) = v;
+        float ss = 0.f;
+        if (r < a.rows)
+          for (int k = lane * 4; k < K; k += 128) {
+            const float4 v = *reinterpret_cast<const float4*>(&sraw[r * K + k]);
+            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+          }
+        for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        sc[r] = rsqrtf(ss / (float)K + a.eps);
+      }
+    }
+    // normalise (optional) and scatter into the two-plane layout
+    for (int q = tid; q < (K >> 2); q += GT_CONS * 32) {
+      const int dst = (q & 1) * KH + (q >> 1) * 4;
+      float4 w4 = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (nw) w4 = *reinterpret_cast<const float4*>(&snw[q * 4]);
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        if (r < a.rows) {
+          float4 v = *reinterpret_cast<const float4*>(&sraw[r * K + q * 4]);
+          if (nw) { v.x = w4.x * (v.x * sc[r]); v.y = w4.y * (v.y * sc[r]); v.z = w4.z * (v.z * sc[r]); v.w = w4.w * (v.w * sc[r]); }
+          *reinterpret_cast<float4*>(&sx[r * K + dst]) = v;
+        }
       }
     }
   }
@@ -366,10 +390,11 @@ __global__ void __launch_bounds__((GT_CONS + 1) * 32, 1) llm_gemv_tma_kernel(Gem
         const uint4 v1 = *reinterpret_cast<const uint4*>(w1 + k + 256);
 #pragma unroll
         for (int r = 0; r < R; r++) {
-          gemv_fma8(acc0[r], u0, &sx[r * K + k]);
-          gemv_fma8(acc1[r], u1, &sx[r * K + k]);
-          gemv_fma8(bcc0[r], v0, &sx[r * K + k + 256]);
-          gemv_fma8(bcc1[r], v1, &sx[r * K + k + 256]);
+          const float* xa = &sx[r * K + (k >> 1)];
+          gemv_fma8p(acc0[r], u0, xa, xa + KH);
+          gemv_fma8p(acc1[r], u1, xa, xa + KH);
+          gemv_fma8p(bcc0[r], v0, xa + 128, xa + KH + 128);
+          gemv_fma8p(bcc1[r], v1, xa + 128, xa + KH + 128);
         }
       }
       if (k < K) {
@@ -377,8 +402,9 @@ __global__ void __launch_bounds__((GT_CONS + 1) * 32, 1) llm_gemv_tma_kernel(Gem
         const uint4 u1 = *reinterpret_cast<const uint4*>(w1 + k);
 #pragma unroll
         for (int r = 0; r < R; r++) {
-          gemv_fma8(acc0[r], u0, &sx[r * K + k]);
-          gemv_fma8(acc1[r], u1, &sx[r * K + k]);
+          const float* xa = &sx[r * K + (k >> 1)];
+          gemv_fma8p(acc0[r], u0, xa, xa + KH);
+          gemv_fma8p(acc1[r], u1, xa, xa + KH);
         }
       }
 #pragma unroll
@@ -1064,14 +1090,15 @@ static hvx_status launch_gemv_tma(hvx_engine* e, cudaStream_t st, GemvArgs a, in
   // CTA must be able to become resident (and prefetch its weights) while this one still computes
   const int ppc = cdiv(pairs, ctas);
   const size_t pair_bytes = (size_t)4 * a.K;
-  const size_t x_bytes = ((size_t)R * a.K + (a.norm_w ? a.K : 0)) * sizeof(float) + 128;
-  const size_t budget = x_bytes < 100 * 1024 ? 108 * 1024 - x_bytes : 216 * 1024 - x_bytes;
+  const size_t x_bytes = ((size_t)2 * R * a.K + a.K) * sizeof(float) + 128;      // two-plane rows + norm weights + landing rows
+  const size_t budget = 216 * 1024 - x_bytes;
   size_t slot = std::min((size_t)GT_SLOT / pair_bytes, (size_t)ppc) * pair_bytes;        // whole pairs, at most the share
   slot = std::max(slot, pair_bytes);
   int ns = (int)std::min((size_t)GT_NS, std::max((size_t)1, budget / slot));
   ns = std::min(ns, cdiv(ppc, (int)(slot / pair_bytes)));
   HVX_CHECK(slot * ns + x_bytes <= 220 * 1024, HVX_ERR_UNSUPPORTED, "gemv: shared memory budget exceeded (K=%d R=%d)", a.K, R);
   a.slot_bytes = (int)slot; a.n_slots = ns;
+  { const char* pb = getenv("HVX_GEMV_PIECE"); a.piece_bytes = pb ? atoi(pb) : 4096; }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(ctas, n_batch, 1);
@@ -1092,7 +1119,7 @@ static hvx_status launch_gemv8(hvx_engine* e, cudaStream_t st, GemvArgs a, int R
   a.rows = R;
   {
     const int Rt0 = R <= 1 ? 1 : R <= 2 ? 2 : R <= 4 ? 4 : 8;
-    const size_t x_bytes = ((size_t)Rt0 * a.K + (a.norm_w ? a.K : 0)) * sizeof(float) + 128;
+    const size_t x_bytes = ((size_t)2 * Rt0 * a.K + a.K) * sizeof(float) + 128;
     if (a.K <= GT_KMAX && a.K % 8 == 0 && x_bytes + (size_t)4 * a.K <= 216 * 1024 && !getenv("HVX_NO_TMA_GEMV")) {
       switch (Rt0) {
         case 1: return launch_gemv_tma<1>(e, st, a, n_batch);
