@@ -263,13 +263,26 @@ dit_attention_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     tc::tmem_ld_32x32(tmem_s + lane_off + 96, sreg + 96);
     tc::tmem_ld_wait();
     const int kbase = j * 128;
-    float m_tile = -INFINITY;
+    // 8 independent max chains (a single 128-long fmax chain is ~500 cycles of pure latency per tile)
+    float mt[8];
 #pragma unroll
-    for (int i = 0; i < 128; i++) {
-      const float s = (kbase + i < klim_row) ? __uint_as_float(sreg[i]) * sc : -INFINITY;
-      sreg[i] = __float_as_uint(s);
-      m_tile = fmaxf(m_tile, s);
+    for (int i = 0; i < 8; i++) mt[i] = -INFINITY;
+    if (kbase + 128 <= klim_row) {                      // whole tile visible: no masking
+#pragma unroll
+      for (int i = 0; i < 128; i++) {
+        const float s = __uint_as_float(sreg[i]) * sc;
+        sreg[i] = __float_as_uint(s);
+        mt[i & 7] = fmaxf(mt[i & 7], s);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 128; i++) {
+        const float s = (kbase + i < klim_row) ? __uint_as_float(sreg[i]) * sc : -INFINITY;
+        sreg[i] = __float_as_uint(s);
+        mt[i & 7] = fmaxf(mt[i & 7], s);
+      }
     }
+    const float m_tile = fmaxf(fmaxf(fmaxf(mt[0], mt[1]), fmaxf(mt[2], mt[3])), fmaxf(fmaxf(mt[4], mt[5]), fmaxf(mt[6], mt[7])));
     // lazy rescale, decided per warp so the TMEM accesses stay warp-uniform
     const bool need = m_tile > m_run + 8.0f;
     if (__any_sync(0xffffffffu, need)) {
@@ -290,14 +303,14 @@ dit_attention_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         tc::tmem_st_wait();
       }
     }
-    float psum = 0.f;
+    float ps[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int c0 = 0; c0 < 128; c0 += 32) {
       uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
         const float p0 = tc::ex2(__uint_as_float(sreg[c0 + i]) - m_run), p1 = tc::ex2(__uint_as_float(sreg[c0 + i + 1]) - m_run);
-        psum += p0 + p1;
+        ps[(i >> 1) & 3] += p0 + p1;
         pk[i >> 1] = tc::pack16(p0, p1, a.f16);
       }
       uint8_t* rowp = sp + (c0 >> 6) * (128 * 128) + tid * 128;
@@ -308,7 +321,7 @@ dit_attention_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         *reinterpret_cast<uint4*>(rowp + (((cb + qd) ^ (tid & 7)) << 4)) = val;
       }
     }
-    l_run += psum;
+    l_run += (ps[0] + ps[1]) + (ps[2] + ps[3]);
     tc::fence_proxy_async();
     tc::tc_fence_before();
     __syncthreads();
@@ -353,6 +366,190 @@ dit_attention_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   if (warp == 0) { __syncwarp(); tc::tmem_dealloc(tmem_s, AT_TMEM_COLS); }
 }
 
+// v3: 64-key tiles with the score accumulator double-buffered in TMEM (2 x 64 + 64 columns -> 256 allocated, two CTAs
+// per SM as before).  Q.K^T of tile j+1 is issued before the softmax of tile j starts and P.V of tile j runs under the
+// softmax of tile j+1, so the threads never wait for the tensor pipe (v1/v2 spent ~1/3 of their samples spinning on
+// s_full); K / V^T tiles stream through a 3-stage TMA ring.
+constexpr int A3_Q_BYTES = 128 * 128;
+constexpr int A3_K_BYTES = 64 * 128;         // 64 keys x 64 dims
+constexpr int A3_V_BYTES = 64 * 128;         // 64 dims x 64 keys (V^T)
+constexpr int A3_P_BYTES = 128 * 128;        // 128 rows x 64 keys
+constexpr int A3_STAGES = 3;
+constexpr int A3_OFF_Q = 0;
+constexpr int A3_OFF_KV = A3_OFF_Q + A3_Q_BYTES;
+constexpr int A3_OFF_P = A3_OFF_KV + A3_STAGES * (A3_K_BYTES + A3_V_BYTES);
+constexpr int A3_OFF_BAR = A3_OFF_P + A3_P_BYTES;
+constexpr int A3_SMEM = A3_OFF_BAR + 128 + 1024;
+
+__global__ void __launch_bounds__(128)
+dit_attention_v3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                        const __grid_constant__ CUtensorMap tm_v, int k_col0, AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + A3_OFF_BAR);
+  uint64_t* kv_full = q_full + 1;            // [3]
+  uint64_t* s_full = kv_full + A3_STAGES;    // [2]
+  uint64_t* o_done = s_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * 128;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int T = a.T;
+  const int row_in_batch = q0 + tid;
+  const int klim_row = a.chunk > 0 ? min(T, (row_in_batch / a.chunk + 1) * a.chunk) : T;
+  const int klim_tile = a.chunk > 0 ? min(T, ((min(q0 + 127, T - 1)) / a.chunk + 1) * a.chunk) : T;
+  const int nkv = (klim_tile + 63) / 64;
+
+  if (tid == 0) {
+    tc::tma_prefetch_desc(&tm_q); tc::tma_prefetch_desc(&tm_k); tc::tma_prefetch_desc(&tm_v);
+    tc::mbar_init(q_full, 1);
+    for (int i = 0; i < A3_STAGES; i++) tc::mbar_init(&kv_full[i], 1);
+    tc::mbar_init(&s_full[0], 1); tc::mbar_init(&s_full[1], 1); tc::mbar_init(o_done, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 0) tc::tmem_alloc(tmem_slot, 256);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + 128;
+  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  const uint32_t idesc = a.f16 ? tc::umma_idesc_f16(128, 64) : tc::umma_idesc_bf16(128, 64);
+
+  auto load_kv = [&](int j) {
+    const int st = j % A3_STAGES;
+    uint8_t* sk = smem + A3_OFF_KV + st * (A3_K_BYTES + A3_V_BYTES);
+    tc::mbar_expect_tx(&kv_full[st], A3_K_BYTES + A3_V_BYTES);
+    tc::tma_load_2d(sk, &tm_k, &kv_full[st], k_col0 + h * 64, b * T + j * 64);
+    tc::tma_load_2d(sk + A3_K_BYTES, &tm_v, &kv_full[st], j * 64, (b * a.heads + h) * 64);
+  };
+  auto issue_qk = [&](int j) {                 // S[j & 1] = Q K_j^T
+    const int st = j % A3_STAGES;
+    tc::mbar_wait(&kv_full[st], (j / A3_STAGES) & 1);
+    tc::tc_fence_after();
+    const uint64_t dq = tc::umma_desc_k128(tc::smem_u32(smem + A3_OFF_Q));
+    const uint64_t dk = tc::umma_desc_k128(tc::smem_u32(smem + A3_OFF_KV + st * (A3_K_BYTES + A3_V_BYTES)));
+#pragma unroll
+    for (int k = 0; k < 4; k++) tc::umma_f16(tmem_base + (uint32_t)((j & 1) * 64), dq + 2 * k, dk + 2 * k, idesc, k ? 1u : 0u);
+    tc::umma_commit(&s_full[j & 1]);
+  };
+  if (tid == 0) {
+    tc::mbar_expect_tx(q_full, A3_Q_BYTES);
+    tc::tma_load_2d(smem + A3_OFF_Q, &tm_q, q_full, h * 64, b * T + q0);
+    load_kv(0);
+    if (nkv > 1) load_kv(1);
+    tc::mbar_wait(q_full, 0);
+    issue_qk(0);
+  }
+  const float sc = 0.125f * 1.4426950408889634f;     // dim_head^-0.5 * log2(e)
+  float m_run = -INFINITY, l_run = 0.f;
+  uint8_t* sp = smem + A3_OFF_P;
+
+  for (int j = 0; j < nkv; j++) {
+    if (tid == 0 && j + 1 < nkv) issue_qk(j + 1);      // S[(j+1)&1] was drained before the barrier of iteration j-1
+    __syncwarp();
+    tc::mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+    tc::tc_fence_after();
+    uint32_t sreg[64];
+    tc::tmem_ld_32x32(tmem_base + lane_off + (uint32_t)((j & 1) * 64), sreg);
+    tc::tmem_ld_32x32(tmem_base + lane_off + (uint32_t)((j & 1) * 64 + 32), sreg + 32);
+    tc::tmem_ld_wait();
+    const int kbase = j * 64;
+    float mt[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    if (kbase + 64 <= klim_row) {
+#pragma unroll
+      for (int i = 0; i < 64; i++) { const float s = __uint_as_float(sreg[i]) * sc; sreg[i] = __float_as_uint(s); mt[i & 3] = fmaxf(mt[i & 3], s); }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 64; i++) {
+        const float s = (kbase + i < klim_row) ? __uint_as_float(sreg[i]) * sc : -INFINITY;
+        sreg[i] = __float_as_uint(s);
+        mt[i & 3] = fmaxf(mt[i & 3], s);
+      }
+    }
+    const float m_tile = fmaxf(fmaxf(mt[0], mt[1]), fmaxf(mt[2], mt[3]));
+    // P.V of tile j-1 must have retired before P is overwritten / O is rescaled / its K,V stage is refilled
+    if (j > 0) { tc::mbar_wait(o_done, (j - 1) & 1); tc::tc_fence_after(); }
+    if (tid == 0 && j + 2 < nkv) load_kv(j + 2);       // stage (j+2)%3 == (j-1)%3 is free now
+    const bool need = m_tile > m_run + 8.0f;
+    if (__any_sync(0xffffffffu, need)) {
+      const float m_new = need ? m_tile : m_run;
+      const float alpha = need ? tc::ex2(m_run - m_new) : 1.0f;
+      m_run = m_new;
+      l_run *= alpha;
+      if (j > 0) {
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t v[32];
+          tc::tmem_ld_32x32(tmem_o + lane_off + (uint32_t)c0, v);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tc::tmem_st_32x32(tmem_o + lane_off + (uint32_t)c0, v);
+        }
+        tc::tmem_st_wait();
+      }
+    }
+    float ps[4] = {0.f, 0.f, 0.f, 0.f};
+    uint8_t* rowp = sp + tid * 128;
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const float p0 = tc::ex2(__uint_as_float(sreg[c0 + i]) - m_run), p1 = tc::ex2(__uint_as_float(sreg[c0 + i + 1]) - m_run);
+        ps[(i >> 1) & 3] += p0 + p1;
+        pk[i >> 1] = tc::pack16(p0, p1, a.f16);
+      }
+      const int cb = c0 >> 3;
+#pragma unroll
+      for (int qd = 0; qd < 4; qd++) {
+        uint4 val = make_uint4(pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2], pk[4 * qd + 3]);
+        *reinterpret_cast<uint4*>(rowp + (((cb + qd) ^ (tid & 7)) << 4)) = val;
+      }
+    }
+    l_run += (ps[0] + ps[1]) + (ps[2] + ps[3]);
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc::tc_fence_after();
+      const int st = j % A3_STAGES;
+      const uint64_t dp = tc::umma_desc_k128(tc::smem_u32(sp));
+      const uint64_t dv = tc::umma_desc_k128(tc::smem_u32(smem + A3_OFF_KV + st * (A3_K_BYTES + A3_V_BYTES) + A3_K_BYTES));
+#pragma unroll
+      for (int k = 0; k < 4; k++) tc::umma_f16(tmem_o, dp + 2 * k, dv + 2 * k, idesc, (j | k) ? 1u : 0u);
+      tc::umma_commit(o_done);
+    }
+    __syncwarp();
+  }
+  tc::mbar_wait(o_done, (nkv - 1) & 1);
+  tc::tc_fence_after();
+  {
+    uint32_t v[64];
+    tc::tmem_ld_32x32(tmem_o + lane_off, v);
+    tc::tmem_ld_32x32(tmem_o + lane_off + 32, v + 32);
+    tc::tmem_ld_wait();
+    if (row_in_batch < T) {
+      const float inv = 1.0f / l_run;
+      __nv_bfloat16* o = a.out + (size_t)(b * T + row_in_batch) * a.ld_out + h * 64;
+#pragma unroll
+      for (int i = 0; i < 64; i += 8) {
+        uint4 pk;
+        pk.x = tc::pack16(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv, a.f16);
+        pk.y = tc::pack16(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv, a.f16);
+        pk.z = tc::pack16(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv, a.f16);
+        pk.w = tc::pack16(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv, a.f16);
+        *reinterpret_cast<uint4*>(o + i) = pk;
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { __syncwarp(); tc::tmem_dealloc(tmem_base, 256); }
+}
+
 hvx_status dit_attention(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* qk, int ld_qk, int k_col0,
                          const __nv_bfloat16* vt, int vt_ld, const AttnArgs& a) {
   CUtensorMap tq, tk, tv;
@@ -369,7 +566,14 @@ hvx_status dit_attention(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* qk
   }
   dim3 grid(cdiv(a.T, 128), a.heads, a.n_batch);
   if (getenv("HVX_ATTN_V1")) dit_attention_kernel<<<grid, 128, AT_SMEM, st>>>(tq, tk, tv, k_col0, a);
-  else dit_attention_v2_kernel<<<grid, 128, AT_SMEM, st>>>(tq, tk, tv, k_col0, a);
+  else if (getenv("HVX_ATTN_V2")) dit_attention_v2_kernel<<<grid, 128, AT_SMEM, st>>>(tq, tk, tv, k_col0, a);
+  else {
+    static bool a3 = false;
+    if (!a3) { HVX_CUDA(cudaFuncSetAttribute(dit_attention_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM)); a3 = true; }
+    CUtensorMap tk64;
+    HVX_CHECK(make_tmap_bf16_2d(&tk64, qk, rows, ld_qk, ld_qk, 64, 64), HVX_ERR_CUDA, "attention: tensor map K(64) failed");
+    dit_attention_v3_kernel<<<grid, 128, A3_SMEM, st>>>(tq, tk64, tv, k_col0, a);
+  }
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
 }
