@@ -379,7 +379,7 @@ constexpr int A3_OFF_Q = 0;
 constexpr int A3_OFF_KV = A3_OFF_Q + A3_Q_BYTES;
 constexpr int A3_OFF_P = A3_OFF_KV + A3_STAGES * (A3_K_BYTES + A3_V_BYTES);
 constexpr int A3_OFF_BAR = A3_OFF_P + A3_P_BYTES;
-constexpr int A3_SMEM = A3_OFF_BAR + 128 + 1024;
+constexpr int A3_SMEM = A3_OFF_BAR + 128 + 2048 + 1024;   // barriers + v4's pair-exchange scratch + alignment slack
 
 __global__ void __launch_bounds__(128)
 dit_attention_v3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -550,6 +550,181 @@ dit_attention_v3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   if (warp == 0) { __syncwarp(); tc::tmem_dealloc(tmem_base, 256); }
 }
 
+// v4 = v3 with two threads per query row (256 threads: warps w and w+4 share TMEM lanes 32*(w%4).., each takes 32 of the 64
+// score columns and 32 of the 64 output columns): twice the warps per scheduler to hide the TMEM / MUFU / shared-memory latencies.
+__global__ void __launch_bounds__(256)
+dit_attention_v4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                        const __grid_constant__ CUtensorMap tm_v, int k_col0, AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + A3_OFF_BAR);
+  uint64_t* kv_full = q_full + 1;            // [3]
+  uint64_t* s_full = kv_full + A3_STAGES;    // [2]
+  uint64_t* o_done = s_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+  float* s_xch = reinterpret_cast<float*>(smem + A3_OFF_BAR + 128);      // [2 (parity)][2 (half)][128 rows] pair exchange
+
+  const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7;
+  const int q0 = blockIdx.x * 128;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int T = a.T;
+  const int row_in_batch = q0 + row;
+  const int klim_row = a.chunk > 0 ? min(T, (row_in_batch / a.chunk + 1) * a.chunk) : T;
+  const int klim_tile = a.chunk > 0 ? min(T, ((min(q0 + 127, T - 1)) / a.chunk + 1) * a.chunk) : T;
+  const int nkv = (klim_tile + 63) / 64;
+
+  if (tid == 0) {
+    tc::tma_prefetch_desc(&tm_q); tc::tma_prefetch_desc(&tm_k); tc::tma_prefetch_desc(&tm_v);
+    tc::mbar_init(q_full, 1);
+    for (int i = 0; i < A3_STAGES; i++) tc::mbar_init(&kv_full[i], 1);
+    tc::mbar_init(&s_full[0], 1); tc::mbar_init(&s_full[1], 1); tc::mbar_init(o_done, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 0) tc::tmem_alloc(tmem_slot, 256);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + 128;
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+  const uint32_t pair_bar = 1 + (warp & 3);          // named barrier shared by warps w and w+4 (64 threads)
+  const uint32_t idesc = a.f16 ? tc::umma_idesc_f16(128, 64) : tc::umma_idesc_bf16(128, 64);
+
+  auto load_kv = [&](int j) {
+    const int st = j % A3_STAGES;
+    uint8_t* sk = smem + A3_OFF_KV + st * (A3_K_BYTES + A3_V_BYTES);
+    tc::mbar_expect_tx(&kv_full[st], A3_K_BYTES + A3_V_BYTES);
+    tc::tma_load_2d(sk, &tm_k, &kv_full[st], k_col0 + h * 64, b * T + j * 64);
+    tc::tma_load_2d(sk + A3_K_BYTES, &tm_v, &kv_full[st], j * 64, (b * a.heads + h) * 64);
+  };
+  auto issue_qk = [&](int j) {                 // S[j & 1] = Q K_j^T
+    const int st = j % A3_STAGES;
+    tc::mbar_wait(&kv_full[st], (j / A3_STAGES) & 1);
+    tc::tc_fence_after();
+    const uint64_t dq = tc::umma_desc_k128(tc::smem_u32(smem + A3_OFF_Q));
+    const uint64_t dk = tc::umma_desc_k128(tc::smem_u32(smem + A3_OFF_KV + st * (A3_K_BYTES + A3_V_BYTES)));
+#pragma unroll
+    for (int k = 0; k < 4; k++) tc::umma_f16(tmem_base + (uint32_t)((j & 1) * 64), dq + 2 * k, dk + 2 * k, idesc, k ? 1u : 0u);
+    tc::umma_commit(&s_full[j & 1]);
+  };
+  if (tid == 0) {
+    tc::mbar_expect_tx(q_full, A3_Q_BYTES);
+    tc::tma_load_2d(smem + A3_OFF_Q, &tm_q, q_full, h * 64, b * T + q0);
+    load_kv(0);
+    if (nkv > 1) load_kv(1);
+    tc::mbar_wait(q_full, 0);
+    issue_qk(0);
+  }
+  const float sc = 0.125f * 1.4426950408889634f;     // dim_head^-0.5 * log2(e)
+  float m_run = -INFINITY, l_run = 0.f;
+  uint8_t* sp = smem + A3_OFF_P;
+
+  for (int j = 0; j < nkv; j++) {
+    if (tid == 0 && j + 1 < nkv) issue_qk(j + 1);      // S[(j+1)&1] was drained before the barrier of iteration j-1
+    __syncwarp();
+    tc::mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+    tc::tc_fence_after();
+    uint32_t sreg[32];
+    tc::tmem_ld_32x32(tmem_base + lane_off + (uint32_t)((j & 1) * 64 + half * 32), sreg);
+    tc::tmem_ld_wait();
+    const int kbase = j * 64 + half * 32;
+    float mt[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    if (kbase + 32 <= klim_row) {
+#pragma unroll
+      for (int i = 0; i < 32; i++) { const float s = __uint_as_float(sreg[i]) * sc; sreg[i] = __float_as_uint(s); mt[i & 3] = fmaxf(mt[i & 3], s); }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; i++) {
+        const float s = (kbase + i < klim_row) ? __uint_as_float(sreg[i]) * sc : -INFINITY;
+        sreg[i] = __float_as_uint(s);
+        mt[i & 3] = fmaxf(mt[i & 3], s);
+      }
+    }
+    float m_tile = fmaxf(fmaxf(mt[0], mt[1]), fmaxf(mt[2], mt[3]));
+    // row maximum over both halves: exchange with the partner thread (same row, other 32 columns)
+    s_xch[((j & 1) * 2 + half) * 128 + row] = m_tile;
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    m_tile = fmaxf(m_tile, s_xch[((j & 1) * 2 + (half ^ 1)) * 128 + row]);
+    // P.V of tile j-1 must have retired before P is overwritten / O is rescaled / its K,V stage is refilled
+    if (j > 0) { tc::mbar_wait(o_done, (j - 1) & 1); tc::tc_fence_after(); }
+    if (tid == 0 && j + 2 < nkv) load_kv(j + 2);       // stage (j+2)%3 == (j-1)%3 is free now
+    const bool need = m_tile > m_run + 8.0f;
+    if (__any_sync(0xffffffffu, need)) {
+      const float m_new = need ? m_tile : m_run;
+      const float alpha = need ? tc::ex2(m_run - m_new) : 1.0f;
+      m_run = m_new;
+      l_run *= alpha;
+      if (j > 0) {
+        uint32_t v[32];
+        tc::tmem_ld_32x32(tmem_o + lane_off + (uint32_t)(half * 32), v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+        tc::tmem_st_32x32(tmem_o + lane_off + (uint32_t)(half * 32), v);
+        tc::tmem_st_wait();
+      }
+    }
+    float ps[4] = {0.f, 0.f, 0.f, 0.f};
+    uint8_t* rowp = sp + row * 128;
+    {
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const float p0 = tc::ex2(__uint_as_float(sreg[i]) - m_run), p1 = tc::ex2(__uint_as_float(sreg[i + 1]) - m_run);
+        ps[(i >> 1) & 3] += p0 + p1;
+        pk[i >> 1] = tc::pack16(p0, p1, a.f16);
+      }
+      const int cb = half * 4;
+#pragma unroll
+      for (int qd = 0; qd < 4; qd++) {
+        uint4 val = make_uint4(pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2], pk[4 * qd + 3]);
+        *reinterpret_cast<uint4*>(rowp + (((cb + qd) ^ (row & 7)) << 4)) = val;
+      }
+    }
+    l_run += (ps[0] + ps[1]) + (ps[2] + ps[3]);
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc::tc_fence_after();
+      const int st = j % A3_STAGES;
+      const uint64_t dp = tc::umma_desc_k128(tc::smem_u32(sp));
+      const uint64_t dv = tc::umma_desc_k128(tc::smem_u32(smem + A3_OFF_KV + st * (A3_K_BYTES + A3_V_BYTES) + A3_K_BYTES));
+#pragma unroll
+      for (int k = 0; k < 4; k++) tc::umma_f16(tmem_o, dp + 2 * k, dv + 2 * k, idesc, (j | k) ? 1u : 0u);
+      tc::umma_commit(o_done);
+    }
+    __syncwarp();
+  }
+  tc::mbar_wait(o_done, (nkv - 1) & 1);
+  tc::tc_fence_after();
+  {
+    // total row sum = both halves
+    s_xch[half * 128 + row] = l_run;
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    const float l_tot = l_run + s_xch[(half ^ 1) * 128 + row];
+    uint32_t v[32];
+    tc::tmem_ld_32x32(tmem_o + lane_off + (uint32_t)(half * 32), v);
+    tc::tmem_ld_wait();
+    if (row_in_batch < T) {
+      const float inv = 1.0f / l_tot;
+      __nv_bfloat16* o = a.out + (size_t)(b * T + row_in_batch) * a.ld_out + h * 64 + half * 32;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 pk;
+        pk.x = tc::pack16(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv, a.f16);
+        pk.y = tc::pack16(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv, a.f16);
+        pk.z = tc::pack16(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv, a.f16);
+        pk.w = tc::pack16(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv, a.f16);
+        *reinterpret_cast<uint4*>(o + i) = pk;
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { __syncwarp(); tc::tmem_dealloc(tmem_base, 256); }
+}
+
 hvx_status dit_attention(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* qk, int ld_qk, int k_col0,
                          const __nv_bfloat16* vt, int vt_ld, const AttnArgs& a) {
   CUtensorMap tq, tk, tv;
@@ -572,7 +747,10 @@ hvx_status dit_attention(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* qk
     if (!a3) { HVX_CUDA(cudaFuncSetAttribute(dit_attention_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM)); a3 = true; }
     CUtensorMap tk64;
     HVX_CHECK(make_tmap_bf16_2d(&tk64, qk, rows, ld_qk, ld_qk, 64, 64), HVX_ERR_CUDA, "attention: tensor map K(64) failed");
-    dit_attention_v3_kernel<<<grid, 128, A3_SMEM, st>>>(tq, tk64, tv, k_col0, a);
+    static bool a4 = false;
+    if (!a4) { HVX_CUDA(cudaFuncSetAttribute(dit_attention_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM)); a4 = true; }
+    if (getenv("HVX_ATTN_V3")) dit_attention_v3_kernel<<<grid, 128, A3_SMEM, st>>>(tq, tk64, tv, k_col0, a);
+    else dit_attention_v4_kernel<<<grid, 256, A3_SMEM, st>>>(tq, tk64, tv, k_col0, a);
   }
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
