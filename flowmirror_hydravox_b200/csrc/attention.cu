@@ -725,6 +725,192 @@ dit_attention_v4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   if (warp == 0) { __syncwarp(); tc::tmem_dealloc(tmem_base, 256); }
 }
 
+// v5: warp-specialised v3.  Warp 4 is the only one that talks to the TMA unit and the tensor core (loads K / V^T tiles,
+// issues Q.K^T two tiles ahead and P.V as soon as the 128 softmax threads have published P through an mbarrier); the four
+// softmax warps never issue an MMA and never meet at a CTA-wide barrier, so each proceeds as soon as its own score tile
+// and P buffer are ready.  P is double-buffered so writing P_{j+1} does not wait for P.V_j.
+constexpr int A5_P_BYTES = 2 * 128 * 128;
+constexpr int A5_OFF_P = A3_OFF_KV + A3_STAGES * (A3_K_BYTES + A3_V_BYTES);
+constexpr int A5_OFF_BAR = A5_OFF_P + A5_P_BYTES;
+constexpr int A5_SMEM = A5_OFF_BAR + 256 + 1024;
+
+__global__ void __launch_bounds__(160)
+dit_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                        const __grid_constant__ CUtensorMap tm_v, int k_col0, AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + A5_OFF_BAR);
+  uint64_t* kv_full = q_full + 1;            // [3]  TMA -> MMA warp
+  uint64_t* s_full = kv_full + A3_STAGES;    // [2]  tensor core -> softmax warps
+  uint64_t* p_ready = s_full + 2;            // [2]  softmax warps (128 arrivals) -> MMA warp
+  uint64_t* o_done = p_ready + 2;            // [2]  P.V_j retired (parity buffers by j&1): frees P[j&1], K/V stage, O for rescale
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * 128;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int T = a.T;
+  const int klim_tile = a.chunk > 0 ? min(T, ((min(q0 + 127, T - 1)) / a.chunk + 1) * a.chunk) : T;
+  const int nkv = (klim_tile + 63) / 64;
+
+  if (tid == 0) {
+    tc::tma_prefetch_desc(&tm_q); tc::tma_prefetch_desc(&tm_k); tc::tma_prefetch_desc(&tm_v);
+    tc::mbar_init(q_full, 1);
+    for (int i = 0; i < A3_STAGES; i++) tc::mbar_init(&kv_full[i], 1);
+    for (int i = 0; i < 2; i++) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&p_ready[i], 128); tc::mbar_init(&o_done[i], 1); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 0) tc::tmem_alloc(tmem_slot, 256);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + 128;
+  const uint32_t idesc = a.f16 ? tc::umma_idesc_f16(128, 64) : tc::umma_idesc_bf16(128, 64);
+
+  if (warp == 4) {
+    // ---------------- TMA + tensor-core warp (one elected lane)
+    if (lane == 0) {
+      auto load_kv = [&](int j) {
+        const int st = j % A3_STAGES;
+        uint8_t* sk = smem + A3_OFF_KV + st * (A3_K_BYTES + A3_V_BYTES);
+        tc::mbar_expect_tx(&kv_full[st], A3_K_BYTES + A3_V_BYTES);
+        tc::tma_load_2d(sk, &tm_k, &kv_full[st], k_col0 + h * 64, b * T + j * 64);
+        tc::tma_load_2d(sk + A3_K_BYTES, &tm_v, &kv_full[st], j * 64, (b * a.heads + h) * 64);
+      };
+      auto issue_qk = [&](int j) {
+        const int st = j % A3_STAGES;
+        tc::mbar_wait(&kv_full[st], (j / A3_STAGES) & 1);
+        tc::tc_fence_after();
+        const uint64_t dq = tc::umma_desc_k128(tc::smem_u32(smem + A3_OFF_Q));
+        const uint64_t dk = tc::umma_desc_k128(tc::smem_u32(smem + A3_OFF_KV + st * (A3_K_BYTES + A3_V_BYTES)));
+#pragma unroll
+        for (int k = 0; k < 4; k++) tc::umma_f16(tmem_base + (uint32_t)((j & 1) * 64), dq + 2 * k, dk + 2 * k, idesc, k ? 1u : 0u);
+        tc::umma_commit(&s_full[j & 1]);
+      };
+      tc::mbar_expect_tx(q_full, A3_Q_BYTES);
+      tc::tma_load_2d(smem + A3_OFF_Q, &tm_q, q_full, h * 64, b * T + q0);
+      for (int j = 0; j < min(nkv, A3_STAGES); j++) load_kv(j);
+      tc::mbar_wait(q_full, 0);
+      issue_qk(0);
+      if (nkv > 1) issue_qk(1);
+      for (int j = 0; j < nkv; j++) {
+        // P_j published (which also means S_j has been read: S[j&1] may be overwritten by Q.K_{j+2})
+        tc::mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
+        tc::tc_fence_after();
+        const int st = j % A3_STAGES;
+        const uint64_t dp = tc::umma_desc_k128(tc::smem_u32(smem + A5_OFF_P + (j & 1) * (128 * 128)));
+        const uint64_t dv = tc::umma_desc_k128(tc::smem_u32(smem + A3_OFF_KV + st * (A3_K_BYTES + A3_V_BYTES) + A3_K_BYTES));
+#pragma unroll
+        for (int k = 0; k < 4; k++) tc::umma_f16(tmem_o, dp + 2 * k, dv + 2 * k, idesc, (j | k) ? 1u : 0u);
+        tc::umma_commit(&o_done[j & 1]);
+        if (j + 2 < nkv) issue_qk(j + 2);
+        if (j + A3_STAGES < nkv) {              // refill this tile's K/V stage once P.V_j has retired
+          tc::mbar_wait(&o_done[j & 1], (j >> 1) & 1);
+          load_kv(j + A3_STAGES);
+        }
+      }
+    }
+  } else {
+    // ---------------- softmax warps: thread == query row == TMEM lane
+    const int row_in_batch = q0 + tid;
+    const int klim_row = a.chunk > 0 ? min(T, (row_in_batch / a.chunk + 1) * a.chunk) : T;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const float sc = 0.125f * 1.4426950408889634f;     // dim_head^-0.5 * log2(e)
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < nkv; j++) {
+      tc::mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc::tc_fence_after();
+      uint32_t sreg[64];
+      tc::tmem_ld_32x32(tmem_base + lane_off + (uint32_t)((j & 1) * 64), sreg);
+      tc::tmem_ld_32x32(tmem_base + lane_off + (uint32_t)((j & 1) * 64 + 32), sreg + 32);
+      tc::tmem_ld_wait();
+      const int kbase = j * 64;
+      float mt[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      if (kbase + 64 <= klim_row) {
+#pragma unroll
+        for (int i = 0; i < 64; i++) { const float s = __uint_as_float(sreg[i]) * sc; sreg[i] = __float_as_uint(s); mt[i & 3] = fmaxf(mt[i & 3], s); }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; i++) {
+          const float s = (kbase + i < klim_row) ? __uint_as_float(sreg[i]) * sc : -INFINITY;
+          sreg[i] = __float_as_uint(s);
+          mt[i & 3] = fmaxf(mt[i & 3], s);
+        }
+      }
+      const float m_tile = fmaxf(fmaxf(mt[0], mt[1]), fmaxf(mt[2], mt[3]));
+      const bool need = m_tile > m_run + 8.0f;
+      if (__any_sync(0xffffffffu, need)) {
+        const float m_new = need ? m_tile : m_run;
+        const float alpha = need ? tc::ex2(m_run - m_new) : 1.0f;
+        m_run = m_new;
+        l_run *= alpha;
+        if (j > 0) {
+          // O may only be rescaled once P.V_{j-1} has retired (and nothing newer can be in flight: P.V_j needs this P)
+          tc::mbar_wait(&o_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+          tc::tc_fence_after();
+#pragma unroll
+          for (int c0 = 0; c0 < 64; c0 += 32) {
+            uint32_t v[32];
+            tc::tmem_ld_32x32(tmem_o + lane_off + (uint32_t)c0, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tc::tmem_st_32x32(tmem_o + lane_off + (uint32_t)c0, v);
+          }
+          tc::tmem_st_wait();
+        }
+      }
+      // P buffer j&1 was last read by P.V_{j-2}
+      if (j >= 2) tc::mbar_wait(&o_done[j & 1], ((j - 2) >> 1) & 1);
+      float ps[4] = {0.f, 0.f, 0.f, 0.f};
+      uint8_t* rowp = smem + A5_OFF_P + (j & 1) * (128 * 128) + tid * 128;
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = tc::ex2(__uint_as_float(sreg[c0 + i]) - m_run), p1 = tc::ex2(__uint_as_float(sreg[c0 + i + 1]) - m_run);
+          ps[(i >> 1) & 3] += p0 + p1;
+          pk[i >> 1] = tc::pack16(p0, p1, a.f16);
+        }
+        const int cb = c0 >> 3;
+#pragma unroll
+        for (int qd = 0; qd < 4; qd++) {
+          uint4 val = make_uint4(pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2], pk[4 * qd + 3]);
+          *reinterpret_cast<uint4*>(rowp + (((cb + qd) ^ (tid & 7)) << 4)) = val;
+        }
+      }
+      l_run += (ps[0] + ps[1]) + (ps[2] + ps[3]);
+      tc::fence_proxy_async();                 // generic-proxy P stores -> visible to the tensor core
+      tc::tc_fence_before();                   // orders this thread's TMEM reads / rescale before the MMA warp's next issue
+      tc::mbar_arrive(&p_ready[j & 1]);
+    }
+    tc::mbar_wait(&o_done[(nkv - 1) & 1], ((nkv - 1) >> 1) & 1);
+    tc::tc_fence_after();
+    uint32_t v[64];
+    tc::tmem_ld_32x32(tmem_o + lane_off, v);
+    tc::tmem_ld_32x32(tmem_o + lane_off + 32, v + 32);
+    tc::tmem_ld_wait();
+    if (row_in_batch < T) {
+      const float inv = 1.0f / l_run;
+      __nv_bfloat16* o = a.out + (size_t)(b * T + row_in_batch) * a.ld_out + h * 64;
+#pragma unroll
+      for (int i = 0; i < 64; i += 8) {
+        uint4 pk;
+        pk.x = tc::pack16(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv, a.f16);
+        pk.y = tc::pack16(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv, a.f16);
+        pk.z = tc::pack16(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv, a.f16);
+        pk.w = tc::pack16(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv, a.f16);
+        *reinterpret_cast<uint4*>(o + i) = pk;
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { __syncwarp(); tc::tmem_dealloc(tmem_base, 256); }
+}
+
 hvx_status dit_attention(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* qk, int ld_qk, int k_col0,
                          const __nv_bfloat16* vt, int vt_ld, const AttnArgs& a) {
   CUtensorMap tq, tk, tv;
@@ -749,8 +935,11 @@ hvx_status dit_attention(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* qk
     HVX_CHECK(make_tmap_bf16_2d(&tk64, qk, rows, ld_qk, ld_qk, 64, 64), HVX_ERR_CUDA, "attention: tensor map K(64) failed");
     static bool a4 = false;
     if (!a4) { HVX_CUDA(cudaFuncSetAttribute(dit_attention_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM)); a4 = true; }
+    static bool a5 = false;
+    if (!a5) { HVX_CUDA(cudaFuncSetAttribute(dit_attention_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A5_SMEM)); a5 = true; }
     if (getenv("HVX_ATTN_V3")) dit_attention_v3_kernel<<<grid, 128, A3_SMEM, st>>>(tq, tk64, tv, k_col0, a);
-    else dit_attention_v4_kernel<<<grid, 256, A3_SMEM, st>>>(tq, tk64, tv, k_col0, a);
+    else if (getenv("HVX_ATTN_V4")) dit_attention_v4_kernel<<<grid, 256, A3_SMEM, st>>>(tq, tk64, tv, k_col0, a);
+    else dit_attention_v5_kernel<<<grid, 160, A5_SMEM, st>>>(tq, tk64, tv, k_col0, a);
   }
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
