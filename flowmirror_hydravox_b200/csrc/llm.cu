@@ -601,23 +601,27 @@ __global__ void __launch_bounds__(256) llm_attn_kernel(AttnDecArgs a) {
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     if ((uint32_t)(g % a.splits) == rank) {            // this CTA merges head g: read its partial from every CTA of the cluster
       const uint32_t local = tc::smem_u32(&s_part[g][0]);
-      float Mx = -INFINITY;
-      for (int c = 0; c < a.splits; c++) {
-        uint32_t ra; float mv;
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local), "r"(c));
-        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(mv) : "r"(ra));
-        Mx = fmaxf(Mx, mv);
+      // issue every remote load before any dependent math: 16 x 4 independent DSMEM reads in flight instead of 16 round trips
+      float mv[16], lv[16], x0[16], x1[16];
+#pragma unroll
+      for (int c = 0; c < 16; c++) {
+        if (c < a.splits) {
+          uint32_t ra;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local), "r"(c));
+          asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(mv[c]) : "r"(ra));
+          asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(lv[c]) : "r"(ra + 4));
+          asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(x0[c]) : "r"(ra + 16 + 4 * lane));
+          asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(x1[c]) : "r"(ra + 16 + 128 + 4 * lane));
+        } else { mv[c] = -INFINITY; lv[c] = 0.f; x0[c] = 0.f; x1[c] = 0.f; }
       }
+      float Mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 16; c++) Mx = fmaxf(Mx, mv[c]);
       float Ls = 0.f, a_lo = 0.f, a_hi = 0.f;
-      for (int c = 0; c < a.splits; c++) {
-        uint32_t ra; float mv, lv, x0, x1;
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local), "r"(c));
-        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(mv) : "r"(ra));
-        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(lv) : "r"(ra + 4));
-        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(x0) : "r"(ra + 16 + 4 * lane));
-        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(x1) : "r"(ra + 16 + 128 + 4 * lane));
-        const float w = (mv == -INFINITY) ? 0.f : expf(mv - Mx);
-        Ls += lv * w; a_lo += x0 * w; a_hi += x1 * w;
+#pragma unroll
+      for (int c = 0; c < 16; c++) {
+        const float w = (mv[c] == -INFINITY) ? 0.f : expf(mv[c] - Mx);
+        Ls += lv[c] * w; a_lo += x0[c] * w; a_hi += x1[c] * w;
       }
       const float inv = 1.0f / Ls;
       if (a.out) { a.out[(size_t)row * a.ldo + qh * 64 + lane] = a_lo * inv; a.out[(size_t)row * a.ldo + qh * 64 + 32 + lane] = a_hi * inv; }
