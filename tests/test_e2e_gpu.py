@@ -108,3 +108,18 @@ def test_load_pt_contract(mm, tmp_path):
     assert mm.load_pt(None, str(p))["status"] == "success"
     bad = mm.load_pt(str(tmp_path / "missing.pt"), None)
     assert bad["status"] == "error" and "error" in bad and "message" in bad
+
+
+def test_segmented_synthesis_batches_independent_segments(mm):
+    """inference_tts_with_segmentation(last_prompt=False): the segments are independent utterances, so one batched call +
+    the reference's pause stitching must equal per-segment synthesis stitched the same way."""
+    import random
+    from flowmirror_hydravox_b200 import output
+    reqs = _requests()
+    u = torch.rand(len(reqs), 1024, generator=torch.Generator().manual_seed(9))
+    kw = dict(head_k=2, sampling=dict(top_p=0.9, top_k=10, win_size=24, tau_r=0.2), n_timesteps=5, min_ratio=4, max_ratio=4)
+    merged = output.synthesize_segments(mm, reqs, rng=random.Random(1), u=u, **kw)
+    singles = [mm.synthesize_batch([r], u=u[i:i + 1], **kw)[0] for i, r in enumerate(reqs)]
+    ref = output.stitch_segments(singles, 24000, random.Random(1))
+    assert merged.shape == ref.shape and (merged - ref).abs().max().item() < 1e-5
+    assert len(output.audio_to_base64(merged, 24000)) > 100

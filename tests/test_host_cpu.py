@@ -85,3 +85,23 @@ def test_no_cpu_fallback():
     from flowmirror_hydravox_b200.model_manager import ModelManager
     with pytest.raises(L.HvxError):
         ModelManager(hd=D.HIFT_TINY, fd=D.FLOW_TINY, ld=D.LLM_TINY)
+
+
+def test_stitching_and_wav_encoding():
+    """pause insertion of inference_tts_with_segmentation (infer_speech_model.py:419-441) and audio_to_base64 (:504-521)."""
+    import base64, io, random
+    from scipy.io import wavfile
+    from flowmirror_hydravox_b200 import output
+    segs = [torch.full((1, 100), 0.1), torch.full((1, 50), -0.2), torch.full((1, 70), 0.3)]
+    out = output.stitch_segments(segs, 24000, random.Random(3))
+    r = random.Random(3)
+    pauses = [int(r.uniform(50, 150) * 24000 / 1000) for _ in range(2)]
+    assert out.shape == (1, 220 + sum(pauses)) and all(1200 <= p <= 3600 for p in pauses)
+    assert torch.equal(out[:, :100], segs[0]) and out[:, 100:100 + pauses[0]].abs().max() == 0
+    assert torch.equal(out[:, -70:], segs[2])
+    b64 = output.audio_to_base64(out, 24000)
+    sr, data = wavfile.read(io.BytesIO(base64.b64decode(b64)))
+    assert sr == 24000 and data.dtype.kind == "f" and data.shape[0] == out.shape[1]
+    assert torch.equal(torch.from_numpy(data.copy()).reshape(1, -1), out)
+    with pytest.raises(ValueError):
+        output.stitch_segments([], 24000)
