@@ -29,7 +29,7 @@ class Config(C.Structure):
         ("flow_mel", C.c_int), ("flow_spk_in", C.c_int), ("flow_vocab", C.c_int), ("flow_pla_ch", C.c_int),
         ("flow_dim", C.c_int), ("flow_depth", C.c_int), ("flow_heads", C.c_int), ("flow_dim_head", C.c_int),
         ("flow_ff_mult", C.c_int), ("flow_chunk", C.c_int), ("flow_pos_k", C.c_int), ("flow_pos_groups", C.c_int),
-        ("flow_noise_frames", C.c_int), ("flow_cfg_rate", C.c_float),
+        ("flow_noise_frames", C.c_int), ("flow_cfg_rate", C.c_float), ("flow_precise", C.c_int),
         ("llm_hidden", C.c_int), ("llm_layers", C.c_int), ("llm_q_heads", C.c_int), ("llm_kv_heads", C.c_int),
         ("llm_head_dim", C.c_int), ("llm_inter", C.c_int), ("llm_text_vocab", C.c_int), ("llm_speech_vocab", C.c_int),
         ("llm_mtp_heads", C.c_int), ("llm_mtp_inter", C.c_int), ("llm_max_ctx", C.c_int), ("llm_max_seqs", C.c_int),
@@ -52,7 +52,7 @@ class Request(C.Structure):
 
 
 def make_config(hd: D.HiftDims, fd: D.FlowDims, ld: D.LlmDims, max_ctx: int = 8192, max_seqs: int = 32,
-                kv_f32: bool = False) -> Config:
+                kv_f32: bool = False, flow_precise: bool = False) -> Config:
     c = Config()
     c.hift_mel, c.hift_base, c.hift_f0_ch, c.hift_harmonics, c.hift_sr = hd.mel, hd.base, hd.f0_ch, hd.harmonics, hd.sr
     c.hift_n_ups = len(hd.ups)
@@ -70,6 +70,7 @@ def make_config(hd: D.HiftDims, fd: D.FlowDims, ld: D.LlmDims, max_ctx: int = 81
     c.flow_dim, c.flow_depth, c.flow_heads, c.flow_dim_head = fd.dim, fd.depth, fd.heads, fd.dim_head
     c.flow_ff_mult, c.flow_chunk, c.flow_pos_k, c.flow_pos_groups = fd.ff_mult, fd.chunk, fd.pos_k, fd.pos_groups
     c.flow_noise_frames, c.flow_cfg_rate = fd.noise_frames, fd.cfg_rate
+    c.flow_precise = int(bool(flow_precise))
     c.llm_hidden, c.llm_layers, c.llm_q_heads, c.llm_kv_heads = ld.hidden, ld.layers, ld.q_heads, ld.kv_heads
     c.llm_head_dim, c.llm_inter, c.llm_text_vocab, c.llm_speech_vocab = ld.head_dim, ld.inter, ld.text_vocab, ld.speech_vocab
     c.llm_mtp_heads, c.llm_mtp_inter, c.llm_max_ctx, c.llm_max_seqs = ld.mtp_heads, ld.mtp_inter, max_ctx, max_seqs
@@ -110,14 +111,15 @@ class Engine:
     """Owns one hvx_engine (one per process/GPU, like one reference worker per GPU)."""
 
     def __init__(self, hd=D.HIFT_FULL, fd=D.FLOW_FULL, ld=D.LLM_FULL, max_ctx=8192, max_seqs=32, device="cuda:0",
-                 kv_f32=False):
+                 kv_f32=False, flow_precise=False):
         if not torch.cuda.is_available():
             raise HvxError("no CUDA device: the HydraVox B200 engine has no CPU fallback")
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
         torch.zeros(1, device=self.device)          # make sure the primary context exists
         self.hd, self.fd, self.ld = hd, fd, ld
-        self.cfg = make_config(hd, fd, ld, max_ctx, max_seqs, kv_f32)
+        self.cfg = make_config(hd, fd, ld, max_ctx, max_seqs, kv_f32, flow_precise)
+        self.flow_precise = bool(flow_precise)
         self.h = C.c_void_p()
         check(lib().hvx_create(C.byref(self.h), C.byref(self.cfg)))
         self._keep = {0: {}, 1: {}, 2: {}}          # tensors borrowed by the engine

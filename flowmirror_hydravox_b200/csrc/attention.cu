@@ -892,7 +892,16 @@ dit_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     tc::tmem_ld_32x32(tmem_o + lane_off, v);
     tc::tmem_ld_32x32(tmem_o + lane_off + 32, v + 32);
     tc::tmem_ld_wait();
-    if (row_in_batch < T) {
+    if (row_in_batch < T && a.lo_off) {
+      const float inv = 1.0f / l_run;
+      uint16_t* o = reinterpret_cast<uint16_t*>(a.out) + (size_t)(b * T + row_in_batch) * (2 * a.ld_out) + h * 64;
+#pragma unroll
+      for (int i = 0; i < 64; i++) {
+        const float y = __uint_as_float(v[i]) * inv;
+        o[i] = tc::cvt16(y, a.f16);
+        o[a.lo_off + i] = tc::lo16(y, a.f16);
+      }
+    } else if (row_in_batch < T) {
       const float inv = 1.0f / l_run;
       __nv_bfloat16* o = a.out + (size_t)(b * T + row_in_batch) * a.ld_out + h * 64;
 #pragma unroll
@@ -926,6 +935,7 @@ hvx_status dit_attention(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* qk
     attr_set = true;
   }
   dim3 grid(cdiv(a.T, 128), a.heads, a.n_batch);
+  HVX_CHECK(!a.lo_off || !(getenv("HVX_ATTN_V1") || getenv("HVX_ATTN_V2")), HVX_ERR_UNSUPPORTED, "attention: split output needs the v5 kernel");
   if (getenv("HVX_ATTN_V1")) dit_attention_kernel<<<grid, 128, AT_SMEM, st>>>(tq, tk, tv, k_col0, a);
   else if (getenv("HVX_ATTN_V2")) dit_attention_v2_kernel<<<grid, 128, AT_SMEM, st>>>(tq, tk, tv, k_col0, a);
   else {
@@ -937,6 +947,7 @@ hvx_status dit_attention(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* qk
     if (!a4) { HVX_CUDA(cudaFuncSetAttribute(dit_attention_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM)); a4 = true; }
     static bool a5 = false;
     if (!a5) { HVX_CUDA(cudaFuncSetAttribute(dit_attention_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A5_SMEM)); a5 = true; }
+    HVX_CHECK(!a.lo_off || !(getenv("HVX_ATTN_V3") || getenv("HVX_ATTN_V4")), HVX_ERR_UNSUPPORTED, "attention: split output needs the v5 kernel");
     if (getenv("HVX_ATTN_V3")) dit_attention_v3_kernel<<<grid, 128, A3_SMEM, st>>>(tq, tk64, tv, k_col0, a);
     else if (getenv("HVX_ATTN_V4")) dit_attention_v4_kernel<<<grid, 256, A3_SMEM, st>>>(tq, tk64, tv, k_col0, a);
     else dit_attention_v5_kernel<<<grid, 160, A5_SMEM, st>>>(tq, tk64, tv, k_col0, a);

@@ -21,7 +21,8 @@ struct AttnArgs {
   int n_batch;
   int chunk;        // >0: streaming block-causal mask, key j visible to query i iff j < (i/chunk+1)*chunk
   int f16;          // 1: q/k/v/out are fp16 instead of bf16
-  int ld_out;       // = heads*64
+  int ld_out;       // = heads*64 (row stride is 2*ld_out when lo_off > 0)
+  int lo_off = 0;   // > 0: output written as split precision, hi at [col], lo at [lo_off + col] (flow parity mode, v5 kernel)
   __nv_bfloat16* out;   // [n_batch*T][heads*64]
 };
 

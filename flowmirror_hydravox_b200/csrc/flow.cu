@@ -46,7 +46,7 @@ __global__ void flow_spk_kernel(const float* __restrict__ emb, const float* __re
 // token embedding rows: fp32 copy (residual) and a fp16 copy padded to Cp columns and followed by zero
 // rows (conv look-ahead pad)
 __global__ void flow_embed_kernel(const int32_t* __restrict__ tok, const float* __restrict__ table, float* __restrict__ e32,
-                                  __half* __restrict__ e16, int n_tok, int n_rows16, int C, int Cp, int vocab) {
+                                  __half* __restrict__ e16, int n_tok, int n_rows16, int C, int Cp, int vocab, int split) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_rows16 * Cp) return;
   const int r = i / Cp, c = i - r * Cp;
@@ -57,7 +57,9 @@ __global__ void flow_embed_kernel(const int32_t* __restrict__ tok, const float* 
     v = table[(size_t)id * C + c];
     e32[(size_t)r * C + c] = v;
   }
-  e16[i] = __float2half_rn(v);
+  const __half hi = __float2half_rn(v);
+  if (split) { e16[(size_t)r * 2 * Cp + c] = hi; e16[(size_t)r * 2 * Cp + Cp + c] = __float2half_rn(v - __half2float(hi)); }
+  else e16[i] = hi;
 }
 
 // mu = repeat_interleave(mu_tok, 2); cond = prompt mel | 0; x = noise^T   (flow.py:404-419, flow_matching.py:223)
@@ -128,7 +130,7 @@ __global__ void dit_unpack_cm_kernel(const float* __restrict__ v, float* __restr
 __global__ void __launch_bounds__(256) flow_time_embed_kernel(const float* __restrict__ t_dev, const float* __restrict__ freqs,
                                                                const float* __restrict__ w0, const float* __restrict__ b0,
                                                                const float* __restrict__ w2, const float* __restrict__ b2,
-                                                               __half* __restrict__ st16, int dim) {
+                                                               __half* __restrict__ st16, int dim, int split) {
   __shared__ float s_in[256];
   __shared__ float s_h[2048];
   const float t = t_dev[blockIdx.x];
@@ -150,7 +152,14 @@ __global__ void __launch_bounds__(256) flow_time_embed_kernel(const float* __res
     float acc = 0.f;
     for (int i = lane; i < dim; i += 32) acc = fmaf(w2[(size_t)j * dim + i], s_h[i], acc);
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) { const float v = acc + b2[j]; st16[(size_t)blockIdx.x * dim + j] = __float2half_rn(v / (1.0f + expf(-v))); }
+    if (lane == 0) {
+      const float v = acc + b2[j];
+      const float y = v / (1.0f + expf(-v));
+      __half* orow = st16 + (size_t)blockIdx.x * dim * (split ? 2 : 1);
+      const __half hi = __float2half_rn(y);
+      orow[j] = hi;
+      if (split) orow[dim + j] = __float2half_rn(y - __half2float(hi));
+    }
   }
 }
 
@@ -166,7 +175,7 @@ __global__ void flow_rope_kernel(const float* __restrict__ inv_freq, float* __re
 // out16 = LayerNorm(h) * (1 + scale) + shift   (modules.py:230-244,262-265; eps 1e-6, no affine)
 __global__ void __launch_bounds__(256) dit_ln_mod_kernel(const float* __restrict__ h, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, __half* __restrict__ out, int M,
-                                                          int D) {
+                                                          int D, int split) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= M) return;
   const float* hr = h + (size_t)row * D;
@@ -184,12 +193,15 @@ __global__ void __launch_bounds__(256) dit_ln_mod_kernel(const float* __restrict
     if (k < n) { const float d = v[k] - mean; q += d * d; }
   for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = rsqrtf(q / (float)D + 1e-6f);
-  __half* orow = out + (size_t)row * D;
+  __half* orow = out + (size_t)row * D * (split ? 2 : 1);       // split: [hi | lo] per row (parity mode)
 #pragma unroll
   for (int k = 0; k < 32; k++)
     if (k < n) {
       const int c = k * 32 + lane;
-      orow[c] = __float2half_rn((v[k] - mean) * rstd * (1.0f + scale[c]) + shift[c]);
+      const float y = (v[k] - mean) * rstd * (1.0f + scale[c]) + shift[c];
+      const __half hi = __float2half_rn(y);
+      orow[c] = hi;
+      if (split) orow[D + c] = __float2half_rn(y - __half2float(hi));
     }
 }
 
@@ -220,6 +232,7 @@ struct FlowState {
   float* freqs_dev = nullptr;
   DevBuf ws, ws_small;
   int rope_T = -1;
+  int precise = 0;            // three-term split-fp16 GEMMs (hvx_config.flow_precise)
   // carve-up of ws for the current T (set by flow_plan)
   int T = 0, Tp = 0;
   __half *xin, *h0h, *c1, *n16, *qk, *vt, *ao, *f1;
@@ -254,36 +267,38 @@ hvx_status flow_finalize(hvx_engine* e) {
   FLOW_GET(get_t(e, "spk.w", HVX_F32, &f->spk_w, (int64_t)mel * c.flow_spk_in));
   FLOW_GET(get_t(e, "spk.b", HVX_F32, &f->spk_b, mel));
   FLOW_GET(get_t(e, "emb", HVX_F32, &f->emb, (int64_t)c.flow_vocab * mel));
-  FLOW_GET(get_t(e, "pla1.w", HVX_F16, &f->pla1_w, (int64_t)c.flow_pla_ch * 4 * ((mel + 63) / 64 * 64)));
+  FLOW_GET(get_t(e, "pla1.w", HVX_F16, &f->pla1_w, (c.flow_precise ? 2 : 1) * (int64_t)c.flow_pla_ch * 4 * ((mel + 63) / 64 * 64)));
   FLOW_GET(get_t(e, "pla1.b", HVX_F32, &f->pla1_b, c.flow_pla_ch));
-  FLOW_GET(get_t(e, "pla2.w", HVX_F16, &f->pla2_w, (int64_t)mel * 3 * c.flow_pla_ch));
+  FLOW_GET(get_t(e, "pla2.w", HVX_F16, &f->pla2_w, (c.flow_precise ? 2 : 1) * (int64_t)mel * 3 * c.flow_pla_ch));
   FLOW_GET(get_t(e, "pla2.b", HVX_F32, &f->pla2_b, mel));
   FLOW_GET(get_t(e, "tm0.w", HVX_F32, &f->tm0_w, (int64_t)dim * 256));
   FLOW_GET(get_t(e, "tm0.b", HVX_F32, &f->tm0_b, dim));
   FLOW_GET(get_t(e, "tm2.w", HVX_F32, &f->tm2_w, (int64_t)dim * dim));
   FLOW_GET(get_t(e, "tm2.b", HVX_F32, &f->tm2_b, dim));
-  FLOW_GET(get_t(e, "in.w", HVX_F16, &f->in_w, (int64_t)dim * 4 * mel));
+  const int64_t wx = c.flow_precise ? 2 : 1;          // parity mode: GEMM weights arrive as [hi | lo] (twice as wide)
+  f->precise = c.flow_precise ? 1 : 0;
+  FLOW_GET(get_t(e, "in.w", HVX_F16, &f->in_w, wx * dim * 4 * mel));
   FLOW_GET(get_t(e, "in.b", HVX_F32, &f->in_b, dim));
-  FLOW_GET(get_t(e, "pos1.w", HVX_F16, &f->pos1_w, dim * kpos));
+  FLOW_GET(get_t(e, "pos1.w", HVX_F16, &f->pos1_w, (c.flow_precise ? 2 : 1) * dim * kpos));
   FLOW_GET(get_t(e, "pos1.b", HVX_F32, &f->pos1_b, dim));
-  FLOW_GET(get_t(e, "pos2.w", HVX_F16, &f->pos2_w, dim * kpos));
+  FLOW_GET(get_t(e, "pos2.w", HVX_F16, &f->pos2_w, (c.flow_precise ? 2 : 1) * dim * kpos));
   FLOW_GET(get_t(e, "pos2.b", HVX_F32, &f->pos2_b, dim));
   FLOW_GET(get_t(e, "rope.inv_freq", HVX_F32, &f->inv_freq, 32));
   const int64_t nmod = (int64_t)c.flow_depth * 6 * dim + 2 * dim;
-  FLOW_GET(get_t(e, "mod.w", HVX_F16, &f->mod_w, nmod * dim));
+  FLOW_GET(get_t(e, "mod.w", HVX_F16, &f->mod_w, wx * nmod * dim));
   FLOW_GET(get_t(e, "mod.b", HVX_F32, &f->mod_b, nmod));
-  FLOW_GET(get_t(e, "proj.w", HVX_F16, &f->proj_w, (int64_t)mel * dim));
+  FLOW_GET(get_t(e, "proj.w", HVX_F16, &f->proj_w, wx * mel * dim));
   FLOW_GET(get_t(e, "proj.b", HVX_F32, &f->proj_b, mel));
   for (int i = 0; i < c.flow_depth; i++) {
     const std::string p = "blk" + std::to_string(i) + ".";
     FlowBlk& b = f->blk[i];
-    FLOW_GET(get_t(e, p + "qkv.w", HVX_F16, &b.qkv_w, (int64_t)3 * inner * dim));
+    FLOW_GET(get_t(e, p + "qkv.w", HVX_F16, &b.qkv_w, wx * 3 * inner * dim));
     FLOW_GET(get_t(e, p + "qkv.b", HVX_F32, &b.qkv_b, 3 * inner));
-    FLOW_GET(get_t(e, p + "out.w", HVX_F16, &b.out_w, (int64_t)dim * inner));
+    FLOW_GET(get_t(e, p + "out.w", HVX_F16, &b.out_w, wx * dim * inner));
     FLOW_GET(get_t(e, p + "out.b", HVX_F32, &b.out_b, dim));
-    FLOW_GET(get_t(e, p + "ff1.w", HVX_F16, &b.ff1_w, (int64_t)ff * dim));
+    FLOW_GET(get_t(e, p + "ff1.w", HVX_F16, &b.ff1_w, wx * ff * dim));
     FLOW_GET(get_t(e, p + "ff1.b", HVX_F32, &b.ff1_b, ff));
-    FLOW_GET(get_t(e, p + "ff2.w", HVX_F16, &b.ff2_w, (int64_t)dim * ff));
+    FLOW_GET(get_t(e, p + "ff2.w", HVX_F16, &b.ff2_w, wx * dim * ff));
     FLOW_GET(get_t(e, p + "ff2.b", HVX_F32, &b.ff2_b, dim));
   }
   if (!f->freqs_dev) {
@@ -314,9 +329,10 @@ static hvx_status flow_plan(hvx_engine* e, cudaStream_t st, int T) {
   const int Tp = (T + 7) & ~7;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
-  const size_t o_xin = take(M * 8 * mel * 2), o_h0 = take(M * dim * 4), o_h0h = take(M * dim * 2), o_c1 = take(M * dim * 2);
-  const size_t o_h = take(M * dim * 4), o_n = take(M * dim * 2), o_qk = take(M * 2 * inner * 2);
-  const size_t o_vt = take((size_t)2 * inner * Tp * 2), o_ao = take(M * inner * 2), o_f1 = take(M * ff * 2);
+  const size_t o_xin = take(M * 8 * mel * 2), o_h0 = take(M * dim * 4), o_h0h = take(M * dim * 2 * (f->precise ? 2 : 1)), o_c1 = take(M * dim * 2 * (f->precise ? 2 : 1));
+  const size_t ax = f->precise ? 2 : 1;
+  const size_t o_h = take(M * dim * 4), o_n = take(M * dim * 2 * ax), o_qk = take(M * 2 * inner * 2);
+  const size_t o_vt = take((size_t)2 * inner * Tp * 2), o_ao = take(M * inner * 2 * ax), o_f1 = take(M * ff * 2 * ax);
   const size_t o_v = take(M * mel * 4), o_rc = take((size_t)T * 32 * 4), o_rs = take((size_t)T * 32 * 4);
   const bool grew = off > f->ws.bytes;
   uint8_t* w = (uint8_t*)f->ws.get(off);
@@ -337,6 +353,16 @@ static hvx_status flow_plan(hvx_engine* e, cudaStream_t st, int T) {
   return HVX_OK;
 }
 
+// y = x W^T for the DiT linears.  Fast mode: fp16 x fp16.  Parity mode: x = [hi | lo] (row stride 2K), W = [hi | lo]
+// (row stride 2K), three products A_hi*W_hi + A_lo*W_hi + A_hi*W_lo accumulated in fp32 on the tensor core.
+static hvx_status flow_linear(hvx_engine* e, cudaStream_t st, const __half* x, const __half* w, int M, int N, int K, const GemmEpi& p) {
+  FlowState* f = e->flow;
+  if (!f->precise)
+    return gemm_bf16(e, st, (const __nv_bfloat16*)x, K, (const __nv_bfloat16*)w, K, M, N, K, p);
+  GemmAddr ga; ga.split3_kb = K / 64;
+  return gemm_bf16(e, st, (const __nv_bfloat16*)x, 2 * K, (const __nv_bfloat16*)w, 2 * K, M, N, 3 * K, p, &ga);
+}
+
 static GemmEpi epi16(void* out, int ldo, const float* bias, int act) {
   GemmEpi p; p.mode = EPI_BF16; p.f16 = 1; p.act = act; p.bias = bias; p.out = out; p.ldo = ldo; return p;
 }
@@ -349,43 +375,53 @@ static hvx_status flow_nfe(hvx_engine* e, cudaStream_t st, const float* mod, int
   hvx_status rc;
   // input embedding: Linear(320 -> dim) + causal grouped conv position embedding (dit.py:76-98, modules.py:115-144)
   { GemmEpi p; p.mode = EPI_F32; p.f16 = 1; p.bias = f->in_b; p.out = f->h0; p.ldo = dim; p.out2 = (__nv_bfloat16*)f->h0h;
-    GemmAddr gs; gs.b_kb_mod = (4 * mel) / 64;          // A = [hi | lo] against the same weights
-    if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->xin, 8 * mel, (const __nv_bfloat16*)f->in_w, 4 * mel, M, dim, 8 * mel, p, &gs))) return rc; }
+    if (f->precise) { p.ldo2 = 2 * dim; p.lo_off = dim; }
+    if (f->precise) {
+      if ((rc = flow_linear(e, st, f->xin, f->in_w, M, dim, 4 * mel, p))) return rc;
+    } else {
+      GemmAddr gs; gs.b_kb_mod = (4 * mel) / 64;          // A = [hi | lo] against the same weights
+      if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->xin, 8 * mel, (const __nv_bfloat16*)f->in_w, 4 * mel, M, dim, 8 * mel, p, &gs))) return rc;
+    } }
   GemmAddr ga; ga.n_batch = 2; ga.rows_per_batch = T; ga.a_cols = dim; ga.a_col_per_ntile = 64; ga.kb_per_tap = 1;
   ga.a_row0 = -(c.flow_pos_k - 1); ga.a_row_step = 1;
   const int kpos = c.flow_pos_k * 64;
-  { GemmEpi p = epi16(f->c1, dim, f->pos1_b, ACT_MISH);
-    if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->h0h, dim, (const __nv_bfloat16*)f->pos1_w, kpos, M, dim, kpos, p, &ga))) return rc; }
+  const int px = f->precise ? 2 : 1;
+  int kconv = kpos;
+  if (f->precise) { ga.a_cols = 2 * dim; ga.a_lo_off = dim; ga.split3_kb = c.flow_pos_k; kconv = 3 * kpos; }
+  { GemmEpi p = epi16(f->c1, px * dim, f->pos1_b, ACT_MISH);
+    p.lo_off = f->precise ? dim : 0;
+    if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->h0h, px * dim, (const __nv_bfloat16*)f->pos1_w, px * kpos, M, dim, kconv, p, &ga))) return rc; }
   { GemmEpi p; p.mode = EPI_F32; p.f16 = 1; p.act = ACT_MISH; p.bias = f->pos2_b; p.out = f->h; p.ldo = dim; p.resid = f->h0;
-    if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->c1, dim, (const __nv_bfloat16*)f->pos2_w, kpos, M, dim, kpos, p, &ga))) return rc; }
+    if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->c1, px * dim, (const __nv_bfloat16*)f->pos2_w, px * kpos, M, dim, kconv, p, &ga))) return rc; }
   for (int i = 0; i < c.flow_depth; i++) {
     const FlowBlk& b = f->blk[i];
     const float* m = mod + (size_t)i * 6 * dim;       // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
-    dit_ln_mod_kernel<<<cdiv(M, 8), 256, 0, st>>>(f->h, m + dim, m, f->n16, M, dim);
+    dit_ln_mod_kernel<<<cdiv(M, 8), 256, 0, st>>>(f->h, m + dim, m, f->n16, M, dim, f->precise);
     HVX_LAUNCH_CHECK(e);
     { GemmEpi p; p.mode = EPI_QKV; p.f16 = 1; p.bias = b.qkv_b; p.out = f->qk; p.ldo = 2 * inner; p.n_qk = 2 * inner;
       p.vt = (__nv_bfloat16*)f->vt; p.vt_ld = f->Tp; p.T = T; p.heads = c.flow_heads; p.rows_per_batch = T;
       p.rope_cos = f->rope_c; p.rope_sin = f->rope_s;
-      if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->n16, dim, (const __nv_bfloat16*)b.qkv_w, dim, M, 3 * inner, dim, p))) return rc; }
+      if ((rc = flow_linear(e, st, f->n16, b.qkv_w, M, 3 * inner, dim, p))) return rc; }
     { AttnArgs a; a.T = T; a.heads = c.flow_heads; a.n_batch = 2; a.chunk = streaming ? c.flow_chunk : 0; a.f16 = 1;
-      a.ld_out = inner; a.out = (__nv_bfloat16*)f->ao;
+      a.ld_out = inner; a.out = (__nv_bfloat16*)f->ao; a.lo_off = f->precise ? inner : 0;
       if ((rc = dit_attention(e, st, (const __nv_bfloat16*)f->qk, 2 * inner, inner, (const __nv_bfloat16*)f->vt, f->Tp, a))) return rc; }
     { GemmEpi p; p.mode = EPI_RESID_GATE; p.f16 = 1; p.bias = b.out_b; p.out = f->h; p.ldo = dim; p.gate = m + 2 * dim;
       p.gate_ld = 0; p.rows_per_batch = T;
-      if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->ao, inner, (const __nv_bfloat16*)b.out_w, inner, M, dim, inner, p))) return rc; }
-    dit_ln_mod_kernel<<<cdiv(M, 8), 256, 0, st>>>(f->h, m + 4 * dim, m + 3 * dim, f->n16, M, dim);
+      if ((rc = flow_linear(e, st, f->ao, b.out_w, M, dim, inner, p))) return rc; }
+    dit_ln_mod_kernel<<<cdiv(M, 8), 256, 0, st>>>(f->h, m + 4 * dim, m + 3 * dim, f->n16, M, dim, f->precise);
     HVX_LAUNCH_CHECK(e);
-    { GemmEpi p = epi16(f->f1, ff, b.ff1_b, ACT_GELU_TANH);
-      if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->n16, dim, (const __nv_bfloat16*)b.ff1_w, dim, M, ff, dim, p))) return rc; }
+    { GemmEpi p = epi16(f->f1, f->precise ? 2 * ff : ff, b.ff1_b, ACT_GELU_TANH);
+      p.lo_off = f->precise ? ff : 0;
+      if ((rc = flow_linear(e, st, f->n16, b.ff1_w, M, ff, dim, p))) return rc; }
     { GemmEpi p; p.mode = EPI_RESID_GATE; p.f16 = 1; p.bias = b.ff2_b; p.out = f->h; p.ldo = dim; p.gate = m + 5 * dim;
       p.gate_ld = 0; p.rows_per_batch = T;
-      if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->f1, ff, (const __nv_bfloat16*)b.ff2_w, ff, M, dim, ff, p))) return rc; }
+      if ((rc = flow_linear(e, st, f->f1, b.ff2_w, M, dim, ff, p))) return rc; }
   }
   const float* mf = mod + (size_t)c.flow_depth * 6 * dim;     // AdaLayerNormZero_Final: (scale, shift)  (modules.py:262)
-  dit_ln_mod_kernel<<<cdiv(M, 8), 256, 0, st>>>(f->h, mf, mf + dim, f->n16, M, dim);
+  dit_ln_mod_kernel<<<cdiv(M, 8), 256, 0, st>>>(f->h, mf, mf + dim, f->n16, M, dim, f->precise);
   HVX_LAUNCH_CHECK(e);
   { GemmEpi p; p.mode = EPI_F32; p.f16 = 1; p.bias = f->proj_b; p.out = f->v; p.ldo = mel;
-    if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->n16, dim, (const __nv_bfloat16*)f->proj_w, dim, M, mel, dim, p))) return rc; }
+    if ((rc = flow_linear(e, st, f->n16, f->proj_w, M, mel, dim, p))) return rc; }
   return HVX_OK;
 }
 
@@ -395,10 +431,10 @@ static hvx_status flow_mods(hvx_engine* e, cudaStream_t st, const float* t_dev, 
   const hvx_config& c = e->cfg;
   const int dim = c.flow_dim;
   const int nmod = c.flow_depth * 6 * dim + 2 * dim;
-  flow_time_embed_kernel<<<n, 256, 0, st>>>(t_dev, f->freqs_dev, f->tm0_w, f->tm0_b, f->tm2_w, f->tm2_b, st16, dim);
+  flow_time_embed_kernel<<<n, 256, 0, st>>>(t_dev, f->freqs_dev, f->tm0_w, f->tm0_b, f->tm2_w, f->tm2_b, st16, dim, f->precise);
   HVX_LAUNCH_CHECK(e);
   GemmEpi p; p.mode = EPI_F32; p.f16 = 1; p.bias = f->mod_b; p.out = mod; p.ldo = nmod;
-  return gemm_bf16(e, st, (const __nv_bfloat16*)st16, dim, (const __nv_bfloat16*)f->mod_w, dim, n, nmod, dim, p);
+  return flow_linear(e, st, st16, f->mod_w, n, nmod, dim, p);
 }
 
 }  // namespace hvx
@@ -427,10 +463,10 @@ extern "C" hvx_status hvx_flow_inference(hvx_engine* e, const int32_t* tokens, i
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
   const int Cp = (mel + 63) / 64 * 64;                              // embedding rows padded to whole 64-wide k-blocks
-  const size_t o_spk = take(mel * 4), o_e32 = take((size_t)ntok * mel * 4), o_e16 = take((size_t)(ntok + 3) * Cp * 2);
-  const size_t o_y1 = take((size_t)L1 * pc * 2), o_mut = take((size_t)L1 * mel * 4);
+  const size_t o_spk = take(mel * 4), o_e32 = take((size_t)ntok * mel * 4), o_e16 = take((size_t)(ntok + 3) * Cp * 4);
+  const size_t o_y1 = take((size_t)L1 * pc * 4), o_mut = take((size_t)L1 * mel * 4);
   const size_t o_mu = take((size_t)T * mel * 4), o_cond = take((size_t)T * mel * 4), o_x = take((size_t)T * mel * 4);
-  const size_t o_mod = take((size_t)n_timesteps * nmod * 4), o_t = take(64 * 4), o_st = take((size_t)64 * dim * 2);
+  const size_t o_mod = take((size_t)n_timesteps * nmod * 4), o_t = take(64 * 4), o_st = take((size_t)64 * dim * 4);
   uint8_t* w = (uint8_t*)f->ws_small.get(off);
   HVX_CHECK(w, HVX_ERR_CUDA, "flow: buffer allocation of %zu bytes failed", off);
   f->spks = (float*)(w + o_spk); f->e32 = (float*)(w + o_e32); f->e16 = (__half*)(w + o_e16); f->y1p = (__half*)(w + o_y1);
@@ -442,16 +478,20 @@ extern "C" hvx_status hvx_flow_inference(hvx_engine* e, const int32_t* tokens, i
   // ---- pre-net (flow.py:387-419)
   flow_spk_kernel<<<1, 256, 0, st>>>(embedding, f->spk_w, f->spk_b, f->spks, c.flow_spk_in, mel);
   HVX_LAUNCH_CHECK(e);
-  flow_embed_kernel<<<cdiv((ntok + 3) * Cp, 256), 256, 0, st>>>(tokens, f->emb, f->e32, f->e16, ntok, ntok + 3, mel, Cp, c.flow_vocab);
+  const int px = f->precise ? 2 : 1;
+  flow_embed_kernel<<<cdiv((ntok + 3) * Cp, 256), 256, 0, st>>>(tokens, f->emb, f->e32, f->e16, ntok, ntok + 3, mel, Cp, c.flow_vocab, f->precise);
   HVX_LAUNCH_CHECK(e);
   { // conv1 k4, 3 look-ahead rows (zero rows after the last token when finalize): implicit GEMM, K = 4*Cp
-    GemmEpi p = epi16(f->y1p, pc, f->pla1_b, ACT_LRELU);
-    GemmAddr ga; ga.rows_per_batch = L1; ga.a_rows = ntok + 3; ga.a_cols = Cp; ga.kb_per_tap = Cp / 64; ga.a_row_step = 1;
-    if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->e16, Cp, (const __nv_bfloat16*)f->pla1_w, 4 * Cp, L1, pc, 4 * Cp, p, &ga))) return rc; }
+    GemmEpi p = epi16(f->y1p, px * pc, f->pla1_b, ACT_LRELU);
+    p.lo_off = f->precise ? pc : 0;
+    GemmAddr ga; ga.rows_per_batch = L1; ga.a_rows = ntok + 3; ga.a_cols = px * Cp; ga.kb_per_tap = Cp / 64; ga.a_row_step = 1;
+    if (f->precise) { ga.a_lo_off = Cp; ga.split3_kb = 4 * Cp / 64; }
+    if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->e16, px * Cp, (const __nv_bfloat16*)f->pla1_w, px * 4 * Cp, L1, pc, (f->precise ? 3 : 1) * 4 * Cp, p, &ga))) return rc; }
   { // conv2 k3 causal (left pad 2 = out-of-bounds rows) + residual
     GemmEpi p; p.mode = EPI_F32; p.f16 = 1; p.bias = f->pla2_b; p.out = f->mu_tok; p.ldo = mel; p.resid = f->e32;
-    GemmAddr ga; ga.rows_per_batch = L1; ga.a_cols = pc; ga.kb_per_tap = pc / 64; ga.a_row0 = -2; ga.a_row_step = 1;
-    if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->y1p, pc, (const __nv_bfloat16*)f->pla2_w, 3 * pc, L1, mel, 3 * pc, p, &ga))) return rc; }
+    GemmAddr ga; ga.rows_per_batch = L1; ga.a_cols = px * pc; ga.kb_per_tap = pc / 64; ga.a_row0 = -2; ga.a_row_step = 1;
+    if (f->precise) { ga.a_lo_off = pc; ga.split3_kb = 3 * pc / 64; }
+    if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->y1p, px * pc, (const __nv_bfloat16*)f->pla2_w, px * 3 * pc, L1, mel, (f->precise ? 3 : 1) * 3 * pc, p, &ga))) return rc; }
   flow_init_kernel<<<cdiv(T * mel, 256), 256, 0, st>>>(f->mu_tok, prompt_feat, noise, f->mu, f->cond, f->x, T, mel, mel_len1,
                                                         c.flow_noise_frames);
   HVX_LAUNCH_CHECK(e);
@@ -496,7 +536,7 @@ extern "C" hvx_status hvx_dit_estimator(hvx_engine* e, const float* x, const flo
   const int nmod = c.flow_depth * 6 * dim + 2 * dim;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
-  const size_t o_mod = take((size_t)nmod * 4), o_st = take((size_t)64 * dim * 2);
+  const size_t o_mod = take((size_t)nmod * 4), o_st = take((size_t)64 * dim * 4);
   uint8_t* w = (uint8_t*)f->ws_small.get(off);
   HVX_CHECK(w, HVX_ERR_CUDA, "estimator: buffer allocation failed");
   float* mod = (float*)(w + o_mod);

@@ -95,7 +95,7 @@ __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx,
         if (epi.lo_off) {
 #pragma unroll
           for (int j = 0; j < 32; j++)
-            if (col0 + j < N) o[epi.lo_off + j] = __float2bfloat16(f[j] - __bfloat162float(__float2bfloat16(f[j])));
+            if (col0 + j < N) reinterpret_cast<uint16_t*>(o)[epi.lo_off + j] = tc::lo16(f[j], epi.f16);
         }
         if (col0 + 32 <= N) {
 #pragma unroll
@@ -123,7 +123,7 @@ __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx,
           #pragma unroll
           for (int j = 0; j < 32; j++) if (col0 + j < N) {
             reinterpret_cast<uint16_t*>(o2)[j] = tc::cvt16(f[j], epi.f16);
-            if (epi.lo_off) o2[epi.lo_off + j] = __float2bfloat16(f[j] - __bfloat162float(__float2bfloat16(f[j])));
+            if (epi.lo_off) reinterpret_cast<uint16_t*>(o2)[epi.lo_off + j] = tc::lo16(f[j], epi.f16);
           }
         }
       } else if (MODE == EPI_RESID_GATE) {
@@ -153,7 +153,7 @@ __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx,
           if (col0 + j < N) {
             const float y = (f[j] / (1.0f + expf(-f[j]))) * f[j + 1];
             o[j >> 1] = tc::cvt16(y, epi.f16);
-            if (epi.lo_off) o[epi.lo_off + (j >> 1)] = tc::cvt16(y - __bfloat162float(__float2bfloat16(y)), 0);
+            if (epi.lo_off) o[epi.lo_off + (j >> 1)] = tc::lo16(y, epi.f16);
           }
       } else if (MODE == EPI_QKV) {
         const int t = row - bidx * epi.T;       // rows_per_batch == T
@@ -228,11 +228,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         tc::mbar_wait(&empty_bar[s], ph ^ 1);
         tc::mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
         uint8_t* sa = smem + s * S::STAGE_BYTES;
-        const int tap = ad.kb_per_tap ? kb / ad.kb_per_tap : 0;
-        const int kin = ad.kb_per_tap ? kb - tap * ad.kb_per_tap : kb;
-        tc::tma_load_3d(sa, &tma_a, &full_bar[s], ad.a_col0 + blockIdx.x * ad.a_col_per_ntile + kin * BK,
+        int term = 0, kbt = kb;                       // split precision: which of the three products, k-block inside it
+        if (ad.split3_kb) { term = kb / ad.split3_kb; kbt = kb - term * ad.split3_kb; }
+        const int tap = ad.kb_per_tap ? kbt / ad.kb_per_tap : 0;
+        const int kin = ad.kb_per_tap ? kbt - tap * ad.kb_per_tap : kbt;
+        const int kbb = ad.split3_kb ? kbt + (term == 2 ? ad.split3_kb : 0) : (ad.b_kb_mod ? kb % ad.b_kb_mod : kb);
+        tc::tma_load_3d(sa, &tma_a, &full_bar[s], ad.a_col0 + blockIdx.x * ad.a_col_per_ntile + kin * BK + (term == 1 ? ad.a_lo_off : 0),
                         m0 + ad.a_row0 + tap * ad.a_row_step, batch);
-        tc::tma_load_2d(sa + S::A_BYTES, &tma_b, &full_bar[s], (ad.b_kb_mod ? kb % ad.b_kb_mod : kb) * BK, n0);
+        tc::tma_load_2d(sa + S::A_BYTES, &tma_b, &full_bar[s], kbb * BK, n0);
       }
     }
   } else if (warp == 1) {
@@ -335,8 +338,10 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           tc::mbar_wait(&empty_bar[s], ph ^ 1);
           tc::mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
           uint8_t* sa = smem + s * S::STAGE_BYTES;
-          tc::tma_load_3d(sa, &tma_a, &full_bar[s], kb * BK, mt * BM, 0);
-          tc::tma_load_2d(sa + S::A_BYTES, &tma_b, &full_bar[s], kb * BK, nt * PBN);
+          int kba = kb, kbb = kb;
+          if (ad.split3_kb) { kba = kb < 2 * ad.split3_kb ? kb : kb - 2 * ad.split3_kb; kbb = kb < ad.split3_kb ? kb : kb - ad.split3_kb; }
+          tc::tma_load_3d(sa, &tma_a, &full_bar[s], kba * BK, mt * BM, 0);
+          tc::tma_load_2d(sa + S::A_BYTES, &tma_b, &full_bar[s], kbb * BK, nt * PBN);
         }
       }
     }
@@ -479,12 +484,13 @@ hvx_status gemm_bf16(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* A, int
   GemmAddr ad;
   if (addr) ad = *addr;
   if (ad.rows_per_batch == 0) ad.rows_per_batch = M;
-  if (ad.a_cols == 0) ad.a_cols = K;
+  if (ad.split3_kb && ad.a_lo_off == 0) ad.a_lo_off = ad.split3_kb * BK;
+  if (ad.a_cols == 0) ad.a_cols = ad.split3_kb ? 2 * ad.split3_kb * BK : K;
   if (ad.a_rows == 0) ad.a_rows = ad.rows_per_batch;
   HVX_CHECK((lda % 8) == 0 && (ldb % 8) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0, HVX_ERR_ARG,
             "gemm: operands must be 16-byte aligned with leading dims multiple of 8 (lda=%d ldb=%d)", lda, ldb);
   CUtensorMap ta, tb;
-  const uint64_t kB = ad.b_kb_mod ? (uint64_t)ad.b_kb_mod * BK : (uint64_t)K;      // width of the weight matrix
+  const uint64_t kB = ad.split3_kb ? (uint64_t)2 * ad.split3_kb * BK : ad.b_kb_mod ? (uint64_t)ad.b_kb_mod * BK : (uint64_t)K;      // width of the weight matrix
   HVX_CHECK(make_tmap_bf16_3d(&ta, A, ad.n_batch, ad.a_rows, ad.a_cols, lda, BM, BK), HVX_ERR_CUDA,
             "gemm: cuTensorMapEncodeTiled(A) failed");
   // big plain GEMMs (the DiT linears): persistent 128 x 256 tiles

@@ -63,6 +63,10 @@ struct GemmAddr {
   // split-precision activations: A = [hi | lo] (two bf16 halves of an fp32 value, K' = 2K) against the same
   // weights: k-block kb of A multiplies k-block kb % b_kb_mod of B (0 = off)
   int b_kb_mod = 0;
+  // three-term split precision (flow parity mode): A = [hi | lo] (2K0 wide), B = [hi | lo] (2K0 wide), K' = 3*K0:
+  //   k-blocks [0,n0) -> A_hi*B_hi, [n0,2n0) -> A_lo*B_hi, [2n0,3n0) -> A_hi*B_lo   with n0 = split3_kb = K0/64 (0 = off)
+  int split3_kb = 0;
+  int a_lo_off = 0;            // element offset of the lo half inside an A row (0 -> split3_kb * 64); convs: the row width
 };
 
 hvx_status gemm_bf16(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb,

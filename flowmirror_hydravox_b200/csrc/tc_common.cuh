@@ -141,6 +141,12 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, int f16) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+// residual of a after rounding to the 16-bit type: a - float(cvt16(a)), itself rounded to 16 bits (split precision hi|lo)
+__device__ __forceinline__ uint16_t lo16(float a, int f16) {
+  if (f16) { __half t = __float2half_rn(a - __half2float(__float2half_rn(a))); return *reinterpret_cast<uint16_t*>(&t); }
+  __nv_bfloat16 t = __float2bfloat16(a - __bfloat162float(__float2bfloat16(a)));
+  return *reinterpret_cast<uint16_t*>(&t);
+}
 __device__ __forceinline__ uint16_t cvt16(float a, int f16) {
   if (f16) { __half t = __float2half_rn(a); return *reinterpret_cast<uint16_t*>(&t); }
   __nv_bfloat16 t = __float2bfloat16(a);

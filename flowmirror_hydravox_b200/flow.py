@@ -27,7 +27,7 @@ class NativeFlow:
         assert self.noise.shape[1] == self.dims.noise_frames
 
     def load_state_dict(self, sd, strict=True):
-        self.engine.set_tensors(L.STAGE_FLOW, pack_flow(sd, self.dims))
+        self.engine.set_tensors(L.STAGE_FLOW, pack_flow(sd, self.dims, precise=getattr(self.engine, "flow_precise", False)))
         self.engine.finalize(L.STAGE_FLOW)
         return self
 

@@ -57,7 +57,15 @@ def pack_hift(sd: Dict[str, torch.Tensor], d: D.HiftDims) -> Dict[str, torch.Ten
     return o
 
 
-def pack_flow(sd: Dict[str, torch.Tensor], d: D.FlowDims) -> Dict[str, torch.Tensor]:
+def _split16(w: torch.Tensor) -> torch.Tensor:
+    """[N][K] fp32 -> [N][2K] fp16 = [hi | lo] with lo = fp16(w - hi): ~22 mantissa bits for the parity-mode GEMMs."""
+    w = w.to(torch.float32)
+    hi = w.to(torch.float16)
+    lo = (w - hi.float()).to(torch.float16)
+    return torch.cat([hi, lo], dim=1).contiguous()
+
+
+def pack_flow(sd: Dict[str, torch.Tensor], d: D.FlowDims, precise: bool = False) -> Dict[str, torch.Tensor]:
     """CausalMaskedDiffWithDiT state_dict (flow.py:296-365, DiT/dit.py:104-143) -> engine tensors.
     GEMM operands are fp16 (the reference serves this stage with .half(), infer_speech_model.py:105-117),
     biases / tiny layers fp32.  Conv weights become implicit-GEMM B operands: column = tap*C + ci."""
@@ -106,6 +114,21 @@ def pack_flow(sd: Dict[str, torch.Tensor], d: D.FlowDims) -> Dict[str, torch.Ten
     o["mod.b"] = torch.cat(mods_b, 0).to(f).contiguous()
     o["proj.w"] = sd[p + "proj_out.weight"].to(h).contiguous()
     o["proj.b"] = sd[p + "proj_out.bias"].to(f).contiguous()
+    if precise:                                   # parity mode: every GEMM operand gets split-fp16 weights from the fp32 originals
+        o["pla1.w"] = _split16(w1p.reshape(w1.shape[0], -1))
+        o["pla2.w"] = _split16(w2.permute(0, 2, 1).reshape(w2.shape[0], -1))
+        for i, c in enumerate(("conv1", "conv2"), 1):
+            w = sd[p + f"input_embed.conv_pos_embed.{c}.0.weight"].to(f)
+            o[f"pos{i}.w"] = _split16(w.permute(0, 2, 1).reshape(w.shape[0], -1))
+        o["in.w"] = _split16(sd[p + "input_embed.proj.weight"])
+        o["proj.w"] = _split16(sd[p + "proj_out.weight"])
+        o["mod.w"] = _split16(torch.cat(mods_w, 0))
+        for i in range(d.depth):
+            bp = p + f"transformer_blocks.{i}."
+            o[f"blk{i}.qkv.w"] = _split16(torch.cat([sd[bp + f"attn.to_{n}.weight"] for n in "qkv"], 0))
+            o[f"blk{i}.out.w"] = _split16(sd[bp + "attn.to_out.0.weight"])
+            o[f"blk{i}.ff1.w"] = _split16(sd[bp + "ff.ff.0.0.weight"])
+            o[f"blk{i}.ff2.w"] = _split16(sd[bp + "ff.ff.2.weight"])
     return o
 
 

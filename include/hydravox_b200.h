@@ -45,6 +45,7 @@ typedef struct hvx_config {
   int flow_mel, flow_spk_in, flow_vocab, flow_pla_ch, flow_dim, flow_depth, flow_heads, flow_dim_head;
   int flow_ff_mult, flow_chunk, flow_pos_k, flow_pos_groups, flow_noise_frames;
   float flow_cfg_rate;
+  int flow_precise;  /* 0: fp16 x fp16 GEMMs (the reference's serving precision); 1: three-term split-fp16 GEMMs (parity mode, <= 1e-3 on mel) */
   /* llm: cosyvoice/llm/llm_multi_head_v3.py:622-689 + HF Qwen2Config */
   int llm_hidden, llm_layers, llm_q_heads, llm_kv_heads, llm_head_dim, llm_inter, llm_text_vocab;
   int llm_speech_vocab, llm_mtp_heads, llm_mtp_inter, llm_max_ctx, llm_max_seqs;

@@ -64,6 +64,31 @@ def test_estimator_seam(flows, golden, name):
     assert err.mean().item() < 1e-3 * max(scale, 1.0) and err.max().item() < 2e-2 * max(scale, 1.0)
 
 
+@pytest.mark.parametrize("name,fd", [("tiny", D.FLOW_TINY), ("full", D.FLOW_FULL), ("mid", D.FLOW_FULL)])
+def test_flow_parity_mode_meets_north_star(golden, name, fd):
+    """flow_precise=1: three-term split-fp16 GEMMs (A_hi W_hi + A_lo W_hi + A_hi W_lo, fp32 accumulate).  north_star:
+    <= 1e-3 max-abs on mel frames against the reference path (here: the reference modules evaluated in fp32)."""
+    if not os.path.exists(os.path.join(os.path.dirname(__file__), "golden", f"flow_{name}.pt")):
+        pytest.skip("fixture not minted")
+    from flowmirror_hydravox_b200 import _lib as L
+    from flowmirror_hydravox_b200.flow import NativeFlow
+    g = golden(f"flow_{name}")
+    e = L.Engine(fd=fd, flow_precise=True)
+    f = NativeFlow(e)
+    f.load_state_dict(synth.flow_state_dict(fd, g["seed"]))
+    for key, streaming, finalize in (("full", False, True), ("stream", True, True), ("chunk", True, False)):
+        mel = _run(f, g, streaming, finalize)
+        err = (mel - g["mel_" + key]).abs()
+        print(f"[flow precise {name}/{key}] max-abs {err.max():.3e} mean-abs {err.mean():.3e}")
+        assert err.max().item() < 1e-3
+    i = g["est_in"]
+    out = f.estimator(i["x"], None, i["mu"], i["t"], i["spks"], i["cond"]).cpu()
+    err = (out - g["est_out"]).abs()
+    print(f"[estimator precise {name}] max-abs {err.max():.3e} mean-abs {err.mean():.3e}")
+    assert err.max().item() < 1e-3
+    e.close()
+
+
 def test_flow_mid_fixture(golden):
     """full dims, 400 frames (4 attention tiles, 8 streaming chunks), 10 Euler steps."""
     if not os.path.exists(os.path.join(os.path.dirname(__file__), "golden", "flow_mid.pt")):
