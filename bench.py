@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--ratio", type=float, default=8.0, help="speech tokens per text token (min=max, SURVEY 8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--first-audio-runs", type=int, default=20, help="streaming first-audio latency samples (0 = skip)")
+    ap.add_argument("--parity-mode-steps", type=int, default=2, help="also time the parity mode (fp32 KV cache, split-fp16 flow GEMMs); 0 = skip")
     ap.add_argument("--cpu-tokens", type=int, default=128, help="speech tokens in the CPU baseline sample (~10-20 s of CPU work)")
     return ap.parse_args()
 
@@ -327,6 +328,30 @@ def native_arm(a):
                     "ms_per_step": ms_e2e / a.steps, "rtf": 25.0 * world / e2e if e2e else None,
                     "stage_ms_per_step": {k: v / a.steps for k, v in stage_acc.items()}},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof}
+    # the same step in parity mode (the mode whose mel error is <= 1e-3 against the fp32 reference, tests/test_flow_gpu.py)
+    if a.parity_mode_steps > 0 and world == 1:
+        del flush
+        torch.cuda.empty_cache()
+        pm = ModelManager(hd=hd, fd=fd, ld=ld, device=f"cuda:{local}", max_ctx=max_ctx, max_seqs=max(a.batch, 1), n_timesteps=a.cfm_steps,
+                          sine_seconds=n_tok / 25 + 2, kv_f32=True, flow_precise=True)
+        pm.load_state_dicts(synth.llm_state_dict(ld, 0, dtype=torch.bfloat16, eos_scale=0.0), synth.flow_state_dict(fd, 0),
+                            synth.hift_state_dict(hd, 0))
+        def pm_step():
+            w, t = pm.synthesize_batch(reqs, head_k=a.head_k, sampling=SAMPLING, n_timesteps=a.cfm_steps, min_ratio=a.ratio,
+                                       max_ratio=a.ratio, u=u_all, return_tokens=True)
+            return sum(len(x) for x in t)
+        pm_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_pm = sum(pm_step() for _ in range(a.parity_mode_steps))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        line["parity_mode"] = {"e2e_value": n_pm / dt, "unit": "tokens/s", "rtf": 25.0 * dt / n_pm, "steps": a.parity_mode_steps,
+                               "stage_ms": dict(pm.last_stage_ms),
+                               "what": "fp32 KV cache + three-term split-fp16 flow GEMMs (mel max-abs 2e-4 vs the fp32 reference); "
+                                       "the headline numbers use the serving mode (bf16 KV cache, fp16 flow operands = reference precision)"}
+        pm.engine.close()
+        del pm
     # BASELINE config 5: first-audio latency of the streaming path (AR decode overlapped with chunked flow + vocoder)
     if a.first_audio_runs > 0:
         from flowmirror_hydravox_b200.streaming import StreamingSynthesizer

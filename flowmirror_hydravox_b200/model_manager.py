@@ -40,8 +40,11 @@ def _clean(sd: Dict) -> Dict[str, torch.Tensor]:
 class ModelManager:
     def __init__(self, hd: D.HiftDims = D.HIFT_FULL, fd: D.FlowDims = D.FLOW_FULL, ld: D.LlmDims = D.LLM_FULL,
                  device: str = "cuda:0", max_ctx: int = 8192, max_seqs: int = 32, kv_f32: bool = False, seed: int = 0,
-                 n_timesteps: int = 10, sine_seconds: float = 300.0):
-        self.engine = L.Engine(hd=hd, fd=fd, ld=ld, max_ctx=max_ctx, max_seqs=max_seqs, device=device, kv_f32=kv_f32)
+                 n_timesteps: int = 10, sine_seconds: float = 300.0, flow_precise: bool = False):
+        """kv_f32 / flow_precise select the parity mode (fp32 KV cache, three-term split-fp16 flow GEMMs); the default is the
+        serving mode (bf16 KV cache, fp16 x fp16 flow GEMMs = the reference's own serving precision)."""
+        self.engine = L.Engine(hd=hd, fd=fd, ld=ld, max_ctx=max_ctx, max_seqs=max_seqs, device=device, kv_f32=kv_f32,
+                               flow_precise=flow_precise)
         self.device = "cuda"
         self.configs = {"sample_rate": hd.sr}
         self.models = {"llm": NativeLLM(self.engine, seed=seed), "flow": NativeFlow(self.engine, n_timesteps=n_timesteps),

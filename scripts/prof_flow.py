@@ -5,7 +5,8 @@ from flowmirror_hydravox_b200 import dims as D, synth, _lib as L
 from flowmirror_hydravox_b200.flow import NativeFlow
 fd = D.FLOW_FULL
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-e = L.Engine(fd=fd); f = NativeFlow(e); f.load_state_dict(synth.flow_state_dict(fd, 0))
+import os
+e = L.Engine(fd=fd, flow_precise=os.environ.get("HVX_FLOW_PRECISE") == "1"); f = NativeFlow(e); f.load_state_dict(synth.flow_state_dict(fd, 0))
 u = synth.utterance(D.LLM_FULL, fd, 128, seed=1986)
 tok = torch.randint(0, fd.vocab, (1, 1024), generator=torch.Generator().manual_seed(3))
 for it in range(2):
