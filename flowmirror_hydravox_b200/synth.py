@@ -75,6 +75,27 @@ def hift_state_dict(d: HiftDims, seed: int = 0) -> Dict[str, torch.Tensor]:
     return sd
 
 
+def hift_t_state_dict(d: HiftDims, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Checkpoint of the non-causal HiFTGenerator variant (generator.py:378-569, SURVEY 8 a12'): same parameter names as the
+    causal one; `ups.{i}` are weight-normed ConvTranspose1d weights (Cin, Cout, k), `source_downs` have kernel 2u / stride u,
+    the F0 predictor is ConvRNNF0Predictor (k3, pad 1)."""
+    sd = hift_state_dict(d, seed)
+    g = _gen(seed + 7)
+    for i, (u, k) in enumerate(zip(d.ups, d.up_k)):
+        cin, cout = d.base >> i, d.base >> (i + 1)
+        v = _randn(g, cin, cout, k)
+        sd[f"ups.{i}.parametrizations.weight.original1"] = v
+        sd[f"ups.{i}.parametrizations.weight.original0"] = v.reshape(cin, -1).norm(dim=1).reshape(cin, 1, 1) * (1.0 / (cin * k / u) ** 0.5)
+        sd[f"ups.{i}.bias"] = _randn(g, cout, std=0.05)
+    v = _randn(g, d.base, d.mel, 7)
+    sd["conv_pre.parametrizations.weight.original1"] = v
+    sd["conv_pre.parametrizations.weight.original0"] = v.reshape(d.base, -1).norm(dim=1).reshape(d.base, 1, 1) * (0.5 / (d.mel * 7) ** 0.5)
+    v = _randn(g, d.f0_ch, d.mel, 3)
+    sd["f0_predictor.condnet.0.parametrizations.weight.original1"] = v
+    sd["f0_predictor.condnet.0.parametrizations.weight.original0"] = v.reshape(d.f0_ch, -1).norm(dim=1).reshape(d.f0_ch, 1, 1) * (0.5 / (d.mel * 3) ** 0.5)
+    return sd
+
+
 def hift_sine_table(d: HiftDims, n_frames: int, seed: int = 11) -> torch.Tensor:
     """Stand-in for SineGen2.sine_waves (generator.py:226): uniform[0,1) rows, (n_frames*frame, H)."""
     return torch.rand(n_frames * d.frame_samples, d.harmonics, generator=_gen(seed))

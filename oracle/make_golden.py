@@ -68,6 +68,40 @@ def golden_hift(name, dims, T, seed):
                     sd_checksum=checksum(sd)), os.path.join(OUT, f"hift_{name}.pt"))
 
 
+def golden_hift_t(name, dims, T, seed):
+    """a12': the non-causal ConvTranspose1d HiFTGenerator.  Its source module is stochastic (fresh noise + random initial
+    phase per call): the fixture pins decode(mel, s) for an explicit source s, the F0 predictor, and the whole
+    `inference` with the global RNG seeded (the oracle replays the same draws through hift_ref.draw_source_noise)."""
+    m = refshim.build_hift_t(dims)
+    sd = synth.hift_t_state_dict(dims, seed)
+    m.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(seed + 200)
+    mel = torch.rand(1, dims.mel, T, generator=g) * 6.0 - 6.0
+    s = torch.tanh(torch.randn(1, 1, T * dims.frame_samples, generator=g) * 0.3)
+    wav = m.decode(x=mel, s=s)
+    f0 = m.f0_predictor(mel)
+    wav_o = hift_ref.decode_transposed(sd, mel, s, dims)
+    f0_o = hift_ref.f0_predict_nc(hift_ref.fold_weight_norm(sd), mel)
+    e, ef = (wav - wav_o).abs().max().item(), ((f0 - f0_o).abs() / (f0.abs() + 1)).max().item()
+    print(f"[hift_t:{name}] T={T} ref-vs-oracle wav max-abs {e:.2e} f0 rel {ef:.2e}; rms {wav.pow(2).mean().sqrt():.3f} sat {(wav.abs() >= 0.99).float().mean():.3f}")
+    assert e < 5e-6 and ef < 1e-4
+    torch.manual_seed(seed + 300)
+    wav_i, s_i = m.inference(speech_feat=mel)
+    torch.manual_seed(seed + 300)
+    noise = hift_ref.draw_source_noise(T * dims.frame_samples, dims.harmonics)
+    wav_io, s_io = hift_ref.inference_transposed(sd, mel, noise, dims, f0=f0)
+    es, ei = (s_i - s_io).abs().max().item(), (wav_i - wav_io).abs().max().item()
+    cache = s[:, :, : 3 * dims.frame_samples]
+    torch.manual_seed(seed + 300)
+    wav_c, s_c = m.inference(speech_feat=mel, cache_source=cache)
+    wav_co, _ = hift_ref.inference_transposed(sd, mel, noise, dims, f0=f0, cache_source=cache)
+    ec = (wav_c - wav_co).abs().max().item()
+    print(f"[hift_t:{name}] inference (RNG pinned): source max-abs {es:.2e} wav max-abs {ei:.2e} (cache_source {ec:.2e}); voiced {(f0 > 10).float().mean():.2f}")
+    assert es < 2e-4 and ei < 2e-3 and ec < 2e-3
+    torch.save(dict(dims=name, seed=seed, T=T, mel=mel, s=s, wav=wav, f0=f0, noise=noise, wav_inf=wav_i, src_inf=s_i,
+                    wav_cache=wav_c, sd_checksum=checksum(sd)), os.path.join(OUT, f"hift_t_{name}.pt"))
+
+
 def golden_flow(name, dims, N, P, n_steps, seed):
     refshim.install()
     import cosyvoice.flow.flow as flowmod
@@ -170,9 +204,16 @@ def golden_llm(name, dims, n_text, n_ptext, P, cases, seed):
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if sys.argv[1:] == ["hift_t"]:                                  # regenerate only the a12' fixtures
+        with torch.no_grad():
+            golden_hift_t("tiny", D.HIFT_TINY, 29, 0)
+            golden_hift_t("full", D.HIFT_FULL, 20, 0)
+        return
     with torch.no_grad():
         golden_hift("tiny", D.HIFT_TINY, 37, 0)
         golden_hift("full", D.HIFT_FULL, 24, 0)
+        golden_hift_t("tiny", D.HIFT_TINY, 29, 0)
+        golden_hift_t("full", D.HIFT_FULL, 20, 0)
         golden_flow("tiny", D.FLOW_TINY, 21, 10, 10, 0)
         golden_flow("full", D.FLOW_FULL, 24, 8, 4, 0)
         sp1 = dict(top_p=0.9, top_k=10, win_size=24, tau_r=0.2)     # server tts defaults (router.py:22-44)

@@ -202,6 +202,24 @@ def build_hift(cfg, seed=0):
     return m.eval()
 
 
+def build_hift_t(cfg, seed=0):
+    """The reference's non-causal HiFTGenerator (ConvTranspose1d upsampling, generator.py:378-569) at cfg dims (eval)."""
+    install()
+    from cosyvoice.hifigan.generator import HiFTGenerator
+    from cosyvoice.hifigan.f0_predictor import ConvRNNF0Predictor
+    torch.manual_seed(seed)
+    m = HiFTGenerator(
+        in_channels=cfg.mel, base_channels=cfg.base, nb_harmonics=cfg.harmonics - 1,
+        sampling_rate=cfg.sr, nsf_alpha=0.1, nsf_sigma=0.003, nsf_voiced_threshold=10,
+        upsample_rates=list(cfg.ups), upsample_kernel_sizes=list(cfg.up_k),
+        istft_params={"n_fft": cfg.n_fft, "hop_len": cfg.hop},
+        resblock_kernel_sizes=list(cfg.rb_k), resblock_dilation_sizes=[list(cfg.rb_d)] * len(cfg.rb_k),
+        source_resblock_kernel_sizes=list(cfg.src_k),
+        source_resblock_dilation_sizes=[list(cfg.rb_d)] * len(cfg.src_k),
+        lrelu_slope=0.1, audio_limit=0.99, f0_predictor=ConvRNNF0Predictor(1, cfg.mel, cfg.f0_ch))
+    return m.eval()
+
+
 def build_flow(cfg, seed=0, dtype=torch.float32):
     install()
     from cosyvoice.flow.flow import CausalMaskedDiffWithDiT

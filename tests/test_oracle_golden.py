@@ -31,6 +31,35 @@ def test_hift_oracle_matches_reference(golden, name, dims):
     assert (wav_s - g["wav"][:, :n]).abs().max() < 2e-3   # F0 differs in the look-ahead frames only
 
 
+@pytest.mark.parametrize("name,dims", [("tiny", D.HIFT_TINY), ("full", D.HIFT_FULL)])
+def test_hift_transposed_oracle_matches_reference(golden, name, dims):
+    """a12': the non-causal ConvTranspose1d HiFTGenerator (generator.py:378-569), fixtures from the unmodified module."""
+    g = golden(f"hift_t_{name}")
+    sd = synth.hift_t_state_dict(dims, g["seed"])
+    assert abs(_checksum(sd) - g["sd_checksum"]) < 1e-6 * g["sd_checksum"]
+    w = hift_ref.fold_weight_norm(sd)
+    f0 = hift_ref.f0_predict_nc(w, g["mel"])
+    assert ((f0 - g["f0"]).abs() / (g["f0"].abs() + 1)).max() < 1e-4
+    wav = hift_ref.decode_transposed(sd, g["mel"], g["s"], dims)
+    assert wav.shape == g["wav"].shape == (1, g["T"] * dims.frame_samples)
+    assert (wav - g["wav"]).abs().max() < 5e-6
+    # whole inference with the RNG pinned: source bit-for-bit up to fp32 rounding, waveform through it
+    wav_i, src = hift_ref.inference_transposed(sd, g["mel"], g["noise"], dims, f0=g["f0"])
+    assert (src - g["src_inf"]).abs().max() < 1e-5
+    assert (wav_i - g["wav_inf"]).abs().max() < 5e-6
+    wav_c, _ = hift_ref.inference_transposed(sd, g["mel"], g["noise"], dims, f0=g["f0"], cache_source=g["s"][:, :, : 3 * dims.frame_samples])
+    assert (wav_c - g["wav_cache"]).abs().max() < 5e-6
+
+
+def test_hift_source_noise_replays_reference_rng(golden):
+    """draw_source_noise consumes the global generator like SineGen2.forward did when the fixture was minted
+    (rand(1,H), then randn_like of a (1,n,H) view of (1,H,n) memory)."""
+    g = golden("hift_t_tiny")
+    torch.manual_seed(g["seed"] + 300)
+    n = hift_ref.draw_source_noise(g["T"] * D.HIFT_TINY.frame_samples, D.HIFT_TINY.harmonics)
+    assert n.shape == g["noise"].shape and torch.equal(n, g["noise"])
+
+
 @pytest.mark.parametrize("name,dims", [("tiny", D.FLOW_TINY), ("full", D.FLOW_FULL)])
 def test_flow_oracle_matches_reference(golden, name, dims):
     g = golden(f"flow_{name}")
