@@ -36,6 +36,8 @@ struct ConvArgs {
   float slope;
   int post_elu, accumulate, reflect1;
   float out_scale;
+  int zstuff;           // 1: the x`up` input is zero-stuffed (x[v/up] at v % up == 0, else 0) instead of nearest-repeated:
+                        //    ConvTranspose1d(k, stride up) == conv of the zero-stuffed signal with the tap-reversed kernel
 };
 
 __device__ __forceinline__ float pre_activate(float v, int mode, float slope, float a) {
@@ -52,7 +54,7 @@ __global__ void __launch_bounds__(256) conv1d_tile_kernel(ConvArgs p) {
   const int co0 = blockIdx.y * CO_TILE;
   const int halo = (p.K - 1) * p.dil;
   const int W = T_TILE + halo;
-  const int Lup = p.Lin * p.up;
+  const int Lup = p.zstuff ? (p.Lin - 1) * p.up + 1 : p.Lin * p.up;
   float acc[8][8];
 #pragma unroll
   for (int c = 0; c < 8; c++)
@@ -75,7 +77,7 @@ __global__ void __launch_bounds__(256) conv1d_tile_kernel(ConvArgs p) {
       int ci = i / W, o = i - ci * W;
       int v = t0 + o - p.pad_left;
       float val = 0.f;
-      if (ci0 + ci < p.Cin && v >= 0 && v < Lup) {
+      if (ci0 + ci < p.Cin && v >= 0 && v < Lup && (!p.zstuff || v % p.up == 0)) {
         float a = (p.pre_act == 2) ? __ldg(p.alpha + ci0 + ci) : 0.f;
         val = pre_activate(__ldg(p.x + (size_t)(ci0 + ci) * p.ldx + v / p.up), p.pre_act, p.slope, a);
       }
@@ -197,6 +199,42 @@ __global__ void source_synth_kernel(const float* __restrict__ f0, const float* _
   float acc = 0.f;
   for (int h = 0; h < H; h++) {
     float sw = sinamp[(size_t)i * H + h] * uv + namp * __ldg(table + (size_t)n * H + h);
+    acc = fmaf(__ldg(lw + h), sw, acc);
+  }
+  s[n] = tanhf(acc + lb[0]);
+}
+
+// ---- non-causal SineGen2 (generator.py:233-317 with causal=False): frame-rate phase, linearly up-sampled
+// phase[i][h] = ((cum*2)*pi)*frame   (:257-258; same fp32 op order)
+__global__ void frame_phase_kernel(const float* __restrict__ cum, float* __restrict__ phase, int n, float frame) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  phase[i] = ((cum[i] * 2.0f) * 3.14159265358979323846f) * frame;
+}
+
+// s[n] = tanh(b + sum_h w[h]*(0.1*sin(lerp(phase))*uv + namp*noise[n][h]))   (:258-260,300-316,366-368)
+// lerp = F.interpolate(mode='linear', align_corners=False, scale_factor=frame): src = max(0, (n+0.5)/frame - 0.5)
+__global__ void source_synth_nc_kernel(const float* __restrict__ f0, const float* __restrict__ phase,
+                                       const float* __restrict__ noise, const float* __restrict__ lw,
+                                       const float* __restrict__ lb, float* __restrict__ s, int n_samples, int frame,
+                                       int H, int T, float inv_scale) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_samples) return;
+  const int i = n / frame;
+  const float uv = f0[i] > 10.0f ? 1.0f : 0.0f;
+  const float namp = uv * 0.003f + ((1.0f - uv) * 0.1f) / 3.0f;
+  float srcf = __fsub_rn(__fmul_rn(inv_scale, (float)n + 0.5f), 0.5f);
+  if (srcf < 0.f) srcf = 0.f;
+  int i0 = (int)srcf;
+  if (i0 > T - 1) i0 = T - 1;
+  const int i1 = i0 + (i0 < T - 1 ? 1 : 0);
+  float lam = srcf - (float)i0;
+  lam = fminf(fmaxf(lam, 0.f), 1.f);
+  const float w0 = 1.0f - lam;
+  float acc = 0.f;
+  for (int h = 0; h < H; h++) {
+    const float ph = __fadd_rn(__fmul_rn(w0, phase[(size_t)i0 * H + h]), __fmul_rn(lam, phase[(size_t)i1 * H + h]));
+    const float sw = (sinf(ph) * 0.1f) * uv + namp * __ldg(noise + (size_t)n * H + h);
     acc = fmaf(__ldg(lw + h), sw, acc);
   }
   s[n] = tanhf(acc + lb[0]);
@@ -352,7 +390,7 @@ hvx_status hift_finalize(hvx_engine* e) {
 void hift_free(hvx_engine* e) { delete e->hift; e->hift = nullptr; }
 
 struct ConvOpt {
-  int dil = 1, up = 1, pad_left = -1 /* -1: (K-1)*dil */, pre_act = 0, post_elu = 0, accumulate = 0, reflect1 = 0;
+  int dil = 1, up = 1, pad_left = -1 /* -1: (K-1)*dil */, pre_act = 0, post_elu = 0, accumulate = 0, reflect1 = 0, zstuff = 0;
   float slope = 0.f, out_scale = 1.f;
   const float* alpha = nullptr; const float* res1 = nullptr; const float* res2 = nullptr;
   int Lout = -1, ldx = -1;
@@ -367,7 +405,7 @@ static hvx_status run_conv(hvx_engine* e, cudaStream_t st, const ConvW& c, const
   a.pad_left = o.pad_left < 0 ? (c.K - 1) * o.dil : o.pad_left;
   a.Lin = Lin; a.Lout = o.Lout < 0 ? Lin * o.up : o.Lout; a.ldx = o.ldx < 0 ? Lin : o.ldx;
   a.pre_act = o.pre_act; a.slope = o.slope; a.post_elu = o.post_elu; a.accumulate = o.accumulate;
-  a.reflect1 = o.reflect1; a.out_scale = o.out_scale;
+  a.reflect1 = o.reflect1; a.out_scale = o.out_scale; a.zstuff = o.zstuff;
   dim3 grid(cdiv(a.Lout, T_TILE), cdiv(c.Cout, CO_TILE));
   conv1d_tile_kernel<<<grid, 256, 0, st>>>(a);
   HVX_LAUNCH_CHECK(e);
@@ -376,15 +414,18 @@ static hvx_status run_conv(hvx_engine* e, cudaStream_t st, const ConvW& c, const
 
 // x_out = resblock(x_in); the last conv's epilogue optionally adds `extra` and/or accumulates
 // out_scale*(result) into `acc_out` instead of writing x_out.
+// symmetric: "same" padding (k*d-d)/2 on both sides (ResBlock of the non-causal HiFTGenerator, generator.py:46-108) instead of causal
 static hvx_status run_resblock(hvx_engine* e, cudaStream_t st, const ResBlockW& r, int ndil, const int* dils,
                                const float* x_in, float* work, float* tmp, int L, const float* extra, float* final_out,
-                               int final_accumulate, float final_scale) {
+                               int final_accumulate, float final_scale, bool symmetric = false) {
   const float* cur = x_in;
   for (int j = 0; j < ndil; j++) {
     ConvOpt o1; o1.dil = dils[j]; o1.pre_act = 2; o1.alpha = r.a1[j];
+    if (symmetric) o1.pad_left = (r.c1[j].K - 1) * dils[j] / 2;
     hvx_status s = run_conv(e, st, r.c1[j], cur, L, tmp, o1);
     if (s) return s;
     ConvOpt o2; o2.pre_act = 2; o2.alpha = r.a2[j]; o2.res1 = cur;
+    if (symmetric) o2.pad_left = (r.c2[j].K - 1) / 2;
     float* dst = work;
     if (j == ndil - 1) {
       o2.res2 = extra; o2.accumulate = final_accumulate; o2.out_scale = final_scale;
@@ -497,6 +538,105 @@ extern "C" hvx_status hvx_hift_vocode(hvx_engine* e, const float* mel, int T, in
   istft_frames_kernel<<<cdiv(F, 128), 128, 0, st>>>(post, fbuf, F);
   HVX_LAUNCH_CHECK(e);
   istft_ola_kernel<<<cdiv(n_out, 256), 256, 0, st>>>(fbuf, wav, F, n_out, 0.99f);
+  HVX_LAUNCH_CHECK(e);
+  return HVX_OK;
+}
+
+// Non-causal HiFTGenerator.inference (cosyvoice/hifigan/generator.py:557-569; decode :506-540; ConvRNNF0Predictor
+// f0_predictor.py:9-55; SineGen2 with causal=False :233-317).  Same packed tensors as the causal vocoder
+// (weights.pack_hift_t stores the ConvTranspose1d kernels tap-reversed), symmetric "same" padding everywhere, transposed
+// convolutions as zero-stuffed convolutions.  noise_dev (frame*T, harmonics): the randn draw of :310, explicit;
+// cache_source_dev (n_cache samples) overwrites the head of the source (:566-567); n_cache == frame*T needs no noise.
+extern "C" hvx_status hvx_hift_t_vocode(hvx_engine* e, const float* mel, int T, const float* noise, const float* cache_source,
+                                        int n_cache, const float* f0_in, float* f0_out, float* wav, float* src, void* stream) {
+  HVX_CHECK(e && e->hift, HVX_ERR_STATE, "hift stage not finalized");
+  const hvx_config& c = e->cfg;
+  HiftState* h = e->hift;
+  cudaStream_t st = (cudaStream_t)stream;
+  int frame = c.hift_hop, up_prod = 1;
+  for (int i = 0; i < c.hift_n_ups; i++) { frame *= c.hift_ups[i]; up_prod *= c.hift_ups[i]; }
+  const int H = c.hift_harmonics;
+  HVX_CHECK(T >= 1 && mel && wav, HVX_ERR_ARG, "hift_t: bad arguments (T=%d)", T);
+  const int Ns = T * frame, Fs = Ns / 4 + 1, F = T * up_prod + 1;
+  HVX_CHECK(n_cache >= 0 && n_cache <= Ns && (n_cache == 0 || cache_source), HVX_ERR_ARG, "hift_t: cache_source length %d outside [0,%d]", n_cache, Ns);
+  HVX_CHECK(noise || n_cache == Ns, HVX_ERR_ARG, "hift_t: the source needs its noise draw (or a cache_source covering it)");
+  for (int i = 0; i < c.hift_n_ups; i++)
+    HVX_CHECK(h->ups[i].K >= c.hift_ups[i] && (h->ups[i].K - c.hift_ups[i]) % 2 == 0, HVX_ERR_UNSUPPORTED,
+              "hift_t: upsample kernel %d / rate %d: only k-u even is built (output length u*L)", h->ups[i].K, c.hift_ups[i]);
+  const int C0 = c.hift_base, CF = c.hift_f0_ch;
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += (n + 63) & ~(size_t)63; return o; };
+  const size_t o_fa = take((size_t)CF * T), o_fb = take((size_t)CF * T), o_f0 = take(T);
+  const size_t o_cum = take((size_t)T * H), o_ph = take((size_t)T * H), o_s = take(Ns);
+  const size_t o_stft = take((size_t)18 * Fs), o_x0 = take((size_t)C0 * T);
+  size_t maxCL = 0;
+  { int L = T; for (int i = 0; i < c.hift_n_ups; i++) { L = L * c.hift_ups[i]; size_t cl = (size_t)(C0 >> (i + 1)) * (L + 1); if (cl > maxCL) maxCL = cl; } }
+  const size_t o_x = take(maxCL), o_xs = take(maxCL), o_si = take(maxCL), o_work = take(maxCL), o_tmp = take(maxCL);
+  const size_t o_post = take((size_t)18 * F), o_fbuf = take((size_t)16 * F);
+  float* ws = (float*)h->ws.get(off * sizeof(float));
+  HVX_CHECK(ws, HVX_ERR_CUDA, "hift_t: workspace allocation of %zu bytes failed", off * sizeof(float));
+  float *fa = ws + o_fa, *fb = ws + o_fb, *f0 = ws + o_f0, *cum = ws + o_cum, *phase = ws + o_ph, *s = ws + o_s;
+  float *sstft = ws + o_stft, *x0 = ws + o_x0, *x = ws + o_x, *xs = ws + o_xs, *si = ws + o_si, *work = ws + o_work;
+  float *tmp = ws + o_tmp, *post = ws + o_post, *fbuf = ws + o_fbuf;
+  hvx_status rc;
+
+  // ---- F0 predictor: 5 x (conv k3 pad 1 + ELU), Linear, abs (f0_predictor.py:25-55)
+  if (f0_in) {
+    HVX_CUDA(cudaMemcpyAsync(f0, f0_in, sizeof(float) * T, cudaMemcpyDeviceToDevice, st));
+  } else {
+    const float* a = mel; float* b = fa;
+    for (int i = 0; i < 5; i++) {
+      ConvOpt o; o.post_elu = 1; o.pad_left = (h->f0c[i].K - 1) / 2;
+      if ((rc = run_conv(e, st, h->f0c[i], a, T, b, o))) return rc;
+      a = b; b = (b == fa) ? fb : fa;
+    }
+    f0_head_kernel<<<cdiv(T, 128), 128, 0, st>>>(a, h->cls_w, h->cls_b, f0, CF, T);
+    HVX_LAUNCH_CHECK(e);
+  }
+  if (f0_out) HVX_CUDA(cudaMemcpyAsync(f0_out, f0, sizeof(float) * T, cudaMemcpyDeviceToDevice, st));
+
+  // ---- harmonic source
+  if (n_cache < Ns) {
+    phase_scan_kernel<<<1, H * 32, H * 32 * sizeof(double), st>>>(f0, cum, T, H, (float)c.hift_sr);
+    HVX_LAUNCH_CHECK(e);
+    frame_phase_kernel<<<cdiv(T * H, 256), 256, 0, st>>>(cum, phase, T * H, (float)frame);
+    HVX_LAUNCH_CHECK(e);
+    source_synth_nc_kernel<<<cdiv(Ns, 256), 256, 0, st>>>(f0, phase, noise, h->lin_w, h->lin_b, s, Ns, frame, H, T, (float)(1.0 / (double)frame));
+    HVX_LAUNCH_CHECK(e);
+  }
+  if (n_cache > 0) HVX_CUDA(cudaMemcpyAsync(s, cache_source, sizeof(float) * n_cache, cudaMemcpyDeviceToDevice, st));
+  if (src) HVX_CUDA(cudaMemcpyAsync(src, s, sizeof(float) * Ns, cudaMemcpyDeviceToDevice, st));
+  stft16_kernel<<<cdiv(Fs, 128), 128, 0, st>>>(s, sstft, Ns, Fs);
+  HVX_LAUNCH_CHECK(e);
+
+  // ---- decode (generator.py:506-540)
+  { ConvOpt o; o.pad_left = (h->conv_pre.K - 1) / 2;
+    if ((rc = run_conv(e, st, h->conv_pre, mel, T, x0, o))) return rc; }
+  const float* cur = x0;
+  int L = T, down = up_prod;
+  for (int i = 0; i < c.hift_n_ups; i++) {
+    const int u = c.hift_ups[i], K = h->ups[i].K;
+    const int last = (i == c.hift_n_ups - 1);
+    const int Lo = L * u + (last ? 1 : 0);
+    // ConvTranspose1d(k, stride u, padding (k-u)/2): zero-stuff, left pad k-1-(k-u)/2, output length u*L
+    { ConvOpt o; o.pre_act = 1; o.slope = 0.1f; o.up = u; o.zstuff = 1; o.pad_left = K - 1 - (K - u) / 2; o.Lout = L * u; o.reflect1 = last;
+      if ((rc = run_conv(e, st, h->ups[i], cur, L, x, o))) return rc; }
+    down /= u;
+    { const ConvW& d = h->sdown[i];                                // Conv1d(18, C, 2*down, down, padding=down/2) or k1 (:452-460)
+      dim3 grid(cdiv(Lo, 128), d.Cout);
+      conv1d_strided_kernel<<<grid, 128, 0, st>>>(sstft, d.w, d.b, si, d.Cin, d.Cout, d.K, down, down > 1 ? down / 2 : 0, Fs, Lo);
+      HVX_LAUNCH_CHECK(e); }
+    if ((rc = run_resblock(e, st, h->srb[i], c.hift_n_dil, c.hift_rb_d, si, work, tmp, Lo, x, x, 0, 1.0f, true))) return rc;
+    for (int j = 0; j < c.hift_n_rb; j++)
+      if ((rc = run_resblock(e, st, h->rb[i * c.hift_n_rb + j], c.hift_n_dil, c.hift_rb_d, x, work, tmp, Lo, nullptr, xs,
+                             j > 0, 1.0f / c.hift_n_rb, true))) return rc;
+    cur = xs; L = Lo;
+  }
+  { ConvOpt o; o.pre_act = 1; o.slope = 0.01f; o.pad_left = (h->conv_post.K - 1) / 2;
+    if ((rc = run_conv(e, st, h->conv_post, cur, L, post, o))) return rc; }
+  istft_frames_kernel<<<cdiv(F, 128), 128, 0, st>>>(post, fbuf, F);
+  HVX_LAUNCH_CHECK(e);
+  istft_ola_kernel<<<cdiv(Ns, 256), 256, 0, st>>>(fbuf, wav, F, Ns, 0.99f);
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
 }

@@ -6,7 +6,7 @@ import ctypes as C
 import torch
 
 from . import _lib as L
-from .weights import pack_hift
+from .weights import pack_hift, pack_hift_t
 
 
 class NativeHiFT:
@@ -60,3 +60,63 @@ class NativeHiFT:
         if return_f0:
             return wav, src, f0_out
         return wav, src
+
+
+class NativeHiFTTransposed:
+    """Drop-in for the non-causal `HiFTGenerator` (cosyvoice/hifigan/generator.py:378-569): ConvTranspose1d up-sampling,
+    "same"-padded ResBlocks, ConvRNNF0Predictor on the GPU.  `inference(speech_feat, cache_source)` has the reference's
+    signature (:557-569); the source module's Gaussian draw (:310) comes from `generator` (a torch.Generator on the engine's
+    device, fresh noise per call like the reference) or from an explicit `noise` (n_samples, harmonics) — the pinned-RNG path."""
+
+    def __init__(self, engine: "L.Engine", generator: torch.Generator | None = None):
+        self.engine = engine
+        self.dims = engine.hd
+        self.generator = generator
+
+    def load_state_dict(self, sd, strict=True):
+        self.engine.set_tensors(L.STAGE_HIFT, pack_hift_t(sd, self.dims))
+        self.engine.finalize(L.STAGE_HIFT)
+        return self
+
+    def eval(self):
+        return self
+
+    def cuda(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    @torch.no_grad()
+    def inference(self, speech_feat: torch.Tensor, cache_source: torch.Tensor | None = None, noise: torch.Tensor | None = None,
+                  f0: torch.Tensor | None = None, return_f0: bool = False):
+        """speech_feat (1, mel, T) fp32 -> (speech (1, frame*T), source (1, 1, frame*T))."""
+        assert speech_feat.dim() == 3 and speech_feat.shape[0] == 1
+        d, dev = self.dims, self.engine.device
+        mel = speech_feat[0].to(dev, torch.float32).contiguous()
+        T = mel.shape[1]
+        n = T * d.frame_samples
+        cache = None
+        if cache_source is not None and cache_source.numel():
+            cache = cache_source.reshape(-1)[:n].to(dev, torch.float32).contiguous()
+        n_cache = 0 if cache is None else cache.numel()
+        if noise is None and n_cache < n:
+            noise = torch.randn(n, d.harmonics, device=dev, dtype=torch.float32, generator=self.generator)
+        if noise is not None:
+            noise = noise.reshape(-1, d.harmonics)[:n].to(dev, torch.float32).contiguous()
+            if noise.shape[0] < n:
+                raise L.HvxError("noise shorter than the utterance")
+        wav = torch.empty(1, n, device=dev, dtype=torch.float32)
+        src = torch.empty(1, 1, n, device=dev, dtype=torch.float32)
+        f0_out = torch.empty(T, device=dev, dtype=torch.float32)
+        f0_in = None if f0 is None else f0.reshape(-1).to(dev, torch.float32).contiguous()
+        L.check(L.lib().hvx_hift_t_vocode(self.engine.h, L.ptr(mel), T, L.ptr(noise), L.ptr(cache), n_cache, L.ptr(f0_in),
+                                          L.ptr(f0_out), L.ptr(wav), L.ptr(src), L.stream_ptr()))
+        if return_f0:
+            return wav, src, f0_out
+        return wav, src
+
+    @torch.no_grad()
+    def decode(self, x: torch.Tensor, s: torch.Tensor):
+        """HiFTGenerator.decode (:506-540): mel (1, mel, T) and an explicit source s (1, 1, frame*T) -> speech (1, frame*T)."""
+        return self.inference(x, cache_source=s)[0]

@@ -29,7 +29,20 @@ def _conv(sd, base, out, name):
     out[name + ".b"] = sd[base + ".bias"].float().contiguous()
 
 
-def pack_hift(sd: Dict[str, torch.Tensor], d: D.HiftDims) -> Dict[str, torch.Tensor]:
+def _conv_transpose(sd, base, out, name):
+    """Weight-normed ConvTranspose1d (Cin, Cout, K), norm over (Cout, K) per input channel (dim 0).  Stored tap-reversed as
+    [Cin][K][Cout]: conv_transpose(x, w, stride u) == conv(zero_stuff(x, u), flip_k(w)) — what conv1d_tile_kernel runs."""
+    w = _fold_wn(sd, base)                               # (Cin, Cout, K)
+    out[name + ".w"] = w.flip(2).permute(0, 2, 1).contiguous()
+    out[name + ".b"] = sd[base + ".bias"].float().contiguous()
+
+
+def pack_hift_t(sd: Dict[str, torch.Tensor], d: D.HiftDims) -> Dict[str, torch.Tensor]:
+    """HiFTGenerator (generator.py:378-569) state_dict -> the same packed tensor names as the causal vocoder."""
+    return pack_hift(sd, d, transposed=True)
+
+
+def pack_hift(sd: Dict[str, torch.Tensor], d: D.HiftDims, transposed: bool = False) -> Dict[str, torch.Tensor]:
     o: Dict[str, torch.Tensor] = {}
     for i, idx in enumerate((0, 2, 4, 6, 8)):
         _conv(sd, f"f0_predictor.condnet.{idx}", o, f"f0.c{i}")
@@ -48,7 +61,7 @@ def pack_hift(sd: Dict[str, torch.Tensor], d: D.HiftDims) -> Dict[str, torch.Ten
             o[f"{dst}.a2.{j}"] = sd[f"{src}.activations2.{j}.alpha"].float().contiguous()
 
     for i in range(len(d.ups)):
-        _conv(sd, f"ups.{i}", o, f"ups.{i}")
+        (_conv_transpose if transposed else _conv)(sd, f"ups.{i}", o, f"ups.{i}")
         _conv(sd, f"source_downs.{i}", o, f"sdown.{i}")
         rb(f"source_resblocks.{i}", f"srb.{i}")
         for j in range(len(d.rb_k)):

@@ -87,6 +87,16 @@ hvx_status hvx_hift_vocode(hvx_engine* e, const float* mel_dev, int T, int final
                            const float* sine_table_dev, const float* f0_in_dev, float* f0_out_dev,
                            float* wav_dev, float* src_dev, void* stream);
 
+/* ---- HiFT, transposed-conv variant: replaces HiFTGenerator.inference (cosyvoice/hifigan/generator.py:557-569; decode
+ * :506-540; ConvRNNF0Predictor cosyvoice/hifigan/f0_predictor.py:9-55; SineGen2 with causal=False :233-317) — weight-normed
+ * ConvTranspose1d(k, u, padding=(k-u)/2) up-sampling, "same"-padded ResBlocks, F0 predictor on the GPU.
+ * noise_dev (frame*T, harmonics) fp32: the Gaussian draw of generator.py:310 made explicit (NULL allowed only when
+ * cache_source covers the whole source); cache_source_dev (n_cache samples) overwrites the head of the source (:566-567).
+ * The engine's HiFT stage must have been loaded with the transposed packing (weights.pack_hift_t). */
+hvx_status hvx_hift_t_vocode(hvx_engine* e, const float* mel_dev, int T, const float* noise_dev,
+                             const float* cache_source_dev, int n_cache, const float* f0_in_dev, float* f0_out_dev,
+                             float* wav_dev, float* src_dev, void* stream);
+
 /* ---- flow: replaces CausalMaskedDiffWithDiT.inference (cosyvoice/flow/flow.py:367-430) ----
  * tokens = prompt||new speech tokens (n_prompt + n_tok), embedding (spk_in) fp32,
  * prompt_feat (2*n_prompt, mel) fp32 or NULL; noise_dev = CausalConditionalCFM.rand_noise

@@ -77,3 +77,72 @@ def test_hift_full_size_properties(engines):
     n = wav_c.shape[1]
     assert n == (Tc - 8) * 480
     assert (wav_c - wav[:, :n]).abs().max().item() < 2e-3
+
+
+# ---------------------------------------------------------------- a12': non-causal ConvTranspose1d HiFTGenerator
+@pytest.fixture(scope="module")
+def engines_t():
+    from flowmirror_hydravox_b200 import _lib as L
+    from flowmirror_hydravox_b200.hift import NativeHiFTTransposed
+    out = {}
+    for name, hd in (("tiny", D.HIFT_TINY), ("full", D.HIFT_FULL)):
+        e = L.Engine(hd=hd)
+        h = NativeHiFTTransposed(e)
+        h.load_state_dict(synth.hift_t_state_dict(hd, 0))
+        out[name] = (e, h, hd)
+    yield out
+    for e, _, _ in out.values():
+        e.close()
+
+
+@pytest.mark.parametrize("name", ["tiny", "full"])
+def test_hift_transposed_matches_reference_fixture(engines_t, golden, name):
+    e, h, hd = engines_t[name]
+    g = golden(f"hift_t_{name}")
+    # decode(mel, s) with an explicit source: the deterministic part of HiFTGenerator (generator.py:506-540)
+    wav = h.decode(g["mel"], g["s"])
+    assert wav.shape == g["wav"].shape
+    err = (wav.cpu() - g["wav"]).abs()
+    assert err.pow(2).mean().sqrt().item() < 1e-4 and err.max().item() < 1e-3, (err.pow(2).mean().sqrt().item(), err.max().item())
+    # F0 predictor (ConvRNNF0Predictor) on the GPU vs the reference's fp32 result
+    _, _, f0 = h.inference(g["mel"], noise=g["noise"], return_f0=True)
+    rel = ((f0.cpu() - g["f0"][0]).abs() / (g["f0"][0].abs() + 1)).max().item()
+    assert rel < 2e-4, rel
+    # whole inference, RNG pinned (noise explicit), F0 pinned: source module + decode
+    wav_i, src = h.inference(g["mel"], noise=g["noise"], f0=g["f0"])
+    assert (src.cpu() - g["src_inf"]).abs().max().item() < 5e-4      # phase ~1e4 rad in fp32: 1 ulp = 1e-3 rad x 0.1 amplitude
+    e_i = (wav_i.cpu() - g["wav_inf"]).abs()
+    assert e_i.pow(2).mean().sqrt().item() < 1e-4, e_i.pow(2).mean().sqrt().item()
+    # cache_source overwrites the head of the source (:566-567)
+    cache = g["s"][:, :, : 3 * hd.frame_samples]
+    wav_c, src_c = h.inference(g["mel"], cache_source=cache, noise=g["noise"], f0=g["f0"])
+    assert torch.equal(src_c.cpu()[:, :, : cache.shape[2]], cache)
+    assert (wav_c.cpu() - g["wav_cache"]).pow(2).mean().sqrt().item() < 1e-4
+
+
+@pytest.mark.parametrize("T", [1, 2, 7, 150])
+def test_hift_transposed_matches_oracle_lengths(engines_t, T):
+    from oracle import hift_ref
+    e, h, hd = engines_t["tiny"]
+    sd = synth.hift_t_state_dict(hd, 0)
+    g = torch.Generator().manual_seed(T)
+    mel = torch.rand(1, hd.mel, T, generator=g) * 6 - 6
+    noise = torch.randn(T * hd.frame_samples, hd.harmonics, generator=g)
+    w = hift_ref.fold_weight_norm(sd)
+    f0 = hift_ref.f0_predict_nc(w, mel)
+    ref, s_ref = hift_ref.inference_transposed(sd, mel, noise, hd, f0=f0)
+    wav = h.decode(mel, s_ref)                         # source pinned: decode parity at any length
+    assert wav.shape == ref.shape == (1, T * hd.frame_samples)
+    assert (wav.cpu() - ref).pow(2).mean().sqrt().item() < 1e-4
+    _, src = h.inference(mel, noise=noise, f0=f0)
+    tol = 5e-4 if T <= 7 else 2e-2                      # fp32 phase grows with the clip: 150 frames reach ~1e5 rad
+    assert (src.cpu() - s_ref).abs().max().item() < tol
+
+
+def test_hift_transposed_fresh_noise_is_stochastic_like_reference(engines_t):
+    """Without pinned noise every call draws fresh Gaussian noise, as SineGen2 does (generator.py:310)."""
+    e, h, hd = engines_t["tiny"]
+    mel = torch.rand(1, hd.mel, 12, generator=torch.Generator().manual_seed(0)) * 6 - 6
+    a, _ = h.inference(mel)
+    b, _ = h.inference(mel)
+    assert a.shape == (1, 12 * hd.frame_samples) and torch.isfinite(a).all() and not torch.equal(a, b)
