@@ -745,6 +745,7 @@ struct SampArgs {
   // standalone mode (hvx_sample): explicit history instead of out_tokens
   const int32_t* history = nullptr; int n_history = 0; int min_len_override = -1;
   int32_t* ids_out = nullptr; int32_t* u_used = nullptr;
+  unsigned long long* fused_bar = nullptr;  // grid-barrier counter of the fused decode-step kernel: re-armed here, between two steps
 };
 
 // block-wide reductions on double-buffered scratch: one __syncthreads each
@@ -787,6 +788,7 @@ __global__ void __launch_bounds__(SAMP_THREADS) llm_sampler_kernel(SampArgs a) {
   asm volatile("griddepcontrol.launch_dependents;");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const int seq = blockIdx.x, j = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, V = a.vocab;
+  if (a.fused_bar && seq == 0 && j == 0 && tid == 0) *a.fused_bar = 0ull;
   SeqState* st = a.seqs ? &a.seqs[seq] : nullptr;
   if (st && st->done) return;
   const int topk = a.top_k < SAMP_MAXK ? a.top_k : SAMP_MAXK;
@@ -954,6 +956,10 @@ struct LlmLayer {
   const float *qkv_b, *ln1, *ln2;
 };
 
+}  // namespace hvx
+#include "llm_fused.cuh"
+namespace hvx {
+
 struct SeqDesc {
   const int32_t* text = nullptr; int n_text_total = 0, n_text_new = 0;
   const int32_t* pspeech = nullptr; int n_ps = 0;
@@ -981,6 +987,10 @@ struct LlmState {
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;              // default stream, which cannot be captured into a graph
   cudaGraphExec_t graph = nullptr; int graph_key[4] = {0, 0, 0, 0};
   SampArgs graph_samp;
+  // fused persistent decode step (llm_fused.cuh)
+  LlmLayer* layers_dev = nullptr;
+  unsigned long long* fused_bar = nullptr;
+  int* fused_abort = nullptr;
 };
 
 template <typename T>
@@ -1047,11 +1057,17 @@ hvx_status llm_finalize(hvx_engine* e) {
     HVX_CUDA(cudaMalloc(&L->inv_freq, sizeof(inv)));
     HVX_CUDA(cudaMemcpy(L->inv_freq, inv, sizeof(inv), cudaMemcpyHostToDevice));
     L->desc.resize(c.llm_max_seqs);
+    HVX_CUDA(cudaMalloc(&L->layers_dev, sizeof(LlmLayer) * 64));
+    HVX_CUDA(cudaMalloc(&L->fused_bar, sizeof(unsigned long long)));
+    HVX_CUDA(cudaMemset(L->fused_bar, 0, sizeof(unsigned long long)));
+    HVX_CUDA(cudaMalloc(&L->fused_abort, sizeof(int)));
+    HVX_CUDA(cudaMemset(L->fused_abort, 0, sizeof(int)));
     HVX_CUDA(cudaStreamCreateWithFlags(&L->own, cudaStreamNonBlocking));
     HVX_CUDA(cudaEventCreateWithFlags(&L->ev_in, cudaEventDisableTiming));
     HVX_CUDA(cudaEventCreateWithFlags(&L->ev_out, cudaEventDisableTiming));
   }
   if (L->graph) { cudaGraphExecDestroy(L->graph); L->graph = nullptr; }
+  HVX_CUDA(cudaMemcpy(L->layers_dev, L->layer, sizeof(LlmLayer) * 64, cudaMemcpyHostToDevice));
   return HVX_OK;
 }
 
@@ -1060,6 +1076,7 @@ void llm_free(hvx_engine* e) {
   if (!L) return;
   if (L->graph) cudaGraphExecDestroy(L->graph);
   cudaFree(L->kc); cudaFree(L->vc); cudaFree(L->seqs); cudaFree(L->n_active); cudaFree(L->inv_freq);
+  cudaFree(L->layers_dev); cudaFree(L->fused_bar); cudaFree(L->fused_abort);
   if (L->n_active_host) cudaFreeHost(L->n_active_host);
   if (L->own) cudaStreamDestroy(L->own);
   if (L->ev_in) cudaEventDestroy(L->ev_in);
@@ -1224,7 +1241,8 @@ static hvx_status llm_bufs(hvx_engine* e, LlmState* L, DevBuf& buf, int rows, in
   const size_t o_h = take(rp * H * 4), o_q = take(rp * H * 4), o_att = take(rp * H * 4), o_act = take(rp * I * 4);
   const size_t o_hn = take(sp * H * 4), o_mv = take(head_k * sp * H * 4), o_mh1 = take(head_k * sp * H * 4);
   const size_t o_mact = take(head_k * sp * MI * 4), o_mo = take(head_k * sp * H * 4), o_log = take(head_k * sp * V * 4);
-  const size_t o_part = take((size_t)rows * c.llm_q_heads * splits * 68 * 4), o_cnt = take((size_t)rows * c.llm_kv_heads * 4);
+  const int part_splits = std::max(splits, e->sm_count / std::max(1, c.llm_kv_heads));     // the fused step splits over all SMs
+  const size_t o_part = take((size_t)rows * c.llm_q_heads * part_splits * 68 * 4), o_cnt = take((size_t)rows * c.llm_kv_heads * 4);
   const size_t o_x16 = take(rp * H * 4), o_att16 = take(rp * H * 4), o_act16 = take(std::max(rp * I, sp * MI) * 4);
   const size_t o_hn16 = take(256), o_m16 = take(sp * H * 4);        // split bf16 [hi | lo] rows
   const bool grew = off > buf.bytes;
@@ -1412,6 +1430,87 @@ static hvx_status launch_sampler(hvx_engine* e, cudaStream_t st, SampArgs a, int
   return HVX_OK;
 }
 
+// ---- fused persistent decode step (llm_fused.cuh): one sequence, head_k <= 4
+struct FusedPlan { bool ok = false; int R = 0, n_slots = 0, x_bytes = 0; size_t smem = 0; };
+
+static FusedPlan fused_plan(hvx_engine* e, int n_seq, int head_k, bool force = false) {
+  FusedPlan f;
+  const hvx_config& c = e->cfg;
+  // Opt-in (HVX_FUSED_DECODE=1): numerically equivalent to the kernel-per-op step (tests/test_llm_gpu.py), but at round 1 it
+  // is slower on B200 (938 vs 780 us per step at ctx 800: ~1.9 us per grid barrier x 6 per layer, see profiles/README.md)
+  const char* env = getenv("HVX_FUSED_DECODE");
+  if (!force && !(env && atoi(env) != 0)) return f;
+  if (n_seq != 1 || head_k > 4) return f;
+  const int H = c.llm_hidden, I = c.llm_inter, MI = c.llm_mtp_inter, G = e->sm_count;
+  f.R = head_k <= 1 ? 1 : head_k <= 2 ? 2 : 4;
+  const int group = c.llm_q_heads / c.llm_kv_heads;
+  if (f.R * group > 2 * fused::NW || H % 8 || I % 8 || MI % 8 || H > 2048) return f;
+  // every phase: a unit (two rows of one k-segment) fits a slot, k-split partial sums fit the scratch
+  auto unit_ok = [&](int N, int K, int nb, int RB) {
+    const int ks = fused::pick_ksplit(K), seg = K / ks;
+    if (seg * 4 > fused::SLOT || seg % 8) return false;
+    const int pairs = cdiv(((N + 1) / 2) * nb, G);
+    return ks == 1 || pairs * ks * 2 * RB <= fused::RED_FLOATS;
+  };
+  const int NQKV = (c.llm_q_heads + 2 * c.llm_kv_heads) * 64;
+  if (!unit_ok(NQKV, H, 1, f.R) || !unit_ok(H, H, 1, f.R) || !unit_ok(2 * I, H, 1, f.R) || !unit_ok(H, I, 1, f.R) ||
+      !unit_ok(H, H, head_k, 1) || !unit_ok(2 * MI, H, head_k, 1) || !unit_ok(H, MI, head_k, 1) || !unit_ok(c.llm_speech_vocab, H, 1, f.R))
+    return f;
+  size_t xb = (size_t)f.R * std::max(H, I) * 4;
+  xb = std::max(xb, (size_t)head_k * H * 4);
+  xb = std::max(xb, (size_t)2 * fused::ATT_CHUNK * (c.llm_kv_f32 ? ATT_LD32 * 4 : ATT_LD * 2));
+  xb = (xb + 127) & ~(size_t)127;
+  const size_t budget = 216 * 1024;        // + 9 KB static shared memory <= 227 KB
+  if (xb + (size_t)H * 4 + 3 * fused::SLOT > budget) return f;
+  f.n_slots = (int)std::min((size_t)fused::MAXNS, (budget - xb - (size_t)H * 4) / fused::SLOT);
+  f.x_bytes = (int)xb;
+  f.smem = xb + (size_t)f.n_slots * fused::SLOT + (size_t)H * 4;
+  f.ok = true;
+  return f;
+}
+
+static hvx_status launch_fused_step(hvx_engine* e, cudaStream_t st, LlmState* L, const StepBufs& b, int head_k, const FusedPlan& f,
+                                    int max_phases = 1 << 30, unsigned long long* dbg = nullptr) {
+  const hvx_config& c = e->cfg;
+  fused::Args a;
+  a.layers = L->layers_dev; a.n_layers = c.llm_layers; a.H = c.llm_hidden; a.I = c.llm_inter; a.q_heads = c.llm_q_heads;
+  a.kv_heads = c.llm_kv_heads; a.MI = c.llm_mtp_inter; a.V = c.llm_speech_vocab; a.head_k = head_k; a.max_ctx = c.llm_max_ctx;
+  a.eps = c.llm_eps; a.scale = 1.0f / sqrtf((float)c.llm_head_dim);
+  a.norm = L->norm; a.m_v_w = L->m_v_w; a.m_o_w = L->m_o_w; a.m_gu_w = L->m_gu_w; a.m_down_w = L->m_down_w; a.dec_w = L->dec_w;
+  a.m_v_b = L->m_v_b; a.m_ln1 = L->m_ln1; a.m_ln2 = L->m_ln2;
+  a.kc = L->kc; a.vc = L->vc; a.layer_stride = L->layer_stride; a.seq_stride = L->seq_stride; a.kv_f32 = L->kv_f32;
+  a.inv_freq = L->inv_freq; a.seqs = L->seqs;
+  a.h = b.h; a.q = b.q; a.att = b.att; a.act = b.act; a.part = b.part;
+  a.m_v = b.m_v; a.m_h1 = b.m_h1; a.m_act = b.m_act; a.m_o = b.m_o; a.logits = b.logits;
+  a.bar = L->fused_bar; a.abort_flag = L->fused_abort; a.n_slots = f.n_slots; a.x_bytes = f.x_bytes; a.max_phases = max_phases; a.dbg = dbg;
+  { const char* pc = getenv("HVX_FUSED_PACE"); a.pace_clk = pc ? atoi(pc) : 0; }
+  static bool attr = false;
+  if (!attr) {
+    HVX_CUDA(cudaFuncSetAttribute(fused::llm_fused_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+    HVX_CUDA(cudaFuncSetAttribute(fused::llm_fused_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+    HVX_CUDA(cudaFuncSetAttribute(fused::llm_fused_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+    attr = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(e->sm_count, 1, 1);
+  cfg.blockDim = dim3(fused::THREADS, 1, 1);
+  cfg.dynamicSmemBytes = f.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;        // all CTAs co-resident (grid barriers), or the launch fails
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  switch (f.R) {
+    case 1: HVX_CUDA(cudaLaunchKernelEx(&cfg, fused::llm_fused_step_kernel<1>, a)); break;
+    case 2: HVX_CUDA(cudaLaunchKernelEx(&cfg, fused::llm_fused_step_kernel<2>, a)); break;
+    default: HVX_CUDA(cudaLaunchKernelEx(&cfg, fused::llm_fused_step_kernel<4>, a)); break;
+  }
+  HVX_LAUNCH_CHECK(e);
+  return HVX_OK;
+}
+
 static int attn_splits(int sm, int rows, int kv_heads) {
   int s = (2 * sm) / std::max(1, rows * kv_heads);
   const char* cap = getenv("HVX_ATTN_SPLITS");
@@ -1497,11 +1596,38 @@ extern "C" hvx_status hvx_llm_generate(hvx_engine* e, int n_seq, int head_k, con
   sa.top_p = sp->top_p; sa.top_k = sp->top_k; sa.win_size = sp->win_size; sa.rep_thr = (double)sp->win_size * sp->tau_r;
   sa.u = u_dev; sa.u_stride = u_stride; sa.seqs = L->seqs; sa.out_tokens = out_tokens; sa.max_out = max_out; sa.out_counts = out_counts;
   sa.semb = L->semb; sa.h = b.h; sa.H = c.llm_hidden; sa.n_active = L->n_active; sa.max_ctx = c.llm_max_ctx;
+  const FusedPlan fp = fused_plan(e, n_seq, head_k);
+  if (fp.ok) { sa.fused_bar = L->fused_bar; HVX_CUDA(cudaMemsetAsync(L->fused_abort, 0, sizeof(int), st)); }
 
   // first sample straight from the prefill's last hidden state
   if ((rc = llm_heads(e, st, L, b, n_seq, head_k, head_k))) return rc;
   if ((rc = launch_sampler(e, st, sa, n_seq))) return rc;
 
+  // every running step emits exactly head_k tokens per live sequence (or stops it), the first sample is already out
+  int max_steps = 0;
+  for (int s = 0; s < n_seq; s++) {
+    const int ml = std::min((int)((float)L->desc[s].n_text_new * L->desc[s].max_ratio), max_out);
+    max_steps = std::max(max_steps, cdiv(std::max(ml - head_k, 0), head_k));
+  }
+  const int poll = 16;
+  if (fp.ok) {
+    // one sequence: the whole step is ONE persistent cooperative kernel (llm_fused.cuh) + the sampler
+    for (int step = 0; step < max_steps;) {
+      const int n = std::min(poll, max_steps - step);
+      for (int i = 0; i < n; i++) {
+        if ((rc = launch_fused_step(e, st, L, b, head_k, fp))) return rc;
+        if ((rc = launch_sampler(e, st, sa, n_seq))) return rc;
+      }
+      step += n;
+      HVX_CUDA(cudaMemcpyAsync(L->n_active_host, L->n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+      HVX_CUDA(cudaStreamSynchronize(st));
+      if (*L->n_active_host <= 0) break;
+    }
+    int aborted = 0;
+    HVX_CUDA(cudaMemcpyAsync(&aborted, L->fused_abort, sizeof(int), cudaMemcpyDeviceToHost, st));
+    HVX_CUDA(cudaStreamSynchronize(st));
+    HVX_CHECK(aborted == 0, HVX_ERR_CUDA, "llm: fused decode step timed out on a barrier (code %d)", aborted);
+  } else {
   // one decode step = fixed launch sequence -> CUDA graph (re-captured when shapes or buffers change)
   const int key[4] = {n_seq, head_k, (int)((uintptr_t)b.h >> 8), (int)((uintptr_t)out_tokens >> 4) ^ (int)((uintptr_t)u_dev >> 4) ^ (sp->top_k << 20) ^ sp->win_size};
   const bool same = L->graph && !memcmp(key, L->graph_key, sizeof(key)) && !memcmp(&sa, &L->graph_samp, sizeof(sa));
@@ -1524,13 +1650,6 @@ extern "C" hvx_status hvx_llm_generate(hvx_engine* e, int n_seq, int head_k, con
     e->graph_launches = e->launches - l0;
     e->launches = l0;
   }
-  // every running step emits exactly head_k tokens per live sequence (or stops it), the first sample is already out
-  int max_steps = 0;
-  for (int s = 0; s < n_seq; s++) {
-    const int ml = std::min((int)((float)L->desc[s].n_text_new * L->desc[s].max_ratio), max_out);
-    max_steps = std::max(max_steps, cdiv(std::max(ml - head_k, 0), head_k));
-  }
-  const int poll = 16;
   for (int step = 0; step < max_steps;) {
     const int n = std::min(poll, max_steps - step);
     for (int i = 0; i < n; i++) HVX_CUDA(cudaGraphLaunch(L->graph, st));
@@ -1539,6 +1658,7 @@ extern "C" hvx_status hvx_llm_generate(hvx_engine* e, int n_seq, int head_k, con
     HVX_CUDA(cudaMemcpyAsync(L->n_active_host, L->n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
     HVX_CUDA(cudaStreamSynchronize(st));
     if (*L->n_active_host <= 0) break;
+  }
   }
   // surface sampler failures the way the reference raises (llm_multi_head_v3.py:165)
   std::vector<SeqState> hs(n_seq);
@@ -1597,9 +1717,63 @@ extern "C" hvx_status hvx_sample(hvx_engine* e, const float* logp, int n_heads, 
 }
 
 
+__global__ void llm_debug_rows_kernel(const __nv_bfloat16* __restrict__ semb, float* __restrict__ h, int H, int vocab) {
+  const int r = blockIdx.x, id = (7 + 13 * r) % vocab;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) h[(size_t)r * H + i] = __bfloat162float(semb[(size_t)id * H + i]);
+}
+
+// Parity probe for the two decode-step implementations (tests/test_llm_gpu.py): one step of sequence slot 0 at context
+// length `ctx` over whatever the KV cache holds, rows = speech embeddings of fixed token ids, through either the
+// kernel-per-op path (fused = 0) or the persistent fused kernel (fused = 1).  n_layers > 0 stops after that many layers
+// (heads skipped).  Outputs: residual stream rows [head_k][hidden] and, after a full step, logits [head_k][vocab].
+extern "C" hvx_status hvx_llm_debug_step(hvx_engine* e, int head_k, int ctx, int use_fused, int n_layers, float* h_out_dev,
+                                         float* logits_out_dev) {
+  HVX_CHECK(e && e->llm && h_out_dev, HVX_ERR_ARG, "llm_debug_step: bad argument");
+  hvx_config& c = e->cfg;
+  HVX_CHECK(head_k >= 1 && head_k <= c.llm_mtp_heads && ctx >= 1 && ctx + head_k < c.llm_max_ctx, HVX_ERR_ARG, "llm_debug_step: bad shape");
+  LlmState* L = e->llm;
+  cudaStream_t st = L->own;
+  const int rows = head_k, H = c.llm_hidden, V = c.llm_speech_vocab;
+  const int splits = attn_splits(e->sm_count, rows, c.llm_kv_heads);
+  StepBufs b;
+  hvx_status rc;
+  if ((rc = llm_bufs(e, L, L->ws, rows, 1, head_k, splits, &b, st))) return rc;
+  SeqState x;
+  memset(&x, 0, sizeof(x));
+  x.ctx = ctx; x.n_new = head_k; x.max_len = 1 << 30;
+  HVX_CUDA(cudaMemcpyAsync(L->seqs, &x, sizeof(x), cudaMemcpyHostToDevice, st));
+  HVX_CUDA(cudaStreamSynchronize(st));
+  llm_debug_rows_kernel<<<rows, 128, 0, st>>>(L->semb, b.h, H, V);
+  HVX_LAUNCH_CHECK(e);
+  const int full_layers = c.llm_layers;
+  const bool partial = n_layers > 0 && n_layers < full_layers;
+  if (partial) c.llm_layers = n_layers;
+  if (use_fused) {
+    const FusedPlan fp = fused_plan(e, 1, head_k, true);
+    if (!fp.ok) { c.llm_layers = full_layers; HVX_CHECK(false, HVX_ERR_UNSUPPORTED, "llm_debug_step: the fused step does not cover this shape"); }
+    cudaMemsetAsync(L->fused_bar, 0, sizeof(unsigned long long), st);
+    cudaMemsetAsync(L->fused_abort, 0, sizeof(int), st);
+    rc = launch_fused_step(e, st, L, b, head_k, fp, partial ? 5 * n_layers : (1 << 30));
+  } else {
+    rc = llm_layers(e, st, L, b, rows, L->seqs, head_k, 0, 0, splits);
+    if (!rc && !partial) rc = llm_heads(e, st, L, b, 1, head_k, head_k);
+  }
+  c.llm_layers = full_layers;
+  if (rc) return rc;
+  HVX_CUDA(cudaMemcpyAsync(h_out_dev, b.h, sizeof(float) * rows * H, cudaMemcpyDeviceToDevice, st));
+  if (logits_out_dev && !partial) HVX_CUDA(cudaMemcpyAsync(logits_out_dev, b.logits, sizeof(float) * rows * V, cudaMemcpyDeviceToDevice, st));
+  int aborted = 0;
+  HVX_CUDA(cudaMemcpyAsync(&aborted, L->fused_abort, sizeof(int), cudaMemcpyDeviceToHost, st));
+  HVX_CUDA(cudaStreamSynchronize(st));
+  HVX_CHECK(aborted == 0, HVX_ERR_CUDA, "llm_debug_step: fused decode step timed out on a barrier (code %d)", aborted);
+  if (L->graph) { cudaGraphExecDestroy(L->graph); L->graph = nullptr; }
+  return HVX_OK;
+}
+
 // Kernel-class timing for bench.py's roofline: runs one class of decode-step kernels back to back on the engine's own
 // stream (same launch path as the decode graph: PDL, persistent grids) over the real weights, CUDA-event timed.
-//   which: 0 whole step without sampler, 1 qkv gemv, 2 attention, 3 o-proj gemv, 4 gate-up gemv, 5 down gemv, 6 MTP heads + logits
+//   which: 0 whole step without sampler, 1 qkv gemv, 2 attention, 3 o-proj gemv, 4 gate-up gemv, 5 down gemv, 6 MTP heads + logits,
+//          7 whole step without sampler as the persistent fused kernel (llm_fused.cuh)
 // ms_out[0] = milliseconds per repetition (one repetition = all layers' kernels of that class)
 extern "C" hvx_status hvx_llm_bench_kernels(hvx_engine* e, int n_seq, int head_k, int ctx, int which, int reps, float* ms_out) {
   HVX_CHECK(e && e->llm && ms_out && reps >= 1, HVX_ERR_ARG, "llm_bench_kernels: bad argument");
@@ -1620,12 +1794,26 @@ extern "C" hvx_status hvx_llm_bench_kernels(hvx_engine* e, int n_seq, int head_k
   HVX_CUDA(cudaEventCreate(&e0)); HVX_CUDA(cudaEventCreate(&e1));
   unsigned long long* dbg_dev = nullptr;
   if (which == 4 && getenv("HVX_GEMV_TIMELINE")) { HVX_CUDA(cudaMalloc(&dbg_dev, 64 * 8 * 8)); HVX_CUDA(cudaMemset(dbg_dev, 0, 64 * 8 * 8)); }
+  unsigned long long* fdbg = nullptr;
+  if (which == 7 && getenv("HVX_FUSED_TIMELINE")) { HVX_CUDA(cudaMalloc(&fdbg, 1024 * 8)); HVX_CUDA(cudaMemset(fdbg, 0, 1024 * 8)); }
   auto body = [&]() -> hvx_status {
     if (which == 0) {
       if ((rc = llm_layers(e, st, L, b, rows, L->seqs, head_k, 0, 0, splits))) return rc;
       return llm_heads(e, st, L, b, n_seq, head_k, head_k);
     }
     if (which == 6) return llm_heads(e, st, L, b, n_seq, head_k, head_k);
+    if (which == 7) {                                   // the whole step as the persistent fused kernel
+      const FusedPlan fp = fused_plan(e, n_seq, head_k, true);
+      HVX_CHECK(fp.ok, HVX_ERR_UNSUPPORTED, "llm_bench_kernels: the fused step does not cover this shape");
+      HVX_CUDA(cudaMemsetAsync(L->fused_bar, 0, sizeof(unsigned long long), st));
+      return launch_fused_step(e, st, L, b, head_k, fp, 1 << 30, fdbg);
+    }
+    if (which == 8) {                                   // 100 back-to-back grid barriers of the fused kernel's grid
+      const FusedPlan fp = fused_plan(e, n_seq, head_k, true);
+      HVX_CHECK(fp.ok, HVX_ERR_UNSUPPORTED, "llm_bench_kernels: the fused step does not cover this shape");
+      HVX_CUDA(cudaMemsetAsync(L->fused_bar, 0, sizeof(unsigned long long), st));
+      return launch_fused_step(e, st, L, b, head_k, fp, -100);
+    }
     for (int l = 0; l < c.llm_layers; l++) {
       const LlmLayer& y = L->layer[l];
       if (which == 1) {
@@ -1658,6 +1846,28 @@ extern "C" hvx_status hvx_llm_bench_kernels(hvx_engine* e, int n_seq, int head_k
   cudaEventElapsedTime(&ms, e0, e1);
   ms_out[0] = ms / reps;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (fdbg) {
+    unsigned long long h[1024];
+    cudaMemcpy(h, fdbg, sizeof(h), cudaMemcpyDeviceToHost);
+    const char* nm[5] = {"qkv", "attn", "o", "gu", "down"};
+    const int nbar = 5 * c.llm_layers + 4;
+    fprintf(stderr, "[fused timeline, CTA 0, ns since kernel start] consumer: exit of the grid barrier after each phase | producer: phase fully issued\n");
+    for (int i = 1; i <= nbar; i++) {
+      const int l = (i - 1) / 5, ph = (i - 1) % 5;
+      if (l >= 2 && l < c.llm_layers - 1 && i <= 5 * c.llm_layers) continue;
+      if (i <= 5 * c.llm_layers) fprintf(stderr, "  L%02d %-5s  +%6llu  (dt %5llu)\n", l, nm[ph], h[i] - h[0], h[i] - h[i - 1]);
+      else fprintf(stderr, "  head phase %d  +%6llu  (dt %5llu)\n", i - 5 * c.llm_layers, h[i] - h[0], h[i] - h[i - 1]);
+    }
+    for (int i = 0; i < 4 * c.llm_layers + 5; i++) {
+      if (i >= 12 && i < 4 * c.llm_layers - 4) continue;
+      fprintf(stderr, "  producer phase %3d issued at +%6lld\n", i, (long long)(h[256 + i] - h[0]));
+    }
+    // SM-clock marks of CTA 0 inside layer 1 (16 per layer): stage | work done (barrier entry) | barrier exit
+    const char* mn[14] = {"qkv: rows staged+normed", "qkv: dot+RoPE+cache done", "qkv: barrier", "attn: partials done", "attn: barrier",
+                          "o: partials merged+staged", "o: dot done", "o: barrier", "gu: rows staged+normed", "gu: dot done", "gu: barrier", "down: act staged", "down: dot done", "down: barrier"};
+    for (int i = 0; i < 14; i++) fprintf(stderr, "  L01 %-26s +%6llu clk\n", mn[i], h[600 + 14 + i] - h[600 + 13]);
+    cudaFree(fdbg);
+  }
   if (dbg_dev) {
     unsigned long long h[64 * 8];
     cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);

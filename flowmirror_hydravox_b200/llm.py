@@ -120,6 +120,18 @@ class NativeLLM:
         return hid, lp
 
     @torch.no_grad()
+    def debug_step(self, head_k: int, ctx: int, fused: bool, n_layers: int = 0):
+        """One decode step of slot 0 at context `ctx` over the current KV cache through the kernel-per-op path or the
+        persistent fused kernel (hvx_llm_debug_step) -> (residual rows (head_k, hidden), logits (head_k, vocab) or None)."""
+        d, dev = self.dims, self.engine.device
+        h = torch.zeros(head_k, d.hidden, device=dev, dtype=torch.float32)
+        full = n_layers <= 0 or n_layers >= d.layers
+        lg = torch.zeros(head_k, d.speech_vocab, device=dev, dtype=torch.float32) if full else None
+        L.check(L.lib().hvx_llm_debug_step(self.engine.h, int(head_k), int(ctx), int(bool(fused)), int(n_layers), L.ptr(h), L.ptr(lg)))
+        torch.cuda.synchronize()
+        return h, lg
+
+    @torch.no_grad()
     def sample(self, logp: torch.Tensor, history: Sequence[int], min_len: int, u: torch.Tensor, sampling: Optional[Dict] = None):
         """sampling_ids (:151-166) for every row of logp (heads, vocab) against the same history snapshot."""
         dev = self.engine.device

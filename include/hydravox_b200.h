@@ -166,9 +166,15 @@ hvx_status hvx_attention_bf16(hvx_engine* e, const void* qk_dev, const void* vt_
                               int B, int T, int H, int chunk, void* stream);
 
 /* bench.py roofline helper: one class of decode-step kernels (0 whole step w/o sampler, 1 qkv, 2 attention, 3 o-proj,
- * 4 gate-up, 5 down, 6 MTP heads + logits) repeated `reps` times on the engine's stream, CUDA-event timed;
+ * 4 gate-up, 5 down, 6 MTP heads + logits, 7 whole step as the fused persistent kernel) repeated `reps` times on the engine's stream, CUDA-event timed;
  * ms_out[0] = ms per repetition (all layers' launches of that class). */
 hvx_status hvx_llm_bench_kernels(hvx_engine* e, int n_seq, int head_k, int ctx, int which, int reps, float* ms_out);
+
+/* Parity probe for the two decode-step implementations: one step of sequence slot 0 at context length ctx through the
+ * kernel-per-op path (use_fused=0) or the persistent fused kernel (use_fused=1); n_layers>0 stops after that many layers.
+ * h_out_dev [head_k][hidden], logits_out_dev [head_k][speech_vocab] (full step only). */
+hvx_status hvx_llm_debug_step(hvx_engine* e, int head_k, int ctx, int use_fused, int n_layers, float* h_out_dev,
+                              float* logits_out_dev);
 
 /* bookkeeping for bench.py: number of kernels this library has launched since creation. */
 int64_t hvx_kernel_launches(hvx_engine* e);

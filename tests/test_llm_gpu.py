@@ -194,3 +194,58 @@ def test_generate_full_fixed_length(llms):
     a = m.generate_batch([req], head_k=2, sampling=sp, min_ratio=8, max_ratio=8, u=mk())[0]
     b = m.generate_batch([req], head_k=2, sampling=sp, min_ratio=8, max_ratio=8, u=mk())[0]
     assert len(a) == 192 and max(a) < ld.speech_token_size and a == b
+
+
+# ---------------------------------------------------------------- persistent fused decode step (csrc/llm_fused.cuh)
+def _fill_cache(m, ld, n_text=24, n_ps=20, seed=3):
+    """a prefill puts real keys/values into the cache of slot 0; returns the context length"""
+    g = torch.Generator().manual_seed(seed)
+    text = torch.randint(0, ld.text_vocab, (n_text,), generator=g)
+    ps = torch.randint(0, ld.speech_token_size, (n_ps,), generator=g)
+    m.probe(text, torch.zeros(0, dtype=torch.long), ps)
+    return 2 + n_text + n_ps
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny32", "full", "full32"])
+@pytest.mark.parametrize("head_k", [1, 2, 3])
+def test_fused_step_equals_kernel_per_op_step(llms, name, head_k):
+    """The one-launch persistent step must reproduce the kernel-per-op step (same math, other summation order):
+    after 1 layer, after all layers, and on the logits of every MTP head."""
+    e, m, ld, _ = llms[name]
+    ctx = _fill_cache(m, ld)
+    for nl in (1, 0):
+        h0, lg0 = m.debug_step(head_k, ctx, fused=False, n_layers=nl)
+        h1, lg1 = m.debug_step(head_k, ctx, fused=True, n_layers=nl)
+        scale = h0.abs().max().item() + 1e-6
+        assert (h1 - h0).abs().max().item() < 2e-4 * max(1.0, scale), (name, head_k, nl, (h1 - h0).abs().max().item(), scale)
+        if nl == 0 and not name.endswith("32") and ld is D.LLM_FULL:
+            continue                                        # bf16 cache at 24 layers: rounding flips, see test_probe_matches_reference_fixture
+        if lg0 is not None:
+            lp0, lp1 = lg0.log_softmax(-1), lg1.log_softmax(-1)
+            assert (lp1 - lp0).abs().max().item() < 2e-3, (name, head_k, (lp1 - lp0).abs().max().item())
+
+
+def test_fused_step_long_context(llms):
+    """many key splits per q head (ctx 1600 -> 10 splits x 14 heads = 140 CTAs), several key iterations per warp"""
+    e, m, ld, _ = llms["full32"]
+    ctx = _fill_cache(m, ld, n_text=700, n_ps=900, seed=5)
+    h0, lg0 = m.debug_step(2, ctx, fused=False)
+    h1, lg1 = m.debug_step(2, ctx, fused=True)
+    assert (h1 - h0).abs().max().item() < 2e-4 * max(1.0, h0.abs().max().item())
+    assert (lg1.log_softmax(-1) - lg0.log_softmax(-1)).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("name", ["tiny", "tinyz"])
+def test_generate_fused_equals_unfused(llms, name, monkeypatch):
+    e, m, ld, _ = llms[name]
+    g = torch.Generator().manual_seed(11)
+    req = dict(text=torch.randint(0, ld.text_vocab, (9,), generator=g), prompt_text=torch.randint(0, ld.text_vocab, (3,), generator=g),
+               prompt_speech=torch.randint(0, ld.speech_token_size, (7,), generator=g))
+    u = torch.rand(1, 2048, generator=g)
+    lo, hi = (6, 6) if name == "tinyz" else (2, 20)         # "tiny" has live stop tokens: natural stop instead of a forced length
+    for K in (1, 2, 4):
+        monkeypatch.setenv("HVX_FUSED_DECODE", "0")
+        a = m.generate_batch([req], head_k=K, u=u, min_ratio=lo, max_ratio=hi)[0]
+        monkeypatch.setenv("HVX_FUSED_DECODE", "1")
+        b = m.generate_batch([req], head_k=K, u=u, min_ratio=lo, max_ratio=hi)[0]
+        assert len(b) > 0 and a == b, (K, a, b)
