@@ -34,7 +34,7 @@ struct ConvArgs {
   int Cin, Cout, K, dil, up, pad_left, Lin, Lout, ldx;
   int pre_act;          // 0 none, 1 leaky-relu(slope), 2 snake(alpha)
   float slope;
-  int post_elu, accumulate, reflect1;
+  int post_elu /* 1 ELU, 2 tanh */, accumulate, reflect1;
   float out_scale;
   int zstuff;           // 1: the x`up` input is zero-stuffed (x[v/up] at v % up == 0, else 0) instead of nearest-repeated:
                         //    ConvTranspose1d(k, stride up) == conv of the zero-stuffed signal with the tap-reversed kernel
@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(256) conv1d_tile_kernel(ConvArgs p) {
       const int t = t0 + lane + 32 * j;
       if (t >= p.Lout) continue;
       float v = acc[c][j] + b;
-      if (p.post_elu) v = v > 0.f ? v : expm1f(v);
+      if (p.post_elu == 1) v = v > 0.f ? v : expm1f(v);
+      else if (p.post_elu == 2) v = tanhf(v);
       const int nrep = (p.reflect1 && t == 1) ? 2 : 1;
       for (int r = 0; r < nrep; r++) {
         const size_t idx = (size_t)co * Ly + (r == 1 ? 0 : t + (p.reflect1 ? 1 : 0));
@@ -417,14 +418,16 @@ static hvx_status run_conv(hvx_engine* e, cudaStream_t st, const ConvW& c, const
 // symmetric: "same" padding (k*d-d)/2 on both sides (ResBlock of the non-causal HiFTGenerator, generator.py:46-108) instead of causal
 static hvx_status run_resblock(hvx_engine* e, cudaStream_t st, const ResBlockW& r, int ndil, const int* dils,
                                const float* x_in, float* work, float* tmp, int L, const float* extra, float* final_out,
-                               int final_accumulate, float final_scale, bool symmetric = false) {
+                               int final_accumulate, float final_scale, bool symmetric = false, bool lrelu = false) {
   const float* cur = x_in;
   for (int j = 0; j < ndil; j++) {
     ConvOpt o1; o1.dil = dils[j]; o1.pre_act = 2; o1.alpha = r.a1[j];
+    if (lrelu) { o1.pre_act = 1; o1.slope = 0.1f; o1.alpha = nullptr; }   // ResBlock1 of the classic HiFi-GAN (matcha/hifigan/models.py:86-93)
     if (symmetric) o1.pad_left = (r.c1[j].K - 1) * dils[j] / 2;
     hvx_status s = run_conv(e, st, r.c1[j], cur, L, tmp, o1);
     if (s) return s;
     ConvOpt o2; o2.pre_act = 2; o2.alpha = r.a2[j]; o2.res1 = cur;
+    if (lrelu) { o2.pre_act = 1; o2.slope = 0.1f; o2.alpha = nullptr; }
     if (symmetric) o2.pad_left = (r.c2[j].K - 1) / 2;
     float* dst = work;
     if (j == ndil - 1) {
@@ -638,5 +641,63 @@ extern "C" hvx_status hvx_hift_t_vocode(hvx_engine* e, const float* mel, int T, 
   HVX_LAUNCH_CHECK(e);
   istft_ola_kernel<<<cdiv(Ns, 256), 256, 0, st>>>(fbuf, wav, F, Ns, 0.99f);
   HVX_LAUNCH_CHECK(e);
+  return HVX_OK;
+}
+
+// Classic HiFi-GAN Generator.forward (matcha/hifigan/models.py:148-193; ResBlock1 :14-93): conv_pre k7 -> per stage
+// leaky-relu(0.1) + weight-normed ConvTranspose1d(k, u, padding (k-u)/2) + mean of the ResBlock1s -> leaky-relu(0.01) ->
+// conv_post k7 -> tanh.  Packed tensors (weights.pack_hifigan): conv_pre, ups.i (tap-reversed), rb.n.c1.j / rb.n.c2.j,
+// conv_post; stage count / rates / kernel sizes from hvx_config.hift_* (no F0, source or ISTFT head on this variant).
+extern "C" hvx_status hvx_hifigan_vocode(hvx_engine* e, const float* mel, int T, float* wav, void* stream) {
+  HVX_CHECK(e && mel && wav && T >= 1, HVX_ERR_ARG, "hifigan: bad arguments (T=%d)", T);
+  const hvx_config& c = e->cfg;
+  HVX_CHECK(c.hift_n_ups >= 1 && c.hift_n_ups <= 4 && c.hift_n_rb >= 1 && c.hift_n_rb <= 3 && c.hift_n_dil >= 1 && c.hift_n_dil <= 4,
+            HVX_ERR_UNSUPPORTED, "hifigan: %d stages x %d resblocks x %d dilations unsupported", c.hift_n_ups, c.hift_n_rb, c.hift_n_dil);
+  if (!e->hift) e->hift = new HiftState();
+  HiftState* h = e->hift;
+  cudaStream_t st = (cudaStream_t)stream;
+  hvx_status rc;
+  if ((rc = get_conv(e, "conv_pre", &h->conv_pre))) return rc;
+  if ((rc = get_conv(e, "conv_post", &h->conv_post))) return rc;
+  HVX_CHECK(h->conv_post.Cout == 1, HVX_ERR_STATE, "hifigan: conv_post has %d output channels (the stage holds HiFT weights?)", h->conv_post.Cout);
+  for (int i = 0; i < c.hift_n_ups; i++) {
+    if ((rc = get_conv(e, "ups." + std::to_string(i), &h->ups[i]))) return rc;
+    HVX_CHECK(h->ups[i].K >= c.hift_ups[i] && (h->ups[i].K - c.hift_ups[i]) % 2 == 0, HVX_ERR_UNSUPPORTED,
+              "hifigan: upsample kernel %d / rate %d: only k-u even is built (output length u*L)", h->ups[i].K, c.hift_ups[i]);
+    for (int j = 0; j < c.hift_n_rb; j++) {
+      ResBlockW& r = h->rb[i * c.hift_n_rb + j];
+      const std::string pfx = "rb." + std::to_string(i * c.hift_n_rb + j);
+      for (int d = 0; d < c.hift_n_dil; d++) {
+        if ((rc = get_conv(e, pfx + ".c1." + std::to_string(d), &r.c1[d]))) return rc;
+        if ((rc = get_conv(e, pfx + ".c2." + std::to_string(d), &r.c2[d]))) return rc;
+        r.a1[d] = r.a2[d] = nullptr;
+      }
+    }
+  }
+  const int C0 = h->conv_pre.Cout;
+  size_t off = 0, maxCL = 0;
+  auto take = [&](size_t n) { size_t o = off; off += (n + 63) & ~(size_t)63; return o; };
+  { int L = T; for (int i = 0; i < c.hift_n_ups; i++) { L *= c.hift_ups[i]; size_t cl = (size_t)h->ups[i].Cout * L; if (cl > maxCL) maxCL = cl; } }
+  const size_t o_x0 = take((size_t)C0 * T), o_x = take(maxCL), o_xs = take(maxCL), o_work = take(maxCL), o_tmp = take(maxCL);
+  float* ws = (float*)h->ws.get(off * sizeof(float));
+  HVX_CHECK(ws, HVX_ERR_CUDA, "hifigan: workspace allocation of %zu bytes failed", off * sizeof(float));
+  float *x0 = ws + o_x0, *x = ws + o_x, *xs = ws + o_xs, *work = ws + o_work, *tmp = ws + o_tmp;
+
+  { ConvOpt o; o.pad_left = (h->conv_pre.K - 1) / 2;
+    if ((rc = run_conv(e, st, h->conv_pre, mel, T, x0, o))) return rc; }
+  const float* cur = x0;
+  int L = T;
+  for (int i = 0; i < c.hift_n_ups; i++) {
+    const int u = c.hift_ups[i], K = h->ups[i].K;
+    { ConvOpt o; o.pre_act = 1; o.slope = 0.1f; o.up = u; o.zstuff = 1; o.pad_left = K - 1 - (K - u) / 2; o.Lout = L * u;
+      if ((rc = run_conv(e, st, h->ups[i], cur, L, x, o))) return rc; }
+    L *= u;
+    for (int j = 0; j < c.hift_n_rb; j++)
+      if ((rc = run_resblock(e, st, h->rb[i * c.hift_n_rb + j], c.hift_n_dil, c.hift_rb_d, x, work, tmp, L, nullptr, xs,
+                             j > 0, 1.0f / c.hift_n_rb, true, true))) return rc;
+    cur = xs;
+  }
+  { ConvOpt o; o.pre_act = 1; o.slope = 0.01f; o.pad_left = (h->conv_post.K - 1) / 2; o.post_elu = 2;
+    if ((rc = run_conv(e, st, h->conv_post, cur, L, wav, o))) return rc; }
   return HVX_OK;
 }

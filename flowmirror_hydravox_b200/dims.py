@@ -80,6 +80,10 @@ FLOW_FULL = FlowDims()
 LLM_FULL = LlmDims()
 
 HIFT_TINY = HiftDims(base=64, f0_ch=64)
+# classic HiFi-GAN v1 generator (matcha/hifigan/config.py:1-28, models.py:148-193): 22.05 kHz, hop 256 = 8*8*2*2, no ISTFT head
+# (hop=1 makes frame_samples the product of the rates); f0_ch / harmonics / n_fft / src_k are unused by this variant
+HIFIGAN_V1 = HiftDims(sr=22050, ups=(8, 8, 2, 2), up_k=(16, 16, 4, 4), hop=1)
+HIFIGAN_TINY = HiftDims(sr=22050, base=64, ups=(4, 2, 2), up_k=(8, 4, 4), hop=1, rb_k=(3, 7))
 FLOW_TINY = FlowDims(vocab=512, pla_ch=128, depth=2, noise_frames=600)   # dim stays 1024: the reference hard-codes 16 conv groups
 LLM_TINY = LlmDims(hidden=128, layers=2, q_heads=2, kv_heads=1, inter=256, text_vocab=512,
                    speech_vocab=456, mtp_heads=3, mtp_attn_heads=2, mtp_inter=384)

@@ -6,7 +6,7 @@ import ctypes as C
 import torch
 
 from . import _lib as L
-from .weights import pack_hift, pack_hift_t
+from .weights import pack_hift, pack_hift_t, pack_hifigan
 
 
 class NativeHiFT:
@@ -120,3 +120,42 @@ class NativeHiFTTransposed:
     def decode(self, x: torch.Tensor, s: torch.Tensor):
         """HiFTGenerator.decode (:506-540): mel (1, mel, T) and an explicit source s (1, 1, frame*T) -> speech (1, frame*T)."""
         return self.inference(x, cache_source=s)[0]
+
+
+class NativeHiFiGAN:
+    """Drop-in for the classic HiFi-GAN `Generator` (matcha/hifigan/models.py:148-193): `forward(x)` / `__call__` take a mel
+    (B, mel, T) fp32 and return the waveform (B, 1, prod(upsample_rates)*T) in (-1, 1), one hvx_hifigan_vocode per batch row.
+    Build the engine with `hd=dims.HIFIGAN_V1` (or any HiftDims carrying this generator's rates / kernel sizes)."""
+
+    def __init__(self, engine: "L.Engine"):
+        self.engine = engine
+        self.dims = engine.hd
+
+    def load_state_dict(self, sd, strict=True):
+        self.engine.set_tensors(L.STAGE_HIFT, pack_hifigan(sd, self.dims))
+        return self
+
+    def eval(self):
+        return self
+
+    def cuda(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def remove_weight_norm(self):          # models.py:195-203 — the packed weights are already folded
+        return None
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        assert x.dim() == 3 and x.shape[1] == self.dims.mel
+        dev = self.engine.device
+        mel = x.to(dev, torch.float32).contiguous()
+        B, _, T = mel.shape
+        wav = torch.empty(B, 1, T * self.dims.frame_samples, device=dev, dtype=torch.float32)
+        for b in range(B):
+            L.check(L.lib().hvx_hifigan_vocode(self.engine.h, L.ptr(mel[b]), T, L.ptr(wav[b]), L.stream_ptr()))
+        return wav
+
+    __call__ = forward

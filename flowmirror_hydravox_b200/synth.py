@@ -96,6 +96,35 @@ def hift_t_state_dict(d: HiftDims, seed: int = 0) -> Dict[str, torch.Tensor]:
     return sd
 
 
+def hifigan_state_dict(d: HiftDims, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Checkpoint of the classic HiFi-GAN `Generator` (matcha/hifigan/models.py:148-193) with torch.nn.utils.weight_norm keys
+    (`weight_g`, `weight_v`): Conv1d norms over (in, k) per output channel, ConvTranspose1d norms per input channel (dim 0)."""
+    g = _gen(seed + 21)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def wn(name, shape, fan, gain):
+        v = _randn(g, *shape)
+        sd[name + ".weight_v"] = v
+        sd[name + ".weight_g"] = v.reshape(shape[0], -1).norm(dim=1).reshape(shape[0], 1, 1) * (gain / fan ** 0.5)
+
+    wn("conv_pre", (d.base, d.mel, 7), d.mel * 7, 1.0)
+    sd["conv_pre.bias"] = _randn(g, d.base, std=0.05)
+    for i, (u, k) in enumerate(zip(d.ups, d.up_k)):
+        cin, cout = d.base >> i, d.base >> (i + 1)
+        wn(f"ups.{i}", (cin, cout, k), cin * k / u, 1.0)
+        sd[f"ups.{i}.bias"] = _randn(g, cout, std=0.05)
+        for j, rk in enumerate(d.rb_k):
+            n = i * len(d.rb_k) + j
+            for c in ("convs1", "convs2"):
+                for t in range(len(d.rb_d)):
+                    wn(f"resblocks.{n}.{c}.{t}", (cout, cout, rk), cout * rk, 0.8)
+                    sd[f"resblocks.{n}.{c}.{t}.bias"] = _randn(g, cout, std=0.05)
+    ch = d.base >> len(d.ups)
+    wn("conv_post", (1, ch, 7), ch * 7, 0.3)
+    sd["conv_post.bias"] = _randn(g, 1, std=0.05)
+    return sd
+
+
 def hift_sine_table(d: HiftDims, n_frames: int, seed: int = 11) -> torch.Tensor:
     """Stand-in for SineGen2.sine_waves (generator.py:226): uniform[0,1) rows, (n_frames*frame, H)."""
     return torch.rand(n_frames * d.frame_samples, d.harmonics, generator=_gen(seed))

@@ -17,8 +17,11 @@ def _fold_wn(sd, base):
     """w = v * (g / ||v||) over (in, k) per out channel — torch._weight_norm op order."""
     if base + ".weight" in sd:
         return sd[base + ".weight"].float()
-    g = sd[base + ".parametrizations.weight.original0"].float()
-    v = sd[base + ".parametrizations.weight.original1"].float()
+    if base + ".weight_g" in sd:                         # torch.nn.utils.weight_norm (the classic HiFi-GAN checkpoints)
+        g, v = sd[base + ".weight_g"].float(), sd[base + ".weight_v"].float()
+    else:
+        g = sd[base + ".parametrizations.weight.original0"].float()
+        v = sd[base + ".parametrizations.weight.original1"].float()
     n = v.reshape(v.shape[0], -1).norm(2, 1).reshape(-1, 1, 1)
     return v * (g / n)
 
@@ -40,6 +43,22 @@ def _conv_transpose(sd, base, out, name):
 def pack_hift_t(sd: Dict[str, torch.Tensor], d: D.HiftDims) -> Dict[str, torch.Tensor]:
     """HiFTGenerator (generator.py:378-569) state_dict -> the same packed tensor names as the causal vocoder."""
     return pack_hift(sd, d, transposed=True)
+
+
+def pack_hifigan(sd: Dict[str, torch.Tensor], d: D.HiftDims) -> Dict[str, torch.Tensor]:
+    """Classic HiFi-GAN `Generator` (matcha/hifigan/models.py:148-193) state_dict (weight-normed or with the norm removed,
+    :195-203) -> packed tensors for hvx_hifigan_vocode."""
+    o: Dict[str, torch.Tensor] = {}
+    _conv(sd, "conv_pre", o, "conv_pre")
+    _conv(sd, "conv_post", o, "conv_post")
+    for i in range(len(d.ups)):
+        _conv_transpose(sd, f"ups.{i}", o, f"ups.{i}")
+        for j in range(len(d.rb_k)):
+            n = i * len(d.rb_k) + j
+            for t in range(len(d.rb_d)):
+                _conv(sd, f"resblocks.{n}.convs1.{t}", o, f"rb.{n}.c1.{t}")
+                _conv(sd, f"resblocks.{n}.convs2.{t}", o, f"rb.{n}.c2.{t}")
+    return o
 
 
 def pack_hift(sd: Dict[str, torch.Tensor], d: D.HiftDims, transposed: bool = False) -> Dict[str, torch.Tensor]:

@@ -97,6 +97,12 @@ hvx_status hvx_hift_t_vocode(hvx_engine* e, const float* mel_dev, int T, const f
                              const float* cache_source_dev, int n_cache, const float* f0_in_dev, float* f0_out_dev,
                              float* wav_dev, float* src_dev, void* stream);
 
+/* ---- classic HiFi-GAN: replaces Generator.forward (matcha/hifigan/models.py:148-193; ResBlock1 :14-93) — conv_pre,
+ * leaky-relu + weight-normed ConvTranspose1d(k, u, padding=(k-u)/2) up-sampling (v1: rates 8,8,2,2, kernels 16,16,4,4), the mean
+ * of the ResBlock1 stacks per stage, conv_post, tanh.  mel_dev (mel, T) fp32 -> wav_dev (prod(rates)*T) fp32 in (-1, 1).
+ * The engine's HiFT stage holds weights.pack_hifigan tensors; stage geometry comes from hvx_config.hift_*. */
+hvx_status hvx_hifigan_vocode(hvx_engine* e, const float* mel_dev, int T, float* wav_dev, void* stream);
+
 /* ---- flow: replaces CausalMaskedDiffWithDiT.inference (cosyvoice/flow/flow.py:367-430) ----
  * tokens = prompt||new speech tokens (n_prompt + n_tok), embedding (spk_in) fp32,
  * prompt_feat (2*n_prompt, mel) fp32 or NULL; noise_dev = CausalConditionalCFM.rand_noise

@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from flowmirror_hydravox_b200 import dims as D, synth  # noqa: E402
-from oracle import flow_ref, hift_ref, llm_ref, refshim  # noqa: E402
+from oracle import flow_ref, hift_ref, hifigan_ref, llm_ref, refshim  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -100,6 +100,22 @@ def golden_hift_t(name, dims, T, seed):
     assert es < 2e-4 and ei < 2e-3 and ec < 2e-3
     torch.save(dict(dims=name, seed=seed, T=T, mel=mel, s=s, wav=wav, f0=f0, noise=noise, wav_inf=wav_i, src_inf=s_i,
                     wav_cache=wav_c, sd_checksum=checksum(sd)), os.path.join(OUT, f"hift_t_{name}.pt"))
+
+
+def golden_hifigan(name, dims, T, seed):
+    """a12' (second variant): the classic HiFi-GAN Generator vendored under matcha/hifigan."""
+    m = refshim.build_hifigan(dims)
+    sd = synth.hifigan_state_dict(dims, seed)
+    m.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(seed + 400)
+    mel = torch.rand(2, dims.mel, T, generator=g) * 6.0 - 6.0
+    with torch.no_grad():
+        wav = m(mel)
+    wav_o = hifigan_ref.generator(sd, mel, dims)
+    e = (wav - wav_o).abs().max().item()
+    print(f"[hifigan:{name}] T={T} ref-vs-oracle wav max-abs {e:.2e}; out {tuple(wav.shape)} rms {wav.pow(2).mean().sqrt():.3f} |max| {wav.abs().max():.3f}")
+    assert e < 5e-6 and wav.shape[-1] == T * dims.frame_samples
+    torch.save(dict(dims=name, seed=seed, T=T, mel=mel, wav=wav, sd_checksum=checksum(sd)), os.path.join(OUT, f"hifigan_{name}.pt"))
 
 
 def golden_flow(name, dims, N, P, n_steps, seed):
@@ -204,6 +220,11 @@ def golden_llm(name, dims, n_text, n_ptext, P, cases, seed):
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if sys.argv[1:] == ["hifigan"]:
+        with torch.no_grad():
+            golden_hifigan("tiny", D.HIFIGAN_TINY, 37, 0)
+            golden_hifigan("v1", D.HIFIGAN_V1, 24, 0)
+        return
     if sys.argv[1:] == ["hift_t"]:                                  # regenerate only the a12' fixtures
         with torch.no_grad():
             golden_hift_t("tiny", D.HIFT_TINY, 29, 0)
@@ -214,6 +235,8 @@ def main():
         golden_hift("full", D.HIFT_FULL, 24, 0)
         golden_hift_t("tiny", D.HIFT_TINY, 29, 0)
         golden_hift_t("full", D.HIFT_FULL, 20, 0)
+        golden_hifigan("tiny", D.HIFIGAN_TINY, 37, 0)
+        golden_hifigan("v1", D.HIFIGAN_V1, 24, 0)
         golden_flow("tiny", D.FLOW_TINY, 21, 10, 10, 0)
         golden_flow("full", D.FLOW_FULL, 24, 8, 4, 0)
         sp1 = dict(top_p=0.9, top_k=10, win_size=24, tau_r=0.2)     # server tts defaults (router.py:22-44)

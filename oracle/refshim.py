@@ -220,6 +220,16 @@ def build_hift_t(cfg, seed=0):
     return m.eval()
 
 
+def build_hifigan(cfg):
+    """The reference's classic HiFi-GAN `Generator` (matcha/hifigan/models.py:148-193) at cfg dims (eval, weight-normed)."""
+    install()
+    from matcha.hifigan.models import Generator
+    h = _AttrDict(resblock="1", upsample_rates=list(cfg.ups), upsample_kernel_sizes=list(cfg.up_k),
+                  upsample_initial_channel=cfg.base, resblock_kernel_sizes=list(cfg.rb_k),
+                  resblock_dilation_sizes=[list(cfg.rb_d)] * len(cfg.rb_k))
+    return Generator(h).eval()
+
+
 def build_flow(cfg, seed=0, dtype=torch.float32):
     install()
     from cosyvoice.flow.flow import CausalMaskedDiffWithDiT

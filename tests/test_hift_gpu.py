@@ -146,3 +146,55 @@ def test_hift_transposed_fresh_noise_is_stochastic_like_reference(engines_t):
     a, _ = h.inference(mel)
     b, _ = h.inference(mel)
     assert a.shape == (1, 12 * hd.frame_samples) and torch.isfinite(a).all() and not torch.equal(a, b)
+
+
+# ---------------------------------------------------------------- a12' (second variant): classic HiFi-GAN Generator
+@pytest.fixture(scope="module")
+def engines_gan():
+    from flowmirror_hydravox_b200 import _lib as L
+    from flowmirror_hydravox_b200.hift import NativeHiFiGAN
+    out = {}
+    for name, hd in (("tiny", D.HIFIGAN_TINY), ("v1", D.HIFIGAN_V1)):
+        e = L.Engine(hd=hd)
+        h = NativeHiFiGAN(e)
+        h.load_state_dict(synth.hifigan_state_dict(hd, 0))
+        out[name] = (e, h, hd)
+    yield out
+    for e, _, _ in out.values():
+        e.close()
+
+
+@pytest.mark.parametrize("name", ["tiny", "v1"])
+def test_hifigan_matches_reference_fixture(engines_gan, golden, name):
+    """hvx_hifigan_vocode vs the unmodified matcha.hifigan.models.Generator (tests/golden/hifigan_*.pt), batch of 2."""
+    e, h, hd = engines_gan[name]
+    g = golden(f"hifigan_{name}")
+    wav = h(g["mel"])
+    assert wav.shape == g["wav"].shape
+    err = (wav.cpu() - g["wav"]).abs()
+    assert err.pow(2).mean().sqrt().item() < 1e-5 and err.max().item() < 1e-4, (err.pow(2).mean().sqrt().item(), err.max().item())
+
+
+@pytest.mark.parametrize("T", [1, 2, 5, 300])
+def test_hifigan_matches_oracle_lengths(engines_gan, T):
+    from oracle import hifigan_ref
+    e, h, hd = engines_gan["tiny"]
+    sd = synth.hifigan_state_dict(hd, 0)
+    mel = torch.rand(1, hd.mel, T, generator=torch.Generator().manual_seed(T)) * 6 - 6
+    ref = hifigan_ref.generator(sd, mel, hd)
+    wav = h(mel)
+    assert wav.shape == ref.shape == (1, 1, T * hd.frame_samples)
+    assert (wav.cpu() - ref).abs().max().item() < 1e-4
+
+
+def test_hifigan_rejects_hift_weights(engines_gan):
+    """an engine whose HiFT stage holds the 18-channel ISTFT head must not be run as a classic HiFi-GAN"""
+    from flowmirror_hydravox_b200 import _lib as L
+    from flowmirror_hydravox_b200.hift import NativeHiFT, NativeHiFiGAN
+    e = L.Engine(hd=D.HIFT_TINY)
+    try:
+        NativeHiFT(e).load_state_dict(synth.hift_state_dict(D.HIFT_TINY, 0))
+        with pytest.raises(L.HvxError):
+            NativeHiFiGAN(e)(torch.zeros(1, D.HIFT_TINY.mel, 4))
+    finally:
+        e.close()

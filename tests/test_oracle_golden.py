@@ -51,6 +51,30 @@ def test_hift_transposed_oracle_matches_reference(golden, name, dims):
     assert (wav_c - g["wav_cache"]).abs().max() < 5e-6
 
 
+@pytest.mark.parametrize("name,dims", [("tiny", D.HIFIGAN_TINY), ("v1", D.HIFIGAN_V1)])
+def test_hifigan_oracle_matches_reference(golden, name, dims):
+    """a12' (second variant): classic HiFi-GAN Generator (matcha/hifigan/models.py:148-193), fixtures from the unmodified module."""
+    from oracle import hifigan_ref
+    g = golden(f"hifigan_{name}")
+    sd = synth.hifigan_state_dict(dims, g["seed"])
+    assert abs(_checksum(sd) - g["sd_checksum"]) < 1e-6 * g["sd_checksum"]
+    wav = hifigan_ref.generator(sd, g["mel"], dims)
+    assert wav.shape == g["wav"].shape == (2, 1, g["T"] * dims.frame_samples)
+    assert (wav - g["wav"]).abs().max() < 5e-6
+    # the packed (folded, tap-reversed) weights are the same linear maps: conv of the zero-stuffed signal == conv_transpose
+    from flowmirror_hydravox_b200.weights import pack_hifigan
+    pk = pack_hifigan(sd, dims)
+    x = torch.randn(1, dims.base, 9, generator=torch.Generator().manual_seed(1))
+    u, k = dims.ups[0], dims.up_k[0]
+    ref = torch.nn.functional.conv_transpose1d(x, hifigan_ref.fold(sd, "ups.0"), sd["ups.0.bias"], stride=u, padding=(k - u) // 2)
+    z = torch.zeros(1, dims.base, (9 - 1) * u + 1)
+    z[:, :, ::u] = x
+    pl = k - 1 - (k - u) // 2
+    z = torch.nn.functional.pad(z, (pl, 9 * u + k - 1 - pl - z.shape[2]))
+    mine = torch.nn.functional.conv1d(z, pk["ups.0.w"].permute(2, 0, 1), pk["ups.0.b"])
+    assert mine.shape == ref.shape and (mine - ref).abs().max() < 1e-5
+
+
 def test_hift_source_noise_replays_reference_rng(golden):
     """draw_source_noise consumes the global generator like SineGen2.forward did when the fixture was minted
     (rand(1,H), then randn_like of a (1,n,H) view of (1,H,n) memory)."""
