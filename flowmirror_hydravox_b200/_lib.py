@@ -12,7 +12,7 @@ from . import dims as D
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhydravox_b200.so")
 
-STAGE_LLM, STAGE_FLOW, STAGE_HIFT = 0, 1, 2
+STAGE_LLM, STAGE_FLOW, STAGE_HIFT, STAGE_UNET = 0, 1, 2, 3
 _DT = {torch.float32: 0, torch.bfloat16: 1, torch.int32: 2, torch.float16: 3}
 
 
@@ -34,6 +34,8 @@ class Config(C.Structure):
         ("llm_head_dim", C.c_int), ("llm_inter", C.c_int), ("llm_text_vocab", C.c_int), ("llm_speech_vocab", C.c_int),
         ("llm_mtp_heads", C.c_int), ("llm_mtp_inter", C.c_int), ("llm_max_ctx", C.c_int), ("llm_max_seqs", C.c_int),
         ("llm_rope_theta", C.c_float), ("llm_eps", C.c_float), ("llm_kv_f32", C.c_int),
+        ("unet_mel", C.c_int), ("unet_ch", C.c_int), ("unet_n_blocks", C.c_int), ("unet_n_mid", C.c_int),
+        ("unet_heads", C.c_int), ("unet_ff_mult", C.c_int), ("unet_chunk", C.c_int),
     ]
 
 
@@ -52,7 +54,7 @@ class Request(C.Structure):
 
 
 def make_config(hd: D.HiftDims, fd: D.FlowDims, ld: D.LlmDims, max_ctx: int = 8192, max_seqs: int = 32,
-                kv_f32: bool = False, flow_precise: bool = False) -> Config:
+                kv_f32: bool = False, flow_precise: bool = False, ud: D.UnetDims | None = None) -> Config:
     c = Config()
     c.hift_mel, c.hift_base, c.hift_f0_ch, c.hift_harmonics, c.hift_sr = hd.mel, hd.base, hd.f0_ch, hd.harmonics, hd.sr
     c.hift_n_ups = len(hd.ups)
@@ -76,6 +78,9 @@ def make_config(hd: D.HiftDims, fd: D.FlowDims, ld: D.LlmDims, max_ctx: int = 81
     c.llm_mtp_heads, c.llm_mtp_inter, c.llm_max_ctx, c.llm_max_seqs = ld.mtp_heads, ld.mtp_inter, max_ctx, max_seqs
     c.llm_rope_theta, c.llm_eps = ld.rope_theta, ld.eps
     c.llm_kv_f32 = int(bool(kv_f32))
+    if ud is not None:
+        c.unet_mel, c.unet_ch, c.unet_n_blocks, c.unet_n_mid = ud.mel, ud.ch, ud.n_blocks, ud.n_mid
+        c.unet_heads, c.unet_ff_mult, c.unet_chunk = ud.heads, ud.ff_mult, ud.chunk
     return c
 
 
@@ -111,18 +116,18 @@ class Engine:
     """Owns one hvx_engine (one per process/GPU, like one reference worker per GPU)."""
 
     def __init__(self, hd=D.HIFT_FULL, fd=D.FLOW_FULL, ld=D.LLM_FULL, max_ctx=8192, max_seqs=32, device="cuda:0",
-                 kv_f32=False, flow_precise=False):
+                 kv_f32=False, flow_precise=False, ud=None):
         if not torch.cuda.is_available():
             raise HvxError("no CUDA device: the HydraVox B200 engine has no CPU fallback")
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
         torch.zeros(1, device=self.device)          # make sure the primary context exists
-        self.hd, self.fd, self.ld = hd, fd, ld
-        self.cfg = make_config(hd, fd, ld, max_ctx, max_seqs, kv_f32, flow_precise)
+        self.hd, self.fd, self.ld, self.ud = hd, fd, ld, ud
+        self.cfg = make_config(hd, fd, ld, max_ctx, max_seqs, kv_f32, flow_precise, ud)
         self.flow_precise = bool(flow_precise)
         self.h = C.c_void_p()
         check(lib().hvx_create(C.byref(self.h), C.byref(self.cfg)))
-        self._keep = {0: {}, 1: {}, 2: {}}          # tensors borrowed by the engine
+        self._keep = {0: {}, 1: {}, 2: {}, 3: {}}          # tensors borrowed by the engine
 
     def set_tensors(self, stage: int, tensors: dict):
         for name, t in tensors.items():

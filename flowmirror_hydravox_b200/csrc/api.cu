@@ -40,6 +40,7 @@ extern "C" hvx_status hvx_destroy(hvx_engine* e) {
   hift_free(e);
   flow_free(e);
   llm_free(e);
+  unet_free(e);
   delete e;
   return HVX_OK;
 }
@@ -47,7 +48,7 @@ extern "C" hvx_status hvx_destroy(hvx_engine* e) {
 extern "C" hvx_status hvx_set_tensor(hvx_engine* e, int stage, const char* name, const void* dptr, int dtype,
                                      const int64_t* shape, int ndim) {
   HVX_CHECK(e && name && dptr && shape, HVX_ERR_ARG, "hvx_set_tensor: null argument");
-  HVX_CHECK(stage >= 0 && stage < 3 && ndim >= 1 && ndim <= 4, HVX_ERR_ARG, "hvx_set_tensor(%s): bad stage/ndim", name);
+  HVX_CHECK(stage >= 0 && stage < 4 && ndim >= 1 && ndim <= 4, HVX_ERR_ARG, "hvx_set_tensor(%s): bad stage/ndim", name);
   Tensor t;
   t.p = dptr; t.dtype = dtype; t.ndim = ndim;
   for (int i = 0; i < ndim; i++) t.shape[i] = shape[i];
@@ -61,6 +62,7 @@ extern "C" hvx_status hvx_finalize(hvx_engine* e, int stage) {
     case HVX_STAGE_HIFT: return hift_finalize(e);
     case HVX_STAGE_FLOW: return flow_finalize(e);
     case HVX_STAGE_LLM: return llm_finalize(e);
+    case HVX_STAGE_UNET: return unet_finalize(e);
   }
   set_error("hvx_finalize: bad stage %d", stage);
   return HVX_ERR_ARG;

@@ -42,15 +42,17 @@ struct DevBuf {              // engine-owned scratch that grows on demand (never
 struct HiftState;
 struct FlowState;
 struct LlmState;
+struct UnetState;
 
 }  // namespace hvx
 
 struct hvx_engine {
   hvx_config cfg;
-  std::unordered_map<std::string, hvx::Tensor> tensors[3];
+  std::unordered_map<std::string, hvx::Tensor> tensors[4];
   hvx::HiftState* hift = nullptr;
   hvx::FlowState* flow = nullptr;
   hvx::LlmState* llm = nullptr;
+  hvx::UnetState* unet = nullptr;
   int64_t launches = 0;
   hvx::DevBuf samp_ws;             // sampler tables (llm.cu)
   void* samp_arrive = nullptr;
@@ -94,6 +96,8 @@ hvx_status flow_finalize(hvx_engine* e);
 void flow_free(hvx_engine* e);
 hvx_status llm_finalize(hvx_engine* e);
 void llm_free(hvx_engine* e);
+hvx_status unet_finalize(hvx_engine* e);
+void unet_free(hvx_engine* e);
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 }  // namespace hvx

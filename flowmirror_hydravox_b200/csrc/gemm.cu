@@ -74,6 +74,7 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == ACT_SILU) return v / (1.0f + expf(-v));
   if (act == ACT_MISH) { const float sp = v > 20.0f ? v : log1pf(expf(v)); return v * tanhf(sp); }
   if (act == ACT_LRELU) return v > 0.f ? v : 0.01f * v;
+  if (act == ACT_GELU_ERF) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
   return v;
 }
 
@@ -160,7 +161,7 @@ __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx,
         if (col0 < epi.n_qk) {
           const int dq = epi.n_qk >> 1;
           const int cl = col0 % dq;
-          if (cl < 64) {
+          if (cl < 64 && epi.rope_cos) {            // null table: no rotary (U-Net estimator, unet.cu)
             const float* cs = epi.rope_cos + (size_t)t * 32 + (cl >> 1);
             const float* sn = epi.rope_sin + (size_t)t * 32 + (cl >> 1);
 #pragma unroll
@@ -435,6 +436,7 @@ static hvx_status launch_gemm_persist_t(hvx_engine* e, cudaStream_t st, const CU
       case EPI_BF16 * 8 + ACT_GELU_TANH: return CALL(EPI_BF16, ACT_GELU_TANH);                   \
       case EPI_BF16 * 8 + ACT_MISH: return CALL(EPI_BF16, ACT_MISH);                             \
       case EPI_BF16 * 8 + ACT_LRELU: return CALL(EPI_BF16, ACT_LRELU);                           \
+      case EPI_BF16 * 8 + ACT_GELU_ERF: return CALL(EPI_BF16, ACT_GELU_ERF);                     \
       case EPI_F32 * 8 + ACT_NONE: return CALL(EPI_F32, ACT_NONE);                               \
       case EPI_F32 * 8 + ACT_GELU_TANH: return CALL(EPI_F32, ACT_GELU_TANH);                     \
       case EPI_F32 * 8 + ACT_MISH: return CALL(EPI_F32, ACT_MISH);                               \

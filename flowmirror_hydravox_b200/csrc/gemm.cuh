@@ -13,7 +13,7 @@
 namespace hvx {
 
 enum { EPI_BF16 = 0, EPI_F32 = 1, EPI_RESID_GATE = 2, EPI_QKV = 3, EPI_LLM_QKV = 4, EPI_SWIGLU = 5 };
-enum { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_SILU = 2, ACT_MISH = 3, ACT_LRELU = 4 /* slope 0.01 */ };
+enum { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_SILU = 2, ACT_MISH = 3, ACT_LRELU = 4 /* slope 0.01 */, ACT_GELU_ERF = 5 /* exact, F.gelu default */ };
 
 struct GemmEpi {
   int mode = EPI_BF16;

@@ -55,6 +55,29 @@ class FlowDims:
 
 
 @dataclass(frozen=True)
+class UnetDims:
+    """CausalConditionalDecoder (cosyvoice/flow/decoder.py:294-400) as the CosyVoice2-generation configs instantiate it:
+    in_channels 320 = x|mu|spks|cond, channels [256] (one down / one up block, no resampling), 4 transformer blocks per
+    stage, 12 mid blocks, 8 heads x 64, GELU feed-forward x4, 50-frame streaming chunks."""
+    mel: int = 80
+    ch: int = 256
+    n_blocks: int = 4
+    n_mid: int = 12
+    heads: int = 8
+    head_dim: int = 64
+    ff_mult: int = 4
+    chunk: int = 50
+
+    @property
+    def in_ch(self) -> int:
+        return 4 * self.mel
+
+    @property
+    def n_res(self) -> int:               # resnet blocks: down + mid + up
+        return self.n_mid + 2
+
+
+@dataclass(frozen=True)
 class LlmDims:
     hidden: int = 896
     layers: int = 24
@@ -78,6 +101,8 @@ class LlmDims:
 HIFT_FULL = HiftDims()
 FLOW_FULL = FlowDims()
 LLM_FULL = LlmDims()
+UNET_FULL = UnetDims()
+UNET_TINY = UnetDims(mel=16, ch=128, n_blocks=2, n_mid=2, heads=2, chunk=6)
 
 HIFT_TINY = HiftDims(base=64, f0_ch=64)
 # classic HiFi-GAN v1 generator (matcha/hifigan/config.py:1-28, models.py:148-193): 22.05 kHz, hop 256 = 8*8*2*2, no ISTFT head

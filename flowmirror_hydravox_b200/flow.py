@@ -4,7 +4,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib as L
-from .weights import pack_flow
+from .weights import pack_flow, pack_unet
 
 
 def rand_noise(mel: int = 80, frames: int = 15000) -> torch.Tensor:
@@ -77,3 +77,53 @@ class NativeFlow:
         L.check(L.lib().hvx_dit_estimator(self.engine.h, *[L.ptr(a) for a in args], T, int(bool(streaming)), L.ptr(out),
                                           L.stream_ptr()))
         return out
+
+
+class NativeUNetEstimator:
+    """Drop-in for `CausalConditionalDecoder` (cosyvoice/flow/decoder.py:294-494) as ConditionalCFM.estimator: the call
+    `estimator(x, mask, mu, t, spks, cond, streaming=...)` of flow_matching.py:128 on (2, mel, T) CFG-stacked tensors.
+    Build the engine with `ud=dims.UNET_FULL`; `Engine(flow_precise=True)` selects the three-term split-fp16 parity mode."""
+
+    def __init__(self, engine: "L.Engine"):
+        if engine.ud is None:
+            raise L.HvxError("engine was created without U-Net dims (Engine(ud=dims.UNET_FULL))")
+        self.engine = engine
+        self.dims = engine.ud
+
+    def load_state_dict(self, sd, strict=True):
+        self.engine.set_tensors(L.STAGE_UNET, pack_unet(sd, self.dims, precise=getattr(self.engine, "flow_precise", False)))
+        self.engine.finalize(L.STAGE_UNET)
+        return self
+
+    def eval(self):
+        return self
+
+    def cuda(self):
+        return self
+
+    def half(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    @torch.no_grad()
+    def forward(self, x, mask, mu, t, spks=None, cond=None, streaming=False, out=None, _dump=None):
+        dev = self.engine.device
+        if x.dim() != 3 or x.shape[0] != 2 or x.shape[1] != self.dims.mel:
+            raise ValueError(f"estimator input must be (2, {self.dims.mel}, T) — the CFG batch of solve_euler; got {tuple(x.shape)}")
+        if mask is not None and not bool((mask != 0).all()):
+            raise ValueError("padded batches are not built: the seam's mask is all-true at inference (flow_matching.py:104-111)")
+        T = int(x.shape[2])
+        args = [a.to(dev, torch.float32).contiguous() for a in (x, mu, t.reshape(-1).expand(2) if t.numel() == 1 else t, spks, cond)]
+        if out is None:            # `out=` (and device-resident fp32 inputs) keeps every pointer stable: the CUDA-graph replay path
+            out = torch.empty(2, self.dims.mel, T, device=dev, dtype=torch.float32)
+        if _dump is None:
+            L.check(L.lib().hvx_unet_estimator(self.engine.h, *[L.ptr(a) for a in args], T, int(bool(streaming)), L.ptr(out),
+                                               L.stream_ptr()))
+        else:
+            L.check(L.lib().hvx_unet_estimator_debug(self.engine.h, *[L.ptr(a) for a in args], T, int(bool(streaming)), L.ptr(out),
+                                                     L.ptr(_dump), int(_dump.shape[0]), L.stream_ptr()))
+        return out
+
+    __call__ = forward

@@ -130,6 +130,58 @@ def hift_sine_table(d: HiftDims, n_frames: int, seed: int = 11) -> torch.Tensor:
     return torch.rand(n_frames * d.frame_samples, d.harmonics, generator=_gen(seed))
 
 
+# --------------------------------------------------------------------------- U-Net estimator (a7')
+def unet_state_dict(d, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Checkpoint of CausalConditionalDecoder (cosyvoice/flow/decoder.py:294-400) at dims.UnetDims: same keys and shapes as
+    the reference module's state_dict (pinned by load_state_dict(strict=True) in oracle/make_golden.py)."""
+    g = _gen(seed + 31)
+    sd: Dict[str, torch.Tensor] = {}
+    C, inner, tdim = d.ch, d.heads * d.head_dim, 4 * d.ch
+
+    def lin(name, out, inp, gain=1.0, bias=True):
+        sd[name + ".weight"] = _randn(g, out, inp, std=gain / inp ** 0.5)
+        if bias:
+            sd[name + ".bias"] = _randn(g, out, std=0.05)
+
+    def conv(name, out, inp, k, gain=1.0):
+        sd[name + ".weight"] = _randn(g, out, inp, k, std=gain / (inp * k) ** 0.5)
+        sd[name + ".bias"] = _randn(g, out, std=0.05)
+
+    def ln(name, n):
+        sd[name + ".weight"] = 1.0 + 0.1 * _randn(g, n)
+        sd[name + ".bias"] = _randn(g, n, std=0.05)
+
+    def resnet(p, cin):
+        lin(p + ".mlp.1", C, tdim)
+        for b, ci in (("block1", cin), ("block2", C)):
+            conv(f"{p}.{b}.block.0", C, ci, 3, gain=1.4)
+            ln(f"{p}.{b}.block.2", C)
+        conv(p + ".res_conv", C, cin, 1)
+
+    def tfm(p):
+        ln(p + ".norm1", C)
+        for n in "qkv":
+            lin(f"{p}.attn1.to_{n}", inner, C, gain=1.5 if n != "v" else 1.0, bias=False)
+        lin(p + ".attn1.to_out.0", C, inner, gain=0.5)
+        ln(p + ".norm3", C)
+        lin(p + ".ff.net.0.proj", d.ff_mult * C, C)
+        lin(p + ".ff.net.2", C, d.ff_mult * C, gain=0.5)
+
+    lin("time_mlp.linear_1", tdim, d.in_ch)
+    lin("time_mlp.linear_2", tdim, tdim)
+    stages = [("down_blocks.0", d.in_ch)] + [(f"mid_blocks.{i}", C) for i in range(d.n_mid)] + [("up_blocks.0", 2 * C)]
+    for p, cin in stages:
+        resnet(p + ".0", cin)
+        for j in range(d.n_blocks):
+            tfm(f"{p}.1.{j}")
+        if not p.startswith("mid"):
+            conv(p + ".2", C, C, 3)
+    conv("final_block.block.0", C, C, 3, gain=1.4)
+    ln("final_block.block.2", C)
+    conv("final_proj", d.mel, C, 1)
+    return sd
+
+
 # --------------------------------------------------------------------------- flow
 def flow_state_dict(d: FlowDims, seed: int = 0) -> Dict[str, torch.Tensor]:
     g = _gen(seed)

@@ -164,6 +164,51 @@ def pack_flow(sd: Dict[str, torch.Tensor], d: D.FlowDims, precise: bool = False)
     return o
 
 
+def pack_unet(sd: Dict[str, torch.Tensor], d: D.UnetDims, precise: bool = False) -> Dict[str, torch.Tensor]:
+    """CausalConditionalDecoder state_dict (cosyvoice/flow/decoder.py:294-400, channels == (C,)) -> engine tensors of the
+    HVX_STAGE_UNET stage.  GEMM operands fp16 ([hi | lo] in parity mode); causal k3 convs become implicit-GEMM B operands with
+    column = tap*Cin + ci; q/k/v fused; every resnet's time-embedding Linear stacked into one fp32 matrix."""
+    import math
+    f = torch.float32
+    cvt = _split16 if precise else (lambda w: w.to(torch.float16).contiguous())
+    o: Dict[str, torch.Tensor] = {}
+    half = d.in_ch // 2
+    o["time.freqs"] = torch.exp(torch.arange(half).float() * -(math.log(10000) / (half - 1))).contiguous()   # SinusoidalPosEmb
+    for i, n in ((1, "linear_1"), (2, "linear_2")):
+        o[f"time.l{i}.w"] = sd[f"time_mlp.{n}.weight"].to(f).contiguous()
+        o[f"time.l{i}.b"] = sd[f"time_mlp.{n}.bias"].to(f).contiguous()
+
+    def conv(key):
+        w = sd[key + ".weight"].to(f)                                    # (Cout, Cin, k)
+        return cvt(w.permute(0, 2, 1).reshape(w.shape[0], -1)), sd[key + ".bias"].to(f).contiguous()
+
+    stages = ["down_blocks.0"] + [f"mid_blocks.{i}" for i in range(d.n_mid)] + ["up_blocks.0"]
+    rw, rb = [], []
+    for i, p in enumerate(stages):
+        r = p + ".0"
+        rw.append(sd[r + ".mlp.1.weight"].to(f)); rb.append(sd[r + ".mlp.1.bias"].to(f))
+        for n, blk in ((1, "block1"), (2, "block2")):
+            o[f"res{i}.c{n}.w"], o[f"res{i}.c{n}.b"] = conv(f"{r}.{blk}.block.0")
+            o[f"res{i}.ln{n}.g"] = sd[f"{r}.{blk}.block.2.weight"].to(f).contiguous()
+            o[f"res{i}.ln{n}.b"] = sd[f"{r}.{blk}.block.2.bias"].to(f).contiguous()
+        o[f"res{i}.rc.w"], o[f"res{i}.rc.b"] = conv(r + ".res_conv")
+        for j in range(d.n_blocks):
+            t, q = f"{p}.1.{j}", f"tfm{i * d.n_blocks + j}"
+            o[q + ".n1.g"], o[q + ".n1.b"] = sd[t + ".norm1.weight"].to(f).contiguous(), sd[t + ".norm1.bias"].to(f).contiguous()
+            o[q + ".n3.g"], o[q + ".n3.b"] = sd[t + ".norm3.weight"].to(f).contiguous(), sd[t + ".norm3.bias"].to(f).contiguous()
+            o[q + ".qkv.w"] = cvt(torch.cat([sd[f"{t}.attn1.to_{n}.weight"].to(f) for n in "qkv"], 0))
+            o[q + ".out.w"], o[q + ".out.b"] = cvt(sd[t + ".attn1.to_out.0.weight"].to(f)), sd[t + ".attn1.to_out.0.bias"].to(f).contiguous()
+            o[q + ".ff1.w"], o[q + ".ff1.b"] = cvt(sd[t + ".ff.net.0.proj.weight"].to(f)), sd[t + ".ff.net.0.proj.bias"].to(f).contiguous()
+            o[q + ".ff2.w"], o[q + ".ff2.b"] = cvt(sd[t + ".ff.net.2.weight"].to(f)), sd[t + ".ff.net.2.bias"].to(f).contiguous()
+    o["rmlp.w"], o["rmlp.b"] = torch.cat(rw, 0).contiguous(), torch.cat(rb, 0).contiguous()
+    o["down.w"], o["down.b"] = conv("down_blocks.0.2")
+    o["up.w"], o["up.b"] = conv("up_blocks.0.2")
+    o["fin.w"], o["fin.b"] = conv("final_block.block.0")
+    o["fin.g"], o["fin.bt"] = sd["final_block.block.2.weight"].to(f).contiguous(), sd["final_block.block.2.bias"].to(f).contiguous()
+    o["proj.w"], o["proj.b"] = conv("final_proj")
+    return o
+
+
 def _rope_pair_perm(n_heads: int, head_dim: int = 64) -> torch.Tensor:
     """Row order that puts the HF half-split RoPE pair (d, d + head_dim/2) on adjacent rows (2i, 2i+1)."""
     half = head_dim // 2

@@ -29,7 +29,7 @@ extern "C" {
 typedef int hvx_status;
 enum { HVX_OK = 0, HVX_ERR_ARG = 1, HVX_ERR_CUDA = 2, HVX_ERR_STATE = 3, HVX_ERR_UNSUPPORTED = 4 };
 
-enum { HVX_STAGE_LLM = 0, HVX_STAGE_FLOW = 1, HVX_STAGE_HIFT = 2 };
+enum { HVX_STAGE_LLM = 0, HVX_STAGE_FLOW = 1, HVX_STAGE_HIFT = 2, HVX_STAGE_UNET = 3 };
 enum { HVX_F32 = 0, HVX_BF16 = 1, HVX_I32 = 2, HVX_F16 = 3 };
 
 typedef struct hvx_engine hvx_engine;
@@ -51,6 +51,9 @@ typedef struct hvx_config {
   int llm_speech_vocab, llm_mtp_heads, llm_mtp_inter, llm_max_ctx, llm_max_seqs;
   float llm_rope_theta, llm_eps;
   int llm_kv_f32;   /* 0: KV cache in bf16 (serving default); 1: fp32 (parity mode, tests) */
+  /* U-Net estimator: cosyvoice/flow/decoder.py:294-400 with channels == (unet_ch,); 0 channels = stage unused.
+   * Precision follows flow_precise. */
+  int unet_mel, unet_ch, unet_n_blocks, unet_n_mid, unet_heads, unet_ff_mult, unet_chunk;
 } hvx_config;
 
 /* Sampler parameters bound per request by server/worker.py:57-65 (ras_sampling keywords,
@@ -118,6 +121,18 @@ hvx_status hvx_flow_inference(hvx_engine* e, const int32_t* tokens_dev, int n_pr
 hvx_status hvx_dit_estimator(hvx_engine* e, const float* x_dev, const float* mu_dev, const float* t_dev,
                              const float* spks_dev, const float* cond_dev, int T, int streaming,
                              float* out_dev, void* stream);
+
+/* U-Net estimator at the same seam — replaces CausalConditionalDecoder.forward (cosyvoice/flow/decoder.py:405-494) behind
+ * ConditionalCFM.forward_estimator (flow_matching.py:126-153): x, mu, cond (2, mel, T), t (2), spks (2, mel) fp32 -> dphi/dt
+ * (2, mel, T) in out_dev.  The seam's mask is all-true at inference and is not an argument.  Weights: stage HVX_STAGE_UNET
+ * (weights.pack_unet). */
+hvx_status hvx_unet_estimator(hvx_engine* e, const float* x_dev, const float* mu_dev, const float* t_dev,
+                              const float* spks_dev, const float* cond_dev, int T, int streaming,
+                              float* out_dev, void* stream);
+/* same, and copies the fp32 residual stream (2T, unet_ch) after every resnet / transformer block into dump_dev (parity tests) */
+hvx_status hvx_unet_estimator_debug(hvx_engine* e, const float* x_dev, const float* mu_dev, const float* t_dev,
+                                    const float* spks_dev, const float* cond_dev, int T, int streaming,
+                                    float* out_dev, float* dump_dev, int n_dump, void* stream);
 
 /* ---- LLM: replaces CosyVoice3LM.inference / inference_wrapper
  * (cosyvoice/llm/llm_multi_head_v3.py:861-960).

@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from flowmirror_hydravox_b200 import dims as D, synth  # noqa: E402
-from oracle import flow_ref, hift_ref, hifigan_ref, llm_ref, refshim  # noqa: E402
+from oracle import flow_ref, hift_ref, hifigan_ref, llm_ref, refshim, unet_ref  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -116,6 +116,39 @@ def golden_hifigan(name, dims, T, seed):
     print(f"[hifigan:{name}] T={T} ref-vs-oracle wav max-abs {e:.2e}; out {tuple(wav.shape)} rms {wav.pow(2).mean().sqrt():.3f} |max| {wav.abs().max():.3f}")
     assert e < 5e-6 and wav.shape[-1] == T * dims.frame_samples
     torch.save(dict(dims=name, seed=seed, T=T, mel=mel, wav=wav, sd_checksum=checksum(sd)), os.path.join(OUT, f"hifigan_{name}.pt"))
+
+
+def golden_unet(name, dims, T, seed):
+    """a7': the U-Net estimator CausalConditionalDecoder at the forward_estimator seam (CFG batch of 2, all-true mask),
+    offline and with the streaming chunk mask."""
+    m = refshim.build_unet(dims)
+    sd = synth.unet_state_dict(dims, seed)
+    m.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(seed + 500)
+    x = torch.randn(2, dims.mel, T, generator=g)
+    mu = torch.randn(2, dims.mel, T, generator=g)
+    cond = torch.randn(2, dims.mel, T, generator=g) * 2.0 - 3.0
+    spks = torch.randn(2, dims.mel, generator=g)
+    mu[1], cond[1], spks[1] = 0, 0, 0                                  # the CFG row (flow_matching.py:100-112)
+    x[1] = x[0]
+    t = torch.tensor([0.3141, 0.3141])
+    mask = torch.ones(2, 1, T)
+    out = {}
+    for key, streaming in (("full", False), ("stream", True)):
+        y = m(x, mask, mu, t, spks, cond, streaming=streaming)
+        y_o = unet_ref.estimator(sd, x, mask, mu, t, spks, cond, dims, streaming=streaming)
+        e = (y - y_o).abs().max().item()
+        print(f"[unet:{name}] T={T} {key}: ref-vs-oracle max-abs {e:.2e}; |out| mean {y.abs().mean():.3f} max {y.abs().max():.2f}")
+        assert e < 2e-4 * max(1.0, y.abs().max().item())
+        out["y_" + key] = y
+    # ragged batch: the second row is padded (mask 0 from frame T-5 on) -- the reference's padding-mask path
+    mask2 = mask.clone(); mask2[1, :, T - 5:] = 0
+    y = m(x, mask2, mu, t, spks, cond, streaming=False)
+    y_o = unet_ref.estimator(sd, x, mask2, mu, t, spks, cond, dims)
+    assert (y - y_o).abs().max().item() < 2e-4 * max(1.0, y.abs().max().item())
+    print(f"[unet:{name}] stream-vs-full max-abs {(out['y_full'] - out['y_stream']).abs().max():.2e}")
+    torch.save(dict(dims=name, seed=seed, T=T, x=x, mu=mu, cond=cond, spks=spks, t=t, sd_checksum=checksum(sd), **out),
+               os.path.join(OUT, f"unet_{name}.pt"))
 
 
 def golden_flow(name, dims, N, P, n_steps, seed):
@@ -220,6 +253,11 @@ def golden_llm(name, dims, n_text, n_ptext, P, cases, seed):
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if sys.argv[1:] == ["unet"]:
+        with torch.no_grad():
+            golden_unet("tiny", D.UNET_TINY, 37, 0)
+            golden_unet("full", D.UNET_FULL, 130, 0)
+        return
     if sys.argv[1:] == ["hifigan"]:
         with torch.no_grad():
             golden_hifigan("tiny", D.HIFIGAN_TINY, 37, 0)
@@ -237,6 +275,8 @@ def main():
         golden_hift_t("full", D.HIFT_FULL, 20, 0)
         golden_hifigan("tiny", D.HIFIGAN_TINY, 37, 0)
         golden_hifigan("v1", D.HIFIGAN_V1, 24, 0)
+        golden_unet("tiny", D.UNET_TINY, 37, 0)
+        golden_unet("full", D.UNET_FULL, 130, 0)
         golden_flow("tiny", D.FLOW_TINY, 21, 10, 10, 0)
         golden_flow("full", D.FLOW_FULL, 24, 8, 4, 0)
         sp1 = dict(top_p=0.9, top_k=10, win_size=24, tau_r=0.2)     # server tts defaults (router.py:22-44)

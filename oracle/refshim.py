@@ -139,6 +139,54 @@ def apply_rotary_pos_emb(t, freqs, scale=1.0):
 _installed = False
 
 
+# ---------------------------------------------------------------------------
+# diffusers 0.29 stand-ins for the U-Net estimator's transformer blocks (matcha/models/components/transformer.py:5-14):
+# published semantics of `Attention` with AttnProcessor2_0 (self-attention, no norms), `GELU`, `LoRACompatibleLinear`.
+# ---------------------------------------------------------------------------
+class DiffusersGELU(nn.Module):
+    def __init__(self, dim_in, dim_out, approximate="none", bias=True):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out, bias=bias)
+        self.approximate = approximate
+
+    def forward(self, hidden_states):
+        return torch.nn.functional.gelu(self.proj(hidden_states), approximate=self.approximate)
+
+
+class DiffusersAttention(nn.Module):
+    def __init__(self, query_dim, cross_attention_dim=None, heads=8, dim_head=64, dropout=0.0, bias=False,
+                 upcast_attention=False, out_bias=True, **_):
+        super().__init__()
+        inner = dim_head * heads
+        self.heads = heads
+        kv_dim = cross_attention_dim if cross_attention_dim is not None else query_dim
+        self.to_q = nn.Linear(query_dim, inner, bias=bias)
+        self.to_k = nn.Linear(kv_dim, inner, bias=bias)
+        self.to_v = nn.Linear(kv_dim, inner, bias=bias)
+        self.to_out = nn.ModuleList([nn.Linear(inner, query_dim, bias=out_bias), nn.Dropout(dropout)])
+
+    def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **_):
+        B, T, _c = hidden_states.shape
+        ctx = hidden_states if encoder_hidden_states is None else encoder_hidden_states
+        q, k, v = self.to_q(hidden_states), self.to_k(ctx), self.to_v(ctx)
+        hd = q.shape[-1] // self.heads
+        q, k, v = (z.view(B, -1, self.heads, hd).transpose(1, 2) for z in (q, k, v))
+        if attention_mask is not None:                     # prepare_attention_mask: (B, T, S) -> per head
+            attention_mask = attention_mask.repeat_interleave(self.heads, dim=0).view(B, self.heads, -1, attention_mask.shape[-1])
+        o = torch.nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=attention_mask, dropout_p=0.0, is_causal=False)
+        o = o.transpose(1, 2).reshape(B, -1, self.heads * hd).to(q.dtype)
+        return self.to_out[1](self.to_out[0](o))
+
+
+def _install_diffusers():
+    att = importlib.import_module("diffusers.models.attention")
+    att.GELU = DiffusersGELU
+    importlib.import_module("diffusers.models.attention_processor").Attention = DiffusersAttention
+    importlib.import_module("diffusers.models.lora").LoRACompatibleLinear = nn.Linear
+    importlib.import_module("diffusers.utils.torch_utils").maybe_allow_in_graph = lambda cls: cls
+    importlib.import_module("diffusers.models.activations").get_activation = lambda name: {"silu": nn.SiLU, "swish": nn.SiLU, "mish": nn.Mish, "gelu": nn.GELU}[name]()
+
+
 def install():
     """Make ``cosyvoice.*`` / ``matcha.*`` importable from the reference tree."""
     global _installed
@@ -162,6 +210,8 @@ def install():
     xt = importlib.import_module("x_transformers.x_transformers")
     xt.RotaryEmbedding = RotaryEmbedding
     xt.apply_rotary_pos_emb = apply_rotary_pos_emb
+    if "diffusers" in finder_roots:
+        _install_diffusers()
     _installed = True
 
 
@@ -228,6 +278,16 @@ def build_hifigan(cfg):
                   upsample_initial_channel=cfg.base, resblock_kernel_sizes=list(cfg.rb_k),
                   resblock_dilation_sizes=[list(cfg.rb_d)] * len(cfg.rb_k))
     return Generator(h).eval()
+
+
+def build_unet(cfg):
+    """The reference's CausalConditionalDecoder (cosyvoice/flow/decoder.py:294-494) at cfg dims (oracle.dims.UnetDims), eval."""
+    install()
+    from cosyvoice.flow.decoder import CausalConditionalDecoder
+    m = CausalConditionalDecoder(in_channels=cfg.in_ch, out_channels=cfg.mel, channels=[cfg.ch], dropout=0.0,
+                                 attention_head_dim=cfg.head_dim, n_blocks=cfg.n_blocks, num_mid_blocks=cfg.n_mid,
+                                 num_heads=cfg.heads, act_fn="gelu", static_chunk_size=cfg.chunk, num_decoding_left_chunks=-1)
+    return m.eval()
 
 
 def build_flow(cfg, seed=0, dtype=torch.float32):

@@ -84,6 +84,29 @@ def test_hift_source_noise_replays_reference_rng(golden):
     assert n.shape == g["noise"].shape and torch.equal(n, g["noise"])
 
 
+@pytest.mark.parametrize("name,dims", [("tiny", D.UNET_TINY), ("full", D.UNET_FULL)])
+def test_unet_oracle_matches_reference(golden, name, dims):
+    """a7': the U-Net estimator CausalConditionalDecoder (cosyvoice/flow/decoder.py:405-494), fixtures from the reference module."""
+    from oracle import unet_ref
+    g = golden(f"unet_{name}")
+    sd = synth.unet_state_dict(dims, g["seed"])
+    assert abs(_checksum(sd) - g["sd_checksum"]) < 1e-6 * g["sd_checksum"]
+    mask = torch.ones(2, 1, g["T"])
+    for key, streaming in (("full", False), ("stream", True)):
+        y = unet_ref.estimator(sd, g["x"], mask, g["mu"], g["t"], g["spks"], g["cond"], dims, streaming=streaming)
+        assert y.shape == g["y_" + key].shape == (2, dims.mel, g["T"])
+        assert (y - g["y_" + key]).abs().max() < 5e-5
+    # packing keeps every parameter: conv B operands are the same linear maps
+    from flowmirror_hydravox_b200.weights import pack_unet
+    pk = pack_unet(sd, dims)
+    w = sd["mid_blocks.0.0.block1.block.0.weight"]
+    assert torch.equal(pk["res1.c1.w"].float().reshape(dims.ch, 3, dims.ch), w.permute(0, 2, 1).half().float())
+    pk2 = pack_unet(sd, dims, precise=True)
+    hi, lo = pk2["tfm0.qkv.w"].float().chunk(2, dim=1)
+    full = torch.cat([sd[f"down_blocks.0.1.0.attn1.to_{n}.weight"] for n in "qkv"], 0)
+    assert (hi + lo - full).abs().max() < 1e-6
+
+
 @pytest.mark.parametrize("name,dims", [("tiny", D.FLOW_TINY), ("full", D.FLOW_FULL)])
 def test_flow_oracle_matches_reference(golden, name, dims):
     g = golden(f"flow_{name}")

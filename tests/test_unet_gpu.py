@@ -1,0 +1,131 @@
+"""GPU parity of the U-Net estimator (SURVEY 8 a7': CausalConditionalDecoder, cosyvoice/flow/decoder.py:405-494) through
+hvx_unet_estimator against fixtures minted from the unmodified reference module (oracle/make_golden.py)."""
+import pytest
+import torch
+
+from flowmirror_hydravox_b200 import dims as D, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def unets():
+    from flowmirror_hydravox_b200 import _lib as L
+    from flowmirror_hydravox_b200.flow import NativeUNetEstimator
+    out = {}
+    for name, ud, precise in (("tiny", D.UNET_TINY, False), ("full", D.UNET_FULL, False), ("tiny_p", D.UNET_TINY, True), ("full_p", D.UNET_FULL, True)):
+        e = L.Engine(ud=ud, flow_precise=precise)
+        m = NativeUNetEstimator(e)
+        m.load_state_dict(synth.unet_state_dict(ud, 0))
+        out[name] = (e, m, ud)
+    yield out
+    for e, _, _ in out.values():
+        e.close()
+
+
+def _localise(m, ud, g, streaming):
+    """residual stream after every resnet / transformer block vs the oracle — printed when a parity assert is about to fail"""
+    from oracle import unet_ref
+    import torch.nn.functional as F
+    sd = {k: v.float() for k, v in synth.unet_state_dict(ud, 0).items()}
+    T = g["T"]
+    mask = torch.ones(2, 1, T)
+    temb = unet_ref.time_embedding(sd, g["t"], ud.in_ch)
+    bias = unet_ref.attn_bias(mask, streaming, ud.chunk)
+    h = torch.cat([g["x"], g["mu"], g["spks"].unsqueeze(-1).expand(-1, -1, T), g["cond"]], 1)
+    ref = []
+    stages = ["down_blocks.0"] + [f"mid_blocks.{i}" for i in range(ud.n_mid)] + ["up_blocks.0"]
+    skip = None
+    for p in stages:
+        if p.startswith("up"):
+            h = torch.cat([h, skip], 1)
+        h = unet_ref._resnet(sd, p + ".0", h, mask, temb)
+        ref.append(h.transpose(1, 2).reshape(2 * T, -1))
+        h = h.transpose(1, 2)
+        for j in range(ud.n_blocks):
+            h = unet_ref._tfm(sd, f"{p}.1.{j}", h, bias, ud.heads)
+            ref.append(h.reshape(2 * T, -1))
+        h = h.transpose(1, 2)
+        if not p.startswith("mid"):
+            if p.startswith("down"):
+                skip = h
+            h = unet_ref._cconv(h, sd[p + ".2.weight"], sd[p + ".2.bias"])
+    dump = torch.zeros(len(ref), 2 * T, ud.ch, device="cuda")
+    m(g["x"], None, g["mu"], g["t"], g["spks"], g["cond"], streaming=streaming, _dump=dump)
+    for i, r in enumerate(ref):
+        err = (dump[i].cpu() - r).abs().max().item()
+        print(f"  slab {i:3d} ({'resnet' if i % (1 + ud.n_blocks) == 0 else 'tfm'}): max-abs {err:.3e}  |ref| max {r.abs().max():.2f}")
+
+
+@pytest.mark.parametrize("name", ["tiny", "full", "tiny_p", "full_p"])
+@pytest.mark.parametrize("mode", ["full", "stream"])
+def test_unet_matches_reference_fixture(unets, golden, name, mode):
+    e, m, ud = unets[name]
+    g = golden("unet_" + name.split("_")[0])
+    streaming = mode == "stream"
+    out = m(g["x"], torch.ones(2, 1, g["T"]), g["mu"], g["t"], g["spks"], g["cond"], streaming=streaming).cpu()
+    ref = g["y_" + mode]
+    err = (out - ref).abs()
+    precise = name.endswith("_p")
+    print(f"[unet {name} {mode}] max-abs {err.max():.3e} mean-abs {err.mean():.3e} mean|out| {ref.abs().mean():.3f}")
+    # parity mode: north_star's 1e-3 on mel-valued outputs; serving mode (fp16 operands): export_onnx.py:111 rtol 1e-2 scale
+    tol = 1e-3 if precise else 2e-2
+    if not (err.max().item() < tol):
+        _localise(m, ud, g, streaming)
+    assert err.max().item() < tol, (err.max().item(), err.mean().item())
+    assert err.mean().item() < (1e-4 if precise else 3e-3)
+
+
+@pytest.mark.parametrize("T", [1, 5, 64, 129, 300])
+def test_unet_lengths_vs_oracle(unets, T):
+    """any T of the TensorRT profile range (cli/model.py:93-98 lists 4..3000), tile-edge cases included; parity mode"""
+    from oracle import unet_ref
+    e, m, ud = unets["tiny_p"]
+    sd = synth.unet_state_dict(ud, 0)
+    g = torch.Generator().manual_seed(100 + T)
+    x, mu, cond = (torch.randn(2, ud.mel, T, generator=g) for _ in range(3))
+    spks, t = torch.randn(2, ud.mel, generator=g), torch.tensor([0.77, 0.77])
+    for streaming in (False, True):
+        ref = unet_ref.estimator(sd, x, torch.ones(2, 1, T), mu, t, spks, cond, ud, streaming=streaming)
+        out = m(x, None, mu, t, spks, cond, streaming=streaming).cpu()
+        assert out.shape == ref.shape
+        assert (out - ref).abs().max().item() < 1e-3, (T, streaming, (out - ref).abs().max().item())
+
+
+def test_unet_graph_replay_rereads_inputs(unets):
+    """solve_euler calls the seam with the same buffers every step (flow_matching.py:93-123): the third call onwards replays a
+    captured CUDA graph and must see the new contents of x and t; a different T falls back to an eager run and re-captures"""
+    from oracle import unet_ref
+    e, m, ud = unets["tiny_p"]
+    sd = synth.unet_state_dict(ud, 0)
+    g = torch.Generator().manual_seed(7)
+    for T in (40, 23, 40):
+        x, mu, cond = (torch.randn(2, ud.mel, T, generator=g).cuda() for _ in range(3))
+        spks, t = torch.randn(2, ud.mel, generator=g).cuda(), torch.tensor([0.1, 0.1]).cuda()
+        out = torch.empty(2, ud.mel, T, device="cuda")
+        n0 = e.launches()
+        for step in range(4):
+            x.copy_(torch.randn(2, ud.mel, T, generator=g))
+            t.fill_(0.1 + 0.2 * step)
+            y = m(x, None, mu, t, spks, cond, out=out)
+            assert y.data_ptr() == out.data_ptr()
+            ref = unet_ref.estimator(sd, x.cpu(), torch.ones(2, 1, T), mu.cpu(), t.cpu(), spks.cpu(), cond.cpu(), ud)
+            assert (y.cpu() - ref).abs().max().item() < 1e-3, (T, step, (y.cpu() - ref).abs().max().item())
+        assert (e.launches() - n0) % 4 == 0 and e.launches() > n0          # replayed steps count the kernels inside the graph
+
+
+def test_unet_rejects_bad_input(unets):
+    from flowmirror_hydravox_b200 import _lib as L
+    e, m, ud = unets["tiny"]
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, ud.mel, 8), None, torch.zeros(1, ud.mel, 8), torch.zeros(1), torch.zeros(1, ud.mel), torch.zeros(1, ud.mel, 8))
+    mask = torch.ones(2, 1, 8); mask[1, :, 5:] = 0
+    with pytest.raises(ValueError):
+        m(torch.zeros(2, ud.mel, 8), mask, torch.zeros(2, ud.mel, 8), torch.zeros(2), torch.zeros(2, ud.mel), torch.zeros(2, ud.mel, 8))
+    e2 = L.Engine()
+    try:
+        from flowmirror_hydravox_b200.flow import NativeUNetEstimator
+        with pytest.raises(L.HvxError):
+            NativeUNetEstimator(e2)
+    finally:
+        e2.close()
