@@ -1437,7 +1437,8 @@ static FusedPlan fused_plan(hvx_engine* e, int n_seq, int head_k, bool force = f
   FusedPlan f;
   const hvx_config& c = e->cfg;
   // Opt-in (HVX_FUSED_DECODE=1): numerically equivalent to the kernel-per-op step (tests/test_llm_gpu.py), but at round 1 it
-  // is slower on B200 (938 vs 780 us per step at ctx 800: ~1.9 us per grid barrier x 6 per layer, see profiles/README.md)
+  // is slower on B200 (1739 vs 783 us per step at ctx 800, scripts/bench_llm_kernels.py: 120 grid barriers and the per-phase
+  // activation re-staging cost more than the PDL-chained launches they replace)
   const char* env = getenv("HVX_FUSED_DECODE");
   if (!force && !(env && atoi(env) != 0)) return f;
   if (n_seq != 1 || head_k > 4) return f;
