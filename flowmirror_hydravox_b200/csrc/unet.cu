@@ -164,7 +164,7 @@ struct UnetState {
   std::vector<UnetTfm> tfm;
   const __half *down_w, *up_w, *fin_w, *proj_w;
   const float *down_b, *up_b, *fin_b, *fin_g, *fin_bt, *proj_b;
-  DevBuf ws;
+  DevBuf ws, ws_solve;
   int precise = 0, vt_T = -1;
   // one estimator evaluation = a fixed sequence of ~490 small launches: replayed as a CUDA graph on an engine-owned stream
   // once the same (pointers, T, mask mode) has been seen twice — the Euler loop of solve_euler calls the seam with stable
@@ -406,11 +406,10 @@ static hvx_status unet_run(hvx_engine* e, const float* x, const float* mu, const
   return HVX_OK;
 }
 
-extern "C" hvx_status hvx_unet_estimator(hvx_engine* e, const float* x, const float* mu, const float* t, const float* spks,
-                                         const float* cond, int T, int streaming, float* out, void* stream) {
+static hvx_status unet_estimate(hvx_engine* e, const float* x, const float* mu, const float* t, const float* spks,
+                                const float* cond, int T, int streaming, float* out, cudaStream_t user) {
   HVX_CHECK(e && e->unet, HVX_ERR_STATE, "unet stage not finalized");
   UnetState* u = e->unet;
-  cudaStream_t user = (cudaStream_t)stream;
   if (getenv("HVX_UNET_NO_GRAPH")) return unet_run(e, x, mu, t, spks, cond, T, streaming, out, nullptr, 0, user);
   UnetState::Key key{x, mu, t, spks, cond, out, u->ws.p, T, streaming};
   const bool replay = u->gexec && !memcmp(&key, &u->gkey, sizeof(key));
@@ -447,6 +446,87 @@ extern "C" hvx_status hvx_unet_estimator(hvx_engine* e, const float* x, const fl
   e->launches += u->glaunches;
   HVX_CUDA(cudaEventRecord(u->ev_out, u->own));
   HVX_CUDA(cudaStreamWaitEvent(user, u->ev_out, 0));
+  return HVX_OK;
+}
+
+extern "C" hvx_status hvx_unet_estimator(hvx_engine* e, const float* x, const float* mu, const float* t, const float* spks,
+                                         const float* cond, int T, int streaming, float* out, void* stream) {
+  return unet_estimate(e, x, mu, t, spks, cond, T, streaming, out, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ CFM Euler solve over the U-Net estimator
+// CFG staging of solve_euler (flow_matching.py:93-112): x_in = [x; x], mu_in = [mu; 0], spks_in = [spks; 0], cond_in = [cond; 0],
+// with z = rand_noise[:, :, :T] * temperature (:223)
+__global__ void cfm_stage_kernel(const float* __restrict__ noise, int noise_ld, float temperature, const float* __restrict__ mu,
+                                 const float* __restrict__ spks, const float* __restrict__ cond, float* __restrict__ x_in,
+                                 float* __restrict__ mu_in, float* __restrict__ spks_in, float* __restrict__ cond_in, int C, int T) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = C * T;
+  if (i >= n) return;
+  const int c = i / T, t = i - c * T;
+  const float z = noise[(size_t)c * noise_ld + t] * temperature;
+  x_in[i] = z; x_in[n + i] = z;
+  mu_in[i] = mu[i]; mu_in[n + i] = 0.f;
+  cond_in[i] = cond ? cond[i] : 0.f; cond_in[n + i] = 0.f;
+  if (i < C) { spks_in[i] = spks ? spks[i] : 0.f; spks_in[C + i] = 0.f; }
+}
+
+__global__ void cfm_set_t_kernel(float* __restrict__ t_in, const float* __restrict__ tv, int s) {
+  if (threadIdx.x < 2) t_in[threadIdx.x] = tv[s];
+}
+
+// dphi = (1 + cfg) * v[0] - cfg * v[1];  x += dt * dphi   (flow_matching.py:113-118), both CFG rows of x_in updated
+__global__ void cfm_euler_kernel(const float* __restrict__ v, float* __restrict__ x_in, int n, float dt, float cfg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float d = __fsub_rn(__fmul_rn(1.0f + cfg, v[i]), __fmul_rn(cfg, v[n + i]));
+  const float x = __fadd_rn(x_in[i], __fmul_rn(dt, d));
+  x_in[i] = x; x_in[n + i] = x;
+}
+
+extern "C" hvx_status hvx_cfm_solve_unet(hvx_engine* e, const float* mu, const float* spks, const float* cond, const float* noise,
+                                         int noise_ld, int T, int n_timesteps, float temperature, int streaming, float* mel_out,
+                                         void* stream) {
+  HVX_CHECK(e && e->unet, HVX_ERR_STATE, "unet stage not finalized");
+  HVX_CHECK(mu && noise && mel_out && T >= 1 && T <= noise_ld, HVX_ERR_ARG, "cfm_solve_unet: bad argument (T=%d, noise table %d frames)", T, noise_ld);
+  HVX_CHECK(n_timesteps >= 1 && n_timesteps <= 64, HVX_ERR_ARG, "cfm_solve_unet: n_timesteps=%d out of range [1,64]", n_timesteps);
+  UnetState* u = e->unet;
+  const hvx_config& c = e->cfg;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = c.unet_mel, n = C * T;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_x = take((size_t)2 * n * 4), o_mu = take((size_t)2 * n * 4), o_cond = take((size_t)2 * n * 4), o_v = take((size_t)2 * n * 4);
+  const size_t o_spk = take((size_t)2 * C * 4), o_t = take(8), o_tv = take(64 * 4);
+  uint8_t* w = (uint8_t*)u->ws_solve.get(off);
+  HVX_CHECK(w, HVX_ERR_CUDA, "cfm_solve_unet: buffer allocation of %zu bytes failed", off);
+  float *x_in = (float*)(w + o_x), *mu_in = (float*)(w + o_mu), *cond_in = (float*)(w + o_cond), *v = (float*)(w + o_v);
+  float *spks_in = (float*)(w + o_spk), *t_in = (float*)(w + o_t), *tv_dev = (float*)(w + o_tv);
+  cfm_stage_kernel<<<cdiv(n, 256), 256, 0, st>>>(noise, noise_ld, temperature, mu, spks, cond, x_in, mu_in, spks_in, cond_in, C, T);
+  HVX_LAUNCH_CHECK(e);
+  // cosine t-schedule carried in fp32 exactly like solve_euler (flow_matching.py:225-227,93-122; same arithmetic as flow.cu)
+  float ts[65], tv[64], dtv[64];
+  for (int i = 0; i <= n_timesteps; i++) {
+    const float step = 1.0f / (float)n_timesteps;
+    const float lin = (i < (n_timesteps + 1) / 2) ? (float)i * step : 1.0f - (float)(n_timesteps - i) * step;   // torch.linspace
+    ts[i] = 1.0f - cosf((lin * 0.5f) * 3.14159265358979323846f);
+  }
+  { float t = ts[0], dt = ts[1] - ts[0];
+    for (int s = 1; s <= n_timesteps; s++) {
+      tv[s - 1] = t; dtv[s - 1] = dt;
+      t = t + dt;
+      if (s < n_timesteps) dt = ts[s + 1] - t;
+    } }
+  HVX_CUDA(cudaMemcpyAsync(tv_dev, tv, sizeof(float) * n_timesteps, cudaMemcpyHostToDevice, st));
+  for (int s = 0; s < n_timesteps; s++) {
+    cfm_set_t_kernel<<<1, 32, 0, st>>>(t_in, tv_dev, s);
+    HVX_LAUNCH_CHECK(e);
+    const hvx_status rc = unet_estimate(e, x_in, mu_in, t_in, spks_in, cond_in, T, streaming, v, st);
+    if (rc) return rc;
+    cfm_euler_kernel<<<cdiv(n, 256), 256, 0, st>>>(v, x_in, n, dtv[s], c.flow_cfg_rate);
+    HVX_LAUNCH_CHECK(e);
+  }
+  HVX_CUDA(cudaMemcpyAsync(mel_out, x_in, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
   return HVX_OK;
 }
 

@@ -103,6 +103,7 @@ FLOW_FULL = FlowDims()
 LLM_FULL = LlmDims()
 UNET_FULL = UnetDims()
 UNET_TINY = UnetDims(mel=16, ch=128, n_blocks=2, n_mid=2, heads=2, chunk=6)
+UNET_SMALL = UnetDims(ch=128, n_blocks=1, n_mid=1, heads=2, chunk=10)     # mel stays 80: solve_euler hard-codes it (flow_matching.py:94-99)
 
 HIFT_TINY = HiftDims(base=64, f0_ch=64)
 # classic HiFi-GAN v1 generator (matcha/hifigan/config.py:1-28, models.py:148-193): 22.05 kHz, hop 256 = 8*8*2*2, no ISTFT head

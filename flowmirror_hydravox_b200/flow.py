@@ -127,3 +127,48 @@ class NativeUNetEstimator:
         return out
 
     __call__ = forward
+
+
+class NativeUNetCFM:
+    """Drop-in for `CausalConditionalCFM` whose estimator is the U-Net (cosyvoice/flow/flow_matching.py:197-228 + solve_euler
+    :71-124): `forward(mu, mask, n_timesteps, temperature, spks, cond, streaming) -> (mel fp32 (1, mel, T), None)` in one
+    hvx_cfm_solve_unet call — noise slice, cosine schedule, CFG staging, estimator, Euler update all on the device."""
+
+    def __init__(self, engine: "L.Engine", noise: torch.Tensor | None = None):
+        import ctypes as C
+        self._cf = C.c_float
+        self.engine = engine
+        self.estimator = NativeUNetEstimator(engine)
+        self.dims = self.estimator.dims
+        n = rand_noise(self.dims.mel, 50 * 300) if noise is None else noise
+        self.rand_noise = n.reshape(self.dims.mel, -1).to(engine.device, torch.float32).contiguous()
+
+    def load_state_dict(self, sd, strict=True):
+        """accepts the CFM module's state_dict (keys `estimator.*`) or the estimator's own"""
+        est = {k[len("estimator."):]: v for k, v in sd.items() if k.startswith("estimator.")}
+        self.estimator.load_state_dict(est or sd)
+        return self
+
+    def eval(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    @torch.no_grad()
+    def forward(self, mu, mask=None, n_timesteps=10, temperature=1.0, spks=None, cond=None, streaming=False):
+        d, dev = self.dims, self.engine.device
+        if mu.dim() != 3 or mu.shape[0] != 1 or mu.shape[1] != d.mel:
+            raise ValueError(f"mu must be (1, {d.mel}, T); got {tuple(mu.shape)}")
+        if mask is not None and not bool((mask != 0).all()):
+            raise ValueError("padded batches are not built (the reference solves one utterance at a time)")
+        T = int(mu.shape[2])
+        f = lambda a: None if a is None else a.to(dev, torch.float32).contiguous()
+        mu_d, spks_d, cond_d = f(mu), f(spks), f(cond)
+        out = torch.empty(1, d.mel, T, device=dev, dtype=torch.float32)
+        L.check(L.lib().hvx_cfm_solve_unet(self.engine.h, L.ptr(mu_d), L.ptr(spks_d), L.ptr(cond_d), L.ptr(self.rand_noise),
+                                           int(self.rand_noise.shape[1]), T, int(n_timesteps), self._cf(float(temperature)),
+                                           int(bool(streaming)), L.ptr(out), L.stream_ptr()))
+        return out, None
+
+    __call__ = forward

@@ -134,6 +134,15 @@ hvx_status hvx_unet_estimator_debug(hvx_engine* e, const float* x_dev, const flo
                                     const float* spks_dev, const float* cond_dev, int T, int streaming,
                                     float* out_dev, float* dump_dev, int n_dump, void* stream);
 
+/* CFM Euler solve over the U-Net estimator — replaces CausalConditionalCFM.forward + ConditionalCFM.solve_euler
+ * (cosyvoice/flow/flow_matching.py:203-228,71-124) when the estimator is the U-Net: z = noise[:, :T] * temperature, cosine
+ * t-schedule, per step CFG staging (row 1 has mu/spks/cond zeroed), estimator, v = (1+cfg)*v0 - cfg*v1, x += dt*v.
+ * mu_dev, cond_dev (mel, T), spks_dev (mel) fp32 (cond/spks may be NULL = zeros); noise_dev (mel, noise_ld) = rand_noise;
+ * mel_out_dev (mel, T) fp32.  cfg rate = hvx_config.flow_cfg_rate. */
+hvx_status hvx_cfm_solve_unet(hvx_engine* e, const float* mu_dev, const float* spks_dev, const float* cond_dev,
+                              const float* noise_dev, int noise_ld, int T, int n_timesteps, float temperature,
+                              int streaming, float* mel_out_dev, void* stream);
+
 /* ---- LLM: replaces CosyVoice3LM.inference / inference_wrapper
  * (cosyvoice/llm/llm_multi_head_v3.py:861-960).
  * hvx_llm_begin resets sequence slot `seq` and stores its prompt rows

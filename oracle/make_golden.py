@@ -151,6 +151,29 @@ def golden_unet(name, dims, T, seed):
                os.path.join(OUT, f"unet_{name}.pt"))
 
 
+def golden_unet_cfm(name, dims, T, n_steps, seed):
+    """the whole Euler solve over the U-Net estimator: CausalConditionalCFM.forward (flow_matching.py:203-228)"""
+    cfm = refshim.build_unet_cfm(dims)
+    sd = synth.unet_state_dict(dims, seed)
+    cfm.estimator.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(seed + 600)
+    mu = torch.randn(1, dims.mel, T, generator=g)
+    cond = torch.zeros(1, dims.mel, T)
+    cond[:, :, : T // 3] = torch.rand(1, dims.mel, T // 3, generator=g) * 6.0 - 6.0      # prompt mel in the head, zeros after (flow.py:415-419)
+    spks = torch.randn(1, dims.mel, generator=g)
+    out = {}
+    for key, streaming in (("full", False), ("stream", True)):
+        y, _ = cfm(mu, torch.ones(1, 1, T), n_steps, spks=spks, cond=cond, streaming=streaming)
+        y_o = unet_ref.cfm_solve(sd, mu, spks, cond, cfm.rand_noise, n_steps, dims, streaming=streaming)
+        e = (y - y_o).abs().max().item()
+        print(f"[unet_cfm:{name}] T={T} steps={n_steps} {key}: ref-vs-oracle max-abs {e:.2e}; |mel| mean {y.abs().mean():.3f} max {y.abs().max():.2f}")
+        assert e < 5e-4 * max(1.0, y.abs().max().item())
+        out["mel_" + key] = y.clone()
+    assert torch.equal(cfm.rand_noise, __import__("flowmirror_hydravox_b200.flow", fromlist=["rand_noise"]).rand_noise(dims.mel, 15000))
+    torch.save(dict(dims=name, seed=seed, T=T, n_steps=n_steps, mu=mu, cond=cond, spks=spks, sd_checksum=checksum(sd), **out),
+               os.path.join(OUT, f"unet_cfm_{name}.pt"))
+
+
 def golden_flow(name, dims, N, P, n_steps, seed):
     refshim.install()
     import cosyvoice.flow.flow as flowmod
@@ -257,6 +280,8 @@ def main():
         with torch.no_grad():
             golden_unet("tiny", D.UNET_TINY, 37, 0)
             golden_unet("full", D.UNET_FULL, 130, 0)
+            golden_unet_cfm("small", D.UNET_SMALL, 57, 10, 0)
+            golden_unet_cfm("full", D.UNET_FULL, 96, 5, 0)
         return
     if sys.argv[1:] == ["hifigan"]:
         with torch.no_grad():
@@ -277,6 +302,8 @@ def main():
         golden_hifigan("v1", D.HIFIGAN_V1, 24, 0)
         golden_unet("tiny", D.UNET_TINY, 37, 0)
         golden_unet("full", D.UNET_FULL, 130, 0)
+        golden_unet_cfm("small", D.UNET_SMALL, 57, 10, 0)
+        golden_unet_cfm("full", D.UNET_FULL, 96, 5, 0)
         golden_flow("tiny", D.FLOW_TINY, 21, 10, 10, 0)
         golden_flow("full", D.FLOW_FULL, 24, 8, 4, 0)
         sp1 = dict(top_p=0.9, top_k=10, win_size=24, tau_r=0.2)     # server tts defaults (router.py:22-44)

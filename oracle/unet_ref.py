@@ -98,3 +98,24 @@ def estimator(sd: Dict[str, torch.Tensor], x, mask, mu, t, spks, cond, dims, str
     h = _cconv(h * mask, sd["up_blocks.0.2.weight"], sd["up_blocks.0.2.bias"])
     h = _block(sd, "final_block", h, mask)
     return F.conv1d(h * mask, sd["final_proj.weight"], sd["final_proj.bias"]) * mask
+
+
+def cfm_solve(sd, mu, spks, cond, noise, n_timesteps, dims, cfg_rate=0.7, temperature=1.0, streaming=False):
+    """CausalConditionalCFM.forward + solve_euler (cosyvoice/flow/flow_matching.py:203-228,71-124) over `estimator`:
+    mu, cond (1, mel, T), spks (1, mel), noise = rand_noise (1, mel, >=T) -> (1, mel, T)"""
+    T = mu.shape[2]
+    x = noise[:, :, :T].float() * temperature
+    t_span = torch.linspace(0, 1, n_timesteps + 1)
+    t_span = 1 - torch.cos(t_span * 0.5 * torch.pi)
+    t, dt = t_span[0].unsqueeze(0), t_span[1] - t_span[0]
+    mask = torch.ones(2, 1, T)
+    zeros = torch.zeros_like(mu)
+    for step in range(1, n_timesteps + 1):
+        d = estimator(sd, torch.cat([x, x]), mask, torch.cat([mu, zeros]), torch.cat([t, t]), torch.cat([spks, torch.zeros_like(spks)]),
+                      torch.cat([cond, zeros]), dims, streaming=streaming)
+        d = (1.0 + cfg_rate) * d[:1] - cfg_rate * d[1:]
+        x = x + dt * d
+        t = t + dt
+        if step < n_timesteps:
+            dt = t_span[step + 1] - t
+    return x

@@ -30,3 +30,21 @@ for precise in (False, True):
     ms = a.elapsed_time(b) / 10
     print(f"precise={int(precise)}: {ms:.3f} ms per NFE, {flops / ms / 1e9:.1f} TFLOP/s, {(e.launches() - n0) // 10} launches per NFE")
     e.close()
+
+# whole Euler solve (hvx_cfm_solve_unet): CausalConditionalCFM.forward at n_timesteps = 10 (the reference's default) and 25
+from flowmirror_hydravox_b200.flow import NativeUNetCFM
+e = L.Engine(ud=ud)
+cfm = NativeUNetCFM(e); cfm.load_state_dict(synth.unet_state_dict(ud, 0))
+mu1, cond1, spk1 = mu[:1].contiguous(), cond[:1].contiguous(), spks[:1].contiguous()
+for steps in (10, 25):
+    for _ in range(2):
+        cfm(mu1, None, steps, spks=spk1, cond=cond1)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(3):
+        cfm(mu1, None, steps, spks=spk1, cond=cond1)
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 3
+    print(f"solve, {steps} Euler steps, T={T} ({T / 50:.1f} s of audio): {ms:.1f} ms, {flops * steps / ms / 1e9:.1f} TFLOP/s")
+e.close()

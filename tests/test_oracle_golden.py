@@ -107,6 +107,21 @@ def test_unet_oracle_matches_reference(golden, name, dims):
     assert (hi + lo - full).abs().max() < 1e-6
 
 
+def test_unet_cfm_oracle_matches_reference(golden):
+    """CausalConditionalCFM.forward over the U-Net estimator (flow_matching.py:203-228): the oracle's Euler solve vs the fixture"""
+    from oracle import unet_ref
+    from flowmirror_hydravox_b200.flow import rand_noise
+    dims = D.UNET_SMALL
+    g = golden("unet_cfm_small")
+    sd = synth.unet_state_dict(dims, g["seed"])
+    assert abs(_checksum(sd) - g["sd_checksum"]) < 1e-6 * g["sd_checksum"]
+    noise = rand_noise(dims.mel, 15000)
+    for key, streaming in (("full", False), ("stream", True)):
+        y = unet_ref.cfm_solve(sd, g["mu"], g["spks"], g["cond"], noise, g["n_steps"], dims, streaming=streaming)
+        assert y.shape == g["mel_" + key].shape == (1, dims.mel, g["T"])
+        assert (y - g["mel_" + key]).abs().max() < 5e-5
+
+
 @pytest.mark.parametrize("name,dims", [("tiny", D.FLOW_TINY), ("full", D.FLOW_FULL)])
 def test_flow_oracle_matches_reference(golden, name, dims):
     g = golden(f"flow_{name}")

@@ -114,6 +114,29 @@ def test_unet_graph_replay_rereads_inputs(unets):
         assert (e.launches() - n0) % 4 == 0 and e.launches() > n0          # replayed steps count the kernels inside the graph
 
 
+@pytest.mark.parametrize("name,ud", [("small", D.UNET_SMALL), ("full", D.UNET_FULL)])
+@pytest.mark.parametrize("precise", [True, False])
+def test_unet_cfm_solve_matches_reference_fixture(golden, name, ud, precise):
+    """hvx_cfm_solve_unet (noise slice, cosine schedule, CFG staging, estimator, Euler) vs the reference's
+    CausalConditionalCFM.forward over its own U-Net estimator, offline and streaming; the solve replays the estimator graph"""
+    from flowmirror_hydravox_b200 import _lib as L
+    from flowmirror_hydravox_b200.flow import NativeUNetCFM
+    g = golden("unet_cfm_" + name)
+    e = L.Engine(ud=ud, flow_precise=precise)
+    try:
+        cfm = NativeUNetCFM(e)
+        cfm.load_state_dict({"estimator." + k: v for k, v in synth.unet_state_dict(ud, 0).items()})
+        for key, streaming in (("full", False), ("stream", True)):
+            for rep in range(2):                                    # second solve: the graph captured by the first is replayed from step 0
+                mel, _ = cfm(g["mu"], torch.ones(1, 1, g["T"]), g["n_steps"], spks=g["spks"], cond=g["cond"], streaming=streaming)
+                err = (mel.cpu() - g["mel_" + key]).abs()
+                print(f"[unet cfm {name} precise={precise} {key}] mel max-abs {err.max():.3e} mean-abs {err.mean():.3e}")
+                assert mel.shape == (1, ud.mel, g["T"])
+                assert err.max().item() < (1e-3 if precise else 2e-2), (key, rep, err.max().item())   # north_star: 1e-3 on mel frames
+    finally:
+        e.close()
+
+
 def test_unet_rejects_bad_input(unets):
     from flowmirror_hydravox_b200 import _lib as L
     e, m, ud = unets["tiny"]
