@@ -74,7 +74,17 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == ACT_SILU) return v / (1.0f + expf(-v));
   if (act == ACT_MISH) { const float sp = v > 20.0f ? v : log1pf(expf(v)); return v * tanhf(sp); }
   if (act == ACT_LRELU) return v > 0.f ? v : 0.01f * v;
-  if (act == ACT_GELU_ERF) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+  if (act == ACT_GELU_ERF) {
+    // exact-erf GELU (F.gelu default).  erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, below fp32 noise of the GEMM):
+    // one rcp + one ex2 + 7 FMAs instead of erff's ~35-instruction branchy polynomial — the epilogue of the 128x256 ff1
+    // tile was longer than its K = 256 main loop (31 us per launch under ncu)
+    const float z = fabsf(v) * 0.70710678118654752f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f); p = fmaf(p, t, -0.284496736f); p = fmaf(p, t, 0.254829592f);
+    const float er = 1.0f - p * t * __expf(-z * z);          // erf(|v|/sqrt2)
+    return 0.5f * v * (1.0f + copysignf(er, v));
+  }
   return v;
 }
 
@@ -112,13 +122,25 @@ __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx,
         }
       } else if (MODE == EPI_F32) {
         float* o = reinterpret_cast<float*>(epi.out) + (size_t)row * epi.ldo + col0;
-        if (epi.resid) {
-          const float* r = epi.resid + (size_t)row * epi.ldo + col0;
+        const bool vec = col0 + 32 <= N && (epi.ldo & 3) == 0 && ((uintptr_t)epi.out & 15) == 0 &&
+                         (!epi.resid || ((uintptr_t)epi.resid & 15) == 0);          // a thread owns 128 contiguous bytes of its row
+        if (vec) {
+          if (epi.resid) {
+            const float4* r = reinterpret_cast<const float4*>(epi.resid + (size_t)row * epi.ldo + col0);
+#pragma unroll
+            for (int j = 0; j < 8; j++) { const float4 rr = r[j]; f[4 * j] += rr.x; f[4 * j + 1] += rr.y; f[4 * j + 2] += rr.z; f[4 * j + 3] += rr.w; }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; j++) reinterpret_cast<float4*>(o)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        } else {
+          if (epi.resid) {
+            const float* r = epi.resid + (size_t)row * epi.ldo + col0;
+            #pragma unroll
+            for (int j = 0; j < 32; j++) if (col0 + j < N) f[j] += r[j];
+          }
           #pragma unroll
-          for (int j = 0; j < 32; j++) if (col0 + j < N) f[j] += r[j];
+          for (int j = 0; j < 32; j++) if (col0 + j < N) o[j] = f[j];
         }
-        #pragma unroll
-        for (int j = 0; j < 32; j++) if (col0 + j < N) o[j] = f[j];
         if (epi.out2) {
           __nv_bfloat16* o2 = epi.out2 + (size_t)row * (epi.ldo2 ? epi.ldo2 : epi.ldo) + col0;
           #pragma unroll
@@ -502,7 +524,8 @@ hvx_status gemm_bf16(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* A, int
     return launch_gemm_persist(e, st, ta, tb, M, N, K, epi, ad);
   }
   const int ctas128 = cdiv(N, 128) * cdiv(ad.rows_per_batch, BM) * ad.n_batch;
-  if (N <= 64 || ad.a_col_per_ntile == 64 || ctas128 < 96) {
+  static const int min128 = getenv("HVX_GEMM_MIN_CTAS128") ? atoi(getenv("HVX_GEMM_MIN_CTAS128")) : 96;   // below: 128 x 64 tiles fill the SMs better
+  if (N <= 64 || ad.a_col_per_ntile == 64 || ctas128 < min128) {
     HVX_CHECK(make_tmap_bf16_2d(&tb, B, N, kB, ldb, 64, BK), HVX_ERR_CUDA, "gemm: cuTensorMapEncodeTiled(B) failed");
     return launch_gemm<64, 4>(e, st, ta, tb, M, N, K, epi, ad);
   }

@@ -58,91 +58,98 @@ __global__ void unet_cast_kernel(const float* __restrict__ a, const float* __res
 }
 
 // y = act(LayerNorm(h) * gamma + beta) (+ add[batch])   eps 1e-5 (nn.LayerNorm default); act 1 = Mish.
-// One warp per row, D <= 1024 (multiple of 32).  Output fp16 operand rows (out16, [hi | lo] when split) or fp32 (out32).
+// One warp per row, D <= 1024 and a multiple of 128: a lane owns float4 columns (k*32 + lane), so every load/store
+// instruction of the warp covers 512 contiguous bytes.  Output fp16 operand rows (out16, [hi | lo] when split) or fp32 (out32).
 __global__ void __launch_bounds__(256) unet_ln_kernel(const float* __restrict__ h, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, const float* __restrict__ add, int add_ld,
                                                        int rows_per_batch, int act, __half* __restrict__ out16,
                                                        float* __restrict__ out32, int M, int D, int split) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= M) return;
-  const float* hr = h + (size_t)row * D;
-  float v[32];
-  const int n = D >> 5;
+  const float4* hr = reinterpret_cast<const float4*>(h + (size_t)row * D);
+  float4 v[8];
+  const int n = D >> 7;
   float s = 0.f;
 #pragma unroll
-  for (int k = 0; k < 32; k++)
-    if (k < n) { v[k] = hr[k * 32 + lane]; s += v[k]; }
+  for (int k = 0; k < 8; k++)
+    if (k < n) { v[k] = hr[k * 32 + lane]; s += (v[k].x + v[k].y) + (v[k].z + v[k].w); }
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s / (float)D;
   float q = 0.f;
 #pragma unroll
-  for (int k = 0; k < 32; k++)
-    if (k < n) { const float d = v[k] - mean; q += d * d; }
+  for (int k = 0; k < 8; k++)
+    if (k < n) {
+      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
   for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = rsqrtf(q / (float)D + 1e-5f);
   const float* ar = add ? add + (size_t)(row / rows_per_batch) * add_ld : nullptr;
 #pragma unroll
-  for (int k = 0; k < 32; k++)
+  for (int k = 0; k < 8; k++)
     if (k < n) {
-      const int c = k * 32 + lane;
-      float y = (v[k] - mean) * rstd * gamma[c] + beta[c];
-      if (act == 1) { const float sp = y > 20.0f ? y : log1pf(expf(y)); y = y * tanhf(sp); }
-      if (ar) y += ar[c];
-      if (out32) out32[(size_t)row * D + c] = y;
+      const int c4 = k * 32 + lane;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4), bt = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+      float y[4] = {(v[k].x - mean) * rstd * g.x + bt.x, (v[k].y - mean) * rstd * g.y + bt.y,
+                    (v[k].z - mean) * rstd * g.z + bt.z, (v[k].w - mean) * rstd * g.w + bt.w};
+      if (act == 1) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) { const float sp = y[e] > 20.0f ? y[e] : log1pf(expf(y[e])); y[e] = y[e] * tanhf(sp); }
+      }
+      if (ar) {
+        const float4 aa = __ldg(reinterpret_cast<const float4*>(ar) + c4);
+        y[0] += aa.x; y[1] += aa.y; y[2] += aa.z; y[3] += aa.w;
+      }
+      if (out32) reinterpret_cast<float4*>(out32 + (size_t)row * D)[c4] = make_float4(y[0], y[1], y[2], y[3]);
       if (out16) {
         __half* orow = out16 + (size_t)row * D * (split ? 2 : 1);
-        const __half hi = __float2half_rn(y);
-        orow[c] = hi;
-        if (split) orow[D + c] = __float2half_rn(y - __half2float(hi));
+        const __half2 h01 = __floats2half2_rn(y[0], y[1]), h23 = __floats2half2_rn(y[2], y[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&h01); pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+        reinterpret_cast<uint2*>(orow)[c4] = pk;
+        if (split) {
+          const __half2 l01 = __floats2half2_rn(y[0] - __low2float(h01), y[1] - __high2float(h01));
+          const __half2 l23 = __floats2half2_rn(y[2] - __low2float(h23), y[3] - __high2float(h23));
+          pk.x = *reinterpret_cast<const uint32_t*>(&l01); pk.y = *reinterpret_cast<const uint32_t*>(&l23);
+          reinterpret_cast<uint2*>(orow + D)[c4] = pk;
+        }
       }
     }
 }
 
-// SinusoidalPosEmb(in_ch) -> Linear -> SiLU -> Linear, then the Mish every resnet's mlp applies first
-// (matcha/models/components/decoder.py:14-28,73-113,49).  One block per batch row; fp32 throughout.
-__global__ void __launch_bounds__(256) unet_time_kernel(const float* __restrict__ t_dev, const float* __restrict__ freqs,
-                                                         const float* __restrict__ w1, const float* __restrict__ b1,
-                                                         const float* __restrict__ w2, const float* __restrict__ b2,
-                                                         float* __restrict__ out, int in_ch, int tdim) {
-  __shared__ float s_in[1024];
-  __shared__ float s_h[4096];
-  const float t = t_dev[blockIdx.x];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = in_ch >> 1;
-  for (int i = tid; i < half; i += 256) {
-    const float a = (1000.0f * t) * freqs[i];
-    s_in[i] = sinf(a);
-    s_in[i + half] = cosf(a);
+// Time embedding: SinusoidalPosEmb(in_ch) -> Linear -> SiLU -> Linear, then the Mish every resnet's mlp applies first, then every
+// resnet's Linear(tdim -> C) (matcha/models/components/decoder.py:14-28,73-113,49,57).  fp32 throughout; three launches of
+// warp-per-output mat-vecs (grid.y = CFG row) — a 2-block version of the same math took 745 us, 7 % of an NFE.
+__global__ void __launch_bounds__(256) unet_time1_kernel(const float* __restrict__ t_dev, const float* __restrict__ freqs,
+                                                          const float* __restrict__ w1, const float* __restrict__ b1,
+                                                          float* __restrict__ out, int in_ch, int tdim) {
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, half = in_ch >> 1;
+  if (j >= tdim) return;
+  const float t = t_dev[blockIdx.y];
+  float acc = 0.f;
+  for (int i = lane; i < in_ch; i += 32) {
+    const float a = (1000.0f * t) * freqs[i < half ? i : i - half];
+    acc = fmaf(w1[(size_t)j * in_ch + i], i < half ? sinf(a) : cosf(a), acc);
   }
-  __syncthreads();
-  for (int j = warp; j < tdim; j += 8) {
-    float acc = 0.f;
-    for (int i = lane; i < in_ch; i += 32) acc = fmaf(w1[(size_t)j * in_ch + i], s_in[i], acc);
-    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) { const float v = acc + b1[j]; s_h[j] = v / (1.0f + expf(-v)); }
-  }
-  __syncthreads();
-  for (int j = warp; j < tdim; j += 8) {
-    float acc = 0.f;
-    for (int i = lane; i < tdim; i += 32) acc = fmaf(w2[(size_t)j * tdim + i], s_h[i], acc);
-    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-      const float v = acc + b2[j];
-      const float sp = v > 20.0f ? v : log1pf(expf(v));
-      out[(size_t)blockIdx.x * tdim + j] = v * tanhf(sp);
-    }
-  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) { const float v = acc + b1[j]; out[(size_t)blockIdx.y * tdim + j] = v / (1.0f + expf(-v)); }
 }
 
-// every resnet's Linear(tdim -> C) on Mish(t_emb): out[b][j] for j in [0, n_res*C); a warp per output
+// out[b][j] = act(w[j] . in[b] + bias[j]); act 1 = Mish.  A warp per output.
 __global__ void __launch_bounds__(256) unet_rmlp_kernel(const float* __restrict__ temb, const float* __restrict__ w,
-                                                         const float* __restrict__ b, float* __restrict__ out, int n_out, int tdim) {
+                                                         const float* __restrict__ b, float* __restrict__ out, int n_out, int tdim,
+                                                         int act) {
   const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (j >= n_out) return;
   const float* tr = temb + (size_t)blockIdx.y * tdim;
   float acc = 0.f;
   for (int i = lane; i < tdim; i += 32) acc = fmaf(w[(size_t)j * tdim + i], tr[i], acc);
   for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) out[(size_t)blockIdx.y * n_out + j] = acc + b[j];
+  if (lane == 0) {
+    float v = acc + b[j];
+    if (act == 1) { const float sp = v > 20.0f ? v : log1pf(expf(v)); v = v * tanhf(sp); }
+    out[(size_t)blockIdx.y * n_out + j] = v;
+  }
 }
 
 // v (2T, C) frame-major -> out (2, C, T)
@@ -197,8 +204,8 @@ static hvx_status uget(hvx_engine* e, const std::string& name, int dtype, const 
 hvx_status unet_finalize(hvx_engine* e) {
   const hvx_config& c = e->cfg;
   const int C = c.unet_ch, mel = c.unet_mel, in_ch = 4 * mel, inner = c.unet_heads * 64, ff = C * c.unet_ff_mult, tdim = 4 * C;
-  HVX_CHECK(C > 0 && C % 64 == 0 && C <= 1024 && in_ch % 64 == 0 && in_ch <= 1024 && tdim <= 4096, HVX_ERR_UNSUPPORTED,
-            "unet: channels %d / mel %d unsupported (multiples of 64 / 16)", C, mel);
+  HVX_CHECK(C > 0 && C % 128 == 0 && C <= 1024 && in_ch % 64 == 0 && in_ch <= 1024 && tdim <= 4096, HVX_ERR_UNSUPPORTED,
+            "unet: channels %d / mel %d unsupported (multiples of 128 / 16)", C, mel);
   HVX_CHECK(c.unet_n_blocks >= 1 && c.unet_n_mid >= 0 && c.unet_heads >= 1 && c.unet_ff_mult >= 1, HVX_ERR_UNSUPPORTED, "unet: bad dims");
   if (!e->unet) e->unet = new UnetState();
   UnetState* u = e->unet;
@@ -268,7 +275,7 @@ struct UnetRun {
   int T, M, C, inner, ff, px;
   // workspace
   __half *a16, *b16, *qk, *vt, *ao, *f1;
-  float *h, *tmp, *skip, *temb, *radd, *v;
+  float *h, *tmp, *skip, *temb, *temb1, *radd, *v;
   int Tp;
 
   // y = x W^T, fp16 operands; parity mode: three-term split products (flow.cu: flow_linear)
@@ -350,14 +357,14 @@ static hvx_status unet_run(hvx_engine* e, const float* x, const float* mu, const
   const int wmax = std::max(in_ch, 2 * C);
   const size_t o_a = take(M * wmax * 2 * r.px), o_b = take(M * C * 2 * r.px), o_qk = take(M * 2 * r.inner * 2);
   const size_t o_vt = take((size_t)2 * r.inner * r.Tp * 2), o_ao = take(M * r.inner * 2 * r.px), o_f1 = take(M * r.ff * 2 * r.px);
-  const size_t o_h = take(M * C * 4), o_tmp = take(M * C * 4), o_skip = take(M * C * 4), o_te = take((size_t)2 * tdim * 4);
+  const size_t o_h = take(M * C * 4), o_tmp = take(M * C * 4), o_skip = take(M * C * 4), o_te = take((size_t)2 * tdim * 4), o_te1 = take((size_t)2 * tdim * 4);
   const size_t o_ra = take((size_t)2 * n_res * C * 4), o_v = take(M * mel * 4);
   const bool grew = off > u->ws.bytes;
   uint8_t* w = (uint8_t*)u->ws.get(off);
   HVX_CHECK(w, HVX_ERR_CUDA, "unet: workspace allocation of %zu bytes failed", off);
   r.a16 = (__half*)(w + o_a); r.b16 = (__half*)(w + o_b); r.qk = (__half*)(w + o_qk); r.vt = (__half*)(w + o_vt);
   r.ao = (__half*)(w + o_ao); r.f1 = (__half*)(w + o_f1); r.h = (float*)(w + o_h); r.tmp = (float*)(w + o_tmp);
-  r.skip = (float*)(w + o_skip); r.temb = (float*)(w + o_te); r.radd = (float*)(w + o_ra); r.v = (float*)(w + o_v);
+  r.skip = (float*)(w + o_skip); r.temb = (float*)(w + o_te); r.temb1 = (float*)(w + o_te1); r.radd = (float*)(w + o_ra); r.v = (float*)(w + o_v);
   r.n_add_ld = n_res * C;
   if (grew || u->vt_T != T) {                       // V^T pad columns must hold finite values
     HVX_CUDA(cudaMemsetAsync(r.vt, 0, (size_t)2 * r.inner * r.Tp * 2, st));
@@ -372,9 +379,11 @@ static hvx_status unet_run(hvx_engine* e, const float* x, const float* mu, const
   };
 
   // time embedding and every resnet's conditioning vector (decoder.py:424-425, matcha decoder.py:57)
-  unet_time_kernel<<<2, 256, 0, st>>>(t, u->freqs, u->tm1_w, u->tm1_b, u->tm2_w, u->tm2_b, r.temb, in_ch, tdim);
+  unet_time1_kernel<<<dim3(cdiv(tdim, 8), 2), 256, 0, st>>>(t, u->freqs, u->tm1_w, u->tm1_b, r.temb1, in_ch, tdim);
   HVX_LAUNCH_CHECK(e);
-  unet_rmlp_kernel<<<dim3(cdiv(n_res * C, 8), 2), 256, 0, st>>>(r.temb, u->rmlp_w, u->rmlp_b, r.radd, n_res * C, tdim);
+  unet_rmlp_kernel<<<dim3(cdiv(tdim, 8), 2), 256, 0, st>>>(r.temb1, u->tm2_w, u->tm2_b, r.temb, tdim, tdim, 1);
+  HVX_LAUNCH_CHECK(e);
+  unet_rmlp_kernel<<<dim3(cdiv(n_res * C, 8), 2), 256, 0, st>>>(r.temb, u->rmlp_w, u->rmlp_b, r.radd, n_res * C, tdim, 0);
   HVX_LAUNCH_CHECK(e);
   unet_pack_kernel<<<cdiv(2 * T * in_ch, 256), 256, 0, st>>>(x, mu, spks, cond, r.a16, T, mel, u->precise);
   HVX_LAUNCH_CHECK(e);
