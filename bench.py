@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--first-audio-runs", type=int, default=20, help="streaming first-audio latency samples (0 = skip)")
     ap.add_argument("--parity-mode-steps", type=int, default=2, help="also time the parity mode (fp32 KV cache, split-fp16 flow GEMMs); 0 = skip")
+    ap.add_argument("--no-variants", action="store_true", help="skip the timing of the alternate estimator / vocoders (SURVEY 8 a7', a12')")
     ap.add_argument("--cpu-tokens", type=int, default=128, help="speech tokens in the CPU baseline sample (~10-20 s of CPU work)")
     return ap.parse_args()
 
@@ -370,6 +371,9 @@ def native_arm(a):
                                "total_ms_p50": tot_ms[len(tot_ms) // 2], "audio_s": n_s / hd.sr,
                                "config": "batch=1, 16+64 text tokens, 125-token prompt, inference_head_num=2, 10 CFM steps, first chunk = "
                                          "25+3 tokens; request -> first waveform chunk on the host (wall clock)"}
+    # SURVEY 8 a7' / a12': the alternate estimator (U-Net) and the transposed-conv vocoders on the same frame count, CUDA events
+    if not a.no_variants and world == 1:
+        line["variants"] = variants(mm.engine.device, 2 * (n_tok + 125), a.cfm_steps, tf_peak)
     if not a.no_cpu_baseline:
         threads = os.cpu_count() or 1
         r = cpu_oracle_run(a, a.cpu_tokens, threads)
@@ -378,6 +382,51 @@ def native_arm(a):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def variants(device, T, cfm_steps, tf_peak):
+    """CUDA-event timings of hvx_cfm_solve_unet, hvx_hifigan_vocode and hvx_hift_t_vocode at T mel frames (inputs resident)."""
+    import torch
+    from flowmirror_hydravox_b200 import _lib as L, dims as D, synth
+    from flowmirror_hydravox_b200.flow import NativeUNetCFM
+    from flowmirror_hydravox_b200.hift import NativeHiFiGAN, NativeHiFTTransposed
+
+    def timed(fn, reps=3):
+        fn(); fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    out = {}
+    g = torch.Generator().manual_seed(5)
+    ud = D.UNET_FULL
+    C, inner, ff = ud.ch, ud.heads * ud.head_dim, ud.ch * ud.ff_mult
+    res = lambda cin: 3 * cin * C + 3 * C * C + cin * C
+    mac = res(ud.in_ch) + ud.n_mid * res(C) + res(2 * C) + ud.n_res * ud.n_blocks * (C * 3 * inner + inner * C + 2 * C * ff) + 9 * C * C + C * ud.mel
+    flops = (2 * (2 * T) * mac + 2 * ud.n_res * ud.n_blocks * 4 * T * T * inner) * cfm_steps
+    e = L.Engine(ud=ud, device=str(device))
+    cfm = NativeUNetCFM(e); cfm.load_state_dict(synth.unet_state_dict(ud, 0))
+    mu, cond = (torch.randn(1, ud.mel, T, generator=g).to(device) for _ in range(2))
+    spk = torch.randn(1, ud.mel, generator=g).to(device)
+    ms = timed(lambda: cfm(mu, None, cfm_steps, spks=spk, cond=cond))
+    tf = flops / ms / 1e9
+    out["unet_cfm_solve"] = {"ms": ms, "frames": T, "euler_steps": cfm_steps, "tflops": tf, "frac_of_bf16_peak": tf / tf_peak,
+                             "what": "hvx_cfm_solve_unet: CausalConditionalCFM.forward over the U-Net estimator (71.3 M params), fp16 operands"}
+    e.close()
+    for name, hd, cls, sdf in (("hifigan_v1", D.HIFIGAN_V1, NativeHiFiGAN, synth.hifigan_state_dict),
+                               ("hift_transposed", D.HIFT_FULL, NativeHiFTTransposed, synth.hift_t_state_dict)):
+        e = L.Engine(hd=hd, device=str(device))
+        v = cls(e); v.load_state_dict(sdf(hd, 0))
+        mel = (torch.rand(1, hd.mel, T, generator=g) * 6 - 6).to(device)
+        ms = timed((lambda: v(mel)) if cls is NativeHiFiGAN else (lambda: v.inference(mel)))
+        audio_s = T * hd.frame_samples / hd.sr
+        out[name] = {"ms": ms, "frames": T, "audio_s": audio_s, "rtf": ms / 1e3 / audio_s}
+        e.close()
+    return out
 
 
 def main():

@@ -173,35 +173,49 @@ __global__ void flow_rope_kernel(const float* __restrict__ inv_freq, float* __re
 }
 
 // out16 = LayerNorm(h) * (1 + scale) + shift   (modules.py:230-244,262-265; eps 1e-6, no affine)
+// One warp per row, D <= 1024 and a multiple of 128: a lane owns float4 columns (k*32 + lane) — 512 contiguous bytes per warp
+// load instruction, 8-byte fp16 stores.
 __global__ void __launch_bounds__(256) dit_ln_mod_kernel(const float* __restrict__ h, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, __half* __restrict__ out, int M,
                                                           int D, int split) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= M) return;
-  const float* hr = h + (size_t)row * D;
-  float v[32];
-  const int n = D >> 5;                    // D <= 1024, multiple of 32
+  const float4* hr = reinterpret_cast<const float4*>(h + (size_t)row * D);
+  float4 v[8];
+  const int n = D >> 7;
   float s = 0.f;
 #pragma unroll
-  for (int k = 0; k < 32; k++)
-    if (k < n) { v[k] = hr[k * 32 + lane]; s += v[k]; }
+  for (int k = 0; k < 8; k++)
+    if (k < n) { v[k] = hr[k * 32 + lane]; s += (v[k].x + v[k].y) + (v[k].z + v[k].w); }
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s / (float)D;
   float q = 0.f;
 #pragma unroll
-  for (int k = 0; k < 32; k++)
-    if (k < n) { const float d = v[k] - mean; q += d * d; }
+  for (int k = 0; k < 8; k++)
+    if (k < n) {
+      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
   for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = rsqrtf(q / (float)D + 1e-6f);
   __half* orow = out + (size_t)row * D * (split ? 2 : 1);       // split: [hi | lo] per row (parity mode)
 #pragma unroll
-  for (int k = 0; k < 32; k++)
+  for (int k = 0; k < 8; k++)
     if (k < n) {
-      const int c = k * 32 + lane;
-      const float y = (v[k] - mean) * rstd * (1.0f + scale[c]) + shift[c];
-      const __half hi = __float2half_rn(y);
-      orow[c] = hi;
-      if (split) orow[D + c] = __float2half_rn(y - __half2float(hi));
+      const int c4 = k * 32 + lane;
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + c4), sh = __ldg(reinterpret_cast<const float4*>(shift) + c4);
+      const float y0 = (v[k].x - mean) * rstd * (1.0f + sc.x) + sh.x, y1 = (v[k].y - mean) * rstd * (1.0f + sc.y) + sh.y;
+      const float y2 = (v[k].z - mean) * rstd * (1.0f + sc.z) + sh.z, y3 = (v[k].w - mean) * rstd * (1.0f + sc.w) + sh.w;
+      const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&h01); pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+      reinterpret_cast<uint2*>(orow)[c4] = pk;
+      if (split) {
+        const __half2 l01 = __floats2half2_rn(y0 - __low2float(h01), y1 - __high2float(h01));
+        const __half2 l23 = __floats2half2_rn(y2 - __low2float(h23), y3 - __high2float(h23));
+        pk.x = *reinterpret_cast<const uint32_t*>(&l01); pk.y = *reinterpret_cast<const uint32_t*>(&l23);
+        reinterpret_cast<uint2*>(orow + D)[c4] = pk;
+      }
     }
 }
 
@@ -258,8 +272,8 @@ hvx_status flow_finalize(hvx_engine* e) {
   const hvx_config& c = e->cfg;
   const int dim = c.flow_dim, inner = c.flow_heads * c.flow_dim_head, ff = dim * c.flow_ff_mult, mel = c.flow_mel;
   HVX_CHECK(c.flow_dim_head == 64, HVX_ERR_UNSUPPORTED, "flow: dim_head must be 64");
-  HVX_CHECK(dim % 64 == 0 && dim <= 1024 && dim / c.flow_pos_groups == 64, HVX_ERR_UNSUPPORTED,
-            "flow: dim must be a multiple of 64 (<=1024) with 64-channel conv groups (dim=%d groups=%d)", dim, c.flow_pos_groups);
+  HVX_CHECK(dim % 128 == 0 && dim <= 1024 && dim / c.flow_pos_groups == 64, HVX_ERR_UNSUPPORTED,
+            "flow: dim must be a multiple of 128 (<=1024) with 64-channel conv groups (dim=%d groups=%d)", dim, c.flow_pos_groups);
   HVX_CHECK(c.flow_depth <= 64 && mel % 16 == 0 && c.flow_pla_ch % 64 == 0, HVX_ERR_UNSUPPORTED, "flow: unsupported dims");
   if (!e->flow) e->flow = new FlowState();
   FlowState* f = e->flow;
