@@ -827,18 +827,19 @@ dit_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       tc::tmem_ld_wait();
       const int kbase = j * 64;
       float mt[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      // raw scores stay in registers: the max is taken on them (sc > 0) and the scale rides in the ex2 argument as one FFMA
       if (kbase + 64 <= klim_row) {
 #pragma unroll
-        for (int i = 0; i < 64; i++) { const float s = __uint_as_float(sreg[i]) * sc; sreg[i] = __float_as_uint(s); mt[i & 3] = fmaxf(mt[i & 3], s); }
+        for (int i = 0; i < 64; i++) mt[i & 3] = fmaxf(mt[i & 3], __uint_as_float(sreg[i]));
       } else {
 #pragma unroll
         for (int i = 0; i < 64; i++) {
-          const float s = (kbase + i < klim_row) ? __uint_as_float(sreg[i]) * sc : -INFINITY;
+          const float s = (kbase + i < klim_row) ? __uint_as_float(sreg[i]) : -INFINITY;
           sreg[i] = __float_as_uint(s);
           mt[i & 3] = fmaxf(mt[i & 3], s);
         }
       }
-      const float m_tile = fmaxf(fmaxf(mt[0], mt[1]), fmaxf(mt[2], mt[3]));
+      const float m_tile = fmaxf(fmaxf(mt[0], mt[1]), fmaxf(mt[2], mt[3])) * sc;
       const bool need = m_tile > m_run + 8.0f;
       if (__any_sync(0xffffffffu, need)) {
         const float m_new = need ? m_tile : m_run;
@@ -870,7 +871,7 @@ dit_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = tc::ex2(__uint_as_float(sreg[c0 + i]) - m_run), p1 = tc::ex2(__uint_as_float(sreg[c0 + i + 1]) - m_run);
+          const float p0 = tc::ex2(fmaf(__uint_as_float(sreg[c0 + i]), sc, -m_run)), p1 = tc::ex2(fmaf(__uint_as_float(sreg[c0 + i + 1]), sc, -m_run));
           ps[(i >> 1) & 3] += p0 + p1;
           pk[i >> 1] = tc::pack16(p0, p1, a.f16);
         }
