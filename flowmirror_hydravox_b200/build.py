@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhydravox_b200.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "hift.cu", "gemm.cu", "attention.cu", "flow.cu", "unet.cu", "llm.cu", "pipeline.cu"]
+SOURCES = ["api.cu", "frontend.cu", "hift.cu", "gemm.cu", "attention.cu", "flow.cu", "unet.cu", "llm.cu", "pipeline.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 

@@ -55,6 +55,7 @@ struct hvx_engine {
   hvx::UnetState* unet = nullptr;
   int64_t launches = 0;
   hvx::DevBuf samp_ws;             // sampler tables (llm.cu)
+  hvx::DevBuf fe_ws;               // frontend spectrum scratch (frontend.cu)
   void* samp_arrive = nullptr;
   int64_t graph_launches = 0;      // kernels inside the captured decode-step graph
   int sm_count = 148;

@@ -81,6 +81,19 @@ hvx_status hvx_set_tensor(hvx_engine* e, int stage, const char* name, const void
                           const int64_t* shape, int ndim);
 hvx_status hvx_finalize(hvx_engine* e, int stage);
 
+/* ---- zero-shot frontend features: framed signal x folded linear basis -> magnitude / power -> filterbank -> log.
+ * Replaces mel_spectrogram (matcha/utils/audio.py:42-82; the flow's prompt_feat, called from
+ * cosyvoice/cli/frontend.py:117-122) and kaldi.fbank + mean subtraction (cosyvoice/cli/frontend.py:108-112).
+ * wav_dev (n_samples) fp32; basis_dev [frame_len][2*n_bins] fp32 = everything linear before the non-linearity (window, DC
+ * removal, pre-emphasis, DFT: re columns then im columns; flowmirror_hydravox_b200/frontend.py builds it); fb_dev
+ * [n_mels][n_bins].  Frames: n_frames = (n_samples + 2*pad_reflect - frame_len) / hop + 1 (checked).  power 0:
+ * sqrt(re^2+im^2+mag_eps), 1: re^2+im^2.  out = log(max(fb . spectrum, log_floor)), frame-major [n_frames][n_mels] or
+ * channel-major [n_mels][n_frames]; subtract_mean removes the per-bin mean over frames (frame-major only). */
+hvx_status hvx_frontend_fbank(hvx_engine* e, const float* wav_dev, int n_samples, int frame_len, int hop, int pad_reflect,
+                              const float* basis_dev, int n_bins, const float* fb_dev, int n_mels, int power,
+                              float mag_eps, float log_floor, int subtract_mean, int channel_major, float* out_dev,
+                              int n_frames, void* stream);
+
 /* ---- HiFT: replaces CausalHiFTGenerator.inference (cosyvoice/hifigan/generator.py:713-726) ----
  * mel_dev (mel, T) fp32 -> wav_dev (frame*T') fp32 clamped to +-0.99, src_dev (frame*T) source.
  * finalize=0 follows the streaming branch (:676-679,708-709,725): T' = T-3-4 frames... see DESIGN.md.

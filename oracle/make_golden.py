@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from flowmirror_hydravox_b200 import dims as D, synth  # noqa: E402
-from oracle import flow_ref, hift_ref, hifigan_ref, llm_ref, refshim, unet_ref  # noqa: E402
+from oracle import flow_ref, frontend_ref, hift_ref, hifigan_ref, llm_ref, refshim, unet_ref  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -174,6 +174,33 @@ def golden_unet_cfm(name, dims, T, n_steps, seed):
                os.path.join(OUT, f"unet_cfm_{name}.pt"))
 
 
+def golden_frontend(seed):
+    """f1: the reference's own mel_spectrogram (matcha/utils/audio.py:42-82) on a synthetic 24 kHz prompt, with the yaml's
+    feat_extractor arguments; torchaudio's kaldi.fbank (the call of cosyvoice/cli/frontend.py:108-112) on a 16 kHz one."""
+    refshim.install()
+    from matcha.utils.audio import mel_spectrogram
+    import torchaudio.compliance.kaldi as kaldi
+    from flowmirror_hydravox_b200.frontend import slaney_mel_basis
+    g = torch.Generator().manual_seed(seed + 700)
+    t = torch.arange(24000 * 2 + 331) / 24000.0
+    y = (0.4 * torch.sin(2 * torch.pi * 220.0 * t) + 0.2 * torch.sin(2 * torch.pi * 1760.0 * t * (1 + 0.1 * t))
+         + 0.05 * torch.randn(t.shape, generator=g))[None].clamp(-1, 1)
+    mel = mel_spectrogram(y, n_fft=1920, num_mels=80, sampling_rate=24000, hop_size=480, win_size=1920, fmin=0, fmax=8000, center=False)
+    basis = slaney_mel_basis(24000, 1920, 80, 0, 8000)
+    mel_o = frontend_ref.mel_spectrogram(y, basis)
+    e = (mel - mel_o).abs().max().item()
+    t16 = torch.arange(16000 * 3 + 77) / 16000.0
+    s16 = (0.3 * torch.sin(2 * torch.pi * 150.0 * t16) + 0.1 * torch.randn(t16.shape, generator=g))[None]
+    fb = kaldi.fbank(s16, num_mel_bins=80, dither=0, sample_frequency=16000)
+    fb = fb - fb.mean(dim=0, keepdim=True)
+    fb_o = frontend_ref.kaldi_fbank(s16)
+    e2 = (fb - fb_o).abs().max().item()
+    print(f"[frontend] mel {tuple(mel.shape)} ref-vs-oracle max-abs {e:.2e} (range {mel.min():.2f}..{mel.max():.2f}); "
+          f"kaldi fbank {tuple(fb.shape)} torchaudio-vs-oracle max-abs {e2:.2e}")
+    assert e < 1e-4 and e2 < 1e-3 and mel.shape == (1, 80, y.shape[1] // 480)
+    torch.save(dict(seed=seed, y24=y, mel=mel, s16=s16, fbank=fb), os.path.join(OUT, "frontend.pt"))
+
+
 def golden_flow(name, dims, N, P, n_steps, seed):
     refshim.install()
     import cosyvoice.flow.flow as flowmod
@@ -276,6 +303,10 @@ def golden_llm(name, dims, n_text, n_ptext, P, cases, seed):
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if sys.argv[1:] == ["frontend"]:
+        with torch.no_grad():
+            golden_frontend(0)
+        return
     if sys.argv[1:] == ["unet"]:
         with torch.no_grad():
             golden_unet("tiny", D.UNET_TINY, 37, 0)
@@ -304,6 +335,7 @@ def main():
         golden_unet("full", D.UNET_FULL, 130, 0)
         golden_unet_cfm("small", D.UNET_SMALL, 57, 10, 0)
         golden_unet_cfm("full", D.UNET_FULL, 96, 5, 0)
+        golden_frontend(0)
         golden_flow("tiny", D.FLOW_TINY, 21, 10, 10, 0)
         golden_flow("full", D.FLOW_FULL, 24, 8, 4, 0)
         sp1 = dict(top_p=0.9, top_k=10, win_size=24, tau_r=0.2)     # server tts defaults (router.py:22-44)

@@ -35,7 +35,7 @@ REF_ROOT = os.environ.get("HVX_REFERENCE_ROOT", "/root/reference")
 
 _STUB_ROOTS = (
     "lightning", "hydra", "gdown", "wget", "matplotlib", "conformer", "diffusers",
-    "omegaconf", "x_transformers", "hyperpyyaml",
+    "omegaconf", "x_transformers", "hyperpyyaml", "librosa",
 )
 
 
@@ -212,6 +212,10 @@ def install():
     xt.apply_rotary_pos_emb = apply_rotary_pos_emb
     if "diffusers" in finder_roots:
         _install_diffusers()
+    if "librosa" in finder_roots:          # matcha/utils/audio.py:4 — librosa.filters.mel, restated (slaney scale and norm)
+        from flowmirror_hydravox_b200.frontend import slaney_mel_basis
+        importlib.import_module("librosa.filters").mel = (
+            lambda sr, n_fft, n_mels, fmin, fmax: slaney_mel_basis(sr, n_fft, n_mels, fmin, fmax).numpy())
     _installed = True
 
 
