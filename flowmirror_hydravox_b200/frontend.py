@@ -160,3 +160,28 @@ class KaldiFbank:
 
     def __call__(self, speech: torch.Tensor) -> torch.Tensor:
         return self.impl.run(speech)
+
+
+class NativeFrontendFeatures:
+    """The two feature extractors of `CosyVoiceFrontEnd` that feed the hot path, with the reference's method names and return
+    shapes (cosyvoice/cli/frontend.py:104-122), already-resampled waveforms in (load_wav / resampling stay on the host side):
+      _extract_speech_feat(speech_24k (1, n))  -> (speech_feat (1, n // 480, 80) on the device, speech_feat_len int32 (1,))
+      _extract_spk_fbank(speech_16k (1, n))    -> mean-normalised fbank (n_frames, 80): the input of the CAM++ session."""
+
+    def __init__(self, engine: "L.Engine", mel_basis: torch.Tensor | None = None):
+        self.engine = engine
+        self.feat_extractor = MelSpectrogram(engine, mel_basis=mel_basis)
+        self.fbank = KaldiFbank(engine)
+
+    def _extract_speech_feat(self, speech: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        feat = self.feat_extractor(speech).squeeze(dim=0).transpose(0, 1).unsqueeze(dim=0)
+        return feat, torch.tensor([feat.shape[1]], dtype=torch.int32, device=feat.device)
+
+    def _extract_spk_fbank(self, speech: torch.Tensor) -> torch.Tensor:
+        return self.fbank(speech)
+
+    @staticmethod
+    def align_prompt(speech_feat: torch.Tensor, speech_token: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """frontend_zero_shot's `force speech_feat % speech_token = 2` (cosyvoice/cli/frontend.py:170-174)"""
+        token_len = min(int(speech_feat.shape[1] / 2), speech_token.shape[1])
+        return speech_feat[:, : 2 * token_len], speech_token[:, :token_len]

@@ -64,3 +64,19 @@ def test_frontend_rejects_short_input(fe):
         fbank(torch.zeros(1, 399))
     with pytest.raises(ValueError):
         mel(torch.zeros(1, 100))
+
+
+def test_frontend_feature_objects_mirror_reference_shapes(fe, golden):
+    """_extract_speech_feat returns (1, T, 80) + length like cosyvoice/cli/frontend.py:117-122; align_prompt trims to 2 frames
+    per prompt token (:170-174)"""
+    e, _, _ = fe
+    g = golden("frontend")
+    ff = F.NativeFrontendFeatures(e)
+    feat, n = ff._extract_speech_feat(g["y24"])
+    assert feat.shape == (1, g["mel"].shape[2], 80) and int(n[0]) == feat.shape[1]
+    assert (feat.cpu() - g["mel"].transpose(1, 2)).abs().max().item() < 1e-3
+    tok = torch.arange(45)[None]
+    f2, t2 = ff.align_prompt(feat, tok)
+    assert f2.shape[1] == 2 * t2.shape[1] == 90
+    fb = ff._extract_spk_fbank(g["s16"])
+    assert fb.shape == g["fbank"].shape and abs(float(fb.mean())) < 1e-4
