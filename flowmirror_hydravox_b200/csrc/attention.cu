@@ -750,7 +750,8 @@ dit_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   const int q0 = blockIdx.x * 128;
   const int h = blockIdx.y, b = blockIdx.z;
   const int T = a.T;
-  const int klim_tile = a.chunk > 0 ? min(T, ((min(q0 + 127, T - 1)) / a.chunk + 1) * a.chunk) : T;
+  const int Tk = a.klen ? a.klen[b] : T;     // keys of this batch row that exist (ragged group: the rest of the slab is padding)
+  const int klim_tile = a.chunk > 0 ? min(Tk, ((min(q0 + 127, T - 1)) / a.chunk + 1) * a.chunk) : Tk;
   const int nkv = (klim_tile + 63) / 64;
 
   if (tid == 0) {
@@ -814,7 +815,7 @@ dit_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   } else {
     // ---------------- softmax warps: thread == query row == TMEM lane
     const int row_in_batch = q0 + tid;
-    const int klim_row = a.chunk > 0 ? min(T, (row_in_batch / a.chunk + 1) * a.chunk) : T;
+    const int klim_row = a.chunk > 0 ? min(Tk, (row_in_batch / a.chunk + 1) * a.chunk) : Tk;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const float sc = 0.125f * 1.4426950408889634f;     // dim_head^-0.5 * log2(e)
     float m_run = -INFINITY, l_run = 0.f;
@@ -936,6 +937,8 @@ hvx_status dit_attention(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* qk
     attr_set = true;
   }
   dim3 grid(cdiv(a.T, 128), a.heads, a.n_batch);
+  HVX_CHECK(!a.klen || !(getenv("HVX_ATTN_V1") || getenv("HVX_ATTN_V2") || getenv("HVX_ATTN_V3") || getenv("HVX_ATTN_V4")), HVX_ERR_UNSUPPORTED,
+            "attention: per-batch key counts need the v5 kernel");
   HVX_CHECK(!a.lo_off || !(getenv("HVX_ATTN_V1") || getenv("HVX_ATTN_V2")), HVX_ERR_UNSUPPORTED, "attention: split output needs the v5 kernel");
   if (getenv("HVX_ATTN_V1")) dit_attention_kernel<<<grid, 128, AT_SMEM, st>>>(tq, tk, tv, k_col0, a);
   else if (getenv("HVX_ATTN_V2")) dit_attention_v2_kernel<<<grid, 128, AT_SMEM, st>>>(tq, tk, tv, k_col0, a);

@@ -19,6 +19,8 @@
 #include "gemm.cuh"
 #include <cmath>
 #include <cstring>
+#include <vector>
+#include <algorithm>
 
 namespace hvx {
 
@@ -76,8 +78,9 @@ __global__ void flow_init_kernel(const float* __restrict__ mu_tok, const float* 
 
 // xin[r] = [x | cond | mu | spks] (DiT InputEmbedding order, dit.py:91-95); rows >= T are the CFG
 // unconditional copy: same x, everything else zero (flow_matching.py:100-112)
+// T = rows of the conditional block = U utterances x Tm frames; spks is per utterance [U][C]
 __global__ void dit_pack_fm_kernel(const float* __restrict__ x, const float* __restrict__ cond, const float* __restrict__ mu,
-                                   const float* __restrict__ spks, __half* __restrict__ xin, int T, int C) {
+                                   const float* __restrict__ spks, __half* __restrict__ xin, int T, int C, int Tm) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int W = 4 * C;
   if (i >= 2 * T * W) return;
@@ -89,7 +92,7 @@ __global__ void dit_pack_fm_kernel(const float* __restrict__ x, const float* __r
   else if (r >= T) v = 0.f;
   else if (part == 1) v = cond[(size_t)t * C + c];
   else if (part == 2) v = mu[(size_t)t * C + c];
-  else v = spks[c];
+  else v = spks[(t / Tm) * C + c];
   // split fp16 (hi | lo): the ODE state and the mel-valued conditioning reach |x| ~ 12 where one fp16 ulp is 7.8e-3
   const __half hi = __float2half_rn(v);
   xin[(size_t)r * 2 * W + j] = hi;
@@ -247,8 +250,10 @@ struct FlowState {
   DevBuf ws, ws_small;
   int rope_T = -1;
   int precise = 0;            // three-term split-fp16 GEMMs (hvx_config.flow_precise)
-  // carve-up of ws for the current T (set by flow_plan)
-  int T = 0, Tp = 0;
+  // carve-up of ws for the current (T, U) (set by flow_plan): U utterances of T (padded) frames each, CFG rows stacked as
+  // [conditional block U*T rows | unconditional block U*T rows]; batch index of a T-row slab = cfg * U + u
+  int T = 0, Tp = 0, U = 1;
+  const int* klen = nullptr;  // [2U] valid frames per slab (device), nullptr when every slab is full (U == 1)
   __half *xin, *h0h, *c1, *n16, *qk, *vt, *ao, *f1;
   float *h0, *h, *v, *rope_c, *rope_s;
   // solve-level buffers (ws_small)
@@ -335,18 +340,18 @@ void flow_free(hvx_engine* e) {
 static inline size_t al256(size_t n) { return (n + 255) & ~(size_t)255; }
 
 // estimator workspace for T frames (2T rows)
-static hvx_status flow_plan(hvx_engine* e, cudaStream_t st, int T) {
+static hvx_status flow_plan(hvx_engine* e, cudaStream_t st, int T, int U = 1) {
   FlowState* f = e->flow;
   const hvx_config& c = e->cfg;
   const int dim = c.flow_dim, inner = c.flow_heads * 64, ff = dim * c.flow_ff_mult, mel = c.flow_mel;
-  const size_t M = 2 * (size_t)T;
+  const size_t M = 2 * (size_t)T * U;
   const int Tp = (T + 7) & ~7;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
   const size_t o_xin = take(M * 8 * mel * 2), o_h0 = take(M * dim * 4), o_h0h = take(M * dim * 2 * (f->precise ? 2 : 1)), o_c1 = take(M * dim * 2 * (f->precise ? 2 : 1));
   const size_t ax = f->precise ? 2 : 1;
   const size_t o_h = take(M * dim * 4), o_n = take(M * dim * 2 * ax), o_qk = take(M * 2 * inner * 2);
-  const size_t o_vt = take((size_t)2 * inner * Tp * 2), o_ao = take(M * inner * 2 * ax), o_f1 = take(M * ff * 2 * ax);
+  const size_t o_vt = take((size_t)2 * U * inner * Tp * 2), o_ao = take(M * inner * 2 * ax), o_f1 = take(M * ff * 2 * ax);
   const size_t o_v = take(M * mel * 4), o_rc = take((size_t)T * 32 * 4), o_rs = take((size_t)T * 32 * 4);
   const bool grew = off > f->ws.bytes;
   uint8_t* w = (uint8_t*)f->ws.get(off);
@@ -356,14 +361,14 @@ static hvx_status flow_plan(hvx_engine* e, cudaStream_t st, int T) {
   f->h = (float*)(w + o_h); f->n16 = (__half*)(w + o_n); f->qk = (__half*)(w + o_qk); f->vt = (__half*)(w + o_vt);
   f->ao = (__half*)(w + o_ao); f->f1 = (__half*)(w + o_f1); f->v = (float*)(w + o_v);
   f->rope_c = (float*)(w + o_rc); f->rope_s = (float*)(w + o_rs);
-  if (f->T != T || f->rope_T != T) {
+  if (f->T != T || f->rope_T != T || f->U != U) {
     // the carve-up moved: V^T pad columns of the new layout may hold stale non-finite bit patterns
-    HVX_CUDA(cudaMemsetAsync(f->vt, 0, (size_t)2 * inner * Tp * 2, st));
+    HVX_CUDA(cudaMemsetAsync(f->vt, 0, (size_t)2 * U * inner * Tp * 2, st));
     flow_rope_kernel<<<cdiv(T * 32, 256), 256, 0, st>>>(f->inv_freq, f->rope_c, f->rope_s, T);
     HVX_LAUNCH_CHECK(e);
     f->rope_T = T;
   }
-  f->T = T; f->Tp = Tp;
+  f->T = T; f->Tp = Tp; f->U = U; f->klen = nullptr;
   return HVX_OK;
 }
 
@@ -385,7 +390,7 @@ static GemmEpi epi16(void* out, int ldo, const float* bias, int act) {
 static hvx_status flow_nfe(hvx_engine* e, cudaStream_t st, const float* mod, int streaming) {
   FlowState* f = e->flow;
   const hvx_config& c = e->cfg;
-  const int T = f->T, M = 2 * T, dim = c.flow_dim, inner = c.flow_heads * 64, ff = dim * c.flow_ff_mult, mel = c.flow_mel;
+  const int T = f->T, nb = 2 * f->U, M = nb * T, dim = c.flow_dim, inner = c.flow_heads * 64, ff = dim * c.flow_ff_mult, mel = c.flow_mel;
   hvx_status rc;
   // input embedding: Linear(320 -> dim) + causal grouped conv position embedding (dit.py:76-98, modules.py:115-144)
   { GemmEpi p; p.mode = EPI_F32; p.f16 = 1; p.bias = f->in_b; p.out = f->h0; p.ldo = dim; p.out2 = (__nv_bfloat16*)f->h0h;
@@ -396,7 +401,7 @@ static hvx_status flow_nfe(hvx_engine* e, cudaStream_t st, const float* mod, int
       GemmAddr gs; gs.b_kb_mod = (4 * mel) / 64;          // A = [hi | lo] against the same weights
       if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->xin, 8 * mel, (const __nv_bfloat16*)f->in_w, 4 * mel, M, dim, 8 * mel, p, &gs))) return rc;
     } }
-  GemmAddr ga; ga.n_batch = 2; ga.rows_per_batch = T; ga.a_cols = dim; ga.a_col_per_ntile = 64; ga.kb_per_tap = 1;
+  GemmAddr ga; ga.n_batch = nb; ga.rows_per_batch = T; ga.a_cols = dim; ga.a_col_per_ntile = 64; ga.kb_per_tap = 1;
   ga.a_row0 = -(c.flow_pos_k - 1); ga.a_row_step = 1;
   const int kpos = c.flow_pos_k * 64;
   const int px = f->precise ? 2 : 1;
@@ -416,7 +421,7 @@ static hvx_status flow_nfe(hvx_engine* e, cudaStream_t st, const float* mod, int
       p.vt = (__nv_bfloat16*)f->vt; p.vt_ld = f->Tp; p.T = T; p.heads = c.flow_heads; p.rows_per_batch = T;
       p.rope_cos = f->rope_c; p.rope_sin = f->rope_s;
       if ((rc = flow_linear(e, st, f->n16, b.qkv_w, M, 3 * inner, dim, p))) return rc; }
-    { AttnArgs a; a.T = T; a.heads = c.flow_heads; a.n_batch = 2; a.chunk = streaming ? c.flow_chunk : 0; a.f16 = 1;
+    { AttnArgs a; a.T = T; a.heads = c.flow_heads; a.n_batch = nb; a.klen = f->klen; a.chunk = streaming ? c.flow_chunk : 0; a.f16 = 1;
       a.ld_out = inner; a.out = (__nv_bfloat16*)f->ao; a.lo_off = f->precise ? inner : 0;
       if ((rc = dit_attention(e, st, (const __nv_bfloat16*)f->qk, 2 * inner, inner, (const __nv_bfloat16*)f->vt, f->Tp, a))) return rc; }
     { GemmEpi p; p.mode = EPI_RESID_GATE; p.f16 = 1; p.bias = b.out_b; p.out = f->h; p.ldo = dim; p.gate = m + 2 * dim;
@@ -455,60 +460,78 @@ static hvx_status flow_mods(hvx_engine* e, cudaStream_t st, const float* t_dev, 
 
 using namespace hvx;
 
-extern "C" hvx_status hvx_flow_inference(hvx_engine* e, const int32_t* tokens, int n_prompt, int n_tok, const float* embedding,
-                                         const float* prompt_feat, const float* noise, int n_timesteps, int streaming,
-                                         int finalize, float* mel_out, void* stream) {
-  HVX_CHECK(e && e->flow, HVX_ERR_STATE, "flow stage not finalized");
-  HVX_CHECK(tokens && embedding && noise && mel_out, HVX_ERR_ARG, "flow: null argument");
-  HVX_CHECK(n_timesteps >= 1 && n_timesteps <= 64, HVX_ERR_ARG, "flow: n_timesteps=%d out of range [1,64]", n_timesteps);
-  HVX_CHECK(n_prompt == 0 || prompt_feat, HVX_ERR_ARG, "flow: prompt tokens without prompt_feat");
+// One CFM solve for U utterances at once (U == 1: the reference's call shape).  Utterance u occupies frames [u*Tm, u*Tm + T_u) of
+// the ODE state; rows beyond T_u are zero padding that stays finite and is never read by a valid row: every op of the estimator
+// is row-wise, causal in time (the position-embedding conv) or key-masked per utterance (attention, klen).
+static hvx_status flow_solve(hvx_engine* e, int U, const int32_t* const* tokens, const int* n_prompt, const int* n_tok,
+                             const float* const* embedding, const float* const* prompt_feat, const float* noise, int n_timesteps,
+                             int streaming, int finalize, float* const* mel_out, cudaStream_t st) {
   FlowState* f = e->flow;
   const hvx_config& c = e->cfg;
-  cudaStream_t st = (cudaStream_t)stream;
   const int mel = c.flow_mel, dim = c.flow_dim, pc = c.flow_pla_ch;
-  const int ntok = n_prompt + n_tok;
-  const int L1 = finalize ? ntok : ntok - 3;                       // look-ahead tokens are context only (flow.py:399-403)
-  HVX_CHECK(L1 >= 1 && n_tok - (finalize ? 0 : 3) >= 1, HVX_ERR_ARG, "flow: too few tokens (%d)", n_tok);
-  const int T = 2 * L1, mel_len1 = 2 * n_prompt, T_out = T - mel_len1;
-  HVX_CHECK(T <= c.flow_noise_frames, HVX_ERR_ARG, "flow: %d frames exceed the noise table (%d)", T, c.flow_noise_frames);
   const int nmod = c.flow_depth * 6 * dim + 2 * dim;
+  std::vector<int> ntok(U), L1(U), Tu(U);
+  int Tm = 0, ntok_max = 0;
+  for (int u = 0; u < U; u++) {
+    HVX_CHECK(tokens[u] && embedding[u] && mel_out[u], HVX_ERR_ARG, "flow: null argument (utterance %d)", u);
+    HVX_CHECK(n_prompt[u] == 0 || prompt_feat[u], HVX_ERR_ARG, "flow: prompt tokens without prompt_feat (utterance %d)", u);
+    ntok[u] = n_prompt[u] + n_tok[u];
+    L1[u] = finalize ? ntok[u] : ntok[u] - 3;                     // look-ahead tokens are context only (flow.py:399-403)
+    HVX_CHECK(L1[u] >= 1 && n_tok[u] - (finalize ? 0 : 3) >= 1, HVX_ERR_ARG, "flow: too few tokens (%d)", n_tok[u]);
+    Tu[u] = 2 * L1[u];
+    HVX_CHECK(Tu[u] <= c.flow_noise_frames, HVX_ERR_ARG, "flow: %d frames exceed the noise table (%d)", Tu[u], c.flow_noise_frames);
+    Tm = std::max(Tm, Tu[u]); ntok_max = std::max(ntok_max, ntok[u]);
+  }
+  const size_t nx = (size_t)U * Tm * mel;                           // elements of the ODE state
 
   // solve-level buffers
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
   const int Cp = (mel + 63) / 64 * 64;                              // embedding rows padded to whole 64-wide k-blocks
-  const size_t o_spk = take(mel * 4), o_e32 = take((size_t)ntok * mel * 4), o_e16 = take((size_t)(ntok + 3) * Cp * 4);
-  const size_t o_y1 = take((size_t)L1 * pc * 4), o_mut = take((size_t)L1 * mel * 4);
-  const size_t o_mu = take((size_t)T * mel * 4), o_cond = take((size_t)T * mel * 4), o_x = take((size_t)T * mel * 4);
-  const size_t o_mod = take((size_t)n_timesteps * nmod * 4), o_t = take(64 * 4), o_st = take((size_t)64 * dim * 4);
+  const size_t o_spk = take((size_t)U * mel * 4), o_e32 = take((size_t)ntok_max * mel * 4), o_e16 = take((size_t)(ntok_max + 3) * Cp * 4);
+  const size_t o_y1 = take((size_t)ntok_max * pc * 4), o_mut = take((size_t)ntok_max * mel * 4);
+  const size_t o_mu = take(nx * 4), o_cond = take(nx * 4), o_x = take(nx * 4);
+  const size_t o_mod = take((size_t)n_timesteps * nmod * 4), o_t = take(64 * 4), o_st = take((size_t)64 * dim * 4), o_kl = take((size_t)2 * U * 4);
   uint8_t* w = (uint8_t*)f->ws_small.get(off);
   HVX_CHECK(w, HVX_ERR_CUDA, "flow: buffer allocation of %zu bytes failed", off);
   f->spks = (float*)(w + o_spk); f->e32 = (float*)(w + o_e32); f->e16 = (__half*)(w + o_e16); f->y1p = (__half*)(w + o_y1);
   f->mu_tok = (float*)(w + o_mut); f->mu = (float*)(w + o_mu); f->cond = (float*)(w + o_cond); f->x = (float*)(w + o_x);
   f->mod = (float*)(w + o_mod); f->t_dev = (float*)(w + o_t); f->st16 = (__half*)(w + o_st);
+  int* klen_dev = (int*)(w + o_kl);
   hvx_status rc;
-  if ((rc = flow_plan(e, st, T))) return rc;
+  if ((rc = flow_plan(e, st, Tm, U))) return rc;
+  if (U > 1) {
+    HVX_CUDA(cudaMemsetAsync(f->mu, 0, (o_x - o_mu) + al256(nx * 4), st));      // mu | cond | x are adjacent: padding frames = 0
+    std::vector<int> kl(2 * U);
+    for (int u = 0; u < U; u++) kl[u] = kl[U + u] = Tu[u];
+    HVX_CUDA(cudaMemcpyAsync(klen_dev, kl.data(), sizeof(int) * 2 * U, cudaMemcpyHostToDevice, st));
+    f->klen = klen_dev;
+  }
 
-  // ---- pre-net (flow.py:387-419)
-  flow_spk_kernel<<<1, 256, 0, st>>>(embedding, f->spk_w, f->spk_b, f->spks, c.flow_spk_in, mel);
-  HVX_LAUNCH_CHECK(e);
+  // ---- pre-net, utterance by utterance (flow.py:387-419); a few small launches each
   const int px = f->precise ? 2 : 1;
-  flow_embed_kernel<<<cdiv((ntok + 3) * Cp, 256), 256, 0, st>>>(tokens, f->emb, f->e32, f->e16, ntok, ntok + 3, mel, Cp, c.flow_vocab, f->precise);
-  HVX_LAUNCH_CHECK(e);
-  { // conv1 k4, 3 look-ahead rows (zero rows after the last token when finalize): implicit GEMM, K = 4*Cp
-    GemmEpi p = epi16(f->y1p, px * pc, f->pla1_b, ACT_LRELU);
-    p.lo_off = f->precise ? pc : 0;
-    GemmAddr ga; ga.rows_per_batch = L1; ga.a_rows = ntok + 3; ga.a_cols = px * Cp; ga.kb_per_tap = Cp / 64; ga.a_row_step = 1;
-    if (f->precise) { ga.a_lo_off = Cp; ga.split3_kb = 4 * Cp / 64; }
-    if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->e16, px * Cp, (const __nv_bfloat16*)f->pla1_w, px * 4 * Cp, L1, pc, (f->precise ? 3 : 1) * 4 * Cp, p, &ga))) return rc; }
-  { // conv2 k3 causal (left pad 2 = out-of-bounds rows) + residual
-    GemmEpi p; p.mode = EPI_F32; p.f16 = 1; p.bias = f->pla2_b; p.out = f->mu_tok; p.ldo = mel; p.resid = f->e32;
-    GemmAddr ga; ga.rows_per_batch = L1; ga.a_cols = px * pc; ga.kb_per_tap = pc / 64; ga.a_row0 = -2; ga.a_row_step = 1;
-    if (f->precise) { ga.a_lo_off = pc; ga.split3_kb = 3 * pc / 64; }
-    if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->y1p, px * pc, (const __nv_bfloat16*)f->pla2_w, px * 3 * pc, L1, mel, (f->precise ? 3 : 1) * 3 * pc, p, &ga))) return rc; }
-  flow_init_kernel<<<cdiv(T * mel, 256), 256, 0, st>>>(f->mu_tok, prompt_feat, noise, f->mu, f->cond, f->x, T, mel, mel_len1,
-                                                        c.flow_noise_frames);
-  HVX_LAUNCH_CHECK(e);
+  for (int u = 0; u < U; u++) {
+    const int nt = ntok[u], l1 = L1[u], mel_len1 = 2 * n_prompt[u];
+    flow_spk_kernel<<<1, 256, 0, st>>>(embedding[u], f->spk_w, f->spk_b, f->spks + (size_t)u * mel, c.flow_spk_in, mel);
+    HVX_LAUNCH_CHECK(e);
+    flow_embed_kernel<<<cdiv((nt + 3) * Cp, 256), 256, 0, st>>>(tokens[u], f->emb, f->e32, f->e16, nt, nt + 3, mel, Cp, c.flow_vocab, f->precise);
+    HVX_LAUNCH_CHECK(e);
+    { // conv1 k4, 3 look-ahead rows (zero rows after the last token when finalize): implicit GEMM, K = 4*Cp
+      GemmEpi p = epi16(f->y1p, px * pc, f->pla1_b, ACT_LRELU);
+      p.lo_off = f->precise ? pc : 0;
+      GemmAddr ga; ga.rows_per_batch = l1; ga.a_rows = nt + 3; ga.a_cols = px * Cp; ga.kb_per_tap = Cp / 64; ga.a_row_step = 1;
+      if (f->precise) { ga.a_lo_off = Cp; ga.split3_kb = 4 * Cp / 64; }
+      if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->e16, px * Cp, (const __nv_bfloat16*)f->pla1_w, px * 4 * Cp, l1, pc, (f->precise ? 3 : 1) * 4 * Cp, p, &ga))) return rc; }
+    { // conv2 k3 causal (left pad 2 = out-of-bounds rows) + residual
+      GemmEpi p; p.mode = EPI_F32; p.f16 = 1; p.bias = f->pla2_b; p.out = f->mu_tok; p.ldo = mel; p.resid = f->e32;
+      GemmAddr ga; ga.rows_per_batch = l1; ga.a_cols = px * pc; ga.kb_per_tap = pc / 64; ga.a_row0 = -2; ga.a_row_step = 1;
+      if (f->precise) { ga.a_lo_off = pc; ga.split3_kb = 3 * pc / 64; }
+      if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->y1p, px * pc, (const __nv_bfloat16*)f->pla2_w, px * 3 * pc, l1, mel, (f->precise ? 3 : 1) * 3 * pc, p, &ga))) return rc; }
+    const size_t xo = (size_t)u * Tm * mel;
+    flow_init_kernel<<<cdiv(Tu[u] * mel, 256), 256, 0, st>>>(f->mu_tok, prompt_feat[u], noise, f->mu + xo, f->cond + xo, f->x + xo, Tu[u], mel,
+                                                              mel_len1, c.flow_noise_frames);
+    HVX_LAUNCH_CHECK(e);
+  }
 
   // ---- cosine t-schedule carried in fp32 exactly like solve_euler (flow_matching.py:93-122,225-227)
   float ts[65], tv[64], dtv[64];
@@ -526,17 +549,43 @@ extern "C" hvx_status hvx_flow_inference(hvx_engine* e, const int32_t* tokens, i
   HVX_CUDA(cudaMemcpyAsync(f->t_dev, tv, sizeof(float) * n_timesteps, cudaMemcpyHostToDevice, st));
   if ((rc = flow_mods(e, st, f->t_dev, n_timesteps, f->st16, f->mod))) return rc;
 
-  // ---- Euler steps
+  // ---- Euler steps over all utterances of the group
+  const int Tall = U * Tm;
   for (int s = 0; s < n_timesteps; s++) {
-    dit_pack_fm_kernel<<<cdiv(2 * T * 4 * mel, 256), 256, 0, st>>>(f->x, f->cond, f->mu, f->spks, f->xin, T, mel);
+    dit_pack_fm_kernel<<<cdiv(2 * Tall * 4 * mel, 256), 256, 0, st>>>(f->x, f->cond, f->mu, f->spks, f->xin, Tall, mel, Tm);
     HVX_LAUNCH_CHECK(e);
     if ((rc = flow_nfe(e, st, f->mod + (size_t)s * nmod, streaming))) return rc;
-    flow_euler_kernel<<<cdiv(T * mel, 256), 256, 0, st>>>(f->v, f->x, T * mel, dtv[s], c.flow_cfg_rate);
+    flow_euler_kernel<<<cdiv(Tall * mel, 256), 256, 0, st>>>(f->v, f->x, Tall * mel, dtv[s], c.flow_cfg_rate);
     HVX_LAUNCH_CHECK(e);
   }
-  flow_out_kernel<<<cdiv(T_out * mel, 256), 256, 0, st>>>(f->x, mel_out, T_out, mel, mel_len1);
-  HVX_LAUNCH_CHECK(e);
+  for (int u = 0; u < U; u++) {
+    const int mel_len1 = 2 * n_prompt[u], T_out = Tu[u] - mel_len1;
+    flow_out_kernel<<<cdiv(T_out * mel, 256), 256, 0, st>>>(f->x + (size_t)u * Tm * mel, mel_out[u], T_out, mel, mel_len1);
+    HVX_LAUNCH_CHECK(e);
+  }
   return HVX_OK;
+}
+
+extern "C" hvx_status hvx_flow_inference(hvx_engine* e, const int32_t* tokens, int n_prompt, int n_tok, const float* embedding,
+                                         const float* prompt_feat, const float* noise, int n_timesteps, int streaming,
+                                         int finalize, float* mel_out, void* stream) {
+  HVX_CHECK(e && e->flow, HVX_ERR_STATE, "flow stage not finalized");
+  HVX_CHECK(tokens && embedding && noise && mel_out, HVX_ERR_ARG, "flow: null argument");
+  HVX_CHECK(n_timesteps >= 1 && n_timesteps <= 64, HVX_ERR_ARG, "flow: n_timesteps=%d out of range [1,64]", n_timesteps);
+  return flow_solve(e, 1, &tokens, &n_prompt, &n_tok, &embedding, &prompt_feat, noise, n_timesteps, streaming, finalize, &mel_out,
+                    (cudaStream_t)stream);
+}
+
+extern "C" hvx_status hvx_flow_inference_batch(hvx_engine* e, int n_utt, const int32_t* const* tokens, const int* n_prompt,
+                                               const int* n_tok, const float* const* embedding, const float* const* prompt_feat,
+                                               const float* noise, int n_timesteps, int streaming, int finalize,
+                                               float* const* mel_out, void* stream) {
+  HVX_CHECK(e && e->flow, HVX_ERR_STATE, "flow stage not finalized");
+  HVX_CHECK(tokens && n_prompt && n_tok && embedding && prompt_feat && noise && mel_out, HVX_ERR_ARG, "flow: null argument");
+  HVX_CHECK(n_utt >= 1 && n_utt <= 64, HVX_ERR_ARG, "flow: %d utterances per solve (1..64)", n_utt);
+  HVX_CHECK(n_timesteps >= 1 && n_timesteps <= 64, HVX_ERR_ARG, "flow: n_timesteps=%d out of range [1,64]", n_timesteps);
+  return flow_solve(e, n_utt, tokens, n_prompt, n_tok, embedding, prompt_feat, noise, n_timesteps, streaming, finalize, mel_out,
+                    (cudaStream_t)stream);
 }
 
 extern "C" hvx_status hvx_dit_estimator(hvx_engine* e, const float* x, const float* mu, const float* t, const float* spks,

@@ -4,6 +4,7 @@
 // F.interpolate for `speed` -> hift.inference -> .cpu().  Host<->device copies are inside the call.
 #include "common.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 namespace hvx {
@@ -117,46 +118,84 @@ extern "C" hvx_status hvx_synthesize_host(hvx_engine* e, const hvx_request* reqs
   HVX_CUDA(cudaStreamSynchronize(st));            // token counts size the next two stages
   float ms_llm = 0.f, ms_flow = 0.f, ms_hift = 0.f;
   cudaEventElapsedTime(&ms_llm, P->ev[0], P->ev[1]);
-  // ---- stages 2+3 per utterance (the reference's flow asserts batch 1, flow.py:387)
+  // ---- stage 2 in groups of similar length (one pass per Euler step for the whole group, hvx_flow_inference_batch; the
+  // reference's flow asserts batch 1, flow.py:387), stage 3 per utterance
+  std::vector<int> order;
   for (int i = 0; i < n_req; i++) {
-    const hvx_request& r = reqs[i];
-    const int n_tok = cnt[i];
-    if (n_tokens_host) n_tokens_host[i] = n_tok;
-    if (n_tok <= 0) { wav_len_host[i] = 0; continue; }
-    const int T = 2 * n_tok;
-    const int T_sp = (r.speed != 1.0f && r.speed > 0.f) ? (int)((float)T / r.speed) : T;       // int(tts_mel.shape[2] / speed)
-    HVX_CHECK(T_sp >= 1 && (size_t)T_sp * frame <= (size_t)wav_stride, HVX_ERR_ARG, "synthesize: wav_stride %d too small for %d samples",
-              wav_stride, T_sp * frame);
+    if (n_tokens_host) n_tokens_host[i] = cnt[i];
+    if (cnt[i] <= 0) wav_len_host[i] = 0; else order.push_back(i);
+  }
+  auto frames = [&](int i) { return 2 * (reqs[i].n_prompt_speech + cnt[i]); };
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return frames(x) > frames(y); });
+  static const int group_frames = getenv("HVX_FLOW_GROUP_FRAMES") ? atoi(getenv("HVX_FLOW_GROUP_FRAMES")) : 8192;   // 0: one by one
+  for (size_t g0 = 0; g0 < order.size();) {
+    // longest first; add utterances while the padded group stays under group_frames and padding under 20 %
+    const int Tmax = frames(order[g0]);
+    size_t g1 = g0 + 1;
+    while (g1 < order.size() && g1 - g0 < 16 && (int)(g1 - g0 + 1) * Tmax <= group_frames && frames(order[g1]) * 5 >= Tmax * 4) g1++;
+    const int U = (int)(g1 - g0);
     size_t m = 0;
     auto take2 = [&](size_t bytes) { size_t o = m; m += (bytes + 255) & ~(size_t)255; return o; };
-    const size_t o_all = take2(sizeof(int32_t) * (r.n_prompt_speech + n_tok)), o_mel = take2(sizeof(float) * mel * T);
-    const size_t o_mel2 = take2(sizeof(float) * mel * T_sp), o_wav = take2(sizeof(float) * (size_t)T_sp * frame);
+    std::vector<size_t> o_all(U), o_mel(U);
+    size_t max_sp = 0;
+    for (int k = 0; k < U; k++) {
+      const int i = order[g0 + k];
+      const hvx_request& r = reqs[i];
+      const int T = 2 * cnt[i];
+      const int T_sp = (r.speed != 1.0f && r.speed > 0.f) ? (int)((float)T / r.speed) : T;     // int(tts_mel.shape[2] / speed)
+      HVX_CHECK(T_sp >= 1 && (size_t)T_sp * frame <= (size_t)wav_stride, HVX_ERR_ARG, "synthesize: wav_stride %d too small for %d samples",
+                wav_stride, T_sp * frame);
+      o_all[k] = take2(sizeof(int32_t) * (r.n_prompt_speech + cnt[i]));
+      o_mel[k] = take2(sizeof(float) * mel * T);
+      max_sp = std::max(max_sp, (size_t)T_sp);
+    }
+    const size_t o_mel2 = take2(sizeof(float) * mel * max_sp), o_wav = take2(sizeof(float) * max_sp * frame);
     uint8_t* dm = (uint8_t*)P->mid.get(m);
     HVX_CHECK(dm, HVX_ERR_CUDA, "synthesize: intermediate allocation failed");
-    int32_t* all_tok = (int32_t*)(dm + o_all);
-    if (r.n_prompt_speech)
-      HVX_CUDA(cudaMemcpyAsync(all_tok, din + of[i].ps, sizeof(int32_t) * r.n_prompt_speech, cudaMemcpyDeviceToDevice, st));
-    HVX_CUDA(cudaMemcpyAsync(all_tok + r.n_prompt_speech, tok_dev + (size_t)i * max_out, sizeof(int32_t) * n_tok, cudaMemcpyDeviceToDevice, st));
-    HVX_CUDA(cudaEventRecord(P->ev[2], st));
-    float* mel_dev = (float*)(dm + o_mel);
-    if ((rc = hvx_flow_inference(e, all_tok, r.n_prompt_speech, n_tok, (const float*)(din + of[i].emb),
-                                 r.n_prompt_speech ? (const float*)(din + of[i].pf) : nullptr, noise_dev, n_timesteps, 0, 1, mel_dev, stream)))
-      return rc;
-    if (T_sp != T) {
-      if ((rc = hvx_speed_interp(e, mel_dev, mel, T, T_sp, (float*)(dm + o_mel2), stream))) return rc;
-      mel_dev = (float*)(dm + o_mel2);
+    std::vector<const int32_t*> toks(U);
+    std::vector<const float*> embs(U), pfs(U);
+    std::vector<float*> mels(U);
+    std::vector<int> np(U), nt(U);
+    for (int k = 0; k < U; k++) {
+      const int i = order[g0 + k];
+      const hvx_request& r = reqs[i];
+      int32_t* all_tok = (int32_t*)(dm + o_all[k]);
+      if (r.n_prompt_speech)
+        HVX_CUDA(cudaMemcpyAsync(all_tok, din + of[i].ps, sizeof(int32_t) * r.n_prompt_speech, cudaMemcpyDeviceToDevice, st));
+      HVX_CUDA(cudaMemcpyAsync(all_tok + r.n_prompt_speech, tok_dev + (size_t)i * max_out, sizeof(int32_t) * cnt[i], cudaMemcpyDeviceToDevice, st));
+      toks[k] = all_tok; embs[k] = (const float*)(din + of[i].emb);
+      pfs[k] = r.n_prompt_speech ? (const float*)(din + of[i].pf) : nullptr;
+      mels[k] = (float*)(dm + o_mel[k]); np[k] = r.n_prompt_speech; nt[k] = cnt[i];
     }
+    HVX_CUDA(cudaEventRecord(P->ev[2], st));
+    if (U == 1) rc = hvx_flow_inference(e, toks[0], np[0], nt[0], embs[0], pfs[0], noise_dev, n_timesteps, 0, 1, mels[0], stream);
+    else rc = hvx_flow_inference_batch(e, U, toks.data(), np.data(), nt.data(), embs.data(), pfs.data(), noise_dev, n_timesteps, 0, 1, mels.data(), stream);
+    if (rc) return rc;
     HVX_CUDA(cudaEventRecord(P->ev[3], st));
-    float* wav_dev = (float*)(dm + o_wav);
-    if ((rc = hvx_hift_vocode(e, mel_dev, T_sp, 1, sine_table_dev, nullptr, nullptr, wav_dev, nullptr, stream))) return rc;
-    HVX_CUDA(cudaMemcpyAsync(wav_host + (size_t)i * wav_stride, wav_dev, sizeof(float) * (size_t)T_sp * frame, cudaMemcpyDeviceToHost, st));
-    HVX_CUDA(cudaEventRecord(P->ev[4], st));
     HVX_CUDA(cudaStreamSynchronize(st));
-    wav_len_host[i] = T_sp * frame;
-    float a = 0.f, b = 0.f;
-    cudaEventElapsedTime(&a, P->ev[2], P->ev[3]);
-    cudaEventElapsedTime(&b, P->ev[3], P->ev[4]);
-    ms_flow += a; ms_hift += b;
+    { float a = 0.f; cudaEventElapsedTime(&a, P->ev[2], P->ev[3]); ms_flow += a; }
+    for (int k = 0; k < U; k++) {
+      const int i = order[g0 + k];
+      const hvx_request& r = reqs[i];
+      const int T = 2 * cnt[i];
+      const int T_sp = (r.speed != 1.0f && r.speed > 0.f) ? (int)((float)T / r.speed) : T;
+      float* mel_dev = mels[k];
+      HVX_CUDA(cudaEventRecord(P->ev[3], st));
+      if (T_sp != T) {
+        if ((rc = hvx_speed_interp(e, mel_dev, mel, T, T_sp, (float*)(dm + o_mel2), stream))) return rc;
+        mel_dev = (float*)(dm + o_mel2);
+      }
+      float* wav_dev = (float*)(dm + o_wav);
+      if ((rc = hvx_hift_vocode(e, mel_dev, T_sp, 1, sine_table_dev, nullptr, nullptr, wav_dev, nullptr, stream))) return rc;
+      HVX_CUDA(cudaMemcpyAsync(wav_host + (size_t)i * wav_stride, wav_dev, sizeof(float) * (size_t)T_sp * frame, cudaMemcpyDeviceToHost, st));
+      HVX_CUDA(cudaEventRecord(P->ev[4], st));
+      HVX_CUDA(cudaStreamSynchronize(st));
+      wav_len_host[i] = T_sp * frame;
+      float b = 0.f;
+      cudaEventElapsedTime(&b, P->ev[3], P->ev[4]);
+      ms_hift += b;
+    }
+    g0 = g1;
   }
   if (stage_ms_host) { stage_ms_host[0] = ms_llm; stage_ms_host[1] = ms_flow; stage_ms_host[2] = ms_hift; }
   return HVX_OK;

@@ -68,6 +68,34 @@ class NativeFlow:
         return mel, None
 
     @torch.no_grad()
+    def inference_batch(self, requests, finalize=True, streaming=False, n_timesteps=None):
+        """Several utterances in one solve (hvx_flow_inference_batch).  requests: dicts with the keyword arguments of `inference`
+        (token, embedding, prompt_token, prompt_feat).  Returns the list of mel tensors `inference` would return one by one."""
+        import ctypes as C
+        d, dev = self.dims, self.engine.device
+        U = len(requests)
+        keep, toks, embs, pfs, outs, n_p, n_t = [], [], [], [], [], [], []
+        for r in requests:
+            token, pt = r["token"], r.get("prompt_token")
+            ntok = int(token.shape[1])
+            npr = 0 if pt is None else int(pt.shape[1])
+            t = (token.reshape(-1) if npr == 0 else torch.cat([pt.reshape(-1), token.reshape(-1)])).to(dev, torch.int32).contiguous()
+            emb = r["embedding"].reshape(-1).to(dev, torch.float32).contiguous()
+            pf = None
+            if npr:
+                pf = r["prompt_feat"].reshape(-1, d.mel).to(dev, torch.float32).contiguous()
+                assert pf.shape[0] == 2 * npr
+            mel = torch.empty(1, d.mel, 2 * (ntok if finalize else ntok - 3), device=dev, dtype=torch.float32)
+            keep += [t, emb, pf]; outs.append(mel)
+            toks.append(t.data_ptr()); embs.append(emb.data_ptr()); pfs.append(0 if pf is None else pf.data_ptr())
+            n_p.append(npr); n_t.append(ntok)
+        vp, ip = C.c_void_p * U, C.c_int * U
+        L.check(L.lib().hvx_flow_inference_batch(self.engine.h, U, vp(*toks), ip(*n_p), ip(*n_t), vp(*embs), vp(*pfs), L.ptr(self.noise),
+                                                 int(n_timesteps or self.n_timesteps), int(bool(streaming)), int(bool(finalize)),
+                                                 vp(*[m.data_ptr() for m in outs]), L.stream_ptr()))
+        return outs
+
+    @torch.no_grad()
     def estimator(self, x, mask, mu, t, spks, cond, streaming=False):
         """The TensorRT seam of ConditionalCFM.forward_estimator (flow_matching.py:126-153): (2,mel,T) tensors."""
         dev = self.engine.device

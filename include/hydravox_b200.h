@@ -128,6 +128,15 @@ hvx_status hvx_flow_inference(hvx_engine* e, const int32_t* tokens_dev, int n_pr
                               const float* noise_dev, int n_timesteps, int streaming, int finalize,
                               float* mel_out_dev, void* stream);
 
+/* The same solve for n_utt utterances in ONE pass per Euler step (the reference solves one utterance per call, flow.py:387; a
+ * serving batch of similar lengths fills the tensor cores better): utterance u occupies frames [u*Tmax, u*Tmax + T_u) of the
+ * ODE state, padding frames are zero, attention keys are masked per utterance.  Arrays of n_utt host-side entries; every pointer
+ * inside them is a device pointer as in hvx_flow_inference.  Results equal the per-utterance calls. */
+hvx_status hvx_flow_inference_batch(hvx_engine* e, int n_utt, const int32_t* const* tokens_dev, const int* n_prompt,
+                                    const int* n_tok, const float* const* embedding_dev,
+                                    const float* const* prompt_feat_dev, const float* noise_dev, int n_timesteps,
+                                    int streaming, int finalize, float* const* mel_out_dev, void* stream);
+
 /* Estimator seam — replaces ConditionalCFM.forward_estimator's TensorRT branch
  * (cosyvoice/flow/flow_matching.py:126-153): x,mu,cond (2,mel,T), t (2), spks (2,mel) fp32;
  * writes dphi/dt (2,mel,T) into out_dev. */

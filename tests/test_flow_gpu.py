@@ -128,3 +128,37 @@ def test_flow_full_size_properties(flows):
     b, _ = f.inference(token=tok2, embedding=u["embedding"][None], streaming=True, n_timesteps=4)
     assert (a[:, :, :150] - b[:, :, :150]).abs().max().item() < 1e-5
     assert (a[:, :, 250:] - b[:, :, 250:]).abs().max().item() > 1e-3
+
+
+# ---------------------------------------------------------------- several utterances per solve (hvx_flow_inference_batch)
+def _utt(fd, n_tok, n_prompt, seed):
+    g = torch.Generator().manual_seed(seed)
+    r = dict(token=torch.randint(0, fd.vocab, (1, n_tok), generator=g), embedding=torch.randn(1, fd.spk_in, generator=g))
+    if n_prompt:
+        r["prompt_token"] = torch.randint(0, fd.vocab, (1, n_prompt), generator=g)
+        r["prompt_feat"] = torch.rand(1, 2 * n_prompt, fd.mel, generator=g) * 6 - 6
+    return r
+
+
+@pytest.mark.parametrize("name", ["tiny", "full"])
+@pytest.mark.parametrize("streaming", [False, True])
+def test_flow_batch_equals_one_by_one(flows, golden, name, streaming):
+    """A ragged group solved in one pass per Euler step gives every utterance the mel it gets alone (rows are independent, the
+    position-embedding conv is causal, attention keys are masked per utterance), and the fixture utterance still matches the
+    reference inside a group."""
+    e, f, fd = flows[name]
+    g = golden(f"flow_{name}")
+    reqs = [dict(token=g["token"], embedding=g["embedding"], prompt_token=g["prompt_token"], prompt_feat=g["prompt_feat"]),
+            _utt(fd, 70, 9, 1), _utt(fd, 33, 0, 2), _utt(fd, 1, 0, 3), _utt(fd, 131, 40, 4)]
+    alone = [f.inference(token=r["token"], embedding=r["embedding"], prompt_token=r.get("prompt_token"), prompt_feat=r.get("prompt_feat"),
+                         streaming=streaming, n_timesteps=g["n_steps"])[0].cpu() for r in reqs]
+    together = [m.cpu() for m in f.inference_batch(reqs, streaming=streaming, n_timesteps=g["n_steps"])]
+    for i, (a, b) in enumerate(zip(alone, together)):
+        assert a.shape == b.shape and torch.isfinite(b).all()
+        assert (a - b).abs().max().item() < 2e-5, (i, (a - b).abs().max().item())
+    ref = g["mel_stream" if streaming else "mel_full"]
+    assert (together[0] - ref).abs().max().item() < 1e-2
+    # the next single solve re-plans the workspace for one utterance
+    again = f.inference(token=reqs[1]["token"], embedding=reqs[1]["embedding"], prompt_token=reqs[1]["prompt_token"],
+                        prompt_feat=reqs[1]["prompt_feat"], streaming=streaming, n_timesteps=g["n_steps"])[0].cpu()
+    assert torch.equal(again, alone[1])
