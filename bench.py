@@ -203,14 +203,26 @@ def native_arm(a):
 
     def step_device():
         toks = llm.generate_batch(dreqs, head_k=a.head_k, u=u_dev, sampling=SAMPLING, min_ratio=a.ratio, max_ratio=a.ratio)
-        n = 0
-        for r, t in zip(dreqs, toks):
-            tk = torch.tensor(t, device=dev, dtype=torch.int32)[None]
-            mel, _ = flow.inference(token=tk, embedding=r["embedding"][None], prompt_token=r["prompt_speech"][None],
-                                    prompt_feat=r["prompt_feat"][None], n_timesteps=a.cfm_steps)
-            hift.inference(speech_feat=mel)
-            n += len(t)
-        return n
+        # flow in groups of similar length, as hvx_synthesize_host forms them (csrc/pipeline.cu: <= 8192 padded frames, <= 20 % padding)
+        items = [dict(token=torch.tensor(t, device=dev, dtype=torch.int32)[None], embedding=r["embedding"][None],
+                      prompt_token=r["prompt_speech"][None], prompt_feat=r["prompt_feat"][None]) for r, t in zip(dreqs, toks)]
+        items.sort(key=lambda it: -(it["token"].shape[1] + it["prompt_token"].shape[1]))
+        fr = lambda it: 2 * (it["token"].shape[1] + it["prompt_token"].shape[1])
+        g0 = 0
+        while g0 < len(items):
+            g1 = g0 + 1
+            while g1 < len(items) and g1 - g0 < 16 and (g1 - g0 + 1) * fr(items[g0]) <= 8192 and fr(items[g1]) * 5 >= fr(items[g0]) * 4:
+                g1 += 1
+            if g1 - g0 == 1:
+                it = items[g0]
+                mels = [flow.inference(token=it["token"], embedding=it["embedding"], prompt_token=it["prompt_token"],
+                                       prompt_feat=it["prompt_feat"], n_timesteps=a.cfm_steps)[0]]
+            else:
+                mels = flow.inference_batch(items[g0:g1], n_timesteps=a.cfm_steps)
+            for mel in mels:
+                hift.inference(speech_feat=mel)
+            g0 = g1
+        return sum(len(t) for t in toks)
 
     def step_e2e():
         wavs, toks = mm.synthesize_batch(reqs, head_k=a.head_k, sampling=SAMPLING, n_timesteps=a.cfm_steps, min_ratio=a.ratio,
