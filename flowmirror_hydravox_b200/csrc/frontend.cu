@@ -115,9 +115,32 @@ __global__ void __launch_bounds__(256) fe_sub_mean_kernel(float* __restrict__ ou
   for (int f = threadIdx.x; f < n_frames; f += 256) out[(size_t)f * n_mels + m] -= mean;
 }
 
+// whisper's dynamic-range step on a natural-log mel x (n elements): y = x * scale (log10); y = max(y, max(y) - range);
+// y = (y + add) / div   (whisper/audio.py log_mel_spectrogram).  One block: n is a few 100 k.
+__global__ void __launch_bounds__(1024) fe_whisper_post_kernel(float* __restrict__ x, int n, float scale, float range, float add, float div) {
+  __shared__ float s_red[32];
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += 1024) m = fmaxf(m, x[i] * scale);
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = s_red[0];
+  for (int i = 1; i < 32; i++) m = fmaxf(m, s_red[i]);
+  const float lo = m - range;
+  for (int i = threadIdx.x; i < n; i += 1024) x[i] = (fmaxf(x[i] * scale, lo) + add) / div;
+}
+
 }  // namespace hvx
 
 using namespace hvx;
+
+extern "C" hvx_status hvx_frontend_whisper_post(hvx_engine* e, float* logmel, int n, float scale, float range, float add, float div,
+                                                void* stream) {
+  HVX_CHECK(e && logmel && n >= 1 && div != 0.f, HVX_ERR_ARG, "frontend: bad argument");
+  fe_whisper_post_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logmel, n, scale, range, add, div);
+  HVX_LAUNCH_CHECK(e);
+  return HVX_OK;
+}
 
 extern "C" hvx_status hvx_frontend_fbank(hvx_engine* e, const float* wav, int n_samples, int frame_len, int hop, int pad_reflect,
                                          const float* basis, int n_bins, const float* fb, int n_mels, int power, float mag_eps,
@@ -127,8 +150,8 @@ extern "C" hvx_status hvx_frontend_fbank(hvx_engine* e, const float* wav, int n_
   HVX_CHECK(frame_len >= 1 && hop >= 1 && n_bins >= 1 && n_mels >= 1 && pad_reflect >= 0 && n_samples >= 1, HVX_ERR_ARG, "frontend: bad geometry");
   HVX_CHECK(pad_reflect < n_samples, HVX_ERR_ARG, "frontend: reflect padding %d needs more than %d samples", pad_reflect, n_samples);
   const int expect = (n_samples + 2 * pad_reflect - frame_len) / hop + 1;
-  HVX_CHECK(n_samples + 2 * pad_reflect >= frame_len && n_frames == expect, HVX_ERR_ARG,
-            "frontend: %d samples give %d frames, caller passed %d", n_samples, n_samples + 2 * pad_reflect >= frame_len ? expect : 0, n_frames);
+  HVX_CHECK(n_samples + 2 * pad_reflect >= frame_len && n_frames >= 1 && n_frames <= expect, HVX_ERR_ARG,
+            "frontend: %d samples give %d frames, caller asked for %d", n_samples, n_samples + 2 * pad_reflect >= frame_len ? expect : 0, n_frames);
   HVX_CHECK(!(subtract_mean && channel_major), HVX_ERR_UNSUPPORTED, "frontend: mean subtraction is built for the frame-major layout");
   HVX_CHECK((size_t)n_bins * sizeof(float) <= 48 * 1024, HVX_ERR_UNSUPPORTED, "frontend: %d bins exceed the shared-memory row", n_bins);
   cudaStream_t st = (cudaStream_t)stream;

@@ -106,11 +106,11 @@ class _Fbank:
         return (n_samples + 2 * self.pad - self.frame_len) // self.hop + 1
 
     @torch.no_grad()
-    def run(self, wav: torch.Tensor) -> torch.Tensor:
+    def run(self, wav: torch.Tensor, drop_last: int = 0) -> torch.Tensor:
         dev = self.engine.device
         w = wav.reshape(-1).to(dev, torch.float32).contiguous()
         n = int(w.numel())
-        nf = self.n_frames(n)
+        nf = self.n_frames(n) - drop_last
         if nf < 1 or self.pad >= n:
             raise ValueError(f"waveform of {n} samples is too short for {self.frame_len}-sample frames")
         out = torch.empty((self.n_mels, nf) if self.channel_major else (nf, self.n_mels), device=dev, dtype=torch.float32)
@@ -160,6 +160,26 @@ class KaldiFbank:
 
     def __call__(self, speech: torch.Tensor) -> torch.Tensor:
         return self.impl.run(speech)
+
+
+class WhisperLogMel:
+    """`whisper.log_mel_spectrogram(speech, n_mels=128)` as cosyvoice/cli/frontend.py:95 calls it (the input of the speech
+    tokenizer): 16 kHz, n_fft 400, hop 160, centred reflect-padded hann STFT, power spectrum without the last frame, slaney mel
+    filterbank, log10 with a 1e-10 floor, clamp to 8 below the maximum, (x + 4) / 4.  speech (1, n) -> (1, n_mels, n // 160).
+    whisper is a pinned dependency of the reference that is not installed here: restated from its published algorithm
+    (oracle/frontend_ref.py: whisper_log_mel), parity unpinned; `filters` may be handed over (whisper's mel_filters.npz)."""
+
+    def __init__(self, engine: "L.Engine", n_mels: int = 128, filters: torch.Tensor | None = None):
+        win = torch.hann_window(400, dtype=torch.float64)
+        fb = slaney_mel_basis(16000, 400, n_mels, 0.0, 8000.0) if filters is None else filters
+        self.impl = _Fbank(engine, dft_basis(400, torch.diag(win)), fb, 400, 160, 200, power=True, mag_eps=0.0, log_floor=1e-10,
+                           subtract_mean=False, channel_major=True)
+
+    def __call__(self, speech: torch.Tensor) -> torch.Tensor:
+        out = self.impl.run(speech, drop_last=1)                       # stft[..., :-1]
+        L.check(L.lib().hvx_frontend_whisper_post(self.impl.engine.h, L.ptr(out), int(out.numel()), C.c_float(1.0 / math.log(10.0)),
+                                                  C.c_float(8.0), C.c_float(4.0), C.c_float(4.0), L.stream_ptr()))
+        return out[None] if speech.dim() == 2 else out
 
 
 class NativeFrontendFeatures:

@@ -94,6 +94,11 @@ hvx_status hvx_frontend_fbank(hvx_engine* e, const float* wav_dev, int n_samples
                               float mag_eps, float log_floor, int subtract_mean, int channel_major, float* out_dev,
                               int n_frames, void* stream);
 
+/* Dynamic-range step of whisper.log_mel_spectrogram (called at cosyvoice/cli/frontend.py:95) on the natural-log mel that
+ * hvx_frontend_fbank wrote: y = x*scale (scale = 1/ln 10), y = max(y, max(y) - range), y = (y + add) / div, in place. */
+hvx_status hvx_frontend_whisper_post(hvx_engine* e, float* logmel_dev, int n, float scale, float range, float add, float div,
+                                     void* stream);
+
 /* ---- HiFT: replaces CausalHiFTGenerator.inference (cosyvoice/hifigan/generator.py:713-726) ----
  * mel_dev (mel, T) fp32 -> wav_dev (frame*T') fp32 clamped to +-0.99, src_dev (frame*T) source.
  * finalize=0 follows the streaming branch (:676-679,708-709,725): T' = T-3-4 frames... see DESIGN.md.

@@ -49,3 +49,13 @@ def kaldi_fbank(speech, num_mel_bins=80, sample_frequency=16000.0, frame_length=
     banks = torch.nn.functional.pad(banks, (0, 1))
     feat = torch.clamp(spec @ banks.T, min=torch.finfo(torch.float32).eps).log()
     return feat - feat.mean(dim=0, keepdim=True) if subtract_mean else feat
+
+
+def whisper_log_mel(audio, filters):
+    """whisper.log_mel_spectrogram (whisper/audio.py; called at cosyvoice/cli/frontend.py:95) restated from the published
+    algorithm — the package is not installed here, parity unpinned.  audio (n,) or (1, n); filters (n_mels, 201)."""
+    stft = torch.stft(audio, 400, 160, window=torch.hann_window(400), return_complex=True)
+    magnitudes = stft[..., :-1].abs() ** 2
+    log_spec = torch.clamp(filters @ magnitudes, min=1e-10).log10()
+    log_spec = torch.maximum(log_spec, log_spec.max() - 8.0)
+    return (log_spec + 4.0) / 4.0

@@ -62,3 +62,17 @@ def test_folded_basis_equals_oracle(golden):
     out = _folded(g["s16"][0], kb, F.kaldi_mel_banks(80, 512, 16000.0), 400, 160, 0, True, 0.0, torch.finfo(torch.float32).eps)
     out = out - out.mean(dim=0, keepdim=True)
     assert out.shape == g["fbank"].shape and (out.float() - g["fbank"]).abs().max() < 2e-3
+
+
+def test_whisper_folded_basis_equals_oracle(golden):
+    """centred reflect-padded frames x (hann . DFT) -> power -> slaney mel -> log10 / clamp / affine == the torch.stft restatement"""
+    import math
+    g = golden("frontend")
+    audio = g["s16"][0]
+    fb = F.slaney_mel_basis(16000, 400, 128, 0.0, 8000.0)
+    ref = frontend_ref.whisper_log_mel(audio, fb)
+    x = _folded(audio, F.dft_basis(400, torch.diag(torch.hann_window(400, dtype=torch.float64))), fb, 400, 160, 200, True, 0.0, 1e-10)
+    x = (x[:-1] / math.log(10.0)).T
+    x = (torch.maximum(x, x.max() - 8.0) + 4.0) / 4.0
+    assert x.shape == ref.shape == (128, audio.numel() // 160)
+    assert (x.float() - ref).abs().max() < 1e-4

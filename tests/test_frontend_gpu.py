@@ -80,3 +80,18 @@ def test_frontend_feature_objects_mirror_reference_shapes(fe, golden):
     assert f2.shape[1] == 2 * t2.shape[1] == 90
     fb = ff._extract_spk_fbank(g["s16"])
     assert fb.shape == g["fbank"].shape and abs(float(fb.mean())) < 1e-4
+
+
+@pytest.mark.parametrize("n", [400, 16000 + 33, 30 * 16000])
+def test_whisper_log_mel_vs_oracle(fe, n):
+    """hvx_frontend_fbank + hvx_frontend_whisper_post vs the restated whisper.log_mel_spectrogram (unpinned: whisper is not installed)"""
+    from oracle import frontend_ref
+    e, _, _ = fe
+    wl = F.WhisperLogMel(e)
+    s = torch.randn(1, n, generator=torch.Generator().manual_seed(n)) * 0.1
+    s[:, : n // 3] *= 1e-4                                            # a quiet stretch: exercises the max-8 clamp
+    ref = frontend_ref.whisper_log_mel(s, F.slaney_mel_basis(16000, 400, 128, 0.0, 8000.0))
+    out = wl(s).cpu()
+    assert out.shape == ref.shape == (1, 128, n // 160)
+    assert (out - ref).abs().max().item() < 1e-3, (out - ref).abs().max().item()
+    assert abs(float(out.min()) - float(ref.min())) < 1e-4            # the clamp floor itself
