@@ -308,7 +308,7 @@ def native_arm(a):
     classes = {"qkv": (1, 2.0 * QKV * H), "o_proj": (3, 2.0 * H * H), "gate_up": (4, 2.0 * 2 * I * H), "down": (5, 2.0 * H * I)}
     kern, kb, kt = {}, 0.0, 0.0
     rows = a.batch * a.head_k
-    if rows <= 32:
+    if rows <= 8:            # the single-pass weight-streaming GEMV step (above 8 rows the step runs on tcgen05 GEMMs)
         for name, (which, nbytes) in classes.items():
             L.check(L.lib().hvx_llm_bench_kernels(mm.engine.h, a.batch, a.head_k, int(ctx_avg), which, 10, ms1))
             us = ms1[0] * 1e3 / ld.layers

@@ -228,7 +228,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const int n0 = blockIdx.x * BN;
   const int batch = blockIdx.y / tiles_per_batch;
   const int m0 = (blockIdx.y - batch * tiles_per_batch) * BM;      // row inside the batch
-  const int nkb = (K + BK - 1) / BK;
+  // split-K (ad.split_k > 1, grid.z): this CTA accumulates k-blocks [kb_lo, kb_lo + nkb) and stores its partial sum to
+  // out + z * split_stride (plain EPI_F32, bias from split 0 only); the caller adds the partials in a fixed order
+  const int nkb_all = (K + BK - 1) / BK;
+  const int kb_lo = (int)(((long long)nkb_all * blockIdx.z) / gridDim.z);
+  const int nkb = (int)(((long long)nkb_all * (blockIdx.z + 1)) / gridDim.z) - kb_lo;
+  if (blockIdx.z) { epi.out = reinterpret_cast<float*>(epi.out) + (size_t)blockIdx.z * ad.split_stride; epi.bias = nullptr; }
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tma_a);
@@ -245,9 +250,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; kb++) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      for (int ki = 0; ki < nkb; ki++) {
+        const int kb = kb_lo + ki;
+        const int s = ki % STAGES;
+        const uint32_t ph = (ki / STAGES) & 1;
         tc::mbar_wait(&empty_bar[s], ph ^ 1);
         tc::mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
         uint8_t* sa = smem + s * S::STAGE_BYTES;
@@ -488,7 +494,7 @@ static hvx_status launch_gemm_t(hvx_engine* e, cudaStream_t st, const CUtensorMa
     attr_set = true;
   }
   const int tiles_per_batch = cdiv(ad.rows_per_batch, BM);
-  dim3 grid(cdiv(N, BN), tiles_per_batch * ad.n_batch);
+  dim3 grid(cdiv(N, BN), tiles_per_batch * ad.n_batch, ad.split_k);
   gemm_bf16_kernel<BN, STAGES, MODE, ACT><<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, M, N, K, epi, ad, tiles_per_batch);
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
@@ -511,6 +517,10 @@ hvx_status gemm_bf16(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* A, int
   if (ad.split3_kb && ad.a_lo_off == 0) ad.a_lo_off = ad.split3_kb * BK;
   if (ad.a_cols == 0) ad.a_cols = ad.split3_kb ? 2 * ad.split3_kb * BK : K;
   if (ad.a_rows == 0) ad.a_rows = ad.rows_per_batch;
+  if (ad.split_k < 1) ad.split_k = 1;
+  HVX_CHECK(ad.split_k == 1 || (epi.mode == EPI_F32 && !epi.resid && !epi.out2 && epi.act == ACT_NONE && ad.split_k <= (K + BK - 1) / BK &&
+                                ad.split_k <= 64 && ad.split_stride >= (size_t)M * epi.ldo),
+            HVX_ERR_ARG, "gemm: split-K needs a plain fp32 epilogue and room for %d partials", ad.split_k);
   HVX_CHECK((lda % 8) == 0 && (ldb % 8) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0, HVX_ERR_ARG,
             "gemm: operands must be 16-byte aligned with leading dims multiple of 8 (lda=%d ldb=%d)", lda, ldb);
   CUtensorMap ta, tb;
@@ -518,12 +528,12 @@ hvx_status gemm_bf16(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* A, int
   HVX_CHECK(make_tmap_bf16_3d(&ta, A, ad.n_batch, ad.a_rows, ad.a_cols, lda, BM, BK), HVX_ERR_CUDA,
             "gemm: cuTensorMapEncodeTiled(A) failed");
   // big plain GEMMs (the DiT linears): persistent 128 x 256 tiles
-  if (ad.n_batch == 1 && ad.kb_per_tap == 0 && ad.b_kb_mod == 0 && ad.a_col0 == 0 && ad.a_col_per_ntile == 0 && ad.a_row0 == 0 &&
+  if (ad.split_k == 1 && ad.n_batch == 1 && ad.kb_per_tap == 0 && ad.b_kb_mod == 0 && ad.a_col0 == 0 && ad.a_col_per_ntile == 0 && ad.a_row0 == 0 &&
       N % PBN == 0 && cdiv(M, BM) * (N / PBN) >= e->sm_count / 2 && !getenv("HVX_NO_PERSIST")) {
     HVX_CHECK(make_tmap_bf16_2d(&tb, B, N, kB, ldb, PBN, BK), HVX_ERR_CUDA, "gemm: cuTensorMapEncodeTiled(B) failed");
     return launch_gemm_persist(e, st, ta, tb, M, N, K, epi, ad);
   }
-  const int ctas128 = cdiv(N, 128) * cdiv(ad.rows_per_batch, BM) * ad.n_batch;
+  const int ctas128 = cdiv(N, 128) * cdiv(ad.rows_per_batch, BM) * ad.n_batch * ad.split_k;
   static const int min128 = getenv("HVX_GEMM_MIN_CTAS128") ? atoi(getenv("HVX_GEMM_MIN_CTAS128")) : 96;   // below: 128 x 64 tiles fill the SMs better
   if (N <= 64 || ad.a_col_per_ntile == 64 || ctas128 < min128) {
     HVX_CHECK(make_tmap_bf16_2d(&tb, B, N, kB, ldb, 64, BK), HVX_ERR_CUDA, "gemm: cuTensorMapEncodeTiled(B) failed");

@@ -67,6 +67,11 @@ struct GemmAddr {
   //   k-blocks [0,n0) -> A_hi*B_hi, [n0,2n0) -> A_lo*B_hi, [2n0,3n0) -> A_hi*B_lo   with n0 = split3_kb = K0/64 (0 = off)
   int split3_kb = 0;
   int a_lo_off = 0;            // element offset of the lo half inside an A row (0 -> split3_kb * 64); convs: the row width
+  // split-K for skinny problems (few output tiles, long K): split_k CTAs per output tile (grid.z) each accumulate a contiguous
+  // share of the k-blocks and store an fp32 partial to out + z * split_stride (EPI_F32 without resid, bias from split 0);
+  // the caller sums the partials in a fixed order (deterministic, no atomics)
+  int split_k = 1;
+  size_t split_stride = 0;
 };
 
 hvx_status gemm_bf16(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb,

@@ -1209,7 +1209,14 @@ static hvx_status launch_gemv8(hvx_engine* e, cudaStream_t st, GemvArgs a, int R
   return HVX_OK;
 }
 
-constexpr int GEMV_MAX_ROWS = 32;      // up to 4 weight passes of 8 rows beat the tensor-core path (few CTAs at small N)
+// rows <= GEMV_MAX_ROWS: weight-streaming GEMV passes of 8 rows; above: tcgen05 GEMMs on split-bf16 activations.  With the
+// split-K skinny GEMMs the tensor-core path wins from the second pass on (16 rows: 2.76 vs 3.06 ms per step), so the default is
+// one pass; HVX_GEMV_MAX_ROWS=32 restores the multi-pass GEMV (kept and tested: tests/test_llm_gpu.py sets it)
+static int gemv_max_rows() {                 // read per call: tests switch paths with the environment variable
+  const char* s = getenv("HVX_GEMV_MAX_ROWS");
+  return s ? std::max(8, std::min(32, atoi(s))) : 8;
+}
+#define GEMV_MAX_ROWS gemv_max_rows()
 
 // rows > 8: one pass over the weights per group of 8 rows
 static hvx_status launch_gemv(hvx_engine* e, cudaStream_t st, GemvArgs a, int R, int n_batch = 1) {
@@ -1226,6 +1233,7 @@ static hvx_status launch_gemv(hvx_engine* e, cudaStream_t st, GemvArgs a, int R,
 }
 
 struct StepBufs {          // per-step activations, `rows` row slots
+  size_t part_floats = 0;  // capacity of `part` (attention partials; between attention calls it holds the split-K partial sums)
   float *h, *q, *att, *act, *hn, *m_v, *m_h1, *m_act, *m_o, *logits, *part;
   __nv_bfloat16 *x16, *att16, *act16, *hn16, *m16;
   int* counters;
@@ -1243,6 +1251,7 @@ static hvx_status llm_bufs(hvx_engine* e, LlmState* L, DevBuf& buf, int rows, in
   const size_t o_mact = take(head_k * sp * MI * 4), o_mo = take(head_k * sp * H * 4), o_log = take(head_k * sp * V * 4);
   const int part_splits = std::max(splits, e->sm_count / std::max(1, c.llm_kv_heads));     // the fused step splits over all SMs
   const size_t o_part = take((size_t)rows * c.llm_q_heads * part_splits * 68 * 4), o_cnt = take((size_t)rows * c.llm_kv_heads * 4);
+  b->part_floats = (size_t)rows * c.llm_q_heads * part_splits * 68;
   const size_t o_x16 = take(rp * H * 4), o_att16 = take(rp * H * 4), o_act16 = take(std::max(rp * I, sp * MI) * 4);
   const size_t o_hn16 = take(256), o_m16 = take(sp * H * 4);        // split bf16 [hi | lo] rows
   const bool grew = off > buf.bytes;
@@ -1306,6 +1315,42 @@ static hvx_status launch_attn(hvx_engine* e, cudaStream_t st, LlmState* L, int l
   return HVX_OK;
 }
 
+// h[i] += bias-free partial sums of a split-K GEMM, added in split order (deterministic)
+__global__ void llm_splitk_reduce_kernel(float* __restrict__ h, const float* __restrict__ part, int S, size_t n4, size_t stride4) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = reinterpret_cast<float4*>(h)[i];
+  for (int z = 0; z < S; z++) {
+    const float4 p = reinterpret_cast<const float4*>(part)[(size_t)z * stride4 + i];
+    a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+  }
+  reinterpret_cast<float4*>(h)[i] = a;
+}
+
+// h (rows x H) += A16 (split bf16 [hi | lo], rows x 2K) . W^T  for the skinny N = H projections of the tcgen05 path (o-proj,
+// down-proj): 14 output tiles for 148 SMs, so the k-blocks are split over grid.z and the partials are added by
+// llm_splitk_reduce_kernel (profiles/r1c_llm_batch32_kernels.txt: these two GEMMs were 34 % of a 128-row decode step)
+static hvx_status llm_skinny_resid_gemm(hvx_engine* e, cudaStream_t st, const StepBufs& b, const __nv_bfloat16* a16, const __nv_bfloat16* w,
+                                        int rows, int H, int K) {
+  static const int want = getenv("HVX_LLM_SPLITK") ? atoi(getenv("HVX_LLM_SPLITK")) : 1;
+  GemmAddr ga; ga.b_kb_mod = K / 64;
+  const int nkb = 2 * K / 64;
+  int S = !want ? 1 : std::min(8, std::max(1, nkb / 7));              // >= 7 k-blocks per CTA
+  while (S > 1 && (size_t)S * rows * H > b.part_floats) S--;
+  if (S <= 1 || (H & 3)) {
+    GemmEpi p; p.mode = EPI_F32; p.out = b.h; p.ldo = H; p.resid = b.h;
+    return gemm_bf16(e, st, a16, 2 * K, w, K, rows, H, 2 * K, p, &ga);
+  }
+  ga.split_k = S; ga.split_stride = (size_t)rows * H;
+  GemmEpi p; p.mode = EPI_F32; p.out = b.part; p.ldo = H;
+  hvx_status rc = gemm_bf16(e, st, a16, 2 * K, w, K, rows, H, 2 * K, p, &ga);
+  if (rc) return rc;
+  const size_t n4 = (size_t)rows * H / 4;
+  llm_splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(b.h, b.part, S, n4, n4);
+  HVX_LAUNCH_CHECK(e);
+  return HVX_OK;
+}
+
 // the 24 transformer layers over `rows` row slots of b.h (in place).  rows <= 8: weight-streaming GEMVs;
 // otherwise the tcgen05 GEMM with bf16 activations.
 static hvx_status llm_layers(hvx_engine* e, cudaStream_t st, LlmState* L, const StepBufs& b, int rows, const SeqState* seqs,
@@ -1338,14 +1383,12 @@ static hvx_status llm_layers(hvx_engine* e, cudaStream_t st, LlmState* L, const 
       { GemmEpi p; p.mode = EPI_LLM_QKV; p.bias = y.qkv_b; p.llm = qe;
         if ((rc = gemm_bf16(e, st, b.x16, 2 * H, y.qkv_w, H, rows, NQKV, 2 * H, p, &gh))) return rc; }
       if ((rc = launch_attn(e, st, L, l, b, rows, seqs, rows_per_seq, seq0, pos0, splits, true))) return rc;
-      { GemmEpi p; p.mode = EPI_F32; p.out = b.h; p.ldo = H; p.resid = b.h;
-        if ((rc = gemm_bf16(e, st, b.att16, 2 * H, y.o_w, H, rows, H, 2 * H, p, &gh))) return rc; }
+      if ((rc = llm_skinny_resid_gemm(e, st, b, b.att16, y.o_w, rows, H, H))) return rc;
       llm_norm16_kernel<<<cdiv(rows, 8), 256, 0, st>>>(b.h, y.ln2, b.x16, rows, H, c.llm_eps);
       HVX_LAUNCH_CHECK(e);
       { GemmEpi p; p.mode = EPI_SWIGLU; p.out = b.act16; p.ldo = 2 * I; p.lo_off = I;
         if ((rc = gemm_bf16(e, st, b.x16, 2 * H, y.gu_w, H, rows, 2 * I, 2 * H, p, &gh))) return rc; }
-      { GemmEpi p; p.mode = EPI_F32; p.out = b.h; p.ldo = H; p.resid = b.h;
-        if ((rc = gemm_bf16(e, st, b.act16, 2 * I, y.down_w, I, rows, H, 2 * I, p, &gi))) return rc; }
+      if ((rc = llm_skinny_resid_gemm(e, st, b, b.act16, y.down_w, rows, H, I))) return rc;
     }
   }
   return HVX_OK;

@@ -138,10 +138,13 @@ def test_generate_batch_equals_single(llms):
         assert batch[i] == single
 
 
-def test_generate_batch_tensor_core_path(llms):
-    """More than 32 live rows (7 sequences x 5 heads) take the tcgen05 path (split-bf16 activations) for every decode
-    linear, 9..32 rows take several 8-row GEMV passes (4 sequences x 3 heads); each sequence must still produce the
+@pytest.mark.parametrize("max_rows", ["8", "32"])
+def test_generate_batch_tensor_core_path(llms, monkeypatch, max_rows):
+    """More than HVX_GEMV_MAX_ROWS live rows take the tcgen05 path (split-bf16 activations, split-K skinny GEMMs) for every
+    decode linear — 35 rows (7 sequences x 5 heads) always, 12 rows (4 sequences x 3 heads) with the default threshold of 8;
+    with HVX_GEMV_MAX_ROWS=32 the 12-row case takes two 8-row GEMV passes instead.  Each sequence must still produce the
     tokens it produces alone on the single-pass weight-streaming GEMV path."""
+    monkeypatch.setenv("HVX_GEMV_MAX_ROWS", max_rows)
     e, m, ld, sd = llms["tinyz"]
     from flowmirror_hydravox_b200 import _lib as L
     from flowmirror_hydravox_b200.llm import NativeLLM
