@@ -49,7 +49,7 @@ class Request(C.Structure):
         ("prompt_speech_host", C.c_void_p), ("n_prompt_speech", C.c_int),
         ("prompt_feat_host", C.c_void_p), ("embedding_host", C.c_void_p),
         ("u_host", C.c_void_p), ("n_u", C.c_int),
-        ("min_ratio", C.c_float), ("max_ratio", C.c_float), ("speed", C.c_float),
+        ("min_ratio", C.c_float), ("max_ratio", C.c_float), ("speed", C.c_double),
     ]
 
 
@@ -128,16 +128,35 @@ class Engine:
         self.h = C.c_void_p()
         check(lib().hvx_create(C.byref(self.h), C.byref(self.cfg)))
         self._keep = {0: {}, 1: {}, 2: {}, 3: {}}          # tensors borrowed by the engine
+        self._pending = {0: None, 1: None, 2: None, 3: None}   # previous tensors of a stage between set_tensors and finalize
 
-    def set_tensors(self, stage: int, tensors: dict):
+    def _register(self, stage: int, tensors: dict):
         for name, t in tensors.items():
-            t = t.to(self.device).contiguous()
-            self._keep[stage][name] = t
             shape = (C.c_int64 * t.ndim)(*t.shape)
             check(lib().hvx_set_tensor(self.h, stage, name.encode(), ptr(t), _DT[t.dtype], shape, t.ndim))
 
+    def set_tensors(self, stage: int, tensors: dict):
+        """Stage a checkpoint: upload the packed tensors and register them with the engine.  The tensors the engine was
+        serving from are kept alive until `finalize` succeeds; if it fails they are registered again, so a bad checkpoint
+        (hot swap through `load_pt`, infer_speech_model.py:169-184) never leaves the engine pointing at freed memory — the
+        reference's failed `load_state_dict` leaves the old weights in place too."""
+        new = {name: t.to(self.device).contiguous() for name, t in tensors.items()}
+        if self._pending[stage] is None:
+            self._pending[stage] = dict(self._keep[stage])          # what to fall back to
+        self._keep[stage] = {**self._keep[stage], **new}
+        self._register(stage, new)
+
     def finalize(self, stage: int):
-        check(lib().hvx_finalize(self.h, stage))
+        old, self._pending[stage] = self._pending[stage], None
+        rc = lib().hvx_finalize(self.h, stage)
+        if rc != 0:
+            msg = lib().hvx_last_error().decode()
+            if old:                                                   # roll back: re-register the previous tensors, rebuild the stage
+                torch.cuda.synchronize(self.device)
+                self._keep[stage] = old
+                self._register(stage, old)
+                lib().hvx_finalize(self.h, stage)
+            raise HvxError(f"hvx error {rc}: {msg}")
 
     def launches(self) -> int:
         return int(lib().hvx_kernel_launches(self.h))

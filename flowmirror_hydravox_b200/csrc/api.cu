@@ -68,4 +68,4 @@ extern "C" hvx_status hvx_finalize(hvx_engine* e, int stage) {
   return HVX_ERR_ARG;
 }
 
-extern "C" int64_t hvx_kernel_launches(hvx_engine* e) { return e ? e->launches : 0; }
+extern "C" int64_t hvx_kernel_launches(hvx_engine* e) { return e ? e->launches.load() : 0; }

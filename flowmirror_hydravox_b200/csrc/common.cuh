@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <cstdio>
 #include <cstdarg>
+#include <atomic>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -53,7 +55,12 @@ struct hvx_engine {
   hvx::FlowState* flow = nullptr;
   hvx::LlmState* llm = nullptr;
   hvx::UnetState* unet = nullptr;
-  int64_t launches = 0;
+  std::atomic<int64_t> launches{0};
+  // One lock per stage (LLM, flow, HiFT, U-Net): calls into DIFFERENT stages may run concurrently from different host threads
+  // (streaming: AR decode on one thread, chunked flow + vocoder on another — they touch disjoint engine state and streams);
+  // calls into the same stage serialise here.  Recursive: hvx_synthesize_host holds all of them and calls the stage entries.
+  std::recursive_mutex mu[4];
+  std::atomic<int> llm_cancel{0};  // hvx_llm_cancel: a running hvx_llm_generate stops after its current batch of steps
   hvx::DevBuf samp_ws;             // sampler tables (llm.cu)
   hvx::DevBuf fe_ws;               // frontend spectrum scratch (frontend.cu)
   void* samp_arrive = nullptr;
@@ -78,6 +85,8 @@ struct hvx_engine {
   do {                                             \
     if (!(cond)) { hvx::set_error(__VA_ARGS__); return (code); } \
   } while (0)
+
+#define HVX_LOCK(e, stage) std::lock_guard<std::recursive_mutex> _hvx_lock_##stage((e)->mu[stage])
 
 #define HVX_LAUNCH_CHECK(e)                                                                    \
   do {                                                                                         \

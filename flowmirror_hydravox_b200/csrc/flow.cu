@@ -128,6 +128,20 @@ __global__ void dit_unpack_cm_kernel(const float* __restrict__ v, float* __restr
   out[i] = v[((size_t)b * T + t) * C + c];
 }
 
+// seam tensors arrive in the flow's serving dtype (spks.dtype, flow_matching.py:99-104): fp32 <-> fp16 / bf16 staging
+__global__ void seam_cast_in_kernel(const void* __restrict__ src, float* __restrict__ dst, int n, int dtype) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dst[i] = dtype == HVX_F16 ? __half2float(reinterpret_cast<const __half*>(src)[i])
+                            : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[i]);
+}
+__global__ void seam_cast_out_kernel(const float* __restrict__ src, void* __restrict__ dst, int n, int dtype) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (dtype == HVX_F16) reinterpret_cast<__half*>(dst)[i] = __float2half_rn(src[i]);
+  else reinterpret_cast<__nv_bfloat16*>(dst)[i] = __float2bfloat16(src[i]);
+}
+
 // SinusPositionEmbedding(256) -> Linear -> SiLU -> Linear, then the SiLU every adaLN applies first
 // (modules.py:71-83,606-616,236).  One block per t value; a warp per output feature.
 __global__ void __launch_bounds__(256) flow_time_embed_kernel(const float* __restrict__ t_dev, const float* __restrict__ freqs,
@@ -570,6 +584,7 @@ extern "C" hvx_status hvx_flow_inference(hvx_engine* e, const int32_t* tokens, i
                                          const float* prompt_feat, const float* noise, int n_timesteps, int streaming,
                                          int finalize, float* mel_out, void* stream) {
   HVX_CHECK(e && e->flow, HVX_ERR_STATE, "flow stage not finalized");
+  HVX_LOCK(e, HVX_STAGE_FLOW);
   HVX_CHECK(tokens && embedding && noise && mel_out, HVX_ERR_ARG, "flow: null argument");
   HVX_CHECK(n_timesteps >= 1 && n_timesteps <= 64, HVX_ERR_ARG, "flow: n_timesteps=%d out of range [1,64]", n_timesteps);
   return flow_solve(e, 1, &tokens, &n_prompt, &n_tok, &embedding, &prompt_feat, noise, n_timesteps, streaming, finalize, &mel_out,
@@ -581,6 +596,7 @@ extern "C" hvx_status hvx_flow_inference_batch(hvx_engine* e, int n_utt, const i
                                                const float* noise, int n_timesteps, int streaming, int finalize,
                                                float* const* mel_out, void* stream) {
   HVX_CHECK(e && e->flow, HVX_ERR_STATE, "flow stage not finalized");
+  HVX_LOCK(e, HVX_STAGE_FLOW);
   HVX_CHECK(tokens && n_prompt && n_tok && embedding && prompt_feat && noise && mel_out, HVX_ERR_ARG, "flow: null argument");
   HVX_CHECK(n_utt >= 1 && n_utt <= 64, HVX_ERR_ARG, "flow: %d utterances per solve (1..64)", n_utt);
   HVX_CHECK(n_timesteps >= 1 && n_timesteps <= 64, HVX_ERR_ARG, "flow: n_timesteps=%d out of range [1,64]", n_timesteps);
@@ -591,6 +607,7 @@ extern "C" hvx_status hvx_flow_inference_batch(hvx_engine* e, int n_utt, const i
 extern "C" hvx_status hvx_dit_estimator(hvx_engine* e, const float* x, const float* mu, const float* t, const float* spks,
                                         const float* cond, int T, int streaming, float* out, void* stream) {
   HVX_CHECK(e && e->flow, HVX_ERR_STATE, "flow stage not finalized");
+  HVX_LOCK(e, HVX_STAGE_FLOW);
   HVX_CHECK(x && mu && t && spks && cond && out && T >= 1, HVX_ERR_ARG, "estimator: bad argument");
   FlowState* f = e->flow;
   const hvx_config& c = e->cfg;
@@ -611,6 +628,42 @@ extern "C" hvx_status hvx_dit_estimator(hvx_engine* e, const float* x, const flo
   HVX_LAUNCH_CHECK(e);
   if ((rc = flow_nfe(e, st, mod, streaming))) return rc;
   dit_unpack_cm_kernel<<<cdiv(2 * T * mel, 256), 256, 0, st>>>(f->v, out, T, mel);
+  HVX_LAUNCH_CHECK(e);
+  return HVX_OK;
+}
+
+// The reference's own estimator plug-in seam, exactly as ConditionalCFM.forward_estimator drives a TensorRT context
+// (cosyvoice/flow/flow_matching.py:126-153): raw device addresses of x (2, mel, T), mu, t (2), spks (2, mel), cond in the flow's
+// serving dtype (spks.dtype: fp32, fp16 or bf16), the result written to out_dev — which the reference binds to x itself (7th
+// address = x.data_ptr(): in place).  kind 0 = DiT estimator (stage FLOW), 1 = U-Net estimator (stage UNET).
+extern "C" hvx_status hvx_estimator_seam(hvx_engine* e, int kind, const void* x, const void* mu, const void* t, const void* spks,
+                                         const void* cond, void* out, int T, int dtype, int streaming, void* stream) {
+  HVX_CHECK(e && (kind == 0 ? (e->flow != nullptr) : (e->unet != nullptr)), HVX_ERR_STATE, "estimator seam: stage not finalized");
+  HVX_CHECK(x && mu && t && spks && cond && out && T >= 1, HVX_ERR_ARG, "estimator seam: bad argument");
+  HVX_CHECK(dtype == HVX_F32 || dtype == HVX_F16 || dtype == HVX_BF16, HVX_ERR_ARG, "estimator seam: dtype %d (fp32, fp16 or bf16)", dtype);
+  auto run = [&](const float* x32, const float* mu32, const float* t32, const float* s32, const float* c32, float* o32) {
+    return kind == 0 ? hvx_dit_estimator(e, x32, mu32, t32, s32, c32, T, streaming, o32, stream)
+                     : hvx_unet_estimator(e, x32, mu32, t32, s32, c32, T, streaming, o32, stream);
+  };
+  if (dtype == HVX_F32)          // in place is safe: x is consumed by the pack kernel before the unpack kernel writes (stream order)
+    return run((const float*)x, (const float*)mu, (const float*)t, (const float*)spks, (const float*)cond, (float*)out);
+  const int mel = kind == 0 ? e->cfg.flow_mel : e->cfg.unet_mel;
+  const size_t nx = (size_t)2 * mel * T, ns = (size_t)2 * mel;
+  static DevBuf seam_ws;         // one engine per process
+  float* w = (float*)seam_ws.get((4 * nx + ns + 2 + 64) * sizeof(float));
+  HVX_CHECK(w, HVX_ERR_CUDA, "estimator seam: staging allocation failed");
+  float *x32 = w, *mu32 = w + nx, *c32 = w + 2 * nx, *o32 = w + 3 * nx, *s32 = w + 4 * nx, *t32 = s32 + ns;
+  cudaStream_t st = (cudaStream_t)stream;
+  const void* src[5] = {x, mu, cond, spks, t};
+  float* dst[5] = {x32, mu32, c32, s32, t32};
+  const size_t cnt[5] = {nx, nx, nx, ns, 2};
+  for (int i = 0; i < 5; i++) {
+    seam_cast_in_kernel<<<cdiv((int)cnt[i], 256), 256, 0, st>>>(src[i], dst[i], (int)cnt[i], dtype);
+    HVX_LAUNCH_CHECK(e);
+  }
+  hvx_status rc = run(x32, mu32, t32, s32, c32, o32);
+  if (rc) return rc;
+  seam_cast_out_kernel<<<cdiv((int)nx, 256), 256, 0, st>>>(o32, out, (int)nx, dtype);
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
 }

@@ -446,8 +446,10 @@ static hvx_status run_resblock(hvx_engine* e, cudaStream_t st, const ResBlockW& 
 using namespace hvx;
 
 extern "C" hvx_status hvx_hift_vocode(hvx_engine* e, const float* mel, int T, int finalize, const float* table,
-                                      const float* f0_in, float* f0_out, float* wav, float* src, void* stream) {
+                                      int64_t n_table_rows, const float* f0_in, float* f0_out, float* wav, float* src, void* stream) {
   HVX_CHECK(e && e->hift, HVX_ERR_STATE, "hift stage not finalized");
+  HVX_LOCK(e, HVX_STAGE_HIFT);
+  HVX_CHECK(mel && table && wav, HVX_ERR_ARG, "hift: null argument");
   const hvx_config& c = e->cfg;
   HiftState* h = e->hift;
   cudaStream_t st = (cudaStream_t)stream;
@@ -458,6 +460,8 @@ extern "C" hvx_status hvx_hift_vocode(hvx_engine* e, const float* mel, int T, in
   const int Tx = finalize ? T : T - 7;             // generator.py:676-679,725
   HVX_CHECK(Tx >= 1 && (finalize || Tx >= 2), HVX_ERR_ARG, "hift: T=%d too short", T);
   const int Ns = Tf0 * frame;                      // source samples
+  HVX_CHECK((int64_t)Ns <= n_table_rows, HVX_ERR_ARG, "hift: the utterance needs %d sine-table rows, the table holds %lld (SineGen2.sine_waves, generator.py:226,306)",
+            Ns, (long long)n_table_rows);
   const int Fs = Ns / 4 + 1;                       // stft frames of the source
   const int F = Tx * up_prod + 1;                  // frames entering the ISTFT
   const int n_out = finalize ? Tx * frame : (Tx - 1) * frame;
@@ -553,6 +557,7 @@ extern "C" hvx_status hvx_hift_vocode(hvx_engine* e, const float* mel, int T, in
 extern "C" hvx_status hvx_hift_t_vocode(hvx_engine* e, const float* mel, int T, const float* noise, const float* cache_source,
                                         int n_cache, const float* f0_in, float* f0_out, float* wav, float* src, void* stream) {
   HVX_CHECK(e && e->hift, HVX_ERR_STATE, "hift stage not finalized");
+  HVX_LOCK(e, HVX_STAGE_HIFT);
   const hvx_config& c = e->cfg;
   HiftState* h = e->hift;
   cudaStream_t st = (cudaStream_t)stream;
@@ -650,6 +655,7 @@ extern "C" hvx_status hvx_hift_t_vocode(hvx_engine* e, const float* mel, int T, 
 // conv_post; stage count / rates / kernel sizes from hvx_config.hift_* (no F0, source or ISTFT head on this variant).
 extern "C" hvx_status hvx_hifigan_vocode(hvx_engine* e, const float* mel, int T, float* wav, void* stream) {
   HVX_CHECK(e && mel && wav && T >= 1, HVX_ERR_ARG, "hifigan: bad arguments (T=%d)", T);
+  HVX_LOCK(e, HVX_STAGE_HIFT);
   const hvx_config& c = e->cfg;
   HVX_CHECK(c.hift_n_ups >= 1 && c.hift_n_ups <= 4 && c.hift_n_rb >= 1 && c.hift_n_rb <= 3 && c.hift_n_dil >= 1 && c.hift_n_dil <= 4,
             HVX_ERR_UNSUPPORTED, "hifigan: %d stages x %d resblocks x %d dilations unsupported", c.hift_n_ups, c.hift_n_rb, c.hift_n_dil);

@@ -1568,6 +1568,7 @@ using namespace hvx;
 extern "C" hvx_status hvx_llm_begin(hvx_engine* e, int seq, const int32_t* text_ids, int n_text_total, int n_text_new,
                                     const int32_t* prompt_speech, int n_prompt_speech, float min_ratio, float max_ratio) {
   HVX_CHECK(e && e->llm, HVX_ERR_STATE, "llm stage not finalized");
+  HVX_LOCK(e, HVX_STAGE_LLM);
   HVX_CHECK(seq >= 0 && seq < e->cfg.llm_max_seqs, HVX_ERR_ARG, "llm_begin: sequence slot %d out of range", seq);
   HVX_CHECK(text_ids && n_text_total >= n_text_new && n_text_new >= 0 && (n_prompt_speech == 0 || prompt_speech), HVX_ERR_ARG,
             "llm_begin: bad arguments");
@@ -1618,6 +1619,7 @@ static hvx_status llm_prefill(hvx_engine* e, cudaStream_t st, LlmState* L, int n
 extern "C" hvx_status hvx_llm_generate(hvx_engine* e, int n_seq, int head_k, const hvx_sampler* sp, const float* u_dev,
                                        int u_stride, int32_t* out_tokens, int max_out, int32_t* out_counts, void* stream) {
   HVX_CHECK(e && e->llm, HVX_ERR_STATE, "llm stage not finalized");
+  HVX_LOCK(e, HVX_STAGE_LLM);
   HVX_CHECK(sp && u_dev && out_tokens && out_counts, HVX_ERR_ARG, "llm_generate: null argument");
   const hvx_config& c = e->cfg;
   HVX_CHECK(n_seq >= 1 && n_seq <= c.llm_max_seqs, HVX_ERR_ARG, "llm_generate: n_seq=%d exceeds max_seqs=%d", n_seq, c.llm_max_seqs);
@@ -1625,6 +1627,7 @@ extern "C" hvx_status hvx_llm_generate(hvx_engine* e, int n_seq, int head_k, con
   HVX_CHECK(sp->top_k >= 1 && sp->top_k <= SAMP_MAXK, HVX_ERR_UNSUPPORTED, "sampler: top_k=%d outside [1,%d]", sp->top_k, SAMP_MAXK);
   LlmState* L = e->llm;
   cudaStream_t user = (cudaStream_t)stream, st = L->own;
+  e->llm_cancel.store(0);
   HVX_CUDA(cudaEventRecord(L->ev_in, user));
   HVX_CUDA(cudaStreamWaitEvent(st, L->ev_in, 0));
   const int rows = n_seq * head_k;
@@ -1692,7 +1695,7 @@ extern "C" hvx_status hvx_llm_generate(hvx_engine* e, int n_seq, int head_k, con
     memcpy(L->graph_key, key, sizeof(key));
     L->graph_samp = sa;
     e->graph_launches = e->launches - l0;
-    e->launches = l0;
+    e->launches -= e->graph_launches;
   }
   for (int step = 0; step < max_steps;) {
     const int n = std::min(poll, max_steps - step);
@@ -1701,7 +1704,7 @@ extern "C" hvx_status hvx_llm_generate(hvx_engine* e, int n_seq, int head_k, con
     step += n;
     HVX_CUDA(cudaMemcpyAsync(L->n_active_host, L->n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
     HVX_CUDA(cudaStreamSynchronize(st));
-    if (*L->n_active_host <= 0) break;
+    if (*L->n_active_host <= 0 || e->llm_cancel.load()) break;
   }
   }
   // surface sampler failures the way the reference raises (llm_multi_head_v3.py:165)
@@ -1718,10 +1721,19 @@ extern "C" hvx_status hvx_llm_generate(hvx_engine* e, int n_seq, int head_k, con
   return HVX_OK;
 }
 
+// Asks a hvx_llm_generate running on another host thread to return after its current batch of decode steps (<= 16) with the
+// tokens emitted so far.  Deliberately takes no stage lock.
+extern "C" hvx_status hvx_llm_cancel(hvx_engine* e) {
+  HVX_CHECK(e, HVX_ERR_ARG, "llm_cancel: null engine");
+  e->llm_cancel.store(1);
+  return HVX_OK;
+}
+
 // Teacher-forced probe: prefill sequence slot `seq` and return the final-normed last hidden state and the
 // log-softmax of every MTP head on it (llm_multi_head_v3.py:883-888).
 extern "C" hvx_status hvx_llm_probe(hvx_engine* e, int seq, float* last_hidden, float* head_logp, void* stream) {
   HVX_CHECK(e && e->llm, HVX_ERR_STATE, "llm stage not finalized");
+  HVX_LOCK(e, HVX_STAGE_LLM);
   HVX_CHECK(seq == 0, HVX_ERR_UNSUPPORTED, "llm_probe: only sequence slot 0 is supported");
   const hvx_config& c = e->cfg;
   LlmState* L = e->llm;
@@ -1773,6 +1785,7 @@ __global__ void llm_debug_rows_kernel(const __nv_bfloat16* __restrict__ semb, fl
 extern "C" hvx_status hvx_llm_debug_step(hvx_engine* e, int head_k, int ctx, int use_fused, int n_layers, float* h_out_dev,
                                          float* logits_out_dev) {
   HVX_CHECK(e && e->llm && h_out_dev, HVX_ERR_ARG, "llm_debug_step: bad argument");
+  HVX_LOCK(e, HVX_STAGE_LLM);
   hvx_config& c = e->cfg;
   HVX_CHECK(head_k >= 1 && head_k <= c.llm_mtp_heads && ctx >= 1 && ctx + head_k < c.llm_max_ctx, HVX_ERR_ARG, "llm_debug_step: bad shape");
   LlmState* L = e->llm;
@@ -1821,6 +1834,7 @@ extern "C" hvx_status hvx_llm_debug_step(hvx_engine* e, int head_k, int ctx, int
 // ms_out[0] = milliseconds per repetition (one repetition = all layers' kernels of that class)
 extern "C" hvx_status hvx_llm_bench_kernels(hvx_engine* e, int n_seq, int head_k, int ctx, int which, int reps, float* ms_out) {
   HVX_CHECK(e && e->llm && ms_out && reps >= 1, HVX_ERR_ARG, "llm_bench_kernels: bad argument");
+  HVX_LOCK(e, HVX_STAGE_LLM);
   const hvx_config& c = e->cfg;
   HVX_CHECK(n_seq >= 1 && n_seq <= c.llm_max_seqs && n_seq * head_k <= GEMV_MAX_ROWS && ctx + head_k < c.llm_max_ctx, HVX_ERR_ARG, "llm_bench_kernels: bad shape");
   LlmState* L = e->llm;

@@ -26,8 +26,21 @@ __global__ void speed_interp_kernel(const float* __restrict__ x, float* __restri
 
 struct PipeState {
   DevBuf in, mid;
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // start, llm end, flow start, flow end, utterance end
+  cudaEvent_t ev[2] = {nullptr, nullptr};      // start, llm end
+  std::vector<cudaEvent_t> gev;                // per flow group: flow start, flow end (= vocoder start), vocoder end
+  cudaEvent_t group_event(size_t i) {
+    while (gev.size() <= i) { cudaEvent_t x = nullptr; if (cudaEventCreate(&x) != cudaSuccess) return nullptr; gev.push_back(x); }
+    return gev[i];
+  }
 };
+
+// int(tts_mel.shape[2] / speed) evaluated like the reference does, on doubles, and never below one frame
+// (infer_speech_model.py:584-587: F.interpolate(size=max(1, int(T / speed))))
+static inline int speed_frames(int T, double speed) {
+  if (speed == 1.0 || !(speed > 0.0)) return T;
+  const int t = (int)((double)T / speed);
+  return t < 1 ? 1 : t;
+}
 static PipeState* g_pipe = nullptr;      // one engine per process (server/worker.py:25-44)
 
 }  // namespace hvx
@@ -42,10 +55,11 @@ extern "C" hvx_status hvx_speed_interp(hvx_engine* e, const float* mel_dev, int 
 }
 
 extern "C" hvx_status hvx_synthesize_host(hvx_engine* e, const hvx_request* reqs, int n_req, int head_k, const hvx_sampler* sp,
-                                          int n_timesteps, const float* noise_dev, const float* sine_table_dev, float* wav_host,
-                                          int wav_stride, int32_t* wav_len_host, int32_t* tokens_host, int tok_stride,
+                                          int n_timesteps, const float* noise_dev, const float* sine_table_dev, int64_t n_table_rows,
+                                          float* wav_host, int wav_stride, int32_t* wav_len_host, int32_t* tokens_host, int tok_stride,
                                           int32_t* n_tokens_host, float* stage_ms_host, void* stream) {
   HVX_CHECK(e && e->llm && e->flow && e->hift, HVX_ERR_STATE, "synthesize: all three stages must be finalized");
+  HVX_LOCK(e, HVX_STAGE_LLM); HVX_LOCK(e, HVX_STAGE_FLOW); HVX_LOCK(e, HVX_STAGE_HIFT);
   HVX_CHECK(reqs && sp && noise_dev && sine_table_dev && wav_host && wav_len_host, HVX_ERR_ARG, "synthesize: null argument");
   HVX_CHECK(n_req >= 1 && n_req <= e->cfg.llm_max_seqs, HVX_ERR_ARG, "synthesize: n_req=%d exceeds max_seqs=%d", n_req, e->cfg.llm_max_seqs);
   const hvx_config& c = e->cfg;
@@ -119,7 +133,9 @@ extern "C" hvx_status hvx_synthesize_host(hvx_engine* e, const hvx_request* reqs
   float ms_llm = 0.f, ms_flow = 0.f, ms_hift = 0.f;
   cudaEventElapsedTime(&ms_llm, P->ev[0], P->ev[1]);
   // ---- stage 2 in groups of similar length (one pass per Euler step for the whole group, hvx_flow_inference_batch; the
-  // reference's flow asserts batch 1, flow.py:387), stage 3 per utterance
+  // reference's flow asserts batch 1, flow.py:387), stage 3 per utterance.  Everything below is stream-ordered: the group
+  // workspace is reused by the next group only after this group's vocoder passes and D2H copies, which were enqueued before
+  // it; the host waits once, at the end.
   std::vector<int> order;
   for (int i = 0; i < n_req; i++) {
     if (n_tokens_host) n_tokens_host[i] = cnt[i];
@@ -127,8 +143,16 @@ extern "C" hvx_status hvx_synthesize_host(hvx_engine* e, const hvx_request* reqs
   }
   auto frames = [&](int i) { return 2 * (reqs[i].n_prompt_speech + cnt[i]); };
   std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return frames(x) > frames(y); });
+  // every utterance is validated before any of stage 2 is enqueued
+  for (int i : order) {
+    const int T_sp = speed_frames(2 * cnt[i], reqs[i].speed);
+    HVX_CHECK((size_t)T_sp * frame <= (size_t)wav_stride, HVX_ERR_ARG, "synthesize: wav_stride %d too small for %d samples", wav_stride, T_sp * frame);
+    HVX_CHECK((int64_t)T_sp * frame <= n_table_rows, HVX_ERR_ARG, "synthesize: request %d needs %lld sine-table rows, the table holds %lld",
+              i, (long long)T_sp * frame, (long long)n_table_rows);
+  }
   static const int group_frames = getenv("HVX_FLOW_GROUP_FRAMES") ? atoi(getenv("HVX_FLOW_GROUP_FRAMES")) : 8192;   // 0: one by one
-  for (size_t g0 = 0; g0 < order.size();) {
+  size_t n_groups = 0;
+  for (size_t g0 = 0; g0 < order.size(); n_groups++) {
     // longest first; add utterances while the padded group stays under group_frames and padding under 20 %
     const int Tmax = frames(order[g0]);
     size_t g1 = g0 + 1;
@@ -136,20 +160,21 @@ extern "C" hvx_status hvx_synthesize_host(hvx_engine* e, const hvx_request* reqs
     const int U = (int)(g1 - g0);
     size_t m = 0;
     auto take2 = [&](size_t bytes) { size_t o = m; m += (bytes + 255) & ~(size_t)255; return o; };
-    std::vector<size_t> o_all(U), o_mel(U);
-    size_t max_sp = 0;
+    std::vector<size_t> o_all(U), o_mel(U), o_mel2(U), o_wav(U);
     for (int k = 0; k < U; k++) {
       const int i = order[g0 + k];
       const hvx_request& r = reqs[i];
       const int T = 2 * cnt[i];
-      const int T_sp = (r.speed != 1.0f && r.speed > 0.f) ? (int)((float)T / r.speed) : T;     // int(tts_mel.shape[2] / speed)
-      HVX_CHECK(T_sp >= 1 && (size_t)T_sp * frame <= (size_t)wav_stride, HVX_ERR_ARG, "synthesize: wav_stride %d too small for %d samples",
-                wav_stride, T_sp * frame);
+      const int T_sp = speed_frames(T, r.speed);
       o_all[k] = take2(sizeof(int32_t) * (r.n_prompt_speech + cnt[i]));
       o_mel[k] = take2(sizeof(float) * mel * T);
-      max_sp = std::max(max_sp, (size_t)T_sp);
+      o_mel2[k] = T_sp != T ? take2(sizeof(float) * mel * T_sp) : 0;
+      o_wav[k] = take2(sizeof(float) * (size_t)T_sp * frame);
     }
-    const size_t o_mel2 = take2(sizeof(float) * mel * max_sp), o_wav = take2(sizeof(float) * max_sp * frame);
+    cudaEvent_t ev_a = P->group_event(3 * n_groups), ev_b = P->group_event(3 * n_groups + 1), ev_c = P->group_event(3 * n_groups + 2);
+    HVX_CHECK(ev_a && ev_b && ev_c, HVX_ERR_CUDA, "synthesize: event creation failed");
+    // the workspace may move when it grows: everything enqueued so far must have drained first (rare: the first call of a shape)
+    if (m > P->mid.bytes) HVX_CUDA(cudaStreamSynchronize(st));
     uint8_t* dm = (uint8_t*)P->mid.get(m);
     HVX_CHECK(dm, HVX_ERR_CUDA, "synthesize: intermediate allocation failed");
     std::vector<const int32_t*> toks(U);
@@ -167,35 +192,35 @@ extern "C" hvx_status hvx_synthesize_host(hvx_engine* e, const hvx_request* reqs
       pfs[k] = r.n_prompt_speech ? (const float*)(din + of[i].pf) : nullptr;
       mels[k] = (float*)(dm + o_mel[k]); np[k] = r.n_prompt_speech; nt[k] = cnt[i];
     }
-    HVX_CUDA(cudaEventRecord(P->ev[2], st));
+    HVX_CUDA(cudaEventRecord(ev_a, st));
     if (U == 1) rc = hvx_flow_inference(e, toks[0], np[0], nt[0], embs[0], pfs[0], noise_dev, n_timesteps, 0, 1, mels[0], stream);
     else rc = hvx_flow_inference_batch(e, U, toks.data(), np.data(), nt.data(), embs.data(), pfs.data(), noise_dev, n_timesteps, 0, 1, mels.data(), stream);
     if (rc) return rc;
-    HVX_CUDA(cudaEventRecord(P->ev[3], st));
-    HVX_CUDA(cudaStreamSynchronize(st));
-    { float a = 0.f; cudaEventElapsedTime(&a, P->ev[2], P->ev[3]); ms_flow += a; }
+    HVX_CUDA(cudaEventRecord(ev_b, st));
     for (int k = 0; k < U; k++) {
       const int i = order[g0 + k];
       const hvx_request& r = reqs[i];
       const int T = 2 * cnt[i];
-      const int T_sp = (r.speed != 1.0f && r.speed > 0.f) ? (int)((float)T / r.speed) : T;
+      const int T_sp = speed_frames(T, r.speed);
       float* mel_dev = mels[k];
-      HVX_CUDA(cudaEventRecord(P->ev[3], st));
       if (T_sp != T) {
-        if ((rc = hvx_speed_interp(e, mel_dev, mel, T, T_sp, (float*)(dm + o_mel2), stream))) return rc;
-        mel_dev = (float*)(dm + o_mel2);
+        if ((rc = hvx_speed_interp(e, mel_dev, mel, T, T_sp, (float*)(dm + o_mel2[k]), stream))) return rc;
+        mel_dev = (float*)(dm + o_mel2[k]);
       }
-      float* wav_dev = (float*)(dm + o_wav);
-      if ((rc = hvx_hift_vocode(e, mel_dev, T_sp, 1, sine_table_dev, nullptr, nullptr, wav_dev, nullptr, stream))) return rc;
+      float* wav_dev = (float*)(dm + o_wav[k]);
+      if ((rc = hvx_hift_vocode(e, mel_dev, T_sp, 1, sine_table_dev, n_table_rows, nullptr, nullptr, wav_dev, nullptr, stream))) return rc;
       HVX_CUDA(cudaMemcpyAsync(wav_host + (size_t)i * wav_stride, wav_dev, sizeof(float) * (size_t)T_sp * frame, cudaMemcpyDeviceToHost, st));
-      HVX_CUDA(cudaEventRecord(P->ev[4], st));
-      HVX_CUDA(cudaStreamSynchronize(st));
       wav_len_host[i] = T_sp * frame;
-      float b = 0.f;
-      cudaEventElapsedTime(&b, P->ev[3], P->ev[4]);
-      ms_hift += b;
     }
+    HVX_CUDA(cudaEventRecord(ev_c, st));
     g0 = g1;
+  }
+  HVX_CUDA(cudaStreamSynchronize(st));
+  for (size_t g = 0; g < n_groups; g++) {
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, P->gev[3 * g], P->gev[3 * g + 1]);
+    cudaEventElapsedTime(&b, P->gev[3 * g + 1], P->gev[3 * g + 2]);
+    ms_flow += a; ms_hift += b;
   }
   if (stage_ms_host) { stage_ms_host[0] = ms_llm; stage_ms_host[1] = ms_flow; stage_ms_host[2] = ms_hift; }
   return HVX_OK;

@@ -446,7 +446,7 @@ static hvx_status unet_estimate(hvx_engine* e, const float* x, const float* mu, 
     cudaGraphDestroy(g);
     HVX_CHECK(ce == cudaSuccess, HVX_ERR_CUDA, "unet: graph instantiate failed: %s", cudaGetErrorString(ce));
     u->glaunches = e->launches - l0;
-    e->launches = l0;
+    e->launches -= u->glaunches;
     u->gkey = key;
   }
   HVX_CUDA(cudaEventRecord(u->ev_in, user));
@@ -460,6 +460,8 @@ static hvx_status unet_estimate(hvx_engine* e, const float* x, const float* mu, 
 
 extern "C" hvx_status hvx_unet_estimator(hvx_engine* e, const float* x, const float* mu, const float* t, const float* spks,
                                          const float* cond, int T, int streaming, float* out, void* stream) {
+  HVX_CHECK(e, HVX_ERR_ARG, "unet_estimator: null engine");
+  HVX_LOCK(e, HVX_STAGE_UNET);
   return unet_estimate(e, x, mu, t, spks, cond, T, streaming, out, (cudaStream_t)stream);
 }
 
@@ -497,6 +499,7 @@ extern "C" hvx_status hvx_cfm_solve_unet(hvx_engine* e, const float* mu, const f
                                          int noise_ld, int T, int n_timesteps, float temperature, int streaming, float* mel_out,
                                          void* stream) {
   HVX_CHECK(e && e->unet, HVX_ERR_STATE, "unet stage not finalized");
+  HVX_LOCK(e, HVX_STAGE_UNET);
   HVX_CHECK(mu && noise && mel_out && T >= 1 && T <= noise_ld, HVX_ERR_ARG, "cfm_solve_unet: bad argument (T=%d, noise table %d frames)", T, noise_ld);
   HVX_CHECK(n_timesteps >= 1 && n_timesteps <= 64, HVX_ERR_ARG, "cfm_solve_unet: n_timesteps=%d out of range [1,64]", n_timesteps);
   UnetState* u = e->unet;
@@ -542,5 +545,7 @@ extern "C" hvx_status hvx_cfm_solve_unet(hvx_engine* e, const float* mu, const f
 extern "C" hvx_status hvx_unet_estimator_debug(hvx_engine* e, const float* x, const float* mu, const float* t, const float* spks,
                                                const float* cond, int T, int streaming, float* out, float* dump_dev, int n_dump,
                                                void* stream) {
+  HVX_CHECK(e, HVX_ERR_ARG, "unet_estimator_debug: null engine");
+  HVX_LOCK(e, HVX_STAGE_UNET);
   return unet_run(e, x, mu, t, spks, cond, T, streaming, out, dump_dev, n_dump, (cudaStream_t)stream);
 }

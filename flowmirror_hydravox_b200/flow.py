@@ -107,12 +107,15 @@ class NativeFlow:
         return out
 
 
-class NativeUNetEstimator:
+class NativeUNetEstimator(torch.nn.Module):
     """Drop-in for `CausalConditionalDecoder` (cosyvoice/flow/decoder.py:294-494) as ConditionalCFM.estimator: the call
     `estimator(x, mask, mu, t, spks, cond, streaming=...)` of flow_matching.py:128 on (2, mel, T) CFG-stacked tensors.
+    It is an `nn.Module` (without parameters: the weights live in the engine), so it can be assigned over the registered
+    submodule `flow.decoder.estimator` and `forward_estimator` takes its nn.Module branch (flow_matching.py:127-128).
     Build the engine with `ud=dims.UNET_FULL`; `Engine(flow_precise=True)` selects the three-term split-fp16 parity mode."""
 
     def __init__(self, engine: "L.Engine"):
+        super().__init__()
         if engine.ud is None:
             raise L.HvxError("engine was created without U-Net dims (Engine(ud=dims.UNET_FULL))")
         self.engine = engine
@@ -152,9 +155,8 @@ class NativeUNetEstimator:
         else:
             L.check(L.lib().hvx_unet_estimator_debug(self.engine.h, *[L.ptr(a) for a in args], T, int(bool(streaming)), L.ptr(out),
                                                      L.ptr(_dump), int(_dump.shape[0]), L.stream_ptr()))
-        return out
+        return out if out.dtype == x.dtype or x.dtype not in (torch.float16, torch.bfloat16) else out.to(x.dtype)   # the seam's dtype (spks.dtype)
 
-    __call__ = forward
 
 
 class NativeUNetCFM:
@@ -200,3 +202,104 @@ class NativeUNetCFM:
         return out, None
 
     __call__ = forward
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The reference's innermost plug-in seam (SURVEY 8b "innermost"): ConditionalCFM.forward_estimator
+# (cosyvoice/flow/flow_matching.py:126-153) treats an estimator that is NOT an nn.Module as a pool of TensorRT execution
+# contexts (TrtContextWrapper, cosyvoice/utils/common.py:198-213; installed by CosyVoice2Model.load_trt,
+# cosyvoice/cli/model.py:82-98):
+#     [context, stream], engine = pool.acquire_estimator()
+#     with stream: context.set_input_shape(name, shape) x6; context.set_tensor_address(engine.get_tensor_name(i), ptr) x7;
+#                  assert context.execute_async_v3(cuda_stream_handle) is True
+#     pool.release_estimator(context, stream)        # result is read from x: the 7th address is x.data_ptr()
+# NativeEstimatorPool is that object backed by hvx_estimator_seam.
+_SEAM_NAMES = ("x", "mask", "mu", "t", "spks", "cond", "estimator_out")     # bin/export_onnx.py:77-78 input/output names
+
+
+class _SeamEngine:
+    """the part of a tensorrt.ICudaEngine forward_estimator touches"""
+    num_io_tensors = len(_SEAM_NAMES)
+
+    def get_tensor_name(self, i: int) -> str:
+        return _SEAM_NAMES[i]
+
+
+class _SeamContext:
+    """the part of a tensorrt.IExecutionContext forward_estimator touches"""
+
+    def __init__(self, pool: "NativeEstimatorPool"):
+        self.pool = pool
+        self.shapes, self.addrs = {}, {}
+
+    def set_input_shape(self, name: str, shape) -> bool:
+        if name not in _SEAM_NAMES[:6]:
+            raise ValueError(f"unknown estimator input {name!r}")
+        self.shapes[name] = tuple(int(s) for s in shape)
+        return True
+
+    def set_tensor_address(self, name: str, addr: int) -> bool:
+        if name not in _SEAM_NAMES:
+            raise ValueError(f"unknown estimator tensor {name!r}")
+        self.addrs[name] = int(addr)
+        return True
+
+    def bound(self):
+        """validate what forward_estimator bound; returns (T, addresses by name)"""
+        p = self.pool
+        mel = p.mel
+        shp = self.shapes
+        missing = [n for n in _SEAM_NAMES if n not in self.addrs] + [n for n in _SEAM_NAMES[:6] if n not in shp]
+        if missing:
+            raise L.HvxError(f"estimator seam: tensors not bound: {sorted(set(missing))}")
+        T = shp["x"][2]
+        if shp["x"] != (2, mel, T) or shp["mu"] != (2, mel, T) or shp["cond"] != (2, mel, T) or shp["mask"] != (2, 1, T) \
+                or shp["t"] != (2,) or shp["spks"] != (2, mel):
+            raise L.HvxError(f"estimator seam: shapes {shp} are not the CFG batch of solve_euler (flow_matching.py:99-104)")
+        if not p.min_T <= T <= p.max_T:               # the TensorRT profile of cli/model.py:93-98
+            raise L.HvxError(f"estimator seam: T={T} outside the profile [{p.min_T}, {p.max_T}]")
+        return T, self.addrs
+
+    def execute_async_v3(self, stream_handle: int) -> bool:
+        import ctypes as C
+        p = self.pool
+        T, a = self.bound()
+        vp = C.c_void_p
+        L.check(L.lib().hvx_estimator_seam(p.engine.h, p.kind, vp(a["x"]), vp(a["mu"]), vp(a["t"]), vp(a["spks"]), vp(a["cond"]),
+                                           vp(a["estimator_out"]), int(T), L._DT[p.dtype], int(bool(p.streaming)),
+                                           vp(int(stream_handle))))
+        return True
+
+
+class NativeEstimatorPool:
+    """Drop-in for `TrtContextWrapper` (cosyvoice/utils/common.py:198-213): assign it to `flow.decoder.estimator` after deleting
+    the nn.Module (`del flow.decoder.estimator`, exactly as load_trt does at cli/model.py:86) and the reference's own
+    `ConditionalCFM.forward_estimator` drives the B200 estimator through raw pointers, in place into `x`.
+
+    owner: a NativeFlow (DiT estimator) or NativeUNetEstimator whose weights are loaded.  dtype: the dtype of the seam tensors =
+    the flow module's dtype (`spks.dtype`; the reference serves in fp16, infer_speech_model.py:105-117).  The TensorRT seam does
+    not carry `streaming` (the mask is baked into the engine); set `pool.streaming = True` for the chunk-mask estimator."""
+
+    def __init__(self, owner, dtype: torch.dtype = torch.float32, trt_concurrent: int = 1, streaming: bool = False,
+                 min_T: int = 1, max_T: int = 15000, context_cls=None, stream_factory=None):
+        """context_cls / stream_factory: test hooks (tests/test_seam_cpu.py drives the reference's forward_estimator through
+        this pool on a CPU box with a context whose execute step is the reference's own nn.Module)."""
+        import queue
+        self.engine = owner.engine
+        self.kind = 1 if isinstance(owner, NativeUNetEstimator) else 0
+        self.mel = owner.dims.mel
+        if dtype not in (torch.float32, torch.float16, torch.bfloat16):
+            raise ValueError(f"estimator seam dtype {dtype}: fp32, fp16 or bf16")
+        self.dtype, self.streaming, self.min_T, self.max_T = dtype, streaming, min_T, max_T
+        self.trt_engine = _SeamEngine()
+        self.trt_context_pool = queue.Queue(maxsize=trt_concurrent)
+        context_cls = context_cls or _SeamContext
+        stream_factory = stream_factory or (lambda: torch.cuda.stream(torch.cuda.Stream(self.engine.device)))
+        for _ in range(trt_concurrent):
+            self.trt_context_pool.put([context_cls(self), stream_factory()])
+
+    def acquire_estimator(self):
+        return self.trt_context_pool.get(), self.trt_engine
+
+    def release_estimator(self, context, stream):
+        self.trt_context_pool.put([context, stream])

@@ -56,7 +56,7 @@ class NativeHiFT:
         f0_out = torch.empty(Tf0, device=dev, dtype=torch.float32)
         f0_in = None if f0 is None else f0.reshape(-1).to(dev, torch.float32).contiguous()
         L.check(L.lib().hvx_hift_vocode(self.engine.h, L.ptr(mel), T, int(bool(finalize)), L.ptr(self.sine_table),
-                                        L.ptr(f0_in), L.ptr(f0_out), L.ptr(wav), L.ptr(src), L.stream_ptr()))
+                                        C.c_int64(int(self.sine_table.shape[0])), L.ptr(f0_in), L.ptr(f0_out), L.ptr(wav), L.ptr(src), L.stream_ptr()))
         if return_f0:
             return wav, src, f0_out
         return wav, src

@@ -157,7 +157,7 @@ class ModelManager:
                 keep.append(t_pf)
             a.embedding_host, a.u_host, a.n_u = t_emb.data_ptr(), t_u.data_ptr(), int(u.shape[1])
             a.min_ratio, a.max_ratio, a.speed = mn, mx, float(r.get("speed", 1.0))
-            if a.speed <= 0:
+            if not a.speed > 0:
                 raise ValueError(f"Invalid speed: {a.speed}")
             keep += [t_text, t_ps, t_emb, t_u]
         min_speed = min(min(float(r.get("speed", 1.0)) for r in requests), 1.0)
@@ -171,7 +171,7 @@ class ModelManager:
         self.h2d_bytes = sum(int(a.n_text_total) * 4 + int(a.n_prompt_speech) * 4 * (1 + 2 * e.fd.mel) + e.fd.spk_in * 4 + int(a.n_u) * 4
                              for a in arr)
         L.check(L.lib().hvx_synthesize_host(e.h, arr, n, head_k, C.byref(sp), steps, L.ptr(flow.noise), L.ptr(hift.sine_table),
-                                            C.c_void_p(wav.data_ptr()), wav_stride, C.c_void_p(wav_len.data_ptr()),
+                                            C.c_int64(int(hift.sine_table.shape[0])), C.c_void_p(wav.data_ptr()), wav_stride, C.c_void_p(wav_len.data_ptr()),
                                             C.c_void_p(toks.data_ptr()), max_tok, C.c_void_p(n_toks.data_ptr()),
                                             C.c_void_p(ms.data_ptr()), L.stream_ptr()))
         self.last_stage_ms = dict(llm=float(ms[0]), flow=float(ms[1]), hift=float(ms[2]))

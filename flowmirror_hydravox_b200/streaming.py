@@ -6,7 +6,10 @@ Mirrors the upstream streaming orchestration the reference vendors in cosyvoice/
   * every ``token_hop_len`` (25) tokens (+ ``pre_lookahead_len`` 3, + the prompt padding on the first chunk) the flow is
     re-run over *all tokens so far* with ``streaming=True, finalize=False`` and the new mel frames are appended to a cache;
   * the vocoder is re-run over the cached mel with ``finalize=False`` and only the new samples are emitted;
-  * the last call uses ``finalize=True``.
+  * the last call uses ``finalize=True`` and — because ``CosyVoice2Model.tts`` does not pass ``stream`` to that last
+    ``token2wav`` (:352-358) — ``streaming=False``: the final mel is computed under full attention, not the chunk mask.
+One request at a time per synthesizer (a lock serialises ``tts``); a consumer that abandons the generator (client disconnect)
+cancels the decode (``hvx_llm_cancel``) and joins the LLM thread before the token buffers and sequence slot 0 can be reused.
 The reference polls the token list every 100 ms (:334); here the consumer watches the device-side token counter that the
 on-device sampler advances every step, so the first chunk starts as soon as its 28 tokens exist.
 """
@@ -32,6 +35,7 @@ class StreamingSynthesizer:
         self.side = torch.cuda.Stream(self.dev)           # flow + vocoder + counter polling; the LLM has its own stream
         self._cnt_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self._bufs = {}
+        self._lock = threading.Lock()                     # the engine has one LLM sequence slot 0 and one set of token buffers per shape
 
     def _poll(self, cnt: torch.Tensor) -> int:
         with torch.cuda.stream(self.side):
@@ -45,6 +49,10 @@ class StreamingSynthesizer:
             debug: Optional[Dict] = None) -> Generator[Dict, None, None]:
         """request: dict with text, prompt_text, prompt_speech, prompt_feat, embedding (CPU or device tensors).
         Yields {'tts_speech': (1, n) CPU tensor} chunks exactly like CosyVoice2Model.tts(stream=True)."""
+        with self._lock:
+            yield from self._tts(request, head_k, sampling, n_timesteps, min_ratio, max_ratio, u, debug)
+
+    def _tts(self, request, head_k, sampling, n_timesteps, min_ratio, max_ratio, u, debug):
         mm, dev = self.mm, self.dev
         llm, flow, hift = mm.models["llm"], mm.models["flow"], mm.models["hift"]
         n_new = int(request["text"].numel())
@@ -81,8 +89,9 @@ class StreamingSynthesizer:
         def token2wav(n_tok: int, finalize: bool):
             nonlocal mel_cache, speech_offset
             with torch.cuda.stream(self.side):
+                # the reference's last token2wav call omits `stream` (cli/model.py:352-358): full attention on the final pass
                 mel, _ = flow.inference(token=out[:, :n_tok], embedding=emb, prompt_token=ptok, prompt_feat=pfeat,
-                                        streaming=True, finalize=finalize, n_timesteps=n_timesteps)
+                                        streaming=not finalize, finalize=finalize, n_timesteps=n_timesteps)
                 mel = mel[:, :, token_offset * 2:]
                 mel_cache = mel if mel_cache is None else torch.cat([mel_cache, mel], dim=2)
                 wav, _ = hift.inference(speech_feat=mel_cache, finalize=finalize)
@@ -95,33 +104,38 @@ class StreamingSynthesizer:
             return res
 
         first = True
-        while True:
-            this_hop = hop + prompt_pad if token_offset == 0 else hop
+        try:
+            while True:
+                this_hop = hop + prompt_pad if token_offset == 0 else hop
+                n = self._poll(cnt)
+                alive = th.is_alive()
+                if n - token_offset >= this_hop + la:
+                    wav = token2wav(token_offset + this_hop + la, finalize=False)
+                    token_offset += this_hop
+                    if first and debug is not None:
+                        debug["first_audio_ms"] = (time.perf_counter() - t_start) * 1e3
+                    first = False
+                    yield {"tts_speech": wav}
+                    continue
+                if not alive:
+                    n = self._poll(cnt)
+                    if n - token_offset < this_hop + la:
+                        break
+                    continue
+                time.sleep(0.0002)
+            th.join()
+            if err:
+                raise err[0]
             n = self._poll(cnt)
-            alive = th.is_alive()
-            if n - token_offset >= this_hop + la:
-                wav = token2wav(token_offset + this_hop + la, finalize=False)
-                token_offset += this_hop
+            if debug is not None:
+                debug["tokens"] = out[0, :n].cpu().tolist()
+                debug["mel_cache"] = lambda: mel_cache
+            if n > 0:
+                wav = token2wav(n, finalize=True)
                 if first and debug is not None:
                     debug["first_audio_ms"] = (time.perf_counter() - t_start) * 1e3
-                first = False
                 yield {"tts_speech": wav}
-                continue
-            if not alive:
-                n = self._poll(cnt)
-                if n - token_offset < this_hop + la:
-                    break
-                continue
-            time.sleep(0.0002)
-        th.join()
-        if err:
-            raise err[0]
-        n = self._poll(cnt)
-        if debug is not None:
-            debug["tokens"] = out[0, :n].cpu().tolist()
-            debug["mel_cache"] = lambda: mel_cache
-        if n > 0:
-            wav = token2wav(n, finalize=True)
-            if first and debug is not None:
-                debug["first_audio_ms"] = (time.perf_counter() - t_start) * 1e3
-            yield {"tts_speech": wav}
+        finally:
+            if th.is_alive():                  # generator abandoned or failed mid-stream: stop the decode before anything is reused
+                L.check(L.lib().hvx_llm_cancel(mm.engine.h))
+                th.join()

@@ -14,8 +14,12 @@
  *     (pinned for best throughput) — the *_host entry points include the H2D/D2H copies;
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); calls are
  *     stream-ordered and do not synchronise unless they return host data;
- *   - one engine per process/GPU, not thread-safe (the reference runs one worker per GPU,
- *     server/worker.py:25-44).
+ *   - one engine per process/GPU (the reference runs one worker per GPU, server/worker.py:25-44).  Threading contract:
+ *     every stage (LLM, flow, HiFT, U-Net) has its own lock inside the engine; entry points of DIFFERENT stages may be
+ *     called concurrently from different host threads on different streams (the streaming path does: AR decode on one
+ *     thread, chunked flow + vocoder on another, cosyvoice/cli/model.py:315-360); calls into the same stage serialise.
+ *     hvx_synthesize_host takes all three locks for its duration.  hvx_set_tensor / hvx_finalize must not run concurrently
+ *     with any compute call.
  */
 #ifndef HYDRAVOX_B200_H
 #define HYDRAVOX_B200_H
@@ -102,10 +106,11 @@ hvx_status hvx_frontend_whisper_post(hvx_engine* e, float* logmel_dev, int n, fl
 /* ---- HiFT: replaces CausalHiFTGenerator.inference (cosyvoice/hifigan/generator.py:713-726) ----
  * mel_dev (mel, T) fp32 -> wav_dev (frame*T') fp32 clamped to +-0.99, src_dev (frame*T) source.
  * finalize=0 follows the streaming branch (:676-679,708-709,725): T' = T-3-4 frames... see DESIGN.md.
- * sine_table_dev: SineGen2.sine_waves rows (n_samples, harmonics) uniform[0,1) (generator.py:226).
+ * sine_table_dev: SineGen2.sine_waves rows (n_table_rows, harmonics) uniform[0,1) (generator.py:226); the call fails with
+ * HVX_ERR_ARG when the utterance needs more rows than the table holds (the reference raises on the shape mismatch at :306).
  * f0_in_dev (optional, T): pins the F0 track (parity tests); f0_out_dev (optional, T) receives it. */
 hvx_status hvx_hift_vocode(hvx_engine* e, const float* mel_dev, int T, int finalize,
-                           const float* sine_table_dev, const float* f0_in_dev, float* f0_out_dev,
+                           const float* sine_table_dev, int64_t n_table_rows, const float* f0_in_dev, float* f0_out_dev,
                            float* wav_dev, float* src_dev, void* stream);
 
 /* ---- HiFT, transposed-conv variant: replaces HiFTGenerator.inference (cosyvoice/hifigan/generator.py:557-569; decode
@@ -161,6 +166,17 @@ hvx_status hvx_unet_estimator_debug(hvx_engine* e, const float* x_dev, const flo
                                     const float* spks_dev, const float* cond_dev, int T, int streaming,
                                     float* out_dev, float* dump_dev, int n_dump, void* stream);
 
+/* The reference's own plug-in seam, as ConditionalCFM.forward_estimator drives a TensorRT execution context
+ * (cosyvoice/flow/flow_matching.py:126-153, pool object cosyvoice/utils/common.py:198-213): raw device addresses in the flow's
+ * serving dtype (spks.dtype: HVX_F32, HVX_F16 or HVX_BF16) for x (2, mel, T), mu, t (2), spks (2, mel), cond; the result goes to
+ * out_dev, which the reference binds to x itself (its 7th address is x.data_ptr()), so out_dev == x_dev is allowed.  The seam's
+ * mask is all-true at inference (flow_matching.py:104-111) and is not an argument.  kind 0: DiT estimator, 1: U-Net estimator.
+ * flowmirror_hydravox_b200/flow.py: NativeEstimatorPool wraps this as acquire_estimator()/release_estimator() + a context with
+ * set_input_shape / set_tensor_address / execute_async_v3. */
+hvx_status hvx_estimator_seam(hvx_engine* e, int kind, const void* x_dev, const void* mu_dev, const void* t_dev,
+                              const void* spks_dev, const void* cond_dev, void* out_dev, int T, int dtype, int streaming,
+                              void* stream);
+
 /* CFM Euler solve over the U-Net estimator — replaces CausalConditionalCFM.forward + ConditionalCFM.solve_euler
  * (cosyvoice/flow/flow_matching.py:203-228,71-124) when the estimator is the U-Net: z = noise[:, :T] * temperature, cosine
  * t-schedule, per step CFG staging (row 1 has mu/spks/cond zeroed), estimator, v = (1+cfg)*v0 - cfg*v1, x += dt*v.
@@ -184,6 +200,10 @@ hvx_status hvx_llm_begin(hvx_engine* e, int seq, const int32_t* text_ids_dev, in
 hvx_status hvx_llm_generate(hvx_engine* e, int n_seq, int head_k, const hvx_sampler* sp,
                             const float* u_dev, int u_stride, int32_t* out_tokens_dev, int max_out,
                             int32_t* out_counts_dev, void* stream);
+/* Ask a hvx_llm_generate that is running on another host thread to stop after its current batch of decode steps (<= 16) and
+ * return the tokens emitted so far — an abandoned streaming request (client disconnect) must not keep writing into the
+ * token buffers the next request reuses.  Lock-free; the next hvx_llm_generate clears the flag. */
+hvx_status hvx_llm_cancel(hvx_engine* e);
 /* Teacher-forced probe for parity tests: final-normed hidden of the last prompt row and the
  * log-softmax of every MTP head on it (llm_multi_head_v3.py:886-888). */
 hvx_status hvx_llm_probe(hvx_engine* e, int seq, float* last_hidden_dev, float* head_logp_dev, void* stream);
@@ -202,11 +222,12 @@ typedef struct hvx_request {
   const float* prompt_feat_host;                                         /* (2*n_prompt_speech, mel) or NULL */
   const float* embedding_host;                                           /* (spk_in) */
   const float* u_host;               int n_u;
-  float min_ratio, max_ratio, speed;
+  float min_ratio, max_ratio;
+  double speed;   /* double: the reference evaluates int(T / speed) on Python floats (infer_speech_model.py:584-587) */
 } hvx_request;
 hvx_status hvx_synthesize_host(hvx_engine* e, const hvx_request* reqs, int n_req, int head_k,
                                const hvx_sampler* sp, int n_timesteps, const float* noise_dev,
-                               const float* sine_table_dev, float* wav_host, int wav_stride,
+                               const float* sine_table_dev, int64_t n_table_rows, float* wav_host, int wav_stride,
                                int32_t* wav_len_host, int32_t* tokens_host, int tok_stride,
                                int32_t* n_tokens_host, float* stage_ms_host, void* stream);
 

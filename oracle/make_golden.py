@@ -68,6 +68,88 @@ def golden_hift(name, dims, T, seed):
                     sd_checksum=checksum(sd)), os.path.join(OUT, f"hift_{name}.pt"))
 
 
+def c2_hift_mel(dims, T, seed):
+    """the mel of the config-2 size HiFT fixture (regenerated from the seed by the test: a CPU generator is bit-reproducible)"""
+    g = torch.Generator().manual_seed(seed + 100)
+    return torch.rand(1, dims.mel, T, generator=g) * 6.0 - 6.0
+
+
+def golden_hift_c2(dims, T, seed):
+    """BASELINE config-2 size (1024 speech tokens -> 2048 mel frames = 40.96 s): the reference module's waveform and its
+    CPU-fp32 F0 track.  Only wav + f0 are stored (3.9 MB); mel and the sine table are regenerated from their seeds."""
+    m = refshim.build_hift(dims)
+    sd = synth.hift_state_dict(dims, seed)
+    m.load_state_dict(sd, strict=True)
+    table = synth.hift_sine_table(dims, T)
+    m.m_source.l_sin_gen.sine_waves = table[None]
+    mel = c2_hift_mel(dims, T, seed)
+    wav, _ = m.inference(speech_feat=mel, finalize=True)
+    f0 = m.f0_predictor(mel)
+    wav_o, _ = hift_ref.inference(sd, mel, table, dims, f0=f0)
+    e = (wav - wav_o).abs().max().item()
+    rms = (wav - wav_o).pow(2).mean().sqrt().item()
+    wav_free, _ = hift_ref.inference(sd, mel, table, dims)
+    rms_free = (wav - wav_free).pow(2).mean().sqrt().item()
+    print(f"[hift:c2] T={T} ref-vs-oracle wav max-abs {e:.2e} rms {rms:.2e} (F0 pinned); rms {rms_free:.2e} (oracle's own F0); "
+          f"voiced {(f0 > 10).float().mean():.2f}")
+    assert e < 2e-5
+    torch.save(dict(dims="c2", seed=seed, T=T, wav=wav, f0=f0, oracle_free_f0_rms=rms_free, sd_checksum=checksum(sd)),
+               os.path.join(OUT, "hift_c2.pt"))
+
+
+def golden_llm_c2(dims, seed, n_text=128, n_ptext=16, P=125, K=2, ratio=8, depths=(0, 1, 64, 255, 511)):
+    """BASELINE config-2 size: 16 + 128 text tokens, 125 prompt speech tokens, inference_head_num=2, fixed-length protocol
+    (min = max ratio 8 -> 1024 speech tokens) through the UNMODIFIED CosyVoice3LM.inference (no KV cache: ~300 TFLOP
+    on the CPU).  Weights are the synthetic checkpoint rounded to bf16 (what the engine holds; the reference serves in bf16,
+    infer_speech_model.py:102) evaluated in fp32, stop logits zeroed (synth.llm_state_dict eos_scale=0) as in bench.py.
+    Stored: the 1024 token ids, and the teacher-forced head log-probs of the reference modules at several depths."""
+    from cosyvoice.utils.common import ras_sampling
+    sp = dict(top_p=0.9, top_k=10, win_size=24, tau_r=0.2)
+    m = refshim.build_llm(dims)
+    sd = {k: v.to(torch.bfloat16).float() for k, v in synth.llm_state_dict(dims, seed, eos_scale=0.0).items()}
+    m.load_state_dict(sd, strict=True)
+    u0 = synth.utterance(dims, D.FLOW_FULL, n_text, seed=1986, prompt_tokens=P, prompt_text=n_ptext)
+    text, ptext, pspeech = u0["text"].long()[None], u0["prompt_text"].long()[None], u0["prompt_speech"].long()[None]
+    u = torch.rand(8192, generator=torch.Generator().manual_seed(seed + 7))
+    m.sampling = partial(ras_sampling, **sp)
+    m.inference_head_num = K
+    us = llm_ref.UStream(u)
+    orig = torch.Tensor.multinomial
+    torch.Tensor.multinomial = lambda self, n, replacement=False: torch.tensor([llm_ref.multinomial_u(self, us.next())])
+    import time
+    t0 = time.time()
+    try:
+        ref = list(m.inference(text=text, text_len=torch.tensor([n_text]), prompt_text=ptext, prompt_text_len=torch.tensor([n_ptext]),
+                               prompt_speech_token=pspeech, prompt_speech_token_len=torch.tensor([P]), embedding=None,
+                               min_token_text_ratio=ratio, max_token_text_ratio=ratio))
+    finally:
+        torch.Tensor.multinomial = orig
+    t_ref = time.time() - t0
+    ora, logps = llm_ref.inference(sd, dims, text[0], ptext[0], pspeech[0], u, head_k=K, sp=sp, min_ratio=ratio, max_ratio=ratio,
+                                   return_logp=True)
+    n_same = next((i for i, (a, b) in enumerate(zip(ref, ora)) if a != b), min(len(ref), len(ora)))
+    print(f"[llm:c2] reference {len(ref)} tokens in {t_ref:.0f} s (u used {us.pos}); oracle {len(ora)}, common prefix {n_same}")
+    assert len(ref) == n_text * ratio
+    # teacher-forced head log-probs from the reference modules at several decode depths (step s: 2*s tokens already emitted)
+    o = llm_ref.LlmOracle(sd, dims)
+    emb = sd["speech_embedding.weight"]
+    lp_ref, e_max = {}, 0.0
+    for s_ in depths:
+        lm_in = torch.cat([o.prompt_embeds(text[0], ptext[0], pspeech[0]), emb[torch.tensor(ref[: K * s_], dtype=torch.long)]], 0)[None]
+        y, _ = m.llm.forward_one_step(lm_in, masks=torch.tril(torch.ones(1, lm_in.shape[1], lm_in.shape[1])).bool())
+        last = y[:, -1:, :]
+        lp = torch.stack([m.llm_decoder(m.mtp_block[j](last)[0][:, -1]).log_softmax(-1)[0] for j in range(K)])
+        lp_ref[s_] = lp
+        if n_same >= K * s_:
+            e_max = max(e_max, (lp - logps[s_][:K]).abs().max().item())
+    print(f"[llm:c2] teacher-forced head log-probs at steps {list(depths)}: reference-vs-oracle max-abs {e_max:.2e}")
+    assert e_max < 5e-4
+    torch.save(dict(dims="c2", seed=seed, n_text=n_text, n_ptext=n_ptext, P=P, K=K, ratio=ratio, sp=sp, text=text[0], prompt_text=ptext[0],
+                    prompt_speech=pspeech[0], u=u, tokens=ref, oracle_tokens=ora, oracle_common_prefix=n_same, depths=list(depths),
+                    head_logp={int(k): v for k, v in lp_ref.items()}, u_used=us.pos, sd_checksum=checksum(sd)),
+               os.path.join(OUT, "llm_c2.pt"))
+
+
 def golden_hift_t(name, dims, T, seed):
     """a12': the non-causal ConvTranspose1d HiFTGenerator.  Its source module is stochastic (fresh noise + random initial
     phase per call): the fixture pins decode(mel, s) for an explicit source s, the F0 predictor, and the whole
@@ -201,7 +283,9 @@ def golden_frontend(seed):
     torch.save(dict(seed=seed, y24=y, mel=mel, s16=s16, fbank=fb), os.path.join(OUT, "frontend.pt"))
 
 
-def golden_flow(name, dims, N, P, n_steps, seed):
+def golden_flow(name, dims, N, P, n_steps, seed, modes=("full", "stream", "chunk"), with_est=True, with_bf16=True):
+    """modes/with_est/with_bf16 trim the work for the BASELINE config-2 size fixture (`c2`: 1024 + 125 tokens -> 2298 frames,
+    25 Euler steps: one fp32 solve of the reference is several CPU-minutes)."""
     refshim.install()
     import cosyvoice.flow.flow as flowmod
     flowmod.torch = _TorchF32Proxy()
@@ -222,36 +306,41 @@ def golden_flow(name, dims, N, P, n_steps, seed):
               prompt_token_len=torch.tensor([P]), prompt_feat=pfeat, prompt_feat_len=torch.tensor([2 * P]))
     out = {}
     for key, streaming, finalize in (("full", False, True), ("stream", True, True), ("chunk", True, False)):
+        if key not in modes:
+            continue
         ref, _ = m.inference(finalize=finalize, streaming=streaming, **kw)
         ora = flow_ref.inference(sd, tok, emb, noise, dims, n_steps, ptok, pfeat, streaming=streaming, finalize=finalize)
         e = (ref - ora).abs().max().item()
         print(f"[flow:{name}] {key} mel {tuple(ref.shape)} ref-vs-oracle max-abs {e:.2e} mean|mel| {ref.abs().mean():.3f}")
         assert e < 2e-4
         out["mel_" + key] = ref
-    # one estimator call (the TRT seam, flow_matching.py:126-153) for kernel-level parity
-    T = 2 * (N + P)
-    xg = torch.randn(2, dims.mel, T, generator=g)
-    mug = torch.randn(2, dims.mel, T, generator=g)
-    cg = torch.randn(2, dims.mel, T, generator=g)
-    sg = torch.randn(2, dims.mel, generator=g)
-    tg = torch.tensor([0.3, 0.3])
-    est = m.decoder.estimator(xg, torch.ones(2, 1, T), mug, tg, sg, cg, streaming=False)
-    est_o = flow_ref.dit_forward(sd, xg, mug, tg, sg, cg, dims)
-    assert (est - est_o).abs().max().item() < 1e-4
-    # what the reference's own low-precision path loses against fp32 (parity budget)
-    mb = refshim.build_flow(dims, dtype=torch.bfloat16)
-    mb.load_state_dict({k: v.to(torch.bfloat16) for k, v in sd.items()}, strict=True)
+    extra = {}
+    if with_est:
+        # one estimator call (the TRT seam, flow_matching.py:126-153) for kernel-level parity
+        T = 2 * (N + P)
+        xg = torch.randn(2, dims.mel, T, generator=g)
+        mug = torch.randn(2, dims.mel, T, generator=g)
+        cg = torch.randn(2, dims.mel, T, generator=g)
+        sg = torch.randn(2, dims.mel, generator=g)
+        tg = torch.tensor([0.3, 0.3])
+        est = m.decoder.estimator(xg, torch.ones(2, 1, T), mug, tg, sg, cg, streaming=False)
+        est_o = flow_ref.dit_forward(sd, xg, mug, tg, sg, cg, dims)
+        assert (est - est_o).abs().max().item() < 1e-4
+        extra.update(est_in=dict(x=xg, mu=mug, cond=cg, spks=sg, t=tg), est_out=est)
     flowmod.torch = torch
-    mb.bf16 = True
-    origb = mb.decoder.forward
-    mb.decoder.forward = lambda **k2: origb(**{**k2, "n_timesteps": n_steps})
-    refb, _ = mb.inference(finalize=True, streaming=False, **kw)
-    dev = (refb - out["mel_full"]).abs()
-    print(f"[flow:{name}] reference bf16 path vs fp32: max-abs {dev.max():.3e} mean-abs {dev.mean():.3e}")
+    if with_bf16:
+        # what the reference's own low-precision path loses against fp32 (parity budget)
+        mb = refshim.build_flow(dims, dtype=torch.bfloat16)
+        mb.load_state_dict({k: v.to(torch.bfloat16) for k, v in sd.items()}, strict=True)
+        mb.bf16 = True
+        origb = mb.decoder.forward
+        mb.decoder.forward = lambda **k2: origb(**{**k2, "n_timesteps": n_steps})
+        refb, _ = mb.inference(finalize=True, streaming=False, **kw)
+        dev = (refb - out["mel_full"]).abs()
+        print(f"[flow:{name}] reference bf16 path vs fp32: max-abs {dev.max():.3e} mean-abs {dev.mean():.3e}")
+        extra.update(ref_bf16_maxabs=float(dev.max()), ref_bf16_meanabs=float(dev.mean()))
     torch.save(dict(dims=name, seed=seed, N=N, P=P, n_steps=n_steps, token=tok, prompt_token=ptok, prompt_feat=pfeat,
-                    embedding=emb, est_in=dict(x=xg, mu=mug, cond=cg, spks=sg, t=tg), est_out=est,
-                    ref_bf16_maxabs=float(dev.max()), ref_bf16_meanabs=float(dev.mean()),
-                    sd_checksum=checksum(sd), **out), os.path.join(OUT, f"flow_{name}.pt"))
+                    embedding=emb, sd_checksum=checksum(sd), **extra, **out), os.path.join(OUT, f"flow_{name}.pt"))
 
 
 def golden_llm(name, dims, n_text, n_ptext, P, cases, seed):
@@ -303,6 +392,20 @@ def golden_llm(name, dims, n_text, n_ptext, P, cases, seed):
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if sys.argv[1:] == ["mid"]:                                     # the 400-frame full-dim flow fixture (tests/golden/flow_mid.pt)
+        with torch.no_grad():
+            golden_flow("mid", D.FLOW_FULL, 150, 50, 10, 1)
+        return
+    if sys.argv[1:2] == ["c2"]:                                     # BASELINE config-2 size fixtures (tens of CPU-minutes)
+        which = sys.argv[2:] or ["hift", "flow", "llm"]
+        with torch.no_grad():
+            if "hift" in which:
+                golden_hift_c2(D.HIFT_FULL, 2048, 0)
+            if "flow" in which:
+                golden_flow("c2", D.FLOW_FULL, 1024, 125, 25, 0, modes=("full",), with_est=False, with_bf16=False)
+            if "llm" in which:
+                golden_llm_c2(D.LLM_FULL, 0)
+        return
     if sys.argv[1:] == ["frontend"]:
         with torch.no_grad():
             golden_frontend(0)
@@ -338,6 +441,7 @@ def main():
         golden_frontend(0)
         golden_flow("tiny", D.FLOW_TINY, 21, 10, 10, 0)
         golden_flow("full", D.FLOW_FULL, 24, 8, 4, 0)
+        golden_flow("mid", D.FLOW_FULL, 150, 50, 10, 1)
         sp1 = dict(top_p=0.9, top_k=10, win_size=24, tau_r=0.2)     # server tts defaults (router.py:22-44)
         sp2 = dict(top_p=0.8, top_k=25, win_size=10, tau_r=0.1)     # ras_sampling defaults (common.py:138)
         sp3 = dict(top_p=0.9, top_k=10, win_size=0, tau_r=0.2)      # win_size=0 edge: always random sampling

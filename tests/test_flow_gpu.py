@@ -162,3 +162,48 @@ def test_flow_batch_equals_one_by_one(flows, golden, name, streaming):
     again = f.inference(token=reqs[1]["token"], embedding=reqs[1]["embedding"], prompt_token=reqs[1]["prompt_token"],
                         prompt_feat=reqs[1]["prompt_feat"], streaming=streaming, n_timesteps=g["n_steps"])[0].cpu()
     assert torch.equal(again, alone[1])
+
+
+# ---------------------------------------------------------------- the reference's raw-pointer seam, real pool
+def _drive_seam_like_the_reference(pool, x, mask, mu, t, spks, cond):
+    """the body of ConditionalCFM.forward_estimator's pool branch (flow_matching.py:129-153), line by line"""
+    [estimator, stream], trt_engine = pool.acquire_estimator()
+    torch.cuda.current_stream().synchronize()
+    with stream:
+        estimator.set_input_shape('x', (2, 80, x.size(2)))
+        estimator.set_input_shape('mask', (2, 1, x.size(2)))
+        estimator.set_input_shape('mu', (2, 80, x.size(2)))
+        estimator.set_input_shape('t', (2,))
+        estimator.set_input_shape('spks', (2, 80))
+        estimator.set_input_shape('cond', (2, 80, x.size(2)))
+        data_ptrs = [x.contiguous().data_ptr(), mask.contiguous().data_ptr(), mu.contiguous().data_ptr(), t.contiguous().data_ptr(),
+                     spks.contiguous().data_ptr(), cond.contiguous().data_ptr(), x.data_ptr()]
+        for i, j in enumerate(data_ptrs):
+            estimator.set_tensor_address(trt_engine.get_tensor_name(i), j)
+        assert estimator.execute_async_v3(torch.cuda.current_stream().cuda_stream) is True
+        torch.cuda.current_stream().synchronize()
+    pool.release_estimator(estimator, stream)
+    return x
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_estimator_pool_seam(flows, golden, dtype):
+    """NativeEstimatorPool behind the reference's own calling sequence: result in place in x, in the seam's dtype."""
+    from flowmirror_hydravox_b200.flow import NativeEstimatorPool
+    e, f, fd = flows["full"]
+    g = golden("flow_full")
+    i = g["est_in"]
+    dev = e.device
+    x, mu, cond, spks, t = (i[k].to(dev, dtype).contiguous() for k in ("x", "mu", "cond", "spks", "t"))
+    mask = torch.ones(2, 1, x.shape[2], device=dev, dtype=dtype)
+    want = f.estimator(x.float(), None, mu.float(), t.float(), spks.float(), cond.float())     # same (rounded) inputs, fp32 seam
+    pool = NativeEstimatorPool(f, dtype=dtype)
+    got = _drive_seam_like_the_reference(pool, x, mask, mu, t, spks, cond)
+    assert got.data_ptr() == x.data_ptr() and got.dtype == dtype
+    err = (got.float() - want).abs().max().item()
+    tol = {torch.float32: 1e-6, torch.float16: 2e-3, torch.bfloat16: 2e-2}[dtype] * max(1.0, want.abs().max().item())
+    print(f"[seam pool {dtype}] max-abs vs fp32 seam {err:.3e}")
+    assert err <= tol
+    if dtype == torch.float32:
+        assert (got.cpu() - g["est_out"]).abs().max().item() < 2e-2 * max(g["est_out"].abs().mean().item(), 1.0)
+    assert pool.trt_context_pool.qsize() == 1

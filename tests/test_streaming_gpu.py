@@ -41,8 +41,9 @@ def test_streaming_matches_oracle_and_offline(mm):
     off = 0
     for mel, n_tok in zip(dbg["mel"], dbg["n_tok"]):
         fin = n_tok == 96 and off + mel.shape[2] // 2 >= 96
+        # the final pass runs under full attention (cli/model.py:352-358 does not pass `stream` to the last token2wav)
         ref = flow_ref.inference(flow_sd, torch.tensor(toks[:n_tok])[None], r["embedding"][None], noise, D.FLOW_TINY, 4,
-                                 r["prompt_speech"][None].long(), r["prompt_feat"][None], streaming=True, finalize=fin)
+                                 r["prompt_speech"][None].long(), r["prompt_feat"][None], streaming=not fin, finalize=fin)
         ref = ref[:, :, 2 * off:]
         assert ref.shape == mel.shape
         assert (ref - mel).abs().max().item() < 1e-2
@@ -52,3 +53,23 @@ def test_streaming_matches_oracle_and_offline(mm):
     full, _ = mm.models["hift"].inference(speech_feat=dbg["mel_cache"]())
     assert (full.cpu() - wav).abs().max().item() < 5e-3
     assert dbg["first_audio_ms"] > 0
+
+
+def test_abandoned_stream_does_not_leak_into_next_request(mm):
+    """A consumer that stops iterating (client disconnect) cancels the decode; the next request on the same synthesizer
+    gets exactly the tokens it gets on a fresh one."""
+    from flowmirror_hydravox_b200.streaming import StreamingSynthesizer
+    r1 = synth.utterance(D.LLM_TINY, D.FLOW_TINY, 24, seed=5, prompt_tokens=7, prompt_text=3)
+    r2 = synth.utterance(D.LLM_TINY, D.FLOW_TINY, 12, seed=6, prompt_tokens=7, prompt_text=3)
+    u = torch.rand(1, 4096, generator=torch.Generator().manual_seed(3))
+    sp = dict(top_p=0.9, top_k=10, win_size=24, tau_r=0.2)
+    s = StreamingSynthesizer(mm)
+    ref = {}
+    list(s.tts(r2, head_k=2, sampling=sp, n_timesteps=2, min_ratio=8, max_ratio=8, u=u, debug=ref))
+    gen = s.tts(r1, head_k=2, sampling=sp, n_timesteps=2, min_ratio=8, max_ratio=8, u=u)
+    next(gen)                      # first chunk only
+    gen.close()                    # abandon: the finally block cancels + joins the LLM thread
+    dbg = {}
+    wav = torch.cat([c["tts_speech"] for c in s.tts(r2, head_k=2, sampling=sp, n_timesteps=2, min_ratio=8, max_ratio=8, u=u, debug=dbg)], 1)
+    assert dbg["tokens"] == ref["tokens"] and len(dbg["tokens"]) == 96
+    assert torch.isfinite(wav).all()
