@@ -1,19 +1,23 @@
 #!/usr/bin/env python
 """bench.py — HydraVox hot path (multi-head AR decode -> CFM Euler -> HiFT) on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--head-k K] [--n-text T] [--cfm-steps S]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|b8|c4] [--mode parity|serving]
   python bench.py --impl reference ...      # the reference algorithm's CPU path (oracle port) on the host cores
 
-A step = one pass of the whole hot path over one batch of synthetic utterances (BASELINE.json configs[1] by
-default: one zero-shot utterance, 16+128 text tokens, 125 prompt speech tokens + 250 prompt mel frames,
-inference_head_num=2, 25 CFM Euler steps, fixed-length protocol min=max ratio 8 -> 1024 speech tokens = 40.96 s
-of audio).  Metric: speech tokens per second through the whole path (RTF = 25 / value, also printed).
+A step = one pass of the whole hot path over one batch of synthetic utterances.  Default workload = BASELINE.json
+configs[2] ("c3"): 32 zero-shot utterances per GPU of MIXED length — n_text ~ U{64..512} text tokens (seed 1986), each with a
+16-token prompt text, 125 prompt speech tokens and 250 prompt mel frames — inference_head_num=4, 25 CFM Euler steps,
+fixed-length protocol min = max ratio 8: 512..4096 speech tokens = 20..164 s of 24 kHz audio per utterance.
+Other workloads: c2 = configs[1] (one 16+128-token utterance, K=2), b8 = 8 mixed-length utterances, c4 = configs[3] shape
+(32 chunks per GPU, n_text ~ U{12..40}, K=2).  Metric: speech tokens per second through the whole path (RTF = 25 / value).
 
-  value      inputs resident in HBM, stage calls through the C-ABI with device pointers, CUDA-event timed
-  e2e        ModelManager.synthesize_batch -> hvx_synthesize_host with pinned HOST buffers: H2D of the request,
-             three stages, D2H of tokens + waveform inside the timed region
-Under torchrun (N>1) every rank runs its own batch (utterances are independent): weak scaling, no
-data-path collective; NCCL is used for the barrier and the max-over-ranks reduction only.
+  value   inputs resident in HBM, stage calls through the C-ABI with device pointers, CUDA-event timed
+  e2e     the public call with HOST buffers.  1 GPU: ModelManager.synthesize_batch -> hvx_synthesize_host (H2D of the requests,
+          three stages, D2H of tokens + waveforms inside the timed region).  N GPUs: rank 0 owns the N*batch requests;
+          parallel.synthesize_sharded deals them (one packed NCCL scatter), every rank synthesises its shard, the waveforms
+          return to rank 0 (one NCCL gather) — all inside the timed region, scatter / gather milliseconds reported.
+Both legs run in the mode whose parity tests/ assert (default `parity`: fp32 KV cache, three-term split-fp16 flow GEMMs:
+mel <= 1e-3 max-abs against the fp32 reference); `serving_mode` reports the reference's own serving precision next to it.
 """
 from __future__ import annotations
 
@@ -33,35 +37,66 @@ sys.path.insert(0, ROOT)
 from flowmirror_hydravox_b200 import dims as D, synth  # noqa: E402
 
 SAMPLING = dict(top_p=0.9, top_k=10, win_size=24, tau_r=0.2)       # server /zero-shot defaults (router.py:22-44)
+RATIO = 8.0                                                         # speech tokens per text token, min = max
+P_TOK, P_TEXT = 125, 16                                             # 5 s zero-shot prompt
+WORKLOADS = {   # name: (utterances per GPU, (n_text lo, hi), inference_head_num, BASELINE.json config it realises)
+    "c3": (32, (64, 512), 4, "configs[2]"),
+    "c2": (1, (128, 128), 2, "configs[1]"),
+    "b8": (8, (64, 512), 4, "configs[2] at batch 8"),
+    "c4": (32, (12, 40), 2, "configs[3] (32 text chunks per GPU)"),
+}
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--batch", type=int, default=1, help="utterances per GPU per step")
-    ap.add_argument("--head-k", type=int, default=2)
-    ap.add_argument("--n-text", type=int, default=128)
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="parity", choices=["parity", "serving"])
+    ap.add_argument("--batch", type=int, default=0, help="override utterances per GPU")
+    ap.add_argument("--head-k", type=int, default=0, help="override inference_head_num")
     ap.add_argument("--cfm-steps", type=int, default=25)
-    ap.add_argument("--ratio", type=float, default=8.0, help="speech tokens per text token (min=max, SURVEY 8d)")
+    ap.add_argument("--e2e-steps", type=int, default=3, help="timed steps of the end-to-end leg (<= --steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--first-audio-runs", type=int, default=20, help="streaming first-audio latency samples (0 = skip)")
-    ap.add_argument("--parity-mode-steps", type=int, default=2, help="also time the parity mode (fp32 KV cache, split-fp16 flow GEMMs); 0 = skip")
-    ap.add_argument("--no-variants", action="store_true", help="skip the timing of the alternate estimator / vocoders (SURVEY 8 a7', a12')")
-    ap.add_argument("--cpu-tokens", type=int, default=128, help="speech tokens in the CPU baseline sample (~10-20 s of CPU work)")
+    ap.add_argument("--no-extras", action="store_true", help="skip serving-mode / batch-1 / first-audio side measurements")
+    ap.add_argument("--first-audio-runs", type=int, default=10, help="streaming first-audio latency samples (0 = skip)")
+    ap.add_argument("--variants", action="store_true", help="also time the alternate estimator / vocoders (SURVEY 8 a7', a12')")
+    ap.add_argument("--cpu-tokens", type=int, default=128, help="speech tokens of the CPU sample utterance (~20-30 s of CPU work)")
+    ap.add_argument("--wire", default="f32", choices=["f32", "s16"], help="waveform gather format of the sharded e2e leg")
     return ap.parse_args()
 
 
-def workload_name(a):
-    return (f"zero-shot utterance x{a.batch}/GPU: 16+{a.n_text} text tokens, 125 prompt speech tokens (+250 prompt mel frames), "
-            f"inference_head_num={a.head_k}, {a.cfm_steps} CFM Euler steps, {int(a.n_text * a.ratio)} speech tokens "
-            f"({a.n_text * a.ratio / 25:.2f} s of 24 kHz audio) per utterance")
+def wl(a):
+    b, rng, k, cfg = WORKLOADS[a.workload]
+    return (a.batch or b), rng, (a.head_k or k), cfg
+
+
+def workload_name(a, world=1):
+    b, (lo, hi), k, cfg = wl(a)
+    length = f"{lo}" if lo == hi else f"U{{{lo}..{hi}}} (seed 1986)"
+    return (f"BASELINE {cfg}: {b} zero-shot utterances per GPU x {world} GPU, n_text = {length} text tokens + {P_TEXT} prompt text tokens, "
+            f"{P_TOK} prompt speech tokens (+{2 * P_TOK} prompt mel frames), inference_head_num={k}, {a.cfm_steps} CFM Euler steps, "
+            f"min=max token/text ratio {RATIO:g} -> {int(lo * RATIO)}..{int(hi * RATIO)} speech tokens per utterance")
+
+
+def make_requests(a, n_total):
+    """the synthetic batch: request i has n_text drawn from U{lo..hi} by a generator seeded 1986, contents seeded 1986+1+i"""
+    _, (lo, hi), _, _ = wl(a)
+    g = torch.Generator().manual_seed(1986)
+    n_texts = torch.randint(lo, hi + 1, (n_total,), generator=g).tolist()
+    reqs = []
+    for i, n in enumerate(n_texts):
+        r = synth.utterance(D.LLM_FULL, D.FLOW_FULL, n, seed=1987 + i, prompt_tokens=P_TOK, prompt_text=P_TEXT)
+        r["min_ratio"] = r["max_ratio"] = RATIO
+        r["u"] = torch.rand(4 * int(n * RATIO) + 1024, generator=torch.Generator().manual_seed(7000 + i))
+        reqs.append(r)
+    return reqs
 
 
 # --------------------------------------------------------------------------- algorithmic work (DESIGN.md §roofline)
-def llm_step_bytes(ld: D.LlmDims, head_k: int, ctx: float, n_seq: int) -> float:
+def llm_step_bytes(ld: D.LlmDims, head_k: int, ctx: float, n_seq: float) -> float:
     """bytes one decode step must read: bf16 weights once + the live KV cache."""
     layer = ld.hidden * (ld.q_heads + 2 * ld.kv_heads) * ld.head_dim + ld.hidden * ld.hidden + 3 * ld.hidden * ld.inter
     mtp = 2 * ld.hidden * ld.hidden + 3 * ld.hidden * ld.mtp_inter           # v, o, gate, up, down (q/k are dead)
@@ -88,7 +123,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.th.start()
         except Exception:
@@ -113,7 +148,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
 
 
 # --------------------------------------------------------------------------- CPU arm (oracle port)
@@ -121,24 +157,29 @@ _CPU_SDS = {}
 
 
 def cpu_oracle_run(a, n_tokens: int, threads: int):
-    """The reference algorithm restated on the CPU (oracle/, fp32 torch): the same three stages on a bounded sample of
-    the workload — one utterance without prompt whose fixed length is n_tokens speech tokens."""
+    """The reference algorithm restated on the CPU (oracle/, fp32 torch) on a BOUNDED sample of the workload: ONE zero-shot
+    utterance of the workload's shape — same prompt (16 prompt text tokens, 125 prompt speech tokens, 250 prompt mel frames), same
+    inference_head_num, same number of CFM steps, full model dims — whose text is shortened so the fixed-length protocol emits
+    n_tokens speech tokens.  Throughput per token on the CPU does not improve with length (attention grows with T^2), so the
+    short sample flatters the CPU arm."""
     from oracle import flow_ref, hift_ref, llm_ref
     torch.set_num_threads(threads)
     ld, fd, hd = D.LLM_FULL, D.FLOW_FULL, D.HIFT_FULL
-    n_text = max(1, int(round(n_tokens / a.ratio)))
+    _, _, head_k, _ = wl(a)
+    n_text = max(1, int(round(n_tokens / RATIO)))
     if not _CPU_SDS:
         _CPU_SDS.update(llm=synth.llm_state_dict(ld, 0, eos_scale=0.0), flow=synth.flow_state_dict(fd, 0), hift=synth.hift_state_dict(hd, 0))
     llm_sd, flow_sd, hift_sd = _CPU_SDS["llm"], _CPU_SDS["flow"], _CPU_SDS["hift"]
-    u = synth.utterance(ld, fd, n_text, seed=1986, zero_shot=False)
+    u = synth.utterance(ld, fd, n_text, seed=1987, prompt_tokens=P_TOK, prompt_text=P_TEXT)
     us = torch.rand(8 * n_tokens + 64, generator=torch.Generator().manual_seed(7))
     noise = synth.flow_noise(fd)
     t0 = time.perf_counter()
     with torch.no_grad():
-        toks = llm_ref.inference(llm_sd, ld, u["text"], u["prompt_text"], u["prompt_speech"], us, head_k=a.head_k, sp=SAMPLING,
-                                 min_ratio=a.ratio, max_ratio=a.ratio)
+        toks = llm_ref.inference(llm_sd, ld, u["text"], u["prompt_text"], u["prompt_speech"], us, head_k=head_k, sp=SAMPLING,
+                                 min_ratio=RATIO, max_ratio=RATIO)
         t1 = time.perf_counter()
-        mel = flow_ref.inference(flow_sd, torch.tensor(toks)[None], u["embedding"][None], noise, fd, a.cfm_steps)
+        mel = flow_ref.inference(flow_sd, torch.tensor(toks)[None], u["embedding"][None], noise, fd, a.cfm_steps,
+                                 u["prompt_speech"][None].long(), u["prompt_feat"][None])
         t2 = time.perf_counter()
         table = synth.hift_sine_table(hd, mel.shape[2])
         wav, _ = hift_ref.inference(hift_sd, mel, table, hd)
@@ -146,8 +187,10 @@ def cpu_oracle_run(a, n_tokens: int, threads: int):
     total = t3 - t0
     return dict(tokens=len(toks), seconds=total, stage_s=dict(llm=t1 - t0, flow=t2 - t1, hift=t3 - t2),
                 tokens_per_s=len(toks) / total, rtf=total / (wav.shape[1] / hd.sr),
-                sample=f"1 utterance, {n_text} text tokens, no prompt, {len(toks)} speech tokens, head_k={a.head_k}, "
-                       f"{a.cfm_steps} CFM steps, full model dims, fp32 oracle port (KV-cached decode), {threads} threads")
+                sample=f"1 zero-shot utterance of the workload's shape: {n_text}+{P_TEXT} text tokens, {P_TOK} prompt speech tokens (+{2 * P_TOK} prompt "
+                       f"mel frames), inference_head_num={head_k}, {a.cfm_steps} CFM steps, {len(toks)} speech tokens ({len(toks) / 25:.2f} s of audio), "
+                       f"full model dims, fp32 oracle port of the reference algorithm (KV-cached decode, i.e. faster than the reference's "
+                       f"own no-cache loop), {threads} threads")
 
 
 def reference_arm(a):
@@ -164,7 +207,10 @@ def reference_arm(a):
     tps = res[0]["tokens"] / secs
     line = {"impl": "reference", "metric": "speech_tokens_per_s", "value": tps, "unit": "tokens/s", "n_gpus": a.gpus, "steps": len(res),
             "warmup": 1 if a.warmup else 0, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(a), "timed_sample": res[0]["sample"]},
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a, max(a.gpus, 1)), "timed_sample": res[0]["sample"],
+                       "note": "the CPU arm times a bounded sample (one short utterance per step) of the same workload shape; tokens/s is "
+                               "per host, not per utterance, so it compares with the GPU arm's whole-batch tokens/s"},
             "rtf": 25.0 / tps, "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": res[0]["sample"],
                                                 "stage_s": res[0]["stage_s"]},
             "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -172,6 +218,19 @@ def reference_arm(a):
 
 
 # --------------------------------------------------------------------------- native arm
+def flow_groups(frames, limit=8192, max_u=16):
+    """the grouping rule of hvx_synthesize_host (csrc/pipeline.cu): longest first, <= limit padded frames, <= 20 % padding"""
+    order = sorted(range(len(frames)), key=lambda i: -frames[i])
+    groups, g0 = [], 0
+    while g0 < len(order):
+        g1 = g0 + 1
+        while g1 < len(order) and g1 - g0 < max_u and (g1 - g0 + 1) * frames[order[g0]] <= limit and frames[order[g1]] * 5 >= frames[order[g0]] * 4:
+            g1 += 1
+        groups.append(order[g0:g1])
+        g0 = g1
+    return groups
+
+
 def native_arm(a):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -181,53 +240,71 @@ def native_arm(a):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from flowmirror_hydravox_b200 import _lib as L
+    from flowmirror_hydravox_b200 import parallel
     from flowmirror_hydravox_b200.model_manager import ModelManager
 
     ld, fd, hd = D.LLM_FULL, D.FLOW_FULL, D.HIFT_FULL
-    n_tok = int(a.n_text * a.ratio)
-    max_ctx = 2 + 16 + a.n_text + 125 + n_tok + 64
-    mm = ModelManager(hd=hd, fd=fd, ld=ld, device=f"cuda:{local}", max_ctx=max_ctx, max_seqs=max(a.batch, 1), n_timesteps=a.cfm_steps,
-                      sine_seconds=n_tok / 25 + 2)
-    mm.load_state_dicts(synth.llm_state_dict(ld, 0, dtype=torch.bfloat16, eos_scale=0.0), synth.flow_state_dict(fd, 0),
-                        synth.hift_state_dict(hd, 0))
+    batch, (lo, hi), head_k, _ = wl(a)
+    max_tok = int(hi * RATIO)
+    max_ctx = 2 + P_TEXT + hi + P_TOK + max_tok + 64
+    parity = a.mode == "parity"
+
+    def build_mm(parity_mode, seqs):
+        mm_ = ModelManager(hd=hd, fd=fd, ld=ld, device=f"cuda:{local}", max_ctx=max_ctx, max_seqs=max(seqs, 1), n_timesteps=a.cfm_steps,
+                           sine_seconds=max_tok / 25 + 2, kv_f32=parity_mode, flow_precise=parity_mode)
+        mm_.load_state_dicts(synth.llm_state_dict(ld, 0, dtype=torch.bfloat16, eos_scale=0.0), synth.flow_state_dict(fd, 0),
+                             synth.hift_state_dict(hd, 0))
+        return mm_
+
+    # the whole job's requests; every rank derives the same list and the same LPT deal, so the device-resident leg runs on
+    # exactly the shards the sharded e2e leg scatters
+    all_reqs = make_requests(a, batch * world)
+    shards = parallel.shard_requests(all_reqs, world)
+    reqs = [all_reqs[i] for i in shards[rank]]
+    mm = build_mm(parity, len(reqs))
     llm, flow, hift = mm.models["llm"], mm.models["flow"], mm.models["hift"]
-    reqs = [synth.utterance(ld, fd, a.n_text, seed=1986 + rank * 1000 + i) for i in range(a.batch)]
-    for r in reqs:
-        r["min_ratio"] = r["max_ratio"] = a.ratio
-    u_all = torch.rand(a.batch, 4 * n_tok + 1024, generator=torch.Generator().manual_seed(rank))
-    # device-resident copies for the `value` leg
-    dreqs = [{k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in r.items()} for r in reqs]
+    u_all = torch.zeros(len(reqs), 4 * max_tok + 1024)
+    for i, r in enumerate(reqs):
+        u_all[i, : r["u"].numel()] = r["u"]
+    dreqs = [{k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in r.items() if k != "u"} for r in reqs]
     u_dev = u_all.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)        # > L2 (126 MB)
 
     def step_device():
-        toks = llm.generate_batch(dreqs, head_k=a.head_k, u=u_dev, sampling=SAMPLING, min_ratio=a.ratio, max_ratio=a.ratio)
-        # flow in groups of similar length, as hvx_synthesize_host forms them (csrc/pipeline.cu: <= 8192 padded frames, <= 20 % padding)
+        toks = llm.generate_batch(dreqs, head_k=head_k, u=u_dev, sampling=SAMPLING, min_ratio=RATIO, max_ratio=RATIO)
         items = [dict(token=torch.tensor(t, device=dev, dtype=torch.int32)[None], embedding=r["embedding"][None],
                       prompt_token=r["prompt_speech"][None], prompt_feat=r["prompt_feat"][None]) for r, t in zip(dreqs, toks)]
-        items.sort(key=lambda it: -(it["token"].shape[1] + it["prompt_token"].shape[1]))
-        fr = lambda it: 2 * (it["token"].shape[1] + it["prompt_token"].shape[1])
-        g0 = 0
-        while g0 < len(items):
-            g1 = g0 + 1
-            while g1 < len(items) and g1 - g0 < 16 and (g1 - g0 + 1) * fr(items[g0]) <= 8192 and fr(items[g1]) * 5 >= fr(items[g0]) * 4:
-                g1 += 1
-            if g1 - g0 == 1:
-                it = items[g0]
+        frames = [2 * (it["token"].shape[1] + it["prompt_token"].shape[1]) for it in items]
+        for grp in flow_groups(frames):
+            if len(grp) == 1:
+                it = items[grp[0]]
                 mels = [flow.inference(token=it["token"], embedding=it["embedding"], prompt_token=it["prompt_token"],
                                        prompt_feat=it["prompt_feat"], n_timesteps=a.cfm_steps)[0]]
             else:
-                mels = flow.inference_batch(items[g0:g1], n_timesteps=a.cfm_steps)
+                mels = flow.inference_batch([items[i] for i in grp], n_timesteps=a.cfm_steps)
             for mel in mels:
                 hift.inference(speech_feat=mel)
-            g0 = g1
         return sum(len(t) for t in toks)
 
+    frame = hd.frame_samples
+    e2e_stats = {}
+
     def step_e2e():
-        wavs, toks = mm.synthesize_batch(reqs, head_k=a.head_k, sampling=SAMPLING, n_timesteps=a.cfm_steps, min_ratio=a.ratio,
-                                         max_ratio=a.ratio, u=u_all, return_tokens=True)
-        return sum(len(t) for t in toks), sum(w.shape[1] for w in wavs)
+        if world == 1:
+            wavs, toks = mm.synthesize_batch(reqs, head_k=head_k, sampling=SAMPLING, n_timesteps=a.cfm_steps, min_ratio=RATIO,
+                                             max_ratio=RATIO, u=u_all, return_tokens=True)
+            return sum(len(t) for t in toks)
+
+        def synth_fn(mine):
+            u = torch.zeros(len(mine), 4 * max_tok + 1024)
+            for i, r in enumerate(mine):
+                u[i, : r["u"].numel()] = r["u"]
+            return mm.synthesize_batch(mine, head_k=head_k, sampling=SAMPLING, n_timesteps=a.cfm_steps, min_ratio=RATIO, max_ratio=RATIO, u=u)
+        st = {}
+        out = parallel.synthesize_sharded(synth_fn, all_reqs if rank == 0 else None, wire=a.wire, stats=st)
+        for k, v in st.items():
+            e2e_stats[k] = e2e_stats.get(k, 0.0) + v
+        return sum(w.shape[1] for w in out) // (2 * frame) if rank == 0 else 0
 
     def barrier():
         torch.cuda.synchronize()
@@ -235,38 +312,49 @@ def native_arm(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    prof_tot = {}
+
+    def timed(fn, steps, profile=False):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         units = 0
         for s in range(steps):
             flush.zero_()                                               # L2 flush between timed iterations
             ev[s][0].record()
-            r = fn()
+            units += fn()
             ev[s][1].record()
-            units += r if isinstance(r, int) else r[0]
+            if profile:                                                 # synchronises AFTER the step's closing event
+                for k, (ms, work, n) in mm.engine.profile_collect().items():
+                    t = prof_tot.setdefault(k, [0.0, 0.0, 0])
+                    t[0] += ms; t[1] += work; t[2] += n
         torch.cuda.synchronize()
         return sum(x.elapsed_time(y) for x, y in ev), units
 
     profiling = os.environ.get("HVX_PROFILE") == "1"       # ncu launch-list runs: one warm-up pass, numbers not reported
-    for _ in range(1 if profiling else max(a.warmup, 3)):
+    n_warm = 1 if profiling else max(a.warmup, 3)
+    for _ in range(n_warm):
         flush.zero_(); step_device()
-    for _ in range(0 if profiling else 2):
+    for _ in range(0 if profiling else 1):
         flush.zero_(); step_e2e()
+    e2e_stats.clear()
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
+    mm.engine.profile(True)
+    mm.engine.profile_collect()
     l0 = mm.engine.launches()
-    ms_dev, tok_dev = timed(step_device, a.steps)
+    ms_dev, tok_dev = timed(step_device, a.steps, profile=True)
     launches = mm.engine.launches() - l0
+    mm.engine.profile(False)
     barrier()
     stage_acc = dict(llm=0.0, flow=0.0, hift=0.0)
+    n_e2e = max(1, min(a.e2e_steps, a.steps))
 
     def e2e_once():
         r = step_e2e()
         for k in stage_acc:
             stage_acc[k] += mm.last_stage_ms[k]
         return r
-    ms_e2e, tok_e2e = timed(e2e_once, a.steps)
+    ms_e2e, tok_e2e = timed(e2e_once, n_e2e)
     barrier()
     clk = clocks.stop()
     t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
@@ -278,6 +366,7 @@ def native_arm(a):
     tok_dev, tok_e2e, launches = cnt.tolist()
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
     value = tok_dev / (ms_dev / 1e3)
@@ -289,84 +378,116 @@ def native_arm(a):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-    # stage rooflines from the device-timed stage splits of the e2e leg (CUDA events inside hvx_synthesize_host)
-    n_steps_llm = a.steps * (n_tok / a.head_k)
-    ctx_avg = 2 + 16 + a.n_text + 125 + n_tok / 2
-    llm_bytes = llm_step_bytes(ld, a.head_k, ctx_avg, a.batch)
-    llm_gbs = llm_bytes * n_steps_llm / (stage_acc["llm"] / 1e3) / 1e9
-    T = 2 * (125 + n_tok)
-    flow_tf = flow_nfe_flops(fd, T) * a.cfm_steps * a.batch * a.steps / (stage_acc["flow"] / 1e3) / 1e12
-    hift_tf = 2 * 336.9e6 * 2 * n_tok * a.batch * a.steps / (stage_acc["hift"] / 1e3) / 1e12
-    tot = sum(stage_acc.values())
-    # dominant kernel = llm_gemv_tma_kernel (the decode linears' weight stream; share of the step in profiles/): each
-    # class of its launches (24 layers back to back, same PDL launch path as the decode graph) is CUDA-event timed on
-    # the engine's stream right after the timed region; achieved = bf16 weight bytes of those launches / that time
-    import ctypes as C
-    ms1 = (C.c_float * 1)()
-    H, I, QKV = ld.hidden, ld.inter, (ld.q_heads + 2 * ld.kv_heads) * ld.head_dim
-    classes = {"qkv": (1, 2.0 * QKV * H), "o_proj": (3, 2.0 * H * H), "gate_up": (4, 2.0 * 2 * I * H), "down": (5, 2.0 * H * I)}
-    kern, kb, kt = {}, 0.0, 0.0
-    rows = a.batch * a.head_k
-    if rows <= 8:            # the single-pass weight-streaming GEMV step (above 8 rows the step runs on tcgen05 GEMMs)
-        for name, (which, nbytes) in classes.items():
-            L.check(L.lib().hvx_llm_bench_kernels(mm.engine.h, a.batch, a.head_k, int(ctx_avg), which, 10, ms1))
-            us = ms1[0] * 1e3 / ld.layers
-            kern[name] = {"us_per_launch": us, "bytes_per_launch": nbytes, "gbs": nbytes / us / 1e3}
-            kb += nbytes * ld.layers
-            kt += ms1[0] * 1e-3
-        L.check(L.lib().hvx_llm_bench_kernels(mm.engine.h, a.batch, a.head_k, int(ctx_avg), 2, 10, ms1))
-        kern["kv_attention"] = {"us_per_launch": ms1[0] * 1e3 / ld.layers}
-        L.check(L.lib().hvx_llm_bench_kernels(mm.engine.h, a.batch, a.head_k, int(ctx_avg), 0, 10, ms1))
-        kern["whole_decode_step_no_sampler_us"] = ms1[0] * 1e3
-    gemv_gbs = kb / kt / 1e9 if kt else None
-    roof = {"bound": "hbm", "achieved": gemv_gbs if gemv_gbs else llm_gbs, "peak": hbm_peak, "unit": "GB/s",
-            "frac": (gemv_gbs if gemv_gbs else llm_gbs) / hbm_peak, "traffic": 8.72e6 + 3.4e6,
-            "kernel": "llm_gemv_tma_kernel<R> (decode linears): bf16 weight bytes of the 96 per-step launches / their CUDA-event time, "
-                      "measured per class back to back on the engine stream after the timed region; traffic = dram read+write of the "
-                      "gate_up launch from profiles/r1_ncu_full_summary.txt (algorithmic 8.72 MB)",
-            "peak_source": peak_src, "per_class": kern,
-            "stages": {"llm": {"share": stage_acc["llm"] / tot, "bound": "hbm", "achieved_gbs": llm_gbs, "frac": llm_gbs / hbm_peak,
-                               "note": "algorithmic bytes per decode step x steps / device time of the whole LLM stage (prefill, sampler, launch gaps included)"},
-                       "flow": {"share": stage_acc["flow"] / tot, "bound": "tensor", "achieved_tflops": flow_tf, "frac": flow_tf / tf_peak},
-                       "hift": {"share": stage_acc["hift"] / tot, "bound": "fp32 cuda cores (algorithmic conv flops)", "achieved_tflops": hift_tf}}}
-    line = {"metric": "speech_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+    peak_src = "measured (MEASURED_PEAKS.json, bf16_tflops_sustained / hbm_gbs)" if peaks else "fallback (B200_PROFILING.md)"
+
+    # ---- roofline: per kernel class, CUDA events around every launch of the class on its own stream DURING the timed steps
+    n_tok_rank = [int(r["text"].numel() * RATIO) for r in reqs]
+    steps_llm = a.steps * (max(n_tok_rank) / head_k)                      # the longest sequence decides the number of decode steps
+    live_seq = sum(n_tok_rank) / max(n_tok_rank)                          # sequences alive per step on average
+    ctx_avg = 2 + P_TEXT + (lo + hi) / 2 + P_TOK + sum(n_tok_rank) / len(n_tok_rank) / 2
+    per_class = {}
+    for k, (ms, work, n) in prof_tot.items():
+        if n == 0:
+            continue
+        d = {"ms_per_step": ms / a.steps, "call_sites_per_step": n / a.steps, "share_of_step": ms / ms_dev}
+        if k in ("gemm", "attention", "hift_conv"):
+            tf = work / ms / 1e9 if ms else 0.0
+            d.update(bound="tensor", algorithmic_tflop_per_step=work / a.steps / 1e12, achieved_tflops=tf, frac=tf / tf_peak)
+            if k == "gemm" and parity:
+                d["tensor_pipe_tflops"] = 3.0 * tf       # three split-fp16 products per algorithmic product
+        elif k == "layernorm":
+            gbs = work / ms / 1e6 if ms else 0.0
+            d.update(bound="hbm", achieved_gbs=gbs, frac=gbs / hbm_peak)
+        elif k == "llm_step":
+            byt = llm_step_bytes(ld, head_k, ctx_avg, live_seq)
+            gbs = byt * work / ms / 1e6 if ms else 0.0
+            d.update(bound="hbm", steps=work / a.steps, us_per_step=1e3 * ms / work if work else None, bytes_per_step=byt,
+                     achieved_gbs=gbs, frac=gbs / hbm_peak)
+        per_class[k] = d
+    dom = max((k for k in per_class if "frac" in per_class[k]), key=lambda k: per_class[k]["ms_per_step"], default=None)
+    kernel_names = {"gemm": "gemm_persist_kernel / gemm_bf16_kernel (tcgen05 + TMA; DiT linears, 3 split-fp16 products each in parity mode)",
+                    "attention": "dit_attention_v5_kernel (tcgen05, S/O in TMEM)", "hift_conv": "HiFT convolutions",
+                    "llm_step": "decode step (CUDA graph: tcgen05 GEMMs above 8 rows, TMA GEMV below)", "layernorm": "dit_ln_mod_kernel"}
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))
+        traffic = tr.get(dom, {}).get("dram_bytes_per_launch")
+    except Exception:
+        tr = {}
+    roof = None
+    if dom:
+        dc = per_class[dom]
+        tensor = dc["bound"] == "tensor"
+        roof = {"bound": dc["bound"], "achieved": dc["achieved_tflops"] if tensor else dc["achieved_gbs"], "peak": tf_peak if tensor else hbm_peak,
+                "unit": "TFLOP/s" if tensor else "GB/s", "frac": dc["frac"], "traffic": traffic,
+                "kernel": f"{kernel_names.get(dom, dom)}: dominant kernel class of the timed steps ({100 * dc['share_of_step']:.0f} % of the step); achieved = "
+                          f"algorithmic work of its launches / summed CUDA-event duration of those launches, events recorded around every launch "
+                          f"on the launching stream inside the timed region",
+                "traffic_source": tr.get(dom, {}).get("source") if traffic else None,
+                "peak_source": peak_src, "per_class": per_class}
+    tot = sum(stage_acc.values()) or 1.0
+    line = {"metric": "speech_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": a.steps, "warmup": n_warm,
             "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(a), "l2": "256 MiB flush between timed steps; per-step weight traffic (2.3 GB) exceeds L2",
-                       "precision": "llm: bf16 weights + bf16 KV cache, fp32 activations/accumulate; flow: fp16 operands, fp32 accumulate/state; hift: fp32",
-                       "utterances_per_gpu": a.batch},
+            "config": {"workload": workload_name(a, world), "mode": a.mode,
+                       "l2": "256 MiB flush between timed steps; per-step weight + activation traffic (> 2 GB) exceeds L2",
+                       "precision": ("llm: bf16 weights, fp32 KV cache, fp32 activations/accumulate; flow: three-term split-fp16 tensor-core products "
+                                     "(A_hi W_hi + A_lo W_hi + A_hi W_lo), fp32 accumulate/state — the mode tests/test_flow_gpu.py::"
+                                     "test_flow_parity_mode_meets_north_star and test_c2_size_parity assert at <= 1e-3 max-abs on mel; hift: fp32"
+                                     if parity else
+                                     "llm: bf16 weights + bf16 KV cache; flow: fp16 operands (the reference's serving precision), fp32 accumulate/state; hift: fp32"),
+                       "utterances_per_gpu": batch, "tokens_per_step": tok_dev / a.steps},
             "rtf": 25.0 / value if value else None, "rtf_per_gpu": 25.0 * world / value if value else None,
-            "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": mm.h2d_bytes, "d2h_bytes_per_step": mm.d2h_bytes,
-                    "ms_per_step": ms_e2e / a.steps, "rtf": 25.0 * world / e2e if e2e else None,
-                    "stage_ms_per_step": {k: v / a.steps for k, v in stage_acc.items()}},
+            "e2e": {"value": e2e, "unit": "tokens/s", "steps": n_e2e, "ms_per_step": ms_e2e / n_e2e, "rtf": 25.0 / e2e if e2e else None,
+                    "h2d_bytes_per_step": mm.h2d_bytes * (world if world > 1 else 1), "d2h_bytes_per_step": mm.d2h_bytes * (world if world > 1 else 1),
+                    "stage_ms_per_step_rank0": {k: v / n_e2e for k, v in stage_acc.items()},
+                    "stage_share": {k: v / tot for k, v in stage_acc.items()},
+                    "api": "ModelManager.synthesize_batch -> hvx_synthesize_host" if world == 1 else
+                           "parallel.synthesize_sharded(ModelManager.synthesize_batch): rank 0 host requests -> packed NCCL scatter -> per-rank synthesis -> NCCL gather -> rank 0 host waveforms"},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof}
-    # the same step in parity mode (the mode whose mel error is <= 1e-3 against the fp32 reference, tests/test_flow_gpu.py)
-    if a.parity_mode_steps > 0 and world == 1:
+    if world > 1:
+        line["e2e"]["collective_ms_per_step_rank0"] = {k: e2e_stats.get(k, 0.0) / n_e2e for k in ("scatter_ms", "synth_ms", "gather_ms")}
+        line["e2e"]["note"] = "bytes are rank 0's shard x N (every rank copies its shard H2D and its waveforms D2H; rank 0 additionally gathers all waveforms)"
+        line["e2e"]["wire"] = a.wire
+    # ---- side measurements (bounded; none of them feeds `value`)
+    if not a.no_extras and world == 1:
         del flush
         torch.cuda.empty_cache()
-        pm = ModelManager(hd=hd, fd=fd, ld=ld, device=f"cuda:{local}", max_ctx=max_ctx, max_seqs=max(a.batch, 1), n_timesteps=a.cfm_steps,
-                          sine_seconds=n_tok / 25 + 2, kv_f32=True, flow_precise=True)
-        pm.load_state_dicts(synth.llm_state_dict(ld, 0, dtype=torch.bfloat16, eos_scale=0.0), synth.flow_state_dict(fd, 0),
-                            synth.hift_state_dict(hd, 0))
-        def pm_step():
-            w, t = pm.synthesize_batch(reqs, head_k=a.head_k, sampling=SAMPLING, n_timesteps=a.cfm_steps, min_ratio=a.ratio,
-                                       max_ratio=a.ratio, u=u_all, return_tokens=True)
-            return sum(len(x) for x in t)
-        pm_step()
+        other = build_mm(not parity, len(reqs))
+
+        def other_step():
+            w, t_ = other.synthesize_batch(reqs, head_k=head_k, sampling=SAMPLING, n_timesteps=a.cfm_steps, min_ratio=RATIO, max_ratio=RATIO,
+                                           u=u_all, return_tokens=True)
+            return sum(len(x) for x in t_)
+        other_step()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        n_pm = sum(pm_step() for _ in range(a.parity_mode_steps))
+        n_o = other_step()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        line["parity_mode"] = {"e2e_value": n_pm / dt, "unit": "tokens/s", "rtf": 25.0 * dt / n_pm, "steps": a.parity_mode_steps,
-                               "stage_ms": dict(pm.last_stage_ms),
-                               "what": "fp32 KV cache + three-term split-fp16 flow GEMMs (mel max-abs 2e-4 vs the fp32 reference); "
-                                       "the headline numbers use the serving mode (bf16 KV cache, fp16 flow operands = reference precision)"}
-        pm.engine.close()
-        del pm
-    # BASELINE config 5: first-audio latency of the streaming path (AR decode overlapped with chunked flow + vocoder)
-    if a.first_audio_runs > 0:
+        line["serving_mode" if parity else "parity_mode"] = {
+            "e2e_value": n_o / dt, "unit": "tokens/s", "rtf": 25.0 * dt / n_o, "steps": 1, "stage_ms": dict(other.last_stage_ms),
+            "what": ("bf16 KV cache + single-product fp16 flow GEMMs = the reference's own serving precision (mel 2-3e-3 max-abs vs the fp32 reference)"
+                     if parity else "fp32 KV cache + three-term split-fp16 flow GEMMs (mel <= 1e-3 max-abs vs the fp32 reference)")}
+        # BASELINE configs[1]: one zero-shot utterance, 16+128 text tokens, inference_head_num=2 (the batch-1 latency case)
+        r1 = synth.utterance(ld, fd, 128, seed=1986, prompt_tokens=P_TOK, prompt_text=P_TEXT)
+        u1 = torch.rand(1, 4 * 1024 + 1024, generator=torch.Generator().manual_seed(0))
+        for m_, key in ((mm, "batch1_c2"), (other, "batch1_c2_other_mode")):
+            f1 = lambda: m_.synthesize_batch([r1], head_k=2, sampling=SAMPLING, n_timesteps=a.cfm_steps, min_ratio=RATIO, max_ratio=RATIO, u=u1,
+                                             return_tokens=True)
+            f1(); f1()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n1 = sum(len(f1()[1][0]) for _ in range(3))
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            line[key] = {"e2e_value": n1 / dt, "unit": "tokens/s", "rtf": 25.0 * dt / n1, "steps": 3, "stage_ms": dict(m_.last_stage_ms),
+                         "mode": a.mode if m_ is mm else ("serving" if parity else "parity"),
+                         "workload": "BASELINE configs[1]: 1 zero-shot utterance, 16+128 text tokens, inference_head_num=2, 25 CFM steps, 1024 speech tokens"}
+        other.engine.close()
+        del other
+    # BASELINE configs[4]: first-audio latency of the streaming path (AR decode overlapped with chunked flow + vocoder)
+    if a.first_audio_runs > 0 and not a.no_extras and world == 1:
         from flowmirror_hydravox_b200.streaming import StreamingSynthesizer
         ss = StreamingSynthesizer(mm)
         rq = synth.utterance(ld, fd, 64, seed=77)
@@ -374,18 +495,16 @@ def native_arm(a):
         for i in range(a.first_audio_runs + 2):
             dbg = {}
             t0 = time.perf_counter()
-            n_s = sum(c["tts_speech"].shape[1] for c in ss.tts(rq, head_k=2, sampling=SAMPLING, n_timesteps=10, min_ratio=a.ratio,
-                                                                 max_ratio=a.ratio, debug=dbg))
+            n_s = sum(c["tts_speech"].shape[1] for c in ss.tts(rq, head_k=2, sampling=SAMPLING, n_timesteps=10, min_ratio=RATIO, max_ratio=RATIO, debug=dbg))
             if i >= 2:
                 lat.append(dbg["first_audio_ms"]); tot_ms.append((time.perf_counter() - t0) * 1e3)
         lat.sort(); tot_ms.sort()
         line["first_audio"] = {"p50_ms": lat[len(lat) // 2], "min_ms": lat[0], "max_ms": lat[-1], "runs": len(lat),
-                               "total_ms_p50": tot_ms[len(tot_ms) // 2], "audio_s": n_s / hd.sr,
-                               "config": "batch=1, 16+64 text tokens, 125-token prompt, inference_head_num=2, 10 CFM steps, first chunk = "
-                                         "25+3 tokens; request -> first waveform chunk on the host (wall clock)"}
-    # SURVEY 8 a7' / a12': the alternate estimator (U-Net) and the transposed-conv vocoders on the same frame count, CUDA events
-    if not a.no_variants and world == 1:
-        line["variants"] = variants(mm.engine.device, 2 * (n_tok + 125), a.cfm_steps, tf_peak)
+                               "total_ms_p50": tot_ms[len(tot_ms) // 2], "audio_s": n_s / hd.sr, "mode": a.mode,
+                               "config": "BASELINE configs[4]: batch=1, 16+64 text tokens, 125-token prompt, inference_head_num=2, 10 CFM steps, "
+                                         "first chunk = 25+3 tokens; request -> first waveform chunk on the host (wall clock)"}
+    if a.variants and world == 1:
+        line["variants"] = variants(mm.engine.device, 2 * (1024 + P_TOK), a.cfm_steps, tf_peak)
     if not a.no_cpu_baseline:
         threads = os.cpu_count() or 1
         r = cpu_oracle_run(a, a.cpu_tokens, threads)
@@ -393,13 +512,13 @@ def native_arm(a):
                                 "stage_s": r["stage_s"], "rtf": r["rtf"]}
     print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
 def variants(device, T, cfm_steps, tf_peak):
     """CUDA-event timings of hvx_cfm_solve_unet, hvx_hifigan_vocode and hvx_hift_t_vocode at T mel frames (inputs resident)."""
-    import torch
-    from flowmirror_hydravox_b200 import _lib as L, dims as D, synth
+    from flowmirror_hydravox_b200 import _lib as L
     from flowmirror_hydravox_b200.flow import NativeUNetCFM
     from flowmirror_hydravox_b200.hift import NativeHiFiGAN, NativeHiFTTransposed
 

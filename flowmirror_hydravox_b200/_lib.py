@@ -161,6 +161,18 @@ class Engine:
     def launches(self) -> int:
         return int(lib().hvx_kernel_launches(self.h))
 
+    PROF_CLASSES = ("gemm", "attention", "hift_conv", "llm_step", "layernorm", "llm_prefill", "_6", "_7")
+
+    def profile(self, on: bool):
+        """bracket every kernel-class launch with CUDA events on its own stream (hvx_profile_enable)"""
+        check(lib().hvx_profile_enable(self.h, int(bool(on))))
+
+    def profile_collect(self) -> dict:
+        """synchronise and return {class: (ms, work, call sites)} accumulated since the last collect (hvx_profile_collect)"""
+        ms, work, n = (C.c_double * 8)(), (C.c_double * 8)(), (C.c_int64 * 8)()
+        check(lib().hvx_profile_collect(self.h, ms, work, n))
+        return {k: (ms[i], work[i], int(n[i])) for i, k in enumerate(self.PROF_CLASSES) if not k.startswith("_")}
+
     def close(self):
         if self.h:
             lib().hvx_destroy(self.h)

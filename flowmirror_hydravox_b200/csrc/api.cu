@@ -69,3 +69,30 @@ extern "C" hvx_status hvx_finalize(hvx_engine* e, int stage) {
 }
 
 extern "C" int64_t hvx_kernel_launches(hvx_engine* e) { return e ? e->launches.load() : 0; }
+
+extern "C" hvx_status hvx_profile_enable(hvx_engine* e, int on) {
+  HVX_CHECK(e, HVX_ERR_ARG, "profile: null engine");
+  std::lock_guard<std::mutex> g(e->prof.mu);
+  e->prof.on = on != 0;
+  return HVX_OK;
+}
+
+extern "C" hvx_status hvx_profile_collect(hvx_engine* e, double* ms_out, double* work_out, int64_t* launches_out) {
+  HVX_CHECK(e && ms_out && work_out && launches_out, HVX_ERR_ARG, "profile: null argument");
+  HVX_CUDA(cudaDeviceSynchronize());
+  Prof& p = e->prof;
+  std::lock_guard<std::mutex> g(p.mu);
+  for (const ProfRec& r : p.recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess && r.cls >= 0 && r.cls < PROF_NCLS) {
+      p.ms[r.cls] += ms; p.work[r.cls] += r.work; p.n[r.cls]++;
+    }
+    p.free_events.push_back(r.a); p.free_events.push_back(r.b);
+  }
+  p.recs.clear();
+  for (int i = 0; i < PROF_NCLS; i++) {
+    ms_out[i] = p.ms[i]; work_out[i] = p.work[i]; launches_out[i] = p.n[i];
+    p.ms[i] = 0; p.work[i] = 0; p.n[i] = 0;
+  }
+  return HVX_OK;
+}

@@ -937,6 +937,7 @@ hvx_status dit_attention(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* qk
     attr_set = true;
   }
   dim3 grid(cdiv(a.T, 128), a.heads, a.n_batch);
+  ProfScope prof_scope(&e->prof, st, PROF_ATTN, a.work > 0 ? a.work : 4.0 * a.n_batch * a.heads * (double)a.T * a.T * 64.0 * (a.chunk > 0 ? 0.5 : 1.0));
   HVX_CHECK(!a.klen || !(getenv("HVX_ATTN_V1") || getenv("HVX_ATTN_V2") || getenv("HVX_ATTN_V3") || getenv("HVX_ATTN_V4")), HVX_ERR_UNSUPPORTED,
             "attention: per-batch key counts need the v5 kernel");
   HVX_CHECK(!a.lo_off || !(getenv("HVX_ATTN_V1") || getenv("HVX_ATTN_V2")), HVX_ERR_UNSUPPORTED, "attention: split output needs the v5 kernel");

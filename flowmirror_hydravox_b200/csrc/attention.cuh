@@ -23,6 +23,7 @@ struct AttnArgs {
   int f16;          // 1: q/k/v/out are fp16 instead of bf16
   int ld_out;       // = heads*64 (row stride is 2*ld_out when lo_off > 0)
   const int* klen = nullptr;   // [n_batch] valid keys per batch row (device; ragged groups, v5 kernel only); nullptr: T
+  double work = 0;  // FLOP of this call for the live profiler (0: 4 * n_batch * heads * T^2 * 64, halved under the chunk mask)
   int lo_off = 0;   // > 0: output written as split precision, hi at [col], lo at [lo_off + col] (flow parity mode, v5 kernel)
   __nv_bfloat16* out;   // [n_batch*T][heads*64]
 };

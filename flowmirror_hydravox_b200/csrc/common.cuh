@@ -41,6 +41,47 @@ struct DevBuf {              // engine-owned scratch that grows on demand (never
   ~DevBuf() { if (p) cudaFree(p); }
 };
 
+// Live per-class kernel timing for bench.py's roofline (include/hydravox_b200.h: hvx_profile_enable / hvx_profile_collect):
+// while enabled, every launch of a class is bracketed by two cudaEventRecord on its own stream; collect() synchronises the
+// device, sums event-to-event durations and work per class, and recycles the events.  Off (the default) costs one branch.
+enum { PROF_GEMM = 0, PROF_ATTN = 1, PROF_HIFT_CONV = 2, PROF_LLM_STEP = 3, PROF_LAYERNORM = 4, PROF_LLM_PREFILL = 5, PROF_NCLS = 8 };
+struct ProfRec { int cls; cudaEvent_t a, b; double work; };
+struct Prof {
+  bool on = false;
+  std::mutex mu;
+  std::vector<cudaEvent_t> free_events;
+  std::vector<ProfRec> recs;
+  double ms[PROF_NCLS] = {0}, work[PROF_NCLS] = {0};
+  long long n[PROF_NCLS] = {0};
+  cudaEvent_t get() {
+    if (!free_events.empty()) { cudaEvent_t x = free_events.back(); free_events.pop_back(); return x; }
+    cudaEvent_t x = nullptr;
+    cudaEventCreate(&x);
+    return x;
+  }
+};
+// RAII bracket around the launches of one call site; inert when profiling is off or the stream is being captured into a graph
+struct ProfScope {
+  Prof* p = nullptr; cudaStream_t st; ProfRec r;
+  ProfScope(Prof* prof_p, cudaStream_t stream, int cls, double work) : st(stream) {
+    if (!prof_p) return;
+    Prof& prof = *prof_p;
+    if (!prof.on) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+    p = &prof;
+    std::lock_guard<std::mutex> g(prof.mu);
+    r.cls = cls; r.work = work; r.a = prof.get(); r.b = prof.get();
+    cudaEventRecord(r.a, st);
+  }
+  ~ProfScope() {
+    if (!p) return;
+    cudaEventRecord(r.b, st);
+    std::lock_guard<std::mutex> g(p->mu);
+    p->recs.push_back(r);
+  }
+};
+
 struct HiftState;
 struct FlowState;
 struct LlmState;
@@ -60,7 +101,9 @@ struct hvx_engine {
   // (streaming: AR decode on one thread, chunked flow + vocoder on another — they touch disjoint engine state and streams);
   // calls into the same stage serialise here.  Recursive: hvx_synthesize_host holds all of them and calls the stage entries.
   std::recursive_mutex mu[4];
-  std::atomic<int> llm_cancel{0};  // hvx_llm_cancel: a running hvx_llm_generate stops after its current batch of steps
+  std::atomic<int> llm_cancel{0};
+  hvx::Prof prof;
+  int prof_gemm_off = 0;           // > 0: gemm_bf16 calls are not counted as PROF_GEMM (they belong to an enclosing LLM scope)  // hvx_llm_cancel: a running hvx_llm_generate stops after its current batch of steps
   hvx::DevBuf samp_ws;             // sampler tables (llm.cu)
   hvx::DevBuf fe_ws;               // frontend spectrum scratch (frontend.cu)
   void* samp_arrive = nullptr;

@@ -268,6 +268,7 @@ struct FlowState {
   // [conditional block U*T rows | unconditional block U*T rows]; batch index of a T-row slab = cfg * U + u
   int T = 0, Tp = 0, U = 1;
   const int* klen = nullptr;  // [2U] valid frames per slab (device), nullptr when every slab is full (U == 1)
+  double attn_work = 0;       // FLOP of one attention call of the current plan: 2 CFG rows * heads * 4 * 64 * sum_u T_u^2
   __half *xin, *h0h, *c1, *n16, *qk, *vt, *ao, *f1;
   float *h0, *h, *v, *rope_c, *rope_s;
   // solve-level buffers (ws_small)
@@ -383,6 +384,7 @@ static hvx_status flow_plan(hvx_engine* e, cudaStream_t st, int T, int U = 1) {
     f->rope_T = T;
   }
   f->T = T; f->Tp = Tp; f->U = U; f->klen = nullptr;
+  f->attn_work = 2.0 * U * c.flow_heads * 4.0 * 64.0 * (double)T * T;
   return HVX_OK;
 }
 
@@ -429,19 +431,22 @@ static hvx_status flow_nfe(hvx_engine* e, cudaStream_t st, const float* mod, int
   for (int i = 0; i < c.flow_depth; i++) {
     const FlowBlk& b = f->blk[i];
     const float* m = mod + (size_t)i * 6 * dim;       // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
-    dit_ln_mod_kernel<<<cdiv(M, 8), 256, 0, st>>>(f->h, m + dim, m, f->n16, M, dim, f->precise);
+    const double ln_bytes = (double)M * dim * (4 + 2 * (f->precise ? 2 : 1));
+    { ProfScope ps(&e->prof, st, PROF_LAYERNORM, ln_bytes);
+      dit_ln_mod_kernel<<<cdiv(M, 8), 256, 0, st>>>(f->h, m + dim, m, f->n16, M, dim, f->precise); }
     HVX_LAUNCH_CHECK(e);
     { GemmEpi p; p.mode = EPI_QKV; p.f16 = 1; p.bias = b.qkv_b; p.out = f->qk; p.ldo = 2 * inner; p.n_qk = 2 * inner;
       p.vt = (__nv_bfloat16*)f->vt; p.vt_ld = f->Tp; p.T = T; p.heads = c.flow_heads; p.rows_per_batch = T;
       p.rope_cos = f->rope_c; p.rope_sin = f->rope_s;
       if ((rc = flow_linear(e, st, f->n16, b.qkv_w, M, 3 * inner, dim, p))) return rc; }
     { AttnArgs a; a.T = T; a.heads = c.flow_heads; a.n_batch = nb; a.klen = f->klen; a.chunk = streaming ? c.flow_chunk : 0; a.f16 = 1;
-      a.ld_out = inner; a.out = (__nv_bfloat16*)f->ao; a.lo_off = f->precise ? inner : 0;
+      a.ld_out = inner; a.out = (__nv_bfloat16*)f->ao; a.lo_off = f->precise ? inner : 0; a.work = f->attn_work * (streaming ? 0.5 : 1.0);
       if ((rc = dit_attention(e, st, (const __nv_bfloat16*)f->qk, 2 * inner, inner, (const __nv_bfloat16*)f->vt, f->Tp, a))) return rc; }
     { GemmEpi p; p.mode = EPI_RESID_GATE; p.f16 = 1; p.bias = b.out_b; p.out = f->h; p.ldo = dim; p.gate = m + 2 * dim;
       p.gate_ld = 0; p.rows_per_batch = T;
       if ((rc = flow_linear(e, st, f->ao, b.out_w, M, dim, inner, p))) return rc; }
-    dit_ln_mod_kernel<<<cdiv(M, 8), 256, 0, st>>>(f->h, m + 4 * dim, m + 3 * dim, f->n16, M, dim, f->precise);
+    { ProfScope ps(&e->prof, st, PROF_LAYERNORM, ln_bytes);
+      dit_ln_mod_kernel<<<cdiv(M, 8), 256, 0, st>>>(f->h, m + 4 * dim, m + 3 * dim, f->n16, M, dim, f->precise); }
     HVX_LAUNCH_CHECK(e);
     { GemmEpi p = epi16(f->f1, f->precise ? 2 * ff : ff, b.ff1_b, ACT_GELU_TANH);
       p.lo_off = f->precise ? ff : 0;
@@ -520,6 +525,8 @@ static hvx_status flow_solve(hvx_engine* e, int U, const int32_t* const* tokens,
     for (int u = 0; u < U; u++) kl[u] = kl[U + u] = Tu[u];
     HVX_CUDA(cudaMemcpyAsync(klen_dev, kl.data(), sizeof(int) * 2 * U, cudaMemcpyHostToDevice, st));
     f->klen = klen_dev;
+    f->attn_work = 0;
+    for (int u = 0; u < U; u++) f->attn_work += 2.0 * c.flow_heads * 4.0 * 64.0 * (double)Tu[u] * Tu[u];
   }
 
   // ---- pre-net, utterance by utterance (flow.py:387-419); a few small launches each

@@ -55,11 +55,14 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int GEMM_THREADS = 192;
 
-template <int BN, int STAGES>
+// TRI = the three-term split-precision product (GemmAddr::split3_kb): one pipeline stage holds the four operand tiles of a k-block
+// [A_hi | A_lo | B_hi | B_lo] and feeds three MMA groups A_hi B_hi + A_lo B_hi + A_hi B_lo from them — every operand tile crosses
+// L2 -> shared memory once instead of 1.5 times (the GEMMs are L2 -> SM bandwidth bound, profiles/README.md).
+template <int BN, int STAGES, bool TRI = false>
 struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = (TRI ? 2 : 1) * (A_BYTES + B_BYTES);
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // barriers + tmem slot + alignment slack
 };
@@ -165,6 +168,94 @@ __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx,
           #pragma unroll
           for (int j = 0; j < 32; j++) if (col0 + j < N) o[j] = fmaf(__ldg(g + j), f[j], o[j]);
         }
+      } else if (MODE == EPI_HIFT) {
+        const HiftEpi& h = epi.hift;
+        const bool full = col0 + 32 <= N;
+        if (h.resid) {
+          const float* r = h.resid + (size_t)row * h.ldr + col0;
+          if (full && (h.ldr & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) { const float4 rr = reinterpret_cast<const float4*>(r)[j]; f[4 * j] += rr.x; f[4 * j + 1] += rr.y; f[4 * j + 2] += rr.z; f[4 * j + 3] += rr.w; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) if (col0 + j < N) f[j] += r[j];
+          }
+        }
+        if (h.resid2) {
+          const float* r = h.resid2 + (size_t)row * h.ldr + col0;
+          if (full && (h.ldr & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) { const float4 rr = reinterpret_cast<const float4*>(r)[j]; f[4 * j] += rr.x; f[4 * j + 1] += rr.y; f[4 * j + 2] += rr.z; f[4 * j + 3] += rr.w; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) if (col0 + j < N) f[j] += r[j];
+          }
+        }
+        if (h.out32) {
+          float* o = h.out32 + (size_t)(row + h.row_shift) * h.ld32 + col0;
+          if (full && (h.ld32 & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              float4 o4 = make_float4(f[4 * j] * h.out_scale, f[4 * j + 1] * h.out_scale, f[4 * j + 2] * h.out_scale, f[4 * j + 3] * h.out_scale);
+              if (h.accumulate) { const float4 c4 = reinterpret_cast<const float4*>(o)[j]; o4.x += c4.x; o4.y += c4.y; o4.z += c4.z; o4.w += c4.w; }
+              reinterpret_cast<float4*>(o)[j] = o4;
+              if (h.dup_row1 && row == 1) reinterpret_cast<float4*>(o - (size_t)(1 + h.row_shift) * h.ld32 + (size_t)0)[j] = o4;
+              f[4 * j] = o4.x; f[4 * j + 1] = o4.y; f[4 * j + 2] = o4.z; f[4 * j + 3] = o4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) if (col0 + j < N) {
+              float ov = f[j] * h.out_scale;
+              if (h.accumulate) ov += o[j];
+              o[j] = ov;
+              if (h.dup_row1 && row == 1) o[j - (ptrdiff_t)(1 + h.row_shift) * h.ld32] = ov;
+              f[j] = ov;
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          if (k >= h.n16) break;
+          float a[32];
+          if (h.act[k] == 2) {
+            const float* al = h.alpha[k] + col0;
+            const float* ia = h.inv_alpha[k] + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              const int jc = (col0 + j < N) ? j : 0;
+              const float sn = sinf(f[j] * __ldg(al + jc));
+              a[j] = f[j] + __ldg(ia + jc) * (sn * sn);
+            }
+          } else if (h.act[k] == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) a[j] = f[j] > 0.f ? f[j] : f[j] * h.slope;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) a[j] = f[j];
+          }
+          uint16_t* o = h.out16[k] + (size_t)row * h.ld16 + col0;
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk, pl;
+              const __half2 h0 = __floats2half2_rn(a[j], a[j + 1]), h1 = __floats2half2_rn(a[j + 2], a[j + 3]);
+              const __half2 h2 = __floats2half2_rn(a[j + 4], a[j + 5]), h3 = __floats2half2_rn(a[j + 6], a[j + 7]);
+              pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+              pk.z = *reinterpret_cast<const uint32_t*>(&h2); pk.w = *reinterpret_cast<const uint32_t*>(&h3);
+              const __half2 l0 = __floats2half2_rn(a[j] - __low2float(h0), a[j + 1] - __high2float(h0));
+              const __half2 l1 = __floats2half2_rn(a[j + 2] - __low2float(h1), a[j + 3] - __high2float(h1));
+              const __half2 l2 = __floats2half2_rn(a[j + 4] - __low2float(h2), a[j + 5] - __high2float(h2));
+              const __half2 l3 = __floats2half2_rn(a[j + 6] - __low2float(h3), a[j + 7] - __high2float(h3));
+              pl.x = *reinterpret_cast<const uint32_t*>(&l0); pl.y = *reinterpret_cast<const uint32_t*>(&l1);
+              pl.z = *reinterpret_cast<const uint32_t*>(&l2); pl.w = *reinterpret_cast<const uint32_t*>(&l3);
+              *reinterpret_cast<uint4*>(o + j) = pk;
+              *reinterpret_cast<uint4*>(o + h.lo_off + j) = pl;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) if (col0 + j < N) { o[j] = tc::cvt16(a[j], 1); o[h.lo_off + j] = tc::lo16(a[j], 1); }
+          }
+        }
       } else if (MODE == EPI_LLM_QKV) {
 #pragma unroll
         for (int j = 0; j < 32; j += 2)
@@ -212,11 +303,11 @@ __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx,
       }
 }
 
-template <int BN, int STAGES, int MODE, int ACT>
+template <int BN, int STAGES, int MODE, int ACT, bool TRI>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N, int K,
                  GemmEpi epi, GemmAddr ad, int tiles_per_batch) {
-  using S = GemmSmem<BN, STAGES>;
+  using S = GemmSmem<BN, STAGES, TRI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
@@ -230,7 +321,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const int m0 = (blockIdx.y - batch * tiles_per_batch) * BM;      // row inside the batch
   // split-K (ad.split_k > 1, grid.z): this CTA accumulates k-blocks [kb_lo, kb_lo + nkb) and stores its partial sum to
   // out + z * split_stride (plain EPI_F32, bias from split 0 only); the caller adds the partials in a fixed order
-  const int nkb_all = (K + BK - 1) / BK;
+  const int nkb_all = TRI ? ad.split3_kb : (K + BK - 1) / BK;       // TRI: one pipeline step per k-block of the un-split product
   const int kb_lo = (int)(((long long)nkb_all * blockIdx.z) / gridDim.z);
   const int nkb = (int)(((long long)nkb_all * (blockIdx.z + 1)) / gridDim.z) - kb_lo;
   if (blockIdx.z) { epi.out = reinterpret_cast<float*>(epi.out) + (size_t)blockIdx.z * ad.split_stride; epi.bias = nullptr; }
@@ -257,14 +348,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         tc::mbar_wait(&empty_bar[s], ph ^ 1);
         tc::mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
         uint8_t* sa = smem + s * S::STAGE_BYTES;
-        int term = 0, kbt = kb;                       // split precision: which of the three products, k-block inside it
-        if (ad.split3_kb) { term = kb / ad.split3_kb; kbt = kb - term * ad.split3_kb; }
-        const int tap = ad.kb_per_tap ? kbt / ad.kb_per_tap : 0;
-        const int kin = ad.kb_per_tap ? kbt - tap * ad.kb_per_tap : kbt;
-        const int kbb = ad.split3_kb ? kbt + (term == 2 ? ad.split3_kb : 0) : (ad.b_kb_mod ? kb % ad.b_kb_mod : kb);
-        tc::tma_load_3d(sa, &tma_a, &full_bar[s], ad.a_col0 + blockIdx.x * ad.a_col_per_ntile + kin * BK + (term == 1 ? ad.a_lo_off : 0),
-                        m0 + ad.a_row0 + tap * ad.a_row_step, batch);
-        tc::tma_load_2d(sa + S::A_BYTES, &tma_b, &full_bar[s], kbb * BK, n0);
+        const int tap = ad.kb_per_tap ? kb / ad.kb_per_tap : 0;
+        const int kin = ad.kb_per_tap ? kb - tap * ad.kb_per_tap : kb;
+        const int acol = ad.a_col0 + blockIdx.x * ad.a_col_per_ntile + kin * BK, arow = m0 + ad.a_row0 + tap * ad.a_row_step;
+        if (TRI) {
+          tc::tma_load_3d(sa, &tma_a, &full_bar[s], acol, arow, batch);
+          tc::tma_load_3d(sa + S::A_BYTES, &tma_a, &full_bar[s], acol + ad.a_lo_off, arow, batch);
+          tc::tma_load_2d(sa + 2 * S::A_BYTES, &tma_b, &full_bar[s], kb * BK, n0);
+          tc::tma_load_2d(sa + 2 * S::A_BYTES + S::B_BYTES, &tma_b, &full_bar[s], (ad.split3_kb + kb) * BK, n0);
+        } else {
+          const int kbb = ad.b_kb_mod ? kb % ad.b_kb_mod : kb;
+          tc::tma_load_3d(sa, &tma_a, &full_bar[s], acol, arow, batch);
+          tc::tma_load_2d(sa + S::A_BYTES, &tma_b, &full_bar[s], kbb * BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -276,11 +372,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         tc::mbar_wait(&full_bar[s], ph);
         tc::tc_fence_after();
         const uint32_t sa = tc::smem_u32(smem + s * S::STAGE_BYTES);
-        const uint64_t adesc = tc::umma_desc_k128(sa);
-        const uint64_t bdesc = tc::umma_desc_k128(sa + S::A_BYTES);
+        if (TRI) {
+          const uint64_t a_hi = tc::umma_desc_k128(sa), a_lo = tc::umma_desc_k128(sa + S::A_BYTES);
+          const uint64_t b_hi = tc::umma_desc_k128(sa + 2 * S::A_BYTES), b_lo = tc::umma_desc_k128(sa + 2 * S::A_BYTES + S::B_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / 16; k++)
-          tc::umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; k++) tc::umma_f16(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < BK / 16; k++) tc::umma_f16(tmem_base, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+#pragma unroll
+          for (int k = 0; k < BK / 16; k++) tc::umma_f16(tmem_base, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+        } else {
+          const uint64_t adesc = tc::umma_desc_k128(sa);
+          const uint64_t bdesc = tc::umma_desc_k128(sa + S::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; k++)
+            tc::umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+        }
         tc::umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs retire
       }
       tc::umma_commit(tmem_full);                // accumulator complete
@@ -316,21 +423,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 // 128 x 256 tiles read 96 B/cycle of operands from shared memory (A 4 KB + B 8 KB per 128-cycle MMA), under
 // the 128 B/cycle port limit that caps 128 x 128 tiles.
 constexpr int PBN = 256;
-constexpr int PSTAGES = 4;
+// TRI (three-term split precision): a stage is [A_hi | A_lo | B_hi | B_lo] = 96 KB feeding 12 MMAs (1536 tensor-core cycles), two stages
+template <bool TRI>
 struct PersistSmem {
+  static constexpr int STAGES = TRI ? 2 : 4;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = PBN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = PSTAGES * STAGE_BYTES;
+  static constexpr int STAGE_BYTES = (TRI ? 2 : 1) * (A_BYTES + B_BYTES);
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;
 };
 
 constexpr int PERSIST_THREADS = 320;     // TMA warp, MMA warp, 8 epilogue warps
-template <int MODE, int ACT>
+template <int MODE, int ACT, bool TRI>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1)
 gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N, int K,
                     GemmEpi epi, GemmAddr ad, int tiles_m, int tiles_n) {
-  using S = PersistSmem;
+  using S = PersistSmem<TRI>;
+  constexpr int PSTAGES = S::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
@@ -340,7 +450,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = (K + BK - 1) / BK;
+  const int nkb = TRI ? ad.split3_kb : (K + BK - 1) / BK;          // TRI: one pipeline step per k-block of the un-split product
   const int n_tiles = tiles_m * tiles_n;
 
   if (warp == 0 && lane == 0) {
@@ -367,10 +477,15 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           tc::mbar_wait(&empty_bar[s], ph ^ 1);
           tc::mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
           uint8_t* sa = smem + s * S::STAGE_BYTES;
-          int kba = kb, kbb = kb;
-          if (ad.split3_kb) { kba = kb < 2 * ad.split3_kb ? kb : kb - 2 * ad.split3_kb; kbb = kb < ad.split3_kb ? kb : kb - ad.split3_kb; }
-          tc::tma_load_3d(sa, &tma_a, &full_bar[s], kba * BK, mt * BM, 0);
-          tc::tma_load_2d(sa + S::A_BYTES, &tma_b, &full_bar[s], kbb * BK, nt * PBN);
+          if (TRI) {
+            tc::tma_load_3d(sa, &tma_a, &full_bar[s], kb * BK, mt * BM, 0);
+            tc::tma_load_3d(sa + S::A_BYTES, &tma_a, &full_bar[s], ad.a_lo_off + kb * BK, mt * BM, 0);
+            tc::tma_load_2d(sa + 2 * S::A_BYTES, &tma_b, &full_bar[s], kb * BK, nt * PBN);
+            tc::tma_load_2d(sa + 2 * S::A_BYTES + S::B_BYTES, &tma_b, &full_bar[s], (ad.split3_kb + kb) * BK, nt * PBN);
+          } else {
+            tc::tma_load_3d(sa, &tma_a, &full_bar[s], kb * BK, mt * BM, 0);
+            tc::tma_load_2d(sa + S::A_BYTES, &tma_b, &full_bar[s], kb * BK, nt * PBN);
+          }
         }
       }
     }
@@ -389,11 +504,22 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           tc::mbar_wait(&full_bar[s], ph);
           tc::tc_fence_after();
           const uint32_t sa = tc::smem_u32(smem + s * S::STAGE_BYTES);
-          const uint64_t adesc = tc::umma_desc_k128(sa);
-          const uint64_t bdesc = tc::umma_desc_k128(sa + S::A_BYTES);
+          if (TRI) {
+            const uint64_t a_hi = tc::umma_desc_k128(sa), a_lo = tc::umma_desc_k128(sa + S::A_BYTES);
+            const uint64_t b_hi = tc::umma_desc_k128(sa + 2 * S::A_BYTES), b_lo = tc::umma_desc_k128(sa + 2 * S::A_BYTES + S::B_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 16; k++)
-            tc::umma_f16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; k++) tc::umma_f16(tacc, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < BK / 16; k++) tc::umma_f16(tacc, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < BK / 16; k++) tc::umma_f16(tacc, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+          } else {
+            const uint64_t adesc = tc::umma_desc_k128(sa);
+            const uint64_t bdesc = tc::umma_desc_k128(sa + S::A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; k++)
+              tc::umma_f16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          }
           tc::umma_commit(&empty_bar[s]);
         }
         tc::umma_commit(&tmem_full[as]);
@@ -439,18 +565,18 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (warp == 1) { __syncwarp(); tc::tmem_dealloc(tmem_base, 2 * PBN); }
 }
 
-template <int MODE, int ACT>
+template <int MODE, int ACT, bool TRI>
 static hvx_status launch_gemm_persist_t(hvx_engine* e, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
                                         int K, const GemmEpi& epi, const GemmAddr& ad) {
-  using S = PersistSmem;
+  using S = PersistSmem<TRI>;
   static bool attr_set = false;
   if (!attr_set) {
-    HVX_CUDA(cudaFuncSetAttribute(gemm_persist_kernel<MODE, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    HVX_CUDA(cudaFuncSetAttribute(gemm_persist_kernel<MODE, ACT, TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set = true;
   }
   const int tiles_m = cdiv(M, BM), tiles_n = cdiv(N, PBN);
   const int grid = std::min(tiles_m * tiles_n, e->sm_count);
-  gemm_persist_kernel<MODE, ACT><<<grid, PERSIST_THREADS, S::TOTAL, st>>>(ta, tb, M, N, K, epi, ad, tiles_m, tiles_n);
+  gemm_persist_kernel<MODE, ACT, TRI><<<grid, PERSIST_THREADS, S::TOTAL, st>>>(ta, tb, M, N, K, epi, ad, tiles_m, tiles_n);
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
 }
@@ -472,6 +598,7 @@ static hvx_status launch_gemm_persist_t(hvx_engine* e, cudaStream_t st, const CU
       case EPI_QKV * 8 + ACT_NONE: return CALL(EPI_QKV, ACT_NONE);                               \
       case EPI_LLM_QKV * 8 + ACT_NONE: return CALL(EPI_LLM_QKV, ACT_NONE);                       \
       case EPI_SWIGLU * 8 + ACT_NONE: return CALL(EPI_SWIGLU, ACT_NONE);                         \
+      case EPI_HIFT * 8 + ACT_NONE: return CALL(EPI_HIFT, ACT_NONE);                             \
     }                                                                                            \
     set_error("gemm: epilogue mode %d with activation %d is not instantiated", epi.mode, epi.act); \
     return HVX_ERR_UNSUPPORTED;                                                                  \
@@ -479,31 +606,36 @@ static hvx_status launch_gemm_persist_t(hvx_engine* e, cudaStream_t st, const CU
 
 static hvx_status launch_gemm_persist(hvx_engine* e, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
                                       int K, const GemmEpi& epi, const GemmAddr& ad) {
-#define PCALL(MD, AC) launch_gemm_persist_t<MD, AC>(e, st, ta, tb, M, N, K, epi, ad)
+  if (ad.split3_kb) {
+#define PCALL3(MD, AC) launch_gemm_persist_t<MD, AC, true>(e, st, ta, tb, M, N, K, epi, ad)
+    HVX_EPI_DISPATCH(PCALL3);
+#undef PCALL3
+  }
+#define PCALL(MD, AC) launch_gemm_persist_t<MD, AC, false>(e, st, ta, tb, M, N, K, epi, ad)
   HVX_EPI_DISPATCH(PCALL);
 #undef PCALL
 }
 
-template <int BN, int STAGES, int MODE, int ACT>
+template <int BN, int STAGES, int MODE, int ACT, bool TRI>
 static hvx_status launch_gemm_t(hvx_engine* e, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
                                 int K, const GemmEpi& epi, const GemmAddr& ad) {
-  using S = GemmSmem<BN, STAGES>;
+  using S = GemmSmem<BN, STAGES, TRI>;
   static bool attr_set = false;
   if (!attr_set) {
-    HVX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, MODE, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    HVX_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, MODE, ACT, TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set = true;
   }
   const int tiles_per_batch = cdiv(ad.rows_per_batch, BM);
   dim3 grid(cdiv(N, BN), tiles_per_batch * ad.n_batch, ad.split_k);
-  gemm_bf16_kernel<BN, STAGES, MODE, ACT><<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, M, N, K, epi, ad, tiles_per_batch);
+  gemm_bf16_kernel<BN, STAGES, MODE, ACT, TRI><<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, M, N, K, epi, ad, tiles_per_batch);
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool TRI>
 static hvx_status launch_gemm(hvx_engine* e, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
                               int K, const GemmEpi& epi, const GemmAddr& ad) {
-#define GCALL(MD, AC) launch_gemm_t<BN, STAGES, MD, AC>(e, st, ta, tb, M, N, K, epi, ad)
+#define GCALL(MD, AC) launch_gemm_t<BN, STAGES, MD, AC, TRI>(e, st, ta, tb, M, N, K, epi, ad)
   HVX_EPI_DISPATCH(GCALL);
 #undef GCALL
 }
@@ -521,8 +653,11 @@ hvx_status gemm_bf16(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* A, int
   HVX_CHECK(ad.split_k == 1 || (epi.mode == EPI_F32 && !epi.resid && !epi.out2 && epi.act == ACT_NONE && ad.split_k <= (K + BK - 1) / BK &&
                                 ad.split_k <= 64 && ad.split_stride >= (size_t)M * epi.ldo),
             HVX_ERR_ARG, "gemm: split-K needs a plain fp32 epilogue and room for %d partials", ad.split_k);
+  HVX_CHECK(!(ad.split3_kb && ad.split_k > 1), HVX_ERR_ARG, "gemm: split-K is not combined with the three-term product");
   HVX_CHECK((lda % 8) == 0 && (ldb % 8) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0, HVX_ERR_ARG,
             "gemm: operands must be 16-byte aligned with leading dims multiple of 8 (lda=%d ldb=%d)", lda, ldb);
+  const double k_alg = ad.split3_kb ? (double)K / 3.0 : (ad.b_kb_mod ? (double)ad.b_kb_mod * BK : (double)K);
+  ProfScope prof_scope(e->prof_gemm_off ? nullptr : &e->prof, st, PROF_GEMM, 2.0 * (double)M * (double)N * k_alg);
   CUtensorMap ta, tb;
   const uint64_t kB = ad.split3_kb ? (uint64_t)2 * ad.split3_kb * BK : ad.b_kb_mod ? (uint64_t)ad.b_kb_mod * BK : (uint64_t)K;      // width of the weight matrix
   HVX_CHECK(make_tmap_bf16_3d(&ta, A, ad.n_batch, ad.a_rows, ad.a_cols, lda, BM, BK), HVX_ERR_CUDA,
@@ -537,10 +672,12 @@ hvx_status gemm_bf16(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* A, int
   static const int min128 = getenv("HVX_GEMM_MIN_CTAS128") ? atoi(getenv("HVX_GEMM_MIN_CTAS128")) : 96;   // below: 128 x 64 tiles fill the SMs better
   if (N <= 64 || ad.a_col_per_ntile == 64 || ctas128 < min128) {
     HVX_CHECK(make_tmap_bf16_2d(&tb, B, N, kB, ldb, 64, BK), HVX_ERR_CUDA, "gemm: cuTensorMapEncodeTiled(B) failed");
-    return launch_gemm<64, 4>(e, st, ta, tb, M, N, K, epi, ad);
+    if (ad.split3_kb) return launch_gemm<64, 2, true>(e, st, ta, tb, M, N, K, epi, ad);        // 2 x 48 KB stages: two CTAs per SM
+    return launch_gemm<64, 4, false>(e, st, ta, tb, M, N, K, epi, ad);
   }
   HVX_CHECK(make_tmap_bf16_2d(&tb, B, N, kB, ldb, 128, BK), HVX_ERR_CUDA, "gemm: cuTensorMapEncodeTiled(B) failed");
-  return launch_gemm<128, 3>(e, st, ta, tb, M, N, K, epi, ad);
+  if (ad.split3_kb) return launch_gemm<128, 3, true>(e, st, ta, tb, M, N, K, epi, ad);         // 3 x 64 KB stages: one CTA per SM
+  return launch_gemm<128, 3, false>(e, st, ta, tb, M, N, K, epi, ad);
 }
 
 }  // namespace hvx

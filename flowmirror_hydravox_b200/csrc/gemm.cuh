@@ -12,8 +12,22 @@
 
 namespace hvx {
 
-enum { EPI_BF16 = 0, EPI_F32 = 1, EPI_RESID_GATE = 2, EPI_QKV = 3, EPI_LLM_QKV = 4, EPI_SWIGLU = 5 };
+enum { EPI_BF16 = 0, EPI_F32 = 1, EPI_RESID_GATE = 2, EPI_QKV = 3, EPI_LLM_QKV = 4, EPI_SWIGLU = 5, EPI_HIFT = 6 };
 enum { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_SILU = 2, ACT_MISH = 3, ACT_LRELU = 4 /* slope 0.01 */, ACT_GELU_ERF = 5 /* exact, F.gelu default */ };
+
+// EPI_HIFT — epilogue of the HiFT implicit-GEMM convolutions (hift.cu; generator.py:110-117,672-711).  Per output element
+//   v = acc + bias (+ resid[row][col]) (+ resid2[row][col])
+//   out32 (optional, fp32 [rows][ld32]):  o = v * out_scale (+ out32's old value when accumulate); v := o
+//       rows are shifted by row_shift, and row 1 is also stored to row 0 when dup_row1 (ReflectionPad1d((1, 0)), generator.py:686)
+//   out16[k] (k < n16, fp16 [rows][ld16] as hi at [col], lo = a - hi at [lo_off + col]):  a = act_k(v) with
+//       act 0: identity, 1: leaky-relu(slope), 2: Snake  a = v + inv_alpha[col] * sin(alpha[col] * v)^2   (activation.py:79-84)
+struct HiftEpi {
+  const float* resid = nullptr; const float* resid2 = nullptr; int ldr = 0;
+  float* out32 = nullptr; int ld32 = 0; float out_scale = 1.f; int accumulate = 0; int row_shift = 0; int dup_row1 = 0;
+  int n16 = 0; uint16_t* out16[3] = {nullptr, nullptr, nullptr}; int act[3] = {0, 0, 0};
+  const float* alpha[3] = {nullptr, nullptr, nullptr}; const float* inv_alpha[3] = {nullptr, nullptr, nullptr};
+  float slope = 0.f; int ld16 = 0; int lo_off = 0;
+};
 
 struct GemmEpi {
   int mode = EPI_BF16;
@@ -41,6 +55,7 @@ struct GemmEpi {
   // EPI_LLM_QKV (Qwen2 prefill / batched decode): RoPE + KV-cache write, see llm_common.cuh
   LlmQkvEpi llm;
   // EPI_SWIGLU: weight rows interleaved (gate_n, up_n); out16[row][n] = silu(acc[2n]) * acc[2n+1], ldo = N/2
+  HiftEpi hift;                     // EPI_HIFT
 };
 
 // A-operand addressing.  A is viewed as [n_batch][a_rows][lda]; output tiles never straddle a batch and

@@ -16,7 +16,10 @@
 //   conv1d_strided_kernel  direct kernel for the three tiny source down-convs (18 -> C, k<=30).
 //   f0_head / phase_scan / frame_sin / source_synth / stft16 / istft16 (frame + overlap-add).
 #include "common.cuh"
+#include "gemm.cuh"
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace hvx {
@@ -312,8 +315,11 @@ __global__ void istft_ola_kernel(const float* __restrict__ fb, float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------
-struct ConvW { const float* w = nullptr; const float* b = nullptr; int Cin = 0, K = 0, Cout = 0; };
-struct ResBlockW { ConvW c1[4], c2[4]; const float* a1[4]; const float* a2[4]; };
+struct ConvW {
+  const float* w = nullptr; const float* b = nullptr; int Cin = 0, K = 0, Cout = 0;
+  const __half* w16 = nullptr; int Cinp = 0;     // tensor-core operand: [Cout][2*K*Cinp] fp16 = [hi | lo], column = tap*Cinp + ci
+};
+struct ResBlockW { ConvW c1[4], c2[4]; const float* a1[4]; const float* a2[4]; const float* ia1[4]; const float* ia2[4]; };
 
 struct HiftState {
   ConvW f0c[5]; const float* cls_w; const float* cls_b;
@@ -322,6 +328,7 @@ struct HiftState {
   ResBlockW srb[4], rb[12];
   DevBuf ws;
   bool tables_ready = false;
+  bool tc_ready = false;       // the split-fp16 implicit-GEMM operands (".w16", ".ia*") are registered: decode runs on tcgen05
 };
 
 static hvx_status get_conv(hvx_engine* e, const std::string& name, ConvW* c) {
@@ -330,6 +337,13 @@ static hvx_status get_conv(hvx_engine* e, const std::string& name, ConvW* c) {
   HVX_CHECK(w && b && w->ndim == 3 && w->dtype == HVX_F32, HVX_ERR_STATE, "hift: missing/invalid tensor %s", name.c_str());
   c->w = w->f32(); c->b = b->f32();
   c->Cin = (int)w->shape[0]; c->K = (int)w->shape[1]; c->Cout = (int)w->shape[2];
+  c->w16 = nullptr; c->Cinp = 0;
+  const Tensor* h = e->find(HVX_STAGE_HIFT, name + ".w16");
+  if (h && h->dtype == HVX_F16 && h->ndim == 2 && h->shape[0] == c->Cout && h->shape[1] % (2 * c->K * 64) == 0 &&
+      h->shape[1] / (2 * c->K) >= c->Cin) {
+    c->w16 = reinterpret_cast<const __half*>(h->p);
+    c->Cinp = (int)(h->shape[1] / (2 * c->K));
+  }
   return HVX_OK;
 }
 
@@ -347,8 +361,18 @@ static hvx_status get_rb(hvx_engine* e, const std::string& pfx, int ndil, ResBlo
     if ((s = get_conv(e, pfx + ".c2." + std::to_string(j), &r->c2[j]))) return s;
     if ((s = get_vec(e, pfx + ".a1." + std::to_string(j), &r->a1[j]))) return s;
     if ((s = get_vec(e, pfx + ".a2." + std::to_string(j), &r->a2[j]))) return s;
+    const Tensor* i1 = e->find(HVX_STAGE_HIFT, pfx + ".ia1." + std::to_string(j));
+    const Tensor* i2 = e->find(HVX_STAGE_HIFT, pfx + ".ia2." + std::to_string(j));
+    r->ia1[j] = i1 ? i1->f32() : nullptr;
+    r->ia2[j] = i2 ? i2->f32() : nullptr;
   }
   return HVX_OK;
+}
+
+static bool rb_tc(const ResBlockW& r, int ndil) {
+  for (int j = 0; j < ndil; j++)
+    if (!r.c1[j].w16 || !r.c2[j].w16 || !r.ia1[j] || !r.ia2[j]) return false;
+  return true;
 }
 
 hvx_status hift_finalize(hvx_engine* e) {
@@ -372,6 +396,11 @@ hvx_status hift_finalize(hvx_engine* e) {
     if ((s = get_rb(e, "srb." + std::to_string(i), c.hift_n_dil, &h->srb[i]))) return s;
     for (int j = 0; j < c.hift_n_rb; j++)
       if ((s = get_rb(e, "rb." + std::to_string(i * c.hift_n_rb + j), c.hift_n_dil, &h->rb[i * c.hift_n_rb + j]))) return s;
+  }
+  h->tc_ready = h->conv_pre.w16 && h->conv_post.w16;
+  for (int i = 0; i < c.hift_n_ups && h->tc_ready; i++) {
+    h->tc_ready = h->ups[i].w16 && rb_tc(h->srb[i], c.hift_n_dil);
+    for (int j = 0; j < c.hift_n_rb && h->tc_ready; j++) h->tc_ready = rb_tc(h->rb[i * c.hift_n_rb + j], c.hift_n_dil);
   }
   if (!h->tables_ready) {
     float cs[16], sn[16], hn[16];
@@ -408,6 +437,7 @@ static hvx_status run_conv(hvx_engine* e, cudaStream_t st, const ConvW& c, const
   a.pre_act = o.pre_act; a.slope = o.slope; a.post_elu = o.post_elu; a.accumulate = o.accumulate;
   a.reflect1 = o.reflect1; a.out_scale = o.out_scale; a.zstuff = o.zstuff;
   dim3 grid(cdiv(a.Lout, T_TILE), cdiv(c.Cout, CO_TILE));
+  ProfScope prof_scope(&e->prof, st, PROF_HIFT_CONV, 2.0 * c.Cin * c.K * c.Cout * (double)a.Lout);
   conv1d_tile_kernel<<<grid, 256, 0, st>>>(a);
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
@@ -441,6 +471,207 @@ static hvx_status run_resblock(hvx_engine* e, cudaStream_t st, const ResBlockW& 
   return HVX_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------ tensor-core decode path
+// The decode stack (conv_pre, up-sampling convs, source / main ResBlocks, conv_post: 99 % of the stage's FLOPs) as implicit
+// GEMMs on tcgen05 (gemm.cu): activations frame-major, fp32 residual streams [L][C] plus split-fp16 operand copies
+// [L][2*Cp] = [hi | lo] of the ACTIVATED values (Snake / leaky-relu applied once, in the producing epilogue), weights
+// [Cout][2*K*Cp] = [hi | lo]; every conv = three tensor-core products A_hi W_hi + A_lo W_hi + A_hi W_lo accumulated in fp32
+// in TMEM (~22 mantissa bits per operand), taps addressed through TMA row offsets (zero fill = the causal padding).
+
+// mel (C, ldx) channel-major fp32 -> A16 [L][2*Cp] frame-major split fp16, channels >= C zero
+__global__ void hift_mel_pack_kernel(const float* __restrict__ mel, __half* __restrict__ a16, int C, int Cp, int L, int ldx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L * Cp) return;
+  const int t = i / Cp, ch = i - t * Cp;
+  const float v = ch < C ? mel[(size_t)ch * ldx + t] : 0.f;
+  const __half hi = __float2half_rn(v);
+  a16[(size_t)t * 2 * Cp + ch] = hi;
+  a16[(size_t)t * 2 * Cp + Cp + ch] = __float2half_rn(v - __half2float(hi));
+}
+
+// nearest x`up` + leaky-relu: x32 [L][C] -> A16 [L*up][2*Cp]   (CausalConv1dUpsample's Upsample, convolution.py:246-257)
+__global__ void hift_act_up_kernel(const float* __restrict__ x, __half* __restrict__ a16, int C, int Cp, int L, int up, float slope) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)L * up * Cp) return;
+  const int ch = (int)(i % Cp);
+  const size_t t = i / Cp;
+  float v = 0.f;
+  if (ch < C) { v = x[(t / up) * C + ch]; v = v > 0.f ? v : v * slope; }
+  const __half hi = __float2half_rn(v);
+  a16[t * 2 * Cp + ch] = hi;
+  a16[t * 2 * Cp + Cp + ch] = __float2half_rn(v - __half2float(hi));
+}
+
+// source down-conv (18 -> C, strided) from the channel-major source STFT: si32 [Lout][C] frame-major and its Snake copy
+__global__ void hift_sdown_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                  float* __restrict__ y32, __half* __restrict__ a16, const float* __restrict__ alpha,
+                                  const float* __restrict__ inv_alpha, int Cin, int Cout, int Cp, int K, int stride, int pad_left,
+                                  int Lin, int Lout) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)Lout * Cout) return;
+  const int co = (int)(i % Cout);
+  const int t = (int)(i / Cout);
+  float acc = bias[co];
+  for (int ci = 0; ci < Cin; ci++) {
+    const float* xr = x + (size_t)ci * Lin;
+    for (int k = 0; k < K; k++) {
+      const int v = t * stride + k - pad_left;
+      if (v >= 0 && v < Lin) acc = fmaf(__ldg(w + ((size_t)ci * K + k) * Cout + co), xr[v], acc);
+    }
+  }
+  y32[i] = acc;
+  const float sn = sinf(acc * alpha[co]);
+  const float a = acc + inv_alpha[co] * (sn * sn);
+  const __half hi = __float2half_rn(a);
+  a16[(size_t)t * 2 * Cp + co] = hi;
+  a16[(size_t)t * 2 * Cp + Cp + co] = __float2half_rn(a - __half2float(hi));
+}
+
+// windowed 16-point inverse real DFT of every frame, conv_post output frame-major [F][ld] (generator.py:499-505, 704-707)
+__global__ void istft_frames_fm_kernel(const float* __restrict__ x, float* __restrict__ fb, int F, int ld) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= F) return;
+  float re[9], im[9];
+#pragma unroll
+  for (int f = 0; f < 9; f++) {
+    const float mag = fminf(expf(x[(size_t)m * ld + f]), 100.0f);
+    const float ph = sinf(x[(size_t)m * ld + 9 + f]);
+    re[f] = mag * cosf(ph);
+    im[f] = mag * sinf(ph);
+  }
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    float acc = re[0] + ((j & 1) ? -re[8] : re[8]);
+#pragma unroll
+    for (int f = 1; f < 8; f++)
+      acc += 2.0f * (re[f] * c_cos16[(f * j) & 15] - im[f] * c_sin16[(f * j) & 15]);
+    fb[(size_t)m * 16 + j] = acc * (1.0f / 16.0f) * c_hann16[j];
+  }
+}
+
+// one convolution as a three-term split-fp16 implicit GEMM: out rows = time, N = Cout, K = taps * Cp
+static hvx_status tc_conv(hvx_engine* e, cudaStream_t st, const ConvW& w, const __half* A, int a_rows, int Lout, int dil, int pad_left,
+                          const HiftEpi& he) {
+  GemmEpi p; p.mode = EPI_HIFT; p.f16 = 1; p.bias = w.b; p.hift = he;
+  GemmAddr ga; ga.rows_per_batch = Lout; ga.a_rows = a_rows; ga.a_cols = 2 * w.Cinp; ga.kb_per_tap = w.Cinp / 64; ga.a_row_step = dil;
+  ga.a_row0 = -pad_left; ga.split3_kb = w.K * w.Cinp / 64; ga.a_lo_off = w.Cinp;
+  ProfScope ps(&e->prof, st, PROF_HIFT_CONV, 2.0 * w.Cin * w.K * w.Cout * (double)Lout);
+  e->prof_gemm_off++;
+  const hvx_status rc = gemm_bf16(e, st, (const __nv_bfloat16*)A, 2 * w.Cinp, (const __nv_bfloat16*)w.w16, 2 * w.K * w.Cinp, Lout, w.Cout,
+                                  3 * w.K * w.Cinp, p, &ga);
+  e->prof_gemm_off--;
+  return rc;
+}
+
+struct TcBufs {            // per-stage carve-up (elements): fp32 [L][C], fp16 [L][2*Cp]
+  float *x_up, *si, *x, *work, *xs;
+  __half *a_in, *a_cur, *a_tmp, *a_r[3];
+};
+
+// one ResBlock on tensor cores.  a_first = Snake_{a1[0]}(x_in) (split fp16, produced by the epilogue that wrote x_in).
+// Last conv: v = c2(...) + cur (+ extra); out32 = final32 (scaled / accumulated); fin16[k] = activated copies of the stored value.
+static hvx_status tc_resblock(hvx_engine* e, cudaStream_t st, const ResBlockW& r, int ndil, const int* dils, const float* x_in,
+                              const __half* a_first, __half* a_cur, __half* a_tmp, float* work, int L, int C, int Cp,
+                              const float* extra, float* final32, int final_acc, float final_scale, int n_fin16, __half* const* fin16,
+                              const int* fin_act, const float* const* fin_alpha, const float* const* fin_ialpha, float fin_slope) {
+  const float* cur = x_in;
+  const __half* a = a_first;
+  for (int j = 0; j < ndil; j++) {
+    HiftEpi e1; e1.n16 = 1; e1.out16[0] = (uint16_t*)a_tmp; e1.act[0] = 2; e1.alpha[0] = r.a2[j]; e1.inv_alpha[0] = r.ia2[j];
+    e1.ld16 = 2 * Cp; e1.lo_off = Cp;
+    hvx_status s = tc_conv(e, st, r.c1[j], a, L, L, dils[j], (r.c1[j].K - 1) * dils[j], e1);
+    if (s) return s;
+    HiftEpi e2; e2.resid = cur; e2.ldr = C; e2.ld16 = 2 * Cp; e2.lo_off = Cp;
+    if (j < ndil - 1) {
+      e2.out32 = work; e2.ld32 = C;
+      e2.n16 = 1; e2.out16[0] = (uint16_t*)a_cur; e2.act[0] = 2; e2.alpha[0] = r.a1[j + 1]; e2.inv_alpha[0] = r.ia1[j + 1];
+    } else {
+      e2.resid2 = extra; e2.out32 = final32; e2.ld32 = C; e2.accumulate = final_acc; e2.out_scale = final_scale;
+      e2.n16 = n_fin16; e2.slope = fin_slope;
+      for (int k = 0; k < n_fin16; k++) { e2.out16[k] = (uint16_t*)fin16[k]; e2.act[k] = fin_act[k]; e2.alpha[k] = fin_alpha[k]; e2.inv_alpha[k] = fin_ialpha[k]; }
+    }
+    s = tc_conv(e, st, r.c2[j], a_tmp, L, L, 1, r.c2[j].K - 1, e2);
+    if (s) return s;
+    cur = work; a = a_cur;
+  }
+  return HVX_OK;
+}
+
+// CausalHiFTGenerator.decode (generator.py:672-711) on tensor cores.  sstft: source STFT channel-major [18][Fs] (fp32 kernels).
+static hvx_status hift_decode_tc(hvx_engine* e, cudaStream_t st, const float* mel, int T, int Lmel, int Tx, const float* sstft, int Fs,
+                                 float* ws, float* post, int* post_ld) {
+  const hvx_config& c = e->cfg;
+  HiftState* h = e->hift;
+  const int nu = c.hift_n_ups, nd = c.hift_n_dil, nr = c.hift_n_rb;
+  hvx_status rc;
+  // workspace carve-up: every region sized for the largest stage
+  size_t max32 = (size_t)c.hift_base * Tx, max16 = (size_t)2 * h->conv_pre.Cinp * T;
+  { int L = Tx;
+    for (int i = 0; i < nu; i++) {
+      const int Cin = c.hift_base >> i, C = c.hift_base >> (i + 1);
+      const int Cp = (C + 63) / 64 * 64, Cinp = (Cin + 63) / 64 * 64;
+      const size_t Lo = (size_t)L * c.hift_ups[i] + 1;
+      max32 = std::max(max32, Lo * C);
+      max16 = std::max(max16, std::max(Lo * 2 * Cp, (size_t)L * c.hift_ups[i] * 2 * Cinp));
+      L = (int)Lo - (i == nu - 1 ? 0 : 1);
+    } }
+  max32 = (max32 + 63) & ~(size_t)63; max16 = (max16 + 127) & ~(size_t)127;
+  float* f32 = ws;
+  __half* f16 = reinterpret_cast<__half*>(ws + 5 * max32);
+  TcBufs b;
+  b.x_up = f32; b.si = f32 + max32; b.x = f32 + 2 * max32; b.work = f32 + 3 * max32; b.xs = f32 + 4 * max32;
+  b.a_in = f16; b.a_cur = f16 + max16; b.a_tmp = f16 + 2 * max16; b.a_r[0] = f16 + 3 * max16; b.a_r[1] = f16 + 4 * max16; b.a_r[2] = f16 + 5 * max16;
+
+  // conv_pre: k5 looking right (pad 0 left, zero fill past the last input frame), mel -> x0 [Tx][base]
+  { const ConvW& w = h->conv_pre;
+    hift_mel_pack_kernel<<<cdiv(Lmel * w.Cinp, 256), 256, 0, st>>>(mel, b.a_in, c.hift_mel, w.Cinp, Lmel, T);
+    HVX_LAUNCH_CHECK(e);
+    HiftEpi he; he.out32 = b.xs; he.ld32 = w.Cout;
+    if ((rc = tc_conv(e, st, w, b.a_in, Lmel, Tx, 1, 0, he))) return rc; }
+  const float* cur = b.xs;       // [L][Cin] fp32
+  int L = Tx, down = 1;
+  for (int i = 0; i < nu; i++) down *= c.hift_ups[i];
+  for (int i = 0; i < nu; i++) {
+    const int u = c.hift_ups[i], last = (i == nu - 1);
+    const int Cin = c.hift_base >> i, C = c.hift_base >> (i + 1);
+    const int Cp = (C + 63) / 64 * 64, Cinp = (Cin + 63) / 64 * 64;
+    const int Lu = L * u, Lo = Lu + (last ? 1 : 0);
+    HVX_CHECK(h->ups[i].Cinp == Cinp && h->ups[i].Cout == C, HVX_ERR_STATE, "hift: ups.%d operand shape mismatch", i);
+    if (Cp != C) HVX_CUDA(cudaMemsetAsync(b.a_cur, 0, sizeof(__half) * 5 * max16, st));     // padded operand columns must be zero
+    // up-sampling conv: leaky-relu(0.1) + nearest x u, causal k (generator.py:681-687)
+    hift_act_up_kernel<<<(unsigned)cdiv((long long)Lu * Cinp, 256), 256, 0, st>>>(cur, b.a_in, Cin, Cinp, L, u, 0.1f);
+    HVX_LAUNCH_CHECK(e);
+    { HiftEpi he; he.out32 = b.x_up; he.ld32 = C; he.row_shift = last ? 1 : 0; he.dup_row1 = last;
+      if ((rc = tc_conv(e, st, h->ups[i], b.a_in, Lu, Lu, 1, h->ups[i].K - 1, he))) return rc; }
+    // source branch: strided down-conv of the source STFT, then its ResBlock, "+ x_up" fused into its last epilogue, which also
+    // writes Snake_{a1[0]}(x) for each of the parallel ResBlocks
+    down /= u;
+    const ResBlockW& srb = h->srb[i];
+    { const ConvW& d = h->sdown[i];
+      hift_sdown_kernel<<<(unsigned)cdiv((long long)Lo * C, 256), 256, 0, st>>>(sstft, d.w, d.b, b.si, b.a_cur, srb.a1[0], srb.ia1[0], d.Cin, C, Cp, d.K,
+                                                                              down, down > 1 ? down - 1 : 0, Fs, Lo);
+      HVX_LAUNCH_CHECK(e); }
+    { __half* fin16[3]; int fin_act[3]; const float* fa[3]; const float* fi[3];
+      for (int j = 0; j < nr; j++) { fin16[j] = b.a_r[j]; fin_act[j] = 2; fa[j] = h->rb[i * nr + j].a1[0]; fi[j] = h->rb[i * nr + j].ia1[0]; }
+      if ((rc = tc_resblock(e, st, srb, nd, c.hift_rb_d, b.si, b.a_cur, b.a_cur, b.a_tmp, b.si, Lo, C, Cp, b.x_up, b.x, 0, 1.0f, nr, fin16, fin_act, fa, fi, 0.f)))
+        return rc; }
+    // mean of the parallel ResBlocks, accumulated in the last epilogues; the very last one also emits leaky-relu(0.01)(xs) for conv_post
+    for (int j = 0; j < nr; j++) {
+      const bool emit = last && j == nr - 1;
+      __half* fin16[1] = {b.a_in}; int fin_act[1] = {1}; const float* fa[1] = {nullptr}; const float* fi[1] = {nullptr};
+      if ((rc = tc_resblock(e, st, h->rb[i * nr + j], nd, c.hift_rb_d, b.x, b.a_r[j], b.a_r[j], b.a_tmp, b.work, Lo, C, Cp, nullptr, b.xs, j > 0,
+                            1.0f / nr, emit ? 1 : 0, fin16, fin_act, fa, fi, 0.01f))) return rc;
+    }
+    cur = b.xs; L = Lo;
+  }
+  { const ConvW& w = h->conv_post;                       // leaky-relu(0.01) (applied above) + causal k7 -> [F][Cout]
+    HiftEpi he; he.out32 = post; he.ld32 = w.Cout;
+    if ((rc = tc_conv(e, st, w, b.a_in, L, L, 1, w.K - 1, he))) return rc;
+    *post_ld = w.Cout; }
+  return HVX_OK;
+}
+
 }  // namespace hvx
 
 using namespace hvx;
@@ -466,6 +697,11 @@ extern "C" hvx_status hvx_hift_vocode(hvx_engine* e, const float* mel, int T, in
   const int F = Tx * up_prod + 1;                  // frames entering the ISTFT
   const int n_out = finalize ? Tx * frame : (Tx - 1) * frame;
   const int C0 = c.hift_base, CF = c.hift_f0_ch;
+  // decode stack on tensor cores (split-fp16 implicit GEMMs) unless the operands were not packed or HVX_HIFT_FP32=1 asks for the
+  // fp32 CUDA-core convolutions (A/B runs)
+  const char* env_fp32 = getenv("HVX_HIFT_FP32");
+  const bool force_fp32 = env_fp32 && atoi(env_fp32);
+  const bool tc = h->tc_ready && !force_fp32;
 
   // workspace carve-up (floats)
   size_t off = 0;
@@ -473,16 +709,31 @@ extern "C" hvx_status hvx_hift_vocode(hvx_engine* e, const float* mel, int T, in
   const size_t o_fa = take((size_t)CF * Tf0), o_fb = take((size_t)CF * Tf0), o_f0 = take(Tf0);
   const size_t o_cum = take((size_t)Tf0 * H), o_sin = take((size_t)Tf0 * H), o_s = take(Ns);
   const size_t o_stft = take((size_t)18 * Fs);
-  const size_t o_x0 = take((size_t)C0 * Tx);
-  size_t maxCL = 0;
-  { int L = Tx; for (int i = 0; i < c.hift_n_ups; i++) { L = L * c.hift_ups[i]; size_t cl = (size_t)(C0 >> (i + 1)) * (L + 1); if (cl > maxCL) maxCL = cl; } }
-  const size_t o_x = take(maxCL), o_xs = take(maxCL), o_si = take(maxCL), o_work = take(maxCL), o_tmp = take(maxCL);
-  const size_t o_post = take((size_t)18 * F), o_fbuf = take((size_t)16 * F);
+  const size_t o_post = take((size_t)std::max(18, h->conv_post.Cout) * F), o_fbuf = take((size_t)16 * F);
+  size_t o_x0 = 0, o_x = 0, o_xs = 0, o_si = 0, o_work = 0, o_tmp = 0, o_tc = 0;
+  if (tc) {
+    size_t max32 = (size_t)C0 * Tx, max16 = (size_t)2 * h->conv_pre.Cinp * T;
+    int L = Tx;
+    for (int i = 0; i < c.hift_n_ups; i++) {
+      const int Cin = C0 >> i, C = C0 >> (i + 1);
+      const size_t Cp = (C + 63) / 64 * 64, Cinp = (Cin + 63) / 64 * 64;
+      const size_t Lo = (size_t)L * c.hift_ups[i] + 1;
+      max32 = std::max(max32, Lo * C);
+      max16 = std::max(max16, std::max(Lo * 2 * Cp, (size_t)L * c.hift_ups[i] * 2 * Cinp));
+      L = (int)Lo - (i == c.hift_n_ups - 1 ? 0 : 1);
+    }
+    max32 = (max32 + 63) & ~(size_t)63; max16 = (max16 + 127) & ~(size_t)127;
+    o_tc = take(5 * max32 + 3 * max16);
+  } else {
+    size_t maxCL = 0;
+    { int L = Tx; for (int i = 0; i < c.hift_n_ups; i++) { L = L * c.hift_ups[i]; size_t cl = (size_t)(C0 >> (i + 1)) * (L + 1); if (cl > maxCL) maxCL = cl; } }
+    o_x0 = take((size_t)C0 * Tx);
+    o_x = take(maxCL); o_xs = take(maxCL); o_si = take(maxCL); o_work = take(maxCL); o_tmp = take(maxCL);
+  }
   float* ws = (float*)h->ws.get(off * sizeof(float));
   HVX_CHECK(ws, HVX_ERR_CUDA, "hift: workspace allocation of %zu bytes failed", off * sizeof(float));
   float *fa = ws + o_fa, *fb = ws + o_fb, *f0 = ws + o_f0, *cum = ws + o_cum, *sinamp = ws + o_sin, *s = ws + o_s;
-  float *sstft = ws + o_stft, *x0 = ws + o_x0, *x = ws + o_x, *xs = ws + o_xs, *si = ws + o_si, *work = ws + o_work;
-  float *tmp = ws + o_tmp, *post = ws + o_post, *fbuf = ws + o_fbuf;
+  float *sstft = ws + o_stft, *post = ws + o_post, *fbuf = ws + o_fbuf;
   hvx_status rc;
 
   // ---- F0 predictor (fp32; reference runs it on the CPU for precision, generator.py:715-717)
@@ -514,6 +765,16 @@ extern "C" hvx_status hvx_hift_vocode(hvx_engine* e, const float* mel, int T, in
   HVX_LAUNCH_CHECK(e);
 
   // ---- decode
+  if (tc) {
+    int post_ld = 0;
+    if ((rc = hift_decode_tc(e, st, mel, T, finalize ? T : T - 3, Tx, sstft, Fs, ws + o_tc, post, &post_ld))) return rc;
+    istft_frames_fm_kernel<<<cdiv(F, 128), 128, 0, st>>>(post, fbuf, F, post_ld);
+    HVX_LAUNCH_CHECK(e);
+    istft_ola_kernel<<<cdiv(n_out, 256), 256, 0, st>>>(fbuf, wav, F, n_out, 0.99f);
+    HVX_LAUNCH_CHECK(e);
+    return HVX_OK;
+  }
+  float *x0 = ws + o_x0, *x = ws + o_x, *xs = ws + o_xs, *si = ws + o_si, *work = ws + o_work, *tmp = ws + o_tmp;
   { ConvOpt o; o.pad_left = 0; o.Lout = Tx; o.ldx = T;           // conv_pre k5, look-right 4
     if ((rc = run_conv(e, st, h->conv_pre, mel, finalize ? T : T - 3, x0, o))) return rc; }
   const float* cur = x0;
@@ -523,7 +784,6 @@ extern "C" hvx_status hvx_hift_vocode(hvx_engine* e, const float* mel, int T, in
     const int u = c.hift_ups[i];
     const int last = (i == c.hift_n_ups - 1);
     const int Lo = L * u + (last ? 1 : 0);
-    const int ch = C0 >> (i + 1);
     { ConvOpt o; o.pre_act = 1; o.slope = 0.1f; o.up = u; o.reflect1 = last;
       if ((rc = run_conv(e, st, h->ups[i], cur, L, x, o))) return rc; }
     // source branch: strided causal down-conv of the source STFT, then its resblock, fused "+ x"
@@ -538,7 +798,7 @@ extern "C" hvx_status hvx_hift_vocode(hvx_engine* e, const float* mel, int T, in
     for (int j = 0; j < c.hift_n_rb; j++)
       if ((rc = run_resblock(e, st, h->rb[i * c.hift_n_rb + j], c.hift_n_dil, c.hift_rb_d, x, work, tmp, Lo, nullptr, xs,
                              j > 0, 1.0f / c.hift_n_rb))) return rc;
-    cur = xs; L = Lo; (void)ch;     // next stage reads xs and writes x (never in place: shapes differ)
+    cur = xs; L = Lo;     // next stage reads xs and writes x (never in place: shapes differ)
   }
   { ConvOpt o; o.pre_act = 1; o.slope = 0.01f;
     if ((rc = run_conv(e, st, h->conv_post, cur, L, post, o))) return rc; }

@@ -1636,7 +1636,11 @@ extern "C" hvx_status hvx_llm_generate(hvx_engine* e, int n_seq, int head_k, con
   hvx_status rc;
   if ((rc = llm_bufs(e, L, L->ws, rows, n_seq, head_k, splits, &b, st))) return rc;
   HVX_CUDA(cudaMemsetAsync(out_counts, 0, sizeof(int32_t) * n_seq, st));
-  if ((rc = llm_prefill(e, st, L, n_seq, head_k, b))) return rc;
+  struct GemmOff { hvx_engine* e; GemmOff(hvx_engine* x) : e(x) { e->prof_gemm_off++; } ~GemmOff() { e->prof_gemm_off--; } } gemm_off(e);
+  { double rows = 0;
+    for (int s = 0; s < n_seq; s++) rows += 2 + L->desc[s].n_text_total + L->desc[s].n_ps;
+    ProfScope ps(&e->prof, st, PROF_LLM_PREFILL, rows);
+    if ((rc = llm_prefill(e, st, L, n_seq, head_k, b))) return rc; }
 
   SampArgs sa;
   sa.logits = b.logits; sa.n_seq = n_seq; sa.head_k = head_k; sa.vocab = c.llm_speech_vocab; sa.stop_from = c.llm_speech_vocab - 200;
@@ -1699,7 +1703,8 @@ extern "C" hvx_status hvx_llm_generate(hvx_engine* e, int n_seq, int head_k, con
   }
   for (int step = 0; step < max_steps;) {
     const int n = std::min(poll, max_steps - step);
-    for (int i = 0; i < n; i++) HVX_CUDA(cudaGraphLaunch(L->graph, st));
+    { ProfScope ps(&e->prof, st, PROF_LLM_STEP, (double)n);
+      for (int i = 0; i < n; i++) HVX_CUDA(cudaGraphLaunch(L->graph, st)); }
     e->launches += (int64_t)n * e->graph_launches;
     step += n;
     HVX_CUDA(cudaMemcpyAsync(L->n_active_host, L->n_active, sizeof(int), cudaMemcpyDeviceToHost, st));

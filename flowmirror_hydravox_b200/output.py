@@ -60,3 +60,57 @@ def synthesize_segments(model_manager, segment_requests: Sequence[Dict], rng: Op
         return model_manager.synthesize_batch(list(segment_requests), **kw)[0]
     wavs = model_manager.synthesize_batch(list(segment_requests), **kw)
     return stitch_segments(wavs, model_manager.configs["sample_rate"], rng)
+
+
+def synthesize_chained(model_manager, segment_requests: Sequence[Dict], reprompt, rng: Optional[random.Random] = None, **kw) -> torch.Tensor:
+    """inference_tts_with_segmentation(last_prompt=True) (infer_speech_model.py:392-413) from the per-segment model inputs
+    onward: segment 0 is synthesised as it is (speaker TTS); every later segment is a zero-shot request whose prompt is the
+    text and the AUDIO of the segment before it, so the chain is serial inside a document (documents shard across GPUs:
+    parallel.shard_documents).
+
+    reprompt(request_i, prev_request, prev_wav) -> request_i with its prompt fields (prompt_text, prompt_speech, prompt_feat,
+    embedding) rebuilt from the previous segment — the zero-shot frontend's job (cosyvoice/cli/frontend.py:157-184: speech
+    tokenizer + CAM++ on the 16 kHz audio, 24 kHz mel of it; `frontend.NativeFrontendFeatures` provides the mel / fbank part
+    on the GPU, the two ONNX networks are the caller's).  Then the reference's pause stitching (:419-441)."""
+    if not segment_requests:
+        raise ValueError("no text segments")
+    wavs: List[torch.Tensor] = []
+    prev_req, prev_wav = None, None
+    for i, req in enumerate(segment_requests):
+        try:
+            cur = dict(req) if i == 0 else reprompt(dict(req), prev_req, prev_wav)
+            wav = model_manager.synthesize_batch([cur], **kw)[0]
+        except Exception as ex:                          # infer_speech_model.py:414-416
+            raise ValueError(f"segment {i + 1} synthesis failed: {ex}")
+        wavs.append(wav)
+        prev_req, prev_wav = cur, wav
+    if len(wavs) == 1:
+        return wavs[0]
+    return stitch_segments(wavs, model_manager.configs["sample_rate"], rng)
+
+
+def synthesize_documents(model_manager, documents: Sequence[Sequence[Dict]], reprompt=None, last_prompt: bool = True,
+                         rng: Optional[random.Random] = None, **kw) -> List[torch.Tensor]:
+    """Several segmented documents on this GPU.  last_prompt=False: every segment of every document is independent -> ONE batched
+    call for all of them.  last_prompt=True: the chains advance in lock-step — step k synthesises segment k of every document
+    that still has one, as one batch — so the serial dependency costs max(len(doc)) batched calls, not sum(len(doc))."""
+    sr = model_manager.configs["sample_rate"]
+    if not last_prompt:
+        flat = [r for doc in documents for r in doc]
+        wavs = model_manager.synthesize_batch(flat, **kw) if flat else []
+        out, p = [], 0
+        for doc in documents:
+            seg = wavs[p: p + len(doc)]; p += len(doc)
+            out.append(seg[0] if len(seg) == 1 else stitch_segments(seg, sr, rng))
+        return out
+    if reprompt is None:
+        raise ValueError("last_prompt=True needs the zero-shot frontend callable `reprompt`")
+    segs: List[List[torch.Tensor]] = [[] for _ in documents]
+    prev: List[Optional[Dict]] = [None] * len(documents)
+    for k in range(max((len(d) for d in documents), default=0)):
+        live = [i for i, d in enumerate(documents) if k < len(d)]
+        cur = [dict(documents[i][k]) if k == 0 else reprompt(dict(documents[i][k]), prev[i], segs[i][-1]) for i in live]
+        wavs = model_manager.synthesize_batch(cur, **kw)
+        for i, r, w in zip(live, cur, wavs):
+            segs[i].append(w); prev[i] = r
+    return [s[0] if len(s) == 1 else stitch_segments(s, sr, rng) for s in segs]

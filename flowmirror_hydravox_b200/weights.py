@@ -26,10 +26,18 @@ def _fold_wn(sd, base):
     return v * (g / n)
 
 
-def _conv(sd, base, out, name):
+def _conv(sd, base, out, name, tc: bool = False):
     w = _fold_wn(sd, base)                               # (Cout, Cin, K)
     out[name + ".w"] = w.permute(1, 2, 0).contiguous()   # [Cin][K][Cout]
     out[name + ".b"] = sd[base + ".bias"].float().contiguous()
+    if tc:
+        # tensor-core operand of the implicit-GEMM convolution (csrc/hift.cu: tc_conv): [Cout][2*K*Cp] fp16 = [hi | lo],
+        # column = tap*Cp + ci, input channels zero-padded to whole 64-wide k-blocks
+        cout, cin, k = w.shape
+        cp = (cin + 63) // 64 * 64
+        wp = torch.zeros(cout, k, cp)
+        wp[:, :, :cin] = w.permute(0, 2, 1)
+        out[name + ".w16"] = _split16(wp.reshape(cout, k * cp))
 
 
 def _conv_transpose(sd, base, out, name):
@@ -69,18 +77,24 @@ def pack_hift(sd: Dict[str, torch.Tensor], d: D.HiftDims, transposed: bool = Fal
     o["f0.cls.b"] = sd["f0_predictor.classifier.bias"].float().reshape(-1).contiguous()
     o["src.lin.w"] = sd["m_source.l_linear.weight"].float().reshape(-1).contiguous()
     o["src.lin.b"] = sd["m_source.l_linear.bias"].float().reshape(-1).contiguous()
-    _conv(sd, "conv_pre", o, "conv_pre")
-    _conv(sd, "conv_post", o, "conv_post")
+    tc = not transposed                 # the causal vocoder's decode stack runs on tensor cores (split-fp16 implicit GEMMs)
+    _conv(sd, "conv_pre", o, "conv_pre", tc)
+    _conv(sd, "conv_post", o, "conv_post", tc)
 
     def rb(src, dst):
         for j in range(len(d.rb_d)):
-            _conv(sd, f"{src}.convs1.{j}", o, f"{dst}.c1.{j}")
-            _conv(sd, f"{src}.convs2.{j}", o, f"{dst}.c2.{j}")
-            o[f"{dst}.a1.{j}"] = sd[f"{src}.activations1.{j}.alpha"].float().contiguous()
-            o[f"{dst}.a2.{j}"] = sd[f"{src}.activations2.{j}.alpha"].float().contiguous()
+            _conv(sd, f"{src}.convs1.{j}", o, f"{dst}.c1.{j}", tc)
+            _conv(sd, f"{src}.convs2.{j}", o, f"{dst}.c2.{j}", tc)
+            for a in ("1", "2"):
+                al = sd[f"{src}.activations{a}.{j}.alpha"].float().contiguous()
+                o[f"{dst}.a{a}.{j}"] = al
+                o[f"{dst}.ia{a}.{j}"] = (1.0 / (al + 1e-9)).contiguous()       # Snake: x + 1/(alpha + 1e-9) * sin(alpha x)^2 (activation.py:79-84)
 
     for i in range(len(d.ups)):
-        (_conv_transpose if transposed else _conv)(sd, f"ups.{i}", o, f"ups.{i}")
+        if transposed:
+            _conv_transpose(sd, f"ups.{i}", o, f"ups.{i}")
+        else:
+            _conv(sd, f"ups.{i}", o, f"ups.{i}", tc)
         _conv(sd, f"source_downs.{i}", o, f"sdown.{i}")
         rb(f"source_resblocks.{i}", f"srb.{i}")
         for j in range(len(d.rb_k)):

@@ -254,6 +254,20 @@ hvx_status hvx_llm_bench_kernels(hvx_engine* e, int n_seq, int head_k, int ctx, 
 hvx_status hvx_llm_debug_step(hvx_engine* e, int head_k, int ctx, int use_fused, int n_layers, float* h_out_dev,
                               float* logits_out_dev);
 
+/* Live per-class kernel timing for bench.py's roofline: while enabled, the launches of each class are bracketed by CUDA events on
+ * their own stream (not under graph capture).  hvx_profile_collect synchronises the device and returns, per class, the summed
+ * event-to-event milliseconds, the summed algorithmic work (FLOP for the tensor classes, bytes for the bandwidth classes) and
+ * the number of bracketed call sites since the last collect, then resets.  Arrays of HVX_PROF_NCLS entries. */
+enum { HVX_PROF_GEMM = 0,        /* tcgen05 GEMMs / implicit-GEMM convolutions: 2*M*N*K of the mathematical product */
+       HVX_PROF_ATTN = 1,        /* DiT / U-Net attention: 4 * queries * visible keys * 64 per head */
+       HVX_PROF_HIFT_CONV = 2,   /* HiFT convolutions: 2 * Cin * K * Cout * Lout */
+       HVX_PROF_LLM_STEP = 3,    /* one decode step (graph launch): work = 1 per step, bytes are computed by the caller */
+       HVX_PROF_LAYERNORM = 4,   /* adaLN LayerNorm + modulate: bytes read + written */
+       HVX_PROF_LLM_PREFILL = 5, /* prompt prefill of one sequence: 2 * rows * weights */
+       HVX_PROF_NCLS = 8 };
+hvx_status hvx_profile_enable(hvx_engine* e, int on);
+hvx_status hvx_profile_collect(hvx_engine* e, double* ms_out, double* work_out, int64_t* launches_out);
+
 /* bookkeeping for bench.py: number of kernels this library has launched since creation. */
 int64_t hvx_kernel_launches(hvx_engine* e);
 

@@ -103,6 +103,7 @@ def golden_llm_c2(dims, seed, n_text=128, n_ptext=16, P=125, K=2, ratio=8, depth
     on the CPU).  Weights are the synthetic checkpoint rounded to bf16 (what the engine holds; the reference serves in bf16,
     infer_speech_model.py:102) evaluated in fp32, stop logits zeroed (synth.llm_state_dict eos_scale=0) as in bench.py.
     Stored: the 1024 token ids, and the teacher-forced head log-probs of the reference modules at several depths."""
+    refshim.install()
     from cosyvoice.utils.common import ras_sampling
     sp = dict(top_p=0.9, top_k=10, win_size=24, tau_r=0.2)
     m = refshim.build_llm(dims)
@@ -344,6 +345,7 @@ def golden_flow(name, dims, N, P, n_steps, seed, modes=("full", "stream", "chunk
 
 
 def golden_llm(name, dims, n_text, n_ptext, P, cases, seed):
+    refshim.install()
     from cosyvoice.utils.common import ras_sampling
     m = refshim.build_llm(dims)
     sd = synth.llm_state_dict(dims, seed)

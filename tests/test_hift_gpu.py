@@ -61,6 +61,28 @@ def test_hift_matches_oracle_lengths(engines, T):
     assert (wav.cpu() - ref).pow(2).mean().sqrt().item() < 1e-4
 
 
+@pytest.mark.parametrize("name,T", [("tiny", 37), ("tiny", 1), ("full", 64), ("full", 3)])
+@pytest.mark.parametrize("finalize", [True, False])
+def test_hift_tensor_core_decode_equals_fp32_decode(engines, monkeypatch, name, T, finalize):
+    """The decode stack as split-fp16 implicit GEMMs on tcgen05 (default) against the fp32 CUDA-core convolutions
+    (HVX_HIFT_FP32=1) on the same F0 track: two implementations of the same arithmetic to ~22 mantissa bits per operand."""
+    e, h, hd = engines[name]
+    if not finalize and T < 9:
+        pytest.skip("streaming branch needs > 8 frames")
+    h.set_sine_table(synth.hift_sine_table(hd, T))
+    g = torch.Generator().manual_seed(100 + T)
+    mel = torch.rand(1, hd.mel, T, generator=g) * 6 - 6
+    monkeypatch.setenv("HVX_HIFT_FP32", "1")
+    ref, _, f0 = h.inference(mel, finalize=finalize, return_f0=True)
+    monkeypatch.setenv("HVX_HIFT_FP32", "0")
+    wav, _ = h.inference(mel, finalize=finalize, f0=f0)
+    d = (wav - ref)
+    rms, mx = d.pow(2).mean().sqrt().item(), d.abs().max().item()
+    print(f"[hift tc vs fp32 {name} T={T} finalize={finalize}] rms {rms:.3e} max-abs {mx:.3e} (wav rms {ref.pow(2).mean().sqrt():.3f})")
+    assert wav.shape == ref.shape and torch.isfinite(wav).all()
+    assert rms < 2e-5 and mx < 5e-4
+
+
 def test_hift_full_size_properties(engines):
     """BASELINE config-2 size (2048 frames = 40.96 s): causal-vocoder property of the reference's own
     self-check (generator.py:729-746) — a streamed prefix equals the offline result."""
