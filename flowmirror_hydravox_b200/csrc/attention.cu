@@ -895,13 +895,26 @@ dit_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     tc::tmem_ld_32x32(tmem_o + lane_off + 32, v + 32);
     tc::tmem_ld_wait();
     if (row_in_batch < T && a.lo_off) {
+      // split precision (flow parity mode): hi at [col], lo = y - hi at [lo_off + col]; 16-byte stores like the plain path
+      // (element-wise 2-byte stores made this epilogue as long as the whole key loop: 249 vs 479 TFLOP/s)
       const float inv = 1.0f / l_run;
       uint16_t* o = reinterpret_cast<uint16_t*>(a.out) + (size_t)(b * T + row_in_batch) * (2 * a.ld_out) + h * 64;
 #pragma unroll
-      for (int i = 0; i < 64; i++) {
-        const float y = __uint_as_float(v[i]) * inv;
-        o[i] = tc::cvt16(y, a.f16);
-        o[a.lo_off + i] = tc::lo16(y, a.f16);
+      for (int i = 0; i < 64; i += 8) {
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) y[j] = __uint_as_float(v[i + j]) * inv;
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          hi[j] = tc::pack16(y[2 * j], y[2 * j + 1], a.f16);
+          float r0, r1;
+          if (a.f16) { const __half2 t = *reinterpret_cast<const __half2*>(&hi[j]); r0 = y[2 * j] - __low2float(t); r1 = y[2 * j + 1] - __high2float(t); }
+          else { const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&hi[j]); r0 = y[2 * j] - __low2float(t); r1 = y[2 * j + 1] - __high2float(t); }
+          lo[j] = tc::pack16(r0, r1, a.f16);
+        }
+        *reinterpret_cast<uint4*>(o + i) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(o + a.lo_off + i) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
     } else if (row_in_batch < T) {
       const float inv = 1.0f / l_run;

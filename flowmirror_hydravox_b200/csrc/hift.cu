@@ -644,6 +644,9 @@ static hvx_status hift_decode_tc(hvx_engine* e, cudaStream_t st, const float* me
     HVX_LAUNCH_CHECK(e);
     { HiftEpi he; he.out32 = b.x_up; he.ld32 = C; he.row_shift = last ? 1 : 0; he.dup_row1 = last;
       if ((rc = tc_conv(e, st, h->ups[i], b.a_in, Lu, Lu, 1, h->ups[i].K - 1, he))) return rc; }
+    // a_in is re-used below as conv_post's operand [Lo][2*Cp]: epilogues write only the C real columns, so with padded channels
+    // the pad columns (and the extra reflected row) must not keep stale bit patterns (0 * NaN)
+    if (Cp != C && last) HVX_CUDA(cudaMemsetAsync(b.a_in, 0, sizeof(__half) * max16, st));
     // source branch: strided down-conv of the source STFT, then its ResBlock, "+ x_up" fused into its last epilogue, which also
     // writes Snake_{a1[0]}(x) for each of the parallel ResBlocks
     down /= u;
