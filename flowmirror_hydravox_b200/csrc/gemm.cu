@@ -5,6 +5,7 @@
 #include <mutex>
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 namespace hvx {
 
@@ -257,18 +258,43 @@ __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx,
           }
         }
       } else if (MODE == EPI_LLM_QKV) {
+        if (col0 + 32 <= N) llm_qkv_store32(epi.llm, row, col0, f);
+        else {
 #pragma unroll
-        for (int j = 0; j < 32; j += 2)
-          if (col0 + j < N) llm_qkv_store(epi.llm, row, col0 + j, f[j], f[j + 1]);
+          for (int j = 0; j < 32; j += 2)
+            if (col0 + j < N) llm_qkv_store(epi.llm, row, col0 + j, f[j], f[j + 1]);
+        }
       } else if (MODE == EPI_SWIGLU) {
         uint16_t* o = reinterpret_cast<uint16_t*>(epi.out) + (size_t)row * epi.ldo + (col0 >> 1);
+        if (col0 + 32 <= N && (epi.ldo & 7) == 0 && (epi.lo_off & 7) == 0) {
+          // 16 outputs of this row: two 16-byte stores for the hi halves, two for the lo halves (2-byte stores, one row per
+          // thread, cost more than the k-loop of the 128-row decode GEMM)
+          uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2)
-          if (col0 + j < N) {
-            const float y = (f[j] / (1.0f + expf(-f[j]))) * f[j + 1];
-            o[j >> 1] = tc::cvt16(y, epi.f16);
-            if (epi.lo_off) o[epi.lo_off + (j >> 1)] = tc::lo16(y, epi.f16);
+          for (int j = 0; j < 8; j++) {
+            const float y0 = (f[4 * j] / (1.0f + expf(-f[4 * j]))) * f[4 * j + 1];
+            const float y1 = (f[4 * j + 2] / (1.0f + expf(-f[4 * j + 2]))) * f[4 * j + 3];
+            hi[j] = tc::pack16(y0, y1, epi.f16);
+            float r0, r1;
+            if (epi.f16) { const __half2 t = *reinterpret_cast<const __half2*>(&hi[j]); r0 = y0 - __low2float(t); r1 = y1 - __high2float(t); }
+            else { const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&hi[j]); r0 = y0 - __low2float(t); r1 = y1 - __high2float(t); }
+            lo[j] = tc::pack16(r0, r1, epi.f16);
           }
+          reinterpret_cast<uint4*>(o)[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          reinterpret_cast<uint4*>(o)[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          if (epi.lo_off) {
+            reinterpret_cast<uint4*>(o + epi.lo_off)[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            reinterpret_cast<uint4*>(o + epi.lo_off)[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2)
+            if (col0 + j < N) {
+              const float y = (f[j] / (1.0f + expf(-f[j]))) * f[j + 1];
+              o[j >> 1] = tc::cvt16(y, epi.f16);
+              if (epi.lo_off) o[epi.lo_off + (j >> 1)] = tc::lo16(y, epi.f16);
+            }
+        }
       } else if (MODE == EPI_QKV) {
         const int t = row - bidx * epi.T;       // rows_per_batch == T
         if (col0 < epi.n_qk) {
@@ -339,6 +365,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  const bool dbg = ad.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  if (dbg && threadIdx.x == 0) ad.dbg[0] = tc::gtimer();
   if (warp == 0) {
     if (lane == 0) {
       for (int ki = 0; ki < nkb; ki++) {
@@ -346,6 +374,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int s = ki % STAGES;
         const uint32_t ph = (ki / STAGES) & 1;
         tc::mbar_wait(&empty_bar[s], ph ^ 1);
+        if (dbg && ki < 64) ad.dbg[1 + ki] = tc::gtimer();
         tc::mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
         uint8_t* sa = smem + s * S::STAGE_BYTES;
         const int tap = ad.kb_per_tap ? kb / ad.kb_per_tap : 0;
@@ -370,6 +399,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         tc::mbar_wait(&full_bar[s], ph);
+        if (dbg && kb < 64) ad.dbg[65 + kb] = tc::gtimer();
         tc::tc_fence_after();
         const uint32_t sa = tc::smem_u32(smem + s * S::STAGE_BYTES);
         if (TRI) {
@@ -398,6 +428,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int row_b = m0 + q * 32 + lane;
     const int row = batch * ad.rows_per_batch + row_b;
     tc::mbar_wait(tmem_full, 0);
+    if (dbg && threadIdx.x == 64) ad.dbg[130] = tc::gtimer();
     tc::tc_fence_after();
     const bool row_ok = row_b < ad.rows_per_batch && row < M;
     const int bidx = row / epi.rows_per_batch;
@@ -413,6 +444,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (dbg && threadIdx.x == 0) ad.dbg[131] = tc::gtimer();
   if (warp == 1) { __syncwarp(); tc::tmem_dealloc(tmem_base, BN); }
 }
 
@@ -581,6 +613,141 @@ static hvx_status launch_gemm_persist_t(hvx_engine* e, cudaStream_t st, const CU
   return HVX_OK;
 }
 
+
+// ------------------------------------------------------------------ CTA-pair variant of the three-term persistent GEMM
+// cta_group::2: the two CTAs of a cluster compute one 256 x 256 output tile with tcgen05.mma M = 256.  CTA r keeps rows
+// [128 r, 128 r + 128) of A (hi and lo) and rows [128 r, 128 r + 128) of the weight tile (hi and lo) in its own shared memory —
+// 64 KB per k-block and CTA for 3 x 128 x 256 x 64 MACs, against 96 KB for the single-CTA tile (the GEMMs are L2 -> SM
+// bandwidth bound) — and its 128 accumulator lanes in its own TMEM (double-buffered: 2 x 256 columns).  Only the leader issues
+// MMAs; both CTAs run a TMA producer (bytes credited to the leader's full barrier) and 8 epilogue warps over their own rows.
+constexpr int PAIR_STAGES = 3;
+struct PairSmem {
+  static constexpr int A_BYTES = BM * BK * 2;            // 128 rows of A (hi or lo)
+  static constexpr int B_BYTES = 128 * BK * 2;           // this CTA's half of the 256-row weight tile (hi or lo)
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int BAR_OFF = PAIR_STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+template <int MODE, int ACT>
+__global__ void __launch_bounds__(PERSIST_THREADS, 1)
+gemm_pair3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N, int K,
+                  GemmEpi epi, GemmAddr ad, int tiles_m, int tiles_n) {
+  using S = PairSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);      // leader's copy is the live one
+  uint64_t* empty_bar = full_bar + PAIR_STAGES;                             // per CTA, signalled by multicast commits
+  uint64_t* tmem_full = empty_bar + PAIR_STAGES;                            // [2] per CTA, multicast commits
+  uint64_t* tmem_empty = tmem_full + 2;                                     // [2] leader's copy: 16 arrivals (8 epilogue warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = tc::cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int nkb = ad.split3_kb;
+  const int n_tiles = tiles_m * tiles_n;                                    // tiles of 256 x 256
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tma_a);
+    tc::tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < PAIR_STAGES; s++) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; s++) { tc::mbar_init(&tmem_full[s], 1); tc::mbar_init(&tmem_empty[s], 16); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc_pair(tmem_slot, 2 * PBN);
+  tc::tc_fence_before();
+  tc::cluster_sync_all();            // barriers of both CTAs initialised before any remote arrive / TMA completion; also a CTA barrier
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+        const int mt = tile / tiles_n, nt = tile - mt * tiles_n;
+        const int row0 = mt * 256 + (int)rank * 128, brow0 = nt * PBN + (int)rank * 128;
+        for (int kb = 0; kb < nkb; kb++, it++) {
+          const int s = it % PAIR_STAGES;
+          const uint32_t ph = (it / PAIR_STAGES) & 1;
+          tc::mbar_wait(&empty_bar[s], ph ^ 1);
+          if (rank == 0) tc::mbar_expect_tx(&full_bar[s], 2 * S::STAGE_BYTES);      // both CTAs' loads land on this barrier
+          uint8_t* sa = smem + s * S::STAGE_BYTES;
+          tc::tma_load_3d_pair(sa, &tma_a, &full_bar[s], kb * BK, row0, 0);
+          tc::tma_load_3d_pair(sa + S::A_BYTES, &tma_a, &full_bar[s], ad.a_lo_off + kb * BK, row0, 0);
+          tc::tma_load_2d_pair(sa + 2 * S::A_BYTES, &tma_b, &full_bar[s], kb * BK, brow0);
+          tc::tma_load_2d_pair(sa + 2 * S::A_BYTES + S::B_BYTES, &tma_b, &full_bar[s], (ad.split3_kb + kb) * BK, brow0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = epi.f16 ? tc::umma_idesc_f16(256, PBN) : tc::umma_idesc_bf16(256, PBN);
+      int it = 0, t = 0;
+      for (int tile = pair; tile < n_tiles; tile += n_pairs, t++) {
+        const int as = t & 1;
+        tc::mbar_wait(&tmem_empty[as], ((t >> 1) & 1) ^ 1);       // both CTAs' epilogues drained this accumulator
+        tc::tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(as * PBN);
+        for (int kb = 0; kb < nkb; kb++, it++) {
+          const int s = it % PAIR_STAGES;
+          const uint32_t ph = (it / PAIR_STAGES) & 1;
+          tc::mbar_wait(&full_bar[s], ph);
+          tc::tc_fence_after();
+          const uint32_t sa = tc::smem_u32(smem + s * S::STAGE_BYTES);
+          const uint64_t a_hi = tc::umma_desc_k128(sa), a_lo = tc::umma_desc_k128(sa + S::A_BYTES);
+          const uint64_t b_hi = tc::umma_desc_k128(sa + 2 * S::A_BYTES), b_lo = tc::umma_desc_k128(sa + 2 * S::A_BYTES + S::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; k++) tc::umma_f16_pair(tacc, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < BK / 16; k++) tc::umma_f16_pair(tacc, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+#pragma unroll
+          for (int k = 0; k < BK / 16; k++) tc::umma_f16_pair(tacc, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+          tc::umma_commit_pair(&empty_bar[s]);                    // frees this stage in both CTAs
+        }
+        tc::umma_commit_pair(&tmem_full[as]);                     // accumulator complete: wakes both CTAs' epilogue warps
+      }
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    int t = 0;
+    for (int tile = pair; tile < n_tiles; tile += n_pairs, t++) {
+      const int mt = tile / tiles_n, nt = tile - mt * tiles_n;
+      const int as = t & 1;
+      const int row = mt * 256 + (int)rank * 128 + q * 32 + lane;
+      const bool row_ok = row < M;
+      const int bidx = row / epi.rows_per_batch;
+      const int colh = nt * PBN + half * (PBN / 2);
+      float pre[PBN / 2];
+      const bool use_pre = MODE == EPI_RESID_GATE && row_ok && colh + PBN / 2 <= N;
+      if (use_pre) {
+        const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(epi.out) + (size_t)row * epi.ldo + colh);
+#pragma unroll
+        for (int j = 0; j < PBN / 8; j++) { const float4 x4 = src[j]; pre[4 * j] = x4.x; pre[4 * j + 1] = x4.y; pre[4 * j + 2] = x4.z; pre[4 * j + 3] = x4.w; }
+      }
+      tc::mbar_wait(&tmem_full[as], (t >> 1) & 1);
+      tc::tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < PBN / 2; c += 32) {
+        uint32_t v[32];
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * PBN + half * (PBN / 2) + c), v);
+        tc::tmem_ld_wait();
+        const int col0 = colh + c;
+        if (!row_ok || col0 >= N) continue;
+        epi_store<MODE, ACT>(epi, row, bidx, col0, N, v, use_pre ? &pre[c] : nullptr);
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive_leader(&tmem_empty[as]);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync_all();            // nobody leaves while the peer's MMAs / commits can still touch this CTA's shared memory
+  if (warp == 1) { __syncwarp(); tc::tmem_dealloc_pair(tmem_base, 2 * PBN); }
+}
+
+
 // the (mode, activation) pairs the path uses; anything else is a programming error
 #define HVX_EPI_DISPATCH(CALL)                                                                   \
   do {                                                                                           \
@@ -603,6 +770,36 @@ static hvx_status launch_gemm_persist_t(hvx_engine* e, cudaStream_t st, const CU
     set_error("gemm: epilogue mode %d with activation %d is not instantiated", epi.mode, epi.act); \
     return HVX_ERR_UNSUPPORTED;                                                                  \
   } while (0)
+
+template <int MODE, int ACT>
+static hvx_status launch_gemm_pair_t(hvx_engine* e, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
+                                     int K, const GemmEpi& epi, const GemmAddr& ad) {
+  using S = PairSmem;
+  static bool attr_set = false;
+  if (!attr_set) {
+    HVX_CUDA(cudaFuncSetAttribute(gemm_pair3_kernel<MODE, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr_set = true;
+  }
+  const int tiles_m = cdiv(M, 256), tiles_n = cdiv(N, PBN);
+  const int n_pairs = std::max(1, std::min(tiles_m * tiles_n, e->sm_count / 2));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * n_pairs); cfg.blockDim = dim3(PERSIST_THREADS); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  HVX_CUDA(cudaLaunchKernelEx(&cfg, gemm_pair3_kernel<MODE, ACT>, ta, tb, M, N, K, epi, ad, tiles_m, tiles_n));
+  HVX_LAUNCH_CHECK(e);
+  return HVX_OK;
+}
+
+static hvx_status launch_gemm_pair(hvx_engine* e, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
+                                   int K, const GemmEpi& epi, const GemmAddr& ad) {
+#define PPCALL(MD, AC) launch_gemm_pair_t<MD, AC>(e, st, ta, tb, M, N, K, epi, ad)
+  HVX_EPI_DISPATCH(PPCALL);
+#undef PPCALL
+}
 
 static hvx_status launch_gemm_persist(hvx_engine* e, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
                                       int K, const GemmEpi& epi, const GemmAddr& ad) {
@@ -656,6 +853,27 @@ hvx_status gemm_bf16(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* A, int
   HVX_CHECK(!(ad.split3_kb && ad.split_k > 1), HVX_ERR_ARG, "gemm: split-K is not combined with the three-term product");
   HVX_CHECK((lda % 8) == 0 && (ldb % 8) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0, HVX_ERR_ARG,
             "gemm: operands must be 16-byte aligned with leading dims multiple of 8 (lda=%d ldb=%d)", lda, ldb);
+  static const bool timeline = getenv("HVX_GEMM_TIMELINE") != nullptr;
+  static unsigned long long* tl_dev = nullptr;
+  if (timeline) {
+    if (!tl_dev) HVX_CUDA(cudaMalloc(&tl_dev, 256 * sizeof(unsigned long long)));
+    HVX_CUDA(cudaMemsetAsync(tl_dev, 0, 256 * sizeof(unsigned long long), st));
+    ad.dbg = tl_dev;
+  }
+  struct TimelineDump {
+    bool on; cudaStream_t st; const unsigned long long* d; int M, N, K;
+    ~TimelineDump() {
+      if (!on) return;
+      unsigned long long h[256];
+      cudaStreamSynchronize(st);
+      cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+      if (!h[0] || !h[131]) return;                 // not the tile kernel
+      fprintf(stderr, "[gemm timeline M=%d N=%d K=%d] CTA(0,0,0): total %.2f us, accumulator complete at %.2f us\n  issue(us) / landed(us) per k-block:", M, N, K,
+              (h[131] - h[0]) * 1e-3, (h[130] - h[0]) * 1e-3);
+      for (int i = 0; i < 64 && h[1 + i]; i++) fprintf(stderr, " %d:%.2f/%.2f", i, (h[1 + i] - h[0]) * 1e-3, h[65 + i] ? (h[65 + i] - h[0]) * 1e-3 : -1.0);
+      fprintf(stderr, "\n");
+    }
+  } timeline_dump{timeline, st, tl_dev, M, N, K};
   const double k_alg = ad.split3_kb ? (double)K / 3.0 : (ad.b_kb_mod ? (double)ad.b_kb_mod * BK : (double)K);
   ProfScope prof_scope(e->prof_gemm_off ? nullptr : &e->prof, st, PROF_GEMM, 2.0 * (double)M * (double)N * k_alg);
   CUtensorMap ta, tb;
@@ -665,6 +883,12 @@ hvx_status gemm_bf16(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* A, int
   // big plain GEMMs (the DiT linears): persistent 128 x 256 tiles
   if (ad.split_k == 1 && ad.n_batch == 1 && ad.kb_per_tap == 0 && ad.b_kb_mod == 0 && ad.a_col0 == 0 && ad.a_col_per_ntile == 0 && ad.a_row0 == 0 &&
       N % PBN == 0 && cdiv(M, BM) * (N / PBN) >= e->sm_count / 2 && !getenv("HVX_NO_PERSIST")) {
+    static const bool no_pair = getenv("HVX_NO_PAIR") != nullptr;
+    if (ad.split3_kb && !no_pair && cdiv(M, 256) * (N / PBN) >= e->sm_count / 4) {
+      // three-term product on CTA pairs (cta_group::2): 128-row halves of the 256-row weight tile per CTA
+      HVX_CHECK(make_tmap_bf16_2d(&tb, B, N, kB, ldb, 128, BK), HVX_ERR_CUDA, "gemm: cuTensorMapEncodeTiled(B) failed");
+      return launch_gemm_pair(e, st, ta, tb, M, N, K, epi, ad);
+    }
     HVX_CHECK(make_tmap_bf16_2d(&tb, B, N, kB, ldb, PBN, BK), HVX_ERR_CUDA, "gemm: cuTensorMapEncodeTiled(B) failed");
     return launch_gemm_persist(e, st, ta, tb, M, N, K, epi, ad);
   }
@@ -695,5 +919,10 @@ extern "C" hvx_status hvx_gemm_bf16(hvx_engine* e, const void* A, const void* B,
   epi.bias = bias;
   epi.out = C;
   epi.ldo = N;
+  if (out_f32 & 4) {                                 // bit 2: A (M, 2K) and B (N, 2K) are split [hi | lo]: three-term product
+    GemmAddr ga; ga.split3_kb = K / 64;
+    HVX_CHECK(K % 64 == 0, HVX_ERR_ARG, "gemm: the three-term product needs K %% 64 == 0");
+    return gemm_bf16(e, (cudaStream_t)stream, (const __nv_bfloat16*)A, 2 * K, (const __nv_bfloat16*)B, 2 * K, M, N, 3 * K, epi, &ga);
+  }
   return gemm_bf16(e, (cudaStream_t)stream, (const __nv_bfloat16*)A, K, (const __nv_bfloat16*)B, K, M, N, K, epi);
 }

@@ -87,6 +87,9 @@ struct GemmAddr {
   // the caller sums the partials in a fixed order (deterministic, no atomics)
   int split_k = 1;
   size_t split_stride = 0;
+  // HVX_GEMM_TIMELINE=1 (diagnostic): %globaltimer stamps of CTA (0,0,0) of the tile kernel — [0] start, [1+kb] TMA of k-block kb
+  // issued, [65+kb] its data landed (MMA side), [130] accumulator complete, [131] epilogue done
+  unsigned long long* dbg = nullptr;
 };
 
 hvx_status gemm_bf16(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb,

@@ -667,6 +667,204 @@ __global__ void __launch_bounds__(256) llm_attn_kernel(AttnDecArgs a) {
   if (tid == 0) a.counters[row * a.kv_heads + kvh] = 0;
 }
 
+
+// ---- decode attention, one block per (sequence, kv head, key slice): the head_k rows a sequence decodes in one step
+// (positions ctx .. ctx+n_new-1) attend over the SAME cache, so the K/V chunk staged in shared memory is shared by all of them —
+// llm_attn_kernel gives every row its own block and re-reads the cache head_k times, which at 32 sequences x 4 rows x 2600 keys
+// (BASELINE configs[2]) made the attention the largest part of the decode step.  Warp (g, p): q head kv*group+g, row pair p
+// (rows 2p, 2p+1); 4 lanes share a key (16 dims each), 8 keys per warp iteration; the chunk ring is double-buffered with
+// cp.async.  Partials go to `part` and the last-arriving block of a (sequence, kv head) merges them (fixed order: deterministic).
+template <bool KV32>
+__global__ void __launch_bounds__(512) llm_attn_seq_kernel(AttnDecArgs a) {
+  using KT = typename std::conditional<KV32, float, __nv_bfloat16>::type;
+  constexpr int LD = KV32 ? ATT_LD32 : ATT_LD;
+  constexpr int SEGS = KV32 ? 16 : 8;
+  constexpr int CHUNK = KV32 ? ATT_KEYS / 2 : ATT_KEYS;
+  constexpr int EPS = 16 / (int)sizeof(KT);
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  KT* sk = reinterpret_cast<KT*>(att_smem);                    // [2][CHUNK * LD]
+  KT* sv = sk + 2 * CHUNK * LD;
+  __shared__ int s_last;
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = warp % a.group, pr = warp / a.group;
+  const int split = blockIdx.x;
+  const int seq = blockIdx.y / a.kv_heads, kvh = blockIdx.y - seq * a.kv_heads;
+  const SeqState& s = a.seqs[seq];
+  if (s.done || s.n_new <= 0) return;
+  const int n_new = min(s.n_new, a.rows_per_seq);
+  const int n_keys = min(s.ctx + n_new, a.max_ctx);
+  const int per = (n_keys + a.splits - 1) / a.splits;
+  const int k_begin = split * per, k_end = min(n_keys, k_begin + per);
+  const int qh = kvh * a.group + g;
+  const int sub = lane & 3, kslot = lane >> 2;
+  const int r0 = 2 * pr;
+  const bool live0 = r0 < n_new, live1 = r0 + 1 < n_new;
+  const int pos0 = s.ctx + r0, pos1 = pos0 + 1;               // last key row r sees
+  float q0[16], q1[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) { q0[i] = 0.f; q1[i] = 0.f; }
+  if (live0) {
+    const float4* qp = reinterpret_cast<const float4*>(a.q + (size_t)(seq * a.rows_per_seq + r0) * a.ldq + qh * 64 + sub * 16);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const float4 t = qp[i]; q0[4 * i] = t.x * a.scale; q0[4 * i + 1] = t.y * a.scale; q0[4 * i + 2] = t.z * a.scale; q0[4 * i + 3] = t.w * a.scale; }
+  }
+  if (live1) {
+    const float4* qp = reinterpret_cast<const float4*>(a.q + (size_t)(seq * a.rows_per_seq + r0 + 1) * a.ldq + qh * 64 + sub * 16);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const float4 t = qp[i]; q1[4 * i] = t.x * a.scale; q1[4 * i + 1] = t.y * a.scale; q1[4 * i + 2] = t.z * a.scale; q1[4 * i + 3] = t.w * a.scale; }
+  }
+  float m0 = -INFINITY, l0 = 0.f, m1 = -INFINITY, l1 = 0.f, o0[16], o1[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) { o0[i] = 0.f; o1[i] = 0.f; }
+  const KT* kb = reinterpret_cast<const KT*>(a.kc) + (size_t)seq * a.seq_stride + (size_t)kvh * a.max_ctx * 64;
+  const KT* vb = reinterpret_cast<const KT*>(a.vc) + (size_t)seq * a.seq_stride + (size_t)kvh * a.max_ctx * 64;
+  auto stage = [&](int c0, int buf) {
+    const int nk = min(CHUNK, k_end - c0);
+    KT* dk = sk + buf * CHUNK * LD;
+    KT* dv = sv + buf * CHUNK * LD;
+    for (int i = tid; i < nk * SEGS; i += blockDim.x) {
+      const int key = i / SEGS, seg = i - key * SEGS;
+      const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dk + key * LD + seg * EPS);
+      const uint32_t d1 = (uint32_t)__cvta_generic_to_shared(dv + key * LD + seg * EPS);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(kb + (size_t)(c0 + key) * 64 + seg * EPS) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d1), "l"(vb + (size_t)(c0 + key) * 64 + seg * EPS) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int buf = 0;
+  if (k_begin < k_end) stage(k_begin, 0);
+  for (int c0 = k_begin; c0 < k_end; c0 += CHUNK, buf ^= 1) {
+    const int nk = min(CHUNK, k_end - c0);
+    if (c0 + CHUNK < k_end) { stage(c0 + CHUNK, buf ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const KT* ck = sk + buf * CHUNK * LD;
+    const KT* cv = sv + buf * CHUNK * LD;
+    if (live0) {
+      for (int k0 = 0; k0 < nk; k0 += 8) {
+        const int key = k0 + kslot;
+        const bool live = key < nk;
+        const int kabs = c0 + key;
+        float kf[16], vf[16];
+        if (live) {
+          if constexpr (KV32) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              const float4 u = *reinterpret_cast<const float4*>(&ck[key * LD + sub * 16 + 4 * i]);
+              const float4 w = *reinterpret_cast<const float4*>(&cv[key * LD + sub * 16 + 4 * i]);
+              kf[4 * i] = u.x; kf[4 * i + 1] = u.y; kf[4 * i + 2] = u.z; kf[4 * i + 3] = u.w;
+              vf[4 * i] = w.x; vf[4 * i + 1] = w.y; vf[4 * i + 2] = w.z; vf[4 * i + 3] = w.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+              const uint4 u = *reinterpret_cast<const uint4*>(&ck[key * LD + sub * 16 + 8 * i]);
+              const uint4 w = *reinterpret_cast<const uint4*>(&cv[key * LD + sub * 16 + 8 * i]);
+              kf[8 * i] = bf_lo(u.x); kf[8 * i + 1] = bf_hi(u.x); kf[8 * i + 2] = bf_lo(u.y); kf[8 * i + 3] = bf_hi(u.y);
+              kf[8 * i + 4] = bf_lo(u.z); kf[8 * i + 5] = bf_hi(u.z); kf[8 * i + 6] = bf_lo(u.w); kf[8 * i + 7] = bf_hi(u.w);
+              vf[8 * i] = bf_lo(w.x); vf[8 * i + 1] = bf_hi(w.x); vf[8 * i + 2] = bf_lo(w.y); vf[8 * i + 3] = bf_hi(w.y);
+              vf[8 * i + 4] = bf_lo(w.z); vf[8 * i + 5] = bf_hi(w.z); vf[8 * i + 6] = bf_lo(w.w); vf[8 * i + 7] = bf_hi(w.w);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; i++) { kf[i] = 0.f; vf[i] = 0.f; }
+        }
+        float sc0 = 0.f, sc1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; i++) { sc0 = fmaf(q0[i], kf[i], sc0); sc1 = fmaf(q1[i], kf[i], sc1); }
+        sc0 += __shfl_xor_sync(0xffffffffu, sc0, 1); sc1 += __shfl_xor_sync(0xffffffffu, sc1, 1);
+        sc0 += __shfl_xor_sync(0xffffffffu, sc0, 2); sc1 += __shfl_xor_sync(0xffffffffu, sc1, 2);
+        if (live && kabs <= pos0) {
+          if (sc0 > m0) {
+            const float al = expf(m0 - sc0);
+            l0 *= al;
+#pragma unroll
+            for (int i = 0; i < 16; i++) o0[i] *= al;
+            m0 = sc0;
+          }
+          const float pw = expf(sc0 - m0);
+          l0 += pw;
+#pragma unroll
+          for (int i = 0; i < 16; i++) o0[i] = fmaf(pw, vf[i], o0[i]);
+        }
+        if (live && live1 && kabs <= pos1) {
+          if (sc1 > m1) {
+            const float al = expf(m1 - sc1);
+            l1 *= al;
+#pragma unroll
+            for (int i = 0; i < 16; i++) o1[i] *= al;
+            m1 = sc1;
+          }
+          const float pw = expf(sc1 - m1);
+          l1 += pw;
+#pragma unroll
+          for (int i = 0; i < 16; i++) o1[i] = fmaf(pw, vf[i], o1[i]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const int q_heads = a.kv_heads * a.group;
+  // merge the 8 key slots of each row (lanes with equal `sub`), publish the partial of this slice
+#pragma unroll
+  for (int rr = 0; rr < 2; rr++) {
+    float* o = rr ? o1 : o0;
+    const float m = rr ? m1 : m0, l = rr ? l1 : l0;
+    const bool lv = rr ? live1 : live0;
+    float M = m;
+    for (int sft = 4; sft < 32; sft <<= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, sft));
+    const float wgt = (m == -INFINITY) ? 0.f : expf(m - M);
+    float Lr = l * wgt;
+    for (int sft = 4; sft < 32; sft <<= 1) Lr += __shfl_xor_sync(0xffffffffu, Lr, sft);
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      float v = o[i] * wgt;
+      for (int sft = 4; sft < 32; sft <<= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+      o[i] = v;
+    }
+    if (lv) {
+      const int row = seq * a.rows_per_seq + r0 + rr;
+      float* pp = a.part + (((size_t)row * q_heads + qh) * a.splits + split) * 68;
+      if (kslot == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) *reinterpret_cast<float4*>(&pp[4 + sub * 16 + 4 * i]) = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+      }
+      if (lane == 0) { pp[0] = M; pp[1] = Lr; }
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&a.counters[seq * a.kv_heads + kvh], 1) == a.splits - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int rr = 0; rr < 2; rr++) {
+    if (!(rr ? live1 : live0)) continue;
+    const int row = seq * a.rows_per_seq + r0 + rr;
+    const float* pb = a.part + ((size_t)row * q_heads + qh) * a.splits * 68;
+    float Mx = -INFINITY;
+    for (int sp = 0; sp < a.splits; sp++) Mx = fmaxf(Mx, __ldcg(pb + sp * 68));
+    float Ls = 0.f, a_lo = 0.f, a_hi = 0.f;
+    for (int sp = 0; sp < a.splits; sp++) {
+      const float ms = __ldcg(pb + sp * 68);
+      const float w = (ms == -INFINITY) ? 0.f : expf(ms - Mx);
+      Ls += __ldcg(pb + sp * 68 + 1) * w;
+      a_lo += __ldcg(pb + sp * 68 + 4 + lane) * w;
+      a_hi += __ldcg(pb + sp * 68 + 36 + lane) * w;
+    }
+    const float inv = 1.0f / Ls;
+    if (a.out) { a.out[(size_t)row * a.ldo + qh * 64 + lane] = a_lo * inv; a.out[(size_t)row * a.ldo + qh * 64 + 32 + lane] = a_hi * inv; }
+    if (a.out16) {
+      store_split(a.out16 + (size_t)row * 2 * a.ldo, a.ldo, qh * 64 + lane, a_lo * inv);
+      store_split(a.out16 + (size_t)row * 2 * a.ldo, a.ldo, qh * 64 + 32 + lane, a_hi * inv);
+    }
+  }
+  if (tid == 0) a.counters[seq * a.kv_heads + kvh] = 0;
+}
+
 // ------------------------------------------------------------------ small kernels
 // prompt rows [sos, embed_tokens(prompt_text || text), task_id, speech_embedding(prompt_speech)]  (:943-952)
 __global__ void llm_prompt_rows_kernel(const int32_t* __restrict__ text, int n_text, const int32_t* __restrict__ pspeech,
@@ -681,6 +879,15 @@ __global__ void llm_prompt_rows_kernel(const int32_t* __restrict__ text, int n_t
   for (int i = threadIdx.x; i < H; i += blockDim.x) h[(size_t)row * H + i] = __bfloat162float(src[i]);
 }
 
+// (cos, sin)(pos * inv_freq[i]) with the very sincosf llm_qkv_store evaluates per element (bit-identical RoPE on both paths)
+__global__ void llm_rope_table_kernel(const float* __restrict__ inv_freq, float2* __restrict__ tab, int max_ctx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 32 * max_ctx) return;
+  float sn, cs;
+  sincosf((float)(i >> 5) * inv_freq[i & 31], &sn, &cs);
+  tab[i] = make_float2(cs, sn);
+}
+
 // rmsnorm rows for the tensor-core path, written as split bf16 [hi | lo] (row length 2H) so the GEMM sees
 // fp32-accurate activations: out = norm_w * (x * rsqrt(mean(x^2) + eps))
 __global__ void __launch_bounds__(256) llm_norm16_kernel(const float* __restrict__ x, const float* __restrict__ w,
@@ -692,7 +899,24 @@ __global__ void __launch_bounds__(256) llm_norm16_kernel(const float* __restrict
   for (int k = lane; k < H; k += 32) { const float v = xr[k]; ss += v * v; }
   for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   const float sc = rsqrtf(ss / (float)H + eps);
-  for (int k = lane; k < H; k += 32) store_split(out + (size_t)row * 2 * H, H, k, w[k] * (xr[k] * sc));
+  __nv_bfloat16* orow = out + (size_t)row * 2 * H;
+  if ((H & 7) == 0) {
+    // 8 features per lane and pass: one 16-byte store for the hi halves, one for the lo halves
+    for (int k = lane * 8; k < H; k += 256) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const float y0 = w[k + 2 * j] * (xr[k + 2 * j] * sc), y1 = w[k + 2 * j + 1] * (xr[k + 2 * j + 1] * sc);
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(y0 - __low2float(h2), y1 - __high2float(h2));
+        hi[j] = *reinterpret_cast<const uint32_t*>(&h2); lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
+      }
+      *reinterpret_cast<uint4*>(orow + k) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(orow + H + k) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  } else {
+    for (int k = lane; k < H; k += 32) store_split(orow, H, k, w[k] * (xr[k] * sc));
+  }
 }
 
 // hn[seq] = final rmsnorm of the last live row of every sequence (llm_multi_head_v3.py:258,883-886)
@@ -974,6 +1198,7 @@ struct LlmState {
   const __nv_bfloat16 *m_v_w, *m_o_w, *m_gu_w, *m_down_w;     // stacked over MTP heads
   const float *m_v_b, *m_ln1, *m_ln2;
   float* inv_freq = nullptr;
+  float2* rope = nullptr;                 // [max_ctx][32] (cos, sin) of pos * inv_freq[i]: the tensor-core path's RoPE operands
   uint8_t *kc = nullptr, *vc = nullptr;                       // [layer][seq][kv_head][max_ctx][64], bf16 or fp32
   int kv_f32 = 0; size_t kv_esz = 2;
   size_t layer_stride = 0, seq_stride = 0;
@@ -1056,6 +1281,9 @@ hvx_status llm_finalize(hvx_engine* e) {
     for (int i = 0; i < 32; i++) inv[i] = 1.0f / powf(c.llm_rope_theta, (float)(2 * i) / 64.0f);   // HF Qwen2RotaryEmbedding
     HVX_CUDA(cudaMalloc(&L->inv_freq, sizeof(inv)));
     HVX_CUDA(cudaMemcpy(L->inv_freq, inv, sizeof(inv), cudaMemcpyHostToDevice));
+    HVX_CUDA(cudaMalloc(&L->rope, sizeof(float2) * 32 * (size_t)c.llm_max_ctx));
+    llm_rope_table_kernel<<<cdiv(32 * c.llm_max_ctx, 256), 256>>>(L->inv_freq, L->rope, c.llm_max_ctx);
+    HVX_CUDA(cudaDeviceSynchronize());
     L->desc.resize(c.llm_max_seqs);
     HVX_CUDA(cudaMalloc(&L->layers_dev, sizeof(LlmLayer) * 64));
     HVX_CUDA(cudaMalloc(&L->fused_bar, sizeof(unsigned long long)));
@@ -1075,7 +1303,7 @@ void llm_free(hvx_engine* e) {
   LlmState* L = e->llm;
   if (!L) return;
   if (L->graph) cudaGraphExecDestroy(L->graph);
-  cudaFree(L->kc); cudaFree(L->vc); cudaFree(L->seqs); cudaFree(L->n_active); cudaFree(L->inv_freq);
+  cudaFree(L->kc); cudaFree(L->vc); cudaFree(L->seqs); cudaFree(L->n_active); cudaFree(L->inv_freq); cudaFree(L->rope);
   cudaFree(L->layers_dev); cudaFree(L->fused_bar); cudaFree(L->fused_abort);
   if (L->n_active_host) cudaFreeHost(L->n_active_host);
   if (L->own) cudaStreamDestroy(L->own);
@@ -1276,7 +1504,7 @@ static LlmQkvEpi make_qkv(hvx_engine* e, LlmState* L, int layer, float* q, const
   p.kc = L->kc + (size_t)layer * L->layer_stride * L->kv_esz; p.vc = L->vc + (size_t)layer * L->layer_stride * L->kv_esz;
   p.kv_f32 = L->kv_f32;
   p.seq_stride = L->seq_stride; p.max_ctx = c.llm_max_ctx; p.q_dim = c.llm_q_heads * 64; p.kv_dim = c.llm_kv_heads * 64;
-  p.inv_freq = L->inv_freq; p.seqs = seqs; p.rows_per_seq = rows_per_seq; p.seq0 = seq0; p.pos0 = pos0; p.n_rows = n_rows;
+  p.inv_freq = L->inv_freq; p.rope = L->rope; p.seqs = seqs; p.rows_per_seq = rows_per_seq; p.seq0 = seq0; p.pos0 = pos0; p.n_rows = n_rows;
   return p;
 }
 
@@ -1290,6 +1518,26 @@ static hvx_status launch_attn(hvx_engine* e, cudaStream_t st, LlmState* L, int l
   a.seqs = seqs; a.rows_per_seq = rows_per_seq; a.seq0 = seq0; a.pos0 = pos0; a.n_rows = rows; a.splits = splits;
   a.part = b.part; a.counters = b.counters; a.out = b.att; a.out16 = want16 ? b.att16 : nullptr; a.ldo = c.llm_hidden;
   a.scale = 1.0f / sqrtf((float)c.llm_head_dim);
+  static const bool no_seq_attn = getenv("HVX_NO_SEQ_ATTN") != nullptr;
+  if (seqs && want16 && rows_per_seq >= 1 && 32 * a.group * ((rows_per_seq + 1) / 2) <= 512 && !no_seq_attn) {
+    // batched decode: one block per (sequence, kv head, key slice); the rows of a sequence share the staged cache chunk
+    const int n_seq = rows / rows_per_seq, pairs = (rows_per_seq + 1) / 2;
+    a.splits = std::max(1, std::min(16, e->sm_count / std::max(1, n_seq * c.llm_kv_heads)));
+    const size_t elt = L->kv_f32 ? (size_t)(ATT_KEYS / 2) * ATT_LD32 * 4 : (size_t)ATT_KEYS * ATT_LD * 2;
+    const size_t smem = 4 * elt;                                            // K and V, two buffers each
+    static bool attr_set = false;
+    if (!attr_set) {
+      HVX_CUDA(cudaFuncSetAttribute(llm_attn_seq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (ATT_KEYS / 2) * ATT_LD32 * 4));
+      HVX_CUDA(cudaFuncSetAttribute(llm_attn_seq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * ATT_KEYS * ATT_LD * 2));
+      attr_set = true;
+    }
+    HVX_CHECK((size_t)rows * c.llm_q_heads * a.splits * 68 <= b.part_floats, HVX_ERR_STATE, "llm: attention partial buffer too small");
+    dim3 sgrid(a.splits, n_seq * c.llm_kv_heads);
+    if (L->kv_f32) HVX_CUDA(launch_pdl(llm_attn_seq_kernel<true>, sgrid, dim3(32 * a.group * pairs), smem, st, a));
+    else HVX_CUDA(launch_pdl(llm_attn_seq_kernel<false>, sgrid, dim3(32 * a.group * pairs), smem, st, a));
+    HVX_LAUNCH_CHECK(e);
+    return HVX_OK;
+  }
   dim3 grid(splits, rows * c.llm_kv_heads);
   if (splits > 1 && splits <= 16 && !getenv("HVX_NO_CLUSTER_ATTN")) {
     static bool np_set = false;
@@ -1679,6 +1927,21 @@ extern "C" hvx_status hvx_llm_generate(hvx_engine* e, int n_seq, int head_k, con
     HVX_CUDA(cudaStreamSynchronize(st));
     HVX_CHECK(aborted == 0, HVX_ERR_CUDA, "llm: fused decode step timed out on a barrier (code %d)", aborted);
   } else {
+  static const bool no_graph = getenv("HVX_LLM_NO_GRAPH") != nullptr;      // diagnostics: eager steps (HVX_GEMM_TIMELINE needs them)
+  if (no_graph) {
+    for (int step = 0; step < max_steps;) {
+      const int n = std::min(poll, max_steps - step);
+      for (int i = 0; i < n; i++) {
+        if ((rc = llm_layers(e, st, L, b, rows, L->seqs, head_k, 0, 0, splits))) return rc;
+        if ((rc = llm_heads(e, st, L, b, n_seq, head_k, head_k))) return rc;
+        if ((rc = launch_sampler(e, st, sa, n_seq))) return rc;
+      }
+      step += n;
+      HVX_CUDA(cudaMemcpyAsync(L->n_active_host, L->n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+      HVX_CUDA(cudaStreamSynchronize(st));
+      if (*L->n_active_host <= 0 || e->llm_cancel.load()) break;
+    }
+  } else {
   // one decode step = fixed launch sequence -> CUDA graph (re-captured when shapes or buffers change)
   const int key[4] = {n_seq, head_k, (int)((uintptr_t)b.h >> 8), (int)((uintptr_t)out_tokens >> 4) ^ (int)((uintptr_t)u_dev >> 4) ^ (sp->top_k << 20) ^ sp->win_size};
   const bool same = L->graph && !memcmp(key, L->graph_key, sizeof(key)) && !memcmp(&sa, &L->graph_samp, sizeof(sa));
@@ -1710,6 +1973,7 @@ extern "C" hvx_status hvx_llm_generate(hvx_engine* e, int n_seq, int head_k, con
     HVX_CUDA(cudaMemcpyAsync(L->n_active_host, L->n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
     HVX_CUDA(cudaStreamSynchronize(st));
     if (*L->n_active_host <= 0 || e->llm_cancel.load()) break;
+  }
   }
   }
   // surface sampler failures the way the reference raises (llm_multi_head_v3.py:165)

@@ -236,7 +236,8 @@ hvx_status hvx_synthesize_host(hvx_engine* e, const hvx_request* reqs, int n_req
 hvx_status hvx_speed_interp(hvx_engine* e, const float* mel_dev, int C, int T, int T_out, float* out_dev, void* stream);
 
 /* ---- diagnostic entries for the kernel-level parity tests (tests/test_gemm_gpu.py) ----
- * C = act(A*B^T + bias): A (M,K) bf16, B (N,K) bf16 (nn.Linear weight layout), C bf16 or fp32. */
+ * C = act(A*B^T + bias): A (M,K) bf16, B (N,K) bf16 (nn.Linear weight layout), C bf16 or fp32.  out_f32 bit 0: fp32 output,
+ * bit 1: fp16 operands, bit 2: split-precision operands A (M,2K) = [hi | lo], B (N,2K) = [hi | lo] -> three-term product. */
 hvx_status hvx_gemm_bf16(hvx_engine* e, const void* A_dev, const void* B_dev, const float* bias_dev, void* C_dev,
                          int M, int N, int K, int out_f32, int act, void* stream);
 /* softmax(q k^T / 8 + mask) v per (batch, head): qk (B*T, 2*H*64) = q|k, vt (B*H*64, vt_ld) = V^T. */

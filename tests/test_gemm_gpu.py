@@ -37,6 +37,36 @@ def test_gemm(eng, M, N, K, out_f32, act):
     assert err < tol, err
 
 
+def _split16(x):
+    hi = x.to(torch.float16)
+    return torch.cat([hi, (x - hi.float()).to(torch.float16)], dim=1).contiguous()
+
+
+@pytest.mark.parametrize("M,N,K", [(4596, 1024, 1024), (4596, 3072, 1024), (4596, 1024, 2048), (16200, 2048, 1024), (300, 1024, 1024),
+                                   (2298, 80, 1024), (130, 256, 256), (4596, 1024, 64)])
+@pytest.mark.parametrize("pair", [True, False])
+def test_gemm_three_term_split_precision(eng, monkeypatch, M, N, K, pair):
+    """A_hi W_hi + A_lo W_hi + A_hi W_lo on split-fp16 operands (the flow's parity mode; tile-sharing stages, and the CTA-pair
+    cta_group::2 kernel for the big shapes unless HVX_NO_PAIR): fp32-level agreement with the fp64 product."""
+    from flowmirror_hydravox_b200 import _lib as L
+    if not pair:
+        monkeypatch.setenv("HVX_NO_PAIR", "1")
+    else:
+        monkeypatch.delenv("HVX_NO_PAIR", raising=False)
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g) * 0.5
+    B = torch.randn(N, K, device="cuda", generator=g) * (1.0 / K ** 0.5)
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = torch.zeros(M, N, device="cuda", dtype=torch.float32)
+    A2, B2 = _split16(A), _split16(B)                       # keep the operands alive for the duration of the call
+    L.check(L.lib().hvx_gemm_bf16(eng.h, L.ptr(A2), L.ptr(B2), L.ptr(bias), L.ptr(out), M, N, K, 1 | 2 | 4, 0, L.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = (A.double() @ B.double().T + bias.double()).float()
+    err = (out - ref).abs().max().item()
+    print(f"[gemm3 {M}x{N}x{K} pair={pair}] max-abs {err:.3e}")
+    assert err < 5e-5, err
+
+
 @pytest.mark.parametrize("B,T,H,chunk", [(1, 128, 1, 0), (2, 200, 2, 0), (2, 1000, 16, 0), (2, 333, 4, 50), (1, 2298, 16, 0)])
 def test_attention(eng, B, T, H, chunk):
     from flowmirror_hydravox_b200 import _lib as L
