@@ -865,6 +865,286 @@ __global__ void __launch_bounds__(512) llm_attn_seq_kernel(AttnDecArgs a) {
   if (tid == 0) a.counters[seq * a.kv_heads + kvh] = 0;
 }
 
+// ---- batched decode attention on the tensor cores (mma.sync m16n8k16, bf16 operands, fp32 accumulate)
+// One block per (sequence, kv head, key slice).  The `group` q heads of the kv head x the n_new <= 4 rows the sequence decodes
+// this step form ONE 32-row query tile (row m = r * group + g), so every staged key is used by all of them from one fragment
+// load: the CUDA-core kernels above spend ~6 instructions per (key, query row), this one < 1.
+//   S (32 x 16 keys per warp and chunk) = Q K^T,  P = exp(S - m),  O (32 x 64) += P V        (flash-decoding, online softmax)
+// Operands are split into bf16 (hi, lo) pairs and multiplied as hi*hi + lo*hi (+ hi*lo when the cache is fp32) — 16+ mantissa
+// bits per operand — so the tokens of a batch stay those of the single-sequence fp32 path (tests/test_llm_gpu.py).
+// 8 warps; warp w owns keys [16 w, 16 w + 16) of every 128-key chunk (cp.async double buffer); per-warp partials are merged
+// through shared memory, slices through `part` + the last-arriver merge of llm_attn_kernel.
+constexpr int AM_CH = 128;            // keys per chunk
+constexpr int AM_LDQ = 72;            // bf16 elements per Q row (144 B: conflict-free ldmatrix)
+constexpr int AM_LDK32 = 72, AM_LDV32 = 68;   // fp32 cache: K rows read as float2 per (key g, dims 2t), V as scalars per (key 2t, dim g)
+constexpr int AM_LD16 = 72;           // bf16 cache
+
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_bf16x2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(x - __low2float(h), y - __high2float(h));
+  hi = *reinterpret_cast<const uint32_t*>(&h); lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+template <bool KV32>
+__global__ void __launch_bounds__(256, 1) llm_attn_mma_kernel(AttnDecArgs a) {
+  using KT = typename std::conditional<KV32, float, __nv_bfloat16>::type;
+  constexpr int LDK = KV32 ? AM_LDK32 : AM_LD16, LDV = KV32 ? AM_LDV32 : AM_LD16;
+  constexpr int SEGS = KV32 ? 16 : 8, EPS = 16 / (int)sizeof(KT);
+  extern __shared__ __align__(16) uint8_t am_smem[];
+  __nv_bfloat16* qhi = reinterpret_cast<__nv_bfloat16*>(am_smem);          // [32][AM_LDQ]
+  __nv_bfloat16* qlo = qhi + 32 * AM_LDQ;
+  KT* sk = reinterpret_cast<KT*>(qlo + 32 * AM_LDQ);                       // [2][AM_CH * LDK]
+  KT* sv = sk + 2 * AM_CH * LDK;                                           // [2][AM_CH * LDV]
+  __shared__ int s_last;
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int split = blockIdx.x;
+  const int seq = blockIdx.y / a.kv_heads, kvh = blockIdx.y - seq * a.kv_heads;
+  const SeqState& s = a.seqs[seq];
+  if (s.done || s.n_new <= 0) return;
+  const int n_new = min(s.n_new, a.rows_per_seq);
+  const int n_rows = n_new * a.group;                                      // live query rows of the tile (<= 32)
+  const int n_keys = min(s.ctx + n_new, a.max_ctx);
+  const int per = (n_keys + a.splits - 1) / a.splits;
+  const int k_begin = split * per, k_end = min(n_keys, k_begin + per);
+  // ---- Q tile: row m = r * group + gq  <-  q[(seq, r)][head kvh*group+gq] * scale, as bf16 hi / lo; zero the staging ring
+  for (int i = tid; i < 32 * 64; i += 256) {
+    const int m = i >> 6, d = i & 63;
+    float v = 0.f;
+    if (m < n_rows) { const int r = m / a.group, gq = m - r * a.group; v = a.q[(size_t)(seq * a.rows_per_seq + r) * a.ldq + (kvh * a.group + gq) * 64 + d] * a.scale; }
+    const __nv_bfloat16 h = __float2bfloat16(v);
+    qhi[m * AM_LDQ + d] = h;
+    qlo[m * AM_LDQ + d] = __float2bfloat16(v - __bfloat162float(h));
+  }
+  { uint4* z = reinterpret_cast<uint4*>(sk);
+    const int nz = (int)((2 * AM_CH * (LDK + LDV) * sizeof(KT)) / 16);
+    for (int i = tid; i < nz; i += 256) z[i] = make_uint4(0, 0, 0, 0); }
+  __syncthreads();
+  const KT* kb = reinterpret_cast<const KT*>(a.kc) + (size_t)seq * a.seq_stride + (size_t)kvh * a.max_ctx * 64;
+  const KT* vb = reinterpret_cast<const KT*>(a.vc) + (size_t)seq * a.seq_stride + (size_t)kvh * a.max_ctx * 64;
+  auto stage = [&](int c0, int buf) {
+    const int nk = min(AM_CH, k_end - c0);
+    KT* dk = sk + buf * AM_CH * LDK;
+    KT* dv = sv + buf * AM_CH * LDV;
+    for (int i = tid; i < nk * SEGS; i += 256) {
+      const int key = i / SEGS, seg = i - key * SEGS;
+      const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dk + key * LDK + seg * EPS);
+      const uint32_t d1 = (uint32_t)__cvta_generic_to_shared(dv + key * LDV + seg * EPS);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(kb + (size_t)(c0 + key) * 64 + seg * EPS) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d1), "l"(vb + (size_t)(c0 + key) * 64 + seg * EPS) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // per-lane rows: index ri = 2 * mt + h  ->  tile row m = mt * 16 + g + 8 * h
+  float O[2][8][4], mrow[4], lrow[4];
+  int plim[4];
+#pragma unroll
+  for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+    for (int nd = 0; nd < 8; nd++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) O[mt][nd][j] = 0.f;
+#pragma unroll
+  for (int ri = 0; ri < 4; ri++) {
+    const int m = (ri >> 1) * 16 + g + 8 * (ri & 1);
+    mrow[ri] = -INFINITY; lrow[ri] = 0.f;
+    plim[ri] = m < n_rows ? s.ctx + m / a.group : -1;                      // last visible key of the row (-1: padding row)
+  }
+  int buf = 0;
+  if (k_begin < k_end) stage(k_begin, 0);
+  for (int c0 = k_begin; c0 < k_end; c0 += AM_CH, buf ^= 1) {
+    const int nk = min(AM_CH, k_end - c0);
+    if (c0 + AM_CH < k_end) { stage(c0 + AM_CH, buf ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const int kw = warp * 16;                                              // this warp's keys inside the chunk
+    if (kw < nk) {
+      const KT* ck = sk + buf * AM_CH * LDK;
+      const KT* cv = sv + buf * AM_CH * LDV;
+      float S[2][2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int n = 0; n < 2; n++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) S[mt][n][j] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ks++) {
+        uint32_t ah[2][4], al[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+          const int row = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, col = ks * 16 + (lane >> 4) * 8;
+          const uint32_t ph = (uint32_t)__cvta_generic_to_shared(qhi + row * AM_LDQ + col);
+          const uint32_t pl = (uint32_t)__cvta_generic_to_shared(qlo + row * AM_LDQ + col);
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(ah[mt][0]), "=r"(ah[mt][1]), "=r"(ah[mt][2]), "=r"(ah[mt][3]) : "r"(ph));
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(al[mt][0]), "=r"(al[mt][1]), "=r"(al[mt][2]), "=r"(al[mt][3]) : "r"(pl));
+        }
+#pragma unroll
+        for (int n = 0; n < 2; n++) {
+          const int key = kw + n * 8 + g;
+          uint32_t bh0, bh1, bl0 = 0, bl1 = 0;
+          if constexpr (KV32) {
+            const float2 x0 = *reinterpret_cast<const float2*>(ck + key * LDK + ks * 16 + 2 * t);
+            const float2 x1 = *reinterpret_cast<const float2*>(ck + key * LDK + ks * 16 + 8 + 2 * t);
+            split_bf16x2(x0.x, x0.y, bh0, bl0);
+            split_bf16x2(x1.x, x1.y, bh1, bl1);
+          } else {
+            bh0 = *reinterpret_cast<const uint32_t*>(ck + key * LDK + ks * 16 + 2 * t);
+            bh1 = *reinterpret_cast<const uint32_t*>(ck + key * LDK + ks * 16 + 8 + 2 * t);
+          }
+#pragma unroll
+          for (int mt = 0; mt < 2; mt++) {
+            mma_bf16_16816(S[mt][n], ah[mt], bh0, bh1);
+            mma_bf16_16816(S[mt][n], al[mt], bh0, bh1);
+            if constexpr (KV32) mma_bf16_16816(S[mt][n], ah[mt], bl0, bl1);
+          }
+        }
+      }
+      // mask + online softmax.  S[mt][n][j]: row ri = 2*mt + (j>>1), key = c0 + kw + n*8 + 2t + (j&1)
+      float tmax[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int n = 0; n < 2; n++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int ri = 2 * mt + (j >> 1);
+            const int kabs = c0 + kw + n * 8 + 2 * t + (j & 1);
+            const bool ok = kabs < k_end && kabs <= plim[ri];
+            S[mt][n][j] = ok ? S[mt][n][j] : -INFINITY;
+            tmax[ri] = fmaxf(tmax[ri], S[mt][n][j]);
+          }
+      float alpha[4];
+#pragma unroll
+      for (int ri = 0; ri < 4; ri++) {
+        tmax[ri] = fmaxf(tmax[ri], __shfl_xor_sync(0xffffffffu, tmax[ri], 1));
+        tmax[ri] = fmaxf(tmax[ri], __shfl_xor_sync(0xffffffffu, tmax[ri], 2));
+        const float mn = fmaxf(mrow[ri], tmax[ri]);
+        alpha[ri] = (mrow[ri] == -INFINITY) ? 0.f : expf(mrow[ri] - mn);     // mn == -inf only while the row has seen no key: alpha unused (O, l are 0)
+        mrow[ri] = mn;
+        lrow[ri] *= alpha[ri];
+      }
+      uint32_t ph[2][4], pl[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++) {
+        float p[2][4];
+#pragma unroll
+        for (int n = 0; n < 2; n++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int ri = 2 * mt + (j >> 1);
+            const float e = (S[mt][n][j] == -INFINITY) ? 0.f : expf(S[mt][n][j] - mrow[ri]);
+            p[n][j] = e;
+            lrow[ri] += e;
+          }
+        split_bf16x2(p[0][0], p[0][1], ph[mt][0], pl[mt][0]);            // a0: row g,   keys 2t, 2t+1
+        split_bf16x2(p[0][2], p[0][3], ph[mt][1], pl[mt][1]);            // a1: row g+8, keys 2t, 2t+1
+        split_bf16x2(p[1][0], p[1][1], ph[mt][2], pl[mt][2]);            // a2: row g,   keys 2t+8, 2t+9
+        split_bf16x2(p[1][2], p[1][3], ph[mt][3], pl[mt][3]);            // a3: row g+8, keys 2t+8, 2t+9
+#pragma unroll
+        for (int nd = 0; nd < 8; nd++) {
+          O[mt][nd][0] *= alpha[2 * mt]; O[mt][nd][1] *= alpha[2 * mt];
+          O[mt][nd][2] *= alpha[2 * mt + 1]; O[mt][nd][3] *= alpha[2 * mt + 1];
+        }
+      }
+#pragma unroll
+      for (int nd = 0; nd < 8; nd++) {
+        // B fragment of V: b0 = (V[kw+2t][d], V[kw+2t+1][d]), b1 = (V[kw+2t+8][d], V[kw+2t+9][d]),  d = nd*8 + g
+        const int d = nd * 8 + g;
+        uint32_t vh0, vh1, vl0 = 0, vl1 = 0;
+        if constexpr (KV32) {
+          split_bf16x2(cv[(kw + 2 * t) * LDV + d], cv[(kw + 2 * t + 1) * LDV + d], vh0, vl0);
+          split_bf16x2(cv[(kw + 2 * t + 8) * LDV + d], cv[(kw + 2 * t + 9) * LDV + d], vh1, vl1);
+        } else {
+          const uint16_t* v16 = reinterpret_cast<const uint16_t*>(cv);
+          vh0 = (uint32_t)v16[(kw + 2 * t) * LDV + d] | ((uint32_t)v16[(kw + 2 * t + 1) * LDV + d] << 16);
+          vh1 = (uint32_t)v16[(kw + 2 * t + 8) * LDV + d] | ((uint32_t)v16[(kw + 2 * t + 9) * LDV + d] << 16);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+          mma_bf16_16816(O[mt][nd], ph[mt], vh0, vh1);
+          mma_bf16_16816(O[mt][nd], pl[mt], vh0, vh1);
+          if constexpr (KV32) mma_bf16_16816(O[mt][nd], ph[mt], vl0, vl1);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- merge the 8 warps' partials through shared memory (the staging ring is free now)
+  float* Ow = reinterpret_cast<float*>(sk);                                // [8][32][64]
+  float* mw = Ow + 8 * 32 * 64;                                            // [8][32]
+  float* lw = mw + 8 * 32;
+#pragma unroll
+  for (int ri = 0; ri < 4; ri++) {
+    lrow[ri] += __shfl_xor_sync(0xffffffffu, lrow[ri], 1);
+    lrow[ri] += __shfl_xor_sync(0xffffffffu, lrow[ri], 2);
+    const int m = (ri >> 1) * 16 + g + 8 * (ri & 1);
+    if (t == 0) { mw[warp * 32 + m] = mrow[ri]; lw[warp * 32 + m] = lrow[ri]; }
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+    for (int nd = 0; nd < 8; nd++) {
+      float* o0 = Ow + ((size_t)warp * 32 + mt * 16 + g) * 64 + nd * 8 + 2 * t;
+      *reinterpret_cast<float2*>(o0) = make_float2(O[mt][nd][0], O[mt][nd][1]);
+      *reinterpret_cast<float2*>(o0 + 8 * 64) = make_float2(O[mt][nd][2], O[mt][nd][3]);
+    }
+  __syncthreads();
+  const int q_heads = a.kv_heads * a.group;
+  for (int i = tid; i < n_rows * 64; i += 256) {
+    const int m = i >> 6, d = i & 63;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; w++) M = fmaxf(M, mw[w * 32 + m]);
+    float acc = 0.f, L = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      const float mv = mw[w * 32 + m];
+      const float wgt = (mv == -INFINITY) ? 0.f : expf(mv - M);
+      acc += wgt * Ow[((size_t)w * 32 + m) * 64 + d];
+      L += wgt * lw[w * 32 + m];
+    }
+    const int r = m / a.group, gq = m - r * a.group;
+    const int row = seq * a.rows_per_seq + r, qh = kvh * a.group + gq;
+    float* pp = a.part + (((size_t)row * q_heads + qh) * a.splits + split) * 68;
+    pp[4 + d] = acc;
+    if (d == 0) { pp[0] = M; pp[1] = L; }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&a.counters[seq * a.kv_heads + kvh], 1) == a.splits - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // last slice of this (sequence, kv head): merge the slices in index order (deterministic) and write the attention rows
+  for (int i = tid; i < n_rows * 64; i += 256) {
+    const int m = i >> 6, d = i & 63;
+    const int r = m / a.group, gq = m - r * a.group;
+    const int row = seq * a.rows_per_seq + r, qh = kvh * a.group + gq;
+    const float* pb = a.part + ((size_t)row * q_heads + qh) * a.splits * 68;
+    float Mx = -INFINITY;
+    for (int sp = 0; sp < a.splits; sp++) Mx = fmaxf(Mx, __ldcg(pb + sp * 68));
+    float Ls = 0.f, acc = 0.f;
+    for (int sp = 0; sp < a.splits; sp++) {
+      const float ms = __ldcg(pb + sp * 68);
+      const float w = (ms == -INFINITY) ? 0.f : expf(ms - Mx);
+      Ls += __ldcg(pb + sp * 68 + 1) * w;
+      acc += __ldcg(pb + sp * 68 + 4 + d) * w;
+    }
+    const float y = acc / Ls;
+    if (a.out) a.out[(size_t)row * a.ldo + qh * 64 + d] = y;
+    if (a.out16) store_split(a.out16 + (size_t)row * 2 * a.ldo, a.ldo, qh * 64 + d, y);
+  }
+  if (tid == 0) a.counters[seq * a.kv_heads + kvh] = 0;
+}
+
 // ------------------------------------------------------------------ small kernels
 // prompt rows [sos, embed_tokens(prompt_text || text), task_id, speech_embedding(prompt_speech)]  (:943-952)
 __global__ void llm_prompt_rows_kernel(const int32_t* __restrict__ text, int n_text, const int32_t* __restrict__ pspeech,
@@ -1518,10 +1798,32 @@ static hvx_status launch_attn(hvx_engine* e, cudaStream_t st, LlmState* L, int l
   a.seqs = seqs; a.rows_per_seq = rows_per_seq; a.seq0 = seq0; a.pos0 = pos0; a.n_rows = rows; a.splits = splits;
   a.part = b.part; a.counters = b.counters; a.out = b.att; a.out16 = want16 ? b.att16 : nullptr; a.ldo = c.llm_hidden;
   a.scale = 1.0f / sqrtf((float)c.llm_head_dim);
-  static const bool no_seq_attn = getenv("HVX_NO_SEQ_ATTN") != nullptr;
-  if (seqs && want16 && rows_per_seq >= 1 && 32 * a.group * ((rows_per_seq + 1) / 2) <= 512 && !no_seq_attn) {
-    // batched decode: one block per (sequence, kv head, key slice); the rows of a sequence share the staged cache chunk
-    const int n_seq = rows / rows_per_seq, pairs = (rows_per_seq + 1) / 2;
+  // batched decode (tensor-core path of the step): one block per (sequence, kv head, key slice); the rows of a sequence share
+  // the staged cache chunk.  Default: the mma.sync kernel (<= 32 query rows per kv head); HVX_ATTN_DECODE=seq: the CUDA-core
+  // per-sequence kernel; HVX_ATTN_DECODE=row: one block per row (llm_attn_kernel)
+  static const char* mode_env = getenv("HVX_ATTN_DECODE");
+  const int mode = !mode_env ? 2 : (!strcmp(mode_env, "row") ? 0 : (!strcmp(mode_env, "seq") ? 1 : 2));
+  const int n_seq_b = rows_per_seq > 0 ? rows / rows_per_seq : 0;
+  if (seqs && want16 && mode == 2 && rows_per_seq >= 1 && rows_per_seq * a.group <= 32 && rows_per_seq <= 4) {
+    a.splits = std::max(1, std::min(16, e->sm_count / std::max(1, n_seq_b * c.llm_kv_heads)));
+    const size_t kv_bytes = L->kv_f32 ? (size_t)2 * AM_CH * (AM_LDK32 + AM_LDV32) * 4 : (size_t)2 * AM_CH * 2 * AM_LD16 * 2;
+    const size_t merge_bytes = (size_t)(8 * 32 * 64 + 2 * 8 * 32) * 4;
+    const size_t smem = (size_t)2 * 32 * AM_LDQ * 2 + std::max(kv_bytes, merge_bytes);
+    static bool attr_set = false;
+    if (!attr_set) {
+      HVX_CUDA(cudaFuncSetAttribute(llm_attn_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      HVX_CUDA(cudaFuncSetAttribute(llm_attn_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    HVX_CHECK((size_t)rows * c.llm_q_heads * a.splits * 68 <= b.part_floats, HVX_ERR_STATE, "llm: attention partial buffer too small");
+    dim3 sgrid(a.splits, n_seq_b * c.llm_kv_heads);
+    if (L->kv_f32) HVX_CUDA(launch_pdl(llm_attn_mma_kernel<true>, sgrid, dim3(256), smem, st, a));
+    else HVX_CUDA(launch_pdl(llm_attn_mma_kernel<false>, sgrid, dim3(256), smem, st, a));
+    HVX_LAUNCH_CHECK(e);
+    return HVX_OK;
+  }
+  if (seqs && want16 && mode >= 1 && rows_per_seq >= 1 && 32 * a.group * ((rows_per_seq + 1) / 2) <= 512) {
+    const int n_seq = n_seq_b, pairs = (rows_per_seq + 1) / 2;
     a.splits = std::max(1, std::min(16, e->sm_count / std::max(1, n_seq * c.llm_kv_heads)));
     const size_t elt = L->kv_f32 ? (size_t)(ATT_KEYS / 2) * ATT_LD32 * 4 : (size_t)ATT_KEYS * ATT_LD * 2;
     const size_t smem = 4 * elt;                                            // K and V, two buffers each
@@ -1563,30 +1865,47 @@ static hvx_status launch_attn(hvx_engine* e, cudaStream_t st, LlmState* L, int l
   return HVX_OK;
 }
 
-// h[i] += bias-free partial sums of a split-K GEMM, added in split order (deterministic)
-__global__ void llm_splitk_reduce_kernel(float* __restrict__ h, const float* __restrict__ part, int S, size_t n4, size_t stride4) {
+// out[i] = resid[i] + partial sums of a split-K GEMM, added in split order (deterministic); optionally the split bf16 copy
+// [hi | lo] of the result (row length H) for the next GEMM
+__global__ void llm_splitk_reduce_kernel(float* __restrict__ out, const float* __restrict__ resid, const float* __restrict__ part, int S,
+                                         size_t n4, size_t stride4, __nv_bfloat16* __restrict__ out16, int H) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
-  float4 a = reinterpret_cast<float4*>(h)[i];
+  float4 a = reinterpret_cast<const float4*>(resid)[i];
   for (int z = 0; z < S; z++) {
     const float4 p = reinterpret_cast<const float4*>(part)[(size_t)z * stride4 + i];
     a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
   }
-  reinterpret_cast<float4*>(h)[i] = a;
+  reinterpret_cast<float4*>(out)[i] = a;
+  if (out16) {
+    const size_t e0 = i * 4, row = e0 / H, col = e0 - row * H;
+    __nv_bfloat16* o = out16 + row * 2 * H;
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+    const __nv_bfloat162 l0 = __floats2bfloat162_rn(a.x - __low2float(h0), a.y - __high2float(h0));
+    const __nv_bfloat162 l1 = __floats2bfloat162_rn(a.z - __low2float(h1), a.w - __high2float(h1));
+    *reinterpret_cast<uint2*>(o + col) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    *reinterpret_cast<uint2*>(o + H + col) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+  }
 }
 
 // h (rows x H) += A16 (split bf16 [hi | lo], rows x 2K) . W^T  for the skinny N = H projections of the tcgen05 path (o-proj,
 // down-proj): 14 output tiles for 148 SMs, so the k-blocks are split over grid.z and the partials are added by
 // llm_splitk_reduce_kernel (profiles/r1c_llm_batch32_kernels.txt: these two GEMMs were 34 % of a 128-row decode step)
 static hvx_status llm_skinny_resid_gemm(hvx_engine* e, cudaStream_t st, const StepBufs& b, const __nv_bfloat16* a16, const __nv_bfloat16* w,
-                                        int rows, int H, int K) {
+                                        int rows, int H, int K, float* out = nullptr, const float* resid = nullptr,
+                                        __nv_bfloat16* out16 = nullptr) {
   static const int want = getenv("HVX_LLM_SPLITK") ? atoi(getenv("HVX_LLM_SPLITK")) : 1;
+  if (!out) out = b.h;
+  if (!resid) resid = b.h;
   GemmAddr ga; ga.b_kb_mod = K / 64;
   const int nkb = 2 * K / 64;
-  int S = !want ? 1 : std::min(8, std::max(1, nkb / 7));              // >= 7 k-blocks per CTA
+  // >= 7 k-blocks per CTA, and enough CTAs for every SM: N = H gives only H/64 output tiles
+  const int tiles = cdiv(H, 64) * cdiv(rows, 128);
+  int S = !want ? 1 : std::min(64, std::max(1, std::min(nkb / 7, cdiv(2 * e->sm_count, tiles))));
   while (S > 1 && (size_t)S * rows * H > b.part_floats) S--;
   if (S <= 1 || (H & 3)) {
-    GemmEpi p; p.mode = EPI_F32; p.out = b.h; p.ldo = H; p.resid = b.h;
+    GemmEpi p; p.mode = EPI_F32; p.out = out; p.ldo = H; p.resid = resid;
+    if (out16) { p.out2 = out16; p.ldo2 = 2 * H; p.lo_off = H; }
     return gemm_bf16(e, st, a16, 2 * K, w, K, rows, H, 2 * K, p, &ga);
   }
   ga.split_k = S; ga.split_stride = (size_t)rows * H;
@@ -1594,7 +1913,7 @@ static hvx_status llm_skinny_resid_gemm(hvx_engine* e, cudaStream_t st, const St
   hvx_status rc = gemm_bf16(e, st, a16, 2 * K, w, K, rows, H, 2 * K, p, &ga);
   if (rc) return rc;
   const size_t n4 = (size_t)rows * H / 4;
-  llm_splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(b.h, b.part, S, n4, n4);
+  llm_splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(out, resid, b.part, S, n4, n4, out16, H);
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
 }
@@ -1690,8 +2009,9 @@ static hvx_status llm_heads(hvx_engine* e, cudaStream_t st, LlmState* L, const S
       HVX_LAUNCH_CHECK(e);
       { GemmEpi p; p.mode = EPI_SWIGLU; p.out = b.act16; p.ldo = 2 * MI; p.lo_off = MI;
         if ((rc = gemm_bf16(e, st, b.x16, 2 * H, L->m_gu_w + (size_t)j * 2 * MI * H, H, n_seq, 2 * MI, 2 * H, p, &gh))) return rc; }
-      { GemmEpi p; p.mode = EPI_F32; p.out = b.m_o + j * sH; p.ldo = H; p.resid = b.m_h1 + j * sH; p.out2 = b.m16; p.ldo2 = 2 * H; p.lo_off = H;
-        if ((rc = gemm_bf16(e, st, b.act16, 2 * MI, L->m_down_w + (size_t)j * H * MI, MI, n_seq, H, 2 * MI, p, &gi))) return rc; }
+      // down-proj: K = mtp_inter (22016 -> 688 k-blocks) against 14 output tiles: split over k like the layers' down-proj
+      if ((rc = llm_skinny_resid_gemm(e, st, b, b.act16, L->m_down_w + (size_t)j * H * MI, n_seq, H, MI, b.m_o + j * sH, b.m_h1 + j * sH, b.m16)))
+        return rc;
       { GemmEpi p; p.mode = EPI_F32; p.out = b.logits + (size_t)j * n_seq * V; p.ldo = V;
         if ((rc = gemm_bf16(e, st, b.m16, 2 * H, L->dec_w, H, n_seq, V, 2 * H, p, &gh))) return rc; }
     }
