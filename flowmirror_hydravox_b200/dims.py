@@ -78,6 +78,40 @@ class UnetDims:
 
 
 @dataclass(frozen=True)
+class UnetNcDims:
+    """The non-causal multi-level `ConditionalDecoder` (cosyvoice/flow/decoder.py:88-291; blocks
+    matcha/models/components/decoder.py:31-158) as the CosyVoice-generation configs instantiate it: in_channels 320, channels
+    [256, 256] (two down / two up levels: Downsample1D = Conv1d(k3, stride 2) and Upsample1D = ConvTranspose1d(4, 2, 1) between
+    them, plain Conv1d(k3) on the last), GroupNorm(8) Block1Ds, 4 transformer blocks per stage, 12 mid blocks, 8 heads x 64."""
+    mel: int = 80
+    channels: tuple = (256, 256)
+    n_blocks: int = 4
+    n_mid: int = 12
+    heads: int = 8
+    head_dim: int = 64
+    ff_mult: int = 4
+    groups: int = 8
+    chunk: int = 0
+
+    @property
+    def in_ch(self) -> int:
+        return 4 * self.mel
+
+    @property
+    def ch(self) -> int:
+        assert len(set(self.channels)) == 1, "the engine builds equal-width levels (the reference configs use [256, 256])"
+        return self.channels[0]
+
+    @property
+    def levels(self) -> int:
+        return len(self.channels)
+
+    @property
+    def n_res(self) -> int:               # resnet blocks: down levels + mid + up levels
+        return self.n_mid + 2 * len(self.channels)
+
+
+@dataclass(frozen=True)
 class LlmDims:
     hidden: int = 896
     layers: int = 24
@@ -103,6 +137,8 @@ FLOW_FULL = FlowDims()
 LLM_FULL = LlmDims()
 UNET_FULL = UnetDims()
 UNET_TINY = UnetDims(mel=16, ch=128, n_blocks=2, n_mid=2, heads=2, chunk=6)
+UNET_NC_FULL = UnetNcDims()
+UNET_NC_TINY = UnetNcDims(mel=16, channels=(128, 128), n_blocks=1, n_mid=1, heads=2)
 UNET_SMALL = UnetDims(ch=128, n_blocks=1, n_mid=1, heads=2, chunk=10)     # mel stays 80: solve_euler hard-codes it (flow_matching.py:94-99)
 
 HIFT_TINY = HiftDims(base=64, f0_ch=64)

@@ -182,6 +182,70 @@ def unet_state_dict(d, seed: int = 0) -> Dict[str, torch.Tensor]:
     return sd
 
 
+def unet_nc_state_dict(d, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Checkpoint of the non-causal multi-level ConditionalDecoder (cosyvoice/flow/decoder.py:88-205) at dims.UnetNcDims: same keys
+    and shapes as the reference module's state_dict (pinned by load_state_dict(strict=True) in oracle/make_golden.py)."""
+    g = _gen(seed + 37)
+    sd: Dict[str, torch.Tensor] = {}
+    C, inner, tdim, L = d.ch, d.heads * d.head_dim, 4 * d.ch, d.levels
+
+    def lin(name, out, inp, gain=1.0, bias=True):
+        sd[name + ".weight"] = _randn(g, out, inp, std=gain / inp ** 0.5)
+        if bias:
+            sd[name + ".bias"] = _randn(g, out, std=0.05)
+
+    def conv(name, out, inp, k, gain=1.0, transpose=False):
+        shape = (inp, out, k) if transpose else (out, inp, k)
+        sd[name + ".weight"] = _randn(g, *shape, std=gain / (inp * k) ** 0.5)
+        sd[name + ".bias"] = _randn(g, out, std=0.05)
+
+    def norm(name, n):
+        sd[name + ".weight"] = 1.0 + 0.1 * _randn(g, n)
+        sd[name + ".bias"] = _randn(g, n, std=0.05)
+
+    def resnet(p, cin):
+        lin(p + ".mlp.1", C, tdim)
+        for b, ci in (("block1", cin), ("block2", C)):
+            conv(f"{p}.{b}.block.0", C, ci, 3, gain=1.4)
+            norm(f"{p}.{b}.block.1", C)                       # GroupNorm(8, C)
+        conv(p + ".res_conv", C, cin, 1)
+
+    def tfm(p):
+        norm(p + ".norm1", C)
+        for n in "qkv":
+            lin(f"{p}.attn1.to_{n}", inner, C, gain=1.5 if n != "v" else 1.0, bias=False)
+        lin(p + ".attn1.to_out.0", C, inner, gain=0.5)
+        norm(p + ".norm3", C)
+        lin(p + ".ff.net.0.proj", d.ff_mult * C, C)
+        lin(p + ".ff.net.2", C, d.ff_mult * C, gain=0.5)
+
+    lin("time_mlp.linear_1", tdim, d.in_ch)
+    lin("time_mlp.linear_2", tdim, tdim)
+    for i in range(L):
+        p = f"down_blocks.{i}"
+        resnet(p + ".0", d.in_ch if i == 0 else C)
+        for j in range(d.n_blocks):
+            tfm(f"{p}.1.{j}")
+        conv(p + (".2" if i == L - 1 else ".2.conv"), C, C, 3)            # Conv1d(k3, pad 1) on the last level, else Downsample1D
+    for i in range(d.n_mid):
+        resnet(f"mid_blocks.{i}.0", C)
+        for j in range(d.n_blocks):
+            tfm(f"mid_blocks.{i}.1.{j}")
+    for i in range(L):
+        p = f"up_blocks.{i}"
+        resnet(p + ".0", 2 * C)
+        for j in range(d.n_blocks):
+            tfm(f"{p}.1.{j}")
+        if i == L - 1:
+            conv(p + ".2", C, C, 3)
+        else:
+            conv(p + ".2.conv", C, C, 4, transpose=True)                 # Upsample1D: ConvTranspose1d(C, C, 4, 2, 1)
+    conv("final_block.block.0", C, C, 3, gain=1.4)
+    norm("final_block.block.1", C)
+    conv("final_proj", d.mel, C, 1)
+    return sd
+
+
 # --------------------------------------------------------------------------- flow
 def flow_state_dict(d: FlowDims, seed: int = 0) -> Dict[str, torch.Tensor]:
     g = _gen(seed)

@@ -234,6 +234,36 @@ def golden_unet(name, dims, T, seed):
                os.path.join(OUT, f"unet_{name}.pt"))
 
 
+def golden_unet_nc(name, dims, T, seed):
+    """a7' (first variant named in SURVEY 8): the non-causal multi-level ConditionalDecoder at the forward_estimator seam, CFG
+    batch of 2: all-true mask (odd and even T: the stride-2 level and the ConvTranspose1d length handling), and a padded
+    batch (row 1 valid up to T - 7) through the reference's padding-mask path."""
+    m = refshim.build_unet_nc(dims)
+    sd = synth.unet_nc_state_dict(dims, seed)
+    m.load_state_dict(sd, strict=True)
+    out = {}
+    for key, Tk, pad in (("full", T, 0), ("odd", T - 1, 0), ("masked", T, 7)):
+        g = torch.Generator().manual_seed(seed + 800 + Tk + pad)
+        x = torch.randn(2, dims.mel, Tk, generator=g)
+        mu = torch.randn(2, dims.mel, Tk, generator=g)
+        cond = torch.randn(2, dims.mel, Tk, generator=g) * 2.0 - 3.0
+        spks = torch.randn(2, dims.mel, generator=g)
+        t = torch.tensor([0.3141, 0.3141])
+        mask = torch.ones(2, 1, Tk)
+        if pad:
+            mask[1, :, Tk - pad:] = 0
+        else:
+            mu[1], cond[1], spks[1] = 0, 0, 0
+            x[1] = x[0]
+        y = m(x, mask, mu, t, spks, cond)
+        y_o = unet_ref.estimator_nc(sd, x, mask, mu, t, spks, cond, dims)
+        e = (y - y_o).abs().max().item()
+        print(f"[unet_nc:{name}] T={Tk} {key}: ref-vs-oracle max-abs {e:.2e}; |out| mean {y.abs().mean():.3f} max {y.abs().max():.2f}")
+        assert e < 2e-4 * max(1.0, y.abs().max().item())
+        out[key] = dict(x=x, mu=mu, cond=cond, spks=spks, t=t, mask=mask, y=y)
+    torch.save(dict(dims=name, seed=seed, T=T, sd_checksum=checksum(sd), **out), os.path.join(OUT, f"unet_nc_{name}.pt"))
+
+
 def golden_unet_cfm(name, dims, T, n_steps, seed):
     """the whole Euler solve over the U-Net estimator: CausalConditionalCFM.forward (flow_matching.py:203-228)"""
     cfm = refshim.build_unet_cfm(dims)
@@ -412,6 +442,11 @@ def main():
         with torch.no_grad():
             golden_frontend(0)
         return
+    if sys.argv[1:] == ["unet_nc"]:
+        with torch.no_grad():
+            golden_unet_nc("tiny", D.UNET_NC_TINY, 38, 0)
+            golden_unet_nc("full", D.UNET_NC_FULL, 130, 0)
+        return
     if sys.argv[1:] == ["unet"]:
         with torch.no_grad():
             golden_unet("tiny", D.UNET_TINY, 37, 0)
@@ -440,6 +475,8 @@ def main():
         golden_unet("full", D.UNET_FULL, 130, 0)
         golden_unet_cfm("small", D.UNET_SMALL, 57, 10, 0)
         golden_unet_cfm("full", D.UNET_FULL, 96, 5, 0)
+        golden_unet_nc("tiny", D.UNET_NC_TINY, 38, 0)
+        golden_unet_nc("full", D.UNET_NC_FULL, 130, 0)
         golden_frontend(0)
         golden_flow("tiny", D.FLOW_TINY, 21, 10, 10, 0)
         golden_flow("full", D.FLOW_FULL, 24, 8, 4, 0)

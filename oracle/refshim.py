@@ -294,6 +294,16 @@ def build_unet(cfg):
     return m.eval()
 
 
+def build_unet_nc(cfg):
+    """The reference's non-causal multi-level ConditionalDecoder (cosyvoice/flow/decoder.py:88-291) at cfg dims (dims.UnetNcDims)."""
+    install()
+    from cosyvoice.flow.decoder import ConditionalDecoder
+    m = ConditionalDecoder(in_channels=cfg.in_ch, out_channels=cfg.mel, channels=list(cfg.channels), dropout=0.0,
+                           attention_head_dim=cfg.head_dim, n_blocks=cfg.n_blocks, num_mid_blocks=cfg.n_mid,
+                           num_heads=cfg.heads, act_fn="gelu")
+    return m.eval()
+
+
 def build_unet_cfm(cfg):
     """CausalConditionalCFM (flow_matching.py:197-228) over the reference U-Net estimator, cfm_params as the CosyVoice2 yaml."""
     install()

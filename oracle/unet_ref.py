@@ -119,3 +119,61 @@ def cfm_solve(sd, mu, spks, cond, noise, n_timesteps, dims, cfg_rate=0.7, temper
         if step < n_timesteps:
             dt = t_span[step + 1] - t
     return x
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The non-causal multi-level ConditionalDecoder (cosyvoice/flow/decoder.py:88-291): Block1D = Conv1d(k3, pad 1) -> GroupNorm(8)
+# -> Mish (matcha/models/components/decoder.py:31-43), ResnetBlock1D :46-61, Downsample1D :64-70 (Conv1d k3 stride 2 pad 1),
+# Upsample1D :116-158 (ConvTranspose1d(4, 2, 1)), skip concatenation and the padding-mask path (mask[:, :, ::2] per level).
+def _block_nc(sd, p, x, mask, groups):
+    h = F.conv1d(x * mask, sd[p + ".block.0.weight"], sd[p + ".block.0.bias"], padding=1)
+    h = F.group_norm(h, groups, sd[p + ".block.1.weight"], sd[p + ".block.1.bias"])
+    return F.mish(h) * mask
+
+
+def _resnet_nc(sd, p, x, mask, temb, groups):
+    h = _block_nc(sd, p + ".block1", x, mask, groups)
+    h = h + F.linear(F.mish(temb), sd[p + ".mlp.1.weight"], sd[p + ".mlp.1.bias"]).unsqueeze(-1)
+    h = _block_nc(sd, p + ".block2", h, mask, groups)
+    return h + F.conv1d(x * mask, sd[p + ".res_conv.weight"], sd[p + ".res_conv.bias"])
+
+
+def estimator_nc(sd: Dict[str, torch.Tensor], x, mask, mu, t, spks, cond, dims):
+    """x, mu, cond (B, mel, T); mask (B, 1, T) 0/1; t (B,); spks (B, mel) -> (B, mel, T)   (decoder.py:210-291)"""
+    sd = {k: v.float() for k, v in sd.items()}
+    x, mask, mu, spks, cond = x.float(), mask.float(), mu.float(), spks.float(), cond.float()
+    temb = time_embedding(sd, t, dims.in_ch)
+    h = torch.cat([x, mu, spks.unsqueeze(-1).expand(-1, -1, x.shape[-1]), cond], dim=1)
+    L, G = dims.levels, dims.groups
+
+    def stage(p, h, m):
+        h = _resnet_nc(sd, p + ".0", h, m, temb, G).transpose(1, 2)
+        bias = attn_bias(m, False, 0)
+        for j in range(dims.n_blocks):
+            h = _tfm(sd, f"{p}.1.{j}", h, bias, dims.heads)
+        return h.transpose(1, 2)
+
+    hiddens, masks = [], [mask]
+    for i in range(L):
+        m = masks[-1]
+        h = stage(f"down_blocks.{i}", h, m)
+        hiddens.append(h)
+        if i == L - 1:
+            h = F.conv1d(h * m, sd[f"down_blocks.{i}.2.weight"], sd[f"down_blocks.{i}.2.bias"], padding=1)
+        else:
+            h = F.conv1d(h * m, sd[f"down_blocks.{i}.2.conv.weight"], sd[f"down_blocks.{i}.2.conv.bias"], stride=2, padding=1)
+        masks.append(m[:, :, ::2])
+    masks = masks[:-1]
+    m_mid = masks[-1]
+    for i in range(dims.n_mid):
+        h = stage(f"mid_blocks.{i}", h, m_mid)
+    for i in range(L):
+        m = masks.pop()
+        skip = hiddens.pop()
+        h = stage(f"up_blocks.{i}", torch.cat([h[:, :, : skip.shape[-1]], skip], dim=1), m)
+        if i == L - 1:
+            h = F.conv1d(h * m, sd[f"up_blocks.{i}.2.weight"], sd[f"up_blocks.{i}.2.bias"], padding=1)
+        else:
+            h = F.conv_transpose1d(h * m, sd[f"up_blocks.{i}.2.conv.weight"], sd[f"up_blocks.{i}.2.conv.bias"], stride=2, padding=1)
+    h = _block_nc(sd, "final_block", h, m, G)
+    return F.conv1d(h * m, sd["final_proj.weight"], sd["final_proj.bias"]) * mask

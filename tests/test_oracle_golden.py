@@ -107,6 +107,22 @@ def test_unet_oracle_matches_reference(golden, name, dims):
     assert (hi + lo - full).abs().max() < 1e-6
 
 
+@pytest.mark.parametrize("name,dims", [("tiny", D.UNET_NC_TINY), ("full", D.UNET_NC_FULL)])
+def test_unet_nc_oracle_matches_reference(golden, name, dims):
+    """a7': the non-causal multi-level ConditionalDecoder (cosyvoice/flow/decoder.py:88-291): GroupNorm blocks, the stride-2
+    level, ConvTranspose1d(4,2,1), skip concatenation and the padding-mask path; fixtures from the reference module."""
+    from oracle import unet_ref
+    g = golden(f"unet_nc_{name}")
+    sd = synth.unet_nc_state_dict(dims, g["seed"])
+    assert abs(_checksum(sd) - g["sd_checksum"]) < 1e-6 * g["sd_checksum"]
+    for key in ("full", "odd", "masked"):
+        c = g[key]
+        y = unet_ref.estimator_nc(sd, c["x"], c["mask"], c["mu"], c["t"], c["spks"], c["cond"], dims)
+        assert y.shape == c["y"].shape
+        assert (y - c["y"]).abs().max() < 2e-4 * max(1.0, c["y"].abs().max().item())
+    assert (g["masked"]["y"][1, :, -7:] == 0).all()
+
+
 def test_unet_cfm_oracle_matches_reference(golden):
     """CausalConditionalCFM.forward over the U-Net estimator (flow_matching.py:203-228): the oracle's Euler solve vs the fixture"""
     from oracle import unet_ref
