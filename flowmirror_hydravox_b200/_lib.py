@@ -36,6 +36,7 @@ class Config(C.Structure):
         ("llm_rope_theta", C.c_float), ("llm_eps", C.c_float), ("llm_kv_f32", C.c_int),
         ("unet_mel", C.c_int), ("unet_ch", C.c_int), ("unet_n_blocks", C.c_int), ("unet_n_mid", C.c_int),
         ("unet_heads", C.c_int), ("unet_ff_mult", C.c_int), ("unet_chunk", C.c_int),
+        ("unet_noncausal", C.c_int), ("unet_levels", C.c_int), ("unet_groups", C.c_int),
     ]
 
 
@@ -81,6 +82,8 @@ def make_config(hd: D.HiftDims, fd: D.FlowDims, ld: D.LlmDims, max_ctx: int = 81
     if ud is not None:
         c.unet_mel, c.unet_ch, c.unet_n_blocks, c.unet_n_mid = ud.mel, ud.ch, ud.n_blocks, ud.n_mid
         c.unet_heads, c.unet_ff_mult, c.unet_chunk = ud.heads, ud.ff_mult, ud.chunk
+        if hasattr(ud, "channels"):                       # dims.UnetNcDims: the non-causal multi-level ConditionalDecoder
+            c.unet_noncausal, c.unet_levels, c.unet_groups = 1, ud.levels, ud.groups
     return c
 
 

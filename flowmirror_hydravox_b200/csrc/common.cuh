@@ -151,6 +151,12 @@ hvx_status llm_finalize(hvx_engine* e);
 void llm_free(hvx_engine* e);
 hvx_status unet_finalize(hvx_engine* e);
 void unet_free(hvx_engine* e);
+// hvx_llm_generate with a progress hook (llm.cu): called between batches of decode steps with every sequence's done flag and
+// emitted-token count; a non-zero return aborts the generation with that status
+typedef hvx_status (*llm_progress_fn)(void* ctx, int n_seq, const int* done, const int* n_out);
+hvx_status llm_generate_progress(hvx_engine* e, int n_seq, int head_k, const hvx_sampler* sp, const float* u_dev, int u_stride,
+                                 int32_t* out_tokens, int max_out, int32_t* out_counts, void* stream, llm_progress_fn progress,
+                                 void* progress_ctx);
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 }  // namespace hvx

@@ -107,22 +107,28 @@ __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx,
       }
       if (MODE == EPI_BF16) {
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(epi.out) + (size_t)row * epi.ldo + col0;
-        if (epi.lo_off) {
-#pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (col0 + j < N) reinterpret_cast<uint16_t*>(o)[epi.lo_off + j] = tc::lo16(f[j], epi.f16);
-        }
         if (col0 + 32 <= N) {
+          // a thread owns 64 contiguous bytes of its row in the hi half and 64 in the lo half: 16-byte stores for both (2-byte
+          // stores of the lo half kept the L1 60 % busy and the ff1 GEMM at 21 % tensor pipe, profiles/r2k)
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             uint4 pk;
             pk.x = tc::pack16(f[j], f[j + 1], epi.f16); pk.y = tc::pack16(f[j + 2], f[j + 3], epi.f16);
             pk.z = tc::pack16(f[j + 4], f[j + 5], epi.f16); pk.w = tc::pack16(f[j + 6], f[j + 7], epi.f16);
             *reinterpret_cast<uint4*>(o + j) = pk;
+            if (epi.lo_off) {
+              uint4 pl;
+              pl.x = tc::pack_lo16(f[j], f[j + 1], pk.x, epi.f16); pl.y = tc::pack_lo16(f[j + 2], f[j + 3], pk.y, epi.f16);
+              pl.z = tc::pack_lo16(f[j + 4], f[j + 5], pk.z, epi.f16); pl.w = tc::pack_lo16(f[j + 6], f[j + 7], pk.w, epi.f16);
+              *reinterpret_cast<uint4*>(o + epi.lo_off + j) = pl;
+            }
           }
         } else {
           #pragma unroll
-          for (int j = 0; j < 32; j++) if (col0 + j < N) reinterpret_cast<uint16_t*>(o)[j] = tc::cvt16(f[j], epi.f16);
+          for (int j = 0; j < 32; j++) if (col0 + j < N) {
+            reinterpret_cast<uint16_t*>(o)[j] = tc::cvt16(f[j], epi.f16);
+            if (epi.lo_off) reinterpret_cast<uint16_t*>(o)[epi.lo_off + j] = tc::lo16(f[j], epi.f16);
+          }
         }
       } else if (MODE == EPI_F32) {
         float* o = reinterpret_cast<float*>(epi.out) + (size_t)row * epi.ldo + col0;
@@ -146,11 +152,28 @@ __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx,
           for (int j = 0; j < 32; j++) if (col0 + j < N) o[j] = f[j];
         }
         if (epi.out2) {
-          __nv_bfloat16* o2 = epi.out2 + (size_t)row * (epi.ldo2 ? epi.ldo2 : epi.ldo) + col0;
-          #pragma unroll
-          for (int j = 0; j < 32; j++) if (col0 + j < N) {
-            reinterpret_cast<uint16_t*>(o2)[j] = tc::cvt16(f[j], epi.f16);
-            if (epi.lo_off) reinterpret_cast<uint16_t*>(o2)[epi.lo_off + j] = tc::lo16(f[j], epi.f16);
+          const int ld2 = epi.ldo2 ? epi.ldo2 : epi.ldo;
+          __nv_bfloat16* o2 = epi.out2 + (size_t)row * ld2 + col0;
+          if (col0 + 32 <= N && (ld2 & 7) == 0 && (epi.lo_off & 7) == 0 && ((uintptr_t)epi.out2 & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              pk.x = tc::pack16(f[j], f[j + 1], epi.f16); pk.y = tc::pack16(f[j + 2], f[j + 3], epi.f16);
+              pk.z = tc::pack16(f[j + 4], f[j + 5], epi.f16); pk.w = tc::pack16(f[j + 6], f[j + 7], epi.f16);
+              *reinterpret_cast<uint4*>(o2 + j) = pk;
+              if (epi.lo_off) {
+                uint4 pl;
+                pl.x = tc::pack_lo16(f[j], f[j + 1], pk.x, epi.f16); pl.y = tc::pack_lo16(f[j + 2], f[j + 3], pk.y, epi.f16);
+                pl.z = tc::pack_lo16(f[j + 4], f[j + 5], pk.z, epi.f16); pl.w = tc::pack_lo16(f[j + 6], f[j + 7], pk.w, epi.f16);
+                *reinterpret_cast<uint4*>(o2 + epi.lo_off + j) = pl;
+              }
+            }
+          } else {
+            #pragma unroll
+            for (int j = 0; j < 32; j++) if (col0 + j < N) {
+              reinterpret_cast<uint16_t*>(o2)[j] = tc::cvt16(f[j], epi.f16);
+              if (epi.lo_off) reinterpret_cast<uint16_t*>(o2)[epi.lo_off + j] = tc::lo16(f[j], epi.f16);
+            }
           }
         }
       } else if (MODE == EPI_RESID_GATE) {

@@ -2186,6 +2186,15 @@ static hvx_status llm_prefill(hvx_engine* e, cudaStream_t st, LlmState* L, int n
 
 extern "C" hvx_status hvx_llm_generate(hvx_engine* e, int n_seq, int head_k, const hvx_sampler* sp, const float* u_dev,
                                        int u_stride, int32_t* out_tokens, int max_out, int32_t* out_counts, void* stream) {
+  return hvx::llm_generate_progress(e, n_seq, head_k, sp, u_dev, u_stride, out_tokens, max_out, out_counts, stream, nullptr, nullptr);
+}
+
+// hvx_llm_generate with a progress hook: after every batch of `poll` decode steps (the decode stream is drained at that point)
+// progress(ctx, n_seq, done[], n_out[]) tells the caller which sequences have stopped and how many tokens each has emitted —
+// hvx_synthesize_host starts the flow + vocoder of finished utterances on the caller's stream while the rest keep decoding.
+hvx_status hvx::llm_generate_progress(hvx_engine* e, int n_seq, int head_k, const hvx_sampler* sp, const float* u_dev, int u_stride,
+                                      int32_t* out_tokens, int max_out, int32_t* out_counts, void* stream, llm_progress_fn progress,
+                                      void* progress_ctx) {
   HVX_CHECK(e && e->llm, HVX_ERR_STATE, "llm stage not finalized");
   HVX_LOCK(e, HVX_STAGE_LLM);
   HVX_CHECK(sp && u_dev && out_tokens && out_counts, HVX_ERR_ARG, "llm_generate: null argument");
@@ -2229,6 +2238,8 @@ extern "C" hvx_status hvx_llm_generate(hvx_engine* e, int n_seq, int head_k, con
     max_steps = std::max(max_steps, cdiv(std::max(ml - head_k, 0), head_k));
   }
   const int poll = 16;
+  std::vector<SeqState> prog_seqs(progress ? n_seq : 0);
+  std::vector<int> prog_done(progress ? n_seq : 0), prog_out(progress ? n_seq : 0);
   if (fp.ok) {
     // one sequence: the whole step is ONE persistent cooperative kernel (llm_fused.cuh) + the sampler
     for (int step = 0; step < max_steps;) {
@@ -2291,7 +2302,12 @@ extern "C" hvx_status hvx_llm_generate(hvx_engine* e, int n_seq, int head_k, con
     e->launches += (int64_t)n * e->graph_launches;
     step += n;
     HVX_CUDA(cudaMemcpyAsync(L->n_active_host, L->n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (progress) HVX_CUDA(cudaMemcpyAsync(prog_seqs.data(), L->seqs, sizeof(SeqState) * n_seq, cudaMemcpyDeviceToHost, st));
     HVX_CUDA(cudaStreamSynchronize(st));
+    if (progress && *L->n_active_host > 0) {
+      for (int s2 = 0; s2 < n_seq; s2++) { prog_done[s2] = prog_seqs[s2].done; prog_out[s2] = prog_seqs[s2].n_out; }
+      if ((rc = progress(progress_ctx, n_seq, prog_done.data(), prog_out.data()))) return rc;
+    }
     if (*L->n_active_host <= 0 || e->llm_cancel.load()) break;
   }
   }
@@ -2302,6 +2318,10 @@ extern "C" hvx_status hvx_llm_generate(hvx_engine* e, int n_seq, int head_k, con
   HVX_CUDA(cudaStreamSynchronize(st));
   HVX_CUDA(cudaEventRecord(L->ev_out, st));
   HVX_CUDA(cudaStreamWaitEvent(user, L->ev_out, 0));
+  if (progress) {                       // final report: every sequence has stopped (or the run was cancelled: n_out so far)
+    for (int s2 = 0; s2 < n_seq; s2++) { prog_done[s2] = 1; prog_out[s2] = hs[s2].n_out; }
+    if ((rc = progress(progress_ctx, n_seq, prog_done.data(), prog_out.data()))) return rc;
+  }
   for (int s = 0; s < n_seq; s++) {
     L->desc[s].begun = false;
     HVX_CHECK(hs[s].status != 1, HVX_ERR_STATE, "sampling reaches max_trials 100 and still get eos when ignore_eos is True (sequence %d)", s);

@@ -4,6 +4,7 @@
 // F.interpolate for `speed` -> hift.inference -> .cpu().  Host<->device copies are inside the call.
 #include "common.cuh"
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <vector>
 
@@ -22,6 +23,16 @@ __global__ void speed_interp_kernel(const float* __restrict__ x, float* __restri
   const int i1 = min(i0 + 1, T - 1);
   const float l1 = src - (float)i0, l0 = 1.0f - l1;
   y[i] = l0 * x[(size_t)c * T + i0] + l1 * x[(size_t)c * T + i1];
+}
+
+// fade_in_out (cosyvoice/utils/common.py:169-177): the first `ov` samples of the new chunk are cross-faded with the previous
+// chunk's tail under a Hamming window of 2*ov taps.  The reference multiplies float32 tensors by a float64 numpy window, i.e. the
+// blend is evaluated in double and rounded once on the store — reproduced here.
+__global__ void fade_in_out_kernel(float* __restrict__ wav, const float* __restrict__ prev_tail, const double* __restrict__ window, int ov) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ov) return;
+  // three separately rounded double operations, as the reference's tensor expression evaluates them (no fused multiply-add)
+  wav[i] = (float)__dadd_rn(__dmul_rn((double)wav[i], window[i]), __dmul_rn((double)prev_tail[i], window[ov + i]));
 }
 
 struct PipeState {
@@ -50,6 +61,14 @@ using namespace hvx;
 extern "C" hvx_status hvx_speed_interp(hvx_engine* e, const float* mel_dev, int C, int T, int T_out, float* out_dev, void* stream) {
   HVX_CHECK(e && mel_dev && out_dev && T >= 1 && T_out >= 1, HVX_ERR_ARG, "speed_interp: bad argument");
   speed_interp_kernel<<<cdiv(C * T_out, 256), 256, 0, (cudaStream_t)stream>>>(mel_dev, out_dev, C, T, T_out);
+  HVX_LAUNCH_CHECK(e);
+  return HVX_OK;
+}
+
+extern "C" hvx_status hvx_fade_in_out(hvx_engine* e, float* wav_dev, const float* prev_tail_dev, const double* window_dev, int overlap,
+                                      void* stream) {
+  HVX_CHECK(e && wav_dev && prev_tail_dev && window_dev && overlap >= 1, HVX_ERR_ARG, "fade_in_out: bad argument");
+  fade_in_out_kernel<<<cdiv(overlap, 256), 256, 0, (cudaStream_t)stream>>>(wav_dev, prev_tail_dev, window_dev, overlap);
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
 }
@@ -121,48 +140,28 @@ extern "C" hvx_status hvx_synthesize_host(hvx_engine* e, const hvx_request* reqs
   }
   int32_t* tok_dev = (int32_t*)(din + o_tok);
   int32_t* cnt_dev = (int32_t*)(din + o_cnt);
-  if ((rc = hvx_llm_generate(e, n_req, head_k, sp, (const float*)(din + o_u), u_stride, tok_dev, max_out, cnt_dev, stream))) return rc;
-  std::vector<int32_t> cnt(n_req);
-  HVX_CUDA(cudaMemcpyAsync(cnt.data(), cnt_dev, sizeof(int32_t) * n_req, cudaMemcpyDeviceToHost, st));
-  if (tokens_host)
-    for (int i = 0; i < n_req; i++)
-      HVX_CUDA(cudaMemcpyAsync(tokens_host + (size_t)i * tok_stride, tok_dev + (size_t)i * max_out, sizeof(int32_t) * of[i].max_out,
-                               cudaMemcpyDeviceToHost, st));
-  HVX_CUDA(cudaEventRecord(P->ev[1], st));
-  HVX_CUDA(cudaStreamSynchronize(st));            // token counts size the next two stages
-  float ms_llm = 0.f, ms_flow = 0.f, ms_hift = 0.f;
-  cudaEventElapsedTime(&ms_llm, P->ev[0], P->ev[1]);
-  // ---- stage 2 in groups of similar length (one pass per Euler step for the whole group, hvx_flow_inference_batch; the
-  // reference's flow asserts batch 1, flow.py:387), stage 3 per utterance.  Everything below is stream-ordered: the group
-  // workspace is reused by the next group only after this group's vocoder passes and D2H copies, which were enqueued before
-  // it; the host waits once, at the end.
-  std::vector<int> order;
-  for (int i = 0; i < n_req; i++) {
-    if (n_tokens_host) n_tokens_host[i] = cnt[i];
-    if (cnt[i] <= 0) wav_len_host[i] = 0; else order.push_back(i);
-  }
-  auto frames = [&](int i) { return 2 * (reqs[i].n_prompt_speech + cnt[i]); };
-  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return frames(x) > frames(y); });
-  // every utterance is validated before any of stage 2 is enqueued
-  for (int i : order) {
-    const int T_sp = speed_frames(2 * cnt[i], reqs[i].speed);
-    HVX_CHECK((size_t)T_sp * frame <= (size_t)wav_stride, HVX_ERR_ARG, "synthesize: wav_stride %d too small for %d samples", wav_stride, T_sp * frame);
-    HVX_CHECK((int64_t)T_sp * frame <= n_table_rows, HVX_ERR_ARG, "synthesize: request %d needs %lld sine-table rows, the table holds %lld",
-              i, (long long)T_sp * frame, (long long)n_table_rows);
-  }
-  static const int group_frames = getenv("HVX_FLOW_GROUP_FRAMES") ? atoi(getenv("HVX_FLOW_GROUP_FRAMES")) : 8192;   // 0: one by one
+
+  // ---- stages 2 + 3 of a group of finished utterances, enqueued on the caller's stream.  Stage 2 solves the group in one pass
+  // per Euler step (hvx_flow_inference_batch; the reference's flow asserts batch 1, flow.py:387), stage 3 runs per utterance.
+  // Everything is stream-ordered: the group workspace is reused by the next group only after this group's vocoder passes and
+  // D2H copies, which were enqueued before it; the host waits once, at the end.
+  std::vector<int32_t> cnt(n_req, 0);
+  std::vector<char> finished(n_req, 0), enqueued(n_req, 0);
   size_t n_groups = 0;
-  for (size_t g0 = 0; g0 < order.size(); n_groups++) {
-    // longest first; add utterances while the padded group stays under group_frames and padding under 20 %
-    const int Tmax = frames(order[g0]);
-    size_t g1 = g0 + 1;
-    while (g1 < order.size() && g1 - g0 < 16 && (int)(g1 - g0 + 1) * Tmax <= group_frames && frames(order[g1]) * 5 >= Tmax * 4) g1++;
-    const int U = (int)(g1 - g0);
+  auto frames = [&](int i) { return 2 * (reqs[i].n_prompt_speech + cnt[i]); };
+  auto enqueue_group = [&](const std::vector<int>& members) -> hvx_status {
+    const int U = (int)members.size();
+    for (int i : members) {
+      const int T_sp = speed_frames(2 * cnt[i], reqs[i].speed);
+      HVX_CHECK((size_t)T_sp * frame <= (size_t)wav_stride, HVX_ERR_ARG, "synthesize: wav_stride %d too small for %d samples", wav_stride, T_sp * frame);
+      HVX_CHECK((int64_t)T_sp * frame <= n_table_rows, HVX_ERR_ARG, "synthesize: request %d needs %lld sine-table rows, the table holds %lld",
+                i, (long long)T_sp * frame, (long long)n_table_rows);
+    }
     size_t m = 0;
     auto take2 = [&](size_t bytes) { size_t o = m; m += (bytes + 255) & ~(size_t)255; return o; };
     std::vector<size_t> o_all(U), o_mel(U), o_mel2(U), o_wav(U);
     for (int k = 0; k < U; k++) {
-      const int i = order[g0 + k];
+      const int i = members[k];
       const hvx_request& r = reqs[i];
       const int T = 2 * cnt[i];
       const int T_sp = speed_frames(T, r.speed);
@@ -182,7 +181,7 @@ extern "C" hvx_status hvx_synthesize_host(hvx_engine* e, const hvx_request* reqs
     std::vector<float*> mels(U);
     std::vector<int> np(U), nt(U);
     for (int k = 0; k < U; k++) {
-      const int i = order[g0 + k];
+      const int i = members[k];
       const hvx_request& r = reqs[i];
       int32_t* all_tok = (int32_t*)(dm + o_all[k]);
       if (r.n_prompt_speech)
@@ -192,30 +191,92 @@ extern "C" hvx_status hvx_synthesize_host(hvx_engine* e, const hvx_request* reqs
       pfs[k] = r.n_prompt_speech ? (const float*)(din + of[i].pf) : nullptr;
       mels[k] = (float*)(dm + o_mel[k]); np[k] = r.n_prompt_speech; nt[k] = cnt[i];
     }
+    hvx_status rc2;
     HVX_CUDA(cudaEventRecord(ev_a, st));
-    if (U == 1) rc = hvx_flow_inference(e, toks[0], np[0], nt[0], embs[0], pfs[0], noise_dev, n_timesteps, 0, 1, mels[0], stream);
-    else rc = hvx_flow_inference_batch(e, U, toks.data(), np.data(), nt.data(), embs.data(), pfs.data(), noise_dev, n_timesteps, 0, 1, mels.data(), stream);
-    if (rc) return rc;
+    if (U == 1) rc2 = hvx_flow_inference(e, toks[0], np[0], nt[0], embs[0], pfs[0], noise_dev, n_timesteps, 0, 1, mels[0], stream);
+    else rc2 = hvx_flow_inference_batch(e, U, toks.data(), np.data(), nt.data(), embs.data(), pfs.data(), noise_dev, n_timesteps, 0, 1, mels.data(), stream);
+    if (rc2) return rc2;
     HVX_CUDA(cudaEventRecord(ev_b, st));
     for (int k = 0; k < U; k++) {
-      const int i = order[g0 + k];
+      const int i = members[k];
       const hvx_request& r = reqs[i];
       const int T = 2 * cnt[i];
       const int T_sp = speed_frames(T, r.speed);
       float* mel_dev = mels[k];
       if (T_sp != T) {
-        if ((rc = hvx_speed_interp(e, mel_dev, mel, T, T_sp, (float*)(dm + o_mel2[k]), stream))) return rc;
+        if ((rc2 = hvx_speed_interp(e, mel_dev, mel, T, T_sp, (float*)(dm + o_mel2[k]), stream))) return rc2;
         mel_dev = (float*)(dm + o_mel2[k]);
       }
       float* wav_dev = (float*)(dm + o_wav[k]);
-      if ((rc = hvx_hift_vocode(e, mel_dev, T_sp, 1, sine_table_dev, n_table_rows, nullptr, nullptr, wav_dev, nullptr, stream))) return rc;
+      if ((rc2 = hvx_hift_vocode(e, mel_dev, T_sp, 1, sine_table_dev, n_table_rows, nullptr, nullptr, wav_dev, nullptr, stream))) return rc2;
       HVX_CUDA(cudaMemcpyAsync(wav_host + (size_t)i * wav_stride, wav_dev, sizeof(float) * (size_t)T_sp * frame, cudaMemcpyDeviceToHost, st));
       wav_len_host[i] = T_sp * frame;
     }
     HVX_CUDA(cudaEventRecord(ev_c, st));
-    g0 = g1;
+    for (int i : members) enqueued[i] = 1;
+    n_groups++;
+    return HVX_OK;
+  };
+  static const int group_frames = getenv("HVX_FLOW_GROUP_FRAMES") ? atoi(getenv("HVX_FLOW_GROUP_FRAMES")) : 8192;   // 0: one by one
+  // partition of the finished, not yet enqueued utterances: longest first; a group takes utterances while its padded size stays
+  // under group_frames and the padding under 20 %
+  auto partition = [&]() {
+    std::vector<int> order;
+    for (int i = 0; i < n_req; i++) if (finished[i] && !enqueued[i] && cnt[i] > 0) order.push_back(i);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return frames(x) > frames(y); });
+    std::vector<std::vector<int>> groups;
+    for (size_t g0 = 0; g0 < order.size();) {
+      const int Tmax = frames(order[g0]);
+      size_t g1 = g0 + 1;
+      while (g1 < order.size() && g1 - g0 < 16 && (int)(g1 - g0 + 1) * Tmax <= group_frames && frames(order[g1]) * 5 >= Tmax * 4) g1++;
+      groups.emplace_back(order.begin() + g0, order.begin() + g1);
+      g0 = g1;
+    }
+    return groups;
+  };
+  // ---- stage 1: multi-head AR decode of all requests together on the decode stream.  HVX_PIPE_OVERLAP (default on): whenever the
+  // decode loop reports finished sequences that fill a group (>= HVX_PIPE_MIN_FRAMES padded frames or 16 utterances), that group
+  // starts its flow + vocoder on the caller's stream — the latency-bound decode of the long utterances and the
+  // throughput-bound flow of the short ones share the GPU.  (The reference is stage-serial per request,
+  // infer_speech_model.py:549-592; results do not depend on the schedule.)
+  static const bool overlap = !(getenv("HVX_PIPE_OVERLAP") && atoi(getenv("HVX_PIPE_OVERLAP")) == 0);
+  static const int min_frames = getenv("HVX_PIPE_MIN_FRAMES") ? atoi(getenv("HVX_PIPE_MIN_FRAMES")) : 4096;
+  struct ProgCtx { decltype(enqueue_group)* enq; decltype(partition)* part; decltype(frames)* frames_of; std::vector<int32_t>* cnt;
+                   std::vector<char>* fin; bool overlap; long long min_frames; };
+  ProgCtx pctx{&enqueue_group, &partition, &frames, &cnt, &finished, overlap, min_frames};
+  auto progress = [](void* vctx, int n, const int* done, const int* n_out) -> hvx_status {
+    ProgCtx* x = (ProgCtx*)vctx;
+    for (int i = 0; i < n; i++)
+      if (done[i] && !(*x->fin)[i]) { (*x->fin)[i] = 1; (*x->cnt)[i] = n_out[i]; }
+    if (!x->overlap) return HVX_OK;
+    // The schedule depends only on the decode's own progress (which sequences have stopped after how many steps), never on how far
+    // the caller's stream has got, so the grouping — and with it every output bit — is reproducible from run to run.
+    for (const std::vector<int>& g : (*x->part)()) {
+      long long fr = 0;
+      for (int i : g) fr += (*x->frames_of)(i);
+      if (fr < x->min_frames && g.size() < 16) continue;            // wait for more finished utterances to fill this group
+      const hvx_status rc3 = (*x->enq)(g);
+      if (rc3) return rc3;
+    }
+    return HVX_OK;
+  };
+  const auto t_llm0 = std::chrono::steady_clock::now();
+  if ((rc = llm_generate_progress(e, n_req, head_k, sp, (const float*)(din + o_u), u_stride, tok_dev, max_out, cnt_dev, stream,
+                                  +progress, &pctx))) return rc;
+  const float ms_llm = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_llm0).count();
+  if (tokens_host)
+    for (int i = 0; i < n_req; i++)
+      HVX_CUDA(cudaMemcpyAsync(tokens_host + (size_t)i * tok_stride, tok_dev + (size_t)i * max_out, sizeof(int32_t) * of[i].max_out,
+                               cudaMemcpyDeviceToHost, st));
+  for (int i = 0; i < n_req; i++) {
+    HVX_CHECK(finished[i], HVX_ERR_STATE, "synthesize: sequence %d was not reported finished", i);
+    if (n_tokens_host) n_tokens_host[i] = cnt[i];
+    if (cnt[i] <= 0) wav_len_host[i] = 0;
   }
+  for (const std::vector<int>& g : partition())
+    if ((rc = enqueue_group(g))) return rc;
   HVX_CUDA(cudaStreamSynchronize(st));
+  float ms_flow = 0.f, ms_hift = 0.f;
   for (size_t g = 0; g < n_groups; g++) {
     float a = 0.f, b = 0.f;
     cudaEventElapsedTime(&a, P->gev[3 * g], P->gev[3 * g + 1]);

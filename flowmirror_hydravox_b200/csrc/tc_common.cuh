@@ -197,6 +197,12 @@ __device__ __forceinline__ uint16_t lo16(float a, int f16) {
   __nv_bfloat16 t = __float2bfloat16(a - __bfloat162float(__float2bfloat16(a)));
   return *reinterpret_cast<uint16_t*>(&t);
 }
+// packed residuals of (a, b) against their packed 16-bit roundings `hi` (= pack16(a, b)): the lo halves of a split-precision pair
+__device__ __forceinline__ uint32_t pack_lo16(float a, float b, uint32_t hi, int f16) {
+  if (f16) { const __half2 t = *reinterpret_cast<const __half2*>(&hi); return pack16(a - __low2float(t), b - __high2float(t), 1); }
+  const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&hi);
+  return pack16(a - __low2float(t), b - __high2float(t), 0);
+}
 __device__ __forceinline__ uint16_t cvt16(float a, int f16) {
   if (f16) { __half t = __float2half_rn(a); return *reinterpret_cast<uint16_t*>(&t); }
   __nv_bfloat16 t = __float2bfloat16(a);

@@ -13,6 +13,19 @@
 // causal left pad); LayerNorm(+Mish, + time embedding) is one warp-per-row kernel between them; attention is
 // dit_attention_kernel (no rotary on this path: EPI_QKV with a null rope table).  The mask input of the seam is all-true at
 // inference (flow_matching.py:104-111 builds it from a single utterance), so the `* mask` products are identities here.
+//
+// Non-causal multi-level variant (hvx_config.unet_noncausal; ConditionalDecoder, cosyvoice/flow/decoder.py:88-291 with the Block1D /
+// ResnetBlock1D / Downsample1D / Upsample1D of matcha/models/components/decoder.py:31-158; restated in oracle/unet_ref.py:
+// estimator_nc): the same GEMM / attention kernels, with
+//   * k3 convolutions zero-padded on both sides (a_row0 = -1),
+//   * GroupNorm(groups) over (C/groups channels x T frames) instead of the channel LayerNorm: unet_gn_stats_kernel (fixed-order
+//     partial sums in double) + unet_gn_apply_kernel (normalise, Mish, + time embedding, x mask),
+//   * Downsample1D (Conv1d k3, stride 2, pad 1) as a 2-tap implicit GEMM over frame PAIRS: the operand row t holds frames
+//     (2t, 2t+1), so y[t] = [0 | w0] . row[t-1] + [w1 | w2] . row[t],
+//   * Upsample1D (ConvTranspose1d(C, C, 4, 2, 1)) as a k3 implicit GEMM with 2C outputs: row m = (y[2m], y[2m+1]),
+//     y[2m] = w3 x[m-1] + w1 x[m], y[2m+1] = w2 x[m] + w0 x[m+1]  (weights.pack_unet_nc builds both operands),
+//   * the padding mask honoured: every conv / GroupNorm input is multiplied by the level's mask (mask[:, :, ::2] per level,
+//     decoder.py:246) and attention keys are limited per batch row (prefix masks, as make_pad_mask builds them).
 #include "attention.cuh"
 #include "gemm.cuh"
 #include <cmath>
@@ -23,7 +36,8 @@ namespace hvx {
 
 // X16[r] = [x | mu | spks | cond] from the seam's channel-major (2, mel, T) tensors (decoder.py:427-433 pack order)
 __global__ void unet_pack_kernel(const float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ spks,
-                                 const float* __restrict__ cond, __half* __restrict__ out, int T, int C, int split) {
+                                 const float* __restrict__ cond, __half* __restrict__ out, int T, int C, int split,
+                                 const float* __restrict__ mask) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int W = 4 * C;
   if (i >= 2 * T * W) return;
@@ -36,6 +50,7 @@ __global__ void unet_pack_kernel(const float* __restrict__ x, const float* __res
   else if (part == 1) v = mu[idx];
   else if (part == 2) v = spks[b * C + c];
   else v = cond[idx];
+  if (mask) v *= mask[(size_t)b * T + t];
   const __half hi = __float2half_rn(v);
   __half* o = out + (size_t)r * W * (split ? 2 : 1);
   o[j] = hi;
@@ -55,6 +70,123 @@ __global__ void unet_cast_kernel(const float* __restrict__ a, const float* __res
   __half* o = out + (size_t)r * W * (split ? 2 : 1);
   o[j] = hi;
   if (split) o[W + j] = __float2half_rn(v - __half2float(hi));
+}
+
+// Non-causal variant: fp32 rows x mask -> fp16 operand rows ([hi | lo] when split).  Source a has a_T rows per batch (only the
+// first T are read: the `x[:, :, :skip.shape[-1]]` slice of decoder.py:270), b (optional, T rows per batch) is concatenated on
+// the channel axis.  pair = 1: operand row `to` holds frames (2 to, 2 to + 1) side by side (the stride-2 conv's operand; a
+// missing odd frame reads as zero).  grid.y = batch.
+__global__ void unet_cast_nc_kernel(const float* __restrict__ a, int a_T, const float* __restrict__ bsrc, __half* __restrict__ out,
+                                    int T, int To, int Ca, int Cb, int split, const float* __restrict__ mask, int mask_ld,
+                                    int mask_step, int pair) {
+  const int W = Ca + Cb, Wo = pair ? 2 * W : W;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (i >= To * Wo) return;
+  const int to = i / Wo, jj = i - to * Wo;
+  const int t = pair ? 2 * to + jj / W : to, j = pair ? jj % W : jj;
+  float v = 0.f;
+  if (t < T) {
+    v = j < Ca ? a[((size_t)b * a_T + t) * Ca + j] : bsrc[((size_t)b * T + t) * Cb + (j - Ca)];
+    if (mask) v *= mask[(size_t)b * mask_ld + (size_t)t * mask_step];
+  }
+  const __half hi = __float2half_rn(v);
+  __half* o = out + ((size_t)b * To + to) * Wo * (split ? 2 : 1);
+  o[jj] = hi;
+  if (split) o[Wo + jj] = __float2half_rn(v - __half2float(hi));
+}
+
+// GroupNorm statistics (nn.GroupNorm(G, C) of Block1D, matcha/models/components/decoder.py:35): per (batch, chunk of GN_ROWS
+// frames, group) the sum and the sum of squares of the frame-major fp32 stream x (B, T, C).  Per-thread fp32 partials over <= 64
+// values, everything above in double and in a fixed order (deterministic).  C/4 divides 256 and G divides C/4.
+constexpr int GN_ROWS = 64;
+__global__ void __launch_bounds__(256) unet_gn_stats_kernel(const float* __restrict__ x, double2* __restrict__ part, int T, int C, int G) {
+  __shared__ float2 sh[256];
+  const int b = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
+  const int c4n = C >> 2, col = threadIdx.x % c4n, rl = threadIdx.x / c4n, rstep = 256 / c4n;
+  const int t0 = chunk * GN_ROWS, t1 = min(T, t0 + GN_ROWS);
+  const float4* xr = reinterpret_cast<const float4*>(x) + (size_t)b * T * c4n;
+  float s = 0.f, q = 0.f;
+  for (int t = t0 + rl; t < t1; t += rstep) {
+    const float4 v = xr[(size_t)t * c4n + col];
+    s += (v.x + v.y) + (v.z + v.w);
+    q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  sh[threadIdx.x] = make_float2(s, q);
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const int gw = c4n / G, g = threadIdx.x;
+    double S = 0.0, Q = 0.0;
+    for (int r = 0; r < rstep; r++)
+      for (int cc = g * gw; cc < (g + 1) * gw; cc++) { const float2 p = sh[r * c4n + cc]; S += (double)p.x; Q += (double)p.y; }
+    part[((size_t)b * nchunk + chunk) * G + g] = make_double2(S, Q);
+  }
+}
+
+// y = (Mish(GroupNorm(x) * gamma + beta) + add[batch]) * mask   (Block1D :41-43, the time-embedding add of ResnetBlock1D :59, and
+// the `* mask` the next conv applies to its input).  A warp per frame, lanes own float4 columns like unet_ln_kernel; the block
+// first folds the chunk partials of its batch row into mean / rstd per group (eps 1e-5).
+__global__ void __launch_bounds__(256) unet_gn_apply_kernel(const float* __restrict__ x, const double2* __restrict__ part, int nchunk,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             const float* __restrict__ add, int add_ld, const float* __restrict__ mask,
+                                                             int mask_ld, int mask_step, __half* __restrict__ out16,
+                                                             float* __restrict__ out32, int T, int C, int G, int split) {
+  __shared__ float s_mean[32], s_rstd[32];
+  const int b = blockIdx.y;
+  if (threadIdx.x < G) {
+    double S = 0.0, Q = 0.0;
+    for (int i = 0; i < nchunk; i++) { const double2 p = part[((size_t)b * nchunk + i) * G + threadIdx.x]; S += p.x; Q += p.y; }
+    const double n = (double)T * (double)(C / G), mean = S / n, var = fmax(Q / n - mean * mean, 0.0);
+    s_mean[threadIdx.x] = (float)mean;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + 1e-5));
+  }
+  __syncthreads();
+  const int t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (t >= T) return;
+  const size_t row = (size_t)b * T + t;
+  const float m = mask ? mask[(size_t)b * mask_ld + (size_t)t * mask_step] : 1.0f;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+  const float* ar = add ? add + (size_t)b * add_ld : nullptr;
+  const int n = C >> 7, gw = C / G;
+  for (int k = 0; k < n; k++) {
+    const int c4 = k * 32 + lane, g = (c4 * 4) / gw;
+    const float4 v = xr[c4];
+    const float mean = s_mean[g], rstd = s_rstd[g];
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + c4), bt = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    float y[4] = {(v.x - mean) * rstd * ga.x + bt.x, (v.y - mean) * rstd * ga.y + bt.y, (v.z - mean) * rstd * ga.z + bt.z,
+                  (v.w - mean) * rstd * ga.w + bt.w};
+#pragma unroll
+    for (int e = 0; e < 4; e++) { const float sp = y[e] > 20.0f ? y[e] : log1pf(expf(y[e])); y[e] = y[e] * tanhf(sp); }
+    if (ar) {
+      const float4 aa = __ldg(reinterpret_cast<const float4*>(ar) + c4);
+      y[0] += aa.x; y[1] += aa.y; y[2] += aa.z; y[3] += aa.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; e++) y[e] *= m;
+    if (out32) reinterpret_cast<float4*>(out32 + row * C)[c4] = make_float4(y[0], y[1], y[2], y[3]);
+    if (out16) {
+      __half* orow = out16 + row * C * (split ? 2 : 1);
+      const __half2 h01 = __floats2half2_rn(y[0], y[1]), h23 = __floats2half2_rn(y[2], y[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&h01); pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+      reinterpret_cast<uint2*>(orow)[c4] = pk;
+      if (split) {
+        const __half2 l01 = __floats2half2_rn(y[0] - __low2float(h01), y[1] - __high2float(h01));
+        const __half2 l23 = __floats2half2_rn(y[2] - __low2float(h23), y[3] - __high2float(h23));
+        pk.x = *reinterpret_cast<const uint32_t*>(&l01); pk.y = *reinterpret_cast<const uint32_t*>(&l23);
+        reinterpret_cast<uint2*>(orow + C)[c4] = pk;
+      }
+    }
+  }
+}
+
+// valid keys per (level, batch row) from the seam's 0/1 prefix mask (B, 1, T): level l sees mask[:, :, ::2^l] (decoder.py:246)
+__global__ void unet_klen_kernel(const float* __restrict__ mask, int T, int levels, int* __restrict__ klen) {
+  const int b = blockIdx.x;
+  int n = 0;
+  for (int t = threadIdx.x; t < T; t += 32) n += mask[(size_t)b * T + t] != 0.f;
+  for (int o = 16; o; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if (threadIdx.x == 0)
+    for (int l = 0; l < levels; l++) { klen[l * 2 + b] = n; n = (n + 1) >> 1; }
 }
 
 // y = act(LayerNorm(h) * gamma + beta) (+ add[batch])   eps 1e-5 (nn.LayerNorm default); act 1 = Mish.
@@ -153,12 +285,12 @@ __global__ void __launch_bounds__(256) unet_rmlp_kernel(const float* __restrict_
 }
 
 // v (2T, C) frame-major -> out (2, C, T)
-__global__ void unet_unpack_kernel(const float* __restrict__ v, float* __restrict__ out, int T, int C) {
+__global__ void unet_unpack_kernel(const float* __restrict__ v, float* __restrict__ out, int T, int C, const float* __restrict__ mask) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * T * C) return;
   const int b = i / (C * T), rem = i - b * C * T;
   const int c = rem / T, t = rem - c * T;
-  out[i] = v[((size_t)b * T + t) * C + c];
+  out[i] = v[((size_t)b * T + t) * C + c] * (mask ? mask[(size_t)b * T + t] : 1.0f);
 }
 
 // ------------------------------------------------------------------ state
@@ -169,14 +301,17 @@ struct UnetState {
   const float *freqs, *tm1_w, *tm1_b, *tm2_w, *tm2_b, *rmlp_w, *rmlp_b;
   std::vector<UnetRes> res;
   std::vector<UnetTfm> tfm;
-  const __half *down_w, *up_w, *fin_w, *proj_w;
-  const float *down_b, *up_b, *fin_b, *fin_g, *fin_bt, *proj_b;
+  std::vector<const __half*> down_w, up_w;              // per level (one level in the causal variant)
+  std::vector<const float*> down_b, up_b;
+  const __half *fin_w, *proj_w;
+  const float *fin_b, *fin_g, *fin_bt, *proj_b;
   DevBuf ws, ws_solve;
   int precise = 0, vt_T = -1;
+  int nc = 0, levels = 1, groups = 8;                  // nc: the non-causal multi-level ConditionalDecoder
   // one estimator evaluation = a fixed sequence of ~490 small launches: replayed as a CUDA graph on an engine-owned stream
   // once the same (pointers, T, mask mode) has been seen twice — the Euler loop of solve_euler calls the seam with stable
   // buffers (flow_matching.py:93-99)
-  struct Key { const void *x, *mu, *t, *spks, *cond, *out, *ws; int T, streaming; };
+  struct Key { const void *x, *mu, *t, *spks, *cond, *out, *ws, *mask; int T, streaming; };
   Key seen{}, gkey{};
   cudaGraphExec_t gexec = nullptr;
   int64_t glaunches = 0;
@@ -210,10 +345,16 @@ hvx_status unet_finalize(hvx_engine* e) {
   if (!e->unet) e->unet = new UnetState();
   UnetState* u = e->unet;
   u->precise = c.flow_precise ? 1 : 0;
+  u->nc = c.unet_noncausal ? 1 : 0;
+  u->levels = u->nc ? c.unet_levels : 1;
+  u->groups = c.unet_groups > 0 ? c.unet_groups : 8;
+  HVX_CHECK(u->levels >= 1 && u->levels <= 4, HVX_ERR_UNSUPPORTED, "unet: %d levels unsupported (1..4)", u->levels);
+  HVX_CHECK(!u->nc || (u->groups <= 32 && (C / 4) % u->groups == 0 && 256 % (C / 4) == 0), HVX_ERR_UNSUPPORTED,
+            "unet: GroupNorm(%d, %d) unsupported (C/4 divides 256, groups divides C/4)", u->groups, C);
   if (u->gexec) { cudaGraphExecDestroy(u->gexec); u->gexec = nullptr; }     // a captured replay holds the old weight pointers
   u->seen = UnetState::Key{}; u->gkey = UnetState::Key{};
   const int64_t wx = u->precise ? 2 : 1;
-  const int n_res = c.unet_n_mid + 2;
+  const int L = u->levels, n_res = c.unet_n_mid + 2 * L;
   UGET(uget(e, "time.freqs", HVX_F32, &u->freqs, in_ch / 2));
   UGET(uget(e, "time.l1.w", HVX_F32, &u->tm1_w, (int64_t)tdim * in_ch));
   UGET(uget(e, "time.l1.b", HVX_F32, &u->tm1_b, tdim));
@@ -225,7 +366,7 @@ hvx_status unet_finalize(hvx_engine* e) {
   u->tfm.assign((size_t)n_res * c.unet_n_blocks, UnetTfm());
   for (int i = 0; i < n_res; i++) {
     UnetRes& r = u->res[i];
-    r.cin = i == 0 ? in_ch : (i == n_res - 1 ? 2 * C : C);
+    r.cin = i == 0 ? in_ch : (i >= n_res - L ? 2 * C : C);
     const std::string p = "res" + std::to_string(i) + ".";
     UGET(uget(e, p + "c1.w", HVX_F16, &r.c1_w, wx * C * 3 * r.cin));
     UGET(uget(e, p + "c1.b", HVX_F32, &r.c1_b, C));
@@ -253,10 +394,16 @@ hvx_status unet_finalize(hvx_engine* e) {
       UGET(uget(e, q + "ff2.b", HVX_F32, &t.ff2_b, C));
     }
   }
-  UGET(uget(e, "down.w", HVX_F16, &u->down_w, wx * C * 3 * C));
-  UGET(uget(e, "down.b", HVX_F32, &u->down_b, C));
-  UGET(uget(e, "up.w", HVX_F16, &u->up_w, wx * C * 3 * C));
-  UGET(uget(e, "up.b", HVX_F32, &u->up_b, C));
+  u->down_w.assign(L, nullptr); u->up_w.assign(L, nullptr); u->down_b.assign(L, nullptr); u->up_b.assign(L, nullptr);
+  for (int l = 0; l < L; l++) {
+    const std::string sfx = u->nc ? std::to_string(l) : std::string();
+    const bool last = l == L - 1;                       // the last level keeps its length: Conv1d(C, C, 3, padding=1)
+    // Downsample1D as a 2-tap conv over frame pairs: (C, 2 taps x 2C); Upsample1D as a k3 conv with 2C outputs: (2C, 3 x C)
+    UGET(uget(e, "down" + sfx + ".w", HVX_F16, &u->down_w[l], wx * C * (last ? 3 : 4) * C));
+    UGET(uget(e, "down" + sfx + ".b", HVX_F32, &u->down_b[l], C));
+    UGET(uget(e, "up" + sfx + ".w", HVX_F16, &u->up_w[l], wx * (last ? 1 : 2) * C * 3 * C));
+    UGET(uget(e, "up" + sfx + ".b", HVX_F32, &u->up_b[l], (last ? 1 : 2) * C));
+  }
   UGET(uget(e, "fin.w", HVX_F16, &u->fin_w, wx * C * 3 * C));
   UGET(uget(e, "fin.b", HVX_F32, &u->fin_b, C));
   UGET(uget(e, "fin.g", HVX_F32, &u->fin_g, C));
@@ -284,11 +431,16 @@ struct UnetRun {
     GemmAddr ga; ga.split3_kb = K / 64;
     return gemm_bf16(e, st, (const __nv_bfloat16*)x, 2 * K, (const __nv_bfloat16*)w, 2 * K, M, N, 3 * K, p, &ga);
   }
-  // CausalConv1d(Cin, N, 3) over frame-major rows (decoder.py:36-62): implicit GEMM, K = 3*Cin, rows t-2..t of the same batch
+  // Conv1d(Cin, N, taps) over frame-major rows as implicit GEMM: K = taps*Cin, operand rows t+row0 .. t+row0+taps-1 of the same
+  // batch, rows outside the batch read as zero (TMA fill) = the convolution's zero padding
+  hvx_status convk(const __half* x, const __half* w, int N, int Cin, int taps, int row0, const GemmEpi& p) const {
+    GemmAddr ga; ga.n_batch = 2; ga.rows_per_batch = T; ga.a_cols = px * Cin; ga.kb_per_tap = Cin / 64; ga.a_row0 = row0; ga.a_row_step = 1;
+    if (u->precise) { ga.a_lo_off = Cin; ga.split3_kb = taps * Cin / 64; }
+    return gemm_bf16(e, st, (const __nv_bfloat16*)x, px * Cin, (const __nv_bfloat16*)w, px * taps * Cin, M, N, (u->precise ? 3 : 1) * taps * Cin, p, &ga);
+  }
+  // CausalConv1d(Cin, N, 3) (decoder.py:36-62): rows t-2..t;  non-causal Conv1d(Cin, N, 3, padding=1): rows t-1..t+1
   hvx_status conv3(const __half* x, const __half* w, int N, int Cin, const GemmEpi& p) const {
-    GemmAddr ga; ga.n_batch = 2; ga.rows_per_batch = T; ga.a_cols = px * Cin; ga.kb_per_tap = Cin / 64; ga.a_row0 = -2; ga.a_row_step = 1;
-    if (u->precise) { ga.a_lo_off = Cin; ga.split3_kb = 3 * Cin / 64; }
-    return gemm_bf16(e, st, (const __nv_bfloat16*)x, px * Cin, (const __nv_bfloat16*)w, px * 3 * Cin, M, N, (u->precise ? 3 : 1) * 3 * Cin, p, &ga);
+    return convk(x, w, N, Cin, 3, u->nc ? -1 : -2, p);
   }
   GemmEpi f32(float* out, int ldo, const float* bias, const float* resid = nullptr) const {
     GemmEpi p; p.mode = EPI_F32; p.f16 = 1; p.bias = bias; p.out = out; p.ldo = ldo; p.resid = resid; return p;
@@ -304,6 +456,38 @@ struct UnetRun {
     return HVX_OK;
   }
 
+  // non-causal variant: the level's mask view and the GroupNorm scratch
+  const float* mask = nullptr; int mask_ld = 0, mask_step = 1; double2* gn_part = nullptr;
+  void set_level(int T_level, int level, const float* mask0, int T0) {
+    T = T_level; M = 2 * T; Tp = (T + 7) & ~7; mask = mask0; mask_ld = T0; mask_step = 1 << level;
+  }
+  // y = (Mish(GroupNorm(in)) + add) * mask -> fp16 operand rows (o16) or fp32 (o32)
+  hvx_status gn(const float* in, const float* g, const float* b, const float* add, __half* o16, float* o32) const {
+    const int nchunk = cdiv(T, GN_ROWS);
+    unet_gn_stats_kernel<<<dim3(nchunk, 2), 256, 0, st>>>(in, gn_part, T, C, u->groups);
+    HVX_LAUNCH_CHECK(e);
+    unet_gn_apply_kernel<<<dim3(cdiv(T, 8), 2), 256, 0, st>>>(in, gn_part, nchunk, g, b, add, n_add_ld, mask, mask_ld, mask_step, o16, o32,
+                                                             T, C, u->groups, u->precise);
+    HVX_LAUNCH_CHECK(e);
+    return HVX_OK;
+  }
+  // fp32 rows x mask -> fp16 operand rows; a has a_T rows per batch, b (optional) is concatenated; pair: two frames per row
+  hvx_status cast_nc(const float* a, int a_T, const float* b, __half* out, int Ca, int Cb, bool pair = false) const {
+    const int To = pair ? (T + 1) / 2 : T, Wo = (Ca + Cb) * (pair ? 2 : 1);
+    unet_cast_nc_kernel<<<dim3(cdiv(To * Wo, 256), 2), 256, 0, st>>>(a, a_T, b, out, T, To, Ca, Cb, u->precise, mask, mask_ld, mask_step, pair);
+    HVX_LAUNCH_CHECK(e);
+    return HVX_OK;
+  }
+  // ResnetBlock1D (matcha decoder.py:46-61): x16 = masked fp16 rows of the block input -> h (fp32)
+  hvx_status resnet_nc(const UnetRes& r, const __half* x16, const float* add) const {
+    hvx_status rc;
+    if ((rc = conv3(x16, r.c1_w, C, r.cin, f32(tmp, C, r.c1_b)))) return rc;
+    if ((rc = gn(tmp, r.ln1_g, r.ln1_b, add, b16, nullptr))) return rc;
+    if ((rc = conv3(b16, r.c2_w, C, C, f32(tmp, C, r.c2_b)))) return rc;
+    if ((rc = gn(tmp, r.ln2_g, r.ln2_b, nullptr, nullptr, h))) return rc;
+    return linear(x16, r.rc_w, C, r.cin, f32(h, C, r.rc_b, h));                      // + res_conv(x * mask)
+  }
+
   // CausalResnetBlock1D: x16 = fp16 rows of the block input (cin wide) -> h (fp32)
   hvx_status resnet(const UnetRes& r, const __half* x16, const float* add) const {
     hvx_status rc;
@@ -317,14 +501,14 @@ struct UnetRun {
   int n_add_ld = 0;
 
   // BasicTransformerBlock (self-attention + GELU feed-forward) in place on h
-  hvx_status block(const UnetTfm& t, int heads, int chunk) const {
+  hvx_status block(const UnetTfm& t, int heads, int chunk, const int* klen = nullptr) const {
     hvx_status rc;
     if ((rc = ln(h, t.n1_g, t.n1_b, nullptr, 0, b16, nullptr))) return rc;
     { GemmEpi p; p.mode = EPI_QKV; p.f16 = 1; p.out = qk; p.ldo = 2 * inner; p.n_qk = 2 * inner; p.vt = (__nv_bfloat16*)vt; p.vt_ld = Tp;
       p.T = T; p.heads = heads; p.rows_per_batch = T;                                 // rope tables null: no rotary on this path
       if ((rc = linear(b16, t.qkv_w, 3 * inner, C, p))) return rc; }
     { AttnArgs a; a.T = T; a.heads = heads; a.n_batch = 2; a.chunk = chunk; a.f16 = 1; a.ld_out = inner; a.out = (__nv_bfloat16*)ao;
-      a.lo_off = u->precise ? inner : 0;
+      a.lo_off = u->precise ? inner : 0; a.klen = klen;
       if ((rc = dit_attention(e, st, (const __nv_bfloat16*)qk, 2 * inner, inner, (const __nv_bfloat16*)vt, Tp, a))) return rc; }
     if ((rc = linear(ao, t.out_w, C, inner, f32(h, C, t.out_b, h)))) return rc;
     if ((rc = ln(h, t.n3_g, t.n3_b, nullptr, 0, b16, nullptr))) return rc;
@@ -341,12 +525,17 @@ using namespace hvx;
 
 // dump_dev (optional): the fp32 residual stream (2T, C) after every resnet and every transformer block, in execution order
 // (n_res * (1 + n_blocks) slabs) — parity localisation for tests; n_dump = slabs the buffer holds.
-static hvx_status unet_run(hvx_engine* e, const float* x, const float* mu, const float* t, const float* spks, const float* cond, int T,
-                           int streaming, float* out, float* dump, int n_dump, cudaStream_t st) {
+static hvx_status unet_run_nc(hvx_engine* e, const float* x, const float* mask, const float* mu, const float* t, const float* spks,
+                              const float* cond, int T, float* out, float* dump, int n_dump, cudaStream_t st);
+
+static hvx_status unet_run(hvx_engine* e, const float* x, const float* mask, const float* mu, const float* t, const float* spks,
+                           const float* cond, int T, int streaming, float* out, float* dump, int n_dump, cudaStream_t st) {
   HVX_CHECK(e && e->unet, HVX_ERR_STATE, "unet stage not finalized");
   HVX_CHECK(x && mu && t && spks && cond && out && T >= 1, HVX_ERR_ARG, "unet estimator: bad argument");
   const hvx_config& c = e->cfg;
   UnetState* u = e->unet;
+  if (u->nc) return unet_run_nc(e, x, mask, mu, t, spks, cond, T, out, dump, n_dump, st);
+  HVX_CHECK(!mask, HVX_ERR_UNSUPPORTED, "unet: the causal variant takes no padding mask (all-true at inference, flow_matching.py:104-111)");
   UnetRun r;
   r.e = e; r.st = st; r.u = u; r.T = T; r.M = 2 * T; r.C = c.unet_ch; r.inner = c.unet_heads * 64; r.ff = r.C * c.unet_ff_mult;
   r.px = u->precise ? 2 : 1; r.Tp = (T + 7) & ~7;
@@ -385,7 +574,7 @@ static hvx_status unet_run(hvx_engine* e, const float* x, const float* mu, const
   HVX_LAUNCH_CHECK(e);
   unet_rmlp_kernel<<<dim3(cdiv(n_res * C, 8), 2), 256, 0, st>>>(r.temb, u->rmlp_w, u->rmlp_b, r.radd, n_res * C, tdim, 0);
   HVX_LAUNCH_CHECK(e);
-  unet_pack_kernel<<<cdiv(2 * T * in_ch, 256), 256, 0, st>>>(x, mu, spks, cond, r.a16, T, mel, u->precise);
+  unet_pack_kernel<<<cdiv(2 * T * in_ch, 256), 256, 0, st>>>(x, mu, spks, cond, r.a16, T, mel, u->precise, nullptr);
   HVX_LAUNCH_CHECK(e);
 
   const int chunk = streaming ? c.unet_chunk : 0;
@@ -402,7 +591,7 @@ static hvx_status unet_run(hvx_engine* e, const float* x, const float* mu, const
     if (down || up) {                                                                  // CausalConv1d(C, C, 3) (decoder.py:349-351,392-396)
       if (down) HVX_CUDA(cudaMemcpyAsync(r.skip, r.h, M * C * 4, cudaMemcpyDeviceToDevice, st));
       if ((rc = r.cast(r.h, nullptr, r.a16, C, 0))) return rc;
-      if ((rc = r.conv3(r.a16, down ? u->down_w : u->up_w, C, C, r.f32(r.h, C, down ? u->down_b : u->up_b)))) return rc;
+      if ((rc = r.conv3(r.a16, down ? u->down_w[0] : u->up_w[0], C, C, r.f32(r.h, C, down ? u->down_b[0] : u->up_b[0])))) return rc;
     }
   }
   // final_block (CausalBlock1D) + final_proj (decoder.py:397-398,492-494)
@@ -410,20 +599,131 @@ static hvx_status unet_run(hvx_engine* e, const float* x, const float* mu, const
   if ((rc = r.conv3(r.a16, u->fin_w, C, C, r.f32(r.tmp, C, u->fin_b)))) return rc;
   if ((rc = r.ln(r.tmp, u->fin_g, u->fin_bt, nullptr, 1, r.b16, nullptr))) return rc;
   if ((rc = r.linear(r.b16, u->proj_w, mel, C, r.f32(r.v, mel, u->proj_b)))) return rc;
-  unet_unpack_kernel<<<cdiv(2 * T * mel, 256), 256, 0, st>>>(r.v, out, T, mel);
+  unet_unpack_kernel<<<cdiv(2 * T * mel, 256), 256, 0, st>>>(r.v, out, T, mel, nullptr);
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
 }
 
-static hvx_status unet_estimate(hvx_engine* e, const float* x, const float* mu, const float* t, const float* spks,
+// The non-causal multi-level ConditionalDecoder.forward (cosyvoice/flow/decoder.py:210-291).  mask: (2, T) 0/1 prefix masks or null.
+static hvx_status unet_run_nc(hvx_engine* e, const float* x, const float* mask, const float* mu, const float* t, const float* spks,
+                              const float* cond, int T, float* out, float* dump, int n_dump, cudaStream_t st) {
+  const hvx_config& c = e->cfg;
+  UnetState* u = e->unet;
+  UnetRun r;
+  r.e = e; r.st = st; r.u = u; r.C = c.unet_ch; r.inner = c.unet_heads * 64; r.ff = r.C * c.unet_ff_mult; r.px = u->precise ? 2 : 1;
+  const int C = r.C, mel = c.unet_mel, in_ch = 4 * mel, tdim = 4 * C, L = u->levels, n_res = c.unet_n_mid + 2 * L, nb = c.unet_n_blocks;
+  int Tl[5];                                               // frames per level: Conv1d(k3, stride 2, pad 1) -> ceil(T / 2)
+  Tl[0] = T;
+  for (int l = 1; l < L; l++) Tl[l] = (Tl[l - 1] + 1) / 2;
+  const size_t M = 2 * (size_t)T, Tp0 = (T + 7) & ~7;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const int wmax = std::max(in_ch, 2 * C);
+  const size_t o_a = take((M + 2) * wmax * 2 * r.px), o_b = take(M * C * 2 * r.px), o_qk = take(M * 2 * r.inner * 2);
+  const size_t o_vt = take((size_t)2 * r.inner * Tp0 * 2), o_ao = take(M * r.inner * 2 * r.px), o_f1 = take(M * r.ff * 2 * r.px);
+  const size_t o_h = take((M + 2) * C * 4), o_tmp = take((M + 2) * C * 4), o_te = take((size_t)2 * tdim * 4), o_te1 = take((size_t)2 * tdim * 4);
+  const size_t o_ra = take((size_t)2 * n_res * C * 4), o_v = take(M * mel * 4), o_kl = take(sizeof(int) * 2 * 4);
+  const size_t o_gn = take(sizeof(double2) * 2 * cdiv(T, GN_ROWS) * 32);
+  size_t o_skip[4];
+  for (int l = 0; l < L; l++) o_skip[l] = take(2 * (size_t)Tl[l] * C * 4);
+  const bool grew = off > u->ws.bytes;
+  uint8_t* w = (uint8_t*)u->ws.get(off);
+  HVX_CHECK(w, HVX_ERR_CUDA, "unet: workspace allocation of %zu bytes failed", off);
+  r.a16 = (__half*)(w + o_a); r.b16 = (__half*)(w + o_b); r.qk = (__half*)(w + o_qk); r.vt = (__half*)(w + o_vt);
+  r.ao = (__half*)(w + o_ao); r.f1 = (__half*)(w + o_f1); r.h = (float*)(w + o_h); r.tmp = (float*)(w + o_tmp);
+  r.temb = (float*)(w + o_te); r.temb1 = (float*)(w + o_te1); r.radd = (float*)(w + o_ra); r.v = (float*)(w + o_v);
+  r.gn_part = (double2*)(w + o_gn);
+  int* klen = (int*)(w + o_kl);
+  r.n_add_ld = n_res * C;
+  if (grew || u->vt_T != T) {                       // V^T pad columns must hold finite values (every later content is a real V)
+    HVX_CUDA(cudaMemsetAsync(r.vt, 0, (size_t)2 * r.inner * Tp0 * 2, st));
+    u->vt_T = T;
+  }
+  hvx_status rc;
+  int slab = 0;
+  auto dump_h = [&]() -> hvx_status {
+    if (dump && slab < n_dump) HVX_CUDA(cudaMemcpyAsync(dump + (size_t)slab * M * C, r.h, (size_t)r.M * C * 4, cudaMemcpyDeviceToDevice, st));
+    slab++;
+    return HVX_OK;
+  };
+
+  unet_time1_kernel<<<dim3(cdiv(tdim, 8), 2), 256, 0, st>>>(t, u->freqs, u->tm1_w, u->tm1_b, r.temb1, in_ch, tdim);
+  HVX_LAUNCH_CHECK(e);
+  unet_rmlp_kernel<<<dim3(cdiv(tdim, 8), 2), 256, 0, st>>>(r.temb1, u->tm2_w, u->tm2_b, r.temb, tdim, tdim, 1);
+  HVX_LAUNCH_CHECK(e);
+  unet_rmlp_kernel<<<dim3(cdiv(n_res * C, 8), 2), 256, 0, st>>>(r.temb, u->rmlp_w, u->rmlp_b, r.radd, n_res * C, tdim, 0);
+  HVX_LAUNCH_CHECK(e);
+  if (mask) { unet_klen_kernel<<<2, 32, 0, st>>>(mask, T, L, klen); HVX_LAUNCH_CHECK(e); }
+  unet_pack_kernel<<<cdiv(2 * T * in_ch, 256), 256, 0, st>>>(x, mu, spks, cond, r.a16, T, mel, u->precise, mask);
+  HVX_LAUNCH_CHECK(e);
+
+  // one stage = ResnetBlock1D + n_blocks transformer blocks at level l, input = masked fp16 rows in a16
+  auto stage = [&](int i, int l) -> hvx_status {
+    hvx_status rc2;
+    if ((rc2 = r.resnet_nc(u->res[i], r.a16, r.radd + (size_t)i * C))) return rc2;
+    if ((rc2 = dump_h())) return rc2;
+    for (int j = 0; j < nb; j++) {
+      if ((rc2 = r.block(u->tfm[(size_t)i * nb + j], c.unet_heads, 0, mask ? klen + 2 * l : nullptr))) return rc2;
+      if ((rc2 = dump_h())) return rc2;
+    }
+    return HVX_OK;
+  };
+  int i = 0;
+  for (int l = 0; l < L; l++, i++) {                                                       // down path (decoder.py:235-246)
+    r.set_level(Tl[l], l, mask, T);
+    if (l > 0) { if ((rc = r.cast_nc(r.h, Tl[l], nullptr, r.a16, C, 0))) return rc; }
+    if ((rc = stage(i, l))) return rc;
+    float* skip = (float*)(w + o_skip[l]);
+    HVX_CUDA(cudaMemcpyAsync(skip, r.h, 2 * (size_t)Tl[l] * C * 4, cudaMemcpyDeviceToDevice, st));
+    if (l == L - 1) {                                                                        // Conv1d(C, C, 3, padding=1)
+      if ((rc = r.cast_nc(r.h, Tl[l], nullptr, r.a16, C, 0))) return rc;
+      if ((rc = r.conv3(r.a16, u->down_w[l], C, C, r.f32(r.h, C, u->down_b[l])))) return rc;
+    } else {                                                                                 // Downsample1D: 2 taps over frame pairs
+      if ((rc = r.cast_nc(r.h, Tl[l], nullptr, r.a16, C, 0, true))) return rc;
+      r.set_level(Tl[l + 1], l + 1, mask, T);
+      if ((rc = r.convk(r.a16, u->down_w[l], C, 2 * C, 2, -1, r.f32(r.h, C, u->down_b[l])))) return rc;
+    }
+  }
+  r.set_level(Tl[L - 1], L - 1, mask, T);
+  for (int k = 0; k < c.unet_n_mid; k++, i++) {                                             // mid blocks (decoder.py:250-263)
+    if ((rc = r.cast_nc(r.h, Tl[L - 1], nullptr, r.a16, C, 0))) return rc;
+    if ((rc = stage(i, L - 1))) return rc;
+  }
+  int src_T = Tl[L - 1];                                                                     // rows per batch of the stream entering the up stage
+  const float* src = r.h;
+  for (int k = 0; k < L; k++, i++) {                                                         // up path (decoder.py:265-287)
+    const int l = L - 1 - k;
+    r.set_level(Tl[l], l, mask, T);
+    if ((rc = r.cast_nc(src, src_T, (const float*)(w + o_skip[l]), r.a16, C, C))) return rc;  // pack([x[:, :, :skip_len], skip])
+    if ((rc = stage(i, l))) return rc;
+    if ((rc = r.cast_nc(r.h, Tl[l], nullptr, r.a16, C, 0))) return rc;
+    if (k == L - 1) {                                                                        // Conv1d(C, C, 3, padding=1)
+      if ((rc = r.conv3(r.a16, u->up_w[k], C, C, r.f32(r.h, C, u->up_b[k])))) return rc;
+      src = r.h; src_T = Tl[l];
+    } else {                                                                                 // Upsample1D: rows (y[2m], y[2m+1]) = 2*Tl[l] frames
+      if ((rc = r.conv3(r.a16, u->up_w[k], 2 * C, C, r.f32(r.tmp, 2 * C, u->up_b[k])))) return rc;
+      src = r.tmp; src_T = 2 * Tl[l];
+    }
+  }
+  // final_block (Block1D) + final_proj, output * mask (decoder.py:288-291); r is at level 0 here
+  if ((rc = r.cast_nc(r.h, T, nullptr, r.a16, C, 0))) return rc;
+  if ((rc = r.conv3(r.a16, u->fin_w, C, C, r.f32(r.tmp, C, u->fin_b)))) return rc;
+  if ((rc = r.gn(r.tmp, u->fin_g, u->fin_bt, nullptr, r.b16, nullptr))) return rc;
+  if ((rc = r.linear(r.b16, u->proj_w, mel, C, r.f32(r.v, mel, u->proj_b)))) return rc;
+  unet_unpack_kernel<<<cdiv(2 * T * mel, 256), 256, 0, st>>>(r.v, out, T, mel, mask);
+  HVX_LAUNCH_CHECK(e);
+  return HVX_OK;
+}
+
+static hvx_status unet_estimate(hvx_engine* e, const float* x, const float* mask, const float* mu, const float* t, const float* spks,
                                 const float* cond, int T, int streaming, float* out, cudaStream_t user) {
   HVX_CHECK(e && e->unet, HVX_ERR_STATE, "unet stage not finalized");
   UnetState* u = e->unet;
-  if (getenv("HVX_UNET_NO_GRAPH")) return unet_run(e, x, mu, t, spks, cond, T, streaming, out, nullptr, 0, user);
-  UnetState::Key key{x, mu, t, spks, cond, out, u->ws.p, T, streaming};
+  if (getenv("HVX_UNET_NO_GRAPH")) return unet_run(e, x, mask, mu, t, spks, cond, T, streaming, out, nullptr, 0, user);
+  UnetState::Key key{x, mu, t, spks, cond, out, u->ws.p, mask, T, streaming};
   const bool replay = u->gexec && !memcmp(&key, &u->gkey, sizeof(key));
   if (!replay && memcmp(&key, &u->seen, sizeof(key))) {                 // first sight of this call shape: run it as it is
-    const hvx_status rc = unet_run(e, x, mu, t, spks, cond, T, streaming, out, nullptr, 0, user);
+    const hvx_status rc = unet_run(e, x, mask, mu, t, spks, cond, T, streaming, out, nullptr, 0, user);
     key.ws = u->ws.p;                                                   // the run may have grown the workspace
     u->seen = key;
     return rc;
@@ -438,7 +738,7 @@ static hvx_status unet_estimate(hvx_engine* e, const float* x, const float* mu, 
     cudaGraph_t g;
     const int64_t l0 = e->launches;
     HVX_CUDA(cudaStreamBeginCapture(u->own, cudaStreamCaptureModeRelaxed));
-    const hvx_status rc = unet_run(e, x, mu, t, spks, cond, T, streaming, out, nullptr, 0, u->own);
+    const hvx_status rc = unet_run(e, x, mask, mu, t, spks, cond, T, streaming, out, nullptr, 0, u->own);
     cudaError_t ce = cudaStreamEndCapture(u->own, &g);
     if (rc) return rc;
     HVX_CHECK(ce == cudaSuccess, HVX_ERR_CUDA, "unet: graph capture failed: %s", cudaGetErrorString(ce));
@@ -462,7 +762,18 @@ extern "C" hvx_status hvx_unet_estimator(hvx_engine* e, const float* x, const fl
                                          const float* cond, int T, int streaming, float* out, void* stream) {
   HVX_CHECK(e, HVX_ERR_ARG, "unet_estimator: null engine");
   HVX_LOCK(e, HVX_STAGE_UNET);
-  return unet_estimate(e, x, mu, t, spks, cond, T, streaming, out, (cudaStream_t)stream);
+  return unet_estimate(e, x, nullptr, mu, t, spks, cond, T, streaming, out, (cudaStream_t)stream);
+}
+
+// the same seam with the decoder's padding mask (cosyvoice/flow/decoder.py:210: forward(x, mask, mu, t, spks, cond)): mask_dev is
+// (2, 1, T) fp32 0/1, each row a prefix mask (make_pad_mask), or null = all true.  Non-causal variant only.
+extern "C" hvx_status hvx_unet_estimator_masked(hvx_engine* e, const float* x, const float* mask, const float* mu, const float* t,
+                                                const float* spks, const float* cond, int T, float* out, float* dump_dev, int n_dump,
+                                                void* stream) {
+  HVX_CHECK(e, HVX_ERR_ARG, "unet_estimator_masked: null engine");
+  HVX_LOCK(e, HVX_STAGE_UNET);
+  if (dump_dev) return unet_run(e, x, mask, mu, t, spks, cond, T, 0, out, dump_dev, n_dump, (cudaStream_t)stream);
+  return unet_estimate(e, x, mask, mu, t, spks, cond, T, 0, out, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------ CFM Euler solve over the U-Net estimator
@@ -533,7 +844,7 @@ extern "C" hvx_status hvx_cfm_solve_unet(hvx_engine* e, const float* mu, const f
   for (int s = 0; s < n_timesteps; s++) {
     cfm_set_t_kernel<<<1, 32, 0, st>>>(t_in, tv_dev, s);
     HVX_LAUNCH_CHECK(e);
-    const hvx_status rc = unet_estimate(e, x_in, mu_in, t_in, spks_in, cond_in, T, streaming, v, st);
+    const hvx_status rc = unet_estimate(e, x_in, nullptr, mu_in, t_in, spks_in, cond_in, T, streaming, v, st);
     if (rc) return rc;
     cfm_euler_kernel<<<cdiv(n, 256), 256, 0, st>>>(v, x_in, n, dtv[s], c.flow_cfg_rate);
     HVX_LAUNCH_CHECK(e);
@@ -547,5 +858,5 @@ extern "C" hvx_status hvx_unet_estimator_debug(hvx_engine* e, const float* x, co
                                                void* stream) {
   HVX_CHECK(e, HVX_ERR_ARG, "unet_estimator_debug: null engine");
   HVX_LOCK(e, HVX_STAGE_UNET);
-  return unet_run(e, x, mu, t, spks, cond, T, streaming, out, dump_dev, n_dump, (cudaStream_t)stream);
+  return unet_run(e, x, nullptr, mu, t, spks, cond, T, streaming, out, dump_dev, n_dump, (cudaStream_t)stream);
 }

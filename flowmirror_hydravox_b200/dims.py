@@ -139,6 +139,7 @@ UNET_FULL = UnetDims()
 UNET_TINY = UnetDims(mel=16, ch=128, n_blocks=2, n_mid=2, heads=2, chunk=6)
 UNET_NC_FULL = UnetNcDims()
 UNET_NC_TINY = UnetNcDims(mel=16, channels=(128, 128), n_blocks=1, n_mid=1, heads=2)
+UNET_NC_SMALL = UnetNcDims(channels=(128, 128), n_blocks=1, n_mid=2, heads=2)   # mel stays 80: solve_euler hard-codes it (flow_matching.py:94-99)
 UNET_SMALL = UnetDims(ch=128, n_blocks=1, n_mid=1, heads=2, chunk=10)     # mel stays 80: solve_euler hard-codes it (flow_matching.py:94-99)
 
 HIFT_TINY = HiftDims(base=64, f0_ch=64)

@@ -4,7 +4,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib as L
-from .weights import pack_flow, pack_unet
+from .weights import pack_flow, pack_unet, pack_unet_nc
 
 
 def rand_noise(mel: int = 80, frames: int = 15000) -> torch.Tensor:
@@ -121,8 +121,14 @@ class NativeUNetEstimator(torch.nn.Module):
         self.engine = engine
         self.dims = engine.ud
 
+    @property
+    def noncausal(self) -> bool:
+        """True: the engine holds the non-causal multi-level ConditionalDecoder (decoder.py:88-291; Engine(ud=dims.UNET_NC_FULL))"""
+        return hasattr(self.dims, "channels")
+
     def load_state_dict(self, sd, strict=True):
-        self.engine.set_tensors(L.STAGE_UNET, pack_unet(sd, self.dims, precise=getattr(self.engine, "flow_precise", False)))
+        pack = pack_unet_nc if self.noncausal else pack_unet
+        self.engine.set_tensors(L.STAGE_UNET, pack(sd, self.dims, precise=getattr(self.engine, "flow_precise", False)))
         self.engine.finalize(L.STAGE_UNET)
         return self
 
@@ -143,13 +149,21 @@ class NativeUNetEstimator(torch.nn.Module):
         dev = self.engine.device
         if x.dim() != 3 or x.shape[0] != 2 or x.shape[1] != self.dims.mel:
             raise ValueError(f"estimator input must be (2, {self.dims.mel}, T) — the CFG batch of solve_euler; got {tuple(x.shape)}")
-        if mask is not None and not bool((mask != 0).all()):
-            raise ValueError("padded batches are not built: the seam's mask is all-true at inference (flow_matching.py:104-111)")
         T = int(x.shape[2])
+        mask_d = None
+        if mask is not None and not bool((mask != 0).all()):
+            if not self.noncausal:
+                raise ValueError("the causal variant takes no padded batch: the seam's mask is all-true at inference (flow_matching.py:104-111)")
+            mask_d = (mask != 0).reshape(2, T).to(dev, torch.float32).contiguous()
+            if not bool((mask_d[:, 1:] <= mask_d[:, :-1]).all()):
+                raise ValueError("padding masks are prefix masks (make_pad_mask): a hole inside the valid frames is not supported")
         args = [a.to(dev, torch.float32).contiguous() for a in (x, mu, t.reshape(-1).expand(2) if t.numel() == 1 else t, spks, cond)]
         if out is None:            # `out=` (and device-resident fp32 inputs) keeps every pointer stable: the CUDA-graph replay path
             out = torch.empty(2, self.dims.mel, T, device=dev, dtype=torch.float32)
-        if _dump is None:
+        if self.noncausal and (mask_d is not None or _dump is not None):
+            L.check(L.lib().hvx_unet_estimator_masked(self.engine.h, L.ptr(args[0]), L.ptr(mask_d), *[L.ptr(a) for a in args[1:]], T,
+                                                      L.ptr(out), L.ptr(_dump), 0 if _dump is None else int(_dump.shape[0]), L.stream_ptr()))
+        elif _dump is None:
             L.check(L.lib().hvx_unet_estimator(self.engine.h, *[L.ptr(a) for a in args], T, int(bool(streaming)), L.ptr(out),
                                                L.stream_ptr()))
         else:
@@ -200,6 +214,42 @@ class NativeUNetCFM:
                                            int(self.rand_noise.shape[1]), T, int(n_timesteps), self._cf(float(temperature)),
                                            int(bool(streaming)), L.ptr(out), L.stream_ptr()))
         return out, None
+
+    __call__ = forward
+
+
+class NativeConditionalCFM(NativeUNetCFM):
+    """Drop-in for the non-causal `ConditionalCFM` (cosyvoice/flow/flow_matching.py:22-69) over the multi-level ConditionalDecoder
+    (Engine(ud=dims.UNET_NC_FULL)): `forward(mu, mask, n_timesteps, temperature, spks, cond, prompt_len, cache) -> (mel, cache)`.
+    The noise is drawn per call (`torch.randn_like(mu)`, :52) and the prompt / 34-frame overlap of z and mu are carried in
+    `cache` exactly as :53-60; the Euler solve is the same hvx_cfm_solve_unet call."""
+
+    def __init__(self, engine: "L.Engine"):
+        super().__init__(engine, noise=torch.zeros(engine.ud.mel, 1))
+
+    @torch.no_grad()
+    def forward(self, mu, mask=None, n_timesteps=10, temperature=1.0, spks=None, cond=None, prompt_len=0, cache=None, z=None):
+        d, dev = self.dims, self.engine.device
+        if mu.dim() != 3 or mu.shape[0] != 1 or mu.shape[1] != d.mel:
+            raise ValueError(f"mu must be (1, {d.mel}, T); got {tuple(mu.shape)}")
+        if mask is not None and not bool((mask != 0).all()):
+            raise ValueError("solve_euler takes one utterance (flow_matching.py:99-104): its mask is all-true")
+        T = int(mu.shape[2])
+        mu = mu.to(dev, torch.float32).clone()
+        z = (torch.randn_like(mu) if z is None else z.to(dev, torch.float32)) * temperature       # z: test hook (pinned noise)
+        if cache is not None and cache.shape[2] != 0:
+            cs = cache.shape[2]
+            z[:, :, :cs] = cache[:, :, :, 0].to(dev, torch.float32)
+            mu[:, :, :cs] = cache[:, :, :, 1].to(dev, torch.float32)
+        z_cache = torch.cat([z[:, :, :prompt_len], z[:, :, -34:]], dim=2)
+        mu_cache = torch.cat([mu[:, :, :prompt_len], mu[:, :, -34:]], dim=2)
+        cache = torch.stack([z_cache, mu_cache], dim=-1)
+        f = lambda a: None if a is None else a.to(dev, torch.float32).contiguous()
+        z, mu_d, spks_d, cond_d = z.contiguous(), mu.contiguous(), f(spks), f(cond)
+        out = torch.empty(1, d.mel, T, device=dev, dtype=torch.float32)
+        L.check(L.lib().hvx_cfm_solve_unet(self.engine.h, L.ptr(mu_d), L.ptr(spks_d), L.ptr(cond_d), L.ptr(z), T, T, int(n_timesteps),
+                                           self._cf(1.0), 0, L.ptr(out), L.stream_ptr()))
+        return out, cache
 
     __call__ = forward
 

@@ -8,6 +8,11 @@ Mirrors the upstream streaming orchestration the reference vendors in cosyvoice/
   * the vocoder is re-run over the cached mel with ``finalize=False`` and only the new samples are emitted;
   * the last call uses ``finalize=True`` and — because ``CosyVoice2Model.tts`` does not pass ``stream`` to that last
     ``token2wav`` (:352-358) — ``streaming=False``: the final mel is computed under full attention, not the chunk mask.
+``StreamingSynthesizerCV2`` is the other orchestration the reference vendors, ``CosyVoice2Model.token2wav`` (:279-313): the
+vocoder (the ConvTranspose1d ``HiFTGenerator``) runs only on the NEW mel frames plus an 8-frame mel cache, its source signal is
+continued from the previous chunk (``cache_source``), the first 3840 samples of every chunk are cross-faded with the previous
+chunk's held-back tail under a Hamming window (``fade_in_out``, cosyvoice/utils/common.py:169-177) and every non-final chunk
+holds its last 3840 samples back.
 One request at a time per synthesizer (a lock serialises ``tts``); a consumer that abandons the generator (client disconnect)
 cancels the decode (``hvx_llm_cancel``) and joins the LLM thread before the token buffers and sequence slot 0 can be reused.
 The reference polls the token list every 100 ms (:334); here the consumer watches the device-side token counter that the
@@ -52,9 +57,19 @@ class StreamingSynthesizer:
         with self._lock:
             yield from self._tts(request, head_k, sampling, n_timesteps, min_ratio, max_ratio, u, debug)
 
+    def _vocode(self, state: Dict, mel: torch.Tensor, finalize: bool) -> torch.Tensor:
+        """CosyVoice3Model.token2wav (cli/model.py:418-430): the causal vocoder re-runs over the cached mel, new samples are emitted"""
+        hift = self.mm.models["hift"]
+        state["mel"] = mel if "mel" not in state else torch.cat([state["mel"], mel], dim=2)
+        wav, _ = hift.inference(speech_feat=state["mel"], finalize=finalize)
+        off = state.get("speech_offset", 0)
+        wav = wav[:, off:]
+        state["speech_offset"] = off + wav.shape[1]
+        return wav
+
     def _tts(self, request, head_k, sampling, n_timesteps, min_ratio, max_ratio, u, debug):
         mm, dev = self.mm, self.dev
-        llm, flow, hift = mm.models["llm"], mm.models["flow"], mm.models["hift"]
+        llm, flow = mm.models["llm"], mm.models["flow"]
         n_new = int(request["text"].numel())
         mn, mx = float(request.get("min_ratio", min_ratio)), float(request.get("max_ratio", max_ratio))
         max_out = int(n_new * mx) + 8
@@ -84,19 +99,16 @@ class StreamingSynthesizer:
         emb = request["embedding"].reshape(1, -1).to(dev, torch.float32)
         hop, la = self.token_hop_len, self.pre_lookahead_len
         prompt_pad = int(math.ceil(P / hop) * hop - P)
-        token_offset, speech_offset, mel_cache = 0, 0, None
+        token_offset = 0
+        state: Dict = {}
 
         def token2wav(n_tok: int, finalize: bool):
-            nonlocal mel_cache, speech_offset
             with torch.cuda.stream(self.side):
                 # the reference's last token2wav call omits `stream` (cli/model.py:352-358): full attention on the final pass
                 mel, _ = flow.inference(token=out[:, :n_tok], embedding=emb, prompt_token=ptok, prompt_feat=pfeat,
                                         streaming=not finalize, finalize=finalize, n_timesteps=n_timesteps)
                 mel = mel[:, :, token_offset * 2:]
-                mel_cache = mel if mel_cache is None else torch.cat([mel_cache, mel], dim=2)
-                wav, _ = hift.inference(speech_feat=mel_cache, finalize=finalize)
-                wav = wav[:, speech_offset:]
-                speech_offset += wav.shape[1]
+                wav = self._vocode(state, mel, finalize)
                 res = wav.cpu()                       # D2H on the side stream, synchronises it
             if debug is not None:
                 debug.setdefault("mel", []).append(mel.cpu())
@@ -129,7 +141,7 @@ class StreamingSynthesizer:
             n = self._poll(cnt)
             if debug is not None:
                 debug["tokens"] = out[0, :n].cpu().tolist()
-                debug["mel_cache"] = lambda: mel_cache
+                debug["mel_cache"] = lambda: state.get("mel")
             if n > 0:
                 wav = token2wav(n, finalize=True)
                 if first and debug is not None:
@@ -139,3 +151,37 @@ class StreamingSynthesizer:
             if th.is_alive():                  # generator abandoned or failed mid-stream: stop the decode before anything is reused
                 L.check(L.lib().hvx_llm_cancel(mm.engine.h))
                 th.join()
+
+
+class StreamingSynthesizerCV2(StreamingSynthesizer):
+    """`CosyVoice2Model.tts(stream=True)` + `CosyVoice2Model.token2wav` (cosyvoice/cli/model.py:279-360): same chunk schedule, but the
+    vocoder is the ConvTranspose1d HiFTGenerator run on [8 cached mel frames | new frames] with the source continued from the
+    previous chunk and the chunk seams cross-faded (`fade_in_out`) — each chunk costs O(new frames), not O(frames so far).
+
+    hift_t: a NativeHiFTTransposed whose weights are loaded.  noise_fn(n_samples) -> (n_samples, harmonics) pins the source
+    module's Gaussian draw per vocoder call (tests); default: fresh noise per call, like the reference."""
+    mel_cache_len = 8                                      # cli/model.py:249
+    def __init__(self, model_manager, hift_t, noise_fn=None):
+        import numpy as np
+        super().__init__(model_manager)
+        self.hift_t, self.noise_fn = hift_t, noise_fn
+        self.source_cache_len = self.mel_cache_len * hift_t.dims.frame_samples            # :250 (8 * 480)
+        self.speech_window = torch.from_numpy(np.hamming(2 * self.source_cache_len)).to(self.dev)   # float64, :252
+
+    def _vocode(self, state: Dict, mel: torch.Tensor, finalize: bool) -> torch.Tensor:
+        ov = self.source_cache_len
+        cache = state.get("hift")
+        src_cache = None
+        if cache is not None:
+            mel = torch.cat([cache["mel"], mel], dim=2)
+            src_cache = cache["source"]
+        noise = None if self.noise_fn is None else self.noise_fn(mel.shape[2] * self.hift_t.dims.frame_samples)
+        wav, src = self.hift_t.inference(speech_feat=mel, cache_source=src_cache, noise=noise)
+        if cache is not None:                              # fade_in_out(tts_speech, cache speech, window) (:295, :308)
+            L.check(L.lib().hvx_fade_in_out(self.mm.engine.h, L.ptr(wav), L.ptr(cache["speech"]), L.ptr(self.speech_window), ov, L.stream_ptr()))
+        if finalize:
+            return wav
+        state["hift"] = {"mel": mel[:, :, -self.mel_cache_len:].contiguous(), "source": src[:, :, -ov:].contiguous(),
+                         "speech": wav[:, -ov:].contiguous()}
+        state["mel"] = mel
+        return wav[:, :-ov]

@@ -223,6 +223,69 @@ def pack_unet(sd: Dict[str, torch.Tensor], d: D.UnetDims, precise: bool = False)
     return o
 
 
+def pack_unet_nc(sd: Dict[str, torch.Tensor], d, precise: bool = False) -> Dict[str, torch.Tensor]:
+    """Non-causal multi-level ConditionalDecoder state_dict (cosyvoice/flow/decoder.py:88-205; dims.UnetNcDims) -> engine tensors of
+    the HVX_STAGE_UNET stage.  As pack_unet, with: GroupNorm affine parameters under the ln* names; Downsample1D (Conv1d k3 stride 2
+    pad 1) repacked as a 2-tap convolution over frame pairs — operand row t = (x[2t], x[2t+1]), y[t] = [0 | w0] row[t-1] +
+    [w1 | w2] row[t]; Upsample1D (ConvTranspose1d(C, C, 4, 2, 1), weight (Cin, Cout, 4)) repacked as a k3 pad-1 convolution with 2C
+    outputs — output row m = (y[2m], y[2m+1]), y[2m] = w3 x[m-1] + w1 x[m], y[2m+1] = w2 x[m] + w0 x[m+1]."""
+    import math
+    f = torch.float32
+    cvt = _split16 if precise else (lambda w: w.to(torch.float16).contiguous())
+    o: Dict[str, torch.Tensor] = {}
+    L, C = d.levels, d.ch
+    half = d.in_ch // 2
+    o["time.freqs"] = torch.exp(torch.arange(half).float() * -(math.log(10000) / (half - 1))).contiguous()
+    for i, n in ((1, "linear_1"), (2, "linear_2")):
+        o[f"time.l{i}.w"] = sd[f"time_mlp.{n}.weight"].to(f).contiguous()
+        o[f"time.l{i}.b"] = sd[f"time_mlp.{n}.bias"].to(f).contiguous()
+
+    def conv(key):
+        w = sd[key + ".weight"].to(f)                                    # (Cout, Cin, k) -> column = tap*Cin + ci
+        return cvt(w.permute(0, 2, 1).reshape(w.shape[0], -1)), sd[key + ".bias"].to(f).contiguous()
+
+    stages = [f"down_blocks.{i}" for i in range(L)] + [f"mid_blocks.{i}" for i in range(d.n_mid)] + [f"up_blocks.{i}" for i in range(L)]
+    rw, rb = [], []
+    for i, p in enumerate(stages):
+        r = p + ".0"
+        rw.append(sd[r + ".mlp.1.weight"].to(f)); rb.append(sd[r + ".mlp.1.bias"].to(f))
+        for n, blk in ((1, "block1"), (2, "block2")):
+            o[f"res{i}.c{n}.w"], o[f"res{i}.c{n}.b"] = conv(f"{r}.{blk}.block.0")
+            o[f"res{i}.ln{n}.g"] = sd[f"{r}.{blk}.block.1.weight"].to(f).contiguous()          # GroupNorm(8, C)
+            o[f"res{i}.ln{n}.b"] = sd[f"{r}.{blk}.block.1.bias"].to(f).contiguous()
+        o[f"res{i}.rc.w"], o[f"res{i}.rc.b"] = conv(r + ".res_conv")
+        for j in range(d.n_blocks):
+            t, q = f"{p}.1.{j}", f"tfm{i * d.n_blocks + j}"
+            o[q + ".n1.g"], o[q + ".n1.b"] = sd[t + ".norm1.weight"].to(f).contiguous(), sd[t + ".norm1.bias"].to(f).contiguous()
+            o[q + ".n3.g"], o[q + ".n3.b"] = sd[t + ".norm3.weight"].to(f).contiguous(), sd[t + ".norm3.bias"].to(f).contiguous()
+            o[q + ".qkv.w"] = cvt(torch.cat([sd[f"{t}.attn1.to_{n}.weight"].to(f) for n in "qkv"], 0))
+            o[q + ".out.w"], o[q + ".out.b"] = cvt(sd[t + ".attn1.to_out.0.weight"].to(f)), sd[t + ".attn1.to_out.0.bias"].to(f).contiguous()
+            o[q + ".ff1.w"], o[q + ".ff1.b"] = cvt(sd[t + ".ff.net.0.proj.weight"].to(f)), sd[t + ".ff.net.0.proj.bias"].to(f).contiguous()
+            o[q + ".ff2.w"], o[q + ".ff2.b"] = cvt(sd[t + ".ff.net.2.weight"].to(f)), sd[t + ".ff.net.2.bias"].to(f).contiguous()
+    o["rmlp.w"], o["rmlp.b"] = torch.cat(rw, 0).contiguous(), torch.cat(rb, 0).contiguous()
+    for l in range(L):
+        if l == L - 1:
+            o[f"down{l}.w"], o[f"down{l}.b"] = conv(f"down_blocks.{l}.2")
+            o[f"up{l}.w"], o[f"up{l}.b"] = conv(f"up_blocks.{l}.2")
+            continue
+        w = sd[f"down_blocks.{l}.2.conv.weight"].to(f)                    # (C, C, 3), stride 2
+        z = torch.zeros_like(w[:, :, 0])
+        o[f"down{l}.w"] = cvt(torch.cat([z, w[:, :, 0], w[:, :, 1], w[:, :, 2]], dim=1))       # (C, [tap0: 0 | w0], [tap1: w1 | w2])
+        o[f"down{l}.b"] = sd[f"down_blocks.{l}.2.conv.bias"].to(f).contiguous()
+        wt = sd[f"up_blocks.{l}.2.conv.weight"].to(f)                     # (Cin, Cout, 4)
+        k = [wt[:, :, i].t() for i in range(4)]                           # (Cout, Cin) per tap
+        z = torch.zeros_like(k[0])
+        even = torch.cat([k[3], k[1], z], dim=1)                          # y[2m]   = w3 x[m-1] + w1 x[m]
+        odd = torch.cat([z, k[2], k[0]], dim=1)                           # y[2m+1] = w2 x[m]   + w0 x[m+1]
+        o[f"up{l}.w"] = cvt(torch.cat([even, odd], dim=0))
+        b = sd[f"up_blocks.{l}.2.conv.bias"].to(f)
+        o[f"up{l}.b"] = torch.cat([b, b]).contiguous()
+    o["fin.w"], o["fin.b"] = conv("final_block.block.0")
+    o["fin.g"], o["fin.bt"] = sd["final_block.block.1.weight"].to(f).contiguous(), sd["final_block.block.1.bias"].to(f).contiguous()
+    o["proj.w"], o["proj.b"] = conv("final_proj")
+    return o
+
+
 def _rope_pair_perm(n_heads: int, head_dim: int = 64) -> torch.Tensor:
     """Row order that puts the HF half-split RoPE pair (d, d + head_dim/2) on adjacent rows (2i, 2i+1)."""
     half = head_dim // 2

@@ -58,6 +58,10 @@ typedef struct hvx_config {
   /* U-Net estimator: cosyvoice/flow/decoder.py:294-400 with channels == (unet_ch,); 0 channels = stage unused.
    * Precision follows flow_precise. */
   int unet_mel, unet_ch, unet_n_blocks, unet_n_mid, unet_heads, unet_ff_mult, unet_chunk;
+  /* unet_noncausal = 1: the non-causal multi-level ConditionalDecoder (cosyvoice/flow/decoder.py:88-291) with unet_levels equal-width
+   * levels (channels == (unet_ch,) * unet_levels: stride-2 Conv1d down / ConvTranspose1d(4,2,1) up between levels) and
+   * GroupNorm(unet_groups) blocks; 0: the causal single-level variant above. */
+  int unet_noncausal, unet_levels, unet_groups;
 } hvx_config;
 
 /* Sampler parameters bound per request by server/worker.py:57-65 (ras_sampling keywords,
@@ -161,6 +165,12 @@ hvx_status hvx_dit_estimator(hvx_engine* e, const float* x_dev, const float* mu_
 hvx_status hvx_unet_estimator(hvx_engine* e, const float* x_dev, const float* mu_dev, const float* t_dev,
                               const float* spks_dev, const float* cond_dev, int T, int streaming,
                               float* out_dev, void* stream);
+/* The same seam for the non-causal multi-level ConditionalDecoder with its padding mask (cosyvoice/flow/decoder.py:210-291,
+ * forward(x, mask, mu, t, spks, cond)): mask_dev (2, 1, T) fp32 0/1, every row a prefix mask as make_pad_mask builds them, or NULL =
+ * all true (what solve_euler passes, flow_matching.py:104).  dump_dev / n_dump as in hvx_unet_estimator_debug (NULL / 0: off). */
+hvx_status hvx_unet_estimator_masked(hvx_engine* e, const float* x_dev, const float* mask_dev, const float* mu_dev, const float* t_dev,
+                                     const float* spks_dev, const float* cond_dev, int T, float* out_dev, float* dump_dev, int n_dump,
+                                     void* stream);
 /* same, and copies the fp32 residual stream (2T, unet_ch) after every resnet / transformer block into dump_dev (parity tests) */
 hvx_status hvx_unet_estimator_debug(hvx_engine* e, const float* x_dev, const float* mu_dev, const float* t_dev,
                                     const float* spks_dev, const float* cond_dev, int T, int streaming,
@@ -234,6 +244,11 @@ hvx_status hvx_synthesize_host(hvx_engine* e, const hvx_request* reqs, int n_req
 /* speed control: replaces F.interpolate(tts_mel, size=int(T/speed), mode='linear')
  * (infer_speech_model.py:584-587,662-665).  mel_dev (C, T) -> out_dev (C, T_out). */
 hvx_status hvx_speed_interp(hvx_engine* e, const float* mel_dev, int C, int T, int T_out, float* out_dev, void* stream);
+
+/* streaming overlap: replaces fade_in_out (cosyvoice/utils/common.py:169-177; called by CosyVoice2Model.token2wav,
+ * cosyvoice/cli/model.py:295-308).  wav_dev[0:overlap) = wav_dev * window[0:overlap) + prev_tail_dev[0:overlap) * window[overlap:2*overlap),
+ * evaluated in double like the reference's float32-tensor x float64-window product.  window_dev: 2*overlap doubles (np.hamming). */
+hvx_status hvx_fade_in_out(hvx_engine* e, float* wav_dev, const float* prev_tail_dev, const double* window_dev, int overlap, void* stream);
 
 /* ---- diagnostic entries for the kernel-level parity tests (tests/test_gemm_gpu.py) ----
  * C = act(A*B^T + bias): A (M,K) bf16, B (N,K) bf16 (nn.Linear weight layout), C bf16 or fp32.  out_f32 bit 0: fp32 output,

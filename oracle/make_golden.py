@@ -264,6 +264,34 @@ def golden_unet_nc(name, dims, T, seed):
     torch.save(dict(dims=name, seed=seed, T=T, sd_checksum=checksum(sd), **out), os.path.join(OUT, f"unet_nc_{name}.pt"))
 
 
+def golden_unet_nc_cfm(name, dims, T, n_steps, seed):
+    """ConditionalCFM.forward (flow_matching.py:36-69) over the non-causal estimator: two chained calls, the second one fed the
+    first one's cache (prompt + 34-frame overlap of z and mu).  z is the reference's own torch.randn_like draw under a pinned seed."""
+    cfm = refshim.build_unet_nc_cfm(dims)
+    sd = synth.unet_nc_state_dict(dims, seed)
+    cfm.estimator.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(seed + 900)
+    P = T // 3
+    out, cache, cache_o = {}, torch.zeros(1, dims.mel, 0, 2), None
+    for call in range(2):
+        mu = torch.randn(1, dims.mel, T, generator=g)
+        cond = torch.zeros(1, dims.mel, T)
+        cond[:, :, :P] = torch.rand(1, dims.mel, P, generator=g) * 6.0 - 6.0
+        spks = torch.randn(1, dims.mel, generator=g)
+        torch.manual_seed(seed + 910 + call)
+        z = torch.randn_like(mu)
+        torch.manual_seed(seed + 910 + call)
+        cache_in = cache.clone()
+        mel, cache = cfm(mu.clone(), torch.ones(1, 1, T), n_steps, temperature=1.0, spks=spks, cond=cond, prompt_len=P, cache=cache)
+        mel_o, cache_o = unet_ref.cfm_forward_nc(sd, mu, z, spks, cond, n_steps, dims, prompt_len=P, cache=cache_in)
+        e = (mel - mel_o).abs().max().item()
+        print(f"[unet_nc_cfm:{name}] call {call} T={T} steps={n_steps}: ref-vs-oracle mel max-abs {e:.2e}, cache equal {torch.equal(cache, cache_o)}")
+        assert e < 5e-4 and torch.equal(cache, cache_o)
+        out[f"call{call}"] = dict(mu=mu, cond=cond, spks=spks, z=z, cache_in=cache_in, mel=mel, cache=cache)
+    torch.save(dict(dims=name, seed=seed, T=T, n_steps=n_steps, prompt_len=P, sd_checksum=checksum(sd), **out),
+               os.path.join(OUT, f"unet_nc_cfm_{name}.pt"))
+
+
 def golden_unet_cfm(name, dims, T, n_steps, seed):
     """the whole Euler solve over the U-Net estimator: CausalConditionalCFM.forward (flow_matching.py:203-228)"""
     cfm = refshim.build_unet_cfm(dims)
@@ -446,6 +474,7 @@ def main():
         with torch.no_grad():
             golden_unet_nc("tiny", D.UNET_NC_TINY, 38, 0)
             golden_unet_nc("full", D.UNET_NC_FULL, 130, 0)
+            golden_unet_nc_cfm("small", D.UNET_NC_SMALL, 75, 6, 0)
         return
     if sys.argv[1:] == ["unet"]:
         with torch.no_grad():
@@ -477,6 +506,7 @@ def main():
         golden_unet_cfm("full", D.UNET_FULL, 96, 5, 0)
         golden_unet_nc("tiny", D.UNET_NC_TINY, 38, 0)
         golden_unet_nc("full", D.UNET_NC_FULL, 130, 0)
+        golden_unet_nc_cfm("small", D.UNET_NC_SMALL, 75, 6, 0)
         golden_frontend(0)
         golden_flow("tiny", D.FLOW_TINY, 21, 10, 10, 0)
         golden_flow("full", D.FLOW_FULL, 24, 8, 4, 0)

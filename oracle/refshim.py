@@ -304,6 +304,17 @@ def build_unet_nc(cfg):
     return m.eval()
 
 
+def build_unet_nc_cfm(cfg):
+    """The non-causal ConditionalCFM (flow_matching.py:22-69) over the reference ConditionalDecoder, cfm_params as the CosyVoice yaml."""
+    install()
+    from cosyvoice.flow.flow_matching import ConditionalCFM
+    return ConditionalCFM(
+        in_channels=3 * cfg.mel, n_spks=1, spk_emb_dim=cfg.mel,
+        cfm_params=_AttrDict(sigma_min=1e-6, solver="euler", t_scheduler="cosine", training_cfg_rate=0.2,
+                             inference_cfg_rate=0.7, reg_loss_type="l1"),
+        estimator=build_unet_nc(cfg)).eval()
+
+
 def build_unet_cfm(cfg):
     """CausalConditionalCFM (flow_matching.py:197-228) over the reference U-Net estimator, cfm_params as the CosyVoice2 yaml."""
     install()

@@ -177,3 +177,32 @@ def estimator_nc(sd: Dict[str, torch.Tensor], x, mask, mu, t, spks, cond, dims):
             h = F.conv_transpose1d(h * m, sd[f"up_blocks.{i}.2.conv.weight"], sd[f"up_blocks.{i}.2.conv.bias"], stride=2, padding=1)
     h = _block_nc(sd, "final_block", h, m, G)
     return F.conv1d(h * m, sd["final_proj.weight"], sd["final_proj.bias"]) * mask
+
+
+def cfm_forward_nc(sd, mu, z, spks, cond, n_timesteps, dims, cfg_rate=0.7, prompt_len=0, cache=None):
+    """ConditionalCFM.forward + solve_euler (cosyvoice/flow/flow_matching.py:36-69,71-124) over estimator_nc.  z = the
+    `torch.randn_like(mu) * temperature` draw of :52 (passed in: RNG pinned); cache (1, mel, n, 2) overwrites the head of z and mu
+    (:53-57) and the new cache = [prompt | last 34 frames] of both (:58-60).  Returns (mel (1, mel, T), cache)."""
+    mu, z = mu.float().clone(), z.float().clone()
+    if cache is not None and cache.shape[2] != 0:
+        cs = cache.shape[2]
+        z[:, :, :cs] = cache[:, :, :, 0]
+        mu[:, :, :cs] = cache[:, :, :, 1]
+    new_cache = torch.stack([torch.cat([z[:, :, :prompt_len], z[:, :, -34:]], dim=2),
+                             torch.cat([mu[:, :, :prompt_len], mu[:, :, -34:]], dim=2)], dim=-1)
+    T = mu.shape[2]
+    x = z
+    t_span = torch.linspace(0, 1, n_timesteps + 1)
+    t_span = 1 - torch.cos(t_span * 0.5 * torch.pi)
+    t, dt = t_span[0].unsqueeze(0), t_span[1] - t_span[0]
+    mask = torch.ones(2, 1, T)
+    zeros = torch.zeros_like(mu)
+    for step in range(1, n_timesteps + 1):
+        d = estimator_nc(sd, torch.cat([x, x]), mask, torch.cat([mu, zeros]), torch.cat([t, t]),
+                         torch.cat([spks, torch.zeros_like(spks)]), torch.cat([cond, zeros]), dims)
+        d = (1.0 + cfg_rate) * d[:1] - cfg_rate * d[1:]
+        x = x + dt * d
+        t = t + dt
+        if step < n_timesteps:
+            dt = t_span[step + 1] - t
+    return x, new_cache

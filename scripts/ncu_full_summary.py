@@ -5,7 +5,12 @@ WANT = [("gpu__time_duration.sum", "time_us"), ("dram__bytes_read.sum", "dram_rd
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_%"), ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2_%"),
         ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_%"),
         ("sm__inst_executed_pipe_tensor.sum", "tensor_inst"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_%"),
-        ("launch__registers_per_thread", "regs"), ("launch__shared_mem_per_block_dynamic", "dyn_smem")]
+        ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_%"), ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1_%"),
+        ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu_%"), ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma_%"),
+        ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu_%"), ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu_%"),
+        ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_%"),
+        ("launch__registers_per_thread", "regs"), ("launch__shared_mem_per_block_dynamic", "dyn_smem"),
+        ("launch__occupancy_limit_shared_mem", "occ_lim_smem"), ("launch__waves_per_multiprocessor", "waves")]
 
 
 def main(paths):

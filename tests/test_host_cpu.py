@@ -105,3 +105,23 @@ def test_stitching_and_wav_encoding():
     assert torch.equal(torch.from_numpy(data.copy()).reshape(1, -1), out)
     with pytest.raises(ValueError):
         output.stitch_segments([], 24000)
+
+
+def test_stream_oracle_fade_in_out_matches_reference_function():
+    """oracle/stream_ref.fade_in_out == cosyvoice/utils/common.py:169-177 (run when /root/reference is present), and the blend is
+    evaluated in float64 (float32 tensor x float64 numpy window)"""
+    import os
+    import numpy as np
+    import torch
+    from oracle import stream_ref
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.randn(1, 9000, generator=g), torch.randn(1, 3840, generator=g)
+    w = np.hamming(2 * 3840)
+    out = stream_ref.fade_in_out(a, b, w)
+    want = (a[:, :3840].double() * torch.from_numpy(w[:3840]) + b.double() * torch.from_numpy(w[3840:])).float()
+    assert torch.equal(out[:, :3840], want) and torch.equal(out[:, 3840:], a[:, 3840:])
+    if os.path.isdir("/root/reference"):
+        from oracle import refshim
+        refshim.install()
+        from cosyvoice.utils.common import fade_in_out as ref_fade
+        assert torch.equal(ref_fade(a.clone(), b, w), out)

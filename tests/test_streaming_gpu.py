@@ -73,3 +73,41 @@ def test_abandoned_stream_does_not_leak_into_next_request(mm):
     wav = torch.cat([c["tts_speech"] for c in s.tts(r2, head_k=2, sampling=sp, n_timesteps=2, min_ratio=8, max_ratio=8, u=u, debug=dbg)], 1)
     assert dbg["tokens"] == ref["tokens"] and len(dbg["tokens"]) == 96
     assert torch.isfinite(wav).all()
+
+
+def test_streaming_cv2_fade_in_out_matches_reference_orchestration(mm):
+    """CosyVoice2Model.token2wav (cli/model.py:279-313): 8-frame mel cache, source continuation, fade_in_out cross-fade and the
+    3840-sample hold-back.  The streamed chunks must equal the restated orchestration (oracle/stream_ref.py) driven over the same
+    per-call mel slices with the same vocoder and the same pinned source noise; hvx_fade_in_out is bit-exact vs the reference blend."""
+    from flowmirror_hydravox_b200 import _lib as L
+    from flowmirror_hydravox_b200.hift import NativeHiFTTransposed
+    from flowmirror_hydravox_b200.streaming import StreamingSynthesizerCV2
+    from oracle import stream_ref
+    hd = D.HIFT_TINY
+    e = L.Engine(hd=hd)
+    try:
+        ht = NativeHiFTTransposed(e)
+        ht.load_state_dict(synth.hift_t_state_dict(hd, 0))
+        noise_all = torch.randn(400 * hd.frame_samples, hd.harmonics, generator=torch.Generator().manual_seed(11)).cuda()
+        noise_fn = lambda n: noise_all[:n]
+        r = synth.utterance(D.LLM_TINY, D.FLOW_TINY, 12, seed=1986, prompt_tokens=7, prompt_text=3)
+        u = torch.rand(1, 2048, generator=torch.Generator().manual_seed(2))
+        sp = dict(top_p=0.9, top_k=10, win_size=24, tau_r=0.2)
+        dbg = {}
+        s = StreamingSynthesizerCV2(mm, ht, noise_fn=noise_fn)
+        chunks = [c["tts_speech"] for c in s.tts(r, head_k=2, sampling=sp, n_timesteps=4, min_ratio=8, max_ratio=8, u=u, debug=dbg)]
+        assert len(dbg["tokens"]) == 96 and len(chunks) == len(dbg["mel"]) >= 3
+        frame, ov = hd.frame_samples, 8 * hd.frame_samples
+        # every non-final chunk holds `ov` samples back, the final one releases them: the total is the whole utterance
+        assert sum(c.shape[1] for c in chunks) == 2 * 96 * frame
+        assert chunks[0].shape[1] == dbg["mel"][0].shape[2] * frame - ov
+
+        def vocoder(mel, cache_source):
+            w, src = ht.inference(mel, cache_source=cache_source, noise=noise_fn(mel.shape[2] * frame))
+            return w.cpu(), src.cpu()
+        ref = stream_ref.token2wav_cv2(vocoder, dbg["mel"], mel_cache_len=8, frame_samples=frame)
+        for i, (a, b) in enumerate(zip(chunks, ref)):
+            assert a.shape == b.shape, (i, a.shape, b.shape)
+            assert torch.equal(a, b), (i, (a - b).abs().max().item())
+    finally:
+        e.close()
