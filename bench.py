@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--mode", default="parity", choices=["parity", "serving"])
     ap.add_argument("--batch", type=int, default=0, help="override utterances per GPU")
     ap.add_argument("--head-k", type=int, default=0, help="override inference_head_num")
+    ap.add_argument("--n-text", type=int, default=0, help="override the text length of every utterance (profiling runs: short utterances)")
     ap.add_argument("--cfm-steps", type=int, default=25)
     ap.add_argument("--e2e-steps", type=int, default=3, help="timed steps of the end-to-end leg (<= --steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -70,6 +71,8 @@ def parse():
 
 def wl(a):
     b, rng, k, cfg = WORKLOADS[a.workload]
+    if getattr(a, "n_text", 0):
+        rng, cfg = (a.n_text, a.n_text), cfg + f" with n_text overridden to {a.n_text}"
     return (a.batch or b), rng, (a.head_k or k), cfg
 
 

@@ -109,6 +109,7 @@ struct hvx_engine {
   void* samp_arrive = nullptr;
   int64_t graph_launches = 0;      // kernels inside the captured decode-step graph
   int sm_count = 148;
+  int sm_reserve = 0;              // SMs the persistent GEMM grids leave free (hvx_synthesize_host: room for the decode stream's kernels)
   const hvx::Tensor* find(int stage, const std::string& name) const {
     auto it = tensors[stage].find(name);
     return it == tensors[stage].end() ? nullptr : &it->second;

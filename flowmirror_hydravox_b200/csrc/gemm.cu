@@ -630,7 +630,7 @@ static hvx_status launch_gemm_persist_t(hvx_engine* e, cudaStream_t st, const CU
     attr_set = true;
   }
   const int tiles_m = cdiv(M, BM), tiles_n = cdiv(N, PBN);
-  const int grid = std::min(tiles_m * tiles_n, e->sm_count);
+  const int grid = std::min(tiles_m * tiles_n, std::max(2, e->sm_count - e->sm_reserve));
   gemm_persist_kernel<MODE, ACT, TRI><<<grid, PERSIST_THREADS, S::TOTAL, st>>>(ta, tb, M, N, K, epi, ad, tiles_m, tiles_n);
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
@@ -804,7 +804,7 @@ static hvx_status launch_gemm_pair_t(hvx_engine* e, cudaStream_t st, const CUten
     attr_set = true;
   }
   const int tiles_m = cdiv(M, 256), tiles_n = cdiv(N, PBN);
-  const int n_pairs = std::max(1, std::min(tiles_m * tiles_n, e->sm_count / 2));
+  const int n_pairs = std::max(1, std::min(tiles_m * tiles_n, std::max(2, e->sm_count - e->sm_reserve) / 2));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * n_pairs); cfg.blockDim = dim3(PERSIST_THREADS); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = st;

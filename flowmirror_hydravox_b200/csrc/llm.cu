@@ -1570,7 +1570,12 @@ hvx_status llm_finalize(hvx_engine* e) {
     HVX_CUDA(cudaMemset(L->fused_bar, 0, sizeof(unsigned long long)));
     HVX_CUDA(cudaMalloc(&L->fused_abort, sizeof(int)));
     HVX_CUDA(cudaMemset(L->fused_abort, 0, sizeof(int)));
-    HVX_CUDA(cudaStreamCreateWithFlags(&L->own, cudaStreamNonBlocking));
+    // the decode stream gets the highest priority: its small latency-bound kernels take the SMs that free up first when a
+    // flow / vocoder group of finished utterances runs beside it (hvx_synthesize_host); HVX_LLM_STREAM_PRIO=0 turns that off
+    { int lo_p = 0, hi_p = 0;
+      HVX_CUDA(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+      const bool prio = !(getenv("HVX_LLM_STREAM_PRIO") && atoi(getenv("HVX_LLM_STREAM_PRIO")) == 0);
+      HVX_CUDA(cudaStreamCreateWithPriority(&L->own, cudaStreamNonBlocking, prio ? hi_p : lo_p)); }
     HVX_CUDA(cudaEventCreateWithFlags(&L->ev_in, cudaEventDisableTiming));
     HVX_CUDA(cudaEventCreateWithFlags(&L->ev_out, cudaEventDisableTiming));
   }

@@ -5,6 +5,11 @@
 #include "common.cuh"
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <memory>
 #include <cstdlib>
 #include <vector>
 
@@ -78,7 +83,8 @@ extern "C" hvx_status hvx_synthesize_host(hvx_engine* e, const hvx_request* reqs
                                           float* wav_host, int wav_stride, int32_t* wav_len_host, int32_t* tokens_host, int tok_stride,
                                           int32_t* n_tokens_host, float* stage_ms_host, void* stream) {
   HVX_CHECK(e && e->llm && e->flow && e->hift, HVX_ERR_STATE, "synthesize: all three stages must be finalized");
-  HVX_LOCK(e, HVX_STAGE_LLM); HVX_LOCK(e, HVX_STAGE_FLOW); HVX_LOCK(e, HVX_STAGE_HIFT);
+  // the calling thread drives the decode (LLM lock); the worker thread below owns the flow and the vocoder for the call
+  HVX_LOCK(e, HVX_STAGE_LLM);
   HVX_CHECK(reqs && sp && noise_dev && sine_table_dev && wav_host && wav_len_host, HVX_ERR_ARG, "synthesize: null argument");
   HVX_CHECK(n_req >= 1 && n_req <= e->cfg.llm_max_seqs, HVX_ERR_ARG, "synthesize: n_req=%d exceeds max_seqs=%d", n_req, e->cfg.llm_max_seqs);
   const hvx_config& c = e->cfg;
@@ -213,7 +219,6 @@ extern "C" hvx_status hvx_synthesize_host(hvx_engine* e, const hvx_request* reqs
       wav_len_host[i] = T_sp * frame;
     }
     HVX_CUDA(cudaEventRecord(ev_c, st));
-    for (int i : members) enqueued[i] = 1;
     n_groups++;
     return HVX_OK;
   };
@@ -234,20 +239,52 @@ extern "C" hvx_status hvx_synthesize_host(hvx_engine* e, const hvx_request* reqs
     }
     return groups;
   };
-  // ---- stage 1: multi-head AR decode of all requests together on the decode stream.  HVX_PIPE_OVERLAP (default on): whenever the
+  // ---- stage 1: multi-head AR decode of all requests together on the decode stream.  HVX_PIPE_OVERLAP=1: whenever the
   // decode loop reports finished sequences that fill a group (>= HVX_PIPE_MIN_FRAMES padded frames or 16 utterances), that group
   // starts its flow + vocoder on the caller's stream — the latency-bound decode of the long utterances and the
   // throughput-bound flow of the short ones share the GPU.  (The reference is stage-serial per request,
   // infer_speech_model.py:549-592; results do not depend on the schedule.)
-  static const bool overlap = !(getenv("HVX_PIPE_OVERLAP") && atoi(getenv("HVX_PIPE_OVERLAP")) == 0);
+  // Measured on the batch-32 mixed-length workload (profiles/r2_pipe_overlap.txt): no gain — 21.75 s stage-serial vs 21.8 s
+  // overlapped.  The decode step's ~250 small kernels (PDL keeps the next one resident while the current one runs) fragment the
+  // SMs so that the flow's 198 KB one-CTA-per-SM persistent GEMMs barely advance while the decode is alive, with or without stream
+  // priorities or reserved SMs.  Kept opt-in (HVX_PIPE_OVERLAP=1); results are bit-identical either way.
+  static const bool overlap = getenv("HVX_PIPE_OVERLAP") && atoi(getenv("HVX_PIPE_OVERLAP")) != 0;
   static const int min_frames = getenv("HVX_PIPE_MIN_FRAMES") ? atoi(getenv("HVX_PIPE_MIN_FRAMES")) : 4096;
-  struct ProgCtx { decltype(enqueue_group)* enq; decltype(partition)* part; decltype(frames)* frames_of; std::vector<int32_t>* cnt;
-                   std::vector<char>* fin; bool overlap; long long min_frames; };
-  ProgCtx pctx{&enqueue_group, &partition, &frames, &cnt, &finished, overlap, min_frames};
+  // Groups are enqueued by a worker thread: one group is ~5000 kernel launches, far more than the driver's launch queue holds,
+  // so the enqueueing thread blocks until the GPU has consumed most of them — the decode loop must not be that thread
+  // (measured: with a single thread the decode advanced 16 steps per flow group and took as long as the whole flow).
+  struct GroupQueue {
+    std::mutex mu; std::condition_variable cv; std::deque<std::vector<int>> q; bool closed = false; hvx_status rc = HVX_OK;
+  } gq;
+  int dev_id = 0;
+  HVX_CUDA(cudaGetDevice(&dev_id));
+  std::thread worker([&]() {
+    cudaSetDevice(dev_id);
+    std::lock_guard<std::recursive_mutex> lf(e->mu[HVX_STAGE_FLOW]), lh(e->mu[HVX_STAGE_HIFT]);
+    for (;;) {
+      std::vector<int> g;
+      { std::unique_lock<std::mutex> lk(gq.mu);
+        gq.cv.wait(lk, [&] { return gq.closed || !gq.q.empty(); });
+        if (gq.q.empty()) return;
+        g = std::move(gq.q.front()); gq.q.pop_front(); }
+      const hvx_status r = gq.rc ? gq.rc : enqueue_group(g);
+      if (r) { std::lock_guard<std::mutex> lk(gq.mu); if (!gq.rc) gq.rc = r; }
+    }
+  });
+  auto push_group = [&](const std::vector<int>& g) {
+    for (int i : g) enqueued[i] = 1;                                  // claimed: the next partition() skips them
+    { std::lock_guard<std::mutex> lk(gq.mu); gq.q.push_back(g); }
+    gq.cv.notify_one();
+  };
+  struct Joiner { GroupQueue& q; std::thread& t; ~Joiner() { { std::lock_guard<std::mutex> lk(q.mu); q.closed = true; } q.cv.notify_all(); if (t.joinable()) t.join(); } } joiner{gq, worker};
+  struct ProgCtx { decltype(push_group)* push; decltype(partition)* part; decltype(frames)* frames_of; std::vector<int32_t>* cnt;
+                   std::vector<char>* fin; bool overlap; long long min_frames; GroupQueue* gq; };
+  ProgCtx pctx{&push_group, &partition, &frames, &cnt, &finished, overlap, min_frames, &gq};
   auto progress = [](void* vctx, int n, const int* done, const int* n_out) -> hvx_status {
     ProgCtx* x = (ProgCtx*)vctx;
     for (int i = 0; i < n; i++)
       if (done[i] && !(*x->fin)[i]) { (*x->fin)[i] = 1; (*x->cnt)[i] = n_out[i]; }
+    { std::lock_guard<std::mutex> lk(x->gq->mu); if (x->gq->rc) return x->gq->rc; }      // a group failed: stop decoding
     if (!x->overlap) return HVX_OK;
     // The schedule depends only on the decode's own progress (which sequences have stopped after how many steps), never on how far
     // the caller's stream has got, so the grouping — and with it every output bit — is reproducible from run to run.
@@ -255,15 +292,21 @@ extern "C" hvx_status hvx_synthesize_host(hvx_engine* e, const hvx_request* reqs
       long long fr = 0;
       for (int i : g) fr += (*x->frames_of)(i);
       if (fr < x->min_frames && g.size() < 16) continue;            // wait for more finished utterances to fill this group
-      const hvx_status rc3 = (*x->enq)(g);
-      if (rc3) return rc3;
+      (*x->push)(g);
     }
     return HVX_OK;
   };
+  // while the decode runs beside the flow, the persistent GEMM grids leave a few SMs free: the decode step is a chain of ~250
+  // small kernels, and a kernel that has to wait for a 148-CTA persistent grid to drain costs 50-100 us each (measured: 20 ms
+  // per decode step instead of 3.7); on reserved SMs it starts at once.  Grids are fixed at enqueue time.
+  static const int reserve_sms = getenv("HVX_PIPE_RESERVE_SMS") ? atoi(getenv("HVX_PIPE_RESERVE_SMS")) : 12;
+  struct Reserve { hvx_engine* e; Reserve(hvx_engine* x, int n) : e(x) { e->sm_reserve = n; } ~Reserve() { e->sm_reserve = 0; } };
+  std::unique_ptr<Reserve> reserve(overlap && n_req > 1 ? new Reserve(e, reserve_sms) : nullptr);
   const auto t_llm0 = std::chrono::steady_clock::now();
   if ((rc = llm_generate_progress(e, n_req, head_k, sp, (const float*)(din + o_u), u_stride, tok_dev, max_out, cnt_dev, stream,
                                   +progress, &pctx))) return rc;
   const float ms_llm = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_llm0).count();
+  reserve.reset();                                  // the decode has drained: the remaining groups get every SM
   if (tokens_host)
     for (int i = 0; i < n_req; i++)
       HVX_CUDA(cudaMemcpyAsync(tokens_host + (size_t)i * tok_stride, tok_dev + (size_t)i * max_out, sizeof(int32_t) * of[i].max_out,
@@ -273,8 +316,11 @@ extern "C" hvx_status hvx_synthesize_host(hvx_engine* e, const hvx_request* reqs
     if (n_tokens_host) n_tokens_host[i] = cnt[i];
     if (cnt[i] <= 0) wav_len_host[i] = 0;
   }
-  for (const std::vector<int>& g : partition())
-    if ((rc = enqueue_group(g))) return rc;
+  for (const std::vector<int>& g : partition()) push_group(g);
+  { std::lock_guard<std::mutex> lk(gq.mu); gq.closed = true; }
+  gq.cv.notify_all();
+  worker.join();
+  if (gq.rc) return gq.rc;
   HVX_CUDA(cudaStreamSynchronize(st));
   float ms_flow = 0.f, ms_hift = 0.f;
   for (size_t g = 0; g < n_groups; g++) {
