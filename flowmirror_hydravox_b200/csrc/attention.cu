@@ -38,9 +38,10 @@ dit_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * 128;
   const int h = blockIdx.y, b = blockIdx.z;
-  const int T = a.T;
-  const int Tk = a.klen ? a.klen[b] : T;     // keys of this batch row that exist (ragged group: the rest of the slab is padding)
-  const int klim_tile = a.chunk > 0 ? min(Tk, ((min(q0 + 127, T - 1)) / a.chunk + 1) * a.chunk) : Tk;
+  const int T = a.T;                                   // key rows per batch row
+  const int Tq = a.Tq > 0 ? a.Tq : T;                  // query rows per batch row (windowed call: Tq < T, queries are frames q_pos0 ..)
+  const int Tk = a.klen ? a.klen[b] : (a.tk > 0 ? a.tk : T);     // keys of this batch row that exist (ragged group: the rest of the slab is padding)
+  const int klim_tile = a.chunk > 0 ? min(Tk, ((a.q_pos0 + min(q0 + 127, Tq - 1)) / a.chunk + 1) * a.chunk) : Tk;
   const int nkv = (klim_tile + 63) / 64;
 
   if (tid == 0) {
@@ -79,7 +80,7 @@ dit_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         tc::umma_commit(&s_full[j & 1]);
       };
       tc::mbar_expect_tx(q_full, A3_Q_BYTES);
-      tc::tma_load_2d(smem + A3_OFF_Q, &tm_q, q_full, h * 64, b * T + q0);
+      tc::tma_load_2d(smem + A3_OFF_Q, &tm_q, q_full, h * 64, b * Tq + q0);
       for (int j = 0; j < min(nkv, A3_STAGES); j++) load_kv(j);
       tc::mbar_wait(q_full, 0);
       issue_qk(0);
@@ -104,7 +105,7 @@ dit_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   } else {
     // ---------------- softmax warps: thread == query row == TMEM lane
     const int row_in_batch = q0 + tid;
-    const int klim_row = a.chunk > 0 ? min(Tk, (row_in_batch / a.chunk + 1) * a.chunk) : Tk;
+    const int klim_row = a.chunk > 0 ? min(Tk, ((a.q_pos0 + row_in_batch) / a.chunk + 1) * a.chunk) : Tk;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const float sc = 0.125f * 1.4426950408889634f;     // dim_head^-0.5 * log2(e)
     float m_run = -INFINITY, l_run = 0.f;
@@ -183,11 +184,11 @@ dit_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     tc::tmem_ld_32x32(tmem_o + lane_off, v);
     tc::tmem_ld_32x32(tmem_o + lane_off + 32, v + 32);
     tc::tmem_ld_wait();
-    if (row_in_batch < T && a.lo_off) {
+    if (row_in_batch < Tq && a.lo_off) {
       // split precision (flow parity mode): hi at [col], lo = y - hi at [lo_off + col]; 16-byte stores like the plain path
       // (element-wise 2-byte stores made this epilogue as long as the whole key loop: 249 vs 479 TFLOP/s)
       const float inv = 1.0f / l_run;
-      uint16_t* o = reinterpret_cast<uint16_t*>(a.out) + (size_t)(b * T + row_in_batch) * (2 * a.ld_out) + h * 64;
+      uint16_t* o = reinterpret_cast<uint16_t*>(a.out) + (size_t)(b * Tq + row_in_batch) * (2 * a.ld_out) + h * 64;
 #pragma unroll
       for (int i = 0; i < 64; i += 8) {
         float y[8];
@@ -205,9 +206,9 @@ dit_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         *reinterpret_cast<uint4*>(o + i) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(o + a.lo_off + i) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
-    } else if (row_in_batch < T) {
+    } else if (row_in_batch < Tq) {
       const float inv = 1.0f / l_run;
-      __nv_bfloat16* o = a.out + (size_t)(b * T + row_in_batch) * a.ld_out + h * 64;
+      __nv_bfloat16* o = a.out + (size_t)(b * Tq + row_in_batch) * a.ld_out + h * 64;
 #pragma unroll
       for (int i = 0; i < 64; i += 8) {
         uint4 pk;
@@ -228,8 +229,15 @@ hvx_status dit_attention(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* qk
                          const __nv_bfloat16* vt, int vt_ld, const AttnArgs& a) {
   CUtensorMap tq, tk64, tv;
   const uint64_t rows = (uint64_t)a.n_batch * a.T;
-  HVX_CHECK(make_tmap_bf16_2d(&tq, qk, rows, ld_qk, ld_qk, 128, 64), HVX_ERR_CUDA, "attention: tensor map Q failed");
-  HVX_CHECK(make_tmap_bf16_2d(&tk64, qk, rows, ld_qk, ld_qk, 64, 64), HVX_ERR_CUDA, "attention: tensor map K failed");
+  const int Tq = a.Tq > 0 ? a.Tq : a.T;
+  HVX_CHECK(a.q_pos0 >= 0 && a.q_pos0 + Tq <= a.T, HVX_ERR_ARG, "attention: query window [%d, %d) outside the %d key rows", a.q_pos0, a.q_pos0 + Tq, a.T);
+  HVX_CHECK(make_tmap_bf16_2d(&tq, qk, (uint64_t)a.n_batch * Tq, ld_qk, ld_qk, 128, 64), HVX_ERR_CUDA, "attention: tensor map Q failed");
+  if (a.k_ptr) {                                       // windowed call: keys live in their own (cache) matrix
+    k_col0 = 0;
+    HVX_CHECK(make_tmap_bf16_2d(&tk64, a.k_ptr, rows, a.ld_k, a.ld_k, 64, 64), HVX_ERR_CUDA, "attention: tensor map K failed");
+  } else {
+    HVX_CHECK(make_tmap_bf16_2d(&tk64, qk, rows, ld_qk, ld_qk, 64, 64), HVX_ERR_CUDA, "attention: tensor map K failed");
+  }
   HVX_CHECK(make_tmap_bf16_2d(&tv, vt, (uint64_t)a.n_batch * a.heads * 64, vt_ld, vt_ld, 64, 64), HVX_ERR_CUDA,
             "attention: tensor map V^T failed");
   static bool attr_set = false;
@@ -237,7 +245,7 @@ hvx_status dit_attention(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* qk
     HVX_CUDA(cudaFuncSetAttribute(dit_attention_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A5_SMEM));
     attr_set = true;
   }
-  dim3 grid(cdiv(a.T, 128), a.heads, a.n_batch);
+  dim3 grid(cdiv(Tq, 128), a.heads, a.n_batch);
   ProfScope prof_scope(&e->prof, st, PROF_ATTN, a.work > 0 ? a.work : 4.0 * a.n_batch * a.heads * (double)a.T * a.T * 64.0 * (a.chunk > 0 ? 0.5 : 1.0));
   dit_attention_v5_kernel<<<grid, 160, A5_SMEM, st>>>(tq, tk64, tv, k_col0, a);
   HVX_LAUNCH_CHECK(e);

@@ -24,6 +24,10 @@ struct AttnArgs {
   int ld_out;       // = heads*64 (row stride is 2*ld_out when lo_off > 0)
   const int* klen = nullptr;   // [n_batch] valid keys per batch row (device; ragged groups, v5 kernel only); nullptr: T
   double work = 0;  // FLOP of this call for the live profiler (0: 4 * n_batch * heads * T^2 * 64, halved under the chunk mask)
+  // windowed call (incremental streaming flow): Tq query rows per batch row — frames q_pos0 .. q_pos0 + Tq of the sequence, read
+  // from `qk` (Tq rows per batch) — against the first tk of T key rows per batch row held in k_ptr (ld_k wide) / vt
+  int Tq = 0, q_pos0 = 0, tk = 0;
+  const __nv_bfloat16* k_ptr = nullptr; int ld_k = 0;
   int lo_off = 0;   // > 0: output written as split precision, hi at [col], lo at [lo_off + col] (flow parity mode, v5 kernel)
   __nv_bfloat16* out;   // [n_batch*T][heads*64]
 };

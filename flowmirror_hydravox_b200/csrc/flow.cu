@@ -274,6 +274,19 @@ struct FlowState {
   // solve-level buffers (ws_small)
   float *spks, *e32, *mu_tok, *mu, *cond, *x, *mod, *t_dev;
   __half *e16, *y1p, *st16;
+  // incremental streaming session (hvx_flow_stream_*): per Euler step s and layer l the keys (rotary applied) and V^T of every
+  // frame evaluated so far, per step the two operands of the causal position-embedding convolutions (their 30-frame left context)
+  struct Stream {
+    bool open = false;
+    int S = 0, Tcap = 0, Tpcap = 0, T_done = 0;
+    DevBuf buf;
+    size_t step_bytes = 0, conv_bytes = 0, k_bytes = 0, v_bytes = 0;
+    float *rope_c = nullptr, *rope_s = nullptr;
+    __half* h0h(int s) const { return (__half*)((uint8_t*)buf.p + (size_t)s * step_bytes); }
+    __half* c1(int s) const { return (__half*)((uint8_t*)buf.p + (size_t)s * step_bytes + conv_bytes); }
+    __half* K(int s, int l) const { return (__half*)((uint8_t*)buf.p + (size_t)s * step_bytes + 2 * conv_bytes + (size_t)l * (k_bytes + v_bytes)); }
+    __half* Vt(int s, int l) const { return (__half*)((uint8_t*)K(s, l) + k_bytes); }
+  } stream;
 };
 
 template <typename T>
@@ -463,6 +476,82 @@ static hvx_status flow_nfe(hvx_engine* e, cudaStream_t st, const float* mod, int
   return HVX_OK;
 }
 
+// One estimator evaluation restricted to the frames [t0, t0 + Tw) of a streaming session at Euler step `step`: the same operator
+// sequence as flow_nfe on 2*Tw rows, with (a) the position-embedding convolutions reading their left context from the session's
+// per-step operand caches, (b) the QKV epilogue writing the new keys / V^T columns into the per-(step, layer) caches at their
+// absolute frames, (c) attention of the Tw window queries over all t0 + Tw cached keys under the block-causal chunk mask.  Under
+// that mask (and causal convolutions) the frames before t0 do not depend on the new ones, so their cached keys / values are
+// exactly what a full re-evaluation would recompute (cosyvoice/flow/DiT/dit.py:145-176 with streaming=True).
+static hvx_status flow_nfe_window(hvx_engine* e, cudaStream_t st, const float* mod, int step, int t0, int Tw) {
+  FlowState* f = e->flow;
+  FlowState::Stream& S = f->stream;
+  const hvx_config& c = e->cfg;
+  const int nb = 2, M = nb * Tw, dim = c.flow_dim, inner = c.flow_heads * 64, ff = dim * c.flow_ff_mult, mel = c.flow_mel;
+  const int px = f->precise ? 2 : 1, T1 = t0 + Tw;
+  hvx_status rc;
+  { GemmEpi p; p.mode = EPI_F32; p.f16 = 1; p.bias = f->in_b; p.out = f->h0; p.ldo = dim; p.out2 = (__nv_bfloat16*)f->h0h;
+    if (f->precise) { p.ldo2 = 2 * dim; p.lo_off = dim; }
+    if (f->precise) {
+      if ((rc = flow_linear(e, st, f->xin, f->in_w, M, dim, 4 * mel, p))) return rc;
+    } else {
+      GemmAddr gs; gs.b_kb_mod = (4 * mel) / 64;
+      if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->xin, 8 * mel, (const __nv_bfloat16*)f->in_w, 4 * mel, M, dim, 8 * mel, p, &gs))) return rc;
+    } }
+  // window rows of a [2][Tw][w] operand -> rows t0.. of the session's [2][Tcap][w] cache
+  auto to_cache = [&](const __half* local, __half* cache, int w) -> hvx_status {
+    for (int b = 0; b < nb; b++)
+      HVX_CUDA(cudaMemcpyAsync(cache + ((size_t)b * S.Tcap + t0) * w, local + (size_t)b * Tw * w, (size_t)Tw * w * sizeof(__half),
+                               cudaMemcpyDeviceToDevice, st));
+    return HVX_OK;
+  };
+  if ((rc = to_cache(f->h0h, S.h0h(step), px * dim))) return rc;
+  GemmAddr ga; ga.n_batch = nb; ga.rows_per_batch = Tw; ga.a_rows = S.Tcap; ga.a_cols = dim; ga.a_col_per_ntile = 64; ga.kb_per_tap = 1;
+  ga.a_row0 = t0 - (c.flow_pos_k - 1); ga.a_row_step = 1;
+  const int kpos = c.flow_pos_k * 64;
+  int kconv = kpos;
+  if (f->precise) { ga.a_cols = 2 * dim; ga.a_lo_off = dim; ga.split3_kb = c.flow_pos_k; kconv = 3 * kpos; }
+  { GemmEpi p = epi16(f->c1, px * dim, f->pos1_b, ACT_MISH);
+    p.lo_off = f->precise ? dim : 0;
+    if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)S.h0h(step), px * dim, (const __nv_bfloat16*)f->pos1_w, px * kpos, M, dim, kconv, p, &ga))) return rc; }
+  if ((rc = to_cache(f->c1, S.c1(step), px * dim))) return rc;
+  { GemmEpi p; p.mode = EPI_F32; p.f16 = 1; p.act = ACT_MISH; p.bias = f->pos2_b; p.out = f->h; p.ldo = dim; p.resid = f->h0;
+    if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)S.c1(step), px * dim, (const __nv_bfloat16*)f->pos2_w, px * kpos, M, dim, kconv, p, &ga))) return rc; }
+  // keys visible to the window under the chunk mask: all T1 of them for its last chunk (T1 is chunk-aligned)
+  const double attn_work = 2.0 * c.flow_heads * 4.0 * 64.0 * (double)Tw * (t0 + 0.5 * Tw);
+  for (int i = 0; i < c.flow_depth; i++) {
+    const FlowBlk& b = f->blk[i];
+    const float* m = mod + (size_t)i * 6 * dim;
+    dit_ln_mod_kernel<<<cdiv(M, 8), 256, 0, st>>>(f->h, m + dim, m, f->n16, M, dim, f->precise);
+    HVX_LAUNCH_CHECK(e);
+    { GemmEpi p; p.mode = EPI_QKV; p.f16 = 1; p.bias = b.qkv_b; p.out = f->qk; p.ldo = inner; p.n_qk = 2 * inner;
+      p.k_out = (__nv_bfloat16*)S.K(step, i); p.k_ld = inner; p.k_batch_rows = S.Tcap; p.t_off = t0;
+      p.vt = (__nv_bfloat16*)S.Vt(step, i); p.vt_ld = S.Tpcap; p.T = Tw; p.heads = c.flow_heads; p.rows_per_batch = Tw;
+      p.rope_cos = S.rope_c; p.rope_sin = S.rope_s;
+      if ((rc = flow_linear(e, st, f->n16, b.qkv_w, M, 3 * inner, dim, p))) return rc; }
+    { AttnArgs a; a.T = S.Tcap; a.heads = c.flow_heads; a.n_batch = nb; a.chunk = c.flow_chunk; a.f16 = 1;
+      a.Tq = Tw; a.q_pos0 = t0; a.tk = T1; a.k_ptr = (const __nv_bfloat16*)S.K(step, i); a.ld_k = inner;
+      a.ld_out = inner; a.out = (__nv_bfloat16*)f->ao; a.lo_off = f->precise ? inner : 0; a.work = attn_work;
+      if ((rc = dit_attention(e, st, (const __nv_bfloat16*)f->qk, inner, 0, (const __nv_bfloat16*)S.Vt(step, i), S.Tpcap, a))) return rc; }
+    { GemmEpi p; p.mode = EPI_RESID_GATE; p.f16 = 1; p.bias = b.out_b; p.out = f->h; p.ldo = dim; p.gate = m + 2 * dim;
+      p.gate_ld = 0; p.rows_per_batch = Tw;
+      if ((rc = flow_linear(e, st, f->ao, b.out_w, M, dim, inner, p))) return rc; }
+    dit_ln_mod_kernel<<<cdiv(M, 8), 256, 0, st>>>(f->h, m + 4 * dim, m + 3 * dim, f->n16, M, dim, f->precise);
+    HVX_LAUNCH_CHECK(e);
+    { GemmEpi p = epi16(f->f1, f->precise ? 2 * ff : ff, b.ff1_b, ACT_GELU_TANH);
+      p.lo_off = f->precise ? ff : 0;
+      if ((rc = flow_linear(e, st, f->n16, b.ff1_w, M, ff, dim, p))) return rc; }
+    { GemmEpi p; p.mode = EPI_RESID_GATE; p.f16 = 1; p.bias = b.ff2_b; p.out = f->h; p.ldo = dim; p.gate = m + 5 * dim;
+      p.gate_ld = 0; p.rows_per_batch = Tw;
+      if ((rc = flow_linear(e, st, f->f1, b.ff2_w, M, dim, ff, p))) return rc; }
+  }
+  const float* mf = mod + (size_t)c.flow_depth * 6 * dim;
+  dit_ln_mod_kernel<<<cdiv(M, 8), 256, 0, st>>>(f->h, mf, mf + dim, f->n16, M, dim, f->precise);
+  HVX_LAUNCH_CHECK(e);
+  { GemmEpi p; p.mode = EPI_F32; p.f16 = 1; p.bias = f->proj_b; p.out = f->v; p.ldo = mel;
+    if ((rc = flow_linear(e, st, f->n16, f->proj_w, M, mel, dim, p))) return rc; }
+  return HVX_OK;
+}
+
 // adaLN modulations of all blocks for n t-values (t_dev on device): mod (n, depth*6*dim + 2*dim)
 static hvx_status flow_mods(hvx_engine* e, cudaStream_t st, const float* t_dev, int n, __half* st16, float* mod) {
   FlowState* f = e->flow;
@@ -478,6 +567,75 @@ static hvx_status flow_mods(hvx_engine* e, cudaStream_t st, const float* t_dev, 
 }  // namespace hvx
 
 using namespace hvx;
+
+// Pre-net of one utterance (flow.py:387-419): speaker projection, token embedding, PreLookaheadLayer (two convolutions as implicit
+// GEMMs), repeat_interleave(2) into mu, prompt mel into cond, the noise slice into x — into slot u of the solve-level buffers
+// (frame offset xo elements).  nt = prompt + new tokens, l1 = tokens that become frames (look-ahead tokens are context only).
+static hvx_status flow_prenet(hvx_engine* e, cudaStream_t st, const int32_t* tokens, int n_prompt, int nt, int l1, const float* embedding,
+                              const float* prompt_feat, const float* noise, int u, size_t xo) {
+  FlowState* f = e->flow;
+  const hvx_config& c = e->cfg;
+  const int mel = c.flow_mel, pc = c.flow_pla_ch, px = f->precise ? 2 : 1, Cp = (mel + 63) / 64 * 64, mel_len1 = 2 * n_prompt;
+  hvx_status rc;
+  flow_spk_kernel<<<1, 256, 0, st>>>(embedding, f->spk_w, f->spk_b, f->spks + (size_t)u * mel, c.flow_spk_in, mel);
+  HVX_LAUNCH_CHECK(e);
+  flow_embed_kernel<<<cdiv((nt + 3) * Cp, 256), 256, 0, st>>>(tokens, f->emb, f->e32, f->e16, nt, nt + 3, mel, Cp, c.flow_vocab, f->precise);
+  HVX_LAUNCH_CHECK(e);
+  { // conv1 k4, 3 look-ahead rows (zero rows after the last token when finalize): implicit GEMM, K = 4*Cp
+    GemmEpi p = epi16(f->y1p, px * pc, f->pla1_b, ACT_LRELU);
+    p.lo_off = f->precise ? pc : 0;
+    GemmAddr ga; ga.rows_per_batch = l1; ga.a_rows = nt + 3; ga.a_cols = px * Cp; ga.kb_per_tap = Cp / 64; ga.a_row_step = 1;
+    if (f->precise) { ga.a_lo_off = Cp; ga.split3_kb = 4 * Cp / 64; }
+    if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->e16, px * Cp, (const __nv_bfloat16*)f->pla1_w, px * 4 * Cp, l1, pc, (f->precise ? 3 : 1) * 4 * Cp, p, &ga))) return rc; }
+  { // conv2 k3 causal (left pad 2 = out-of-bounds rows) + residual
+    GemmEpi p; p.mode = EPI_F32; p.f16 = 1; p.bias = f->pla2_b; p.out = f->mu_tok; p.ldo = mel; p.resid = f->e32;
+    GemmAddr ga; ga.rows_per_batch = l1; ga.a_cols = px * pc; ga.kb_per_tap = pc / 64; ga.a_row0 = -2; ga.a_row_step = 1;
+    if (f->precise) { ga.a_lo_off = pc; ga.split3_kb = 3 * pc / 64; }
+    if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->y1p, px * pc, (const __nv_bfloat16*)f->pla2_w, px * 3 * pc, l1, mel, (f->precise ? 3 : 1) * 3 * pc, p, &ga))) return rc; }
+  flow_init_kernel<<<cdiv(2 * l1 * mel, 256), 256, 0, st>>>(f->mu_tok, prompt_feat, noise, f->mu + xo, f->cond + xo, f->x + xo, 2 * l1, mel,
+                                                           mel_len1, c.flow_noise_frames);
+  HVX_LAUNCH_CHECK(e);
+  return HVX_OK;
+}
+
+// fp32 t-values and step sizes of the cosine schedule, carried exactly like solve_euler (flow_matching.py:93-122,225-227)
+static void flow_schedule(int n_timesteps, float* tv, float* dtv) {
+  float ts[65];
+  for (int i = 0; i <= n_timesteps; i++) {
+    const float step = 1.0f / (float)n_timesteps;
+    const float lin = (i < (n_timesteps + 1) / 2) ? (float)i * step : 1.0f - (float)(n_timesteps - i) * step;   // torch.linspace
+    ts[i] = 1.0f - cosf((lin * 0.5f) * 3.14159265358979323846f);
+  }
+  float t = ts[0], dt = ts[1] - ts[0];
+  for (int s = 1; s <= n_timesteps; s++) {
+    tv[s - 1] = t; dtv[s - 1] = dt;
+    t = t + dt;
+    if (s < n_timesteps) dt = ts[s + 1] - t;
+  }
+}
+
+// solve-level buffers for U utterances of up to Tm frames / ntok_max tokens and n_timesteps modulation sets (ws_small)
+static hvx_status flow_solve_bufs(hvx_engine* e, int U, int Tm, int ntok_max, int n_timesteps, int** klen_dev) {
+  FlowState* f = e->flow;
+  const hvx_config& c = e->cfg;
+  const int mel = c.flow_mel, dim = c.flow_dim, pc = c.flow_pla_ch;
+  const int nmod = c.flow_depth * 6 * dim + 2 * dim;
+  const size_t nx = (size_t)U * Tm * mel;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
+  const int Cp = (mel + 63) / 64 * 64;                              // embedding rows padded to whole 64-wide k-blocks
+  const size_t o_spk = take((size_t)U * mel * 4), o_e32 = take((size_t)ntok_max * mel * 4), o_e16 = take((size_t)(ntok_max + 3) * Cp * 4);
+  const size_t o_y1 = take((size_t)ntok_max * pc * 4), o_mut = take((size_t)ntok_max * mel * 4);
+  const size_t o_mu = take(nx * 4), o_cond = take(nx * 4), o_x = take(nx * 4);
+  const size_t o_mod = take((size_t)n_timesteps * nmod * 4), o_t = take(64 * 4), o_st = take((size_t)64 * dim * 4), o_kl = take((size_t)2 * U * 4);
+  uint8_t* w = (uint8_t*)f->ws_small.get(off);
+  HVX_CHECK(w, HVX_ERR_CUDA, "flow: buffer allocation of %zu bytes failed", off);
+  f->spks = (float*)(w + o_spk); f->e32 = (float*)(w + o_e32); f->e16 = (__half*)(w + o_e16); f->y1p = (__half*)(w + o_y1);
+  f->mu_tok = (float*)(w + o_mut); f->mu = (float*)(w + o_mu); f->cond = (float*)(w + o_cond); f->x = (float*)(w + o_x);
+  f->mod = (float*)(w + o_mod); f->t_dev = (float*)(w + o_t); f->st16 = (__half*)(w + o_st);
+  *klen_dev = (int*)(w + o_kl);
+  return HVX_OK;
+}
 
 // One CFM solve for U utterances at once (U == 1: the reference's call shape).  Utterance u occupies frames [u*Tm, u*Tm + T_u) of
 // the ODE state; rows beyond T_u are zero padding that stays finite and is never read by a valid row: every op of the estimator
@@ -503,24 +661,12 @@ static hvx_status flow_solve(hvx_engine* e, int U, const int32_t* const* tokens,
   }
   const size_t nx = (size_t)U * Tm * mel;                           // elements of the ODE state
 
-  // solve-level buffers
-  size_t off = 0;
-  auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
-  const int Cp = (mel + 63) / 64 * 64;                              // embedding rows padded to whole 64-wide k-blocks
-  const size_t o_spk = take((size_t)U * mel * 4), o_e32 = take((size_t)ntok_max * mel * 4), o_e16 = take((size_t)(ntok_max + 3) * Cp * 4);
-  const size_t o_y1 = take((size_t)ntok_max * pc * 4), o_mut = take((size_t)ntok_max * mel * 4);
-  const size_t o_mu = take(nx * 4), o_cond = take(nx * 4), o_x = take(nx * 4);
-  const size_t o_mod = take((size_t)n_timesteps * nmod * 4), o_t = take(64 * 4), o_st = take((size_t)64 * dim * 4), o_kl = take((size_t)2 * U * 4);
-  uint8_t* w = (uint8_t*)f->ws_small.get(off);
-  HVX_CHECK(w, HVX_ERR_CUDA, "flow: buffer allocation of %zu bytes failed", off);
-  f->spks = (float*)(w + o_spk); f->e32 = (float*)(w + o_e32); f->e16 = (__half*)(w + o_e16); f->y1p = (__half*)(w + o_y1);
-  f->mu_tok = (float*)(w + o_mut); f->mu = (float*)(w + o_mu); f->cond = (float*)(w + o_cond); f->x = (float*)(w + o_x);
-  f->mod = (float*)(w + o_mod); f->t_dev = (float*)(w + o_t); f->st16 = (__half*)(w + o_st);
-  int* klen_dev = (int*)(w + o_kl);
+  int* klen_dev = nullptr;
   hvx_status rc;
+  if ((rc = flow_solve_bufs(e, U, Tm, ntok_max, n_timesteps, &klen_dev))) return rc;
   if ((rc = flow_plan(e, st, Tm, U))) return rc;
   if (U > 1) {
-    HVX_CUDA(cudaMemsetAsync(f->mu, 0, (o_x - o_mu) + al256(nx * 4), st));      // mu | cond | x are adjacent: padding frames = 0
+    HVX_CUDA(cudaMemsetAsync(f->mu, 0, (size_t)((uint8_t*)f->x - (uint8_t*)f->mu) + al256(nx * 4), st));      // mu | cond | x are adjacent: padding frames = 0
     std::vector<int> kl(2 * U);
     for (int u = 0; u < U; u++) kl[u] = kl[U + u] = Tu[u];
     HVX_CUDA(cudaMemcpyAsync(klen_dev, kl.data(), sizeof(int) * 2 * U, cudaMemcpyHostToDevice, st));
@@ -530,43 +676,11 @@ static hvx_status flow_solve(hvx_engine* e, int U, const int32_t* const* tokens,
   }
 
   // ---- pre-net, utterance by utterance (flow.py:387-419); a few small launches each
-  const int px = f->precise ? 2 : 1;
-  for (int u = 0; u < U; u++) {
-    const int nt = ntok[u], l1 = L1[u], mel_len1 = 2 * n_prompt[u];
-    flow_spk_kernel<<<1, 256, 0, st>>>(embedding[u], f->spk_w, f->spk_b, f->spks + (size_t)u * mel, c.flow_spk_in, mel);
-    HVX_LAUNCH_CHECK(e);
-    flow_embed_kernel<<<cdiv((nt + 3) * Cp, 256), 256, 0, st>>>(tokens[u], f->emb, f->e32, f->e16, nt, nt + 3, mel, Cp, c.flow_vocab, f->precise);
-    HVX_LAUNCH_CHECK(e);
-    { // conv1 k4, 3 look-ahead rows (zero rows after the last token when finalize): implicit GEMM, K = 4*Cp
-      GemmEpi p = epi16(f->y1p, px * pc, f->pla1_b, ACT_LRELU);
-      p.lo_off = f->precise ? pc : 0;
-      GemmAddr ga; ga.rows_per_batch = l1; ga.a_rows = nt + 3; ga.a_cols = px * Cp; ga.kb_per_tap = Cp / 64; ga.a_row_step = 1;
-      if (f->precise) { ga.a_lo_off = Cp; ga.split3_kb = 4 * Cp / 64; }
-      if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->e16, px * Cp, (const __nv_bfloat16*)f->pla1_w, px * 4 * Cp, l1, pc, (f->precise ? 3 : 1) * 4 * Cp, p, &ga))) return rc; }
-    { // conv2 k3 causal (left pad 2 = out-of-bounds rows) + residual
-      GemmEpi p; p.mode = EPI_F32; p.f16 = 1; p.bias = f->pla2_b; p.out = f->mu_tok; p.ldo = mel; p.resid = f->e32;
-      GemmAddr ga; ga.rows_per_batch = l1; ga.a_cols = px * pc; ga.kb_per_tap = pc / 64; ga.a_row0 = -2; ga.a_row_step = 1;
-      if (f->precise) { ga.a_lo_off = pc; ga.split3_kb = 3 * pc / 64; }
-      if ((rc = gemm_bf16(e, st, (const __nv_bfloat16*)f->y1p, px * pc, (const __nv_bfloat16*)f->pla2_w, px * 3 * pc, l1, mel, (f->precise ? 3 : 1) * 3 * pc, p, &ga))) return rc; }
-    const size_t xo = (size_t)u * Tm * mel;
-    flow_init_kernel<<<cdiv(Tu[u] * mel, 256), 256, 0, st>>>(f->mu_tok, prompt_feat[u], noise, f->mu + xo, f->cond + xo, f->x + xo, Tu[u], mel,
-                                                              mel_len1, c.flow_noise_frames);
-    HVX_LAUNCH_CHECK(e);
-  }
+  for (int u = 0; u < U; u++)
+    if ((rc = flow_prenet(e, st, tokens[u], n_prompt[u], ntok[u], L1[u], embedding[u], prompt_feat[u], noise, u, (size_t)u * Tm * mel))) return rc;
 
-  // ---- cosine t-schedule carried in fp32 exactly like solve_euler (flow_matching.py:93-122,225-227)
-  float ts[65], tv[64], dtv[64];
-  for (int i = 0; i <= n_timesteps; i++) {
-    const float step = 1.0f / (float)n_timesteps;
-    const float lin = (i < (n_timesteps + 1) / 2) ? (float)i * step : 1.0f - (float)(n_timesteps - i) * step;   // torch.linspace
-    ts[i] = 1.0f - cosf((lin * 0.5f) * 3.14159265358979323846f);
-  }
-  { float t = ts[0], dt = ts[1] - ts[0];
-    for (int s = 1; s <= n_timesteps; s++) {
-      tv[s - 1] = t; dtv[s - 1] = dt;
-      t = t + dt;
-      if (s < n_timesteps) dt = ts[s + 1] - t;
-    } }
+  float tv[64], dtv[64];
+  flow_schedule(n_timesteps, tv, dtv);
   HVX_CUDA(cudaMemcpyAsync(f->t_dev, tv, sizeof(float) * n_timesteps, cudaMemcpyHostToDevice, st));
   if ((rc = flow_mods(e, st, f->t_dev, n_timesteps, f->st16, f->mod))) return rc;
 
@@ -609,6 +723,100 @@ extern "C" hvx_status hvx_flow_inference_batch(hvx_engine* e, int n_utt, const i
   HVX_CHECK(n_timesteps >= 1 && n_timesteps <= 64, HVX_ERR_ARG, "flow: n_timesteps=%d out of range [1,64]", n_timesteps);
   return flow_solve(e, n_utt, tokens, n_prompt, n_tok, embedding, prompt_feat, noise, n_timesteps, streaming, finalize, mel_out,
                     (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ incremental streaming flow
+// The reference re-runs flow.inference(streaming=True, finalize=False) over ALL tokens so far for every 25-token hop and keeps
+// the new mel frames (cosyvoice/cli/model.py:279-297,330-348).  Under the block-causal chunk mask those calls recompute the same
+// values for every earlier frame, so a session keeps what later frames need of them — per Euler step and layer the keys and V^T,
+// per step the operands of the causal position-embedding convolutions — and evaluates only the new frames.
+extern "C" hvx_status hvx_flow_stream_begin(hvx_engine* e, int n_timesteps, int max_frames, void* stream) {
+  HVX_CHECK(e && e->flow, HVX_ERR_STATE, "flow stage not finalized");
+  HVX_LOCK(e, HVX_STAGE_FLOW);
+  const hvx_config& c = e->cfg;
+  HVX_CHECK(n_timesteps >= 1 && n_timesteps <= 64, HVX_ERR_ARG, "flow_stream: n_timesteps=%d out of range [1,64]", n_timesteps);
+  HVX_CHECK(c.flow_chunk > 0, HVX_ERR_UNSUPPORTED, "flow_stream: the flow has no streaming chunk mask (static_chunk_size = 0)");
+  HVX_CHECK(max_frames >= c.flow_chunk && max_frames <= c.flow_noise_frames, HVX_ERR_ARG, "flow_stream: max_frames=%d outside [%d, %d]", max_frames,
+            c.flow_chunk, c.flow_noise_frames);
+  FlowState* f = e->flow;
+  FlowState::Stream& S = f->stream;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int dim = c.flow_dim, inner = c.flow_heads * 64, px = f->precise ? 2 : 1;
+  S.S = n_timesteps;
+  S.Tcap = (max_frames + 127) & ~127;                        // whole key tiles: a 64-key TMA box never leaves the batch row
+  S.Tpcap = S.Tcap;
+  S.conv_bytes = al256((size_t)2 * S.Tcap * px * dim * sizeof(__half));
+  S.k_bytes = al256((size_t)2 * S.Tcap * inner * sizeof(__half));
+  S.v_bytes = al256((size_t)2 * inner * S.Tpcap * sizeof(__half));
+  S.step_bytes = 2 * S.conv_bytes + (size_t)c.flow_depth * (S.k_bytes + S.v_bytes);
+  const size_t rope_bytes = al256((size_t)S.Tcap * 32 * sizeof(float));
+  const size_t total = (size_t)n_timesteps * S.step_bytes + 2 * rope_bytes;
+  uint8_t* w = (uint8_t*)S.buf.get(total);
+  HVX_CHECK(w, HVX_ERR_CUDA, "flow_stream: cache allocation of %.1f GB failed (%d steps x %d frames)", total / 1e9, n_timesteps, S.Tcap);
+  // keys / V^T columns past the frames seen so far are covered by the last key tile: masked, but they must be finite
+  HVX_CUDA(cudaMemsetAsync(w, 0, (size_t)n_timesteps * S.step_bytes, st));
+  S.rope_c = (float*)(w + (size_t)n_timesteps * S.step_bytes);
+  S.rope_s = (float*)(w + (size_t)n_timesteps * S.step_bytes + rope_bytes);
+  flow_rope_kernel<<<cdiv(S.Tcap * 32, 256), 256, 0, st>>>(f->inv_freq, S.rope_c, S.rope_s, S.Tcap);
+  HVX_LAUNCH_CHECK(e);
+  S.T_done = 0;
+  S.open = true;
+  return HVX_OK;
+}
+
+// tokens_dev: prompt + all new tokens so far INCLUDING the 3 look-ahead tokens (what the reference hands to flow.inference with
+// finalize=False).  Writes the mel frames that are new since the previous call — frames [max(T_done, 2*n_prompt), 2*(n_prompt +
+// n_tok - 3)) — to mel_out_dev as (mel, n_new) and returns n_new through n_new_frames (host).
+extern "C" hvx_status hvx_flow_stream_append(hvx_engine* e, const int32_t* tokens, int n_prompt, int n_tok, const float* embedding,
+                                             const float* prompt_feat, const float* noise, float* mel_out, int* n_new_frames, void* stream) {
+  HVX_CHECK(e && e->flow, HVX_ERR_STATE, "flow stage not finalized");
+  HVX_LOCK(e, HVX_STAGE_FLOW);
+  FlowState* f = e->flow;
+  FlowState::Stream& S = f->stream;
+  const hvx_config& c = e->cfg;
+  cudaStream_t st = (cudaStream_t)stream;
+  HVX_CHECK(S.open, HVX_ERR_STATE, "flow_stream_append: no open session (hvx_flow_stream_begin)");
+  HVX_CHECK(tokens && embedding && noise && mel_out && n_new_frames, HVX_ERR_ARG, "flow_stream_append: null argument");
+  HVX_CHECK(n_prompt == 0 || prompt_feat, HVX_ERR_ARG, "flow_stream_append: prompt tokens without prompt_feat");
+  const int mel = c.flow_mel, dim = c.flow_dim, nt = n_prompt + n_tok, l1 = nt - 3, T1 = 2 * l1, t0 = S.T_done, Tw = T1 - t0;
+  const int nmod = c.flow_depth * 6 * dim + 2 * dim;
+  HVX_CHECK(n_tok - 3 >= 1 && Tw > 0, HVX_ERR_ARG, "flow_stream_append: %d tokens add no frame to the %d already done", n_tok, t0);
+  HVX_CHECK(T1 % c.flow_chunk == 0, HVX_ERR_ARG, "flow_stream_append: %d frames are not whole %d-frame chunks (the caller pads the first hop, "
+            "cli/model.py:332-335)", T1, c.flow_chunk);
+  HVX_CHECK(T1 <= S.Tcap, HVX_ERR_ARG, "flow_stream_append: %d frames exceed the session's %d", T1, S.Tcap);
+  int* klen_dev = nullptr;
+  hvx_status rc;
+  if ((rc = flow_solve_bufs(e, 1, T1, nt, S.S, &klen_dev))) return rc;
+  if ((rc = flow_plan(e, st, Tw, 1))) return rc;                       // window-sized activations
+  if ((rc = flow_prenet(e, st, tokens, n_prompt, nt, l1, embedding, prompt_feat, noise, 0, 0))) return rc;
+  float tv[64], dtv[64];
+  flow_schedule(S.S, tv, dtv);
+  HVX_CUDA(cudaMemcpyAsync(f->t_dev, tv, sizeof(float) * S.S, cudaMemcpyHostToDevice, st));
+  if ((rc = flow_mods(e, st, f->t_dev, S.S, f->st16, f->mod))) return rc;
+  float* xw = f->x + (size_t)t0 * mel;
+  for (int s = 0; s < S.S; s++) {
+    dit_pack_fm_kernel<<<cdiv(2 * Tw * 4 * mel, 256), 256, 0, st>>>(xw, f->cond + (size_t)t0 * mel, f->mu + (size_t)t0 * mel, f->spks, f->xin, Tw, mel, Tw);
+    HVX_LAUNCH_CHECK(e);
+    if ((rc = flow_nfe_window(e, st, f->mod + (size_t)s * nmod, s, t0, Tw))) return rc;
+    flow_euler_kernel<<<cdiv(Tw * mel, 256), 256, 0, st>>>(f->v, xw, Tw * mel, dtv[s], c.flow_cfg_rate);
+    HVX_LAUNCH_CHECK(e);
+  }
+  const int first = std::max(t0, 2 * n_prompt), T_out = T1 - first;
+  if (T_out > 0) {
+    flow_out_kernel<<<cdiv(T_out * mel, 256), 256, 0, st>>>(f->x, mel_out, T_out, mel, first);
+    HVX_LAUNCH_CHECK(e);
+  }
+  *n_new_frames = std::max(T_out, 0);
+  S.T_done = T1;
+  return HVX_OK;
+}
+
+extern "C" hvx_status hvx_flow_stream_end(hvx_engine* e) {
+  HVX_CHECK(e && e->flow, HVX_ERR_STATE, "flow stage not finalized");
+  HVX_LOCK(e, HVX_STAGE_FLOW);
+  e->flow->stream.open = false;
+  e->flow->stream.T_done = 0;
+  return HVX_OK;
 }
 
 extern "C" hvx_status hvx_dit_estimator(hvx_engine* e, const float* x, const float* mu, const float* t, const float* spks,

@@ -320,12 +320,13 @@ __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx,
         }
       } else if (MODE == EPI_QKV) {
         const int t = row - bidx * epi.T;       // rows_per_batch == T
+        const int tp = t + epi.t_off;           // absolute frame (windowed call: rotary position, cache row, V^T column)
         if (col0 < epi.n_qk) {
           const int dq = epi.n_qk >> 1;
           const int cl = col0 % dq;
           if (cl < 64 && epi.rope_cos) {            // null table: no rotary (U-Net estimator, unet.cu)
-            const float* cs = epi.rope_cos + (size_t)t * 32 + (cl >> 1);
-            const float* sn = epi.rope_sin + (size_t)t * 32 + (cl >> 1);
+            const float* cs = epi.rope_cos + (size_t)tp * 32 + (cl >> 1);
+            const float* sn = epi.rope_sin + (size_t)tp * 32 + (cl >> 1);
 #pragma unroll
             for (int i = 0; i < 16; i++) {
               const float c = __ldg(cs + i), s = __ldg(sn + i);
@@ -335,6 +336,7 @@ __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx,
             }
           }
           __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(epi.out) + (size_t)row * epi.ldo + col0;
+          if (epi.k_out && col0 >= dq) o = epi.k_out + ((size_t)bidx * epi.k_batch_rows + tp) * epi.k_ld + (col0 - dq);
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             uint4 pk;
@@ -345,7 +347,7 @@ __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx,
         } else {
           const int cv = col0 - epi.n_qk;
           const int h = cv >> 6, d0 = cv & 63;
-          __nv_bfloat16* o = epi.vt + ((size_t)(bidx * epi.heads + h) * 64 + d0) * epi.vt_ld + t;
+          __nv_bfloat16* o = epi.vt + ((size_t)(bidx * epi.heads + h) * 64 + d0) * epi.vt_ld + tp;
 #pragma unroll
           for (int j = 0; j < 32; j++) reinterpret_cast<uint16_t*>(o)[(size_t)j * epi.vt_ld] = tc::cvt16(f[j], epi.f16);
         }

@@ -46,6 +46,11 @@ struct GemmEpi {
   int vt_ld = 0, T = 1, heads = 1, n_qk = 0;
   const float* rope_cos = nullptr;  // [T][32]
   const float* rope_sin = nullptr;
+  // EPI_QKV, windowed call of the incremental streaming flow (flow.cu: flow_nfe_window): the rows are frames t_off .. t_off + T of
+  // every batch row; q goes to `out` (ldo wide, window-local rows), k to the session's key cache k_out[(b * k_batch_rows + t_off + t)]
+  // (k_ld wide) and V^T to column t_off + t of vt; rotary positions are absolute (t_off + t).  k_out == nullptr: q | k side by side in out.
+  __nv_bfloat16* k_out = nullptr;
+  int k_ld = 0, k_batch_rows = 0, t_off = 0;
   // EPI_F32 extras: out_f32 = act(acc+bias) (+ resid[row][col]); optional bf16 copy of the same value
   const float* resid = nullptr;
   __nv_bfloat16* out2 = nullptr;

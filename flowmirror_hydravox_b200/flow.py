@@ -95,6 +95,40 @@ class NativeFlow:
                                                  vp(*[m.data_ptr() for m in outs]), L.stream_ptr()))
         return outs
 
+    # ---- incremental streaming: the repeated `inference(token=all so far, streaming=True, finalize=False)[..., offset:]` calls of
+    # CosyVoice2Model.token2wav (cli/model.py:279-297) as a session that evaluates only the new chunk(s)
+    def stream_begin(self, n_timesteps=None, max_frames=None):
+        steps = int(n_timesteps or self.n_timesteps)
+        frames = int(max_frames or min(self.dims.noise_frames, 4096))
+        L.check(L.lib().hvx_flow_stream_begin(self.engine.h, steps, frames, L.stream_ptr()))
+        return self
+
+    @torch.no_grad()
+    def stream_append(self, token, embedding, prompt_token=None, prompt_feat=None):
+        """token (1, N): every new token so far incl. the 3 look-ahead tokens -> the mel frames that are new since the previous
+        call, (1, mel, n_new) == inference(token, ..., streaming=True, finalize=False)[0][:, :, frames_already_returned:]"""
+        import ctypes as C
+        d, dev = self.dims, self.engine.device
+        n_tok = int(token.shape[1])
+        n_prompt = 0 if prompt_token is None else int(prompt_token.shape[1])
+        toks = token.reshape(-1) if n_prompt == 0 else torch.cat([prompt_token.reshape(-1), token.reshape(-1)])
+        toks = toks.to(dev, torch.int32).contiguous()
+        emb = embedding.reshape(-1).to(dev, torch.float32).contiguous()
+        pf = None
+        if n_prompt:
+            pf = prompt_feat.reshape(-1, d.mel).to(dev, torch.float32).contiguous()
+            assert pf.shape[0] == 2 * n_prompt, "prompt_feat must hold token_mel_ratio frames per prompt token"
+        cap = 2 * (n_tok - 3)
+        mel = torch.empty(d.mel * max(cap, 1), device=dev, dtype=torch.float32)
+        n_new = C.c_int(0)
+        L.check(L.lib().hvx_flow_stream_append(self.engine.h, L.ptr(toks), n_prompt, n_tok, L.ptr(emb), L.ptr(pf), L.ptr(self.noise),
+                                               L.ptr(mel), C.byref(n_new), L.stream_ptr()))
+        n = int(n_new.value)
+        return mel[: d.mel * n].view(1, d.mel, n)
+
+    def stream_end(self):
+        L.check(L.lib().hvx_flow_stream_end(self.engine.h))
+
     @torch.no_grad()
     def estimator(self, x, mask, mu, t, spks, cond, streaming=False):
         """The TensorRT seam of ConditionalCFM.forward_estimator (flow_matching.py:126-153): (2,mel,T) tensors."""

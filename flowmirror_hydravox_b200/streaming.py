@@ -34,8 +34,11 @@ class StreamingSynthesizer:
     token_hop_len = 25            # cli/model.py:396 (must match the flow's static_chunk_size / token_mel_ratio)
     pre_lookahead_len = 3         # flow.pre_lookahead_len
 
-    def __init__(self, model_manager):
+    def __init__(self, model_manager, incremental: bool = False, max_frames: Optional[int] = None):
+        """incremental: non-final chunks evaluate only their new frames through a flow streaming session (hvx_flow_stream_*: per
+        Euler step and layer key / value caches under the chunk mask) instead of re-running the flow over all tokens so far."""
         self.mm = model_manager
+        self.incremental, self.max_frames = incremental, max_frames
         self.dev = model_manager.engine.device
         self.side = torch.cuda.Stream(self.dev)           # flow + vocoder + counter polling; the LLM has its own stream
         self._cnt_host = torch.zeros(1, dtype=torch.int32).pin_memory()
@@ -102,12 +105,19 @@ class StreamingSynthesizer:
         token_offset = 0
         state: Dict = {}
 
+        if self.incremental:
+            with torch.cuda.stream(self.side):
+                flow.stream_begin(n_timesteps, self.max_frames or min(flow.dims.noise_frames, 2 * (P + max_out) + 64))
+
         def token2wav(n_tok: int, finalize: bool):
             with torch.cuda.stream(self.side):
-                # the reference's last token2wav call omits `stream` (cli/model.py:352-358): full attention on the final pass
-                mel, _ = flow.inference(token=out[:, :n_tok], embedding=emb, prompt_token=ptok, prompt_feat=pfeat,
-                                        streaming=not finalize, finalize=finalize, n_timesteps=n_timesteps)
-                mel = mel[:, :, token_offset * 2:]
+                if self.incremental and not finalize:
+                    mel = flow.stream_append(out[:, :n_tok], emb, prompt_token=ptok, prompt_feat=pfeat)
+                else:
+                    # the reference's last token2wav call omits `stream` (cli/model.py:352-358): full attention on the final pass
+                    mel, _ = flow.inference(token=out[:, :n_tok], embedding=emb, prompt_token=ptok, prompt_feat=pfeat,
+                                            streaming=not finalize, finalize=finalize, n_timesteps=n_timesteps)
+                    mel = mel[:, :, token_offset * 2:]
                 wav = self._vocode(state, mel, finalize)
                 res = wav.cpu()                       # D2H on the side stream, synchronises it
             if debug is not None:
@@ -148,6 +158,8 @@ class StreamingSynthesizer:
                     debug["first_audio_ms"] = (time.perf_counter() - t_start) * 1e3
                 yield {"tts_speech": wav}
         finally:
+            if self.incremental:
+                flow.stream_end()
             if th.is_alive():                  # generator abandoned or failed mid-stream: stop the decode before anything is reused
                 L.check(L.lib().hvx_llm_cancel(mm.engine.h))
                 th.join()
@@ -161,9 +173,9 @@ class StreamingSynthesizerCV2(StreamingSynthesizer):
     hift_t: a NativeHiFTTransposed whose weights are loaded.  noise_fn(n_samples) -> (n_samples, harmonics) pins the source
     module's Gaussian draw per vocoder call (tests); default: fresh noise per call, like the reference."""
     mel_cache_len = 8                                      # cli/model.py:249
-    def __init__(self, model_manager, hift_t, noise_fn=None):
+    def __init__(self, model_manager, hift_t, noise_fn=None, incremental: bool = False, max_frames: Optional[int] = None):
         import numpy as np
-        super().__init__(model_manager)
+        super().__init__(model_manager, incremental=incremental, max_frames=max_frames)
         self.hift_t, self.noise_fn = hift_t, noise_fn
         self.source_cache_len = self.mel_cache_len * hift_t.dims.frame_samples            # :250 (8 * 480)
         self.speech_window = torch.from_numpy(np.hamming(2 * self.source_cache_len)).to(self.dev)   # float64, :252

@@ -241,6 +241,21 @@ hvx_status hvx_synthesize_host(hvx_engine* e, const hvx_request* reqs, int n_req
                                int32_t* wav_len_host, int32_t* tokens_host, int tok_stride,
                                int32_t* n_tokens_host, float* stage_ms_host, void* stream);
 
+/* Incremental streaming flow: replaces the repeated `flow.inference(token=all tokens so far, streaming=True, finalize=False)` calls of
+ * CosyVoice2Model.tts / token2wav (cosyvoice/cli/model.py:279-297,330-348), whose result is sliced to the new frames
+ * (`tts_mel[:, :, token_offset * token_mel_ratio:]`).  A session caches, per Euler step and DiT layer, the keys / values of the
+ * frames already evaluated (valid under the block-causal chunk mask, cosyvoice/utils/mask.py:127-236), and every append
+ * evaluates only the new chunk(s).  begin: n_timesteps Euler steps, room for max_frames mel frames (prompt included).
+ * append: tokens_dev = prompt + new tokens so far incl. the 3 look-ahead tokens; 2 * (n_prompt + n_tok - 3) must be a multiple of
+ * the chunk size (the reference's hop schedule guarantees it); mel_out_dev (mel, n_new) receives the new frames,
+ * *n_new_frames_host their count.  The final chunk (finalize=True) is a full-attention pass by the reference's own semantics
+ * (cli/model.py:352-358): use hvx_flow_inference for it. */
+hvx_status hvx_flow_stream_begin(hvx_engine* e, int n_timesteps, int max_frames, void* stream);
+hvx_status hvx_flow_stream_append(hvx_engine* e, const int32_t* tokens_dev, int n_prompt, int n_tok, const float* embedding_dev,
+                                  const float* prompt_feat_dev, const float* noise_dev, float* mel_out_dev, int* n_new_frames_host,
+                                  void* stream);
+hvx_status hvx_flow_stream_end(hvx_engine* e);
+
 /* speed control: replaces F.interpolate(tts_mel, size=int(T/speed), mode='linear')
  * (infer_speech_model.py:584-587,662-665).  mel_dev (C, T) -> out_dev (C, T_out). */
 hvx_status hvx_speed_interp(hvx_engine* e, const float* mel_dev, int C, int T, int T_out, float* out_dev, void* stream);

@@ -207,3 +207,49 @@ def test_estimator_pool_seam(flows, golden, dtype):
     if dtype == torch.float32:
         assert (got.cpu() - g["est_out"]).abs().max().item() < 2e-2 * max(g["est_out"].abs().mean().item(), 1.0)
     assert pool.trt_context_pool.qsize() == 1
+
+
+@pytest.mark.parametrize("name,precise", [("tiny", True), ("tiny", False), ("full", True)])
+def test_flow_stream_incremental_matches_recompute(name, precise):
+    """hvx_flow_stream_*: a session that evaluates only the new 50-frame chunk(s) per hop (per-step, per-layer key / value caches
+    under the block-causal mask) returns the frames the reference's recompute-everything call returns for the same hop:
+    flow.inference(token=all so far, streaming=True, finalize=False)[..., frames_already_returned:]  (cli/model.py:279-297,330-348)"""
+    from flowmirror_hydravox_b200 import _lib as L
+    from flowmirror_hydravox_b200.flow import NativeFlow
+    fd = D.FLOW_TINY if name == "tiny" else D.FLOW_FULL
+    hop, la = fd.chunk // 2, 3                       # 25 tokens per hop (2 frames per token), 3 look-ahead tokens
+    e = L.Engine(fd=fd, flow_precise=precise)
+    try:
+        f = NativeFlow(e, n_timesteps=4 if name == "full" else 6)
+        f.load_state_dict(synth.flow_state_dict(fd, 0))
+        g = torch.Generator().manual_seed(17)
+        P = 40                                       # prompt tokens: the first hop is padded to the chunk grid (cli/model.py:332-335)
+        pad = -P % hop
+        n_total = pad + 4 * hop + la + 7
+        tok = torch.randint(0, fd.vocab, (1, n_total), generator=g)
+        ptok = torch.randint(0, fd.vocab, (1, P), generator=g)
+        pfeat = torch.rand(1, 2 * P, fd.mel, generator=g) * 6 - 6
+        emb = torch.randn(1, fd.spk_in, generator=g)
+        f.stream_begin(max_frames=2 * (P + n_total))
+        off, returned, worst = 0, 0, 0.0
+        while n_total - off >= (hop + pad if off == 0 else hop) + la:
+            this_hop = hop + pad if off == 0 else hop
+            n_tok = off + this_hop + la
+            inc = f.stream_append(tok[:, :n_tok], emb, prompt_token=ptok, prompt_feat=pfeat)
+            ref, _ = f.inference(token=tok[:, :n_tok], embedding=emb, prompt_token=ptok, prompt_feat=pfeat, streaming=True, finalize=False)
+            ref = ref[:, :, returned:]
+            assert inc.shape == ref.shape == (1, fd.mel, 2 * this_hop), (inc.shape, ref.shape)
+            err = (inc - ref).abs().max().item()
+            worst = max(worst, err)
+            returned += inc.shape[2]
+            off += this_hop
+        f.stream_end()
+        print(f"[flow stream {name} precise={precise}] {returned} frames in {off // hop} hops: incremental vs recompute max-abs {worst:.3e}")
+        assert off >= 4 * hop
+        # same arithmetic per output element; only the lazy-rescale decisions of the online softmax (taken per warp of 32 query
+        # rows) can differ between the two tilings
+        assert worst < (1e-4 if precise else 2e-3), worst
+        with pytest.raises(L.HvxError):
+            f.stream_append(tok[:, :30], emb, prompt_token=ptok, prompt_feat=pfeat)          # no open session
+    finally:
+        e.close()

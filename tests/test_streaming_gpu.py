@@ -111,3 +111,24 @@ def test_streaming_cv2_fade_in_out_matches_reference_orchestration(mm):
             assert torch.equal(a, b), (i, (a - b).abs().max().item())
     finally:
         e.close()
+
+
+def test_streaming_incremental_equals_recompute(mm):
+    """StreamingSynthesizer(incremental=True): the same chunks as the recompute-all orchestration (the flow of every non-final chunk
+    runs through a key / value cache session, the final chunk is the reference's full-attention pass either way)"""
+    from flowmirror_hydravox_b200.streaming import StreamingSynthesizer
+    r = synth.utterance(D.LLM_TINY, D.FLOW_TINY, 12, seed=1986, prompt_tokens=7, prompt_text=3)
+    u = torch.rand(1, 2048, generator=torch.Generator().manual_seed(2))
+    sp = dict(top_p=0.9, top_k=10, win_size=24, tau_r=0.2)
+    res = {}
+    for inc in (False, True):
+        dbg = {}
+        s = StreamingSynthesizer(mm, incremental=inc)
+        chunks = [c["tts_speech"] for c in s.tts(r, head_k=2, sampling=sp, n_timesteps=4, min_ratio=8, max_ratio=8, u=u, debug=dbg)]
+        res[inc] = (chunks, dbg)
+    (c0, d0), (c1, d1) = res[False], res[True]
+    assert d0["tokens"] == d1["tokens"] and d0["n_tok"] == d1["n_tok"] and len(c0) == len(c1)
+    for a, b in zip(d0["mel"], d1["mel"]):
+        assert a.shape == b.shape and (a - b).abs().max().item() < 2e-3
+    for a, b in zip(c0, c1):
+        assert a.shape == b.shape and (a - b).abs().max().item() < 5e-3
