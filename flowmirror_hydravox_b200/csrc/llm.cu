@@ -915,13 +915,29 @@ __global__ void __launch_bounds__(256, 1) llm_attn_mma_kernel(AttnDecArgs a) {
   const int per = (n_keys + a.splits - 1) / a.splits;
   const int k_begin = split * per, k_end = min(n_keys, k_begin + per);
   // ---- Q tile: row m = r * group + gq  <-  q[(seq, r)][head kvh*group+gq] * scale, as bf16 hi / lo; zero the staging ring
-  for (int i = tid; i < 32 * 64; i += 256) {
-    const int m = i >> 6, d = i & 63;
-    float v = 0.f;
-    if (m < n_rows) { const int r = m / a.group, gq = m - r * a.group; v = a.q[(size_t)(seq * a.rows_per_seq + r) * a.ldq + (kvh * a.group + gq) * 64 + d] * a.scale; }
-    const __nv_bfloat16 h = __float2bfloat16(v);
-    qhi[m * AM_LDQ + d] = h;
-    qlo[m * AM_LDQ + d] = __float2bfloat16(v - __bfloat162float(h));
+  { // 32 rows x 16 float4: two per thread, both loads in flight before the first use (eight dependent scalar loads per thread
+    // were the kernel's top stall, profiles/r2 decode attention)
+    float4 qv[2];
+#pragma unroll
+    for (int it = 0; it < 2; it++) {
+      const int i = tid + it * 256, m = i >> 4, d4 = (i & 15) * 4;
+      qv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < n_rows) {
+        const int r = m / a.group, gq = m - r * a.group;
+        qv[it] = *reinterpret_cast<const float4*>(a.q + (size_t)(seq * a.rows_per_seq + r) * a.ldq + (kvh * a.group + gq) * 64 + d4);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < 2; it++) {
+      const int i = tid + it * 256, m = i >> 4, d4 = (i & 15) * 4;
+      const float v[4] = {qv[it].x * a.scale, qv[it].y * a.scale, qv[it].z * a.scale, qv[it].w * a.scale};
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const __nv_bfloat16 h = __float2bfloat16(v[j]);
+        qhi[m * AM_LDQ + d4 + j] = h;
+        qlo[m * AM_LDQ + d4 + j] = __float2bfloat16(v[j] - __bfloat162float(h));
+      }
+    }
   }
   { uint4* z = reinterpret_cast<uint4*>(sk);
     const int nz = (int)((2 * AM_CH * (LDK + LDV) * sizeof(KT)) / 16);
@@ -1098,24 +1114,42 @@ __global__ void __launch_bounds__(256, 1) llm_attn_mma_kernel(AttnDecArgs a) {
     }
   __syncthreads();
   const int q_heads = a.kv_heads * a.group;
-  for (int i = tid; i < n_rows * 64; i += 256) {
-    const int m = i >> 6, d = i & 63;
+  // per-row merge weights of the 8 warps, once per row (thread = (warp slot w, row m)); mw is overwritten by the weights,
+  // row maxima go to Mrow, row sums to Lrow
+  float* Mrow = lw + 8 * 32;                                                // [32]
+  float* Lrow = Mrow + 32;                                                  // [32]
+  { const int w = tid >> 5, m = tid & 31;
     float M = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < 8; w++) M = fmaxf(M, mw[w * 32 + m]);
-    float acc = 0.f, L = 0.f;
+    for (int k = 0; k < 8; k++) M = fmaxf(M, mw[k * 32 + m]);
+    const float mv = mw[w * 32 + m];
+    const float wgt = (mv == -INFINITY) ? 0.f : expf(mv - M);
+    __syncthreads();                                                        // every thread has read the maxima of its row
+    mw[w * 32 + m] = wgt;
+    lw[w * 32 + m] *= wgt;
+    if (w == 0) Mrow[m] = M;
+    __syncthreads();
+    if (w == 0) {
+      float L = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; w++) {
-      const float mv = mw[w * 32 + m];
-      const float wgt = (mv == -INFINITY) ? 0.f : expf(mv - M);
-      acc += wgt * Ow[((size_t)w * 32 + m) * 64 + d];
-      L += wgt * lw[w * 32 + m];
+      for (int k = 0; k < 8; k++) L += lw[k * 32 + m];
+      Lrow[m] = L;
     }
-    const int r = m / a.group, gq = m - r * a.group;
-    const int row = seq * a.rows_per_seq + r, qh = kvh * a.group + gq;
-    float* pp = a.part + (((size_t)row * q_heads + qh) * a.splits + split) * 68;
-    pp[4 + d] = acc;
-    if (d == 0) { pp[0] = M; pp[1] = L; }
+    __syncthreads(); }
+#pragma unroll
+  for (int it = 0; it < 8; it++) {
+    const int i = tid + it * 256;
+    if (i < n_rows * 64) {
+      const int m = i >> 6, d = i & 63;
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; w++) acc += mw[w * 32 + m] * Ow[((size_t)w * 32 + m) * 64 + d];
+      const int r = m / a.group, gq = m - r * a.group;
+      const int row = seq * a.rows_per_seq + r, qh = kvh * a.group + gq;
+      float* pp = a.part + (((size_t)row * q_heads + qh) * a.splits + split) * 68;
+      pp[4 + d] = acc;
+      if (d == 0) { pp[0] = Mrow[m]; pp[1] = Lrow[m]; }
+    }
   }
   __threadfence();
   __syncthreads();
@@ -1123,24 +1157,46 @@ __global__ void __launch_bounds__(256, 1) llm_attn_mma_kernel(AttnDecArgs a) {
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  // last slice of this (sequence, kv head): merge the slices in index order (deterministic) and write the attention rows
-  for (int i = tid; i < n_rows * 64; i += 256) {
-    const int m = i >> 6, d = i & 63;
+  // last slice of this (sequence, kv head): merge the slices in index order (deterministic) and write the attention rows.  A
+  // thread owns up to 8 (row, dim) elements; the slice loop is the outer one so that the loads of all of them are in flight
+  // together (one element after the other, each with its own dependent L2 round trips, cost ~10 us of the kernel's ~36)
+  const float* pbs[8];
+  float Mx[8], Ls[8], acc[8];
+#pragma unroll
+  for (int it = 0; it < 8; it++) {
+    const int i = min(tid + it * 256, n_rows * 64 - 1), m = i >> 6;
     const int r = m / a.group, gq = m - r * a.group;
-    const int row = seq * a.rows_per_seq + r, qh = kvh * a.group + gq;
-    const float* pb = a.part + ((size_t)row * q_heads + qh) * a.splits * 68;
-    float Mx = -INFINITY;
-    for (int sp = 0; sp < a.splits; sp++) Mx = fmaxf(Mx, __ldcg(pb + sp * 68));
-    float Ls = 0.f, acc = 0.f;
-    for (int sp = 0; sp < a.splits; sp++) {
-      const float ms = __ldcg(pb + sp * 68);
-      const float w = (ms == -INFINITY) ? 0.f : expf(ms - Mx);
-      Ls += __ldcg(pb + sp * 68 + 1) * w;
-      acc += __ldcg(pb + sp * 68 + 4 + d) * w;
+    pbs[it] = a.part + ((size_t)(seq * a.rows_per_seq + r) * q_heads + kvh * a.group + gq) * a.splits * 68;
+    Mx[it] = -INFINITY; Ls[it] = 0.f; acc[it] = 0.f;
+  }
+  for (int sp = 0; sp < a.splits; sp++)
+#pragma unroll
+    for (int it = 0; it < 8; it++) Mx[it] = fmaxf(Mx[it], __ldcg(pbs[it] + sp * 68));
+  for (int sp = 0; sp < a.splits; sp++) {
+    float ms[8], ls[8], os[8];
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+      const int d = (tid + it * 256) & 63;
+      ms[it] = __ldcg(pbs[it] + sp * 68); ls[it] = __ldcg(pbs[it] + sp * 68 + 1); os[it] = __ldcg(pbs[it] + sp * 68 + 4 + d);
     }
-    const float y = acc / Ls;
-    if (a.out) a.out[(size_t)row * a.ldo + qh * 64 + d] = y;
-    if (a.out16) store_split(a.out16 + (size_t)row * 2 * a.ldo, a.ldo, qh * 64 + d, y);
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+      const float w = (ms[it] == -INFINITY) ? 0.f : expf(ms[it] - Mx[it]);
+      Ls[it] += ls[it] * w;
+      acc[it] += os[it] * w;
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < 8; it++) {
+    const int i = tid + it * 256;
+    if (i < n_rows * 64) {
+      const int m = i >> 6, d = i & 63;
+      const int r = m / a.group, gq = m - r * a.group;
+      const int row = seq * a.rows_per_seq + r, qh = kvh * a.group + gq;
+      const float y = acc[it] / Ls[it];
+      if (a.out) a.out[(size_t)row * a.ldo + qh * 64 + d] = y;
+      if (a.out16) store_split(a.out16 + (size_t)row * 2 * a.ldo, a.ldo, qh * 64 + d, y);
+    }
   }
   if (tid == 0) a.counters[seq * a.kv_heads + kvh] = 0;
 }
@@ -1812,7 +1868,7 @@ static hvx_status launch_attn(hvx_engine* e, cudaStream_t st, LlmState* L, int l
   if (seqs && want16 && mode == 2 && rows_per_seq >= 1 && rows_per_seq * a.group <= 32 && rows_per_seq <= 4) {
     a.splits = std::max(1, std::min(16, e->sm_count / std::max(1, n_seq_b * c.llm_kv_heads)));
     const size_t kv_bytes = L->kv_f32 ? (size_t)2 * AM_CH * (AM_LDK32 + AM_LDV32) * 4 : (size_t)2 * AM_CH * 2 * AM_LD16 * 2;
-    const size_t merge_bytes = (size_t)(8 * 32 * 64 + 2 * 8 * 32) * 4;
+    const size_t merge_bytes = (size_t)(8 * 32 * 64 + 2 * 8 * 32 + 64) * 4;
     const size_t smem = (size_t)2 * 32 * AM_LDQ * 2 + std::max(kv_bytes, merge_bytes);
     static bool attr_set = false;
     if (!attr_set) {
