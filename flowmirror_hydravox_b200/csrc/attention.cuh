@@ -4,7 +4,7 @@
 // One CTA = (batch, head, 128-query tile), 128 threads.  TMEM lane == query row == thread, so the
 // online softmax needs no cross-thread reduction:
 //   S (128x128 fp32, TMEM cols 0..127)   = Q K_j^T      tcgen05.mma M128 N128 K16 x4, operands by TMA (SW128)
-//   P (bf16, smem, SW128 K-major)        = exp2(S*c - m) written by the row's own thread
+//   P (16-bit, TMEM, packed K-major)     = exp2(S*c - m) stored by the row's own thread (tcgen05.st)
 //   O_j (128x64 fp32, TMEM cols 128..191) = P V_j        tcgen05.mma M128 N64 K16 x8, V^T tile by TMA
 //   o_acc (registers)                    = o_acc*alpha + O_j
 // K/V^T tiles are double-buffered; two CTAs co-reside per SM (112 KB smem, 256 TMEM columns each) so
