@@ -409,7 +409,7 @@ def native_arm(a):
         per_class[k] = d
     dom = max((k for k in per_class if "frac" in per_class[k]), key=lambda k: per_class[k]["ms_per_step"], default=None)
     kernel_names = {"gemm": "gemm_persist_kernel / gemm_bf16_kernel (tcgen05 + TMA; DiT linears, 3 split-fp16 products each in parity mode)",
-                    "attention": "dit_attention_v5_kernel (tcgen05, S/O in TMEM)", "hift_conv": "HiFT convolutions",
+                    "attention": "dit_attention_v5_kernel (tcgen05; S, P and O in TMEM)", "hift_conv": "HiFT convolutions",
                     "llm_step": "decode step (CUDA graph: tcgen05 GEMMs above 8 rows, TMA GEMV below)", "layernorm": "dit_ln_mod_kernel"}
     traffic = None
     try:
@@ -426,7 +426,8 @@ def native_arm(a):
                 "kernel": f"{kernel_names.get(dom, dom)}: dominant kernel class of the timed steps ({100 * dc['share_of_step']:.0f} % of the step); achieved = "
                           f"algorithmic work of its launches / summed CUDA-event duration of those launches, events recorded around every launch "
                           f"on the launching stream inside the timed region",
-                "traffic_source": tr.get(dom, {}).get("source") if traffic else None,
+                "traffic_source": (f"{tr[dom]['source']}; one representative launch: {tr[dom]['kernel']}, algorithmic "
+                                   f"{tr[dom]['algorithmic_bytes_per_launch']} B") if traffic else None,
                 "peak_source": peak_src, "per_class": per_class}
     tot = sum(stage_acc.values()) or 1.0
     line = {"metric": "speech_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": a.steps, "warmup": n_warm,
