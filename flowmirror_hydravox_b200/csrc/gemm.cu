@@ -99,11 +99,26 @@ template <int MODE, int ACT>
 __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx, int col0, int N, const uint32_t* v,
                                           const float* pre = nullptr) {
       float f[32];
+      if (epi.bias && col0 + 32 <= N && ((uintptr_t)epi.bias & 15) == 0) {
+        // the chunk's 32 bias values as eight 16-byte loads (the same addresses for every thread of the warp: one transaction
+        // each); 32 scalar loads with their dependent adds were the top stall of the epilogue warps (profiles/r2 ff1 source view)
+        float4 b4[8];
 #pragma unroll
-      for (int j = 0; j < 32; j++) {
-        float x = __uint_as_float(v[j]);
-        if (epi.bias && col0 + j < N) x += __ldg(epi.bias + col0 + j);
-        f[j] = act_apply(x, ACT);
+        for (int j = 0; j < 8; j++) b4[j] = __ldg(reinterpret_cast<const float4*>(epi.bias + col0) + j);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          f[4 * j] = act_apply(__uint_as_float(v[4 * j]) + b4[j].x, ACT);
+          f[4 * j + 1] = act_apply(__uint_as_float(v[4 * j + 1]) + b4[j].y, ACT);
+          f[4 * j + 2] = act_apply(__uint_as_float(v[4 * j + 2]) + b4[j].z, ACT);
+          f[4 * j + 3] = act_apply(__uint_as_float(v[4 * j + 3]) + b4[j].w, ACT);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          float x = __uint_as_float(v[j]);
+          if (epi.bias && col0 + j < N) x += __ldg(epi.bias + col0 + j);
+          f[j] = act_apply(x, ACT);
+        }
       }
       if (MODE == EPI_BF16) {
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(epi.out) + (size_t)row * epi.ldo + col0;
@@ -244,11 +259,27 @@ __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx,
           if (h.act[k] == 2) {
             const float* al = h.alpha[k] + col0;
             const float* ia = h.inv_alpha[k] + col0;
+            if (full && (((uintptr_t)al | (uintptr_t)ia) & 15) == 0) {
+              // Snake parameters of the chunk as 16-byte loads (warp-uniform addresses), all in flight before the first sinf
+              float4 a4[8], i4[8];
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-              const int jc = (col0 + j < N) ? j : 0;
-              const float sn = sinf(f[j] * __ldg(al + jc));
-              a[j] = f[j] + __ldg(ia + jc) * (sn * sn);
+              for (int j = 0; j < 8; j++) { a4[j] = __ldg(reinterpret_cast<const float4*>(al) + j); i4[j] = __ldg(reinterpret_cast<const float4*>(ia) + j); }
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                const float aa[4] = {a4[j].x, a4[j].y, a4[j].z, a4[j].w}, ii[4] = {i4[j].x, i4[j].y, i4[j].z, i4[j].w};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                  const float sn = sinf(f[4 * j + q] * aa[q]);
+                  a[4 * j + q] = f[4 * j + q] + ii[q] * (sn * sn);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j++) {
+                const int jc = (col0 + j < N) ? j : 0;
+                const float sn = sinf(f[j] * __ldg(al + jc));
+                a[j] = f[j] + __ldg(ia + jc) * (sn * sn);
+              }
             }
           } else if (h.act[k] == 1) {
 #pragma unroll

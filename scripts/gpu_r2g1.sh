@@ -1,12 +1,17 @@
 #!/bin/bash
 mkdir -p gpurun_out
 R=/tmp/ncu; mkdir -p $R
-HVX_FLOW_PRECISE=1 timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:"gemm_pair3_kernel<0" -s 4 -c 1 -o $R/ff1 -f python scripts/prof_flow.py 1 > gpurun_out/r2g1_ncu.log 2>&1
+HVX_FLOW_PRECISE=1 timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:gemm_pair3_kernel -s 9 -c 5 -o $R/ff1 -f python scripts/prof_flow.py 1 > gpurun_out/r2g1_ncu.log 2>&1
 tail -2 gpurun_out/r2g1_ncu.log
 ncu -i $R/ff1.ncu-rep --page source --csv --print-source sass 2>/dev/null > $R/src.csv
 python - <<'P'
 import csv
-rows=list(csv.reader(open('/tmp/ncu/src.csv')))
+allrows=list(csv.reader(open('/tmp/ncu/src.csv')))
+starts=[i for i,r in enumerate(allrows) if r and r[0]=="Kernel Name"]
+print("kernels in report:", [allrows[i][1][:60] for i in starts])
+pick=[i for i in starts if "(int)0, (int)1" in allrows[i][1]]
+i0=pick[0]; i1=min([j for j in starts if j>i0]+[len(allrows)])
+rows=allrows[i0:i1]
 hdr=rows[1]
 si=hdr.index("# Samples"); ie=hdr.index("Instructions Executed")
 data=[]
