@@ -125,3 +125,38 @@ def test_stream_oracle_fade_in_out_matches_reference_function():
         refshim.install()
         from cosyvoice.utils.common import fade_in_out as ref_fade
         assert torch.equal(ref_fade(a.clone(), b, w), out)
+
+
+def test_pack_unet_nc_resampling_convs_are_exact_repacks():
+    """weights.pack_unet_nc turns Downsample1D (Conv1d k3, stride 2, pad 1) into a 2-tap convolution over frame pairs and Upsample1D
+    (ConvTranspose1d(C, C, 4, 2, 1)) into a k3 convolution with 2C outputs (matcha/models/components/decoder.py:64-70,116-158): both
+    are the same linear maps, checked here against torch on the CPU (up to the fp16 rounding of the packed weights)."""
+    import torch
+    import torch.nn.functional as F
+    from flowmirror_hydravox_b200 import dims as D, synth
+    from flowmirror_hydravox_b200.weights import pack_unet_nc
+    d = D.UNET_NC_TINY
+    sd = synth.unet_nc_state_dict(d, 0)
+    pk = pack_unet_nc(sd, d)
+    C = d.ch
+    g = torch.Generator().manual_seed(3)
+    for T in (11, 12):                                   # odd and even lengths: ceil(T / 2) output frames
+        x = torch.randn(1, C, T, generator=g)
+        w, b = sd["down_blocks.0.2.conv.weight"].half().float(), sd["down_blocks.0.2.conv.bias"]
+        ref = F.conv1d(x, w, b, stride=2, padding=1)
+        To = (T + 1) // 2
+        pairs = F.pad(x, (0, 2 * To - T)).transpose(1, 2).reshape(To, 2 * C)            # row t = (x[2t], x[2t+1])
+        rows = torch.cat([F.pad(pairs, (0, 0, 1, 0))[:-1], pairs], 1)                   # [row t-1 | row t]
+        y = (rows @ pk["down0.w"].float().t() + pk["down0.b"]).t()[None]
+        assert y.shape == ref.shape and (y - ref).abs().max() < 1e-5
+        wt, bt = sd["up_blocks.0.2.conv.weight"].half().float(), sd["up_blocks.0.2.conv.bias"]
+        ref = F.conv_transpose1d(x, wt, bt, stride=2, padding=1)
+        xr = x[0].t()
+        rows = torch.cat([F.pad(xr, (0, 0, 1, 0))[:-1], xr, F.pad(xr, (0, 0, 0, 1))[1:]], 1)   # [x[m-1] | x[m] | x[m+1]]
+        y = (rows @ pk["up0.w"].float().t() + pk["up0.b"]).reshape(-1, C).t()[None]      # row m = (y[2m], y[2m+1])
+        assert y.shape == ref.shape and (y - ref).abs().max() < 1e-5
+    # parity mode packs [hi | lo]: hi + lo reproduces the fp32 weights
+    pk2 = pack_unet_nc(sd, d, precise=True)
+    hi, lo = pk2["res0.c1.w"].float().chunk(2, dim=1)
+    w = sd["down_blocks.0.0.block1.block.0.weight"]
+    assert (hi + lo - w.permute(0, 2, 1).reshape(w.shape[0], -1)).abs().max() < 1e-6
