@@ -10,7 +10,7 @@ import torch
 from . import dims as D
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhydravox_b200.so")
+LIB_PATH = os.environ.get("HVX_LIB_PATH") or os.path.join(_HERE, "libhydravox_b200.so")      # HVX_LIB_PATH: A/B runs against another build
 
 STAGE_LLM, STAGE_FLOW, STAGE_HIFT, STAGE_UNET = 0, 1, 2, 3
 _DT = {torch.float32: 0, torch.bfloat16: 1, torch.int32: 2, torch.float16: 3}

@@ -95,11 +95,14 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 // fused epilogue of one 32-column chunk of one output row: v = raw fp32 accumulators of columns [col0, col0+32)
 // MODE / ACT are compile-time: one kernel instance carries exactly one epilogue.  (With every mode inlined the kernel was
 // 21.6k SASS instructions and each tile's epilogue ran out of a cold instruction cache: ~25 us of fetch stalls per tile.)
-template <int MODE, int ACT>
+// VEC_BIAS: only the persistent kernels (large problems) carry the 16-byte bias loads.  The extra code path costs the one-tile-per-CTA
+// kernel of the small launches more in instruction fetch than the loads save: with it in every instance the first audio chunk of
+// the streaming path went from 75 to 89 ms (scripts/first_audio.py, A/B against the previous build on one box).
+template <int MODE, int ACT, bool VEC_BIAS = false>
 __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx, int col0, int N, const uint32_t* v,
                                           const float* pre = nullptr) {
       float f[32];
-      if (epi.bias && col0 + 32 <= N && ((uintptr_t)epi.bias & 15) == 0) {
+      if (VEC_BIAS && epi.bias && col0 + 32 <= N && ((uintptr_t)epi.bias & 15) == 0) {
         // the chunk's 32 bias values as eight 16-byte loads (the same addresses for every thread of the warp: one transaction
         // each); 32 scalar loads with their dependent adds were the top stall of the epilogue warps (profiles/r2 ff1 source view)
         float4 b4[8];
@@ -259,27 +262,11 @@ __device__ __forceinline__ void epi_store(const GemmEpi& epi, int row, int bidx,
           if (h.act[k] == 2) {
             const float* al = h.alpha[k] + col0;
             const float* ia = h.inv_alpha[k] + col0;
-            if (full && (((uintptr_t)al | (uintptr_t)ia) & 15) == 0) {
-              // Snake parameters of the chunk as 16-byte loads (warp-uniform addresses), all in flight before the first sinf
-              float4 a4[8], i4[8];
 #pragma unroll
-              for (int j = 0; j < 8; j++) { a4[j] = __ldg(reinterpret_cast<const float4*>(al) + j); i4[j] = __ldg(reinterpret_cast<const float4*>(ia) + j); }
-#pragma unroll
-              for (int j = 0; j < 8; j++) {
-                const float aa[4] = {a4[j].x, a4[j].y, a4[j].z, a4[j].w}, ii[4] = {i4[j].x, i4[j].y, i4[j].z, i4[j].w};
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                  const float sn = sinf(f[4 * j + q] * aa[q]);
-                  a[4 * j + q] = f[4 * j + q] + ii[q] * (sn * sn);
-                }
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j++) {
-                const int jc = (col0 + j < N) ? j : 0;
-                const float sn = sinf(f[j] * __ldg(al + jc));
-                a[j] = f[j] + __ldg(ia + jc) * (sn * sn);
-              }
+            for (int j = 0; j < 32; j++) {
+              const int jc = (col0 + j < N) ? j : 0;
+              const float sn = sinf(f[j] * __ldg(al + jc));
+              a[j] = f[j] + __ldg(ia + jc) * (sn * sn);
             }
           } else if (h.act[k] == 1) {
 #pragma unroll
@@ -641,7 +628,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         tc::tmem_ld_wait();
         const int col0 = colh + c;
         if (!row_ok || col0 >= N) continue;
-        epi_store<MODE, ACT>(epi, row, bidx, col0, N, v, use_pre ? &pre[c] : nullptr);
+        epi_store<MODE, ACT, true>(epi, row, bidx, col0, N, v, use_pre ? &pre[c] : nullptr);
       }
       tc::tc_fence_before();
       __syncwarp();
@@ -790,7 +777,7 @@ gemm_pair3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         tc::tmem_ld_wait();
         const int col0 = colh + c;
         if (!row_ok || col0 >= N) continue;
-        epi_store<MODE, ACT>(epi, row, bidx, col0, N, v, use_pre ? &pre[c] : nullptr);
+        epi_store<MODE, ACT, true>(epi, row, bidx, col0, N, v, use_pre ? &pre[c] : nullptr);
       }
       tc::tc_fence_before();
       __syncwarp();

@@ -1949,12 +1949,36 @@ __global__ void llm_splitk_reduce_kernel(float* __restrict__ out, const float* _
   }
 }
 
+// split-K reduce of the decode QKV projection fused with its epilogue (bias, RoPE, q out, K / V straight into the cache): a thread
+// per (row, even column) pair
+__global__ void llm_qkv_reduce_kernel(const float* __restrict__ part, int S, size_t stride, const float* __restrict__ bias, int rows, int N,
+                                      LlmQkvEpi q) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t pairs = (size_t)rows * (N >> 1);
+  if (i >= pairs) return;
+  const int row = (int)(i / (N >> 1)), n = 2 * (int)(i - (size_t)row * (N >> 1));
+  float2 v = make_float2(bias ? bias[n] : 0.f, bias ? bias[n + 1] : 0.f);
+  for (int z = 0; z < S; z++) {
+    const float2 p = *reinterpret_cast<const float2*>(part + (size_t)z * stride + (size_t)row * N + n);
+    v.x += p.x; v.y += p.y;
+  }
+  llm_qkv_store(q, row, n, v.x, v.y);
+}
+
 // h (rows x H) += A16 (split bf16 [hi | lo], rows x 2K) . W^T  for the skinny N = H projections of the tcgen05 path (o-proj,
 // down-proj): 14 output tiles for 148 SMs, so the k-blocks are split over grid.z and the partials are added by
 // llm_splitk_reduce_kernel (profiles/r1c_llm_batch32_kernels.txt: these two GEMMs were 34 % of a 128-row decode step)
 static hvx_status llm_skinny_resid_gemm(hvx_engine* e, cudaStream_t st, const StepBufs& b, const __nv_bfloat16* a16, const __nv_bfloat16* w,
                                         int rows, int H, int K, float* out = nullptr, const float* resid = nullptr,
-                                        __nv_bfloat16* out16 = nullptr) {
+                                        __nv_bfloat16* out16 = nullptr, const float* norm_w = nullptr, __nv_bfloat16* norm_x16 = nullptr) {
+  // norm_w / norm_x16: the RMSNorm that follows the projection in the layer (its [hi | lo] rows for the next GEMM).  A warp-per-row
+  // kernel fusing the split-K reduce with this norm was measured at 27 us against 3.5 + 4.7 us for the two launches: kept separate.
+  auto norm_after = [&](const float* h) -> hvx_status {
+    if (!norm_w) return HVX_OK;
+    llm_norm16_kernel<<<cdiv(rows, 8), 256, 0, st>>>(h, norm_w, norm_x16, rows, H, e->cfg.llm_eps);
+    HVX_LAUNCH_CHECK(e);
+    return HVX_OK;
+  };
   static const int want = getenv("HVX_LLM_SPLITK") ? atoi(getenv("HVX_LLM_SPLITK")) : 1;
   if (!out) out = b.h;
   if (!resid) resid = b.h;
@@ -1967,7 +1991,8 @@ static hvx_status llm_skinny_resid_gemm(hvx_engine* e, cudaStream_t st, const St
   if (S <= 1 || (H & 3)) {
     GemmEpi p; p.mode = EPI_F32; p.out = out; p.ldo = H; p.resid = resid;
     if (out16) { p.out2 = out16; p.ldo2 = 2 * H; p.lo_off = H; }
-    return gemm_bf16(e, st, a16, 2 * K, w, K, rows, H, 2 * K, p, &ga);
+    const hvx_status rc1 = gemm_bf16(e, st, a16, 2 * K, w, K, rows, H, 2 * K, p, &ga);
+    return rc1 ? rc1 : norm_after(out);
   }
   ga.split_k = S; ga.split_stride = (size_t)rows * H;
   GemmEpi p; p.mode = EPI_F32; p.out = b.part; p.ldo = H;
@@ -1976,7 +2001,7 @@ static hvx_status llm_skinny_resid_gemm(hvx_engine* e, cudaStream_t st, const St
   const size_t n4 = (size_t)rows * H / 4;
   llm_splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(out, resid, b.part, S, n4, n4, out16, H);
   HVX_LAUNCH_CHECK(e);
-  return HVX_OK;
+  return norm_after(out);
 }
 
 // the 24 transformer layers over `rows` row slots of b.h (in place).  rows <= 8: weight-streaming GEMVs;
@@ -2006,17 +2031,33 @@ static hvx_status llm_layers(hvx_engine* e, cudaStream_t st, LlmState* L, const 
       // activations travel as split bf16 [hi | lo] (K' = 2K against the same weights) -> fp32-accurate products
       GemmAddr gh; gh.b_kb_mod = H / 64;
       GemmAddr gi; gi.b_kb_mod = I / 64;
-      llm_norm16_kernel<<<cdiv(rows, 8), 256, 0, st>>>(b.h, y.ln1, b.x16, rows, H, c.llm_eps);
-      HVX_LAUNCH_CHECK(e);
-      { GemmEpi p; p.mode = EPI_LLM_QKV; p.bias = y.qkv_b; p.llm = qe;
-        if ((rc = gemm_bf16(e, st, b.x16, 2 * H, y.qkv_w, H, rows, NQKV, 2 * H, p, &gh))) return rc; }
+      if (l == 0) {                                   // later layers: fused into the previous layer's down-proj reduce
+        llm_norm16_kernel<<<cdiv(rows, 8), 256, 0, st>>>(b.h, y.ln1, b.x16, rows, H, c.llm_eps);
+        HVX_LAUNCH_CHECK(e);
+      }
+      // decode (seqs): the 18 output tiles of the QKV projection leave 130 SMs idle — split-K over grid.z, the epilogue (bias,
+      // RoPE, cache write) runs in the reduce kernel.  The prefill keeps the one-pass epilogue GEMM (its accumulation order is
+      // the one the C2 token-identity fixture was minted against).
+      static const int qkv_splitk = getenv("HVX_LLM_QKV_SPLITK") ? atoi(getenv("HVX_LLM_QKV_SPLITK")) : 4;
+      int Sq = seqs && qkv_splitk > 1 ? std::min(qkv_splitk, (2 * H / 64) / 7) : 1;
+      while (Sq > 1 && (size_t)Sq * rows * NQKV > b.part_floats) Sq--;
+      if (Sq > 1) {
+        GemmAddr gq = gh; gq.split_k = Sq; gq.split_stride = (size_t)rows * NQKV;
+        GemmEpi p; p.mode = EPI_F32; p.out = b.part; p.ldo = NQKV;
+        if ((rc = gemm_bf16(e, st, b.x16, 2 * H, y.qkv_w, H, rows, NQKV, 2 * H, p, &gq))) return rc;
+        const size_t pairs = (size_t)rows * (NQKV / 2);
+        llm_qkv_reduce_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(b.part, Sq, (size_t)rows * NQKV, y.qkv_b, rows, NQKV, qe);
+        HVX_LAUNCH_CHECK(e);
+      } else {
+        GemmEpi p; p.mode = EPI_LLM_QKV; p.bias = y.qkv_b; p.llm = qe;
+        if ((rc = gemm_bf16(e, st, b.x16, 2 * H, y.qkv_w, H, rows, NQKV, 2 * H, p, &gh))) return rc;
+      }
       if ((rc = launch_attn(e, st, L, l, b, rows, seqs, rows_per_seq, seq0, pos0, splits, true))) return rc;
-      if ((rc = llm_skinny_resid_gemm(e, st, b, b.att16, y.o_w, rows, H, H))) return rc;
-      llm_norm16_kernel<<<cdiv(rows, 8), 256, 0, st>>>(b.h, y.ln2, b.x16, rows, H, c.llm_eps);
-      HVX_LAUNCH_CHECK(e);
+      if ((rc = llm_skinny_resid_gemm(e, st, b, b.att16, y.o_w, rows, H, H, nullptr, nullptr, nullptr, y.ln2, b.x16))) return rc;
       { GemmEpi p; p.mode = EPI_SWIGLU; p.out = b.act16; p.ldo = 2 * I; p.lo_off = I;
         if ((rc = gemm_bf16(e, st, b.x16, 2 * H, y.gu_w, H, rows, 2 * I, 2 * H, p, &gh))) return rc; }
-      if ((rc = llm_skinny_resid_gemm(e, st, b, b.act16, y.down_w, rows, H, I))) return rc;
+      const float* next_ln1 = l + 1 < c.llm_layers ? L->layer[l + 1].ln1 : nullptr;
+      if ((rc = llm_skinny_resid_gemm(e, st, b, b.act16, y.down_w, rows, H, I, nullptr, nullptr, nullptr, next_ln1, b.x16))) return rc;
     }
   }
   return HVX_OK;

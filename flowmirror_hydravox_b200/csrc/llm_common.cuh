@@ -62,9 +62,9 @@ __device__ __forceinline__ void llm_qkv_store(const LlmQkvEpi& q, int row, int n
   const bool is_k = !is_q && n < q.q_dim + q.kv_dim;
   if (is_q || is_k) {
     const int i = (n & 63) >> 1;
-    const float a = (float)pos * q.inv_freq[i];
     float sn, cs;
-    sincos_noinline(a, &sn, &cs);
+    if (q.rope) { const float2 t = __ldg(q.rope + (size_t)pos * 32 + i); cs = t.x; sn = t.y; }      // same values as the table path of llm_qkv_store32
+    else sincos_noinline((float)pos * q.inv_freq[i], &sn, &cs);
     const float r0 = v0 * cs - v1 * sn;
     const float r1 = v1 * cs + v0 * sn;
     v0 = r0; v1 = r1;
