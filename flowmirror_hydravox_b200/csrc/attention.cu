@@ -57,9 +57,6 @@ dit_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   const int h = blockIdx.y, b = blockIdx.z;
   const int T = a.T;                                   // key rows per batch row
   const int Tq = a.Tq > 0 ? a.Tq : T;                  // query rows per batch row (windowed call: Tq < T, queries are frames q_pos0 ..)
-  const int Tk = a.klen ? a.klen[b] : (a.tk > 0 ? a.tk : T);     // keys of this batch row that exist (ragged group: the rest of the slab is padding)
-  const int klim_tile = a.chunk > 0 ? min(Tk, ((a.q_pos0 + min(q0 + 127, Tq - 1)) / a.chunk + 1) * a.chunk) : Tk;
-  const int nkv = (klim_tile + 63) / 64;
 
   if (tid == 0) {
     tc::tma_prefetch_desc(&tm_q); tc::tma_prefetch_desc(&tm_k); tc::tma_prefetch_desc(&tm_v);
@@ -70,9 +67,14 @@ dit_attention_v5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     tc::fence_barrier_init();
   }
   if (warp == 0) tc::tmem_alloc(tmem_slot, 256);
+  pdl_trigger();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
+  pdl_wait();                                          // first global read below (klen); the prologue above overlapped the predecessor
+  const int Tk = a.klen ? a.klen[b] : (a.tk > 0 ? a.tk : T);     // keys of this batch row that exist (ragged group: the rest of the slab is padding)
+  const int klim_tile = a.chunk > 0 ? min(Tk, ((a.q_pos0 + min(q0 + 127, Tq - 1)) / a.chunk + 1) * a.chunk) : Tk;
+  const int nkv = (klim_tile + 63) / 64;
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + 128;
   const uint32_t idesc = a.f16 ? tc::umma_idesc_f16(128, 64) : tc::umma_idesc_bf16(128, 64);
@@ -286,8 +288,8 @@ hvx_status dit_attention(hvx_engine* e, cudaStream_t st, const __nv_bfloat16* qk
   // one thread per query row is the faster form once P stays in tensor memory (568 vs 526 TFLOP/s at T = 2298); HVX_ATTN_HALVES=2
   // selects two threads per row
   static const int halves = getenv("HVX_ATTN_HALVES") ? atoi(getenv("HVX_ATTN_HALVES")) : 1;
-  if (halves == 2) dit_attention_v5_kernel<2><<<grid, 288, A5_SMEM, st>>>(tq, tk64, tv, k_col0, a);
-  else dit_attention_v5_kernel<1><<<grid, 160, A5_SMEM, st>>>(tq, tk64, tv, k_col0, a);
+  if (halves == 2) HVX_CUDA(launch_pdl_ex(dit_attention_v5_kernel<2>, grid, dim3(288), (size_t)A5_SMEM, st, 1, tq, tk64, tv, k_col0, a));
+  else HVX_CUDA(launch_pdl_ex(dit_attention_v5_kernel<1>, grid, dim3(160), (size_t)A5_SMEM, st, 1, tq, tk64, tv, k_col0, a));
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
 }

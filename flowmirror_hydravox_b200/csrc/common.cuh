@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdarg>
 #include <atomic>
+#include <cstring>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -160,4 +161,32 @@ hvx_status llm_generate_progress(hvx_engine* e, int n_seq, int head_k, const hvx
                                  void* progress_ctx);
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Launch with programmatic dependent launch allowed: the kernel may become resident while its predecessor in the stream drains and
+// run its prologue (barrier init, TMEM allocation, descriptor prefetch); it executes `griddepcontrol.wait` (hvx::pdl_wait) before
+// it touches any global memory, so ordering with the predecessor's results is unchanged.  Only kernels that contain the wait are
+// launched this way.  cluster > 1: thread-block cluster of that many CTAs along x.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[n].val.programmaticStreamSerializationAllowed = 1;
+  n++;
+  if (cluster > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = (unsigned)cluster; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+    n++;
+  }
+  cfg.attrs = at; cfg.numAttrs = (unsigned)n;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+#ifdef __CUDACC__
+// let the next kernel of the stream start its prologue; then wait until the previous kernel has completed and its writes are visible
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 }  // namespace hvx

@@ -195,6 +195,8 @@ __global__ void flow_rope_kernel(const float* __restrict__ inv_freq, float* __re
 __global__ void __launch_bounds__(256) dit_ln_mod_kernel(const float* __restrict__ h, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, __half* __restrict__ out, int M,
                                                           int D, int split) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= M) return;
   const float4* hr = reinterpret_cast<const float4*>(h + (size_t)row * D);
@@ -446,7 +448,7 @@ static hvx_status flow_nfe(hvx_engine* e, cudaStream_t st, const float* mod, int
     const float* m = mod + (size_t)i * 6 * dim;       // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
     const double ln_bytes = (double)M * dim * (4 + 2 * (f->precise ? 2 : 1));
     { ProfScope ps(&e->prof, st, PROF_LAYERNORM, ln_bytes);
-      dit_ln_mod_kernel<<<cdiv(M, 8), 256, 0, st>>>(f->h, m + dim, m, f->n16, M, dim, f->precise); }
+      HVX_CUDA(launch_pdl_ex(dit_ln_mod_kernel, dim3(cdiv(M, 8)), dim3(256), (size_t)0, st, 1, f->h, m + dim, m, f->n16, M, dim, f->precise)); }
     HVX_LAUNCH_CHECK(e);
     { GemmEpi p; p.mode = EPI_QKV; p.f16 = 1; p.bias = b.qkv_b; p.out = f->qk; p.ldo = 2 * inner; p.n_qk = 2 * inner;
       p.vt = (__nv_bfloat16*)f->vt; p.vt_ld = f->Tp; p.T = T; p.heads = c.flow_heads; p.rows_per_batch = T;
@@ -459,7 +461,7 @@ static hvx_status flow_nfe(hvx_engine* e, cudaStream_t st, const float* mod, int
       p.gate_ld = 0; p.rows_per_batch = T;
       if ((rc = flow_linear(e, st, f->ao, b.out_w, M, dim, inner, p))) return rc; }
     { ProfScope ps(&e->prof, st, PROF_LAYERNORM, ln_bytes);
-      dit_ln_mod_kernel<<<cdiv(M, 8), 256, 0, st>>>(f->h, m + 4 * dim, m + 3 * dim, f->n16, M, dim, f->precise); }
+      HVX_CUDA(launch_pdl_ex(dit_ln_mod_kernel, dim3(cdiv(M, 8)), dim3(256), (size_t)0, st, 1, f->h, m + 4 * dim, m + 3 * dim, f->n16, M, dim, f->precise)); }
     HVX_LAUNCH_CHECK(e);
     { GemmEpi p = epi16(f->f1, f->precise ? 2 * ff : ff, b.ff1_b, ACT_GELU_TANH);
       p.lo_off = f->precise ? ff : 0;
@@ -469,7 +471,7 @@ static hvx_status flow_nfe(hvx_engine* e, cudaStream_t st, const float* mod, int
       if ((rc = flow_linear(e, st, f->f1, b.ff2_w, M, dim, ff, p))) return rc; }
   }
   const float* mf = mod + (size_t)c.flow_depth * 6 * dim;     // AdaLayerNormZero_Final: (scale, shift)  (modules.py:262)
-  dit_ln_mod_kernel<<<cdiv(M, 8), 256, 0, st>>>(f->h, mf, mf + dim, f->n16, M, dim, f->precise);
+  HVX_CUDA(launch_pdl_ex(dit_ln_mod_kernel, dim3(cdiv(M, 8)), dim3(256), (size_t)0, st, 1, f->h, mf, mf + dim, f->n16, M, dim, f->precise));
   HVX_LAUNCH_CHECK(e);
   { GemmEpi p; p.mode = EPI_F32; p.f16 = 1; p.bias = f->proj_b; p.out = f->v; p.ldo = mel;
     if ((rc = flow_linear(e, st, f->n16, f->proj_w, M, mel, dim, p))) return rc; }
@@ -521,7 +523,7 @@ static hvx_status flow_nfe_window(hvx_engine* e, cudaStream_t st, const float* m
   for (int i = 0; i < c.flow_depth; i++) {
     const FlowBlk& b = f->blk[i];
     const float* m = mod + (size_t)i * 6 * dim;
-    dit_ln_mod_kernel<<<cdiv(M, 8), 256, 0, st>>>(f->h, m + dim, m, f->n16, M, dim, f->precise);
+    HVX_CUDA(launch_pdl_ex(dit_ln_mod_kernel, dim3(cdiv(M, 8)), dim3(256), (size_t)0, st, 1, f->h, m + dim, m, f->n16, M, dim, f->precise));
     HVX_LAUNCH_CHECK(e);
     { GemmEpi p; p.mode = EPI_QKV; p.f16 = 1; p.bias = b.qkv_b; p.out = f->qk; p.ldo = inner; p.n_qk = 2 * inner;
       p.k_out = (__nv_bfloat16*)S.K(step, i); p.k_ld = inner; p.k_batch_rows = S.Tcap; p.t_off = t0;
@@ -535,7 +537,7 @@ static hvx_status flow_nfe_window(hvx_engine* e, cudaStream_t st, const float* m
     { GemmEpi p; p.mode = EPI_RESID_GATE; p.f16 = 1; p.bias = b.out_b; p.out = f->h; p.ldo = dim; p.gate = m + 2 * dim;
       p.gate_ld = 0; p.rows_per_batch = Tw;
       if ((rc = flow_linear(e, st, f->ao, b.out_w, M, dim, inner, p))) return rc; }
-    dit_ln_mod_kernel<<<cdiv(M, 8), 256, 0, st>>>(f->h, m + 4 * dim, m + 3 * dim, f->n16, M, dim, f->precise);
+    HVX_CUDA(launch_pdl_ex(dit_ln_mod_kernel, dim3(cdiv(M, 8)), dim3(256), (size_t)0, st, 1, f->h, m + 4 * dim, m + 3 * dim, f->n16, M, dim, f->precise));
     HVX_LAUNCH_CHECK(e);
     { GemmEpi p = epi16(f->f1, f->precise ? 2 * ff : ff, b.ff1_b, ACT_GELU_TANH);
       p.lo_off = f->precise ? ff : 0;
@@ -545,7 +547,7 @@ static hvx_status flow_nfe_window(hvx_engine* e, cudaStream_t st, const float* m
       if ((rc = flow_linear(e, st, f->f1, b.ff2_w, M, dim, ff, p))) return rc; }
   }
   const float* mf = mod + (size_t)c.flow_depth * 6 * dim;
-  dit_ln_mod_kernel<<<cdiv(M, 8), 256, 0, st>>>(f->h, mf, mf + dim, f->n16, M, dim, f->precise);
+  HVX_CUDA(launch_pdl_ex(dit_ln_mod_kernel, dim3(cdiv(M, 8)), dim3(256), (size_t)0, st, 1, f->h, mf, mf + dim, f->n16, M, dim, f->precise));
   HVX_LAUNCH_CHECK(e);
   { GemmEpi p; p.mode = EPI_F32; p.f16 = 1; p.bias = f->proj_b; p.out = f->v; p.ldo = mel;
     if ((rc = flow_linear(e, st, f->n16, f->proj_w, M, mel, dim, p))) return rc; }

@@ -403,9 +403,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, BN);
+  pdl_trigger();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
+  pdl_wait();                          // everything above overlaps the predecessor's tail; nothing global has been touched yet
   const uint32_t tmem_base = *tmem_slot;
 
   const bool dbg = ad.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
@@ -536,9 +538,11 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, 2 * PBN);
+  pdl_trigger();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -651,7 +655,7 @@ static hvx_status launch_gemm_persist_t(hvx_engine* e, cudaStream_t st, const CU
   }
   const int tiles_m = cdiv(M, BM), tiles_n = cdiv(N, PBN);
   const int grid = std::min(tiles_m * tiles_n, std::max(2, e->sm_count - e->sm_reserve));
-  gemm_persist_kernel<MODE, ACT, TRI><<<grid, PERSIST_THREADS, S::TOTAL, st>>>(ta, tb, M, N, K, epi, ad, tiles_m, tiles_n);
+  HVX_CUDA(launch_pdl_ex(gemm_persist_kernel<MODE, ACT, TRI>, dim3(grid), dim3(PERSIST_THREADS), S::TOTAL, st, 1, ta, tb, M, N, K, epi, ad, tiles_m, tiles_n));
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
 }
@@ -700,8 +704,10 @@ gemm_pair3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   }
   if (warp == 1) tc::tmem_alloc_pair(tmem_slot, 2 * PBN);
   tc::tc_fence_before();
+  pdl_trigger();
   tc::cluster_sync_all();            // barriers of both CTAs initialised before any remote arrive / TMA completion; also a CTA barrier
   tc::tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -825,14 +831,7 @@ static hvx_status launch_gemm_pair_t(hvx_engine* e, cudaStream_t st, const CUten
   }
   const int tiles_m = cdiv(M, 256), tiles_n = cdiv(N, PBN);
   const int n_pairs = std::max(1, std::min(tiles_m * tiles_n, std::max(2, e->sm_count - e->sm_reserve) / 2));
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(2 * n_pairs); cfg.blockDim = dim3(PERSIST_THREADS); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  HVX_CUDA(cudaLaunchKernelEx(&cfg, gemm_pair3_kernel<MODE, ACT>, ta, tb, M, N, K, epi, ad, tiles_m, tiles_n));
+  HVX_CUDA(launch_pdl_ex(gemm_pair3_kernel<MODE, ACT>, dim3(2 * n_pairs), dim3(PERSIST_THREADS), S::TOTAL, st, 2, ta, tb, M, N, K, epi, ad, tiles_m, tiles_n));
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
 }
@@ -867,7 +866,7 @@ static hvx_status launch_gemm_t(hvx_engine* e, cudaStream_t st, const CUtensorMa
   }
   const int tiles_per_batch = cdiv(ad.rows_per_batch, BM);
   dim3 grid(cdiv(N, BN), tiles_per_batch * ad.n_batch, ad.split_k);
-  gemm_bf16_kernel<BN, STAGES, MODE, ACT, TRI><<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, M, N, K, epi, ad, tiles_per_batch);
+  HVX_CUDA(launch_pdl_ex(gemm_bf16_kernel<BN, STAGES, MODE, ACT, TRI>, grid, dim3(GEMM_THREADS), S::TOTAL, st, 1, ta, tb, M, N, K, epi, ad, tiles_per_batch));
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
 }

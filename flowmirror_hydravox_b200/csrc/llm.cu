@@ -1228,6 +1228,8 @@ __global__ void llm_rope_table_kernel(const float* __restrict__ inv_freq, float2
 // fp32-accurate activations: out = norm_w * (x * rsqrt(mean(x^2) + eps))
 __global__ void __launch_bounds__(256) llm_norm16_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                           __nv_bfloat16* __restrict__ out, int rows, int H, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float* xr = x + (size_t)row * H;
@@ -1930,6 +1932,8 @@ static hvx_status launch_attn(hvx_engine* e, cudaStream_t st, LlmState* L, int l
 // [hi | lo] of the result (row length H) for the next GEMM
 __global__ void llm_splitk_reduce_kernel(float* __restrict__ out, const float* __restrict__ resid, const float* __restrict__ part, int S,
                                          size_t n4, size_t stride4, __nv_bfloat16* __restrict__ out16, int H) {
+  pdl_trigger();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 a = reinterpret_cast<const float4*>(resid)[i];
@@ -1953,6 +1957,8 @@ __global__ void llm_splitk_reduce_kernel(float* __restrict__ out, const float* _
 // per (row, even column) pair
 __global__ void llm_qkv_reduce_kernel(const float* __restrict__ part, int S, size_t stride, const float* __restrict__ bias, int rows, int N,
                                       LlmQkvEpi q) {
+  pdl_trigger();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t pairs = (size_t)rows * (N >> 1);
   if (i >= pairs) return;
@@ -1975,7 +1981,7 @@ static hvx_status llm_skinny_resid_gemm(hvx_engine* e, cudaStream_t st, const St
   // kernel fusing the split-K reduce with this norm was measured at 27 us against 3.5 + 4.7 us for the two launches: kept separate.
   auto norm_after = [&](const float* h) -> hvx_status {
     if (!norm_w) return HVX_OK;
-    llm_norm16_kernel<<<cdiv(rows, 8), 256, 0, st>>>(h, norm_w, norm_x16, rows, H, e->cfg.llm_eps);
+    HVX_CUDA(launch_pdl(llm_norm16_kernel, dim3(cdiv(rows, 8)), dim3(256), 0, st, h, norm_w, norm_x16, rows, H, e->cfg.llm_eps));
     HVX_LAUNCH_CHECK(e);
     return HVX_OK;
   };
@@ -1999,7 +2005,7 @@ static hvx_status llm_skinny_resid_gemm(hvx_engine* e, cudaStream_t st, const St
   hvx_status rc = gemm_bf16(e, st, a16, 2 * K, w, K, rows, H, 2 * K, p, &ga);
   if (rc) return rc;
   const size_t n4 = (size_t)rows * H / 4;
-  llm_splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(out, resid, b.part, S, n4, n4, out16, H);
+  HVX_CUDA(launch_pdl(llm_splitk_reduce_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, out, resid, b.part, S, n4, n4, out16, H));
   HVX_LAUNCH_CHECK(e);
   return norm_after(out);
 }
@@ -2032,7 +2038,7 @@ static hvx_status llm_layers(hvx_engine* e, cudaStream_t st, LlmState* L, const 
       GemmAddr gh; gh.b_kb_mod = H / 64;
       GemmAddr gi; gi.b_kb_mod = I / 64;
       if (l == 0) {                                   // later layers: fused into the previous layer's down-proj reduce
-        llm_norm16_kernel<<<cdiv(rows, 8), 256, 0, st>>>(b.h, y.ln1, b.x16, rows, H, c.llm_eps);
+        HVX_CUDA(launch_pdl(llm_norm16_kernel, dim3(cdiv(rows, 8)), dim3(256), 0, st, b.h, y.ln1, b.x16, rows, H, c.llm_eps));
         HVX_LAUNCH_CHECK(e);
       }
       // decode (seqs): the 18 output tiles of the QKV projection leave 130 SMs idle — split-K over grid.z, the epilogue (bias,
@@ -2046,7 +2052,7 @@ static hvx_status llm_layers(hvx_engine* e, cudaStream_t st, LlmState* L, const 
         GemmEpi p; p.mode = EPI_F32; p.out = b.part; p.ldo = NQKV;
         if ((rc = gemm_bf16(e, st, b.x16, 2 * H, y.qkv_w, H, rows, NQKV, 2 * H, p, &gq))) return rc;
         const size_t pairs = (size_t)rows * (NQKV / 2);
-        llm_qkv_reduce_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(b.part, Sq, (size_t)rows * NQKV, y.qkv_b, rows, NQKV, qe);
+        HVX_CUDA(launch_pdl(llm_qkv_reduce_kernel, dim3((unsigned)((pairs + 255) / 256)), dim3(256), 0, st, b.part, Sq, (size_t)rows * NQKV, y.qkv_b, rows, NQKV, qe));
         HVX_LAUNCH_CHECK(e);
       } else {
         GemmEpi p; p.mode = EPI_LLM_QKV; p.bias = y.qkv_b; p.llm = qe;
@@ -2101,13 +2107,13 @@ static hvx_status llm_heads(hvx_engine* e, cudaStream_t st, LlmState* L, const S
     GemmAddr gh; gh.b_kb_mod = H / 64;
     GemmAddr gi; gi.b_kb_mod = MI / 64;
     for (int j = 0; j < head_k; j++) {
-      llm_norm16_kernel<<<cdiv(n_seq, 8), 256, 0, st>>>(b.hn, L->m_ln1 + (size_t)j * H, b.x16, n_seq, H, c.llm_eps);
+      HVX_CUDA(launch_pdl(llm_norm16_kernel, dim3(cdiv(n_seq, 8)), dim3(256), 0, st, b.hn, L->m_ln1 + (size_t)j * H, b.x16, n_seq, H, c.llm_eps));
       HVX_LAUNCH_CHECK(e);
       { GemmEpi p; p.mode = EPI_BF16; p.bias = L->m_v_b + (size_t)j * H; p.out = b.m16; p.ldo = 2 * H; p.lo_off = H;
         if ((rc = gemm_bf16(e, st, b.x16, 2 * H, L->m_v_w + (size_t)j * H * H, H, n_seq, H, 2 * H, p, &gh))) return rc; }
       { GemmEpi p; p.mode = EPI_F32; p.out = b.m_h1 + j * sH; p.ldo = H; p.resid = b.hn;
         if ((rc = gemm_bf16(e, st, b.m16, 2 * H, L->m_o_w + (size_t)j * H * H, H, n_seq, H, 2 * H, p, &gh))) return rc; }
-      llm_norm16_kernel<<<cdiv(n_seq, 8), 256, 0, st>>>(b.m_h1 + j * sH, L->m_ln2 + (size_t)j * H, b.x16, n_seq, H, c.llm_eps);
+      HVX_CUDA(launch_pdl(llm_norm16_kernel, dim3(cdiv(n_seq, 8)), dim3(256), 0, st, b.m_h1 + j * sH, L->m_ln2 + (size_t)j * H, b.x16, n_seq, H, c.llm_eps));
       HVX_LAUNCH_CHECK(e);
       { GemmEpi p; p.mode = EPI_SWIGLU; p.out = b.act16; p.ldo = 2 * MI; p.lo_off = MI;
         if ((rc = gemm_bf16(e, st, b.x16, 2 * H, L->m_gu_w + (size_t)j * 2 * MI * H, H, n_seq, 2 * MI, 2 * H, p, &gh))) return rc; }
