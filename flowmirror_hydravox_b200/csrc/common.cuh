@@ -173,9 +173,11 @@ static inline cudaError_t launch_pdl_ex(void (*kern)(KArgs...), dim3 grid, dim3 
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[2];
   int n = 0;
-  at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[n].val.programmaticStreamSerializationAllowed = 1;
-  n++;
+  if (cluster >= 0) {                     // cluster < 0: plain launch (no programmatic serialization), cluster size -cluster
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    n++;
+  } else cluster = -cluster;
   if (cluster > 1) {
     at[n].id = cudaLaunchAttributeClusterDimension;
     at[n].val.clusterDim.x = (unsigned)cluster; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;

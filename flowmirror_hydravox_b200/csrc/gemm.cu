@@ -655,7 +655,7 @@ static hvx_status launch_gemm_persist_t(hvx_engine* e, cudaStream_t st, const CU
   }
   const int tiles_m = cdiv(M, BM), tiles_n = cdiv(N, PBN);
   const int grid = std::min(tiles_m * tiles_n, std::max(2, e->sm_count - e->sm_reserve));
-  HVX_CUDA(launch_pdl_ex(gemm_persist_kernel<MODE, ACT, TRI>, dim3(grid), dim3(PERSIST_THREADS), S::TOTAL, st, 1, ta, tb, M, N, K, epi, ad, tiles_m, tiles_n));
+  HVX_CUDA(launch_pdl_ex(gemm_persist_kernel<MODE, ACT, TRI>, dim3(grid), dim3(PERSIST_THREADS), S::TOTAL, st, ad.no_pdl ? -1 : 1, ta, tb, M, N, K, epi, ad, tiles_m, tiles_n));
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
 }
@@ -866,7 +866,7 @@ static hvx_status launch_gemm_t(hvx_engine* e, cudaStream_t st, const CUtensorMa
   }
   const int tiles_per_batch = cdiv(ad.rows_per_batch, BM);
   dim3 grid(cdiv(N, BN), tiles_per_batch * ad.n_batch, ad.split_k);
-  HVX_CUDA(launch_pdl_ex(gemm_bf16_kernel<BN, STAGES, MODE, ACT, TRI>, grid, dim3(GEMM_THREADS), S::TOTAL, st, 1, ta, tb, M, N, K, epi, ad, tiles_per_batch));
+  HVX_CUDA(launch_pdl_ex(gemm_bf16_kernel<BN, STAGES, MODE, ACT, TRI>, grid, dim3(GEMM_THREADS), S::TOTAL, st, ad.no_pdl ? -1 : 1, ta, tb, M, N, K, epi, ad, tiles_per_batch));
   HVX_LAUNCH_CHECK(e);
   return HVX_OK;
 }

@@ -92,6 +92,10 @@ struct GemmAddr {
   // the caller sums the partials in a fixed order (deterministic, no atomics)
   int split_k = 1;
   size_t split_stride = 0;
+  // 1: launch without programmatic dependent launch.  The batched decode step is sized so that its GEMMs fill the SMs in exactly one
+  // wave at two CTAs per SM; successors that become resident early (waiting in griddepcontrol.wait with their shared memory and
+  // TMEM held) break that wave in two: 3.24 -> 3.54 ms per 128-row step with PDL on the decode GEMMs.
+  int no_pdl = 0;
   // HVX_GEMM_TIMELINE=1 (diagnostic): %globaltimer stamps of CTA (0,0,0) of the tile kernel — [0] start, [1+kb] TMA of k-block kb
   // issued, [65+kb] its data landed (MMA side), [130] accumulator complete, [131] epilogue done
   unsigned long long* dbg = nullptr;

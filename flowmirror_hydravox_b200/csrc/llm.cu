@@ -1981,14 +1981,14 @@ static hvx_status llm_skinny_resid_gemm(hvx_engine* e, cudaStream_t st, const St
   // kernel fusing the split-K reduce with this norm was measured at 27 us against 3.5 + 4.7 us for the two launches: kept separate.
   auto norm_after = [&](const float* h) -> hvx_status {
     if (!norm_w) return HVX_OK;
-    HVX_CUDA(launch_pdl(llm_norm16_kernel, dim3(cdiv(rows, 8)), dim3(256), 0, st, h, norm_w, norm_x16, rows, H, e->cfg.llm_eps));
+    HVX_CUDA(launch_pdl_ex(llm_norm16_kernel, dim3(cdiv(rows, 8)), dim3(256), (size_t)0, st, -1, h, norm_w, norm_x16, rows, H, e->cfg.llm_eps));
     HVX_LAUNCH_CHECK(e);
     return HVX_OK;
   };
   static const int want = getenv("HVX_LLM_SPLITK") ? atoi(getenv("HVX_LLM_SPLITK")) : 1;
   if (!out) out = b.h;
   if (!resid) resid = b.h;
-  GemmAddr ga; ga.b_kb_mod = K / 64;
+  GemmAddr ga; ga.b_kb_mod = K / 64; ga.no_pdl = 1;
   const int nkb = 2 * K / 64;
   // >= 7 k-blocks per CTA, and enough CTAs for every SM: N = H gives only H/64 output tiles
   const int tiles = cdiv(H, 64) * cdiv(rows, 128);
@@ -2005,7 +2005,7 @@ static hvx_status llm_skinny_resid_gemm(hvx_engine* e, cudaStream_t st, const St
   hvx_status rc = gemm_bf16(e, st, a16, 2 * K, w, K, rows, H, 2 * K, p, &ga);
   if (rc) return rc;
   const size_t n4 = (size_t)rows * H / 4;
-  HVX_CUDA(launch_pdl(llm_splitk_reduce_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, out, resid, b.part, S, n4, n4, out16, H));
+  HVX_CUDA(launch_pdl_ex(llm_splitk_reduce_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), (size_t)0, st, -1, out, resid, b.part, S, n4, n4, out16, H));
   HVX_LAUNCH_CHECK(e);
   return norm_after(out);
 }
@@ -2035,10 +2035,10 @@ static hvx_status llm_layers(hvx_engine* e, cudaStream_t st, LlmState* L, const 
       if ((rc = launch_gemv(e, st, d, rows))) return rc;
     } else {
       // activations travel as split bf16 [hi | lo] (K' = 2K against the same weights) -> fp32-accurate products
-      GemmAddr gh; gh.b_kb_mod = H / 64;
-      GemmAddr gi; gi.b_kb_mod = I / 64;
+      GemmAddr gh; gh.b_kb_mod = H / 64; gh.no_pdl = 1;
+      GemmAddr gi; gi.b_kb_mod = I / 64; gi.no_pdl = 1;
       if (l == 0) {                                   // later layers: fused into the previous layer's down-proj reduce
-        HVX_CUDA(launch_pdl(llm_norm16_kernel, dim3(cdiv(rows, 8)), dim3(256), 0, st, b.h, y.ln1, b.x16, rows, H, c.llm_eps));
+        HVX_CUDA(launch_pdl_ex(llm_norm16_kernel, dim3(cdiv(rows, 8)), dim3(256), (size_t)0, st, -1, b.h, y.ln1, b.x16, rows, H, c.llm_eps));
         HVX_LAUNCH_CHECK(e);
       }
       // decode (seqs): the 18 output tiles of the QKV projection leave 130 SMs idle — split-K over grid.z, the epilogue (bias,
@@ -2052,7 +2052,7 @@ static hvx_status llm_layers(hvx_engine* e, cudaStream_t st, LlmState* L, const 
         GemmEpi p; p.mode = EPI_F32; p.out = b.part; p.ldo = NQKV;
         if ((rc = gemm_bf16(e, st, b.x16, 2 * H, y.qkv_w, H, rows, NQKV, 2 * H, p, &gq))) return rc;
         const size_t pairs = (size_t)rows * (NQKV / 2);
-        HVX_CUDA(launch_pdl(llm_qkv_reduce_kernel, dim3((unsigned)((pairs + 255) / 256)), dim3(256), 0, st, b.part, Sq, (size_t)rows * NQKV, y.qkv_b, rows, NQKV, qe));
+        HVX_CUDA(launch_pdl_ex(llm_qkv_reduce_kernel, dim3((unsigned)((pairs + 255) / 256)), dim3(256), (size_t)0, st, -1, b.part, Sq, (size_t)rows * NQKV, y.qkv_b, rows, NQKV, qe));
         HVX_LAUNCH_CHECK(e);
       } else {
         GemmEpi p; p.mode = EPI_LLM_QKV; p.bias = y.qkv_b; p.llm = qe;
@@ -2104,16 +2104,16 @@ static hvx_status llm_heads(hvx_engine* e, cudaStream_t st, LlmState* L, const S
       if ((rc = launch_gemv(e, st, g, n_seq, head_k))) return rc;
     }
   } else {
-    GemmAddr gh; gh.b_kb_mod = H / 64;
-    GemmAddr gi; gi.b_kb_mod = MI / 64;
+    GemmAddr gh; gh.b_kb_mod = H / 64; gh.no_pdl = 1;
+    GemmAddr gi; gi.b_kb_mod = MI / 64; gi.no_pdl = 1;
     for (int j = 0; j < head_k; j++) {
-      HVX_CUDA(launch_pdl(llm_norm16_kernel, dim3(cdiv(n_seq, 8)), dim3(256), 0, st, b.hn, L->m_ln1 + (size_t)j * H, b.x16, n_seq, H, c.llm_eps));
+      HVX_CUDA(launch_pdl_ex(llm_norm16_kernel, dim3(cdiv(n_seq, 8)), dim3(256), (size_t)0, st, -1, b.hn, L->m_ln1 + (size_t)j * H, b.x16, n_seq, H, c.llm_eps));
       HVX_LAUNCH_CHECK(e);
       { GemmEpi p; p.mode = EPI_BF16; p.bias = L->m_v_b + (size_t)j * H; p.out = b.m16; p.ldo = 2 * H; p.lo_off = H;
         if ((rc = gemm_bf16(e, st, b.x16, 2 * H, L->m_v_w + (size_t)j * H * H, H, n_seq, H, 2 * H, p, &gh))) return rc; }
       { GemmEpi p; p.mode = EPI_F32; p.out = b.m_h1 + j * sH; p.ldo = H; p.resid = b.hn;
         if ((rc = gemm_bf16(e, st, b.m16, 2 * H, L->m_o_w + (size_t)j * H * H, H, n_seq, H, 2 * H, p, &gh))) return rc; }
-      HVX_CUDA(launch_pdl(llm_norm16_kernel, dim3(cdiv(n_seq, 8)), dim3(256), 0, st, b.m_h1 + j * sH, L->m_ln2 + (size_t)j * H, b.x16, n_seq, H, c.llm_eps));
+      HVX_CUDA(launch_pdl_ex(llm_norm16_kernel, dim3(cdiv(n_seq, 8)), dim3(256), (size_t)0, st, -1, b.m_h1 + j * sH, L->m_ln2 + (size_t)j * H, b.x16, n_seq, H, c.llm_eps));
       HVX_LAUNCH_CHECK(e);
       { GemmEpi p; p.mode = EPI_SWIGLU; p.out = b.act16; p.ldo = 2 * MI; p.lo_off = MI;
         if ((rc = gemm_bf16(e, st, b.x16, 2 * H, L->m_gu_w + (size_t)j * 2 * MI * H, H, n_seq, 2 * MI, 2 * H, p, &gh))) return rc; }
