@@ -437,7 +437,7 @@ def native_arm(a):
                        "l2": "256 MiB flush between timed steps; per-step weight + activation traffic (> 2 GB) exceeds L2",
                        "precision": ("llm: bf16 weights, fp32 KV cache, fp32 activations/accumulate; flow: three-term split-fp16 tensor-core products "
                                      "(A_hi W_hi + A_lo W_hi + A_hi W_lo), fp32 accumulate/state — the mode tests/test_flow_gpu.py::"
-                                     "test_flow_parity_mode_meets_north_star and test_c2_size_parity assert at <= 1e-3 max-abs on mel; hift: fp32"
+                                     "test_flow_parity_mode_meets_north_star and tests/test_c2_gpu.py::test_flow_c2_size_parity assert at <= 1e-3 max-abs on mel; hift: fp32"
                                      if parity else
                                      "llm: bf16 weights + bf16 KV cache; flow: fp16 operands (the reference's serving precision), fp32 accumulate/state; hift: fp32"),
                        "utterances_per_gpu": batch, "tokens_per_step": tok_dev / a.steps,
