@@ -18,6 +18,8 @@ Other workloads: c2 = configs[1] (one 16+128-token utterance, K=2), b8 = 8 mixed
           return to rank 0 (one NCCL gather) — all inside the timed region, scatter / gather milliseconds reported.
 Both legs run in the mode whose parity tests/ assert (default `parity`: fp32 KV cache, three-term split-fp16 flow GEMMs:
 mel <= 1e-3 max-abs against the fp32 reference); `serving_mode` reports the reference's own serving precision next to it.
+Baselines on the same line (never the product path): `cpu_baseline` = the oracle port of the reference algorithm on the host cores,
+`gpu_eager_baseline` = the same eager PyTorch code with its tensors on the B200 (SURVEY 8d's GPU comparator), one utterance each.
 """
 from __future__ import annotations
 
@@ -159,12 +161,13 @@ class ClockSampler:
 _CPU_SDS = {}
 
 
-def cpu_oracle_run(a, n_tokens: int, threads: int):
-    """The reference algorithm restated on the CPU (oracle/, fp32 torch) on a BOUNDED sample of the workload: ONE zero-shot
+def cpu_oracle_run(a, n_tokens: int, threads: int, device: str = "cpu"):
+    """The reference algorithm restated in eager PyTorch (oracle/, fp32) on a BOUNDED sample of the workload: ONE zero-shot
     utterance of the workload's shape — same prompt (16 prompt text tokens, 125 prompt speech tokens, 250 prompt mel frames), same
     inference_head_num, same number of CFM steps, full model dims — whose text is shortened so the fixed-length protocol emits
     n_tokens speech tokens.  Throughput per token on the CPU does not improve with length (attention grows with T^2), so the
-    short sample flatters the CPU arm."""
+    short sample flatters the CPU arm.  device="cuda:i" runs the very same eager code with its tensors on the GPU: the
+    `gpu_eager_baseline` comparator of SURVEY 8(d) (a baseline leg like the CPU one — never the product path)."""
     from oracle import flow_ref, hift_ref, llm_ref
     torch.set_num_threads(threads)
     ld, fd, hd = D.LLM_FULL, D.FLOW_FULL, D.HIFT_FULL
@@ -172,28 +175,63 @@ def cpu_oracle_run(a, n_tokens: int, threads: int):
     n_text = max(1, int(round(n_tokens / RATIO)))
     if not _CPU_SDS:
         _CPU_SDS.update(llm=synth.llm_state_dict(ld, 0, eos_scale=0.0), flow=synth.flow_state_dict(fd, 0), hift=synth.hift_state_dict(hd, 0))
-    llm_sd, flow_sd, hift_sd = _CPU_SDS["llm"], _CPU_SDS["flow"], _CPU_SDS["hift"]
+    on_gpu = device != "cpu"
+    key = lambda k: k + "@" + device if on_gpu else k
+    if on_gpu and key("llm") not in _CPU_SDS:
+        for k in ("llm", "flow", "hift"):
+            _CPU_SDS[key(k)] = {n: v.float().to(device) for n, v in _CPU_SDS[k].items()}
+    llm_sd, flow_sd, hift_sd = _CPU_SDS[key("llm")], _CPU_SDS[key("flow")], _CPU_SDS[key("hift")]
     u = synth.utterance(ld, fd, n_text, seed=1987, prompt_tokens=P_TOK, prompt_text=P_TEXT)
+    u = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in u.items()}
     us = torch.rand(8 * n_tokens + 64, generator=torch.Generator().manual_seed(7))
-    noise = synth.flow_noise(fd)
+    noise = synth.flow_noise(fd).to(device)
+    sync = (lambda: torch.cuda.synchronize(device)) if on_gpu else (lambda: None)
+    sync()
     t0 = time.perf_counter()
+    ctx = lambda: torch.device(device)                   # the oracle's factory calls (arange, zeros, ...) follow the context
     with torch.no_grad():
-        toks = llm_ref.inference(llm_sd, ld, u["text"], u["prompt_text"], u["prompt_speech"], us, head_k=head_k, sp=SAMPLING,
-                                 min_ratio=RATIO, max_ratio=RATIO)
-        t1 = time.perf_counter()
-        mel = flow_ref.inference(flow_sd, torch.tensor(toks)[None], u["embedding"][None], noise, fd, a.cfm_steps,
-                                 u["prompt_speech"][None].long(), u["prompt_feat"][None])
-        t2 = time.perf_counter()
-        table = synth.hift_sine_table(hd, mel.shape[2])
-        wav, _ = hift_ref.inference(hift_sd, mel, table, hd)
+        with ctx():
+            toks = llm_ref.inference(llm_sd, ld, u["text"], u["prompt_text"], u["prompt_speech"], us, head_k=head_k, sp=SAMPLING,
+                                     min_ratio=RATIO, max_ratio=RATIO)
+            sync(); t1 = time.perf_counter()
+            mel = flow_ref.inference(flow_sd, torch.tensor(toks)[None], u["embedding"][None], noise, fd, a.cfm_steps,
+                                     u["prompt_speech"][None].long(), u["prompt_feat"][None])
+            sync(); t2 = time.perf_counter()
+        table = synth.hift_sine_table(hd, mel.shape[2]).to(device)
+        with ctx():
+            wav, _ = hift_ref.inference(hift_sd, mel, table, hd)
+        wav = wav.cpu()
         t3 = time.perf_counter()
     total = t3 - t0
+    where = (f"eager PyTorch fp32 on {torch.cuda.get_device_name(device)} (TF32 matmul/conv "
+             f"{'on' if torch.backends.cuda.matmul.allow_tf32 else 'off'})") if on_gpu else f"{threads} threads"
     return dict(tokens=len(toks), seconds=total, stage_s=dict(llm=t1 - t0, flow=t2 - t1, hift=t3 - t2),
                 tokens_per_s=len(toks) / total, rtf=total / (wav.shape[1] / hd.sr),
                 sample=f"1 zero-shot utterance of the workload's shape: {n_text}+{P_TEXT} text tokens, {P_TOK} prompt speech tokens (+{2 * P_TOK} prompt "
                        f"mel frames), inference_head_num={head_k}, {a.cfm_steps} CFM steps, {len(toks)} speech tokens ({len(toks) / 25:.2f} s of audio), "
                        f"full model dims, fp32 oracle port of the reference algorithm (KV-cached decode, i.e. faster than the reference's "
-                       f"own no-cache loop), {threads} threads")
+                       f"own no-cache loop), {where}")
+
+
+def gpu_eager_baseline(a, device: str, n_tokens: int):
+    """SURVEY 8(d)'s honest GPU comparator: the reference algorithm as eager PyTorch kernels (cuBLAS / cuDNN / ATen; the
+    oracle port with its tensors on the B200, batch 1 like the reference) on one utterance of the workload's shape.  TF32 is
+    switched on for the baseline's matmuls and convolutions (the reference serves in bf16 / fp16; fp32-without-TF32 would
+    flatter the engine).  Any failure is reported, never raised: this leg must not cost the bench its line."""
+    prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = True
+        cpu_oracle_run(a, 32, 1, device)                                  # warm-up: cuBLAS / cuDNN handles and heuristics
+        r = cpu_oracle_run(a, n_tokens, os.cpu_count() or 1, device)
+        return {"value": r["tokens_per_s"], "unit": "tokens/s", "rtf": r["rtf"], "stage_s": r["stage_s"], "sample": r["sample"],
+                "kind": "oracle port of the reference algorithm, eager PyTorch, batch 1 (the reference has no batched path)"}
+    except Exception as e:                                                # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+        for k in [k for k in _CPU_SDS if "@" in k]:
+            del _CPU_SDS[k]
+        torch.cuda.empty_cache()
 
 
 def reference_arm(a):
@@ -521,7 +559,9 @@ def native_arm(a):
                                          "first chunk = 25+3 tokens; request -> first waveform chunk on the host (wall clock)"}
     if a.variants and world == 1:
         line["variants"] = variants(mm.engine.device, 2 * (1024 + P_TOK), a.cfm_steps, tf_peak)
-    if not a.no_cpu_baseline:
+    if not a.no_extras and world == 1:
+        line["gpu_eager_baseline"] = gpu_eager_baseline(a, f"cuda:{local}", 1024)
+    if not a.no_cpu_baseline and world == 1:                 # rank 0 at N = 1 only
         threads = os.cpu_count() or 1
         r = cpu_oracle_run(a, a.cpu_tokens, threads)
         line["cpu_baseline"] = {"value": r["tokens_per_s"], "unit": "tokens/s", "cores": threads, "kind": "port", "sample": r["sample"],

@@ -24,10 +24,12 @@ def _nvcc():
 
 
 def _digest(paths):
+    """content hash of the sources, keyed by file NAME (not path): the stamp stays valid when the tree is copied elsewhere
+    together with its built library (the GPU box runs a snapshot of the repo under another root)"""
     h = hashlib.sha256()
-    for p in sorted(paths):
+    for p in sorted(paths, key=os.path.basename):
         with open(p, "rb") as f:
-            h.update(p.encode() + b"\0" + f.read())
+            h.update(os.path.basename(p).encode() + b"\0" + f.read())
     return h.hexdigest()
 
 
