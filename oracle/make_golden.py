@@ -151,6 +151,80 @@ def golden_llm_c2(dims, seed, n_text=128, n_ptext=16, P=125, K=2, ratio=8, depth
                os.path.join(OUT, "llm_c2.pt"))
 
 
+def golden_e2e_c1(seed=0, n_text=32, K=1, ratio=8, n_steps=10):
+    """BASELINE configs[0] ("C1", SURVEY 8d: one 32-text-token utterance, inference_head_num=1, 10 CFM Euler steps, no prompt ->
+    256 speech tokens, 512 mel frames, 245 760 samples = 10.24 s) through the three UNMODIFIED reference modules at full dims,
+    chained the way `inference_tts` chains them (infer_speech_model.py:629-668: empty prompt text, no prompt speech tokens, the
+    flow called with token / embedding only, the vocoder on the flow's mel).  Each stage's restatement is checked on the way."""
+    ld, fd, hd = D.LLM_FULL, D.FLOW_FULL, D.HIFT_FULL
+    refshim.install()
+    from cosyvoice.utils.common import ras_sampling
+    import cosyvoice.flow.flow as flowmod
+    import time
+    sp = dict(top_p=0.9, top_k=10, win_size=24, tau_r=0.2)         # server tts defaults (router.py:22-44)
+    u0 = synth.utterance(ld, fd, n_text, seed=1986, zero_shot=False)
+    text = u0["text"].long()[None]
+    u = torch.rand(4096, generator=torch.Generator().manual_seed(seed + 7))
+    # ---- stage 1: CosyVoice3LM.inference (no KV cache), weights = the bf16-rounded synthetic checkpoint evaluated in fp32
+    m = refshim.build_llm(ld)
+    sd_l = {k: v.to(torch.bfloat16).float() for k, v in synth.llm_state_dict(ld, seed, eos_scale=0.0).items()}
+    m.load_state_dict(sd_l, strict=True)
+    m.sampling = partial(ras_sampling, **sp)
+    m.inference_head_num = K
+    us = llm_ref.UStream(u)
+    orig = torch.Tensor.multinomial
+    torch.Tensor.multinomial = lambda self, n, replacement=False: torch.tensor([llm_ref.multinomial_u(self, us.next())])
+    t0 = time.time()
+    try:
+        toks = list(m.inference(text=text, text_len=torch.tensor([n_text]), prompt_text=torch.zeros(1, 0, dtype=torch.long),
+                                prompt_text_len=torch.tensor([0]), prompt_speech_token=None, prompt_speech_token_len=torch.tensor([0]),
+                                embedding=None, min_token_text_ratio=ratio, max_token_text_ratio=ratio))
+    finally:
+        torch.Tensor.multinomial = orig
+    ora = llm_ref.inference(sd_l, ld, text[0], torch.zeros(0, dtype=torch.long), torch.zeros(0, dtype=torch.long), u, head_k=K, sp=sp,
+                            min_ratio=ratio, max_ratio=ratio)
+    print(f"[e2e:c1] llm: reference {len(toks)} tokens in {time.time() - t0:.0f} s (u used {us.pos}); oracle identical: {ora == toks}")
+    assert len(toks) == n_text * ratio and ora == toks
+    del m
+    # ---- stage 2: CausalMaskedDiffWithDiT.inference in fp32 (n_timesteps=10 is the reference's own hard-coded value, flow.py:425)
+    assert n_steps == 10
+    flowmod.torch = _TorchF32Proxy()
+    f = refshim.build_flow(fd)
+    sd_f = synth.flow_state_dict(fd, seed)
+    f.load_state_dict(sd_f, strict=True)
+    f.bf16 = True
+    noise = synth.flow_noise(fd)
+    assert torch.equal(f.decoder.rand_noise[:, :, : noise.shape[2]], noise), "rand_noise recipe drifted"
+    tok = torch.tensor(toks)[None]
+    emb = u0["embedding"][None]
+    mel, _ = f.inference(token=tok, token_len=torch.tensor([tok.shape[1]]), embedding=emb, streaming=False, finalize=True)
+    flowmod.torch = torch
+    mel_o = flow_ref.inference(sd_f, tok, emb, noise, fd, n_steps)
+    e_mel = (mel - mel_o).abs().max().item()
+    print(f"[e2e:c1] flow: mel {tuple(mel.shape)} ref-vs-oracle max-abs {e_mel:.2e} mean|mel| {mel.abs().mean():.3f}")
+    assert mel.shape == (1, fd.mel, 2 * len(toks)) and e_mel < 2e-4
+    del f
+    # ---- stage 3: CausalHiFTGenerator.inference on the reference's mel (F0 predictor on the CPU in fp32, as the reference runs it)
+    h = refshim.build_hift(hd)
+    sd_h = synth.hift_state_dict(hd, seed)
+    h.load_state_dict(sd_h, strict=True)
+    table = synth.hift_sine_table(hd, mel.shape[2])
+    h.m_source.l_sin_gen.sine_waves = table[None]
+    wav, _ = h.inference(speech_feat=mel)
+    f0 = h.f0_predictor(mel)
+    wav_o, _ = hift_ref.inference(sd_h, mel, table, hd, f0=f0)
+    e_wav = (wav - wav_o).abs().max().item()
+    wav_free, _ = hift_ref.inference(sd_h, mel, table, hd)
+    rms_free = (wav - wav_free).pow(2).mean().sqrt().item()
+    print(f"[e2e:c1] hift: {wav.shape[1]} samples, ref-vs-oracle max-abs {e_wav:.2e} (F0 pinned), rms {rms_free:.2e} (oracle's own F0); "
+          f"wav rms {wav.pow(2).mean().sqrt():.3f}")
+    assert wav.shape == (1, mel.shape[2] * hd.frame_samples) and e_wav < 2e-5
+    torch.save(dict(dims="c1", seed=seed, n_text=n_text, K=K, ratio=ratio, n_steps=n_steps, sp=sp, text=u0["text"], embedding=u0["embedding"],
+                    u=u, u_used=us.pos, tokens=toks, mel=mel, wav=wav, f0=f0, oracle_free_f0_rms=rms_free,
+                    sd_checksum=dict(llm=checksum(sd_l), flow=checksum(sd_f), hift=checksum(sd_h))),
+               os.path.join(OUT, "e2e_c1.pt"))
+
+
 def golden_hift_t(name, dims, T, seed):
     """a12': the non-causal ConvTranspose1d HiFTGenerator.  Its source module is stochastic (fresh noise + random initial
     phase per call): the fixture pins decode(mel, s) for an explicit source s, the F0 predictor, and the whole
@@ -465,6 +539,10 @@ def main():
                 golden_flow("c2", D.FLOW_FULL, 1024, 125, 25, 0, modes=("full",), with_est=False, with_bf16=False)
             if "llm" in which:
                 golden_llm_c2(D.LLM_FULL, 0)
+        return
+    if sys.argv[1:] == ["c1"]:                                      # BASELINE configs[0]: the three reference modules chained
+        with torch.no_grad():
+            golden_e2e_c1()
         return
     if sys.argv[1:] == ["frontend"]:
         with torch.no_grad():

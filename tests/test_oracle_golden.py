@@ -200,3 +200,28 @@ def test_sampler_edges():
     logp = torch.log(torch.tensor([0.25, 0.25, 0.25, 0.25]))
     us = llm_ref.UStream(torch.tensor([0.30]))
     assert llm_ref.nucleus_sampling(logp, us, top_p=0.6, top_k=25) == 0   # kept {0,1,2}: .3*.75=.225<.25
+
+
+@pytest.mark.slow
+def test_e2e_c1_oracle_chain_matches_reference_chain(golden):
+    """BASELINE configs[0] at full dims: the CPU restatements chained (llm_ref -> flow_ref -> hift_ref) against the fixture the three
+    unmodified reference modules produced when chained like inference_tts (oracle/make_golden.py c1): 256 token ids identical,
+    mel within 2e-4, waveform within 2e-5 with the reference's F0 track."""
+    import os
+    if not os.path.exists(os.path.join(os.path.dirname(__file__), "golden", "e2e_c1.pt")):
+        pytest.skip("e2e_c1 fixture not minted")
+    g = golden("e2e_c1")
+    ld, fd, hd = D.LLM_FULL, D.FLOW_FULL, D.HIFT_FULL
+    sd_l = {k: v.to(torch.bfloat16).float() for k, v in synth.llm_state_dict(ld, g["seed"], eos_scale=0.0).items()}
+    assert abs(_checksum(sd_l) - g["sd_checksum"]["llm"]) < 1e-6 * g["sd_checksum"]["llm"]
+    us = llm_ref.UStream(g["u"])
+    empty = torch.zeros(0, dtype=torch.long)
+    toks = llm_ref.inference(sd_l, ld, g["text"], empty, empty, us, head_k=g["K"], sp=g["sp"], min_ratio=g["ratio"], max_ratio=g["ratio"])
+    assert toks == g["tokens"] and us.pos == g["u_used"]
+    del sd_l
+    mel = flow_ref.inference(synth.flow_state_dict(fd, g["seed"]), torch.tensor(toks)[None], g["embedding"][None], synth.flow_noise(fd), fd,
+                             g["n_steps"])
+    assert mel.shape == g["mel"].shape and (mel - g["mel"]).abs().max() < 2e-4
+    table = synth.hift_sine_table(hd, mel.shape[2])
+    wav, _ = hift_ref.inference(synth.hift_state_dict(hd, g["seed"]), g["mel"], table, hd, f0=g["f0"])
+    assert wav.shape == g["wav"].shape and (wav - g["wav"]).abs().max() < 2e-5
