@@ -219,6 +219,13 @@ def install():
     _installed = True
 
 
+def add_stub_roots(*roots):
+    """Import-only stand-ins for further third-party modules (e.g. the frontend's onnxruntime / whisper / inflect / wetext when the
+    reference's server-side host module is imported for a call-sequence test); a module that really exists is never stubbed."""
+    install()
+    globals()["_STUB_ROOTS"] = tuple(_STUB_ROOTS) + tuple(r for r in roots if r not in _STUB_ROOTS and not _really_exists(r))
+
+
 def _really_exists(root):
     for p in sys.path:
         if os.path.isdir(os.path.join(p, root)) or os.path.isfile(os.path.join(p, root + ".py")):
