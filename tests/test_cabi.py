@@ -27,3 +27,41 @@ def test_engine_fails_loudly_without_gpu():
         pytest.skip("GPU present")
     with pytest.raises(L.HvxError):
         L.Engine()
+
+
+def test_header_is_plain_c_and_links_from_a_c_program(tmp_path):
+    """The boundary a non-Python host would bind (cgo / JNI / plain C): include/hydravox_b200.h compiles as C99, a C program links
+    against the library, and — with no GPU here — hvx_create fails with a status and a message instead of crashing."""
+    import shutil
+    import subprocess
+    import torch
+    from flowmirror_hydravox_b200 import build
+    if shutil.which("gcc") is None:
+        import pytest
+        pytest.skip("gcc not found")
+    lib = build.build()
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "hydravox_b200.h"
+int main(void) {
+  hvx_config cfg; memset(&cfg, 0, sizeof cfg);
+  hvx_engine* e = 0;
+  printf("version %d\n", hvx_version());
+  hvx_status rc = hvx_create(&e, &cfg);
+  printf("create rc=%d err=%s\n", rc, hvx_last_error());
+  if (rc == HVX_OK) hvx_destroy(e);
+  return 0;
+}
+''')
+    exe = tmp_path / "host"
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", f"-I{inc}", str(src), "-o", str(exe), lib,
+                        f"-Wl,-rpath,{os.path.dirname(lib)}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "version " in out.stdout
+    if not torch.cuda.is_available():
+        assert "create rc=0" not in out.stdout and "err=" in out.stdout and len(out.stdout.split("err=")[1].strip()) > 0
