@@ -160,3 +160,33 @@ def test_pack_unet_nc_resampling_convs_are_exact_repacks():
     hi, lo = pk2["res0.c1.w"].float().chunk(2, dim=1)
     w = sd["down_blocks.0.0.block1.block.0.weight"]
     assert (hi + lo - w.permute(0, 2, 1).reshape(w.shape[0], -1)).abs().max() < 1e-6
+
+
+def test_product_path_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package (or the C sources) may import, call or load it — the engine has no
+    CPU fallback.  Checked on the syntax tree of every module of the package and by a fresh interpreter's sys.modules after import."""
+    import ast
+    import glob
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "flowmirror_hydravox_b200")
+    for path in glob.glob(os.path.join(pkg, "*.py")):
+        for node in ast.walk(ast.parse(open(path).read())):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            assert not any(n == "oracle" or n.startswith("oracle.") for n in names), path
+    code = ("import sys; sys.path.insert(0, %r); import flowmirror_hydravox_b200 as p; "
+            "from flowmirror_hydravox_b200 import _lib, llm, flow, hift, model_manager, streaming, parallel, output, frontend, synth, dims; "
+            "print(sorted(m for m in sys.modules if m == 'oracle' or m.startswith('oracle.')))" % root)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-1500:]
+    assert out.stdout.strip().splitlines()[-1] == "[]"
+    import re
+    for path in glob.glob(os.path.join(pkg, "csrc", "*")):          # the C sources cannot reach Python or another library at run time
+        src = re.sub(r"//[^\n]*|/\*.*?\*/", "", open(path, errors="ignore").read(), flags=re.S)
+        assert not re.search(r"\b(dlopen|popen|system|execv\w*|Py_\w+)\s*\(", src), path
