@@ -32,3 +32,16 @@ def test_reference_arm_line_keeps_the_contract():
 def test_reference_arm_other_ranks_exit_without_work():
     r = _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}, "--gpus", "2", "--steps", "1", "--warmup", "0")
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_native_arm_fails_loudly_without_a_gpu():
+    """no CPU fallback: the native arm of the bench exits non-zero with an error and prints no JSON line when there is no CUDA device"""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("GPU present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--no-extras", "--no-cpu-baseline"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0
+    assert not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert "Error" in r.stderr
